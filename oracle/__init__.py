@@ -1,0 +1,429 @@
+"""CPU oracle for the Seal-3D hot path -- TEST INFRASTRUCTURE ONLY.
+
+numpy-facing wrappers over ``liboracle.so`` (``seal_oracle.c``, a CPU restatement of the
+reference kernels, each function citing the reference file:line it follows) plus the few
+pieces that are plain numpy (the NGP field of nerf/network.py composed from the C ops, the
+distillation losses, Adam).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this package.  The product package never does: it
+fails loudly when its CUDA library is missing.
+
+Pinning status: see the header of seal_oracle.c and DESIGN.md ("Oracle").
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "seal_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        base = [cc, "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-o", so, src, "-lm"]
+        try:
+            subprocess.check_call(base[:1] + ["-fopenmp"] + base[1:])
+        except (subprocess.CalledProcessError, OSError):
+            subprocess.check_call(base)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_num_threads.restype = C.c_int
+    return _LIB
+
+
+def num_threads():
+    return int(lib().orc_num_threads())
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+u32, f32, i64, cint = C.c_uint32, C.c_float, C.c_int64, C.c_int
+
+# ---------------------------------------------------------------- raymarching
+
+
+def near_far_from_aabb(rays_o, rays_d, aabb, min_near=0.2):
+    rays_o, rays_d, aabb = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3), _f32(aabb)
+    N = rays_o.shape[0]
+    nears, fars = np.empty(N, np.float32), np.empty(N, np.float32)
+    lib().orc_near_far_from_aabb(_p(rays_o), _p(rays_d), _p(aabb), u32(N), f32(min_near), _p(nears), _p(fars))
+    return nears, fars
+
+
+def sph_from_ray(rays_o, rays_d, radius):
+    rays_o, rays_d = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3)
+    N = rays_o.shape[0]
+    coords = np.empty((N, 2), np.float32)
+    lib().orc_sph_from_ray(_p(rays_o), _p(rays_d), f32(radius), u32(N), _p(coords))
+    return coords
+
+
+def morton3D(coords):
+    coords = _i32(coords)
+    out = np.empty(coords.shape[0], np.int32)
+    lib().orc_morton3D(_p(coords), u32(coords.shape[0]), _p(out))
+    return out
+
+
+def morton3D_invert(indices):
+    indices = _i32(indices)
+    out = np.empty((indices.shape[0], 3), np.int32)
+    lib().orc_morton3D_invert(_p(indices), u32(indices.shape[0]), _p(out))
+    return out
+
+
+def packbits(grid, thresh):
+    grid = _f32(grid)
+    N = grid.size // 8
+    out = np.empty(N, np.uint8)
+    lib().orc_packbits(_p(grid), u32(N), f32(thresh), _p(out))
+    return out
+
+
+def march_rays_train(rays_o, rays_d, bound, bitfield, Cc, H, nears, fars, noises=None, dt_gamma=0.0, max_steps=1024,
+                     M=None):
+    """Returns xyzs[M,3], dirs[M,3], deltas[M,2], rays[N,3] (id, offset, count), counter[2].
+    Deterministic ray-major slot order (see seal_oracle.c)."""
+    rays_o, rays_d = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3)
+    N = rays_o.shape[0]
+    if noises is None:
+        noises = np.zeros(N, np.float32)
+    if M is None:
+        M = N * max_steps
+    xyzs, dirs, deltas = np.zeros((M, 3), np.float32), np.zeros((M, 3), np.float32), np.zeros((M, 2), np.float32)
+    rays = np.empty((N, 3), np.int32)
+    counter = np.zeros(2, np.int32)
+    bitfield = np.ascontiguousarray(bitfield, np.uint8)
+    lib().orc_march_rays_train(_p(rays_o), _p(rays_d), _p(bitfield), f32(bound), f32(dt_gamma), u32(max_steps), u32(N),
+                               u32(Cc), u32(H), u32(M), _p(_f32(nears)), _p(_f32(fars)), _p(xyzs), _p(dirs), _p(deltas),
+                               _p(rays), _p(counter), _p(_f32(noises)))
+    return xyzs, dirs, deltas, rays, counter
+
+
+def composite_rays_train_forward(sigmas, rgbs, deltas, rays, T_thresh=1e-4):
+    sigmas, rgbs, deltas, rays = _f32(sigmas), _f32(rgbs), _f32(deltas), _i32(rays)
+    M, N = sigmas.shape[0], rays.shape[0]
+    ws, depth, image = np.empty(N, np.float32), np.empty(N, np.float32), np.empty((N, 3), np.float32)
+    lib().orc_composite_rays_train_forward(_p(sigmas), _p(rgbs), _p(deltas), _p(rays), u32(M), u32(N), f32(T_thresh),
+                                           _p(ws), _p(depth), _p(image))
+    return ws, depth, image
+
+
+def composite_rays_train_backward(grad_ws, grad_image, sigmas, rgbs, deltas, rays, ws, image, T_thresh=1e-4):
+    sigmas, rgbs, deltas, rays = _f32(sigmas), _f32(rgbs), _f32(deltas), _i32(rays)
+    M, N = sigmas.shape[0], rays.shape[0]
+    gs, gc = np.zeros(M, np.float32), np.zeros((M, 3), np.float32)
+    lib().orc_composite_rays_train_backward(_p(_f32(grad_ws)), _p(_f32(grad_image)), _p(sigmas), _p(rgbs), _p(deltas),
+                                            _p(rays), _p(_f32(ws)), _p(_f32(image)), u32(M), u32(N), f32(T_thresh),
+                                            _p(gs), _p(gc))
+    return gs, gc
+
+
+def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, bitfield, Cc, H, nears, fars, noises=None,
+               dt_gamma=0.0, max_steps=1024, align=-1):
+    M = n_alive * n_step
+    if align > 0:
+        M += align - (M % align)
+    xyzs, dirs, deltas = np.zeros((M, 3), np.float32), np.zeros((M, 3), np.float32), np.zeros((M, 2), np.float32)
+    if noises is None:
+        noises = np.zeros(n_alive, np.float32)
+    bitfield = np.ascontiguousarray(bitfield, np.uint8)
+    lib().orc_march_rays(u32(n_alive), u32(n_step), _p(_i32(rays_alive)), _p(_f32(rays_t)), _p(_f32(rays_o)),
+                         _p(_f32(rays_d)), f32(bound), f32(dt_gamma), u32(max_steps), u32(Cc), u32(H), _p(bitfield),
+                         _p(_f32(nears)), _p(_f32(fars)), _p(xyzs), _p(dirs), _p(deltas), _p(_f32(noises)))
+    return xyzs, dirs, deltas
+
+
+def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh=1e-2):
+    """In place on rays_alive (int32), rays_t, weights_sum, depth, image (float32, contiguous)."""
+    for a, t in ((rays_alive, np.int32), (rays_t, np.float32), (weights_sum, np.float32), (depth, np.float32),
+                 (image, np.float32)):
+        assert a.dtype == t and a.flags.c_contiguous
+    lib().orc_composite_rays(u32(n_alive), u32(n_step), f32(T_thresh), _p(rays_alive), _p(rays_t), _p(_f32(sigmas)),
+                             _p(_f32(rgbs)), _p(_f32(deltas)), _p(weights_sum), _p(depth), _p(image))
+
+
+# ---------------------------------------------------------------- gridencoder
+
+
+def grid_offsets(input_dim=3, num_levels=16, level_dim=2, per_level_scale=2.0, base_resolution=16,
+                 log2_hashmap_size=19, desired_resolution=None, align_corners=False):
+    """Level offsets exactly as gridencoder/grid.py:100-127 computes them.  Returns (offsets int32[L+1],
+    per_level_scale)."""
+    if desired_resolution is not None:
+        per_level_scale = np.exp2(np.log2(desired_resolution / base_resolution) / (num_levels - 1))
+    offsets, offset = [], 0
+    max_params = 2 ** log2_hashmap_size
+    for i in range(num_levels):
+        resolution = int(np.ceil(base_resolution * per_level_scale ** i))
+        params = min(max_params, (resolution if align_corners else resolution + 1) ** input_dim)
+        params = int(np.ceil(params / 8) * 8)
+        offsets.append(offset)
+        offset += params
+    offsets.append(offset)
+    return np.array(offsets, dtype=np.int32), float(per_level_scale)
+
+
+def grid_encode_forward(inputs, emb, offsets, per_level_scale, H, calc_grad_inputs=False, gridtype=0,
+                        align_corners=False, interp=0, half_accum=False):
+    """Returns outputs [L,B,C] (the reference's kernel layout) and dy_dx [B,L*D*C] or None."""
+    inputs, emb, offsets = _f32(inputs), _f32(emb), _i32(offsets)
+    B, D = inputs.shape
+    L, Cc = offsets.shape[0] - 1, emb.shape[1]
+    S = np.float32(np.log2(per_level_scale))
+    out = np.empty((L, B, Cc), np.float32)
+    dy_dx = np.empty((B, L * D * Cc), np.float32) if calc_grad_inputs else None
+    lib().orc_grid_encode_forward(_p(inputs), _p(emb), _p(offsets), _p(out), u32(B), u32(D), u32(Cc), u32(L), f32(S),
+                                  u32(H), _p(dy_dx), u32(gridtype), cint(int(align_corners)), u32(interp),
+                                  cint(int(half_accum)))
+    return out, dy_dx
+
+
+def grid_encode_backward(grad, inputs, emb_shape, offsets, per_level_scale, H, dy_dx=None, gridtype=0,
+                         align_corners=False, interp=0):
+    """grad [L,B,C].  Returns grad_embeddings [sO,C] (+ grad_inputs [B,D] when dy_dx is given)."""
+    grad, inputs, offsets = _f32(grad), _f32(inputs), _i32(offsets)
+    B, D = inputs.shape
+    L, Cc = offsets.shape[0] - 1, emb_shape[1]
+    S = np.float32(np.log2(per_level_scale))
+    ge = np.zeros(emb_shape, np.float32)
+    gi = np.zeros((B, D), np.float32) if dy_dx is not None else None
+    lib().orc_grid_encode_backward(_p(grad), _p(inputs), _p(offsets), _p(ge), u32(B), u32(D), u32(Cc), u32(L), f32(S),
+                                   u32(H), _p(None if dy_dx is None else _f32(dy_dx)), _p(gi), u32(gridtype),
+                                   cint(int(align_corners)), u32(interp))
+    return (ge, gi) if dy_dx is not None else ge
+
+
+def grad_total_variation(inputs, emb, grad, offsets, weight, per_level_scale, H, gridtype=0, align_corners=False):
+    inputs, emb, offsets = _f32(inputs), _f32(emb), _i32(offsets)
+    assert grad.dtype == np.float32 and grad.flags.c_contiguous
+    B, D = inputs.shape
+    L, Cc = offsets.shape[0] - 1, emb.shape[1]
+    S = np.float32(np.log2(per_level_scale))
+    lib().orc_grad_total_variation(_p(inputs), _p(emb), _p(grad), _p(offsets), f32(weight), u32(B), u32(D), u32(Cc),
+                                   u32(L), f32(S), u32(H), u32(gridtype), cint(int(align_corners)))
+
+
+def round_to_half(a):
+    a = _f32(a)
+    out = np.empty_like(a)
+    lib().orc_round_to_half(_p(a), _p(out), i64(a.size))
+    return out
+
+
+# ---------------------------------------------------------------- shencoder / freqencoder
+
+
+def sh_encode_forward(inputs, degree, calc_grad_inputs=False):
+    inputs = _f32(inputs)
+    B, D = inputs.shape
+    out = np.empty((B, degree * degree), np.float32)
+    dy_dx = np.empty((B, D * degree * degree), np.float32) if calc_grad_inputs else None
+    lib().orc_sh_encode_forward(_p(inputs), _p(out), u32(B), u32(D), u32(degree), _p(dy_dx))
+    return out, dy_dx
+
+
+def sh_encode_backward(grad, inputs, degree, dy_dx):
+    grad, inputs, dy_dx = _f32(grad), _f32(inputs), _f32(dy_dx)
+    B, D = inputs.shape
+    gi = np.zeros((B, D), np.float32)
+    lib().orc_sh_encode_backward(_p(grad), _p(inputs), u32(B), u32(D), u32(degree), _p(dy_dx), _p(gi))
+    return gi
+
+
+def freq_encode_forward(inputs, degree):
+    inputs = _f32(inputs)
+    B, D = inputs.shape
+    Cc = D + D * 2 * degree
+    out = np.empty((B, Cc), np.float32)
+    lib().orc_freq_encode_forward(_p(inputs), u32(B), u32(D), u32(degree), u32(Cc), _p(out))
+    return out
+
+
+def freq_encode_backward(grad, outputs, D, degree):
+    grad, outputs = _f32(grad), _f32(outputs)
+    B, Cc = grad.shape
+    gi = np.empty((B, D), np.float32)
+    lib().orc_freq_encode_backward(_p(grad), _p(outputs), u32(B), u32(D), u32(degree), u32(Cc), _p(gi))
+    return gi
+
+
+# ---------------------------------------------------------------- ffmlp
+
+
+def ffmlp_forward(inputs, weights, in_dim, out_dim, hidden, num_layers, act=0, out_act=6, round_half_act=False,
+                  want_buffer=True):
+    inputs, weights = _f32(inputs), _f32(weights)
+    B = inputs.shape[0]
+    fb = np.empty((num_layers, B, hidden), np.float32) if want_buffer else None
+    out = np.empty((B, out_dim), np.float32)
+    lib().orc_ffmlp_forward(_p(inputs), _p(weights), u32(B), u32(in_dim), u32(out_dim), u32(hidden), u32(num_layers),
+                            u32(act), u32(out_act), _p(fb), _p(out), cint(int(round_half_act)))
+    return out, fb
+
+
+def ffmlp_backward(grad, inputs, weights, forward_buffer, in_dim, out_dim, hidden, num_layers, act=0,
+                   calc_grad_inputs=True):
+    grad, inputs, weights, fb = _f32(grad), _f32(inputs), _f32(weights), _f32(forward_buffer)
+    B = inputs.shape[0]
+    bb = np.empty((num_layers, B, hidden), np.float32)
+    gi = np.empty((B, in_dim), np.float32) if calc_grad_inputs else None
+    gw = np.empty_like(weights)
+    lib().orc_ffmlp_backward(_p(grad), _p(inputs), _p(weights), _p(fb), u32(B), u32(in_dim), u32(out_dim), u32(hidden),
+                             u32(num_layers), u32(act), _p(bb), _p(gi), _p(gw))
+    return gw, gi, bb
+
+
+# ---------------------------------------------------------------- Seal proxy mapping
+
+
+def seal_map_mask(points, bounds, tris, test_dir=None):
+    points, bounds, tris = _f32(points), _f32(bounds).reshape(-1, 2, 3), _f32(tris).reshape(-1, 3, 3)
+    P = points.shape[0]
+    mask = np.zeros(P, np.uint8)
+    lib().orc_seal_map_mask(_p(points), i64(P), _p(bounds), u32(bounds.shape[0]), _p(tris), u32(tris.shape[0]),
+                            _p(None if test_dir is None else _f32(test_dir)), _p(mask))
+    return mask.astype(bool)
+
+
+def seal_bbox_map_to_origin(points, dirs, map_data, tris, test_dir=None):
+    """map_data: dict with transform[4,4] (inverse), rotation[3,3] (inverse), scale[3] (=1/scale), center[3],
+    map_bound [2,3]|[nb,2,3], optional empty_bound[2,3] + map_source[3] (seal_utils.py:222-236)."""
+    points, dirs = _f32(points), _f32(dirs)
+    P = points.shape[0]
+    bounds = _f32(map_data["map_bound"]).reshape(-1, 2, 3)
+    tris = _f32(tris).reshape(-1, 3, 3)
+    op, od = np.empty_like(points), np.empty_like(dirs)
+    mask = np.zeros(P, np.uint8)
+    src = _f32(map_data["empty_bound"]) if "map_source" in map_data else None
+    ms = _f32(map_data["map_source"]) if "map_source" in map_data else None
+    lib().orc_seal_bbox_map_to_origin(_p(points), _p(dirs), i64(P), _p(_f32(map_data["transform"])),
+                                      _p(_f32(map_data["rotation"])), _p(_f32(map_data["scale"])),
+                                      _p(_f32(map_data["center"])), _p(bounds), u32(bounds.shape[0]), _p(tris),
+                                      u32(tris.shape[0]), _p(None if test_dir is None else _f32(test_dir)), _p(src),
+                                      _p(ms), _p(op), _p(od), _p(mask))
+    return op, od, mask.astype(bool)
+
+
+def seal_modify_hsv(rgb, mod):
+    rgb = _f32(rgb)
+    out = np.empty_like(rgb)
+    lib().orc_seal_modify_hsv(_p(rgb), i64(rgb.shape[0]), _p(_f32(mod)), _p(out))
+    return out
+
+
+def seal_modify_rgb(rgb, target_rgb, light_offset=0.0):
+    rgb = _f32(rgb)
+    out = np.empty_like(rgb)
+    lib().orc_seal_modify_rgb(_p(rgb), i64(rgb.shape[0]), _p(_f32(target_rgb)), f32(light_offset), _p(out))
+    return out
+
+
+# ---------------------------------------------------------------- NGP field (nerf/network.py:99-128) in numpy
+
+
+class NGPField:
+    """fp32 restatement of NeRFNetwork.forward / backward (nerf/network.py:99-128, activation.py:5-17):
+    sigma = exp(h[0]), geo = h[1:16]; rgb = sigmoid(MLP([SH16 | geo15 | grid2(32)])).  Tables and weights
+    are plain numpy arrays with the state-dict shapes of SURVEY.md appendix B."""
+
+    def __init__(self, emb_sigma, emb_color, w_s0, w_s1, w_c0, w_c1, w_c2, offsets, per_level_scale, H=16, bound=1.0):
+        self.es, self.ec = _f32(emb_sigma), _f32(emb_color)
+        self.w = [_f32(w_s0), _f32(w_s1), _f32(w_c0), _f32(w_c1), _f32(w_c2)]
+        self.offsets, self.pls, self.H, self.bound = _i32(offsets), per_level_scale, H, bound
+
+    def _enc(self, x, emb):
+        u = ((_f32(x) + np.float32(self.bound)) / np.float32(2 * self.bound)).astype(np.float32)
+        out, _ = grid_encode_forward(u, emb, self.offsets, self.pls, self.H)
+        return u, np.ascontiguousarray(out.transpose(1, 0, 2).reshape(u.shape[0], -1))
+
+    def forward(self, x, d, keep=False):
+        ws0, ws1, wc0, wc1, wc2 = self.w
+        u, f_s = self._enc(x, self.es)
+        h1 = np.maximum(f_s @ ws0.T, 0)
+        h2 = h1 @ ws1.T
+        sigma = np.exp(h2[:, 0])
+        sh, _ = sh_encode_forward(d, 4)
+        _, f_c = self._enc(x, self.ec)
+        cin = np.concatenate([sh, h2[:, 1:], f_c], axis=1)
+        c1 = np.maximum(cin @ wc0.T, 0)
+        c2 = np.maximum(c1 @ wc1.T, 0)
+        rgb = 1.0 / (1.0 + np.exp(-(c2 @ wc2.T)))
+        if keep:
+            self._saved = (u, f_s, h1, h2, cin, c1, c2, rgb)
+        return sigma.astype(np.float32), rgb.astype(np.float32)
+
+    def density(self, x):
+        ws0, ws1 = self.w[0], self.w[1]
+        _, f_s = self._enc(x, self.es)
+        h2 = np.maximum(f_s @ ws0.T, 0) @ ws1.T
+        return np.exp(h2[:, 0]).astype(np.float32), h2[:, 1:].astype(np.float32)
+
+    def backward(self, g_sigma, g_rgb):
+        """Returns dict of grads for emb_sigma, emb_color and the 5 weights (after forward(keep=True))."""
+        ws0, ws1, wc0, wc1, wc2 = self.w
+        u, f_s, h1, h2, cin, c1, c2, rgb = self._saved
+        g_o = _f32(g_rgb) * rgb * (1 - rgb)
+        g_wc2 = g_o.T @ c2
+        g_c2 = (g_o @ wc2) * (c2 > 0)
+        g_wc1 = g_c2.T @ c1
+        g_c1 = (g_c2 @ wc1) * (c1 > 0)
+        g_wc0 = g_c1.T @ cin
+        g_cin = g_c1 @ wc0
+        g_h2 = np.empty_like(h2)
+        g_h2[:, 0] = _f32(g_sigma) * np.exp(np.clip(h2[:, 0], -15, 15))
+        g_h2[:, 1:] = g_cin[:, 16:31]
+        g_fc = g_cin[:, 31:]
+        g_ws1 = g_h2.T @ h1
+        g_h1 = (g_h2 @ ws1) * (h1 > 0)
+        g_ws0 = g_h1.T @ f_s
+        g_fs = g_h1 @ ws0
+        L = self.offsets.shape[0] - 1
+
+        def tab(gf, shape):
+            g = np.ascontiguousarray(_f32(gf).reshape(gf.shape[0], L, -1).transpose(1, 0, 2))
+            return grid_encode_backward(g, u, shape, self.offsets, self.pls, self.H)
+
+        return dict(emb_sigma=tab(g_fs, self.es.shape), emb_color=tab(g_fc, self.ec.shape), w_s0=g_ws0, w_s1=g_ws1,
+                    w_c0=g_wc0, w_c1=g_wc1, w_c2=g_wc2)
+
+
+# ---------------------------------------------------------------- distillation losses (numpy)
+
+
+def pretrain_loss(sigma_s, rgb_s, sigma_t, rgb_t):
+    """SealNeRF/trainer.py:456-469: L1(sigma) + L1(rgb), mean reductions.  Returns loss, dL/dsigma_s, dL/drgb_s."""
+    ds, dc = sigma_s - sigma_t, rgb_s - rgb_t
+    loss = np.abs(ds).mean() + np.abs(dc).mean()
+    return loss, np.sign(ds) / ds.size, np.sign(dc) / dc.size
+
+
+def finetune_loss(image_s, depth_s, image_t, depth_t):
+    """nerf/utils.py:484-489,530: mean_rays(mean_c (rgb - gt)^2) + mean|depth - gt_depth|.
+    Returns loss, dL/dimage, dL/ddepth (the latter is dropped by the compositor, raymarching.py:275)."""
+    N = image_s.shape[0]
+    dr = image_s - image_t
+    dd = depth_s - depth_t
+    loss = (dr ** 2).mean(-1).mean() + np.abs(dd).mean()
+    return loss, 2 * dr / (3 * N), np.sign(dd) / N
