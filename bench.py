@@ -1,0 +1,330 @@
+"""bench.py -- training rays/s of the Seal-3D distillation hot path on B200 (BASELINE.json metric).
+
+A "step" = one teacher->student distillation step on a batch of synthetic Lego-shaped rays
+(800x800 cameras, NGP L16/F2 hash grids, analytic occupancy, bbox edit):
+    near/far -> march (student occupancy) -> proxy map + teacher field (no grad) -> student field ->
+    composite both -> MSE(rgb)+L1(depth) -> backward -> [all-reduce of the gradient arena] -> fused Adam
+(+ the density-grid refresh every 16 steps).  Ray batches shard across ranks (weak scaling: every
+GPU gets --rays rays per step); the only collective is the per-step gradient all-reduce.
+
+  python bench.py --gpus 1 --steps 20 --warmup 5
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference      # the CPU restatement of the same step on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = rays/s with the ray batches already resident in HBM;
+`e2e` = the same through the public trainer call with host (pinned) ray buffers copied in and the
+loss read back every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = "seal3d-distill-step/lego800x800-synthetic/ngp-L16-F2-T19/bbox-edit"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=int(os.environ.get("S3D_BENCH_RAYS", 65536)), help="rays per step per GPU")
+    ap.add_argument("--precision", default=os.environ.get("S3D_BENCH_PRECISION", "fp16"), choices=["fp32", "fp16"])
+    ap.add_argument("--cpu-rays", type=int, default=1024, help="rays per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+
+
+class CpuDistill:
+    """The same distillation step composed from the oracle's C / numpy restatement (oracle/), on the host cores."""
+
+    def __init__(self, n_rays):
+        import oracle
+        from seal3d_b200 import synth
+        self.oracle, self.synth, self.n = oracle, synth, n_rays
+        self.bits, _ = synth.lego_like_occupancy()
+        self.offsets, self.pls = synth.grid_offsets()
+        tp, sp = synth.field_params("teacher"), synth.field_params("student")
+        mk = lambda p: oracle.NGPField(p["emb_sigma"], p["emb_color"], p["w_s0"], p["w_s1"], p["w_c0"], p["w_c1"], p["w_c2"], self.offsets, self.pls)
+        self.teacher, self.student = mk(tp), mk(sp)
+        self.md, self.tris = synth.bbox_edit()
+        self.params = [self.student.es, self.student.ec] + self.student.w
+        self.m = [np.zeros_like(p) for p in self.params]
+        self.v = [np.zeros_like(p) for p in self.params]
+        self.t = 0
+        self.aabb = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+
+    def step(self, i):
+        oc = self.oracle
+        o, d = self.synth.rays_for_step(i, self.n)
+        n, f = oc.near_far_from_aabb(o, d, self.aabb, 0.2)
+        noise = np.random.default_rng(i).uniform(0, 1, self.n).astype(np.float32)
+        # count first (M=0 writes nothing), then allocate exactly
+        _, _, _, rays, cnt = oc.march_rays_train(o, d, 1.0, self.bits, 1, 128, n, f, noise, M=0)
+        M = int(cnt[0])
+        xyzs, dirs, deltas, rays, _ = oc.march_rays_train(o, d, 1.0, self.bits, 1, 128, n, f, noise, M=max(M, 1))
+        mx, mdirs, mask = oc.seal_bbox_map_to_origin(xyzs, dirs, self.md, self.tris)
+        sig_t, rgb_t = self.teacher.forward(mx, mdirs)
+        ws_t, dep_t, img_t = oc.composite_rays_train_forward(sig_t, rgb_t, deltas, rays)
+        img_t = img_t + (1 - ws_t)[:, None]
+        sig_s, rgb_s = self.student.forward(xyzs, dirs, keep=True)
+        ws, dep, comp = oc.composite_rays_train_forward(sig_s, rgb_s, deltas, rays)
+        loss, g_img, _ = oc.finetune_loss(comp + (1 - ws)[:, None], dep, img_t, dep_t)
+        g_ws = -g_img.sum(1)
+        gs, gc = oc.composite_rays_train_backward(g_ws, g_img, sig_s, rgb_s, deltas, rays, ws, comp)
+        gr = self.student.backward(gs, gc)
+        grads = [gr["emb_sigma"], gr["emb_color"], gr["w_s0"], gr["w_s1"], gr["w_c0"], gr["w_c1"], gr["w_c2"]]
+        self.t += 1
+        b1, b2, lr, eps = 0.9, 0.99, 1e-2, 1e-15
+        for p, g, m, v in zip(self.params, grads, self.m, self.v):
+            m *= b1; m += (1 - b1) * g
+            v *= b2; v += (1 - b2) * g * g
+            p -= (lr / (1 - b1 ** self.t)) * m / (np.sqrt(v) / np.sqrt(1 - b2 ** self.t) + eps)
+        return float(loss), M
+
+
+def cpu_arm(n_rays, steps, warmup):
+    import oracle
+    c = CpuDistill(n_rays)
+    for i in range(warmup):
+        c.step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        _, M = c.step(warmup + i)
+    dt = time.perf_counter() - t0
+    return dict(value=n_rays * steps / dt, unit="rays/s", cores=oracle.num_threads(), kind="port",
+                sample="%d distillation steps of %d rays (%d samples/step) with the oracle's C/numpy restatement (oracle/)" % (steps, n_rays, M),
+                ms_per_step=1e3 * dt / steps)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+
+
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+
+
+def build_world(dev, precision, seed_rank=0):
+    import torch
+    from seal3d_b200 import synth
+    from seal3d_b200.seal import TeacherNetwork, StudentNetwork, SealBBoxMapper
+    from seal3d_b200.trainer import DistillTrainer
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    bits, grid = synth.lego_like_occupancy()
+    t, s = TeacherNetwork(bound=1).to(dev), StudentNetwork(bound=1).to(dev)
+    for net, kind in ((t, "teacher"), (s, "student")):
+        fp = synth.field_params(kind)
+        net.encoder.embeddings.data.copy_(to(fp["emb_sigma"]))
+        net.encoder_color.embeddings.data.copy_(to(fp["emb_color"]))
+        for lin, k in ((net.sigma_net[0], "w_s0"), (net.sigma_net[1], "w_s1"), (net.color_net[0], "w_c0"), (net.color_net[1], "w_c1"), (net.color_net[2], "w_c2")):
+            lin.weight.data.copy_(to(fp[k]))
+        net.density_bitfield.copy_(to(bits))
+        net.density_grid.copy_(to(grid))
+    md, tris = synth.bbox_edit()
+    mapper = SealBBoxMapper(md, tris, device=dev)
+    for net in (t, s):
+        net.init_mapper(mapper)
+        net.hack_bitfield()
+    t.eval()
+    for p in t.parameters():
+        p.requires_grad_(False)
+    return t, s
+
+
+def roofline_grid_encode(dev, precision):
+    """dominant kernel of the step: the hash-grid gather.  Timed alone on B = 2^22 random points (inputs 48 MB +
+    outputs > L2 between launches), CUDA events on the launching stream; algorithmic bytes per point from
+    SURVEY.md 8(d): 12 + 16*8*2*s + 16*2*s (s = bytes per table element)."""
+    import torch
+    from seal3d_b200 import _lib, synth
+    offsets, pls = synth.grid_offsets()
+    B = 1 << 22
+    dt = torch.float16 if precision == "fp16" else torch.float32
+    s_el = 2 if precision == "fp16" else 4
+    g = torch.Generator(device=dev).manual_seed(8)
+    x = torch.rand(B, 3, device=dev, generator=g)
+    emb = (torch.rand(int(offsets[-1]), 2, device=dev, generator=g) * 2e-4 - 1e-4).to(dt)
+    out = torch.empty(16, B, 2, device=dev, dtype=dt)
+    off = torch.from_numpy(offsets).to(dev)
+    S = float(np.log2(pls))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    times = []
+    for it in range(8):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call("s3d_grid_encode_forward", x, emb, off, out, B, 3, 2, 16, S, 16, None, 0, 0, 0, 0 if s_el == 4 else 1)
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            times.append(e0.elapsed_time(e1) * 1e-3)
+    per_pt = 12 + 16 * 8 * 2 * s_el + 16 * 2 * s_el
+    t = float(np.mean(times))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = B * per_pt / t / 1e9
+    return dict(kernel="k_grid_forward<%s,3,2,all-levels>" % ("half" if s_el == 2 else "float"), bound="hbm", achieved=ach, peak=peak,
+                unit="GB/s", frac=ach / peak, traffic=None, peak_source="MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6.65 TB/s",
+                points=B, bytes_per_point=per_pt, launch_ms=t * 1e3)
+
+
+def gpu_arm(args):
+    import torch
+    from seal3d_b200 import synth, parallel, _lib
+    rank, local, world = parallel.init_from_env()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    from seal3d_b200.trainer import DistillTrainer
+    teacher, student = build_world(dev, args.precision)
+    tr = DistillTrainer(student, teacher, lr=1e-2, precision=args.precision, loss_scale=(128.0 if args.precision == "fp16" else 1.0),
+                        world_size=world, update_interval=16)
+    n = args.rays
+    pool = 4
+    host = []
+    for b in range(pool):
+        o, d = synth.rays_for_step(1000 * rank + b, n)
+        host.append((torch.from_numpy(o).pin_memory(), torch.from_numpy(d).pin_memory()))
+    resident = [(o.to(dev), d.to(dev)) for o, d in host]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (first steps run in exact mode and set mean_count)
+    for i in range(args.warmup):
+        o, d = resident[i % pool]
+        tr.distill_step(o, d, perturb=True, force_all_rays=(i < 2))
+    if tr.student.mean_count <= 0:
+        tr.refresh_occupancy()
+    samples_per_step = float(tr.student.step_counter[:, 0].float().max().item())
+
+    # -- leg 1: resident inputs ---------------------------------------------------------------
+    barrier()
+    clocks = ClockSampler(local)
+    launches0 = _lib.LAUNCHES if hasattr(_lib, "LAUNCHES") else 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        o, d = resident[i % pool]
+        tr.distill_step(o, d, perturb=True)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    ms = parallel.max_over_ranks(ms, dev)
+    clk = clocks.stop()
+
+    # -- leg 2: end to end through the public call, host buffers in, loss out, every step -------
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    last = None
+    for i in range(args.steps):
+        ho, hd = host[i % pool]
+        o, d = ho.to(dev, non_blocking=True), hd.to(dev, non_blocking=True)
+        last = tr.distill_step(o, d, perturb=True).cpu()
+    e1.record()
+    barrier()
+    ms_e2e = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
+
+    if rank != 0:
+        return None
+    rays_total = n * world * args.steps
+    line = {
+        "metric": "training rays/sec (Lego 800x800, NGP L16/F2, distill on)", "value": rays_total / (ms * 1e-3), "unit": "rays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "global_rays_per_step": n * world, "samples_per_step_per_gpu": samples_per_step,
+                   "samples_per_ray": samples_per_step / n, "parallelism": "dp%d (ray shards, one grad all-reduce/step)" % world,
+                   "schedule": "fused teacher+student on shared samples; occupancy refresh every 16 steps",
+                   "l2_note": "each step streams > 126 MB (samples + 4 tables + arena) so successive steps do not reuse L2 contents"},
+        "e2e": {"value": rays_total / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(getattr(_lib, "LAUNCHES", 0) - launches0) if hasattr(_lib, "LAUNCHES") else None,
+        "clocks": clk, "loss_last": [float(v) for v in last.numpy()] if last is not None else None,
+    }
+    return line
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # the reference has no CPU path of its own (every op requires CUDA tensors); the CPU arm is the
+        # oracle's restatement of the same step, on all host threads OpenMP / BLAS give it
+        r = cpu_arm(args.cpu_rays, max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)))
+        line = {"impl": "reference", "metric": "training rays/sec (Lego 800x800, NGP L16/F2, distill on)", "value": r["value"], "unit": "rays/s",
+                "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)), "warmup": max(1, min(args.warmup, 1)), "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "rays_per_step": args.cpu_rays}, "cpu_baseline": r,
+                "e2e": {"value": r["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+    line = gpu_arm(args)
+    if line is None:
+        return
+    import torch
+    if not args.no_roofline:
+        line["roofline"] = roofline_grid_encode(torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))), args.precision)
+    if not args.no_cpu_baseline and line["n_gpus"] == 1:
+        line["cpu_baseline"] = cpu_arm(args.cpu_rays, 2, 1)
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,169 @@
+/*
+ * seal3d_b200.h -- C ABI of libseal3d_b200.so: the sm_100a implementation of Seal-3D's hot path.
+ *
+ * Every entry point below replaces one function of the reference's pybind surface (the file:line
+ * of the declaration it replaces is cited) or adds a fused / training entry that the reference
+ * spreads over Python.  Conventions:
+ *   - plain C: device pointers + sizes, no torch / C++ types.  All array pointers are DEVICE
+ *     pointers unless the parameter name starts with h_ (small host-side constant blocks).
+ *   - the CALLER allocates every output (like the reference, SURVEY.md 8b "Ownership").
+ *   - the last argument is the cudaStream_t to launch on (as void*); calls are asynchronous.
+ *   - return value: 0 ok; > 0 a cudaError_t from the launch; < 0 an argument error
+ *     (S3D_EINVAL = -22, S3D_ENOTSUP = -95: shape not built).  The reference throws
+ *     std::runtime_error / TORCH_CHECK in the same situations; the pybind shims translate
+ *     non-zero codes back into RuntimeError.
+ *   - float tensors are float32 unless a `dtype` argument says otherwise (0 = f32, 1 = f16).
+ */
+#ifndef SEAL3D_B200_H
+#define SEAL3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ raymarching ----------- */
+/* raymarching/src/raymarching.h:7   near_far_from_aabb(rays_o, rays_d, aabb, N, min_near, nears, fars) */
+int s3d_near_far_from_aabb(const float *rays_o, const float *rays_d, const float *aabb, uint32_t N, float min_near,
+                           float *nears, float *fars, void *stream);
+/* raymarching.h:8   sph_from_ray(rays_o, rays_d, radius, N, coords[N,2]) */
+int s3d_sph_from_ray(const float *rays_o, const float *rays_d, float radius, uint32_t N, float *coords, void *stream);
+/* raymarching.h:9   morton3D(coords int32[N,3], N, indices int32[N]) */
+int s3d_morton3D(const int *coords, uint32_t N, int *indices, void *stream);
+/* raymarching.h:10  morton3D_invert(indices, N, coords) */
+int s3d_morton3D_invert(const int *indices, uint32_t N, int *coords, void *stream);
+/* raymarching.h:11  packbits(grid float[C*H^3], N = C*H^3/8, density_thresh, bitfield uint8[N]) */
+int s3d_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t *bitfield, void *stream);
+/* raymarching.h:13  march_rays_train(...).  xyzs/dirs/deltas must be zero-filled by the caller (rows past the
+ * last sample stay zero); rays int32[N,3] = (ray id, first sample, sample count) in ray-major, deterministic
+ * order; counter int32[2] += (total samples, N); noises float[N] or NULL (= 0). */
+int s3d_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
+                         uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float *nears,
+                         const float *fars, float *xyzs, float *dirs, float *deltas, int *rays, int *counter,
+                         const float *noises, void *stream);
+/* the same op in two phases, for an exactly-sized sample buffer (count+scan, then write) */
+int s3d_march_rays_train_count(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                               float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                               const float *nears, const float *fars, int *rays, int *counter, const float *noises,
+                               void *stream);
+int s3d_march_rays_train_write(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                               float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                               const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
+                               const int *rays, const float *noises, void *stream);
+/* raymarching.h:14  composite_rays_train_forward */
+int s3d_composite_rays_train_forward(const float *sigmas, const float *rgbs, const float *deltas, const int *rays,
+                                     uint32_t M, uint32_t N, float T_thresh, float *weights_sum, float *depth,
+                                     float *image, void *stream);
+/* raymarching.h:15  composite_rays_train_backward (grad_sigmas / grad_rgbs zero-filled by the caller) */
+int s3d_composite_rays_train_backward(const float *grad_weights_sum, const float *grad_image, const float *sigmas,
+                                      const float *rgbs, const float *deltas, const int *rays,
+                                      const float *weights_sum, const float *image, uint32_t M, uint32_t N,
+                                      float T_thresh, float *grad_sigmas, float *grad_rgbs, void *stream);
+/* raymarching.h:17  march_rays (inference; outputs zero-filled by the caller, fixed stride n_step) */
+int s3d_march_rays(uint32_t n_alive, uint32_t n_step, const int *rays_alive, const float *rays_t, const float *rays_o,
+                   const float *rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                   const uint8_t *grid, const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
+                   const float *noises, void *stream);
+/* raymarching.h:18  composite_rays (in place; finished rays get rays_alive = -1) */
+int s3d_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int *rays_alive, float *rays_t,
+                       const float *sigmas, const float *rgbs, const float *deltas, float *weights_sum, float *depth,
+                       float *image, void *stream);
+
+/* ------------------------------------------------------------------ gridencoder ----------- */
+/* gridencoder/src/gridencoder.h:12  grid_encode_forward.  inputs float[B,D] in [0,1]; embeddings [sO,C];
+ * offsets int32[L+1]; outputs [L,B,C]; dy_dx [B,L,D,C] or NULL; S = log2(per_level_scale); gridtype 0 hash /
+ * 1 tiled; interp 0 linear / 1 smoothstep.  D in 2..4, C in {1,2,4,8}. */
+int s3d_grid_encode_forward(const float *inputs, const void *embeddings, const int *offsets, void *outputs, uint32_t B,
+                            uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, void *dy_dx, uint32_t gridtype,
+                            int align_corners, uint32_t interp, int dtype, void *stream);
+/* gridencoder.h:13  grid_encode_backward.  grad [L,B,C]; grad_embeddings is accumulated into (caller zero-fills);
+ * dy_dx / grad_inputs [B,D] optional. */
+int s3d_grid_encode_backward(const void *grad, const float *inputs, const void *embeddings, const int *offsets,
+                             void *grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                             const void *dy_dx, void *grad_inputs, uint32_t gridtype, int align_corners, uint32_t interp,
+                             int dtype, void *stream);
+/* gridencoder.h:15  grad_total_variation (float32 tables only) */
+int s3d_grad_total_variation(const void *inputs, const void *embeddings, void *grad, const int *offsets, float weight,
+                             uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                             int align_corners, int dtype, void *stream);
+
+/* ------------------------------------------------------------------ shencoder / freqencoder */
+/* shencoder/src/shencoder.h:9   sh_encode_forward(inputs[B,3], outputs[B,C*C], B, D=3, C=degree<=8, dy_dx[B,3*C*C]|NULL) */
+int s3d_sh_encode_forward(const float *inputs, float *outputs, uint32_t B, uint32_t D, uint32_t C, float *dy_dx,
+                          void *stream);
+/* shencoder.h:10  sh_encode_backward: grad_inputs[B,3] += sum_ch grad * dy_dx */
+int s3d_sh_encode_backward(const float *grad, const float *inputs, uint32_t B, uint32_t D, uint32_t C,
+                           const float *dy_dx, float *grad_inputs, void *stream);
+/* freqencoder/src/freqencoder.h:7   freq_encode_forward(inputs[B,D], B, D, deg, C = D + 2*D*deg, outputs[B,C]) */
+int s3d_freq_encode_forward(const float *inputs, uint32_t B, uint32_t D, uint32_t deg, uint32_t C, float *outputs,
+                            void *stream);
+/* freqencoder.h:10  freq_encode_backward(grad[B,C], outputs[B,C], ..., grad_inputs[B,D]) */
+int s3d_freq_encode_backward(const float *grad, const float *outputs, uint32_t B, uint32_t D, uint32_t deg, uint32_t C,
+                             float *grad_inputs, void *stream);
+
+/* ------------------------------------------------------------------ ffmlp (all tensors float16) */
+/* ffmlp/src/ffmlp.h:8   ffmlp_forward: inputs[B,in], weights flat [hidden*in | hidden*hidden*(nl-1) | out*hidden],
+ * forward_buffer[nl,B,hidden], outputs[B,out].  hidden in {16,32,64}, in % 16 == 0 (<= 256), out <= 16, nl in 2..5. */
+int s3d_ffmlp_forward(const void *inputs, const void *weights, uint32_t B, uint32_t input_dim, uint32_t output_dim,
+                      uint32_t hidden_dim, uint32_t num_layers, uint32_t activation, uint32_t output_activation,
+                      void *forward_buffer, void *outputs, void *stream);
+/* ffmlp.h:9   ffmlp_inference (no activations are written; inference_buffer unused) */
+int s3d_ffmlp_inference(const void *inputs, const void *weights, uint32_t B, uint32_t input_dim, uint32_t output_dim,
+                        uint32_t hidden_dim, uint32_t num_layers, uint32_t activation, uint32_t output_activation,
+                        void *inference_buffer, void *outputs, void *stream);
+/* ffmlp.h:11  ffmlp_backward: grad[B,out], backward_buffer[nl,B,hidden], grad_inputs[B,in] (if calc_grad_inputs),
+ * grad_weights flat (overwritten) */
+int s3d_ffmlp_backward(const void *grad, const void *inputs, const void *weights, const void *forward_buffer, uint32_t B,
+                       uint32_t input_dim, uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers,
+                       uint32_t activation, uint32_t output_activation, int calc_grad_inputs, void *backward_buffer,
+                       void *grad_inputs, void *grad_weights, void *stream);
+/* ffmlp.h:13-14  allocate_splitk / free_splitk: kept for interface parity, nothing to allocate */
+int s3d_allocate_splitk(size_t size);
+int s3d_free_splitk(void);
+
+/* ------------------------------------------------------------------ Seal proxy mapping ---- */
+/* SealNeRF/seal_utils.py:237-279 SealBBoxMapper.map_to_origin (+ :132-153 map_mask, :630-685 points_in_mesh):
+ * h_transform[16] inverse 4x4 row-major, h_rotation[9] inverse 3x3, h_scale[3] = 1/scale, h_center[3];
+ * bounds device [nb,2,3]; tris device [F,3,3]; h_test_dir[3]|NULL; h_src_bound[6]+h_map_source[3]|NULL;
+ * out_points/out_dirs are full copies with the masked rows replaced; mask uint8[P]. */
+int s3d_seal_bbox_map_to_origin(const float *points, const float *dirs, uint32_t P, const float *h_transform,
+                                const float *h_rotation, const float *h_scale, const float *h_center,
+                                const float *bounds, uint32_t nb, const float *tris, uint32_t F, const float *h_test_dir,
+                                const float *h_src_bound, const float *h_map_source, float *out_points, float *out_dirs,
+                                uint8_t *mask, void *stream);
+/* seal_utils.py:48-57,739-769 SealMapper.map_color (hsv shift and/or rgb replacement with V re-lighting around the
+ * batch mean of V), in place on rows with mask != 0; d_stats = device float[2] scratch */
+int s3d_seal_map_color(float *rgbs, const uint8_t *mask, uint32_t M, const float *h_hsv_mod, const float *h_rgb_target,
+                       float light_offset, float *d_stats, void *stream);
+/* SealNeRF/renderer.py:21-66 init_mapper + hack_bitfield: cells [h_cell_lo, h_cell_hi) -> bitfield bytes = 255 */
+int s3d_seal_force_fill_bitfield(uint8_t *bitfield, const int *h_cell_lo, const int *h_cell_hi, uint32_t H,
+                                 uint32_t cascade_index, void *stream);
+
+/* ------------------------------------------------------------------ distillation step glue - */
+/* SealNeRF/trainer.py:456-469: loss[0] += mean|ds| + mean|dc|; grads of the means (either may be NULL) */
+int s3d_pretrain_loss(const float *sigma_s, const float *rgb_s, const float *sigma_t, const float *rgb_t, uint32_t M,
+                      float *loss, float *grad_sigma, float *grad_rgb, void *stream);
+/* nerf/utils.py:484-489,530: student image = comp + (1-ws)*bg; loss[0] += MSE, loss[1] += L1 depth (if depth_t);
+ * grad_image = dL/dcomp, grad_ws = dL/dws */
+int s3d_finetune_loss(const float *comp_s, const float *ws_s, const float *depth_s, const float *image_t,
+                      const float *depth_t, uint32_t N, float bg_color, float *loss, float *grad_image, float *grad_ws,
+                      void *stream);
+/* main_SealNeRF.py:283-284 torch.optim.Adam semantics in one pass over a flat arena; writes the fp16 shadow
+ * (or NULL) and zeroes the gradient when asked.  grad_dtype 0 = f32, 1 = f16. */
+int s3d_adam_step(float *params, void *grads, float *exp_avg, float *exp_avg_sq, void *shadow_f16, uint64_t n, float lr,
+                  float beta1, float beta2, float eps, uint32_t step, float grad_scale, int zero_grad, int grad_dtype,
+                  void *stream);
+int s3d_cast_f32_to_f16(const float *src, void *dst, uint64_t n, void *stream);
+/* nerf/renderer.py:445-538 update_extra_state pieces */
+int s3d_density_cells_to_xyz(const int *cell_morton, uint32_t n, uint32_t H, float bound_cas, uint32_t seed, float *xyz,
+                             void *stream);
+int s3d_density_scatter(const int *cell_morton, const float *sigma, uint32_t n, float density_scale, float *tmp_grid,
+                        void *stream);
+int s3d_density_grid_ema(float *grid, const float *tmp_grid, uint32_t n, float decay, float *sum_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEAL3D_B200_H */

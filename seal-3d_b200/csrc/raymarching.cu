@@ -1,0 +1,558 @@
+// Occupancy-grid ray marching and alpha compositing for sm_100a.
+//
+// Replaces raymarching/src/raymarching.cu of the reference (entry points raymarching.h:7-18).
+// Design differences (not a port):
+//   * march_rays_train is count -> single-CTA exclusive scan -> write.  Sample slots are
+//     assigned ray-major and deterministically (the reference allocates them with two global
+//     atomics per ray, raymarching.cu:405-406, so its slot order changes run to run).
+//   * every float operation whose rounding decides which voxel / lattice point a ray visits is
+//     written with explicit round-to-nearest intrinsics (__fmaf_rn / __fmul_rn / __fadd_rn) at
+//     exactly the places nvcc contracts the reference expressions, so per-ray sample counts
+//     and positions are bit-identical by construction rather than by compiler accident.
+//   * the double-precision detour of raymarching.cu:374-376 is taken only when H is not a
+//     power of two (it is an exact no-op otherwise).
+//   * all launches go to the caller's stream (the reference uses the legacy default stream).
+#include "common.cuh"
+#include <float.h>
+
+namespace {
+
+constexpr float kSqrt3 = 1.7320508075688772f;
+constexpr float kRPi = 0.3183098861837907f;
+
+__host__ __device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__host__ __device__ __forceinline__ uint32_t morton3(uint32_t x, uint32_t y, uint32_t z) {
+    return expand_bits10(x) | (expand_bits10(y) << 1) | (expand_bits10(z) << 2);
+}
+__host__ __device__ __forceinline__ uint32_t compact_bits10(uint32_t x) {
+    x &= 0x49249249u;
+    x = (x | (x >> 2)) & 0xc30c30c3u;
+    x = (x | (x >> 4)) & 0x0f00f00fu;
+    x = (x | (x >> 8)) & 0xff0000ffu;
+    x = (x | (x >> 16)) & 0x0000ffffu;
+    return x;
+}
+
+// ---------------------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------------------
+
+__global__ void k_near_far(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+                           const float *__restrict__ aabb, uint32_t N, float min_near, float *__restrict__ nears,
+                           float *__restrict__ fars) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float rdx = __fdiv_rn(1.0f, rays_d[n * 3]), rdy = __fdiv_rn(1.0f, rays_d[n * 3 + 1]),
+                rdz = __fdiv_rn(1.0f, rays_d[n * 3 + 2]);
+    float tn = __fmul_rn(__fsub_rn(aabb[0], ox), rdx), tf = __fmul_rn(__fsub_rn(aabb[3], ox), rdx);
+    if (tn > tf) { const float s = tn; tn = tf; tf = s; }
+    float yn = __fmul_rn(__fsub_rn(aabb[1], oy), rdy), yf = __fmul_rn(__fsub_rn(aabb[4], oy), rdy);
+    if (yn > yf) { const float s = yn; yn = yf; yf = s; }
+    bool miss = (tn > yf) || (yn > tf);
+    if (!miss) {
+        if (yn > tn) tn = yn;
+        if (yf < tf) tf = yf;
+        float zn = __fmul_rn(__fsub_rn(aabb[2], oz), rdz), zf = __fmul_rn(__fsub_rn(aabb[5], oz), rdz);
+        if (zn > zf) { const float s = zn; zn = zf; zf = s; }
+        miss = (tn > zf) || (zn > tf);
+        if (!miss) {
+            if (zn > tn) tn = zn;
+            if (zf < tf) tf = zf;
+            if (tn < min_near) tn = min_near;
+        }
+    }
+    nears[n] = miss ? FLT_MAX : tn;
+    fars[n] = miss ? FLT_MAX : tf;
+}
+
+__global__ void k_sph_from_ray(const float *__restrict__ rays_o, const float *__restrict__ rays_d, float radius,
+                               uint32_t N, float *__restrict__ coords) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float dx = rays_d[n * 3], dy = rays_d[n * 3 + 1], dz = rays_d[n * 3 + 2];
+    const float A = dx * dx + dy * dy + dz * dz;
+    const float Bh = ox * dx + oy * dy + oz * dz;
+    const float Cc = ox * ox + oy * oy + oz * oz - radius * radius;
+    const float t = (-Bh + sqrtf(Bh * Bh - A * Cc)) / A;
+    const float x = ox + t * dx, y = oy + t * dy, z = oz + t * dz;
+    coords[n * 2] = 2 * atan2f(sqrtf(x * x + z * z), y) * kRPi - 1;
+    coords[n * 2 + 1] = atan2f(z, x) * kRPi;
+}
+
+__global__ void k_morton3D(const int *__restrict__ coords, uint32_t N, int *__restrict__ indices) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    indices[n] = (int)morton3((uint32_t)coords[n * 3], (uint32_t)coords[n * 3 + 1], (uint32_t)coords[n * 3 + 2]);
+}
+
+__global__ void k_morton3D_invert(const int *__restrict__ indices, uint32_t N, int *__restrict__ coords) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int ind = indices[n];  // arithmetic shifts of a signed value, as the reference does
+    coords[n * 3] = (int)compact_bits10((uint32_t)(ind >> 0));
+    coords[n * 3 + 1] = (int)compact_bits10((uint32_t)(ind >> 1));
+    coords[n * 3 + 2] = (int)compact_bits10((uint32_t)(ind >> 2));
+}
+
+// one thread packs 32 cells (128 B of density, 4 B of bitfield) with two 128-bit loads in flight
+__global__ void k_packbits(const float *__restrict__ grid, uint32_t N, float thresh, uint8_t *__restrict__ bitfield) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;  // index of a 4-byte word of the bitfield
+    const uint32_t first = w * 4;
+    if (first >= N) return;
+    if (first + 4 <= N && ((reinterpret_cast<uintptr_t>(grid) | reinterpret_cast<uintptr_t>(bitfield)) & 15) == 0) {
+        const float4 *g = reinterpret_cast<const float4 *>(grid) + (size_t)w * 8;
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float4 v = __ldg(g + i);
+            bits |= (uint32_t)(v.x > thresh) << (4 * i) | (uint32_t)(v.y > thresh) << (4 * i + 1) |
+                    (uint32_t)(v.z > thresh) << (4 * i + 2) | (uint32_t)(v.w > thresh) << (4 * i + 3);
+        }
+        reinterpret_cast<uint32_t *>(bitfield)[w] = bits;
+    } else {
+        for (uint32_t n = first; n < N && n < first + 4; n++) {
+            uint8_t b = 0;
+            for (int i = 0; i < 8; i++) b |= (grid[(size_t)n * 8 + i] > thresh) ? (uint8_t)(1u << i) : 0;
+            bitfield[n] = b;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// marching
+// ---------------------------------------------------------------------------------------
+
+struct MarchCfg {
+    float bound, dt_gamma, dt_min, dt_max, rH, H3f, Hf, Hm1f, halfH;
+    uint32_t C, H;
+    int h_pow2;
+    const uint8_t *grid;
+};
+
+struct Ray {
+    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz, sx, sy, sz;  // s* = 0.5*sign(d*)
+};
+
+__device__ __forceinline__ MarchCfg make_cfg(const uint8_t *grid, float bound, float dt_gamma, uint32_t max_steps,
+                                             uint32_t C, uint32_t H) {
+    MarchCfg c;
+    c.bound = bound; c.dt_gamma = dt_gamma; c.C = C; c.H = H; c.grid = grid;
+    c.Hf = (float)H; c.Hm1f = (float)(H - 1);
+    c.rH = __fdiv_rn(1.0f, c.Hf);
+    c.H3f = (float)(H * H * H);
+    c.dt_min = __fdiv_rn(__fmul_rn(2.0f, kSqrt3), (float)max_steps);                                  // raymarching.cu:345
+    c.dt_max = __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, kSqrt3), (float)(1 << (C - 1))), c.Hf);             // raymarching.cu:346
+    c.h_pow2 = (H & (H - 1)) == 0;
+    c.halfH = 0.5f * c.Hf;
+    return c;
+}
+
+__device__ __forceinline__ Ray load_ray(const float *__restrict__ o, const float *__restrict__ d) {
+    Ray r;
+    r.ox = o[0]; r.oy = o[1]; r.oz = o[2];
+    r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
+    r.rdx = __fdiv_rn(1.0f, r.dx); r.rdy = __fdiv_rn(1.0f, r.dy); r.rdz = __fdiv_rn(1.0f, r.dz);
+    r.sx = copysignf(0.5f, r.dx); r.sy = copysignf(0.5f, r.dy); r.sz = copysignf(0.5f, r.dz);
+    return r;
+}
+
+__device__ __forceinline__ int frexp_exponent(float v) {
+    int e;
+    frexpf(v, &e);
+    return e;
+}
+
+__device__ __forceinline__ int cell_coord(const MarchCfg &c, float x, float mip_rbound) {
+    const float v = __fmaf_rn(x, mip_rbound, 1.0f);
+    const float f = c.h_pow2 ? __fmul_rn(v, c.halfH) : (float)(0.5 * (double)v * (double)c.H);
+    return (int)clampf(f, 0.0f, c.Hm1f);
+}
+
+__device__ __forceinline__ float exit_dist(const MarchCfg &c, int n, float half_sign, float mip_bound, float x, float rd) {
+    // (((n + 0.5 + 0.5*sign) * rH * 2 - 1) * mip_bound - x) * rd      raymarching.cu:390-392
+    const float a = __fadd_rn(__fadd_rn((float)n, 0.5f), half_sign);
+    const float u = __fmaf_rn(__fmul_rn(a, c.rH), 2.0f, -1.0f);
+    return __fmul_rn(__fmaf_rn(u, mip_bound, -x), rd);
+}
+
+__device__ __forceinline__ float step_len(const MarchCfg &c, float t) {
+    return clampf(__fmul_rn(t, c.dt_gamma), c.dt_min, c.dt_max);
+}
+
+// One visit of the marching loop (raymarching.cu:359-400).  Occupied: returns true with the sample
+// position and dt (caller advances t).  Empty: advances t along the step lattice past the voxel.
+__device__ __forceinline__ bool march_visit(const MarchCfg &c, const Ray &r, float &t, float &x, float &y, float &z,
+                                            float &dt) {
+    x = clampf(__fmaf_rn(t, r.dx, r.ox), -c.bound, c.bound);
+    y = clampf(__fmaf_rn(t, r.dy, r.oy), -c.bound, c.bound);
+    z = clampf(__fmaf_rn(t, r.dz, r.oz), -c.bound, c.bound);
+    dt = step_len(c, t);
+    int level = 0;
+    float mip_bound = fminf(1.0f, c.bound);
+    if (c.C > 1) {
+        const float cm1 = (float)c.C - 1.0f;
+        const int l0 = (int)fminf(cm1, fmaxf(0.0f, (float)frexp_exponent(fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))))));
+        const int l1 = (int)fminf(cm1, fmaxf(0.0f, (float)frexp_exponent(__fmul_rn(__fmul_rn(dt, c.Hf), 0.5f))));
+        level = max(l0, l1);
+        mip_bound = fminf(__int_as_float((127 + level) << 23), c.bound);
+    }
+    const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
+    const int nx = cell_coord(c, x, mip_rbound), ny = cell_coord(c, y, mip_rbound), nz = cell_coord(c, z, mip_rbound);
+    const uint32_t index = (uint32_t)__fmaf_rn((float)level, c.H3f, (float)morton3((uint32_t)nx, (uint32_t)ny, (uint32_t)nz));
+    if (__ldg(c.grid + (index >> 3)) & (1u << (index & 7))) return true;
+    const float tx = exit_dist(c, nx, r.sx, mip_bound, x, r.rdx);
+    const float ty = exit_dist(c, ny, r.sy, mip_bound, y, r.rdy);
+    const float tz = exit_dist(c, nz, r.sz, mip_bound, z, r.rdz);
+    const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+    do { t = __fadd_rn(t, step_len(c, t)); } while (t < tt);
+    return false;
+}
+
+__device__ __forceinline__ float perturbed_start(const MarchCfg &c, float t0, float noise) {
+    return __fmaf_rn(step_len(c, t0), noise, t0);  // raymarching.cu:351
+}
+
+// pass 1: count occupied steps per ray -> rays[n] = (n, -, count)
+__global__ void __launch_bounds__(128)
+k_march_count(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
+              float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+              const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
+              int *__restrict__ rays) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const MarchCfg c = make_cfg(grid, bound, dt_gamma, max_steps, C, H);
+    const Ray r = load_ray(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
+    const float far = fars[n];
+    float t = perturbed_start(c, nears[n], noises ? noises[n] : 0.0f);
+    uint32_t num = 0;
+    float x, y, z, dt;
+    while (t < far && num < max_steps) {
+        if (march_visit(c, r, t, x, y, z, dt)) { num++; t = __fadd_rn(t, dt); }
+    }
+    rays[(size_t)n * 3] = (int)n;
+    rays[(size_t)n * 3 + 2] = (int)num;
+}
+
+// single-CTA exclusive scan of rays[:,2] -> rays[:,1]; counter += (sum, N)
+__global__ void __launch_bounds__(1024) k_march_scan(int *__restrict__ rays, uint32_t N, int *__restrict__ counter) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t s_base;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+    const uint32_t chunk = div_up(N, nthr);
+    const uint32_t lo = min(tid * chunk, N), hi = min(lo + chunk, N);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += (uint32_t)rays[(size_t)i * 3 + 2];
+    // block exclusive scan of the per-thread sums
+    uint32_t incl = sum;
+    const uint32_t lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += v;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    if (tid == 0) s_base = (uint32_t)counter[0];
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = (lane < (nthr >> 5)) ? warp_tot[lane] : 0, wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= (uint32_t)d) wi += v;
+        }
+        warp_tot[lane] = wi - w;  // exclusive
+        if (lane == 31) {
+            counter[0] = (int)(s_base + wi);
+            counter[1] = counter[1] + (int)N;
+        }
+    }
+    __syncthreads();
+    uint32_t run = s_base + warp_tot[wid] + (incl - sum);
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint32_t c = (uint32_t)rays[(size_t)i * 3 + 2];
+        rays[(size_t)i * 3 + 1] = (int)run;
+        run += c;
+    }
+}
+
+// pass 2: re-march and write the samples of every ray that fits (raymarching.cu:415-479)
+__global__ void __launch_bounds__(128)
+k_march_write(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
+              float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+              const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
+              const int *__restrict__ rays, float *__restrict__ xyzs, float *__restrict__ dirs,
+              float *__restrict__ deltas) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const uint32_t off = (uint32_t)rays[(size_t)n * 3 + 1], num = (uint32_t)rays[(size_t)n * 3 + 2];
+    if (num == 0 || off + num > M) return;
+    const MarchCfg c = make_cfg(grid, bound, dt_gamma, max_steps, C, H);
+    const Ray r = load_ray(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
+    const float far = fars[n];
+    float t = perturbed_start(c, nears[n], noises ? noises[n] : 0.0f);
+    float last_t = t, x, y, z, dt;
+    float *px = xyzs + (size_t)off * 3, *pd = dirs + (size_t)off * 3, *pl = deltas + (size_t)off * 2;
+    uint32_t step = 0;
+    while (t < far && step < num) {
+        if (march_visit(c, r, t, x, y, z, dt)) {
+            px[0] = x; px[1] = y; px[2] = z;
+            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            t = __fadd_rn(t, dt);
+            *reinterpret_cast<float2 *>(pl) = make_float2(dt, __fsub_rn(t, last_t));
+            last_t = t;
+            px += 3; pd += 3; pl += 2; step++;
+        }
+    }
+}
+
+// inference marcher: n_step samples per alive ray at a fixed stride (raymarching.cu:701-805)
+__global__ void __launch_bounds__(128)
+k_march_rays(uint32_t n_alive, uint32_t n_step, const int *__restrict__ rays_alive, const float *__restrict__ rays_t,
+             const float *__restrict__ rays_o, const float *__restrict__ rays_d, float bound, float dt_gamma,
+             uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t *__restrict__ grid,
+             const float *__restrict__ nears, const float *__restrict__ fars, float *__restrict__ xyzs,
+             float *__restrict__ dirs, float *__restrict__ deltas, const float *__restrict__ noises) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    const MarchCfg c = make_cfg(grid, bound, dt_gamma, max_steps, C, H);
+    const Ray r = load_ray(rays_o + (size_t)index * 3, rays_d + (size_t)index * 3);
+    const float far = fars[index];
+    float t = perturbed_start(c, rays_t[index], noises ? noises[n] : 0.0f);
+    float last_t = t, x, y, z, dt;
+    float *px = xyzs + (size_t)n * n_step * 3, *pd = dirs + (size_t)n * n_step * 3, *pl = deltas + (size_t)n * n_step * 2;
+    uint32_t step = 0;
+    while (t < far && step < n_step) {
+        if (march_visit(c, r, t, x, y, z, dt)) {
+            px[0] = x; px[1] = y; px[2] = z;
+            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            t = __fadd_rn(t, dt);
+            pl[0] = dt; pl[1] = __fsub_rn(t, last_t);
+            last_t = t;
+            px += 3; pd += 3; pl += 2; step++;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// compositing
+// ---------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128)
+k_composite_train_fwd(const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ deltas,
+                      const int *__restrict__ rays, uint32_t M, uint32_t N, float T_thresh,
+                      float *__restrict__ weights_sum, float *__restrict__ depth, float *__restrict__ image) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)rays[(size_t)n * 3], offset = (uint32_t)rays[(size_t)n * 3 + 1],
+                   num = (uint32_t)rays[(size_t)n * 3 + 2];
+    float T = 1.0f, r = 0, g = 0, b = 0, ws = 0, t = 0, d = 0;
+    if (num != 0 && offset + num <= M) {
+        const float *s = sigmas + offset, *c = rgbs + (size_t)offset * 3;
+        const float2 *dl = reinterpret_cast<const float2 *>(deltas) + offset;
+        for (uint32_t step = 0; step < num; step++) {
+            const float2 de = __ldg(dl + step);
+            const float alpha = 1.0f - __expf(-__ldg(s + step) * de.x);
+            const float w = alpha * T;
+            r = fmaf(w, __ldg(c + step * 3), r);
+            g = fmaf(w, __ldg(c + step * 3 + 1), g);
+            b = fmaf(w, __ldg(c + step * 3 + 2), b);
+            t += de.y;
+            d = fmaf(w, t, d);
+            ws += w;
+            T *= 1.0f - alpha;
+            if (T < T_thresh) break;
+        }
+    }
+    weights_sum[index] = ws;
+    depth[index] = d;
+    image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
+}
+
+__global__ void __launch_bounds__(128)
+k_composite_train_bwd(const float *__restrict__ grad_ws, const float *__restrict__ grad_image,
+                      const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ deltas,
+                      const int *__restrict__ rays, const float *__restrict__ weights_sum,
+                      const float *__restrict__ image, uint32_t M, uint32_t N, float T_thresh,
+                      float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)rays[(size_t)n * 3], offset = (uint32_t)rays[(size_t)n * 3 + 1],
+                   num = (uint32_t)rays[(size_t)n * 3 + 2];
+    if (num == 0 || offset + num > M) return;
+    const float gws = grad_ws[index];
+    const float g0 = grad_image[(size_t)index * 3], g1 = grad_image[(size_t)index * 3 + 1], g2 = grad_image[(size_t)index * 3 + 2];
+    const float rf = image[(size_t)index * 3], gf = image[(size_t)index * 3 + 1], bf = image[(size_t)index * 3 + 2];
+    const float tail = gws * (1 - weights_sum[index]);
+    const float *s = sigmas + offset, *c = rgbs + (size_t)offset * 3;
+    const float2 *dl = reinterpret_cast<const float2 *>(deltas) + offset;
+    float *gs = grad_sigmas + offset, *gc = grad_rgbs + (size_t)offset * 3;
+    float T = 1.0f, r = 0, g = 0, b = 0;
+    for (uint32_t step = 0; step < num; step++) {
+        const float2 de = __ldg(dl + step);
+        const float c0 = __ldg(c + step * 3), c1 = __ldg(c + step * 3 + 1), c2 = __ldg(c + step * 3 + 2);
+        const float alpha = 1.0f - __expf(-__ldg(s + step) * de.x);
+        const float w = alpha * T;
+        r = fmaf(w, c0, r); g = fmaf(w, c1, g); b = fmaf(w, c2, b);
+        T *= 1.0f - alpha;
+        gc[step * 3] = g0 * w; gc[step * 3 + 1] = g1 * w; gc[step * 3 + 2] = g2 * w;
+        gs[step] = de.x * (g0 * (T * c0 - (rf - r)) + g1 * (T * c1 - (gf - g)) + g2 * (T * c2 - (bf - b)) + tail);
+        if (T < T_thresh) break;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int *__restrict__ rays_alive,
+                 float *__restrict__ rays_t, const float *__restrict__ sigmas, const float *__restrict__ rgbs,
+                 const float *__restrict__ deltas, float *__restrict__ weights_sum, float *__restrict__ depth,
+                 float *__restrict__ image) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    const float *s = sigmas + (size_t)n * n_step, *c = rgbs + (size_t)n * n_step * 3, *dl = deltas + (size_t)n * n_step * 2;
+    float t = rays_t[index], ws = weights_sum[index], d = depth[index];
+    float r = image[(size_t)index * 3], g = image[(size_t)index * 3 + 1], b = image[(size_t)index * 3 + 2];
+    uint32_t step = 0;
+    while (step < n_step) {
+        if (dl[0] == 0) break;  // zero-filled rows terminate the ray (raymarching.cu:858)
+        const float alpha = 1.0f - __expf(-s[0] * dl[0]);
+        const float T = 1 - ws;
+        const float w = alpha * T;
+        ws += w;
+        t += dl[1];
+        d = fmaf(w, t, d);
+        r = fmaf(w, c[0], r); g = fmaf(w, c[1], g); b = fmaf(w, c[2], b);
+        if (T < T_thresh) break;
+        s++; c += 3; dl += 2; step++;
+    }
+    if (step < n_step) rays_alive[n] = -1; else rays_t[index] = t;
+    weights_sum[index] = ws; depth[index] = d;
+    image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+
+S3D_API int s3d_near_far_from_aabb(const float *rays_o, const float *rays_d, const float *aabb, uint32_t N,
+                                   float min_near, float *nears, float *fars, void *stream) {
+    if (N == 0) return 0;
+    k_near_far<<<div_up(N, 256u), 256, 0, as_stream(stream)>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_sph_from_ray(const float *rays_o, const float *rays_d, float radius, uint32_t N, float *coords,
+                             void *stream) {
+    if (N == 0) return 0;
+    k_sph_from_ray<<<div_up(N, 256u), 256, 0, as_stream(stream)>>>(rays_o, rays_d, radius, N, coords);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_morton3D(const int *coords, uint32_t N, int *indices, void *stream) {
+    if (N == 0) return 0;
+    k_morton3D<<<div_up(N, 256u), 256, 0, as_stream(stream)>>>(coords, N, indices);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_morton3D_invert(const int *indices, uint32_t N, int *coords, void *stream) {
+    if (N == 0) return 0;
+    k_morton3D_invert<<<div_up(N, 256u), 256, 0, as_stream(stream)>>>(indices, N, coords);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t *bitfield, void *stream) {
+    if (N == 0) return 0;
+    const uint32_t words = div_up(N, 4u);
+    k_packbits<<<div_up(words, 256u), 256, 0, as_stream(stream)>>>(grid, N, density_thresh, bitfield);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                 const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
+                                 int *rays, int *counter, const float *noises, void *stream) {
+    if (N == 0) return 0;
+    if (C == 0 || H == 0 || max_steps == 0) return S3D_EINVAL;
+    cudaStream_t st = as_stream(stream);
+    k_march_count<<<div_up(N, 128u), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears,
+                                                    fars, noises, rays);
+    k_march_scan<<<1, 1024, 0, st>>>(rays, N, counter);
+    k_march_write<<<div_up(N, 128u), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears,
+                                                    fars, noises, rays, xyzs, dirs, deltas);
+    S3D_RETURN_LAST();
+}
+
+// Two-phase variant of the same op for callers that want an exactly-sized sample buffer: phase 1 counts and
+// scans (rays[:,0..2] and counter are final afterwards), the host reads counter[0], allocates, phase 2 writes.
+S3D_API int s3d_march_rays_train_count(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                                       float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                       const float *nears, const float *fars, int *rays, int *counter,
+                                       const float *noises, void *stream) {
+    if (N == 0) return 0;
+    if (C == 0 || H == 0 || max_steps == 0) return S3D_EINVAL;
+    cudaStream_t st = as_stream(stream);
+    k_march_count<<<div_up(N, 128u), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears,
+                                                    fars, noises, rays);
+    k_march_scan<<<1, 1024, 0, st>>>(rays, N, counter);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_march_rays_train_write(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                                       float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                       const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
+                                       const int *rays, const float *noises, void *stream) {
+    if (N == 0) return 0;
+    k_march_write<<<div_up(N, 128u), 128, 0, as_stream(stream)>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H,
+                                                                  M, nears, fars, noises, rays, xyzs, dirs, deltas);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_composite_rays_train_forward(const float *sigmas, const float *rgbs, const float *deltas,
+                                             const int *rays, uint32_t M, uint32_t N, float T_thresh,
+                                             float *weights_sum, float *depth, float *image, void *stream) {
+    if (N == 0) return 0;
+    k_composite_train_fwd<<<div_up(N, 128u), 128, 0, as_stream(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh,
+                                                                          weights_sum, depth, image);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_composite_rays_train_backward(const float *grad_weights_sum, const float *grad_image,
+                                              const float *sigmas, const float *rgbs, const float *deltas,
+                                              const int *rays, const float *weights_sum, const float *image, uint32_t M,
+                                              uint32_t N, float T_thresh, float *grad_sigmas, float *grad_rgbs,
+                                              void *stream) {
+    if (N == 0) return 0;
+    k_composite_train_bwd<<<div_up(N, 128u), 128, 0, as_stream(stream)>>>(
+        grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_march_rays(uint32_t n_alive, uint32_t n_step, const int *rays_alive, const float *rays_t,
+                           const float *rays_o, const float *rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                           uint32_t C, uint32_t H, const uint8_t *grid, const float *nears, const float *fars,
+                           float *xyzs, float *dirs, float *deltas, const float *noises, void *stream) {
+    if (n_alive == 0) return 0;
+    k_march_rays<<<div_up(n_alive, 128u), 128, 0, as_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d,
+                                                                       bound, dt_gamma, max_steps, C, H, grid, nears,
+                                                                       fars, xyzs, dirs, deltas, noises);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int *rays_alive, float *rays_t,
+                               const float *sigmas, const float *rgbs, const float *deltas, float *weights_sum,
+                               float *depth, float *image, void *stream) {
+    if (n_alive == 0) return 0;
+    k_composite_rays<<<div_up(n_alive, 128u), 128, 0, as_stream(stream)>>>(n_alive, n_step, T_thresh, rays_alive, rays_t,
+                                                                           sigmas, rgbs, deltas, weights_sum, depth, image);
+    S3D_RETURN_LAST();
+}

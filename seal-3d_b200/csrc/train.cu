@@ -1,0 +1,218 @@
+// Training-step glue kernels for sm_100a: distillation losses (+ their gradients), fused Adam over the
+// gradient arena with fp16 shadow refresh, density-grid EMA update.
+//
+//   pretrain (per sample)  SealNeRF/trainer.py:456-469   L1(sigma) + L1(rgb), mean reductions
+//   finetune (per ray)     nerf/utils.py:484-489,530     mean_rays(mean_c (rgb - gt)^2) + mean |depth - gt|
+//   Adam                   main_SealNeRF.py:283-284      torch.optim.Adam(betas=(0.9,0.99), eps=1e-15), no weight decay
+//   density grid           nerf/renderer.py:521-524      grid = max(grid*decay, tmp) where both >= 0; mean of clamp(grid,0)
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float sgnf(float v) { return (v > 0.0f) - (v < 0.0f); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// loss[0] += sum|ds| / M + sum|dc| / (3M); grads are those of the mean reductions
+__global__ void k_pretrain_loss(const float *__restrict__ sig_s, const float *__restrict__ rgb_s, const float *__restrict__ sig_t,
+                                const float *__restrict__ rgb_t, uint32_t M, float *__restrict__ loss,
+                                float *__restrict__ g_sig, float *__restrict__ g_rgb) {
+    float acc = 0.0f;
+    const float inv_m = 1.0f / (float)M, inv_3m = 1.0f / (3.0f * (float)M);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+        const float ds = sig_s[i] - sig_t[i];
+        acc += fabsf(ds) * inv_m;
+        if (g_sig) g_sig[i] = sgnf(ds) * inv_m;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float dc = rgb_s[(size_t)i * 3 + c] - rgb_t[(size_t)i * 3 + c];
+            acc += fabsf(dc) * inv_3m;
+            if (g_rgb) g_rgb[(size_t)i * 3 + c] = sgnf(dc) * inv_3m;
+        }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(loss, acc);
+}
+
+// student image = comp + (1 - ws) * bg.  loss[0] += MSE part, loss[1] += L1 depth part.
+// grad_image = d loss / d comp ; grad_ws = d loss / d ws = -bg * sum_c grad_image_c.
+__global__ void k_finetune_loss(const float *__restrict__ comp_s, const float *__restrict__ ws_s, const float *__restrict__ depth_s,
+                                const float *__restrict__ image_t, const float *__restrict__ depth_t, uint32_t N, float bg,
+                                float *__restrict__ loss, float *__restrict__ grad_image, float *__restrict__ grad_ws) {
+    float a0 = 0.0f, a1 = 0.0f;
+    const float inv_n = 1.0f / (float)N, k = 2.0f / (3.0f * (float)N);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const float back = (1.0f - ws_s[i]) * bg;
+        float gsum = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float d = comp_s[(size_t)i * 3 + c] + back - image_t[(size_t)i * 3 + c];
+            a0 += d * d * (inv_n / 3.0f);
+            const float g = k * d;
+            grad_image[(size_t)i * 3 + c] = g;
+            gsum += g;
+        }
+        grad_ws[i] = -bg * gsum;
+        if (depth_t) a1 += fabsf(depth_s[i] - depth_t[i]) * inv_n;
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(loss, a0); atomicAdd(loss + 1, a1); }
+}
+
+// One pass over the arena: g = grad * grad_scale; Adam; optional fp16 shadow of the new parameter; grad zeroed.
+template <typename G>
+__global__ void __launch_bounds__(256)
+k_adam(float *__restrict__ p, G *__restrict__ g, float *__restrict__ m, float *__restrict__ v, __half *__restrict__ shadow,
+       size_t n, float lr_over_bc1, float inv_sqrt_bc2, float beta1, float beta2, float eps, float grad_scale, int zero_grad) {
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= n) return;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                           reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(shadow) & 7) == 0;
+    if (i0 + 4 <= n && sizeof(G) == 4 && aligned) {
+        float4 pp = *reinterpret_cast<float4 *>(p + i0), gg = *reinterpret_cast<float4 *>(reinterpret_cast<float *>(g) + i0);
+        float4 mm = *reinterpret_cast<float4 *>(m + i0), vv = *reinterpret_cast<float4 *>(v + i0);
+        float *P = &pp.x, *Gp = &gg.x, *Mp = &mm.x, *Vp = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float gr = Gp[k] * grad_scale;
+            Mp[k] = beta1 * Mp[k] + (1.0f - beta1) * gr;
+            Vp[k] = beta2 * Vp[k] + (1.0f - beta2) * gr * gr;
+            P[k] -= lr_over_bc1 * Mp[k] / (sqrtf(Vp[k]) * inv_sqrt_bc2 + eps);
+        }
+        *reinterpret_cast<float4 *>(p + i0) = pp;
+        *reinterpret_cast<float4 *>(m + i0) = mm;
+        *reinterpret_cast<float4 *>(v + i0) = vv;
+        if (zero_grad) *reinterpret_cast<float4 *>(reinterpret_cast<float *>(g) + i0) = make_float4(0, 0, 0, 0);
+        if (shadow) {
+            __half2 a = __floats2half2_rn(pp.x, pp.y), b = __floats2half2_rn(pp.z, pp.w);
+            *reinterpret_cast<uint2 *>(shadow + i0) = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+        }
+    } else {
+        for (size_t i = i0; i < n && i < i0 + 4; i++) {
+            float gr;
+            if constexpr (sizeof(G) == 4) gr = reinterpret_cast<float *>(g)[i] * grad_scale;
+            else gr = __half2float(reinterpret_cast<__half *>(g)[i]) * grad_scale;
+            const float mi = beta1 * m[i] + (1.0f - beta1) * gr;
+            const float vi = beta2 * v[i] + (1.0f - beta2) * gr * gr;
+            m[i] = mi; v[i] = vi;
+            const float pn = p[i] - lr_over_bc1 * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+            p[i] = pn;
+            if (shadow) shadow[i] = __float2half_rn(pn);
+            if (zero_grad) {
+                if constexpr (sizeof(G) == 4) reinterpret_cast<float *>(g)[i] = 0.0f;
+                else reinterpret_cast<__half *>(g)[i] = __float2half_rn(0.0f);
+            }
+        }
+    }
+}
+
+__global__ void k_f32_to_f16_arena(const float *__restrict__ src, __half *__restrict__ dst, size_t n) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i + 1 < n) {
+        const float2 f = *reinterpret_cast<const float2 *>(src + i);
+        *reinterpret_cast<__half2 *>(dst + i) = __floats2half2_rn(f.x, f.y);
+    } else if (i < n) dst[i] = __float2half_rn(src[i]);
+}
+
+// grid[i] = max(grid[i]*decay, tmp[i]) where both >= 0 ; sum += max(grid[i], 0)
+__global__ void k_density_ema(float *__restrict__ grid, const float *__restrict__ tmp, uint32_t n, float decay, float *__restrict__ sum) {
+    float acc = 0.0f;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float g = grid[i];
+        const float t = tmp[i];
+        if (g >= 0.0f && t >= 0.0f) { g = fmaxf(g * decay, t); grid[i] = g; }
+        acc += fmaxf(g, 0.0f);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sum, acc);
+}
+
+// cell index (morton within cascade) -> jittered query position (nerf/renderer.py:470-479, 503-509)
+__device__ __forceinline__ uint32_t pcg(uint32_t v) {
+    v = v * 747796405u + 2891336453u;
+    const uint32_t w = ((v >> ((v >> 28u) + 4u)) ^ v) * 277803737u;
+    return (w >> 22u) ^ w;
+}
+__global__ void k_density_cells_to_xyz(const int *__restrict__ cell_morton, uint32_t n, uint32_t H, float bound_cas, uint32_t seed,
+                                       float *__restrict__ xyz) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t idx = (uint32_t)cell_morton[i];
+    auto compact = [](uint32_t x) {
+        x &= 0x49249249u; x = (x | (x >> 2)) & 0xc30c30c3u; x = (x | (x >> 4)) & 0x0f00f00fu;
+        x = (x | (x >> 8)) & 0xff0000ffu; x = (x | (x >> 16)) & 0x0000ffffu; return x; };
+    const uint32_t c[3] = {compact(idx), compact(idx >> 1), compact(idx >> 2)};
+    const float hgs = bound_cas / (float)H;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const float u = (float)(pcg(seed ^ pcg(i * 3u + d)) >> 8) * (1.0f / 16777216.0f);  // [0,1)
+        const float base = (2.0f * (float)c[d] / (float)(H - 1) - 1.0f) * (bound_cas - hgs);
+        xyz[(size_t)i * 3 + d] = base + (u * 2.0f - 1.0f) * hgs;
+    }
+}
+// tmp[cell_morton[i]] = sigma[i]
+__global__ void k_density_scatter(const int *__restrict__ cell_morton, const float *__restrict__ sigma, uint32_t n, float scale, float *__restrict__ tmp) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tmp[(uint32_t)cell_morton[i]] = sigma[i] * scale;
+}
+
+}  // namespace
+
+S3D_API int s3d_pretrain_loss(const float *sigma_s, const float *rgb_s, const float *sigma_t, const float *rgb_t, uint32_t M,
+                              float *loss, float *grad_sigma, float *grad_rgb, void *stream) {
+    if (M == 0) return 0;
+    k_pretrain_loss<<<min(div_up(M, 256u), 2048u), 256, 0, as_stream(stream)>>>(sigma_s, rgb_s, sigma_t, rgb_t, M, loss, grad_sigma, grad_rgb);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_finetune_loss(const float *comp_s, const float *ws_s, const float *depth_s, const float *image_t, const float *depth_t,
+                              uint32_t N, float bg_color, float *loss, float *grad_image, float *grad_ws, void *stream) {
+    if (N == 0) return 0;
+    k_finetune_loss<<<min(div_up(N, 256u), 2048u), 256, 0, as_stream(stream)>>>(comp_s, ws_s, depth_s, image_t, depth_t, N, bg_color, loss, grad_image, grad_ws);
+    S3D_RETURN_LAST();
+}
+
+// grad_dtype: 0 = float32, 1 = float16.  step >= 1 (bias correction).  shadow may be NULL.
+S3D_API int s3d_adam_step(float *params, void *grads, float *exp_avg, float *exp_avg_sq, void *shadow_f16, uint64_t n, float lr,
+                          float beta1, float beta2, float eps, uint32_t step, float grad_scale, int zero_grad, int grad_dtype,
+                          void *stream) {
+    if (n == 0) return 0;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    const float lr_over_bc1 = (float)((double)lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    const unsigned blocks = (unsigned)div_up((size_t)n, (size_t)1024);
+    if (grad_dtype == 0)
+        k_adam<float><<<blocks, 256, 0, as_stream(stream)>>>(params, (float *)grads, exp_avg, exp_avg_sq, (__half *)shadow_f16, (size_t)n,
+                                                              lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, grad_scale, zero_grad);
+    else
+        k_adam<__half><<<blocks, 256, 0, as_stream(stream)>>>(params, (__half *)grads, exp_avg, exp_avg_sq, (__half *)shadow_f16, (size_t)n,
+                                                               lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, grad_scale, zero_grad);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_cast_f32_to_f16(const float *src, void *dst, uint64_t n, void *stream) {
+    if (n == 0) return 0;
+    k_f32_to_f16_arena<<<(unsigned)div_up((size_t)n, (size_t)512), 256, 0, as_stream(stream)>>>(src, (__half *)dst, (size_t)n);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_density_grid_ema(float *grid, const float *tmp_grid, uint32_t n, float decay, float *sum_out, void *stream) {
+    if (n == 0) return 0;
+    k_density_ema<<<min(div_up(n, 256u), 2048u), 256, 0, as_stream(stream)>>>(grid, tmp_grid, n, decay, sum_out);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_density_cells_to_xyz(const int *cell_morton, uint32_t n, uint32_t H, float bound_cas, uint32_t seed, float *xyz, void *stream) {
+    if (n == 0) return 0;
+    k_density_cells_to_xyz<<<div_up(n, 256u), 256, 0, as_stream(stream)>>>(cell_morton, n, H, bound_cas, seed, xyz);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_density_scatter(const int *cell_morton, const float *sigma, uint32_t n, float density_scale, float *tmp_grid, void *stream) {
+    if (n == 0) return 0;
+    k_density_scatter<<<div_up(n, 256u), 256, 0, as_stream(stream)>>>(cell_morton, sigma, n, density_scale, tmp_grid);
+    S3D_RETURN_LAST();
+}

@@ -1,0 +1,161 @@
+"""Mirror of ``nerf/renderer.py::NeRFRenderer`` for the cuda-ray path: ``run_cuda`` (training and
+inference), ``update_extra_state`` (density-grid EMA + bitfield + mean_count) and ``render``.
+The non-cuda-ray path (``run`` / ``sample_pdf``) is out of scope.
+
+Two overridable hooks carry Seal-3D's teacher-side proxy mapping without duplicating the loop
+(SealNeRF/renderer.py:291-316, :381-399): ``_map_samples(xyzs, dirs)`` and ``_map_colors(...)``.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import raymarching
+
+
+class NeRFRenderer(nn.Module):
+    def __init__(self, bound=1, cuda_ray=True, density_scale=1, min_near=0.2, density_thresh=0.01, bg_radius=-1):
+        super().__init__()
+        self.bound = bound
+        self.cascade = 1 + math.ceil(math.log2(bound))
+        self.grid_size = 128
+        self.density_scale, self.min_near, self.density_thresh, self.bg_radius = density_scale, min_near, density_thresh, bg_radius
+        aabb = torch.FloatTensor([-bound, -bound, -bound, bound, bound, bound])
+        self.register_buffer("aabb_train", aabb)
+        self.register_buffer("aabb_infer", aabb.clone())
+        self.cuda_ray = cuda_ray
+        if cuda_ray:
+            self.register_buffer("density_grid", torch.zeros([self.cascade, self.grid_size ** 3]))
+            self.register_buffer("density_bitfield", torch.zeros(self.cascade * self.grid_size ** 3 // 8, dtype=torch.uint8))
+            self.mean_density = 0
+            self.iter_density = 0
+            self.register_buffer("step_counter", torch.zeros(16, 2, dtype=torch.int32))
+            self.mean_count = 0
+            self.local_step = 0
+
+    def forward(self, x, d):
+        raise NotImplementedError()
+
+    def density(self, x):
+        raise NotImplementedError()
+
+    def reset_extra_state(self):
+        if not self.cuda_ray:
+            return
+        self.density_grid.zero_()
+        self.mean_density = 0
+        self.iter_density = 0
+        self.step_counter.zero_()
+        self.mean_count = 0
+        self.local_step = 0
+
+    # ---- hooks (identity here; the Seal teacher overrides them) ------------------------------
+    def _map_samples(self, xyzs, dirs):
+        return xyzs, dirs, None
+
+    def _map_colors(self, xyzs, dirs, rgbs, mask):
+        return rgbs
+
+    def _field(self, xyzs, dirs):
+        mx, md, mask = self._map_samples(xyzs, dirs)
+        sigmas, rgbs = self(mx, md)
+        sigmas = self.density_scale * sigmas
+        if mask is not None:
+            rgbs = self._map_colors(mx, md, rgbs, mask)
+        return sigmas, rgbs
+
+    def run_cuda(self, rays_o, rays_d, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False, max_steps=1024,
+                 T_thresh=1e-4, **kwargs):
+        """nerf/renderer.py:256-377.  rays_o/d [B,N,3] (B==1) -> {'image' [B,N,3], 'depth' [B,N], 'weights_sum'}."""
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3)
+        rays_d = rays_d.contiguous().view(-1, 3)
+        N = rays_o.shape[0]
+        device = rays_o.device
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_train if self.training else self.aabb_infer, self.min_near)
+        if bg_color is None:
+            bg_color = 1
+        results = {}
+        if self.training:
+            counter = self.step_counter[self.local_step % 16]
+            counter.zero_()
+            self.local_step += 1
+            xyzs, dirs, deltas, rays = raymarching.march_rays_train(rays_o, rays_d, self.bound, self.density_bitfield, self.cascade,
+                                                                   self.grid_size, nears, fars, counter, self.mean_count, perturb, 128,
+                                                                   force_all_rays, dt_gamma, max_steps)
+            sigmas, rgbs = self._field(xyzs, dirs)
+            weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
+            image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+            results["weights_sum"] = weights_sum
+        else:
+            weights_sum = torch.zeros(N, dtype=torch.float32, device=device)
+            depth = torch.zeros(N, dtype=torch.float32, device=device)
+            image = torch.zeros(N, 3, dtype=torch.float32, device=device)
+            n_alive = N
+            rays_alive = torch.arange(n_alive, dtype=torch.int32, device=device)
+            rays_t = nears.clone()
+            step = 0
+            while step < max_steps:
+                n_alive = rays_alive.shape[0]
+                if n_alive <= 0:
+                    break
+                n_step = max(min(N // n_alive, 8), 1)
+                xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound,
+                                                            self.density_bitfield, self.cascade, self.grid_size, nears, fars, 128,
+                                                            perturb if step == 0 else False, dt_gamma, max_steps)
+                sigmas, rgbs = self._field(xyzs, dirs)
+                raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh)
+                rays_alive = rays_alive[rays_alive >= 0]
+                step += n_step
+            image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        results["depth"] = depth.view(*prefix)
+        results["image"] = image.view(*prefix, 3)
+        return results
+
+    @torch.no_grad()
+    def update_extra_state(self, decay=0.95, S=128, seed=None):
+        """nerf/renderer.py:445-538: full sweep for the first 16 calls, then H^3/4 uniform + H^3/4 occupied cells;
+        EMA-max into density_grid, mean density, packbits with min(mean, density_thresh), mean_count from the ring."""
+        if not self.cuda_ray:
+            return
+        dev = self.density_bitfield.device
+        H = self.grid_size
+        tmp_grid = -torch.ones_like(self.density_grid)
+        seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if seed is None else int(seed)
+        for cas in range(self.cascade):
+            if self.iter_density < 16:
+                cells = torch.arange(H ** 3, dtype=torch.int32, device=dev)
+            else:
+                n = H ** 3 // 4
+                coords = torch.randint(0, H, (n, 3), device=dev)
+                rnd = raymarching.morton3D(coords)
+                occ = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
+                if occ.shape[0] > 0:
+                    pick = occ[torch.randint(0, occ.shape[0], [n], dtype=torch.long, device=dev)].int()
+                    cells = torch.cat([rnd, pick], dim=0)
+                else:
+                    cells = rnd
+            n = cells.shape[0]
+            bound_cas = min(2 ** cas, self.bound)
+            xyz = torch.empty(n, 3, dtype=torch.float32, device=dev)
+            _lib.call("s3d_density_cells_to_xyz", cells, n, H, float(bound_cas), (seed + 7919 * cas) & 0xFFFFFFFF, xyz)
+            chunk = 1 << 21
+            for s in range(0, n, chunk):
+                sig = self.density(xyz[s:s + chunk])["sigma"].reshape(-1).detach().float().contiguous()
+                _lib.call("s3d_density_scatter", cells[s:s + chunk], sig, sig.shape[0], float(self.density_scale), tmp_grid[cas])
+        acc = torch.zeros(1, dtype=torch.float32, device=dev)
+        _lib.call("s3d_density_grid_ema", self.density_grid, tmp_grid, self.density_grid.numel(), float(decay), acc)
+        self.mean_density = float(acc.item()) / self.density_grid.numel()
+        self.iter_density += 1
+        density_thresh = min(self.mean_density, self.density_thresh)
+        self.density_bitfield = raymarching.packbits(self.density_grid, density_thresh, self.density_bitfield)
+        total_step = min(16, self.local_step)
+        if total_step > 0:
+            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+        self.local_step = 0
+
+    def render(self, rays_o, rays_d, **kwargs):
+        if not self.cuda_ray:
+            raise NotImplementedError("only the cuda-ray path is built (nerf/renderer.py:541-573)")
+        return self.run_cuda(rays_o, rays_d, **kwargs)

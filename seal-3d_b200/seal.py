@@ -1,0 +1,124 @@
+"""Seal-3D proxy side: bbox mapper, teacher/student renderers (mirror of the hot-path parts of
+``SealNeRF/seal_utils.py`` and ``SealNeRF/renderer.py``).
+
+``SealBBoxMapper`` takes ready ``map_data`` tensors (the dict SealBBoxMapper.__init__ builds,
+seal_utils.py:222-236) plus the target-mesh triangles; building them from ``seal.json`` needs
+trimesh / pytorch3d and is out of scope.  Use ``synth.bbox_edit`` for an
+axis-aligned or rotated box edit.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from . import raymarching
+from .network import NeRFNetwork
+
+
+class SealBBoxMapper:
+    def __init__(self, map_data, triangles, test_dir=None, device="cuda"):
+        self.device = torch.device(device)
+        md = {k: np.asarray(v, dtype=np.float32) for k, v in map_data.items()}
+        self.map_data = {k: torch.from_numpy(v).to(self.device) for k, v in md.items()}
+        self._h = {k: _lib.host_f32(md[k]) for k in ("transform", "rotation", "scale", "center")}
+        self._h_test = _lib.host_f32(test_dir) if test_dir is not None else None
+        self._h_src = _lib.host_f32(md["empty_bound"]) if "map_source" in md else None
+        self._h_ms = _lib.host_f32(md["map_source"]) if "map_source" in md else None
+        self._h_hsv = _lib.host_f32(md["hsv"]) if "hsv" in md else None
+        self._h_rgb = _lib.host_f32(md["rgb"]) if "rgb" in md else None
+        self._light = float(md["rgb_light_offset"]) if "rgb_light_offset" in md else 0.0
+        self.bounds = torch.from_numpy(md["map_bound"].reshape(-1, 2, 3)).to(self.device).contiguous()
+        self.map_triangles = torch.from_numpy(np.asarray(triangles, np.float32).reshape(-1, 3, 3)).to(self.device).contiguous()
+        self._stats = torch.zeros(2, dtype=torch.float32, device=self.device)
+
+    def map_to_origin(self, points, dirs=None):
+        """seal_utils.py:237-279 -> (points', dirs', mask) ; clones with the masked rows replaced."""
+        points = points.contiguous().float()
+        P = points.shape[0]
+        dirs_c = dirs.contiguous().float() if dirs is not None else None
+        out_p = torch.empty_like(points)
+        out_d = torch.empty_like(dirs_c) if dirs_c is not None else None
+        mask = torch.empty(P, dtype=torch.uint8, device=points.device)
+        _lib.call("s3d_seal_bbox_map_to_origin", points, dirs_c, P, self._h["transform"][1], self._h["rotation"][1],
+                  self._h["scale"][1], self._h["center"][1], self.bounds, self.bounds.shape[0], self.map_triangles,
+                  self.map_triangles.shape[0], self._h_test[1] if self._h_test else None,
+                  self._h_src[1] if self._h_src else None, self._h_ms[1] if self._h_ms else None, out_p, out_d, mask)
+        return out_p, out_d, mask.bool()
+
+    def map_mask(self, points):
+        return self.map_to_origin(points, None)[2]
+
+    def has_color_edit(self):
+        return self._h_hsv is not None or self._h_rgb is not None
+
+    def map_color_(self, rgbs, mask):
+        """in-place colour edit of the masked rows of rgbs [M,3] (float32, contiguous)"""
+        if not self.has_color_edit():
+            return rgbs
+        m8 = mask.to(torch.uint8).contiguous() if mask is not None else None
+        _lib.call("s3d_seal_map_color", rgbs, m8, rgbs.shape[0], self._h_hsv[1] if self._h_hsv else None,
+                  self._h_rgb[1] if self._h_rgb else None, self._light, self._stats)
+        return rgbs
+
+    def map_color(self, points, dirs, colors):
+        """seal_utils.py:48-81 (hsv / rgb edits): returns the edited copy of `colors` [P,3]"""
+        out = colors.detach().float().contiguous().clone()
+        return self.map_color_(out, None)
+
+
+class SealRendererMixin:
+    """SealNeRF/renderer.py:8-74: mapper + occupancy force-fill of the edit region."""
+
+    seal_mapper = None
+    density_bitfield_origin = None
+    density_bitfield_hacked = False
+
+    def init_mapper(self, mapper):
+        self.seal_mapper = mapper
+        bounds = mapper.map_data["force_fill_bound"].detach().cpu().numpy().reshape(-1, 2, 3).copy()
+        lo = np.maximum(bounds[:, 0, :], -self.bound)
+        hi = np.minimum(bounds[:, 1, :], self.bound)
+        H = self.grid_size
+        self._fill_boxes = []
+        for i in range(bounds.shape[0]):
+            cmin = np.floor(((lo[i] + self.bound) / self.bound / 2) * H).astype(np.int32)
+            cmax = np.floor(((hi[i] + self.bound) / self.bound / 2) * H).astype(np.int32)
+            self._fill_boxes.append((_lib.host_i32(np.clip(cmin, 0, H)), _lib.host_i32(np.clip(cmax, 0, H))))
+
+    @torch.no_grad()
+    def hack_bitfield(self):
+        if self.density_bitfield_origin is None:
+            self.density_bitfield_origin = self.density_bitfield.clone()
+        for lo, hi in self._fill_boxes:
+            _lib.call("s3d_seal_force_fill_bitfield", self.density_bitfield, lo[1], hi[1], self.grid_size, 0)
+        self.density_bitfield_hacked = True
+
+    @torch.no_grad()
+    def restore_bitfield(self):
+        self.density_bitfield.copy_(self.density_bitfield_origin)
+        self.density_bitfield_hacked = False
+
+    def update_extra_state(self, decay=0.95, S=128, seed=None):
+        super().update_extra_state(decay, S, seed)
+        self.density_bitfield_origin = None
+        if self.seal_mapper is not None:
+            self.hack_bitfield()
+
+
+class TeacherNetwork(SealRendererMixin, NeRFNetwork):
+    """SealNeRFTeacherRenderer (SealNeRF/renderer.py:77-418): samples are mapped to the original space before the
+    field query and the colours of mapped samples are edited afterwards."""
+
+    def _map_samples(self, xyzs, dirs):
+        if self.seal_mapper is None:
+            return xyzs, dirs, None
+        return self.seal_mapper.map_to_origin(xyzs.view(-1, 3), dirs.view(-1, 3))
+
+    def _map_colors(self, xyzs, dirs, rgbs, mask):
+        if self.seal_mapper is None or not self.seal_mapper.has_color_edit():
+            return rgbs
+        rgbs = rgbs.float().contiguous()
+        return self.seal_mapper.map_color_(rgbs, mask)
+
+
+class StudentNetwork(SealRendererMixin, NeRFNetwork):
+    """SealNeRFStudentRenderder (SealNeRF/renderer.py:421-424): plain renderer + the force-filled bitfield."""

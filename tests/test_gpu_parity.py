@@ -1,0 +1,687 @@
+"""GPU parity tests (run with -m gpu on the B200): the sm_100a kernels, called through the C-ABI, against
+  (1) the CPU oracle (oracle/seal_oracle.c) on the same seeded inputs,
+  (2) the unmodified reference extensions prebuilt in oracle/_ref (same GPU), when present,
+  (3) the golden vectors of tests/golden (reference pure-torch code).
+Integer / index results are compared bit-exactly; float results with the tolerance stated in each test."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import refext
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+AABB = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def to(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def scene():
+    from seal3d_b200 import synth
+    bits, grid = synth.lego_like_occupancy()
+    o, d = synth.rays_for_step(0, 4096)
+    return dict(bits=bits, grid=grid, o=o, d=d, synth=synth)
+
+
+def rm():
+    from seal3d_b200 import raymarching
+    return raymarching
+
+
+# --------------------------------------------------------------------------------- raymarching
+
+
+def test_near_far_bit_exact(scene):
+    o, d = scene["o"], scene["d"]
+    n, f = rm().near_far_from_aabb(to(o), to(d), to(AABB), 0.2)
+    n0, f0 = oracle.near_far_from_aabb(o, d, AABB, 0.2)
+    assert np.array_equal(npy(n), n0) and np.array_equal(npy(f), f0)
+    ref = refext.load("raymarching")
+    rn, rf = torch.empty_like(n), torch.empty_like(f)
+    ref.near_far_from_aabb(to(o), to(d), to(AABB), o.shape[0], 0.2, rn, rf)
+    assert torch.equal(rn, n) and torch.equal(rf, f)
+
+
+def test_morton_packbits_exact():
+    rng = np.random.default_rng(0)
+    c = rng.integers(0, 128, (100000, 3)).astype(np.int32)
+    idx = rm().morton3D(to(c))
+    assert np.array_equal(npy(idx), oracle.morton3D(c))
+    assert np.array_equal(npy(rm().morton3D_invert(idx)), c)
+    grid = rng.uniform(0, 20, (1, 128 ** 3)).astype(np.float32)
+    bits = rm().packbits(to(grid), 10.0)
+    assert np.array_equal(npy(bits), oracle.packbits(grid, 10.0))
+    # ragged tail (N not a multiple of 4 bytes) goes through the scalar path
+    g2 = rng.uniform(0, 20, (1, 8 * 13)).astype(np.float32)
+    assert np.array_equal(npy(rm().packbits(to(g2), 10.0)), oracle.packbits(g2, 10.0))
+
+
+@pytest.mark.parametrize("dt_gamma,perturb", [(0.0, False), (0.0, True), (1.0 / 128, True)])
+def test_march_rays_train_bit_exact(scene, dt_gamma, perturb):
+    o, d, bits = scene["o"], scene["d"], scene["bits"]
+    N = o.shape[0]
+    n0, f0 = oracle.near_far_from_aabb(o, d, AABB, 0.2)
+    noises = np.random.default_rng(5).uniform(0, 1, N).astype(np.float32) if perturb else np.zeros(N, np.float32)
+    x0, d0, l0, r0, c0 = oracle.march_rays_train(o, d, 1.0, bits, 1, 128, n0, f0, noises, dt_gamma=dt_gamma)
+    counter = torch.zeros(2, dtype=torch.int32, device=dev())
+    x, dd, l, r = rm().march_rays_train(to(o), to(d), 1.0, to(bits), 1, 128, to(n0), to(f0), counter, -1, perturb, 128, True,
+                                        dt_gamma, 1024, noises=to(noises))
+    M = int(c0[0])
+    assert M > 50000
+    assert np.array_equal(npy(counter), c0)
+    assert np.array_equal(npy(r), r0)                      # (ray id, offset, count): exact, ray-major
+    assert x.shape[0] % 128 == 0 and x.shape[0] >= M
+    assert np.array_equal(npy(x)[:M], x0[:M]) and np.array_equal(npy(dd)[:M], d0[:M]) and np.array_equal(npy(l)[:M], l0[:M])
+    assert not npy(x)[M:].any()
+    # vs the reference kernel: slot order is atomic-order dependent there -> compare the canonical per-ray view
+    ref = refext.load("raymarching")
+    Mr = M + 128
+    rx, rd_, rl = (torch.zeros(Mr, k, device=dev()) for k in (3, 3, 2))
+    rr = torch.empty(N, 3, dtype=torch.int32, device=dev())
+    rc = torch.zeros(2, dtype=torch.int32, device=dev())
+    ref.march_rays_train(to(o), to(d), to(bits), 1.0, dt_gamma, 1024, N, 1, 128, Mr, to(n0), to(f0), rx, rd_, rl, rr, rc, to(noises))
+    rr_, rx_, rl_ = npy(rr), npy(rx), npy(rl)
+    order = np.argsort(rr_[:, 0], kind="stable")
+    rr_ = rr_[order]
+    assert np.array_equal(rr_[:, 0], np.arange(N)) and np.array_equal(rr_[:, 2], r0[:, 2]) and int(npy(rc)[0]) == M
+    xs, ls = npy(x), npy(l)
+    for i in np.nonzero(r0[:, 2])[0][::17]:
+        a, b, k = r0[i, 1], rr_[i, 1], r0[i, 2]
+        assert np.array_equal(xs[a:a + k], rx_[b:b + k]) and np.array_equal(ls[a:a + k], rl_[b:b + k])
+
+
+def test_march_budget_overflow_drops_trailing_rays(scene):
+    o, d, bits = scene["o"], scene["d"], scene["bits"]
+    n0, f0 = oracle.near_far_from_aabb(o, d, AABB, 0.2)
+    _, _, _, r0, c0 = oracle.march_rays_train(o, d, 1.0, bits, 1, 128, n0, f0)
+    budget = int(c0[0]) // 2
+    x, dd, l, r = rm().march_rays_train(to(o), to(d), 1.0, to(bits), 1, 128, to(n0), to(f0), None, budget, False, 128, False)
+    M = x.shape[0]
+    x0, _, _, _, _ = oracle.march_rays_train(o, d, 1.0, bits, 1, 128, n0, f0, M=M)
+    assert np.array_equal(npy(x), x0) and np.array_equal(npy(r), r0)
+    ws, depth, img = rm().composite_rays_train(torch.ones(M, device=dev()), torch.ones(M, 3, device=dev()), l, r)
+    dropped = (r0[:, 1] + r0[:, 2] > M) & (r0[:, 2] > 0)
+    assert dropped.any() and not npy(ws)[dropped].any()
+
+
+def _samples(scene, n_rays=2048):
+    o, d, bits = scene["o"][:n_rays], scene["d"][:n_rays], scene["bits"]
+    n0, f0 = oracle.near_far_from_aabb(o, d, AABB, 0.2)
+    x0, d0, l0, r0, c0 = oracle.march_rays_train(o, d, 1.0, bits, 1, 128, n0, f0)
+    M = int(c0[0])
+    return x0[:M], d0[:M], l0[:M], r0, M
+
+
+@pytest.mark.parametrize("T_thresh", [1e-4, 0.0])
+def test_composite_train_forward_backward(scene, T_thresh):
+    x0, d0, l0, r0, M = _samples(scene)
+    N = r0.shape[0]
+    rng = np.random.default_rng(1)
+    sig = rng.uniform(0, 40, M).astype(np.float32)
+    rgb = rng.uniform(0, 1, (M, 3)).astype(np.float32)
+    gws, gim = rng.normal(size=N).astype(np.float32), rng.normal(size=(N, 3)).astype(np.float32)
+    s, c = to(sig).requires_grad_(True), to(rgb).requires_grad_(True)
+    ws, depth, img = rm().composite_rays_train(s, c, to(l0), to(r0), T_thresh)
+    torch.autograd.backward([ws, img], [to(gws), to(gim)])
+    ws0, dp0, im0 = oracle.composite_rays_train_forward(sig, rgb, l0, r0, T_thresh)
+    gs0, gc0 = oracle.composite_rays_train_backward(gws, gim, sig, rgb, l0, r0, ws0, im0, T_thresh)
+    # tolerance: fp32 scans of up to ~300 terms with ex2.approx vs libm expf -> 1e-4 relative
+    np.testing.assert_allclose(npy(ws), ws0, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(npy(depth), dp0, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(npy(img), im0, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(npy(c.grad), gc0, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(npy(s.grad), gs0, rtol=2e-3, atol=2e-4)   # differences of nearly equal sums
+    ref = refext.load("raymarching")
+    rws, rdp, rim = torch.empty(N, device=dev()), torch.empty(N, device=dev()), torch.empty(N, 3, device=dev())
+    ref.composite_rays_train_forward(to(sig), to(rgb), to(l0), to(r0), M, N, T_thresh, rws, rdp, rim)
+    rgs, rgc = torch.zeros(M, device=dev()), torch.zeros(M, 3, device=dev())
+    ref.composite_rays_train_backward(to(gws), to(gim), to(sig), to(rgb), to(l0), to(r0), rws, rim, M, N, T_thresh, rgs, rgc)
+    np.testing.assert_allclose(npy(img), npy(rim), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(npy(depth), npy(rdp), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(npy(s.grad), npy(rgs), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(npy(c.grad), npy(rgc), rtol=1e-5, atol=1e-6)
+
+
+def test_inference_march_and_composite_loop(scene):
+    """The eval loop of nerf/renderer.py:335-372 step by step against the oracle (bit-exact marching, 1e-4 compositing)."""
+    o, d, bits = scene["o"][:1024], scene["d"][:1024], scene["bits"]
+    N = o.shape[0]
+    n0, f0 = oracle.near_far_from_aabb(o, d, AABB, 0.2)
+    rng = np.random.default_rng(2)
+    ws, dp, im = (torch.zeros(N, device=dev()), torch.zeros(N, device=dev()), torch.zeros(N, 3, device=dev()))
+    ws0, dp0, im0 = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, 3), np.float32)
+    alive = torch.arange(N, dtype=torch.int32, device=dev())
+    rt = to(n0).clone()
+    alive0, rt0 = np.arange(N, dtype=np.int32), n0.copy()
+    step = 0
+    while step < 1024 and alive.shape[0] > 0:
+        na = alive.shape[0]
+        n_step = max(min(N // na, 8), 1)
+        x, dd, l = rm().march_rays(na, n_step, alive, rt, to(o), to(d), 1.0, to(bits), 1, 128, to(n0), to(f0), 128, False, 0, 1024)
+        x0, d0, l0 = oracle.march_rays(na, n_step, alive0, rt0, o, d, 1.0, bits, 1, 128, n0, f0, align=128)
+        assert np.array_equal(npy(x), x0) and np.array_equal(npy(l), l0)
+        sig = rng.uniform(0, 60, x0.shape[0]).astype(np.float32)
+        rgb = rng.uniform(0, 1, (x0.shape[0], 3)).astype(np.float32)
+        rm().composite_rays(na, n_step, alive, rt, to(sig), to(rgb), l, ws, dp, im, 1e-2)
+        oracle.composite_rays(na, n_step, alive0, rt0, sig, rgb, l0, ws0, dp0, im0, 1e-2)
+        assert np.array_equal(npy(alive) >= 0, alive0 >= 0)
+        alive = alive[alive >= 0]
+        alive0 = alive0[alive0 >= 0]
+        step += n_step
+    assert step > 8
+    np.testing.assert_allclose(npy(im), im0, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(npy(dp), dp0, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(npy(rt), rt0, rtol=1e-6)
+
+
+# --------------------------------------------------------------------------------- gridencoder
+
+
+def _grid(D=3, C=2, L=16, log2T=19, seed=0, desired=2048, scale=1.0):
+    offsets, pls = oracle.grid_offsets(input_dim=D, num_levels=L, level_dim=C, log2_hashmap_size=log2T, desired_resolution=desired)
+    rng = np.random.default_rng(seed)
+    emb = (rng.uniform(-1, 1, (offsets[-1], C)) * scale).astype(np.float32)
+    return offsets, pls, emb
+
+
+def _enc_raw(x, emb, offsets, pls, dtype=torch.float32, calc=False, gridtype=0, ac=False, interp=0):
+    """call the C-ABI exactly like gridencoder/grid.py:54 does; returns outputs [L,B,C], dy_dx"""
+    from seal3d_b200 import _lib
+    B, D = x.shape
+    L, C = offsets.shape[0] - 1, emb.shape[1]
+    e = to(emb).to(dtype)
+    out = torch.empty(L, B, C, device=dev(), dtype=dtype)
+    dy = torch.empty(B, L * D * C, device=dev(), dtype=dtype) if calc else None
+    _lib.call("s3d_grid_encode_forward", to(x), e, to(offsets), out, B, D, C, L, float(np.log2(pls)), 16, dy, gridtype, int(ac), interp,
+              0 if dtype == torch.float32 else 1)
+    return out, dy
+
+
+def test_grid_encode_forward_config1():
+    """BASELINE.json config 1: 4096 random points, D3 L16 C2, CPU ref vs kernel (float32 table)."""
+    offsets, pls, emb = _grid()
+    x = np.random.default_rng(8).uniform(0, 1, (4096, 3)).astype(np.float32)
+    x[0] = [0.0, 1.0, 0.5]
+    x[1] = [1.0001, 0.5, 0.5]
+    x[2] = [-1e-7, 0.5, 0.5]
+    out, dy = _enc_raw(x, emb, offsets, pls, calc=True)
+    ref, rdy = oracle.grid_encode_forward(x, emb, offsets, pls, 16, calc_grad_inputs=True)
+    np.testing.assert_allclose(npy(out), ref, rtol=1e-5, atol=1e-6)   # same op order; only exp2f may differ by an ulp
+    assert not npy(out)[:, 1].any() and not npy(out)[:, 2].any()
+    np.testing.assert_allclose(npy(dy), rdy, rtol=1e-4, atol=1e-3)
+    rext = refext.load("gridencoder")
+    rout = torch.empty_like(out)
+    rext.grid_encode_forward(to(x), to(emb), to(offsets), rout, 4096, 3, 2, 16, float(np.log2(pls)), 16, None, 0, False, 0)
+    assert torch.equal(rout, out), "float32 forward is expected to be bit-identical to the reference kernel"
+
+
+@pytest.mark.parametrize("D,C,gridtype,ac,interp", [(2, 1, 0, False, 0), (2, 4, 1, True, 0), (3, 8, 0, False, 1), (3, 1, 1, False, 1),
+                                                    (4, 2, 0, False, 0), (3, 4, 0, True, 0)])
+def test_grid_encode_forward_shapes(D, C, gridtype, ac, interp):
+    offsets, pls = oracle.grid_offsets(input_dim=D, num_levels=6, level_dim=C, log2_hashmap_size=14, desired_resolution=256, align_corners=ac)
+    rng = np.random.default_rng(D * 10 + C)
+    emb = rng.uniform(-1, 1, (offsets[-1], C)).astype(np.float32)
+    x = rng.uniform(0, 1, (999, D)).astype(np.float32)
+    out, dy = _enc_raw(x, emb, offsets, pls, calc=True, gridtype=gridtype, ac=ac, interp=interp)
+    ref, rdy = oracle.grid_encode_forward(x, emb, offsets, pls, 16, True, gridtype, ac, interp)
+    np.testing.assert_allclose(npy(out), ref, rtol=1e-5, atol=1e-6)
+    if not (interp == 1 and D > 1):
+        np.testing.assert_allclose(npy(dy), rdy, rtol=1e-4, atol=1e-3)
+    if D <= 3:
+        rext = refext.load("gridencoder")
+        rout = torch.empty_like(out)
+        rext.grid_encode_forward(to(x), to(emb), to(offsets), rout, 999, D, C, 6, float(np.log2(pls)), 16, None, gridtype, ac, interp)
+        np.testing.assert_allclose(npy(out), npy(rout), rtol=1e-6, atol=1e-7)
+
+
+def test_grid_encode_forward_half_table():
+    offsets, pls, emb = _grid(scale=1.0)
+    emb = oracle.round_to_half(emb)
+    x = np.random.default_rng(9).uniform(0, 1, (4096, 3)).astype(np.float32)
+    out, _ = _enc_raw(x, emb, offsets, pls, dtype=torch.float16)
+    exact, _ = oracle.grid_encode_forward(x, emb, offsets, pls, 16)             # fp32 accumulate
+    refh, _ = oracle.grid_encode_forward(x, emb, offsets, pls, 16, half_accum=True)  # reference-style fp16 accumulate
+    got = npy(out.float())
+    # ours rounds once: within half an fp16 ulp of the exact blend; the reference's running fp16 sum is looser
+    assert np.abs(got - exact).max() <= 2.0 ** -11 * 1.01
+    assert np.abs(got - exact).max() <= np.abs(refh - exact).max() + 1e-7
+    rext = refext.load("gridencoder")
+    rout = torch.empty_like(out)
+    rext.grid_encode_forward(to(x), to(emb).half(), to(offsets), rout, 4096, 3, 2, 16, float(np.log2(pls)), 16, None, 0, False, 0)
+    np.testing.assert_allclose(got, npy(rout.float()), atol=4e-3)
+
+
+def _ray_ordered_points(scene, n_rays=2048):
+    x0, _, _, _, M = _samples(scene, n_rays)
+    return ((x0 + 1) / 2).astype(np.float32)
+
+
+@pytest.mark.parametrize("big", [False, True])
+def test_grid_encode_backward(scene, big):
+    """scatter-add with the in-warp segmented reduction vs the float64-accumulating oracle (rel 1e-4), on ray-ordered
+    samples (long runs of equal cells) and on random points; big=True takes the one-thread-all-levels path."""
+    from seal3d_b200 import _lib
+    offsets, pls, emb = _grid()
+    pts = _ray_ordered_points(scene, 4096 if big else 256)
+    rnd = np.random.default_rng(3).uniform(0, 1, (pts.shape[0] // 2, 3)).astype(np.float32)
+    x = np.concatenate([pts, rnd])
+    if big:
+        assert x.shape[0] >= (1 << 17)
+    else:
+        x = x[:40000]
+    x[5] = [1.5, 0.2, 0.2]
+    B = x.shape[0]
+    g = np.random.default_rng(4).normal(size=(16, B, 2)).astype(np.float32)
+    ge = torch.zeros(offsets[-1], 2, device=dev())
+    _lib.call("s3d_grid_encode_backward", to(g), to(x), to(emb), to(offsets), ge, B, 3, 2, 16, float(np.log2(pls)), 16, None, None, 0, 0, 0, 0)
+    ref = oracle.grid_encode_backward(g, x, emb.shape, offsets, pls, 16)
+    got = npy(ge)
+    scale = np.abs(ref).max()
+    assert np.abs(got - ref).max() <= 1e-4 * scale + 1e-5
+    np.testing.assert_allclose(got[np.abs(ref) > 1e-2 * scale], ref[np.abs(ref) > 1e-2 * scale], rtol=1e-4)
+    rext = refext.load("gridencoder")
+    rge = torch.zeros_like(ge)
+    rext.grid_encode_backward(to(g), to(x), to(emb), to(offsets), rge, B, 3, 2, 16, float(np.log2(pls)), 16, None, None, 0, False, 0)
+    assert np.abs(npy(rge) - ref).max() <= 1e-3 * scale       # the reference's own float-atomic error
+    assert np.abs(got - ref).max() <= np.abs(npy(rge) - ref).max() * 1.5 + 1e-6 * scale
+
+
+def test_grid_encode_backward_half_and_input_grad():
+    from seal3d_b200 import _lib
+    offsets, pls, emb = _grid(L=8, log2T=15, desired=512)
+    x = np.random.default_rng(5).uniform(0, 1, (5000, 3)).astype(np.float32)
+    g = (np.random.default_rng(6).normal(size=(8, 5000, 2)) * 0.01).astype(np.float32)
+    gh = oracle.round_to_half(g)
+    ge = torch.zeros(offsets[-1], 2, device=dev(), dtype=torch.float16)
+    _lib.call("s3d_grid_encode_backward", to(gh).half(), to(x), to(emb).half(), to(offsets), ge, 5000, 3, 2, 8, float(np.log2(pls)), 16, None, None, 0, 0, 0, 1)
+    ref = oracle.grid_encode_backward(gh, x, emb.shape, offsets, pls, 16)
+    assert np.abs(npy(ge.float()) - ref).max() <= 2e-2 * np.abs(ref).max()      # fp16 atomics
+    # grad_inputs through dy_dx (gridencoder.cu:341-366), float32
+    out, dy = _enc_raw(x, emb, offsets, pls, calc=True)
+    gi = torch.zeros(5000, 3, device=dev())
+    ge32 = torch.zeros(offsets[-1], 2, device=dev())
+    _lib.call("s3d_grid_encode_backward", to(g), to(x), to(emb), to(offsets), ge32, 5000, 3, 2, 8, float(np.log2(pls)), 16, dy, gi, 0, 0, 0, 0)
+    _, rdy = oracle.grid_encode_forward(x, emb, offsets, pls, 16, calc_grad_inputs=True)
+    _, rgi = oracle.grid_encode_backward(g, x, emb.shape, offsets, pls, 16, dy_dx=rdy)
+    np.testing.assert_allclose(npy(gi), rgi, rtol=1e-3, atol=1e-4)
+
+
+def test_grid_encoder_module_autograd_and_tv():
+    from seal3d_b200.gridencoder import GridEncoder
+    enc = GridEncoder(desired_resolution=2048).to(dev())
+    assert list(npy(enc.offsets)[:6]) == [0, 4920, 18744, 51512, 136696, 352696] and enc.embeddings.shape == (6119864, 2)
+    enc.embeddings.data.uniform_(-1, 1)
+    x = (torch.rand(3000, 3, device=dev()) * 2 - 1)
+    y = enc(x, bound=1)
+    w = torch.randn_like(y)
+    (y * w).sum().backward()
+    emb = npy(enc.embeddings)
+    u = ((npy(x) + 1) / 2).astype(np.float32)
+    ref, _ = oracle.grid_encode_forward(u, emb, npy(enc.offsets), enc.per_level_scale, 16)
+    np.testing.assert_allclose(npy(y), ref.transpose(1, 0, 2).reshape(3000, 32), rtol=1e-5, atol=1e-6)
+    gref = oracle.grid_encode_backward(np.ascontiguousarray(npy(w).reshape(3000, 16, 2).transpose(1, 0, 2)), u, emb.shape, npy(enc.offsets),
+                                       enc.per_level_scale, 16)
+    np.testing.assert_allclose(npy(enc.embeddings.grad), gref, rtol=1e-4, atol=1e-5)
+    # TV regulariser adds into .grad
+    before = enc.embeddings.grad.clone()
+    pts = torch.rand(2000, 3, device=dev()) * 2 - 1
+    enc.grad_total_variation(1e-3, pts, 1)
+    g0 = npy(before).copy()
+    oracle.grad_total_variation(((npy(pts) + 1) / 2).astype(np.float32), emb, g0, npy(enc.offsets), 1e-3, enc.per_level_scale, 16)
+    np.testing.assert_allclose(npy(enc.embeddings.grad), g0, rtol=1e-3, atol=1e-6)
+    # autocast: fp16 shadow table, fp32 gradient on the parameter
+    enc.embeddings.grad = None
+    with torch.autocast("cuda", dtype=torch.float16):
+        yh = enc(x, bound=1)
+    assert yh.dtype == torch.float16
+    yh.float().sum().backward()
+    assert enc.embeddings.grad.dtype == torch.float32
+    np.testing.assert_allclose(npy(yh.float()), npy(y), atol=4e-3)
+
+
+def test_grid_encode_full_size_linearity():
+    """B = 2^22 (the roofline batch): encode is linear in the table and every output row depends on its point only."""
+    offsets, pls, e1 = _grid(seed=1)
+    _, _, e2 = _grid(seed=2)
+    x = np.random.default_rng(8).uniform(0, 1, (1 << 22, 3)).astype(np.float32)
+    a, _ = _enc_raw(x, e1, offsets, pls)
+    b, _ = _enc_raw(x, e2, offsets, pls)
+    c, _ = _enc_raw(x, (e1 + e2).astype(np.float32), offsets, pls)
+    assert (a + b - c).abs().max().item() < 2e-5
+    sub = np.arange(0, 1 << 22, 1 << 10)
+    ref, _ = oracle.grid_encode_forward(x[sub], e1, offsets, pls, 16)
+    np.testing.assert_allclose(npy(a[:, to(sub)]), ref, rtol=1e-5, atol=1e-6)
+
+
+# --------------------------------------------------------------------------------- SH / freq
+
+
+@pytest.mark.parametrize("deg", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_sh_forward_backward(deg):
+    from seal3d_b200.shencoder import sh_encode
+    rng = np.random.default_rng(deg)
+    x = rng.normal(size=(3001, 3)).astype(np.float32)
+    x[:2000] /= np.linalg.norm(x[:2000], axis=1, keepdims=True)       # the rest is deliberately off the unit sphere
+    x[2000:] *= 0.5
+    xt = to(x).requires_grad_(True)
+    y = sh_encode(xt, deg, True)
+    g = rng.normal(size=(3001, deg * deg)).astype(np.float32)
+    y.backward(to(g))
+    ref, dy = oracle.sh_encode_forward(x, deg, True)
+    np.testing.assert_allclose(npy(y), ref, rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(npy(xt.grad), oracle.sh_encode_backward(g, x, deg, dy), rtol=2e-4, atol=2e-4)
+    rext = refext.load("shencoder")
+    ry = torch.empty(3001, deg * deg, device=dev())
+    rdy = torch.empty(3001, 3 * deg * deg, device=dev())
+    rext.sh_encode_forward(to(x), ry, 3001, 3, deg, rdy)
+    np.testing.assert_allclose(npy(y), npy(ry), rtol=2e-5, atol=2e-5)
+    rgi = torch.zeros(3001, 3, device=dev())
+    rext.sh_encode_backward(to(g), to(x), 3001, 3, deg, rdy, rgi)
+    np.testing.assert_allclose(npy(xt.grad), npy(rgi), rtol=2e-4, atol=2e-4)
+
+
+def test_sh_matches_reference_closed_form_golden():
+    from seal3d_b200.shencoder import SHEncoder
+    g = np.load(os.path.join(G, "cpu_sh.npz"))
+    for deg in (1, 2, 3, 4, 5):
+        y = SHEncoder(degree=deg)(to(g["dirs"]))
+        np.testing.assert_allclose(npy(y), g["deg%d" % deg], rtol=1e-5, atol=3e-6)
+
+
+def test_freq_encoder():
+    from seal3d_b200.freqencoder import FreqEncoder
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-1, 1, (2000, 3)).astype(np.float32)
+    enc = FreqEncoder(3, 6)
+    xt = to(x).requires_grad_(True)
+    y = enc(xt)
+    g = rng.normal(size=(2000, enc.output_dim)).astype(np.float32)
+    y.backward(to(g))
+    ref = oracle.freq_encode_forward(x, 6)
+    np.testing.assert_allclose(npy(y), ref, atol=2e-5)        # sin.approx (the reference builds with -use_fast_math)
+    np.testing.assert_allclose(npy(xt.grad), oracle.freq_encode_backward(g, npy(y), 3, 6), rtol=1e-4, atol=1e-4)
+    rext = refext.load("freqencoder")
+    ry = torch.empty_like(y)
+    rext.freq_encode_forward(to(x), 2000, 3, 6, enc.output_dim, ry)
+    np.testing.assert_allclose(npy(y), npy(ry), atol=1e-6)
+
+
+# --------------------------------------------------------------------------------- ffmlp (tcgen05)
+
+
+def _ffmlp_case(B, din, dh, dout, nl, seed=0, wscale=None):
+    rng = np.random.default_rng(seed)
+    nW = dh * din + dh * dh * (nl - 1) + dout * dh
+    s = wscale or np.sqrt(3 / dh)
+    W = oracle.round_to_half(rng.uniform(-s, s, nW).astype(np.float32))
+    x = oracle.round_to_half(rng.normal(size=(B, din)).astype(np.float32))
+    return W, x
+
+
+@pytest.mark.parametrize("B,din,dh,nl,act", [(128, 32, 64, 2, 0), (1000, 32, 64, 3, 0), (4096, 64, 64, 2, 0), (640, 16, 32, 2, 0),
+                                             (512, 128, 64, 2, 0), (256, 32, 64, 2, 3), (256, 48, 16, 4, 5)])
+def test_ffmlp_forward(B, din, dh, nl, act):
+    from seal3d_b200 import _lib
+    W, x = _ffmlp_case(B, din, dh, 16, nl)
+    fb = torch.zeros(nl, B, dh, device=dev(), dtype=torch.float16)
+    out = torch.zeros(B, 16, device=dev(), dtype=torch.float16)
+    _lib.call("s3d_ffmlp_forward", to(x).half(), to(W).half(), B, din, 16, dh, nl, act, 6, fb, out)
+    ref, rfb = oracle.ffmlp_forward(x, W, din, 16, dh, nl, act, 6, round_half_act=True)
+    # fp16 storage of activations/outputs, fp32 accumulation: 2^-10 relative + a few ulp of the magnitude
+    tol = 3e-3 * max(1.0, np.abs(ref).max())
+    assert np.abs(npy(fb.float()) - rfb).max() <= 3e-3 * max(1.0, np.abs(rfb).max())
+    assert np.abs(npy(out.float()) - ref).max() <= tol
+    out2 = torch.zeros_like(out)
+    _lib.call("s3d_ffmlp_inference", to(x).half(), to(W).half(), B, din, 16, dh, nl, act, 6, None, out2)
+    assert torch.equal(out, out2)
+    if B % 128 == 0 and act == 0:
+        rext = refext.load("ffmlp")
+        rext.allocate_splitk(nl + 1)
+        rfb_, rout = torch.zeros_like(fb), torch.zeros_like(out)
+        rext.ffmlp_forward(to(x).half(), to(W).half(), B, din, 16, dh, nl, act, 6, rfb_, rout)
+        # the reference accumulates in fp16 (wmma accumulator __half): its own error bounds the comparison
+        assert np.abs(npy(rout.float()) - ref).max() <= 2e-2 * max(1.0, np.abs(ref).max())
+        assert np.abs(npy(out.float()) - ref).max() <= np.abs(npy(rout.float()) - ref).max() + tol
+
+
+@pytest.mark.parametrize("B,din,dh,nl,act", [(128, 32, 64, 2, 0), (1024, 32, 64, 3, 0), (40000, 64, 64, 2, 0), (384, 128, 64, 2, 0),
+                                             (256, 16, 32, 2, 3)])
+def test_ffmlp_backward(B, din, dh, nl, act):
+    from seal3d_b200 import _lib
+    W, x = _ffmlp_case(B, din, dh, 16, nl, seed=1)
+    fb = torch.zeros(nl, B, dh, device=dev(), dtype=torch.float16)
+    out = torch.zeros(B, 16, device=dev(), dtype=torch.float16)
+    _lib.call("s3d_ffmlp_forward", to(x).half(), to(W).half(), B, din, 16, dh, nl, act, 6, fb, out)
+    g = oracle.round_to_half((np.random.default_rng(2).normal(size=(B, 16)) / B).astype(np.float32))
+    bb = torch.zeros(nl, B, dh, device=dev(), dtype=torch.float16)
+    gi = torch.zeros(B, din, device=dev(), dtype=torch.float16)
+    gw = torch.zeros(W.shape[0], device=dev(), dtype=torch.float16)
+    _lib.call("s3d_ffmlp_backward", to(g).half(), to(x).half(), to(W).half(), fb, B, din, 16, dh, nl, act, 6, 1, bb, gi, gw)
+    rgw, rgi, rbb = oracle.ffmlp_backward(g, x, W, npy(fb.float()), din, 16, dh, nl, act)
+    for got, ref, name in ((bb, rbb, "backward_buffer"), (gi, rgi, "grad_inputs"), (gw, rgw, "grad_weights")):
+        err = np.abs(npy(got.float()) - ref).max()
+        assert err <= 4e-3 * np.abs(ref).max() + 1e-7, (name, err, np.abs(ref).max())
+
+
+# --------------------------------------------------------------------------------- proxy + losses + adam
+
+
+def test_proxy_bbox_matches_reference_golden():
+    from seal3d_b200.seal import SealBBoxMapper
+    g = np.load(os.path.join(G, "cpu_proxy.npz"))
+    md = {k[3:]: g[k] for k in g.files if k.startswith("md_")}
+    mapper = SealBBoxMapper(md, g["tris"], device=dev())
+    p, d, m = mapper.map_to_origin(to(g["points"]), to(g["dirs"]))
+    assert np.array_equal(npy(m), g["mask"])
+    np.testing.assert_allclose(npy(p), g["mapped_points"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(npy(d), g["mapped_dirs"], rtol=1e-5, atol=1e-6)
+    keep = ~g["mask"] & ~((g["points"] > md["empty_bound"][0]) & (g["points"] < md["empty_bound"][1])).all(1)
+    assert np.array_equal(npy(p)[keep], g["points"][keep])
+
+
+def test_color_edits_match_reference_golden():
+    from seal3d_b200.seal import SealBBoxMapper
+    from seal3d_b200 import synth
+    g = np.load(os.path.join(G, "cpu_color.npz"))
+    md, tris = synth.bbox_edit(hsv=g["mod"])
+    out = SealBBoxMapper(md, tris, device=dev()).map_color(None, None, to(g["rgb"]))
+    np.testing.assert_allclose(npy(out), g["out_hsv"], rtol=1e-5, atol=1e-5)
+    md["rgb"], md["rgb_light_offset"] = g["target"], g["light"]
+    del md["hsv"]
+    out = SealBBoxMapper(md, tris, device=dev()).map_color(None, None, to(g["rgb"]))
+    np.testing.assert_allclose(npy(out), g["out_rgb"], rtol=1e-5, atol=1e-5)
+    # masked variant == reference semantics rgbs[mask] = map_color(rgbs[mask])
+    mask = np.random.default_rng(0).uniform(size=g["rgb"].shape[0]) < 0.3
+    rg = to(g["rgb"]).clone()
+    SealBBoxMapper(md, tris, device=dev()).map_color_(rg, to(mask))
+    np.testing.assert_allclose(npy(rg)[mask], oracle.seal_modify_rgb(g["rgb"][mask], g["target"], float(g["light"])), rtol=1e-5, atol=1e-5)
+    assert np.array_equal(npy(rg)[~mask], g["rgb"][~mask])
+
+
+def test_losses_and_adam():
+    from seal3d_b200 import _lib
+    rng = np.random.default_rng(0)
+    M = 10007
+    ss, st = rng.uniform(0, 5, M).astype(np.float32), rng.uniform(0, 5, M).astype(np.float32)
+    cs, ct = rng.uniform(0, 1, (M, 3)).astype(np.float32), rng.uniform(0, 1, (M, 3)).astype(np.float32)
+    loss = torch.zeros(2, device=dev())
+    gs, gc = torch.empty(M, device=dev()), torch.empty(M, 3, device=dev())
+    _lib.call("s3d_pretrain_loss", to(ss), to(cs), to(st), to(ct), M, loss, gs, gc)
+    l0, gs0, gc0 = oracle.pretrain_loss(ss, cs, st, ct)
+    np.testing.assert_allclose(npy(loss)[0], l0, rtol=1e-5)
+    np.testing.assert_allclose(npy(gs), gs0, rtol=1e-6)
+    np.testing.assert_allclose(npy(gc), gc0, rtol=1e-6)
+    N = 4099
+    comp, ws, dp = rng.uniform(0, 1, (N, 3)).astype(np.float32), rng.uniform(0, 1, N).astype(np.float32), rng.uniform(0, 3, N).astype(np.float32)
+    it, dt = rng.uniform(0, 1, (N, 3)).astype(np.float32), rng.uniform(0, 3, N).astype(np.float32)
+    loss.zero_()
+    gi, gw = torch.empty(N, 3, device=dev()), torch.empty(N, device=dev())
+    _lib.call("s3d_finetune_loss", to(comp), to(ws), to(dp), to(it), to(dt), N, 1.0, loss, gi, gw)
+    img = comp + (1 - ws)[:, None]
+    l1, gi0, _ = oracle.finetune_loss(img, dp, it, dt)
+    np.testing.assert_allclose(npy(loss).sum(), l1, rtol=1e-5)
+    np.testing.assert_allclose(npy(gi), gi0, rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(npy(gw), -gi0.sum(1), rtol=1e-5, atol=1e-9)
+    # Adam against torch.optim.Adam(betas=(0.9, 0.99), eps=1e-15)
+    n = 100003
+    p0 = torch.randn(n, device=dev())
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    p, m, v = p0.clone(), torch.zeros(n, device=dev()), torch.zeros(n, device=dev())
+    sh = torch.zeros(n, device=dev(), dtype=torch.float16)
+    for step in range(1, 4):
+        g = torch.randn(n, device=dev())
+        p_ref.grad = g.clone()
+        opt.step()
+        gg = (g * 2).contiguous()
+        _lib.call("s3d_adam_step", p, gg, m, v, sh, n, 1e-2, 0.9, 0.99, 1e-15, step, 0.5, 1, 0)
+        assert not gg.any()
+    np.testing.assert_allclose(npy(p), npy(p_ref), rtol=1e-5, atol=1e-6)
+    assert torch.equal(sh, p.half())
+
+
+# --------------------------------------------------------------------------------- field + renderer + trainer
+
+
+def _networks(scene, hsv=None):
+    from seal3d_b200.seal import TeacherNetwork, StudentNetwork, SealBBoxMapper
+    synth = scene["synth"]
+    torch.manual_seed(0)
+    t, s = TeacherNetwork(bound=1).to(dev()), StudentNetwork(bound=1).to(dev())
+    for net, kind in ((t, "teacher"), (s, "student")):
+        fp = synth.field_params(kind)
+        net.encoder.embeddings.data.copy_(to(fp["emb_sigma"]))
+        net.encoder_color.embeddings.data.copy_(to(fp["emb_color"]))
+        for lin, k in ((net.sigma_net[0], "w_s0"), (net.sigma_net[1], "w_s1"), (net.color_net[0], "w_c0"), (net.color_net[1], "w_c1"), (net.color_net[2], "w_c2")):
+            lin.weight.data.copy_(to(fp[k]))
+        net.density_bitfield.copy_(to(scene["bits"]))
+        net.density_grid.copy_(to(scene["grid"]))
+    md, tris = synth.bbox_edit(hsv=hsv)
+    mapper = SealBBoxMapper(md, tris, device=dev())
+    for net in (t, s):
+        net.init_mapper(mapper)
+        net.hack_bitfield()
+    return t, s, md, tris
+
+
+def test_field_forward_backward_vs_oracle(scene):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    t, s, _, _ = _networks(scene)
+    synth = scene["synth"]
+    fp = synth.field_params("teacher")
+    offsets, pls = synth.grid_offsets()
+    f = oracle.NGPField(fp["emb_sigma"], fp["emb_color"], fp["w_s0"], fp["w_s1"], fp["w_c0"], fp["w_c1"], fp["w_c2"], offsets, pls)
+    x0, d0, _, _, M = _samples(scene, 256)
+    x0, d0 = x0[:8192], d0[:8192]
+    sig0, rgb0 = f.forward(x0, d0, keep=True)
+    t.train()
+    sig, rgb = t(to(x0), to(d0))
+    np.testing.assert_allclose(npy(sig), sig0, rtol=1e-4, atol=1e-6)       # north-star tolerance: 1e-4 rel fp32
+    np.testing.assert_allclose(npy(rgb), rgb0, rtol=1e-4, atol=1e-6)
+    rng = np.random.default_rng(0)
+    gs, gc = rng.normal(size=sig0.shape).astype(np.float32), rng.normal(size=rgb0.shape).astype(np.float32)
+    torch.autograd.backward([sig, rgb], [to(gs), to(gc)])
+    ref = f.backward(gs, gc)
+    for name, p in (("w_s0", t.sigma_net[0].weight), ("w_s1", t.sigma_net[1].weight), ("w_c0", t.color_net[0].weight),
+                    ("w_c1", t.color_net[1].weight), ("w_c2", t.color_net[2].weight), ("emb_sigma", t.encoder.embeddings),
+                    ("emb_color", t.encoder_color.embeddings)):
+        sc = np.abs(ref[name]).max()
+        assert np.abs(npy(p.grad) - ref[name]).max() <= 2e-4 * sc + 1e-7, name
+
+
+def test_teacher_render_and_hack_bitfield(scene):
+    t, s, md, tris = _networks(scene, hsv=[0.3, 0.0, 0.0])
+    # force-filled cells: every cell of the union of the source and target boxes is occupied now
+    fb = md["force_fill_bound"]
+    for b in fb:
+        lo = np.floor((b[0] + 1) / 2 * 128).astype(int)
+        hi = np.floor((b[1] + 1) / 2 * 128).astype(int)
+        c = np.stack(np.meshgrid(*[np.arange(lo[i], hi[i]) for i in range(3)], indexing="ij"), -1).reshape(-1, 3).astype(np.int32)
+        idx = oracle.morton3D(c).astype(np.int64)
+        assert np.all(npy(t.density_bitfield)[idx // 8] == 255)
+    t.restore_bitfield()
+    assert np.array_equal(npy(t.density_bitfield), scene["bits"])
+    t.hack_bitfield()
+    # eval render of the teacher == the same loop composed from oracle pieces with the mapped field
+    o, d = scene["o"][:512], scene["d"][:512]
+    t.eval()
+    with torch.no_grad():
+        out = t.render(to(o)[None], to(d)[None], perturb=False, bg_color=1, T_thresh=1e-4)
+    t.train()
+    with torch.no_grad():
+        out2 = t.render(to(o)[None], to(d)[None], perturb=False, force_all_rays=True, bg_color=1, T_thresh=1e-4)
+    # train-mode and eval-mode renders of the same rays agree (different marchers / compositors, same samples)
+    np.testing.assert_allclose(npy(out["image"]), npy(out2["image"]), rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(npy(out["depth"]), npy(out2["depth"]), rtol=2e-3, atol=2e-3)
+    assert npy(out["image"]).min() >= 0 and npy(out["image"]).max() <= 1 + 1e-5
+
+
+def test_update_extra_state_and_distill_steps(scene):
+    from seal3d_b200.trainer import DistillTrainer
+    t, s, _, _ = _networks(scene)
+    tr = DistillTrainer(s, t, lr=1e-2, update_interval=4)
+    o, d = to(scene["o"][:2048]), to(scene["d"][:2048])
+    losses = []
+    for i in range(8):
+        l = tr.distill_step(o, d, perturb=False, force_all_rays=(i < 4))
+        losses.append(float(npy(l).sum()))
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
+    assert s.mean_count > 0 and s.iter_density >= 1
+    assert int(npy(s.density_bitfield).astype(np.int32).sum()) > 0
+    # pretraining: only the tables move
+    w_before = s.sigma_net[0].weight.detach().clone()
+    e_before = s.encoder.embeddings.detach().clone()
+    x0, d0, _, _, M = _samples(scene, 128)
+    pts, dirs = to(x0[:4096]), to(d0[:4096])
+    with torch.no_grad():
+        sig_t, rgb_t = t(pts, dirs)
+    lp = [float(npy(tr.pretrain_step(pts, dirs, sig_t.float().contiguous(), rgb_t.float().contiguous()))[0]) for _ in range(6)]
+    assert lp[-1] < lp[0]
+    assert torch.equal(w_before, s.sigma_net[0].weight.detach()) and not torch.equal(e_before, s.encoder.embeddings.detach())
+
+
+def test_reference_named_extension_modules():
+    """the drop-in boundary: import the shim modules by the reference's module names and call them the way
+    gridencoder/grid.py:54 and raymarching/raymarching.py:45 do"""
+    import sys
+    import seal3d_b200
+    sys.path.insert(0, os.path.dirname(seal3d_b200.__file__))
+    import _gridencoder
+    import _raymarching
+    import _shencoder
+    import _freqencoder
+    import _ffmlp
+    offsets, pls, emb = _grid(L=4, log2T=12, desired=128)
+    x = np.random.default_rng(0).uniform(0, 1, (500, 3)).astype(np.float32)
+    out = torch.empty(4, 500, 2, device=dev())
+    _gridencoder.grid_encode_forward(to(x), to(emb), to(offsets), out, 500, 3, 2, 4, float(np.log2(pls)), 16, None, 0, False, 0)
+    ref, _ = oracle.grid_encode_forward(x, emb, offsets, pls, 16)
+    np.testing.assert_allclose(npy(out), ref, rtol=1e-5, atol=1e-6)
+    o = np.random.default_rng(1).uniform(-2, 2, (100, 3)).astype(np.float32)
+    d = np.random.default_rng(2).normal(size=(100, 3)).astype(np.float32)
+    n, f = torch.empty(100, device=dev()), torch.empty(100, device=dev())
+    _raymarching.near_far_from_aabb(to(o), to(d), to(AABB), 100, 0.2, n, f)
+    n0, f0 = oracle.near_far_from_aabb(o, d, AABB, 0.2)
+    assert np.array_equal(npy(n), n0) and np.array_equal(npy(f), f0)
+    with pytest.raises(RuntimeError):
+        _gridencoder.grid_encode_forward(to(x).cpu(), to(emb), to(offsets), out, 500, 3, 2, 4, float(np.log2(pls)), 16, None, 0, False, 0)
+    y = torch.empty(100, 16, device=dev())
+    _shencoder.sh_encode_forward(to(d), y, 100, 3, 4, None)
+    np.testing.assert_allclose(npy(y), oracle.sh_encode_forward(d, 4)[0], rtol=2e-5, atol=2e-5)
+    _ffmlp.allocate_splitk(3)
+    assert hasattr(_freqencoder, "freq_encode_forward")
