@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=int(os.environ.get("S3D_BENCH_RAYS", 65536)), help="rays per step per GPU")
     ap.add_argument("--precision", default=os.environ.get("S3D_BENCH_PRECISION", "fp16"), choices=["fp32", "fp16"])
+    ap.add_argument("--engine", default=os.environ.get("S3D_BENCH_ENGINE", "fused"), choices=["fused", "autograd"],
+                    help="fused = csrc/field.cu kernels (tcgen05 MLP, interleaved tables); autograd = op-by-op kernels + torch GEMMs")
     ap.add_argument("--cpu-rays", type=int, default=1024, help="rays per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -222,6 +224,44 @@ def roofline_grid_encode(dev, precision):
                 points=B, bytes_per_point=per_pt, launch_ms=t * 1e3)
 
 
+# algorithmic bytes per sample of the step's kernels (DESIGN.md "Kernels"): what one launch must move
+ALGO_BYTES = {
+    # xyz 12 + 16 levels x 8 corners x 8 B (both fp16 tables, interleaved) + 128 B feature row
+    "s3d_ngp_encode": ("k_ngp_encode", 12 + 16 * 8 * 8 + 128),
+    # xyz 12 + 128 B dfeats row + 16 x 8 corners x 16 B fp32 gradient entries (read-modify-write counted once)
+    "s3d_ngp_scatter": ("k_ngp_scatter", 12 + 128 + 16 * 8 * 16),
+    # feature row 128 + dirs 12 + sigma 4 + rgb 12
+    "s3d_ngp_mlp_forward": ("k_ngp_mlp_fwd", 128 + 12 + 16),
+    # feature row 128 + dirs 12 + g_sigma 4 + g_rgb 12 + dfeats 128
+    "s3d_ngp_mlp_backward": ("k_ngp_mlp_bwd", 128 + 12 + 16 + 128),
+    "s3d_grid_encode_forward": ("k_grid_forward", 12 + 16 * 8 * 4 + 64),       # one fp16 table
+    "s3d_grid_encode_backward": ("k_grid_backward", 12 + 16 * 8 * 4 + 64),
+}
+
+
+def step_roofline(breakdown, samples_per_step, step_ms):
+    """roofline of the step's dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events on the
+    launching stream, measured live above), against the measured HBM copy bandwidth"""
+    top = max(breakdown.items(), key=lambda kv: kv[1]["ms_per_step"])
+    name, st = top
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    out = {"kernel": ALGO_BYTES.get(name, (name, None))[0], "bound": "hbm", "peak": peak, "unit": "GB/s", "traffic": None,
+           "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
+           "launch_ms": st["ms_per_call"], "launches_per_step": st["calls_per_step"], "share_of_step": st["ms_per_step"] / step_ms}
+    if name in ALGO_BYTES:
+        per = ALGO_BYTES[name][1]
+        ach = samples_per_step * per / (st["ms_per_call"] * 1e-3) / 1e9
+        out.update(achieved=ach, frac=ach / peak, bytes_per_sample=per, samples_per_launch=samples_per_step)
+    else:
+        out.update(achieved=None, frac=None)
+    return out
+
+
 def gpu_arm(args):
     import torch
     from seal3d_b200 import synth, parallel, _lib
@@ -229,9 +269,13 @@ def gpu_arm(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     from seal3d_b200.trainer import DistillTrainer
+    from seal3d_b200.fused import FusedDistillTrainer
     teacher, student = build_world(dev, args.precision)
-    tr = DistillTrainer(student, teacher, lr=1e-2, precision=args.precision, loss_scale=(128.0 if args.precision == "fp16" else 1.0),
-                        world_size=world, update_interval=16)
+    if args.engine == "fused":
+        tr = FusedDistillTrainer(student, teacher, lr=1e-2, loss_scale=128.0, world_size=world, update_interval=16)
+    else:
+        tr = DistillTrainer(student, teacher, lr=1e-2, precision=args.precision, loss_scale=(128.0 if args.precision == "fp16" else 1.0),
+                            world_size=world, update_interval=16)
     n = args.rays
     pool = 4
     host = []
@@ -281,6 +325,23 @@ def gpu_arm(args):
     barrier()
     ms_e2e = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
 
+    # -- per-kernel breakdown of one step (events around every C-ABI launch; separate from the timed legs) -------
+    breakdown = None
+    if rank == 0 and not args.no_roofline:
+        _lib.PROFILE = []
+        torch.cuda.synchronize()
+        nprof = 3
+        for i in range(nprof):
+            o, d = resident[i % pool]
+            tr.distill_step(o, d, perturb=True)
+        torch.cuda.synchronize()
+        agg = {}
+        for name, a, b in _lib.PROFILE:
+            agg.setdefault(name, [0.0, 0])
+            agg[name][0] += a.elapsed_time(b)
+            agg[name][1] += 1
+        _lib.PROFILE = None
+        breakdown = {k: {"ms_per_step": v[0] / nprof, "calls_per_step": v[1] / nprof, "ms_per_call": v[0] / v[1]} for k, v in agg.items()}
     if rank != 0:
         return None
     rays_total = n * world * args.steps
@@ -296,6 +357,10 @@ def gpu_arm(args):
         "gpu_launches": int(getattr(_lib, "LAUNCHES", 0) - launches0) if hasattr(_lib, "LAUNCHES") else None,
         "clocks": clk, "loss_last": [float(v) for v in last.numpy()] if last is not None else None,
     }
+    line["config"]["engine"] = args.engine
+    if breakdown:
+        line["kernel_breakdown_ms_per_step"] = {k: round(v["ms_per_step"], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms_per_step"])}
+        line["roofline"] = step_roofline(breakdown, samples_per_step, ms / args.steps)
     return line
 
 
@@ -320,7 +385,10 @@ def main():
         return
     import torch
     if not args.no_roofline:
-        line["roofline"] = roofline_grid_encode(torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))), args.precision)
+        d0 = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        line["grid_encode_forward_roofline"] = {p: roofline_grid_encode(d0, p) for p in ("fp32", "fp16")}
+        if "roofline" not in line:
+            line["roofline"] = line["grid_encode_forward_roofline"][args.precision]
     if not args.no_cpu_baseline and line["n_gpus"] == 1:
         line["cpu_baseline"] = cpu_arm(args.cpu_rays, 2, 1)
     print(json.dumps(line))

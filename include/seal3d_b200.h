@@ -89,6 +89,9 @@ int s3d_grad_total_variation(const void *inputs, const void *embeddings, void *g
                              uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
                              int align_corners, int dtype, void *stream);
 
+/* diagnostic: scales[l] = exp2f(l*S)*H - 1 as evaluated on the device (gridencoder.cu:138), float[L] */
+int s3d_grid_level_scales(uint32_t L, float S, uint32_t H, float *scales, void *stream);
+
 /* ------------------------------------------------------------------ shencoder / freqencoder */
 /* shencoder/src/shencoder.h:9   sh_encode_forward(inputs[B,3], outputs[B,C*C], B, D=3, C=degree<=8, dy_dx[B,3*C*C]|NULL) */
 int s3d_sh_encode_forward(const float *inputs, float *outputs, uint32_t B, uint32_t D, uint32_t C, float *dy_dx,
@@ -162,6 +165,26 @@ int s3d_density_cells_to_xyz(const int *cell_morton, uint32_t n, uint32_t H, flo
 int s3d_density_scatter(const int *cell_morton, const float *sigma, uint32_t n, float density_scale, float *tmp_grid,
                         void *stream);
 int s3d_density_grid_ema(float *grid, const float *tmp_grid, uint32_t n, float decay, float *sum_out, void *stream);
+
+/* ------------------------------------------------------------------ fused NGP field (nerf/network.py:99-128) */
+/* The higher-level seam of SURVEY.md 8b: samples -> (sigma, rgb) and back, four kernels, one 128-byte fp16 row per
+ * sample between them.  table4 = both hash tables interleaved, fp16 [N] x {s0,s1,c0,c1}; grad4 = fp32, same layout. */
+int s3d_ngp_interleave_tables(const float *table_sigma, const float *table_color, void *table4, uint64_t n_entries, void *stream);
+int s3d_ngp_encode(const float *xyz, uint32_t M, float bound, const void *table4, const int *offsets, uint32_t L, float S, uint32_t H,
+                   void *feats, int sigma_only, void *stream);
+/* weights: fp16 row-major nn.Linear matrices sigma_net.0 [64,32], sigma_net.1 [16,64], color_net.0 [64,63], .1 [64,64], .2 [3,64];
+ * sigma = density_scale * exp(h[0]); geo [M,15] optional; rgb = sigmoid(...) */
+int s3d_ngp_mlp_forward(const void *feats, const float *dirs, uint32_t M, const void *w_s0, const void *w_s1, const void *w_c0,
+                        const void *w_c1, const void *w_c2, float density_scale, float *sigma, float *rgb, float *geo, int sigma_only,
+                        void *stream);
+/* dfeats [M,64] fp16 = out_scale * dL/dfeats; gw_* fp32 weight gradients (nn.Linear shapes), accumulated into */
+int s3d_ngp_mlp_backward(const void *feats, const float *dirs, uint32_t M, const void *w_s0, const void *w_s1, const void *w_c0,
+                         const void *w_c1, const void *w_c2, float density_scale, const float *g_sigma, const float *g_rgb, void *dfeats,
+                         float out_scale, float *gw_s0, float *gw_s1, float *gw_c0, float *gw_c1, float *gw_c2, int train_mlp, void *stream);
+int s3d_ngp_scatter(const float *xyz, const void *dfeats, uint32_t M, float bound, float *grad4, const int *offsets, uint32_t L, float S,
+                    uint32_t H, float grad_scale, void *stream);
+int s3d_ngp_adam_tables(float *table_sigma, float *table_color, float *grad4, float *exp_avg4, float *exp_avg_sq4, void *table4,
+                        uint64_t n_entries, float lr, float beta1, float beta2, float eps, uint32_t step, float grad_scale, void *stream);
 
 #ifdef __cplusplus
 }

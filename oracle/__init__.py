@@ -167,6 +167,22 @@ def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, we
 # ---------------------------------------------------------------- gridencoder
 
 
+class level_scales:
+    """with oracle.level_scales(float32[L]): ...  -- use the given per-level scales instead of libm's exp2f (see
+    seal_oracle.c: the one value of the path that differs between CUDA's and glibc's math library)"""
+
+    def __init__(self, scales):
+        self.s = None if scales is None else np.ascontiguousarray(scales, dtype=np.float32)
+
+    def __enter__(self):
+        lib().orc_set_level_scales(_p(self.s))
+        return self
+
+    def __exit__(self, *a):
+        lib().orc_set_level_scales(None)
+
+
+
 def grid_offsets(input_dim=3, num_levels=16, level_dim=2, per_level_scale=2.0, base_resolution=16,
                  log2_hashmap_size=19, desired_resolution=None, align_corners=False):
     """Level offsets exactly as gridencoder/grid.py:100-127 computes them.  Returns (offsets int32[L+1],

@@ -405,10 +405,17 @@ typedef struct {
     float scale;
 } level_info;
 
+/* Optional precomputed per-level scales.  exp2f is the one value of this path that is not reproducible across math
+ * libraries (CUDA's exp2f is not correctly rounded, glibc's is): a 1-ulp difference in exp2f(7) moves
+ * pos = x*scale+0.5 of the finest level by ~1e-4.  GPU parity tests therefore read the device's scales back
+ * (s3d_grid_level_scales) and install them here; everything else is restated independently. */
+static const float *volatile g_level_scales = NULL;
+ORC_API void orc_set_level_scales(const float *scales) { g_level_scales = scales; }
 static inline level_info level_setup(const int *offsets, uint32_t level, float S, uint32_t H) {
+    const float *ls = g_level_scales;
     level_info li;
     li.hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
-    li.scale = fmaf(exp2f((float)level * S), (float)H, -1.0f); /* gridencoder.cu:138 */
+    li.scale = ls ? ls[level] : fmaf(exp2f((float)level * S), (float)H, -1.0f); /* gridencoder.cu:138 */
     li.resolution = (uint32_t)ceilf(li.scale) + 1;              /* gridencoder.cu:139 */
     return li;
 }

@@ -31,6 +31,7 @@ _SIGS = {
     "s3d_grid_encode_forward": [P, P, P, P, U32, U32, U32, U32, F32, U32, P, U32, I32, U32, I32],
     "s3d_grid_encode_backward": [P, P, P, P, P, U32, U32, U32, U32, F32, U32, P, P, U32, I32, U32, I32],
     "s3d_grad_total_variation": [P, P, P, P, F32, U32, U32, U32, U32, F32, U32, U32, I32, I32],
+    "s3d_grid_level_scales": [U32, F32, U32, P],
     "s3d_sh_encode_forward": [P, P, U32, U32, U32, P],
     "s3d_sh_encode_backward": [P, P, U32, U32, U32, P, P],
     "s3d_freq_encode_forward": [P, U32, U32, U32, U32, P],
@@ -48,11 +49,18 @@ _SIGS = {
     "s3d_density_grid_ema": [P, P, U32, F32, P],
     "s3d_density_cells_to_xyz": [P, U32, U32, F32, U32, P],
     "s3d_density_scatter": [P, P, U32, F32, P],
+    "s3d_ngp_interleave_tables": [P, P, P, U64],
+    "s3d_ngp_encode": [P, U32, F32, P, P, U32, F32, U32, P, I32],
+    "s3d_ngp_mlp_forward": [P, P, U32, P, P, P, P, P, F32, P, P, P, I32],
+    "s3d_ngp_mlp_backward": [P, P, U32, P, P, P, P, P, F32, P, P, P, F32, P, P, P, P, P, I32],
+    "s3d_ngp_scatter": [P, P, U32, F32, P, P, U32, F32, U32, F32],
+    "s3d_ngp_adam_tables": [P, P, P, P, P, P, U64, F32, F32, F32, F32, U32, F32],
 }
 _NO_STREAM = {"s3d_allocate_splitk": [SZ], "s3d_free_splitk": []}
 
 _lib = None
 LAUNCHES = 0  # kernels launched through this binding (bench.py reports the per-run delta)
+PROFILE = None  # set to a list to record (name, start_event, end_event) per call (bench.py's per-kernel breakdown)
 _KERNELS_PER_CALL = {"s3d_march_rays_train": 3, "s3d_march_rays_train_count": 2, "s3d_ffmlp_backward": 2, "s3d_seal_map_color": 2}
 
 
@@ -109,7 +117,14 @@ def call(name, *args):
     f = getattr(lib(), name)
     LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
     stream = torch.cuda.current_stream().cuda_stream
-    rc = f(*[_conv(a) for a in args], stream)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = f(*[_conv(a) for a in args], stream)
+        e1.record()
+        PROFILE.append((name, e0, e1))
+    else:
+        rc = f(*[_conv(a) for a in args], stream)
     if rc != 0:
         if rc > 0:
             raise S3DError("%s: CUDA error %d (%s)" % (name, rc, _cuda_err(rc)))

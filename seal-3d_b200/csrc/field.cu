@@ -1,0 +1,779 @@
+// Fused NGP field for the distillation trainer (sm_100a): samples -> (sigma, rgb) and back.
+//
+// The reference evaluates nerf/network.py:99-128 as ~20 launches per call (2 grid encodes with a full
+// table cast + permute copies, SH, a concat, 5 cuBLAS GEMMs, ~8 elementwise kernels) and writes every
+// intermediate to HBM.  Here the field is four kernels with one 128-byte row per sample between them:
+//
+//   k_ngp_encode    xyz -> feats[M,64] fp16 = [sigma-grid 32 | colour-grid 32].  Both hash tables live in ONE
+//                   interleaved fp16 table (entry = {s0,s1,c0,c1}, 8 bytes): a corner costs one 64-bit load for
+//                   both encoders instead of two 32-bit loads from two tables (the cell geometry is shared).
+//   k_ngp_mlp_fwd   feats + dirs -> sigma, rgb.  All five GEMMs on tcgen05 (M=128 samples per tile, K=16 per MMA,
+//                   fp32 accumulators in TMEM), SH(4) evaluated in registers and written straight into the operand
+//                   tile; activations never leave the SM.  The colour layer reads its 63-wide input from two
+//                   tiles through per-MMA descriptors ([colour feats] from the feature tile, [SH | geo] from the
+//                   scratch tile), so nothing is concatenated.
+//   k_ngp_mlp_bwd   recomputes the forward from feats (cheaper than storing 3x64 activations per sample), then
+//                   data gradients (weights read MN-major = transposed for free) and weight gradients (both
+//                   operands MN-major, K = the 128 samples of the tile) as tcgen05 MMAs; weight gradients
+//                   accumulate in TMEM across all tiles of the persistent CTA and are flushed once.
+//   k_ngp_scatter   xyz + dfeats -> interleaved fp32 gradient table with the in-warp segmented pre-reduction
+//                   (ray-major samples share cells at coarse levels) and one 128-bit RED per corner.
+//
+// Level geometry follows gridencoder.cu:137-156 of the reference (D=3, linear interpolation,
+// align_corners=false); MLP semantics follow nerf/network.py:99-128 and activation.py:5-17.
+#include "tc05.cuh"
+
+namespace {
+
+using namespace tc05;
+
+constexpr uint32_t kMaxLevels = 16;
+constexpr uint32_t kRows = 128;
+constexpr uint32_t kTileBytes = kRows * 128;  // [128 x 64] fp16
+constexpr uint32_t kWTile = 64 * 128;         // [64 x 64] fp16
+constexpr uint32_t kOTile = 16 * 128;         // [16 x 64] fp16
+
+struct Geo {
+    float scale[kMaxLevels];
+    uint32_t res1[kMaxLevels];    // resolution + 1 (dense stride)
+    uint32_t size[kMaxLevels];    // hashmap_size
+    uint32_t offset[kMaxLevels];  // first entry of the level
+    uint32_t hashed;              // bit l: level l uses the xor-prime hash
+    uint32_t pow2;                // bit l: size is a power of two
+};
+
+__device__ void geo_init(Geo &g, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H) {
+    const uint32_t l = threadIdx.x;
+    if (l == 0) { g.hashed = 0; g.pow2 = 0; }
+    __syncthreads();
+    if (l < L) {
+        const uint32_t size = (uint32_t)(offsets[l + 1] - offsets[l]);
+        const float scale = __fmaf_rn(exp2f((float)l * S), (float)H, -1.0f);
+        const uint32_t res1 = (uint32_t)ceilf(scale) + 2;  // resolution + 1
+        g.scale[l] = scale; g.res1[l] = res1; g.size[l] = size; g.offset[l] = (uint32_t)offsets[l];
+        uint32_t stride = 1;
+#pragma unroll
+        for (int d = 0; d < 3; d++) if (stride <= size) stride *= res1;
+        if (stride > size) atomicOr(&g.hashed, 1u << l);
+        if ((size & (size - 1)) == 0) atomicOr(&g.pow2, 1u << l);
+    }
+    __syncthreads();
+}
+
+struct Cell {
+    uint32_t idx[8];
+    float w[8];
+};
+
+// corner indices (entry units, level offset included) and trilinear weights of u in level l
+__device__ __forceinline__ void locate(const Geo &g, uint32_t l, float ux, float uy, float uz, Cell &c, unsigned long long *key) {
+    const float s = g.scale[l];
+    const float px = __fmaf_rn(ux, s, 0.5f), py = __fmaf_rn(uy, s, 0.5f), pz = __fmaf_rn(uz, s, 0.5f);
+    const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
+    const uint32_t gx = (uint32_t)fx0, gy = (uint32_t)fy0, gz = (uint32_t)fz0;
+    const float fx = __fsub_rn(px, fx0), fy = __fsub_rn(py, fy0), fz = __fsub_rn(pz, fz0);
+    if (key) *key = (unsigned long long)gx | ((unsigned long long)gy << 21) | ((unsigned long long)gz << 42);
+    const uint32_t size = g.size[l], off = g.offset[l];
+    const bool hashed = (g.hashed >> l) & 1u, p2 = (g.pow2 >> l) & 1u;
+    const uint32_t r1 = g.res1[l];
+#pragma unroll
+    for (uint32_t i = 0; i < 8; i++) {
+        const uint32_t x = gx + (i & 1u), y = gy + ((i >> 1) & 1u), z = gz + (i >> 2);
+        uint32_t id;
+        if (hashed) {
+            id = x ^ (y * 2654435761u) ^ (z * 805459861u);
+            id = p2 ? (id & (size - 1)) : (id % size);
+        } else {
+            id = x + y * r1;
+            if (r1 * r1 <= size) id += z * r1 * r1;   // get_grid_index stops adding once the stride exceeds the table
+            id = id % size;
+        }
+        c.idx[i] = off + id;
+        // same product order as the reference: ((1 * wx) * wy) * wz
+        float w = (i & 1u) ? fx : __fsub_rn(1.0f, fx);
+        w = __fmul_rn(w, ((i >> 1) & 1u) ? fy : __fsub_rn(1.0f, fy));
+        w = __fmul_rn(w, (i >> 2) ? fz : __fsub_rn(1.0f, fz));
+        c.w[i] = w;
+    }
+}
+
+__device__ __forceinline__ bool to_unit(float x, float y, float z, float bound, float &ux, float &uy, float &uz) {
+    const float inv = 2.0f * bound;  // GridEncoder.forward: (inputs + bound) / (2 * bound)
+    ux = __fdiv_rn(__fadd_rn(x, bound), inv); uy = __fdiv_rn(__fadd_rn(y, bound), inv); uz = __fdiv_rn(__fadd_rn(z, bound), inv);
+    return !(ux < 0.0f || ux > 1.0f || uy < 0.0f || uy > 1.0f || uz < 0.0f || uz > 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// encode: one thread per sample, both tables, all levels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_ngp_encode(const float *__restrict__ xyz, uint32_t M, float bound, const uint2 *__restrict__ table4,
+             const int *__restrict__ offsets, uint32_t L, float S, uint32_t H, __half *__restrict__ feats, int sigma_only) {
+    __shared__ Geo g;
+    geo_init(g, offsets, L, S, H);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    float ux, uy, uz;
+    const bool ok = to_unit(xyz[(size_t)i * 3], xyz[(size_t)i * 3 + 1], xyz[(size_t)i * 3 + 2], bound, ux, uy, uz);
+    uint4 *row = reinterpret_cast<uint4 *>(feats + (size_t)i * 64);
+    for (uint32_t grp = 0; grp < 4; grp++) {      // 4 levels -> one 16-byte chunk per table
+        float fs[8], fc[8];
+#pragma unroll
+        for (uint32_t q = 0; q < 4; q++) {
+            const uint32_t l = grp * 4 + q;
+            float s0 = 0.f, s1 = 0.f, c0 = 0.f, c1 = 0.f;
+            if (ok && l < L) {
+                Cell c;
+                locate(g, l, ux, uy, uz, c, nullptr);
+                uint2 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = __ldg(table4 + c.idx[k]);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&v[k].x));
+                    const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&v[k].y));
+                    s0 = __fmaf_rn(c.w[k], a.x, s0); s1 = __fmaf_rn(c.w[k], a.y, s1);
+                    c0 = __fmaf_rn(c.w[k], b.x, c0); c1 = __fmaf_rn(c.w[k], b.y, c1);
+                }
+            }
+            fs[q * 2] = s0; fs[q * 2 + 1] = s1; fc[q * 2] = c0; fc[q * 2 + 1] = c1;
+        }
+        row[grp] = pack8(fs);
+        if (!sigma_only) row[4 + grp] = pack8(fc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scatter: dfeats -> interleaved fp32 gradient table
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, uint32_t M, float bound,
+              float4 *__restrict__ grad4, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H, float grad_scale) {
+    __shared__ Geo g;
+    geo_init(g, offsets, L, S, H);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // whole warps stay alive
+    float ux = 0, uy = 0, uz = 0;
+    bool ok = false;
+    if (i < M) ok = to_unit(xyz[(size_t)i * 3], xyz[(size_t)i * 3 + 1], xyz[(size_t)i * 3 + 2], bound, ux, uy, uz);
+    const uint32_t lane = lane_id();
+    const uint4 *row = reinterpret_cast<const uint4 *>(dfeats + (size_t)(i < M ? i : 0) * 64);
+    for (uint32_t grp = 0; grp < 4; grp++) {
+        float ds[8], dc[8];
+        if (ok) { unpack8(__ldg(row + grp), ds); unpack8(__ldg(row + 4 + grp), dc); }
+        else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) { ds[k] = 0.f; dc[k] = 0.f; }
+        }
+#pragma unroll
+        for (uint32_t q = 0; q < 4; q++) {
+            const uint32_t l = grp * 4 + q;
+            if (l >= L) break;
+            Cell c;
+            unsigned long long key = ~0ull;
+            if (ok) locate(g, l, ux, uy, uz, c, &key);
+            else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) { c.idx[k] = 0; c.w[k] = 0.f; }
+            }
+            const float g0 = ds[q * 2] * grad_scale, g1 = ds[q * 2 + 1] * grad_scale, g2 = dc[q * 2] * grad_scale, g3 = dc[q * 2 + 1] * grad_scale;
+            const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+            const bool head = (lane == 0) || (prev != key);
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+            if (__popc(heads) <= 16) {
+                // runs of equal cells: fold every run into its head lane (segmented suffix sums), then one RED per corner
+                const uint32_t after = heads >> 1 >> lane;
+                const uint32_t seg_left = after ? (uint32_t)(__ffs(after) - 1) : (31u - lane);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    float a0 = c.w[k] * g0, a1 = c.w[k] * g1, a2 = c.w[k] * g2, a3 = c.w[k] * g3;
+#pragma unroll
+                    for (uint32_t d = 1; d < 32; d <<= 1) {
+                        const float o0 = __shfl_down_sync(0xffffffffu, a0, d), o1 = __shfl_down_sync(0xffffffffu, a1, d);
+                        const float o2 = __shfl_down_sync(0xffffffffu, a2, d), o3 = __shfl_down_sync(0xffffffffu, a3, d);
+                        if (d <= seg_left) { a0 += o0; a1 += o1; a2 += o2; a3 += o3; }
+                    }
+                    if (ok && head) atomicAdd(grad4 + c.idx[k], make_float4(a0, a1, a2, a3));
+                }
+            } else if (ok) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) atomicAdd(grad4 + c.idx[k], make_float4(c.w[k] * g0, c.w[k] * g1, c.w[k] * g2, c.w[k] * g3));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MLP: shared pieces
+// ------------------------------------------------------------------------------------------------
+struct MlpWeights {
+    const __half *ws0, *ws1, *wc0, *wc1, *wc2;  // row-major [64,32] [16,64] [64,63] [64,64] [3,64] (nn.Linear layout)
+};
+
+// weight tiles in shared memory (SW128, K = 64 columns):
+//   Ws0 [64 x 64]  cols 0-31 = W_s0, cols 32-63 = 0
+//   Ws1 [16 x 64]
+//   Wc0 [64 x 64]  cols 0-31 = colour-grid inputs (orig 31..62), 32-47 = SH (orig 0..15), 48-62 = geo (orig 16..30), 63 = 0
+//   Wc1 [64 x 64]
+//   Wc2 [16 x 64]  rows 0-2 = W_c2, rows 3-15 = 0
+__device__ void load_weights(uint8_t *tWs0, uint8_t *tWs1, uint8_t *tWc0, uint8_t *tWc1, uint8_t *tWc2, const MlpWeights &w) {
+    const __half zero = __float2half_rn(0.0f);
+    for (uint32_t i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+        const uint32_t r = i >> 6, c = i & 63;
+        const uint32_t off = sw128_off(r, c >> 3) + (c & 7) * 2;
+        *reinterpret_cast<__half *>(tWs0 + off) = c < 32 ? w.ws0[r * 32 + c] : zero;
+        const uint32_t oc = c < 32 ? 31 + c : (c < 48 ? c - 32 : (c < 63 ? c - 48 + 16 : 0xffffffffu));
+        *reinterpret_cast<__half *>(tWc0 + off) = oc != 0xffffffffu ? w.wc0[r * 63 + oc] : zero;
+        *reinterpret_cast<__half *>(tWc1 + off) = w.wc1[r * 64 + c];
+        if (r < 16) {
+            *reinterpret_cast<__half *>(tWs1 + off) = w.ws1[r * 64 + c];
+            *reinterpret_cast<__half *>(tWc2 + off) = r < 3 ? w.wc2[r * 64 + c] : zero;
+        }
+    }
+}
+
+// real SH, degree 4 (16 values), same polynomials as shencoder.cu:49-68 of the reference, written through the
+// (x + iy)^m factorisation: Y = N * Q_l^m(z) * {c_m | s_m}(x, y)
+__device__ __forceinline__ void sh4(float x, float y, float z, float *o) {
+    const float z2 = z * z;
+    const float c1 = x, s1 = y;
+    const float c2 = x * x - y * y, s2 = 2.0f * x * y;
+    const float c3 = x * c2 - y * s2, s3 = x * s2 + y * c2;
+    o[0] = 0.28209479177387814f;
+    o[1] = -0.48860251190291992f * s1;
+    o[2] = 0.48860251190291992f * z;
+    o[3] = -0.48860251190291992f * c1;
+    o[4] = 0.54627421529603959f * s2;
+    o[5] = -1.0925484305920792f * z * s1;
+    o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+    o[7] = -1.0925484305920792f * z * c1;
+    o[8] = 0.54627421529603959f * c2;
+    o[9] = -0.59004358992664352f * s3;
+    o[10] = 1.4453057213202769f * z * s2;
+    o[11] = 0.45704579946446572f * (1.0f - 5.0f * z2) * s1;
+    o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+    o[13] = 0.45704579946446572f * (1.0f - 5.0f * z2) * c1;
+    o[14] = 1.4453057213202769f * z * c2;
+    o[15] = -0.59004358992664352f * c3;
+}
+
+__device__ __forceinline__ void load_feat_row(uint8_t *tile, const __half *__restrict__ feats, uint32_t row_g, uint32_t r, bool in_range) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(feats + (size_t)row_g * 64);
+#pragma unroll
+    for (uint32_t c16 = 0; c16 < 8; c16++) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (in_range) v = __ldg(src + c16);
+        *reinterpret_cast<uint4 *>(tile + sw128_off(r, c16)) = v;
+    }
+}
+
+__device__ __forceinline__ void sync_tiles() {  // writers -> tensor core, tensor core results -> readers
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+}
+
+struct Issue {
+    uint32_t mbar, parity;
+    __device__ __forceinline__ void commit_and_wait(bool issuer) {
+        if (issuer) mma_commit(mbar);
+        mbar_wait(mbar, parity);
+        parity ^= 1;
+        fence_after_sync();
+    }
+};
+
+// write 32 fp32 values (one half of a 64-wide row) as fp16 into chunks [4*half, 4*half+4) of row r
+__device__ __forceinline__ void store_half_row(uint8_t *tile, uint32_t r, uint32_t half, const float *v) {
+#pragma unroll
+    for (uint32_t q = 0; q < 4; q++) *reinterpret_cast<uint4 *>(tile + sw128_off(r, half * 4 + q)) = pack8(v + q * 8);
+}
+
+// ------------------------------------------------------------------------------------------------
+// MLP forward
+// ------------------------------------------------------------------------------------------------
+struct FwdArgs {
+    const __half *feats;
+    const float *dirs;
+    MlpWeights w;
+    float *sigma, *rgb, *geo;  // geo [M,15] optional (density() callers)
+    uint32_t M, n_tiles;
+    float density_scale;
+    int sigma_only;
+};
+
+__global__ void __launch_bounds__(128)
+k_ngp_mlp_fwd(const FwdArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ uint32_t s_tmem;
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *tF = smem, *tT = tF + kTileBytes, *tWs0 = tT + kTileBytes, *tWc0 = tWs0 + kWTile, *tWc1 = tWc0 + kWTile,
+            *tWs1 = tWc1 + kWTile, *tWc2 = tWs1 + kOTile;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 64);
+    if (tid == 0) mbar_init(smem_u32(&s_mbar), 1);
+    load_weights(tWs0, tWs1, tWc0, tWc1, tWc2, a.w);
+    sync_tiles();
+    const uint32_t tmem = s_tmem, t_row = tmem + ((warp * 32u) << 16);
+    Issue is{smem_u32(&s_mbar), 0};
+    const bool issuer = (tid == 0);
+    const uint32_t aF = smem_u32(tF), aT = smem_u32(tT);
+    const uint32_t id64 = make_idesc(128, 64, false, false), id16 = make_idesc(128, 16, false, false);
+
+    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const uint32_t row = tile * kRows + tid;
+        const bool in_range = row < a.M;
+        load_feat_row(tF, a.feats, row, tid, in_range);
+        sync_tiles();
+        // sigma layer 0: [128 x 32] . W_s0^T  (2 K-steps over the sigma features)
+        if (issuer) { for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, k), desc_kmajor(smem_u32(tWs0), k), id64, k > 0); }
+        is.commit_and_wait(issuer);
+#pragma unroll
+        for (uint32_t h = 0; h < 2; h++) {
+            float v[32];
+            tmem_ld32(t_row + h * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.0f);
+            store_half_row(tT, tid, h, v);
+        }
+        sync_tiles();
+        // sigma layer 1: [128 x 64] . W_s1^T -> 16
+        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(smem_u32(tWs1), k), id16, k > 0); }
+        is.commit_and_wait(issuer);
+        float h2[16];
+        tmem_ld16(t_row, h2);
+        if (in_range) {
+            a.sigma[row] = a.density_scale * __expf(h2[0]);
+            if (a.geo) for (int i = 0; i < 15; i++) a.geo[(size_t)row * 15 + i] = h2[1 + i];
+        }
+        if (a.sigma_only) { fence_before_sync(); __syncthreads(); fence_after_sync(); continue; }
+        // colour input, second half: [SH16 | geo15 | 0] -> columns 0..31 of the scratch tile
+        {
+            float g[32];
+            float dx = 0.f, dy = 0.f, dz = 0.f;
+            if (in_range) { dx = a.dirs[(size_t)row * 3]; dy = a.dirs[(size_t)row * 3 + 1]; dz = a.dirs[(size_t)row * 3 + 2]; }
+            sh4(dx, dy, dz, g);
+#pragma unroll
+            for (int i = 0; i < 15; i++) g[16 + i] = h2[1 + i];
+            g[31] = 0.0f;
+            store_half_row(tT, tid, 0, g);
+        }
+        sync_tiles();
+        // colour layer 0: K-steps 0,1 = colour-grid feats (feature tile cols 32..63), K-steps 2,3 = [SH | geo] (scratch cols 0..31)
+        if (issuer) {
+            for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, 2 + k), desc_kmajor(smem_u32(tWc0), k), id64, k > 0);
+            for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(smem_u32(tWc0), 2 + k), id64, true);
+        }
+        is.commit_and_wait(issuer);
+#pragma unroll
+        for (uint32_t h = 0; h < 2; h++) {
+            float v[32];
+            tmem_ld32(t_row + h * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.0f);
+            store_half_row(tT, tid, h, v);
+        }
+        sync_tiles();
+        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(smem_u32(tWc1), k), id64, k > 0); }
+        is.commit_and_wait(issuer);
+#pragma unroll
+        for (uint32_t h = 0; h < 2; h++) {
+            float v[32];
+            tmem_ld32(t_row + h * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.0f);
+            store_half_row(tT, tid, h, v);
+        }
+        sync_tiles();
+        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(smem_u32(tWc2), k), id16, k > 0); }
+        is.commit_and_wait(issuer);
+        float o[16];
+        tmem_ld16(t_row, o);
+        if (in_range) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) a.rgb[(size_t)row * 3 + c] = 1.0f / (1.0f + __expf(-o[c]));
+        }
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+    }
+    if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
+// ------------------------------------------------------------------------------------------------
+// MLP backward (persistent, 1 CTA / SM)
+// ------------------------------------------------------------------------------------------------
+struct BwdArgs {
+    const __half *feats;
+    const float *dirs;
+    MlpWeights w;
+    const float *g_sigma, *g_rgb;   // dL/dsigma [M] (w.r.t. density_scale * exp(h0)), dL/drgb [M,3]
+    __half *dfeats;                 // [M,64]
+    float *gw_s0, *gw_s1, *gw_c0, *gw_c1, *gw_c2;  // fp32, nn.Linear shapes, accumulated into (atomics)
+    uint32_t M, n_tiles;
+    float density_scale, out_scale;  // out_scale multiplies dfeats (keeps fp16 gradients in range)
+    int train_mlp;
+};
+
+// TMEM columns: [0,64) activation accumulator | [64,128) dWc2 | [128,192) dWc1 | [192,256) dC1^T.F | [256,320) dC1^T.G | [320,384) dWs1 |
+// [384,448) dH1^T.F.  Every weight-gradient MMA is a full 64 x 64 (M = 64, N = 64) block; the flush picks the valid columns.
+__global__ void __launch_bounds__(128)
+k_ngp_mlp_bwd(const BwdArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ uint32_t s_tmem;
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *tF = smem, *tH1 = tF + kTileBytes, *tG = tH1 + kTileBytes, *tC1 = tG + kTileBytes, *tC2 = tC1 + kTileBytes,
+            *tX = tC2 + kTileBytes, *tY = tX + kTileBytes, *tWs0 = tY + kTileBytes, *tWc0 = tWs0 + kWTile, *tWc1 = tWc0 + kWTile,
+            *tWs1 = tWc1 + kWTile, *tWc2 = tWs1 + kOTile;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
+    if (tid == 0) mbar_init(smem_u32(&s_mbar), 1);
+    load_weights(tWs0, tWs1, tWc0, tWc1, tWc2, a.w);
+    sync_tiles();
+    const uint32_t tmem = s_tmem, t_row = tmem + ((warp * 32u) << 16);
+    Issue is{smem_u32(&s_mbar), 0};
+    const bool issuer = (tid == 0);
+    const uint32_t aF = smem_u32(tF), aH1 = smem_u32(tH1), aG = smem_u32(tG), aC1 = smem_u32(tC1), aC2 = smem_u32(tC2), aX = smem_u32(tX), aY = smem_u32(tY);
+    const uint32_t id64 = make_idesc(128, 64, false, false), id16 = make_idesc(128, 16, false, false);
+    const uint32_t id64t = make_idesc(128, 64, false, true);        // B read MN-major (= W^T)
+    const uint32_t idw64 = make_idesc(64, 64, true, true);
+    const uint32_t accC2 = tmem + 64, accC1 = tmem + 128, accC0f = tmem + 192, accC0g = tmem + 256, accS1 = tmem + 320, accS0 = tmem + 384;
+    bool first = true;
+
+    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, first = false) {
+        const uint32_t row = tile * kRows + tid;
+        const bool in_range = row < a.M;
+        // ---------------- recompute the forward, keeping every activation tile ----------------
+        load_feat_row(tF, a.feats, row, tid, in_range);
+        sync_tiles();
+        if (issuer) { for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, k), desc_kmajor(smem_u32(tWs0), k), id64, k > 0); }
+        is.commit_and_wait(issuer);
+#pragma unroll
+        for (uint32_t h = 0; h < 2; h++) {
+            float v[32];
+            tmem_ld32(t_row + h * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.0f);
+            store_half_row(tH1, tid, h, v);
+        }
+        sync_tiles();
+        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aH1, k), desc_kmajor(smem_u32(tWs1), k), id16, k > 0); }
+        is.commit_and_wait(issuer);
+        float h2[16];
+        tmem_ld16(t_row, h2);
+        {
+            float g[32];
+            float dx = 0.f, dy = 0.f, dz = 0.f;
+            if (in_range) { dx = a.dirs[(size_t)row * 3]; dy = a.dirs[(size_t)row * 3 + 1]; dz = a.dirs[(size_t)row * 3 + 2]; }
+            sh4(dx, dy, dz, g);
+#pragma unroll
+            for (int i = 0; i < 15; i++) g[16 + i] = h2[1 + i];
+            g[31] = 0.0f;
+            store_half_row(tG, tid, 0, g);
+            float z[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) z[i] = 0.0f;
+            store_half_row(tG, tid, 1, z);
+        }
+        sync_tiles();
+        if (issuer) {
+            for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, 2 + k), desc_kmajor(smem_u32(tWc0), k), id64, k > 0);
+            for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aG, k), desc_kmajor(smem_u32(tWc0), 2 + k), id64, true);
+        }
+        is.commit_and_wait(issuer);
+#pragma unroll
+        for (uint32_t h = 0; h < 2; h++) {
+            float v[32];
+            tmem_ld32(t_row + h * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.0f);
+            store_half_row(tC1, tid, h, v);
+        }
+        sync_tiles();
+        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aC1, k), desc_kmajor(smem_u32(tWc1), k), id64, k > 0); }
+        is.commit_and_wait(issuer);
+#pragma unroll
+        for (uint32_t h = 0; h < 2; h++) {
+            float v[32];
+            tmem_ld32(t_row + h * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.0f);
+            store_half_row(tC2, tid, h, v);
+        }
+        sync_tiles();
+        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aC2, k), desc_kmajor(smem_u32(tWc2), k), id16, k > 0); }
+        is.commit_and_wait(issuer);
+        // ---------------- output gradients -> tX (16 meaningful columns, zero padded) ----------------
+        {
+            float o[16], d[32];
+            tmem_ld16(t_row, o);
+#pragma unroll
+            for (int i = 0; i < 32; i++) d[i] = 0.0f;
+            if (in_range) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float s = 1.0f / (1.0f + __expf(-o[c]));
+                    d[c] = a.g_rgb[(size_t)row * 3 + c] * s * (1.0f - s);
+                }
+            }
+            store_half_row(tX, tid, 0, d);
+#pragma unroll
+            for (int i = 0; i < 3; i++) d[i] = 0.0f;
+            store_half_row(tX, tid, 1, d);
+        }
+        sync_tiles();
+        // dWc2 += dO^T . C2 ; dC2 = dO . Wc2
+        if (issuer) {
+            if (a.train_mlp) for (uint32_t k = 0; k < 8; k++) mma_f16(accC2, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aC2, k, kTileBytes), idw64, !(first && k == 0));
+            mma_f16(tmem, desc_kmajor(aX, 0), desc_mnmajor(smem_u32(tWc2), 0, kOTile), id64t, false);
+        }
+        is.commit_and_wait(issuer);
+#pragma unroll
+        for (uint32_t h = 0; h < 2; h++) {
+            float v[32];
+            tmem_ld32(t_row + h * 32, v);
+#pragma unroll
+            for (uint32_t q = 0; q < 4; q++) {
+                float act[8];
+                unpack8(*reinterpret_cast<const uint4 *>(tC2 + sw128_off(tid, h * 4 + q)), act);
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[q * 8 + i] = act[i] > 0.0f ? v[q * 8 + i] : 0.0f;
+            }
+            store_half_row(tY, tid, h, v);
+        }
+        sync_tiles();
+        // dWc1 += dC2^T . C1 ; dC1 = dC2 . Wc1
+        if (issuer) {
+            if (a.train_mlp) for (uint32_t k = 0; k < 8; k++) mma_f16(accC1, desc_mnmajor(aY, k, kTileBytes), desc_mnmajor(aC1, k, kTileBytes), idw64, !(first && k == 0));
+            for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aY, k), desc_mnmajor(smem_u32(tWc1), k, kWTile), id64t, k > 0);
+        }
+        is.commit_and_wait(issuer);
+#pragma unroll
+        for (uint32_t h = 0; h < 2; h++) {
+            float v[32];
+            tmem_ld32(t_row + h * 32, v);
+#pragma unroll
+            for (uint32_t q = 0; q < 4; q++) {
+                float act[8];
+                unpack8(*reinterpret_cast<const uint4 *>(tC1 + sw128_off(tid, h * 4 + q)), act);
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[q * 8 + i] = act[i] > 0.0f ? v[q * 8 + i] : 0.0f;
+            }
+            store_half_row(tX, tid, h, v);
+        }
+        sync_tiles();
+        // dWc0 += dC1^T . [colour feats | SH,geo] ; d[colour feats | SH | geo] = dC1 . Wc0p
+        if (issuer) {
+            if (a.train_mlp) {
+                for (uint32_t k = 0; k < 8; k++) mma_f16(accC0f, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aF, k, kTileBytes), idw64, !(first && k == 0));
+                for (uint32_t k = 0; k < 8; k++) mma_f16(accC0g, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aG, k, kTileBytes), idw64, !(first && k == 0));
+            }
+            for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aX, k), desc_mnmajor(smem_u32(tWc0), k, kWTile), id64t, k > 0);
+        }
+        is.commit_and_wait(issuer);
+        float dfc[32];   // gradient w.r.t. the colour-grid features (dfeats cols 32..63)
+        tmem_ld32(t_row, dfc);
+        {
+            float v[32], d[32];
+            tmem_ld32(t_row + 32, v);  // cols 32-47 dSH (dropped), 48-62 dgeo
+#pragma unroll
+            for (int i = 0; i < 32; i++) d[i] = 0.0f;
+            float gs = 0.0f;
+            if (in_range) gs = a.g_sigma[row] * a.density_scale * __expf(fminf(fmaxf(h2[0], -15.0f), 15.0f));  // trunc_exp backward
+            d[0] = gs;
+#pragma unroll
+            for (int i = 0; i < 15; i++) d[1 + i] = v[16 + i];
+            store_half_row(tY, tid, 0, d);
+#pragma unroll
+            for (int i = 0; i < 16; i++) d[i] = 0.0f;
+            store_half_row(tY, tid, 1, d);
+        }
+        sync_tiles();
+        // dWs1 += dh2^T . H1 ; dH1 = dh2 . Ws1
+        if (issuer) {
+            if (a.train_mlp) for (uint32_t k = 0; k < 8; k++) mma_f16(accS1, desc_mnmajor(aY, k, kTileBytes), desc_mnmajor(aH1, k, kTileBytes), idw64, !(first && k == 0));
+            mma_f16(tmem, desc_kmajor(aY, 0), desc_mnmajor(smem_u32(tWs1), 0, kOTile), id64t, false);
+        }
+        is.commit_and_wait(issuer);
+#pragma unroll
+        for (uint32_t h = 0; h < 2; h++) {
+            float v[32];
+            tmem_ld32(t_row + h * 32, v);
+#pragma unroll
+            for (uint32_t q = 0; q < 4; q++) {
+                float act[8];
+                unpack8(*reinterpret_cast<const uint4 *>(tH1 + sw128_off(tid, h * 4 + q)), act);
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[q * 8 + i] = act[i] > 0.0f ? v[q * 8 + i] : 0.0f;
+            }
+            store_half_row(tX, tid, h, v);
+        }
+        sync_tiles();
+        // dWs0 += dH1^T . sigma feats ; d(sigma feats) = dH1 . Ws0p
+        if (issuer) {
+            if (a.train_mlp) for (uint32_t k = 0; k < 8; k++) mma_f16(accS0, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aF, k, kTileBytes), idw64, !(first && k == 0));
+            for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aX, k), desc_mnmajor(smem_u32(tWs0), k, kWTile), id64t, k > 0);
+        }
+        is.commit_and_wait(issuer);
+        {
+            float dfs[32];
+            tmem_ld32(t_row, dfs);
+            if (in_range) {
+                uint4 *dst = reinterpret_cast<uint4 *>(a.dfeats + (size_t)row * 64);
+#pragma unroll
+                for (int i = 0; i < 32; i++) { dfs[i] *= a.out_scale; dfc[i] *= a.out_scale; }
+#pragma unroll
+                for (uint32_t q = 0; q < 4; q++) { dst[q] = pack8(dfs + q * 8); dst[4 + q] = pack8(dfc + q * 8); }
+            }
+        }
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+    }
+
+    // ---- flush weight gradients: accumulator rows (M = 64) live in lanes 0..15 of every 32-lane sub-partition ----
+    if (a.train_mlp && !first) {
+        const uint32_t lane = tid & 31, r = warp * 16 + lane;   // output feature
+        const bool rowok = lane < 16;
+        for (uint32_t half = 0; half < 2; half++) {
+            float v[32];
+            tmem_ld32(t_row + 64 + half * 32, v);   // dWc2 [3 x 64]
+            if (rowok && r < 3) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c2 + r * 64 + half * 32 + i, v[i]);
+            tmem_ld32(t_row + 128 + half * 32, v);  // dWc1 [64 x 64]
+            if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c1 + r * 64 + half * 32 + i, v[i]);
+            tmem_ld32(t_row + 320 + half * 32, v);  // dWs1 [16 x 64]
+            if (rowok && r < 16) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s1 + r * 64 + half * 32 + i, v[i]);
+        }
+        float v[32];
+        tmem_ld32(t_row + 192 + 32, v);             // dC1^T . F, columns 32..63 = colour-grid inputs = original columns 31..62
+        if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c0 + r * 63 + 31 + i, v[i]);
+        tmem_ld32(t_row + 256, v);                  // dC1^T . G, columns 0..30 = [SH | geo] = original columns 0..30
+        if (rowok) for (int i = 0; i < 31; i++) atomicAdd(a.gw_c0 + r * 63 + i, v[i]);
+        tmem_ld32(t_row + 384, v);                  // dH1^T . F, columns 0..31 = sigma-grid inputs
+        if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s0 + r * 32 + i, v[i]);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// interleave two [N,2] fp32 tables into one [N,4] fp16 table {s0,s1,c0,c1}
+__global__ void k_interleave_tables(const float2 *__restrict__ ts, const float2 *__restrict__ tc, uint2 *__restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float2 s = ts[i], c = tc[i];
+    __half2 a = __floats2half2_rn(s.x, s.y), b = __floats2half2_rn(c.x, c.y);
+    out[i] = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+}
+
+// Adam over the two hash tables with an interleaved gradient / shadow layout
+__global__ void __launch_bounds__(256)
+k_adam_tables(float2 *__restrict__ ps, float2 *__restrict__ pc, float4 *__restrict__ g4, float4 *__restrict__ m4, float4 *__restrict__ v4,
+              uint2 *__restrict__ shadow4, size_t n, float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps, float gscale) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 g = g4[i];
+    g4[i] = make_float4(0, 0, 0, 0);
+    // dense Adam semantics: untouched entries still decay their moments and move with the stale momentum
+    float4 m = m4[i], v = v4[i];
+    float2 s = ps[i], c = pc[i];
+    float *G = &g.x, *Mv = &m.x, *V = &v.x;
+    float P[4] = {s.x, s.y, c.x, c.y};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float gr = G[k] * gscale;
+        Mv[k] = b1 * Mv[k] + (1.0f - b1) * gr;
+        V[k] = b2 * V[k] + (1.0f - b2) * gr * gr;
+        P[k] -= lr_over_bc1 * Mv[k] / (sqrtf(V[k]) * inv_sqrt_bc2 + eps);
+    }
+    m4[i] = m; v4[i] = v;
+    ps[i] = make_float2(P[0], P[1]); pc[i] = make_float2(P[2], P[3]);
+    __half2 a = __floats2half2_rn(P[0], P[1]), b = __floats2half2_rn(P[2], P[3]);
+    shadow4[i] = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+}
+
+size_t fwd_smem() { return 1024 + 2 * kTileBytes + 3 * kWTile + 2 * kOTile; }
+size_t bwd_smem() { return 1024 + 7 * kTileBytes + 3 * kWTile + 2 * kOTile; }
+
+int sm_count() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+}  // namespace
+
+// table4: interleaved fp16 table [N] x {s0,s1,c0,c1}; feats [M,64] fp16 (sigma feats 0..31, colour feats 32..63)
+S3D_API int s3d_ngp_encode(const float *xyz, uint32_t M, float bound, const void *table4, const int *offsets, uint32_t L, float S,
+                           uint32_t H, void *feats, int sigma_only, void *stream) {
+    if (M == 0) return 0;
+    if (L > kMaxLevels) return S3D_ENOTSUP;
+    k_ngp_encode<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, M, bound, (const uint2 *)table4, offsets, L, S, H, (__half *)feats, sigma_only);
+    S3D_RETURN_LAST();
+}
+
+// grad4: interleaved fp32 gradient table [N] x {s0,s1,c0,c1}, accumulated into
+S3D_API int s3d_ngp_scatter(const float *xyz, const void *dfeats, uint32_t M, float bound, float *grad4, const int *offsets, uint32_t L,
+                            float S, uint32_t H, float grad_scale, void *stream) {
+    if (M == 0) return 0;
+    if (L > kMaxLevels) return S3D_ENOTSUP;
+    k_ngp_scatter<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale);
+    S3D_RETURN_LAST();
+}
+
+// weights: fp16 row-major nn.Linear matrices sigma_net.0 [64,32], sigma_net.1 [16,64], color_net.0 [64,63], .1 [64,64], .2 [3,64]
+S3D_API int s3d_ngp_mlp_forward(const void *feats, const float *dirs, uint32_t M, const void *w_s0, const void *w_s1, const void *w_c0,
+                                const void *w_c1, const void *w_c2, float density_scale, float *sigma, float *rgb, float *geo,
+                                int sigma_only, void *stream) {
+    if (M == 0) return 0;
+    const size_t smem = fwd_smem();
+    cudaError_t e = cudaFuncSetAttribute(k_ngp_mlp_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    FwdArgs a;
+    a.feats = (const __half *)feats; a.dirs = dirs;
+    a.w = MlpWeights{(const __half *)w_s0, (const __half *)w_s1, (const __half *)w_c0, (const __half *)w_c1, (const __half *)w_c2};
+    a.sigma = sigma; a.rgb = rgb; a.geo = geo; a.M = M; a.n_tiles = div_up(M, kRows); a.density_scale = density_scale; a.sigma_only = sigma_only;
+    const uint32_t grid = min(a.n_tiles, (uint32_t)sm_count() * 3u);
+    k_ngp_mlp_fwd<<<grid, 128, smem, as_stream(stream)>>>(a);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_ngp_mlp_backward(const void *feats, const float *dirs, uint32_t M, const void *w_s0, const void *w_s1, const void *w_c0,
+                                 const void *w_c1, const void *w_c2, float density_scale, const float *g_sigma, const float *g_rgb,
+                                 void *dfeats, float out_scale, float *gw_s0, float *gw_s1, float *gw_c0, float *gw_c1, float *gw_c2,
+                                 int train_mlp, void *stream) {
+    if (M == 0) return 0;
+    const size_t smem = bwd_smem();
+    cudaError_t e = cudaFuncSetAttribute(k_ngp_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    BwdArgs a;
+    a.feats = (const __half *)feats; a.dirs = dirs;
+    a.w = MlpWeights{(const __half *)w_s0, (const __half *)w_s1, (const __half *)w_c0, (const __half *)w_c1, (const __half *)w_c2};
+    a.g_sigma = g_sigma; a.g_rgb = g_rgb; a.dfeats = (__half *)dfeats;
+    a.gw_s0 = gw_s0; a.gw_s1 = gw_s1; a.gw_c0 = gw_c0; a.gw_c1 = gw_c1; a.gw_c2 = gw_c2;
+    a.M = M; a.n_tiles = div_up(M, kRows); a.density_scale = density_scale; a.out_scale = out_scale; a.train_mlp = train_mlp;
+    const uint32_t grid = min(a.n_tiles, (uint32_t)sm_count());
+    k_ngp_mlp_bwd<<<grid, 128, smem, as_stream(stream)>>>(a);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_ngp_interleave_tables(const float *table_sigma, const float *table_color, void *table4, uint64_t n_entries, void *stream) {
+    if (n_entries == 0) return 0;
+    k_interleave_tables<<<(unsigned)div_up((size_t)n_entries, (size_t)256), 256, 0, as_stream(stream)>>>((const float2 *)table_sigma, (const float2 *)table_color, (uint2 *)table4, (size_t)n_entries);
+    S3D_RETURN_LAST();
+}
+
+// Adam (torch semantics, main_SealNeRF.py:283-284) over both tables at once: params fp32 [N,2] each, interleaved
+// grad / moments fp32 [N,4], interleaved fp16 shadow [N,4] refreshed in the same pass; the gradient is zeroed.
+S3D_API int s3d_ngp_adam_tables(float *table_sigma, float *table_color, float *grad4, float *exp_avg4, float *exp_avg_sq4, void *table4,
+                                uint64_t n_entries, float lr, float beta1, float beta2, float eps, uint32_t step, float grad_scale, void *stream) {
+    if (n_entries == 0) return 0;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    k_adam_tables<<<(unsigned)div_up((size_t)n_entries, (size_t)256), 256, 0, as_stream(stream)>>>(
+        (float2 *)table_sigma, (float2 *)table_color, (float4 *)grad4, (float4 *)exp_avg4, (float4 *)exp_avg_sq4, (uint2 *)table4, (size_t)n_entries,
+        (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps, grad_scale);
+    S3D_RETURN_LAST();
+}

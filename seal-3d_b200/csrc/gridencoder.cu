@@ -393,6 +393,11 @@ __global__ void k_grad_tv(const T *__restrict__ inputs, const T *__restrict__ gr
     red_add_entry<T, C>(gg + (size_t)index * C, out);
 }
 
+__global__ void k_level_scales(uint32_t L, float S, uint32_t H, float *__restrict__ out) {
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < L) out[l] = __fmaf_rn(exp2f((float)l * S), (float)H, -1.0f);
+}
+
 // ---- dispatch ----------------------------------------------------------------------------
 
 constexpr uint32_t kBigBatch = 1u << 17;  // from here one thread walks all levels of its point
@@ -435,6 +440,14 @@ int launch_backward(const T *grad, const float *inputs, const int *offsets, T *g
     }
 
 }  // namespace
+
+// the per-level scale exp2f(l*S)*H - 1 exactly as the kernels evaluate it (gridencoder.cu:138 of the reference);
+// diagnostic entry used by the parity tests (see oracle/seal_oracle.c: orc_set_level_scales)
+S3D_API int s3d_grid_level_scales(uint32_t L, float S, uint32_t H, float *scales, void *stream) {
+    if (L == 0) return 0;
+    k_level_scales<<<1, 64, 0, as_stream(stream)>>>(L, S, H, scales);
+    S3D_RETURN_LAST();
+}
 
 // dtype: 0 = float32 table/outputs, 1 = float16 table/outputs (inputs are always float32)
 S3D_API int s3d_grid_encode_forward(const float *inputs, const void *embeddings, const int *offsets, void *outputs,

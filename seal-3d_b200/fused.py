@@ -1,0 +1,249 @@
+"""Fused execution of the NGP field and of the distillation step (no autograd, no intermediate tensors
+beyond one 128-byte feature row per sample), on the kernels of csrc/field.cu.
+
+``FusedNGP`` wraps a ``NeRFNetwork`` (same parameters -- reference checkpoints load into the module as
+usual) and keeps the device-side forms the kernels want: both hash tables interleaved into one fp16
+table, the five MLP matrices in fp16, and -- for a trainable field -- an interleaved fp32 gradient table,
+Adam moments and a flat fp32 arena for the MLP.  ``FusedDistillTrainer`` runs the schedule of
+``DistillTrainer`` (teacher and student on the same sample buffer) on top of it, with the single
+gradient all-reduce per step for data-parallel runs.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from . import raymarching
+
+_MLP = ("sigma_net.0", "sigma_net.1", "color_net.0", "color_net.1", "color_net.2")
+
+
+class FusedNGP:
+    def __init__(self, model, trainable=False):
+        self.model = model
+        enc, encc = model.encoder, model.encoder_color
+        assert enc.level_dim == 2 and encc.level_dim == 2 and enc.input_dim == 3 and enc.gridtype_id == 0 and not enc.align_corners
+        assert torch.equal(enc.offsets, encc.offsets), "the fused field needs both grids to share their level geometry"
+        self.dev = enc.embeddings.device
+        self.N = enc.embeddings.shape[0]
+        self.L = enc.offsets.shape[0] - 1
+        self.S = float(np.log2(enc.per_level_scale))
+        self.H = int(enc.base_resolution)
+        self.offsets = enc.offsets
+        self.bound = float(model.bound)
+        self.density_scale = float(model.density_scale)
+        self.weights = [model.sigma_net[0].weight, model.sigma_net[1].weight, model.color_net[0].weight, model.color_net[1].weight,
+                        model.color_net[2].weight]
+        assert [tuple(w.shape) for w in self.weights] == [(64, 32), (16, 64), (64, 63), (64, 64), (3, 64)], "NGP field shapes (nerf/network.py)"
+        # flat fp32 arena for the MLP (master copy; the module's parameters become views of it)
+        n_mlp = sum(w.numel() for w in self.weights)
+        self.n_mlp = (n_mlp + 7) // 8 * 8
+        self.mlp32 = torch.zeros(self.n_mlp, dtype=torch.float32, device=self.dev)
+        self.mlp16 = torch.zeros(self.n_mlp, dtype=torch.float16, device=self.dev)
+        off = 0
+        self._w_off = []
+        for w in self.weights:
+            k = w.numel()
+            self.mlp32[off:off + k].copy_(w.data.reshape(-1))
+            w.data = self.mlp32[off:off + k].view_as(w.data)
+            self._w_off.append((off, k))
+            off += k
+        self.table4 = torch.empty(self.N, 4, dtype=torch.float16, device=self.dev)
+        self.sync_from_module()
+        self.trainable = trainable
+        if trainable:
+            for p in (enc.embeddings, encc.embeddings):
+                assert p.dtype == torch.float32 and p.is_contiguous()
+            # one contiguous gradient arena: [interleaved table gradient N*4 | MLP gradient] -> one all-reduce
+            self.grad = torch.zeros(self.N * 4 + self.n_mlp, dtype=torch.float32, device=self.dev)
+            self.grad4 = self.grad[:self.N * 4]
+            self.gmlp = self.grad[self.N * 4:]
+            self.m4 = torch.zeros(self.N * 4, dtype=torch.float32, device=self.dev)
+            self.v4 = torch.zeros(self.N * 4, dtype=torch.float32, device=self.dev)
+            self.m_mlp = torch.zeros(self.n_mlp, dtype=torch.float32, device=self.dev)
+            self.v_mlp = torch.zeros(self.n_mlp, dtype=torch.float32, device=self.dev)
+            self.step_tables = 0
+            self.step_mlp = 0
+
+    # -- state --------------------------------------------------------------------------------
+    def sync_from_module(self):
+        """refresh the fp16 forms after the module's parameters were changed from outside (load_state_dict, ...)"""
+        enc, encc = self.model.encoder, self.model.encoder_color
+        _lib.call("s3d_ngp_interleave_tables", enc.embeddings.detach(), encc.embeddings.detach(), self.table4, self.N)
+        _lib.call("s3d_cast_f32_to_f16", self.mlp32, self.mlp16, self.n_mlp)
+
+    def _w16(self):
+        return [self.mlp16[o:] for o, _ in self._w_off]
+
+    def _gw(self):
+        return [self.gmlp[o:] for o, _ in self._w_off]
+
+    # -- forward ------------------------------------------------------------------------------
+    def encode(self, xyz, sigma_only=False):
+        M = xyz.shape[0]
+        feats = torch.empty(M, 64, dtype=torch.float16, device=self.dev)
+        _lib.call("s3d_ngp_encode", xyz, M, self.bound, self.table4, self.offsets, self.L, self.S, self.H, feats, int(sigma_only))
+        return feats
+
+    def mlp_forward(self, feats, dirs, sigma_only=False, want_geo=False):
+        M = feats.shape[0]
+        sigma = torch.empty(M, dtype=torch.float32, device=self.dev)
+        rgb = None if sigma_only else torch.empty(M, 3, dtype=torch.float32, device=self.dev)
+        geo = torch.empty(M, 15, dtype=torch.float32, device=self.dev) if want_geo else None
+        w = self._w16()
+        _lib.call("s3d_ngp_mlp_forward", feats, dirs, M, w[0], w[1], w[2], w[3], w[4], self.density_scale, sigma, rgb, geo, int(sigma_only))
+        return sigma, rgb, geo
+
+    def forward(self, xyz, dirs):
+        """(sigma * density_scale, rgb) like NeRFRenderer._field; also returns the feature rows for the backward"""
+        xyz = xyz.contiguous().float()
+        dirs = dirs.contiguous().float()
+        feats = self.encode(xyz)
+        sigma, rgb, _ = self.mlp_forward(feats, dirs)
+        return sigma, rgb, feats
+
+    def density(self, xyz):
+        """NeRFNetwork.density (nerf/network.py:130-147): {'sigma', 'geo_feat'} (sigma WITHOUT density_scale, like the module)"""
+        xyz = xyz.contiguous().float()
+        feats = self.encode(xyz, sigma_only=True)
+        sigma, _, geo = self.mlp_forward(feats, None, sigma_only=True, want_geo=True)
+        return {"sigma": sigma / self.density_scale, "geo_feat": geo}
+
+    # -- backward / optimizer ---------------------------------------------------------------------
+    def backward(self, xyz, dirs, feats, g_sigma, g_rgb, loss_scale=1.0, train_mlp=True):
+        """accumulates loss_scale * dL/dparams into the gradient arena"""
+        M = feats.shape[0]
+        dfeats = torch.empty(M, 64, dtype=torch.float16, device=self.dev)
+        w, gw = self._w16(), self._gw()
+        _lib.call("s3d_ngp_mlp_backward", feats, dirs, M, w[0], w[1], w[2], w[3], w[4], self.density_scale, g_sigma, g_rgb, dfeats,
+                  1.0, gw[0], gw[1], gw[2], gw[3], gw[4], int(train_mlp))
+        _lib.call("s3d_ngp_scatter", xyz, dfeats, M, self.bound, self.grad4, self.offsets, self.L, self.S, self.H, 1.0)
+
+    def adam_step(self, lr, grad_scale=1.0, beta1=0.9, beta2=0.99, eps=1e-15, train_mlp=True):
+        enc, encc = self.model.encoder, self.model.encoder_color
+        self.step_tables += 1
+        _lib.call("s3d_ngp_adam_tables", enc.embeddings.data, encc.embeddings.data, self.grad4, self.m4, self.v4, self.table4, self.N,
+                  float(lr), beta1, beta2, eps, self.step_tables, float(grad_scale))
+        if train_mlp:
+            self.step_mlp += 1
+            _lib.call("s3d_adam_step", self.mlp32, self.gmlp, self.m_mlp, self.v_mlp, self.mlp16, self.n_mlp, float(lr), beta1, beta2, eps,
+                      self.step_mlp, float(grad_scale), 1, 0)
+        else:
+            self.gmlp.zero_()
+
+
+class FusedDistillTrainer:
+    """Same public steps as trainer.DistillTrainer (pretrain_step / finetune_step / distill_step), fused kernels inside."""
+
+    def __init__(self, student, teacher=None, lr=1e-2, loss_scale=128.0, bg_color=1.0, T_thresh=1e-4, max_steps=1024, dt_gamma=0.0,
+                 world_size=1, update_interval=16):
+        self.student, self.teacher = student, teacher
+        self.S = FusedNGP(student, trainable=True)
+        self.T = FusedNGP(teacher, trainable=False) if teacher is not None else None
+        self.lr, self.loss_scale, self.bg_color, self.T_thresh = lr, float(loss_scale), float(bg_color), T_thresh
+        self.max_steps, self.dt_gamma, self.world_size, self.update_interval = max_steps, dt_gamma, world_size, update_interval
+        self.loss_buf = torch.zeros(2, dtype=torch.float32, device=self.S.dev)
+        self.global_step = 0
+
+    def _reduce_and_step(self, train_mlp=True):
+        if self.world_size > 1:
+            dist.all_reduce(self.S.grad)   # the single collective of the step
+        self.S.adam_step(self.lr, grad_scale=1.0 / (self.world_size * self.loss_scale), train_mlp=train_mlp)
+        self.global_step += 1
+
+    def _march(self, rays_o, rays_d, perturb, force_all_rays):
+        s = self.student
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, s.aabb_train, s.min_near)
+        counter = s.step_counter[s.local_step % 16]
+        counter.zero_()
+        s.local_step += 1
+        return raymarching.march_rays_train(rays_o, rays_d, s.bound, s.density_bitfield, s.cascade, s.grid_size, nears, fars, counter,
+                                            s.mean_count, perturb, 128, force_all_rays, self.dt_gamma, self.max_steps)
+
+    def _composite(self, sigmas, rgbs, deltas, rays):
+        M, N = sigmas.shape[0], rays.shape[0]
+        dev = sigmas.device
+        ws = torch.empty(N, dtype=torch.float32, device=dev)
+        depth = torch.empty(N, dtype=torch.float32, device=dev)
+        image = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        _lib.call("s3d_composite_rays_train_forward", sigmas, rgbs, deltas, rays, M, N, float(self.T_thresh), ws, depth, image)
+        return ws, depth, image
+
+    def _student_backward(self, xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, image_t, depth_t):
+        M, N = sig_s.shape[0], rays.shape[0]
+        dev = sig_s.device
+        ws, depth, comp = self._composite(sig_s, rgb_s, deltas, rays)
+        g_img = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        g_ws = torch.empty(N, dtype=torch.float32, device=dev)
+        self.loss_buf.zero_()
+        _lib.call("s3d_finetune_loss", comp, ws, depth, image_t, depth_t, N, self.bg_color, self.loss_buf, g_img, g_ws)
+        if self.loss_scale != 1.0:
+            g_img.mul_(self.loss_scale)
+            g_ws.mul_(self.loss_scale)
+        g_sig = torch.zeros(M, dtype=torch.float32, device=dev)
+        g_rgb = torch.zeros(M, 3, dtype=torch.float32, device=dev)
+        _lib.call("s3d_composite_rays_train_backward", g_ws, g_img, sig_s, rgb_s, deltas, rays, ws, comp, M, N, float(self.T_thresh), g_sig, g_rgb)
+        self.S.backward(xyzs, dirs, feats, g_sig, g_rgb)
+        return self.loss_buf
+
+    def teacher_targets(self, xyzs, dirs, deltas, rays):
+        """teacher on the student's samples: proxy map -> field -> colour edit -> composite (+ background)"""
+        t = self.teacher
+        mx, md, mask = t._map_samples(xyzs, dirs)
+        sig_t, rgb_t, _ = self.T.forward(mx, md)
+        if mask is not None and t.seal_mapper is not None and t.seal_mapper.has_color_edit():
+            t.seal_mapper.map_color_(rgb_t, mask)
+        ws_t, depth_t, img_t = self._composite(sig_t, rgb_t, deltas, rays)
+        img_t.add_((1 - ws_t).unsqueeze(-1) * self.bg_color)
+        return img_t, depth_t
+
+    @torch.no_grad()
+    def distill_step(self, rays_o, rays_d, perturb=True, force_all_rays=False):
+        self._maybe_update_grid()
+        rays_o, rays_d = rays_o.view(-1, 3), rays_d.view(-1, 3)
+        xyzs, dirs, deltas, rays = self._march(rays_o, rays_d, perturb, force_all_rays)
+        img_t, depth_t = self.teacher_targets(xyzs, dirs, deltas, rays)
+        sig_s, rgb_s, feats = self.S.forward(xyzs, dirs)
+        loss = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, img_t, depth_t)
+        self._reduce_and_step()
+        return loss
+
+    @torch.no_grad()
+    def finetune_step(self, rays_o, rays_d, image_t, depth_t=None, perturb=True, force_all_rays=False):
+        self._maybe_update_grid()
+        rays_o, rays_d = rays_o.view(-1, 3), rays_d.view(-1, 3)
+        xyzs, dirs, deltas, rays = self._march(rays_o, rays_d, perturb, force_all_rays)
+        sig_s, rgb_s, feats = self.S.forward(xyzs, dirs)
+        loss = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, image_t, depth_t)
+        self._reduce_and_step()
+        return loss
+
+    @torch.no_grad()
+    def pretrain_step(self, points, dirs, sigma_t, rgb_t):
+        points, dirs = points.contiguous().float(), dirs.contiguous().float()
+        sig_s, rgb_s, feats = self.S.forward(points, dirs)
+        M = points.shape[0]
+        g_s = torch.empty(M, dtype=torch.float32, device=points.device)
+        g_c = torch.empty(M, 3, dtype=torch.float32, device=points.device)
+        self.loss_buf.zero_()
+        _lib.call("s3d_pretrain_loss", sig_s, rgb_s, sigma_t, rgb_t, M, self.loss_buf, g_s, g_c)
+        if self.loss_scale != 1.0:
+            g_s.mul_(self.loss_scale)
+            g_c.mul_(self.loss_scale)
+        self.S.backward(points, dirs, feats, g_s, g_c, train_mlp=False)
+        self._reduce_and_step(train_mlp=False)
+        return self.loss_buf
+
+    def _maybe_update_grid(self):
+        if self.update_interval and self.global_step % self.update_interval == 0 and self.global_step > 0:
+            self.refresh_occupancy()
+
+    @torch.no_grad()
+    def refresh_occupancy(self, seed=None):
+        seed = 1234 + self.global_step if seed is None else seed
+        orig = self.student.density
+        self.student.density = self.S.density
+        try:
+            self.student.update_extra_state(seed=seed)
+        finally:
+            self.student.density = orig
