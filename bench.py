@@ -122,7 +122,7 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -163,7 +163,8 @@ def build_world(dev, precision, seed_rank=0):
     from seal3d_b200.trainer import DistillTrainer
     to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     bits, grid = synth.lego_like_occupancy()
-    t, s = TeacherNetwork(bound=1).to(dev), StudentNetwork(bound=1).to(dev)
+    # density_thresh 10 = main_nerf.py:49-50 / main_SealNeRF.py defaults
+    t, s = TeacherNetwork(bound=1, density_thresh=10).to(dev), StudentNetwork(bound=1, density_thresh=10).to(dev)
     for net, kind in ((t, "teacher"), (s, "student")):
         fp = synth.field_params(kind)
         net.encoder.embeddings.data.copy_(to(fp["emb_sigma"]))
@@ -272,7 +273,7 @@ def gpu_arm(args):
     from seal3d_b200.fused import FusedDistillTrainer
     teacher, student = build_world(dev, args.precision)
     if args.engine == "fused":
-        tr = FusedDistillTrainer(student, teacher, lr=1e-2, loss_scale=128.0, world_size=world, update_interval=16)
+        tr = FusedDistillTrainer(student, teacher, lr=1e-2, world_size=world, update_interval=16)
     else:
         tr = DistillTrainer(student, teacher, lr=1e-2, precision=args.precision, loss_scale=(128.0 if args.precision == "fp16" else 1.0),
                             world_size=world, update_interval=16)

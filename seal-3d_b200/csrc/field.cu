@@ -256,13 +256,16 @@ __device__ __forceinline__ void sh4(float x, float y, float z, float *o) {
     o[15] = -0.59004358992664352f * c3;
 }
 
-__device__ __forceinline__ void load_feat_row(uint8_t *tile, const __half *__restrict__ feats, uint32_t row_g, uint32_t r, bool in_range) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(feats + (size_t)row_g * 64);
+// Thread layout of the MLP kernels: 256 threads = 2 warpgroups; thread t owns sample row (t & 127) and column half
+// hf = t >> 7 (columns 32*hf .. 32*hf+31) of every 64-wide tile / accumulator.  A warp may only read the 32 TMEM lanes
+// of its sub-partition (warp % 4), which is exactly rows 32*(warp%4) .. +31 for both warpgroups.
+__device__ __forceinline__ void load_feat_half(uint8_t *tile, const __half *__restrict__ feats, uint32_t row_g, uint32_t r, uint32_t hf, bool in_range) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(feats + (size_t)row_g * 64) + hf * 4;
 #pragma unroll
-    for (uint32_t c16 = 0; c16 < 8; c16++) {
+    for (uint32_t q = 0; q < 4; q++) {
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (in_range) v = __ldg(src + c16);
-        *reinterpret_cast<uint4 *>(tile + sw128_off(r, c16)) = v;
+        if (in_range) v = __ldg(src + q);
+        *reinterpret_cast<uint4 *>(tile + sw128_off(r, hf * 4 + q)) = v;
     }
 }
 
@@ -275,8 +278,7 @@ __device__ __forceinline__ void sync_tiles() {  // writers -> tensor core, tenso
 
 struct Issue {
     uint32_t mbar, parity;
-    __device__ __forceinline__ void commit_and_wait(bool issuer) {
-        if (issuer) mma_commit(mbar);
+    __device__ __forceinline__ void wait() {
         mbar_wait(mbar, parity);
         parity ^= 1;
         fence_after_sync();
@@ -287,6 +289,31 @@ struct Issue {
 __device__ __forceinline__ void store_half_row(uint8_t *tile, uint32_t r, uint32_t half, const float *v) {
 #pragma unroll
     for (uint32_t q = 0; q < 4; q++) *reinterpret_cast<uint4 *>(tile + sw128_off(r, half * 4 + q)) = pack8(v + q * 8);
+}
+__device__ __forceinline__ void zero_half_row(uint8_t *tile, uint32_t r, uint32_t half) {
+#pragma unroll
+    for (uint32_t q = 0; q < 4; q++) *reinterpret_cast<uint4 *>(tile + sw128_off(r, half * 4 + q)) = make_uint4(0, 0, 0, 0);
+}
+// accumulator half -> ReLU -> operand tile
+__device__ __forceinline__ void relu_to_tile(uint32_t t_row, uint32_t hf, uint8_t *tile, uint32_t r) {
+    float v[32];
+    tmem_ld32(t_row + hf * 32, v);
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.0f);
+    store_half_row(tile, r, hf, v);
+}
+// gradient half: D (.) relu'(act) -> gradient tile
+__device__ __forceinline__ void masked_to_tile(uint32_t t_row, uint32_t hf, const uint8_t *act_tile, uint8_t *dst_tile, uint32_t r) {
+    float v[32];
+    tmem_ld32(t_row + hf * 32, v);
+#pragma unroll
+    for (uint32_t q = 0; q < 4; q++) {
+        float act[8];
+        unpack8(*reinterpret_cast<const uint4 *>(act_tile + sw128_off(r, hf * 4 + q)), act);
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[q * 8 + i] = act[i] > 0.0f ? v[q * 8 + i] : 0.0f;
+    }
+    store_half_row(dst_tile, r, hf, v);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -302,7 +329,7 @@ struct FwdArgs {
     int sigma_only;
 };
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_ngp_mlp_fwd(const FwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -310,89 +337,73 @@ k_ngp_mlp_fwd(const FwdArgs a) {
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *tF = smem, *tT = tF + kTileBytes, *tWs0 = tT + kTileBytes, *tWc0 = tWs0 + kWTile, *tWc1 = tWc0 + kWTile,
             *tWs1 = tWc1 + kWTile, *tWc2 = tWs1 + kOTile;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, r = tid & 127, hf = tid >> 7;
     if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 64);
     if (tid == 0) mbar_init(smem_u32(&s_mbar), 1);
     load_weights(tWs0, tWs1, tWc0, tWc1, tWc2, a.w);
     sync_tiles();
-    const uint32_t tmem = s_tmem, t_row = tmem + ((warp * 32u) << 16);
+    const uint32_t tmem = s_tmem, t_row = tmem + (((warp & 3u) * 32u) << 16);
     Issue is{smem_u32(&s_mbar), 0};
     const bool issuer = (tid == 0);
     const uint32_t aF = smem_u32(tF), aT = smem_u32(tT);
     const uint32_t id64 = make_idesc(128, 64, false, false), id16 = make_idesc(128, 16, false, false);
 
     for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const uint32_t row = tile * kRows + tid;
+        const uint32_t row = tile * kRows + r;
         const bool in_range = row < a.M;
-        load_feat_row(tF, a.feats, row, tid, in_range);
+        load_feat_half(tF, a.feats, row, r, hf, in_range);
         sync_tiles();
         // sigma layer 0: [128 x 32] . W_s0^T  (2 K-steps over the sigma features)
-        if (issuer) { for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, k), desc_kmajor(smem_u32(tWs0), k), id64, k > 0); }
-        is.commit_and_wait(issuer);
-#pragma unroll
-        for (uint32_t h = 0; h < 2; h++) {
-            float v[32];
-            tmem_ld32(t_row + h * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.0f);
-            store_half_row(tT, tid, h, v);
-        }
+        if (issuer) { for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, k), desc_kmajor(smem_u32(tWs0), k), id64, k > 0); mma_commit(is.mbar); }
+        is.wait();
+        relu_to_tile(t_row, hf, tT, r);
         sync_tiles();
         // sigma layer 1: [128 x 64] . W_s1^T -> 16
-        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(smem_u32(tWs1), k), id16, k > 0); }
-        is.commit_and_wait(issuer);
-        float h2[16];
-        tmem_ld16(t_row, h2);
-        if (in_range) {
-            a.sigma[row] = a.density_scale * __expf(h2[0]);
-            if (a.geo) for (int i = 0; i < 15; i++) a.geo[(size_t)row * 15 + i] = h2[1 + i];
+        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(smem_u32(tWs1), k), id16, k > 0); mma_commit(is.mbar); }
+        is.wait();
+        if (hf == 0) {
+            float h2[16];
+            tmem_ld16(t_row, h2);
+            if (in_range) {
+                a.sigma[row] = a.density_scale * __expf(h2[0]);
+                if (a.geo) for (int i = 0; i < 15; i++) a.geo[(size_t)row * 15 + i] = h2[1 + i];
+            }
+            if (!a.sigma_only) {
+                // colour input, second half: [SH16 | geo15 | 0] -> columns 0..31 of the scratch tile
+                float g[32];
+                float dx = 0.f, dy = 0.f, dz = 0.f;
+                if (in_range) { dx = a.dirs[(size_t)row * 3]; dy = a.dirs[(size_t)row * 3 + 1]; dz = a.dirs[(size_t)row * 3 + 2]; }
+                sh4(dx, dy, dz, g);
+#pragma unroll
+                for (int i = 0; i < 15; i++) g[16 + i] = h2[1 + i];
+                g[31] = 0.0f;
+                store_half_row(tT, r, 0, g);
+            }
         }
         if (a.sigma_only) { fence_before_sync(); __syncthreads(); fence_after_sync(); continue; }
-        // colour input, second half: [SH16 | geo15 | 0] -> columns 0..31 of the scratch tile
-        {
-            float g[32];
-            float dx = 0.f, dy = 0.f, dz = 0.f;
-            if (in_range) { dx = a.dirs[(size_t)row * 3]; dy = a.dirs[(size_t)row * 3 + 1]; dz = a.dirs[(size_t)row * 3 + 2]; }
-            sh4(dx, dy, dz, g);
-#pragma unroll
-            for (int i = 0; i < 15; i++) g[16 + i] = h2[1 + i];
-            g[31] = 0.0f;
-            store_half_row(tT, tid, 0, g);
-        }
         sync_tiles();
         // colour layer 0: K-steps 0,1 = colour-grid feats (feature tile cols 32..63), K-steps 2,3 = [SH | geo] (scratch cols 0..31)
         if (issuer) {
             for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, 2 + k), desc_kmajor(smem_u32(tWc0), k), id64, k > 0);
             for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(smem_u32(tWc0), 2 + k), id64, true);
+            mma_commit(is.mbar);
         }
-        is.commit_and_wait(issuer);
-#pragma unroll
-        for (uint32_t h = 0; h < 2; h++) {
-            float v[32];
-            tmem_ld32(t_row + h * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.0f);
-            store_half_row(tT, tid, h, v);
-        }
+        is.wait();
+        relu_to_tile(t_row, hf, tT, r);
         sync_tiles();
-        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(smem_u32(tWc1), k), id64, k > 0); }
-        is.commit_and_wait(issuer);
-#pragma unroll
-        for (uint32_t h = 0; h < 2; h++) {
-            float v[32];
-            tmem_ld32(t_row + h * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.0f);
-            store_half_row(tT, tid, h, v);
-        }
+        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(smem_u32(tWc1), k), id64, k > 0); mma_commit(is.mbar); }
+        is.wait();
+        relu_to_tile(t_row, hf, tT, r);
         sync_tiles();
-        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(smem_u32(tWc2), k), id16, k > 0); }
-        is.commit_and_wait(issuer);
-        float o[16];
-        tmem_ld16(t_row, o);
-        if (in_range) {
+        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(smem_u32(tWc2), k), id16, k > 0); mma_commit(is.mbar); }
+        is.wait();
+        if (hf == 0) {
+            float o[16];
+            tmem_ld16(t_row, o);
+            if (in_range) {
 #pragma unroll
-            for (int c = 0; c < 3; c++) a.rgb[(size_t)row * 3 + c] = 1.0f / (1.0f + __expf(-o[c]));
+                for (int c = 0; c < 3; c++) a.rgb[(size_t)row * 3 + c] = 1.0f / (1.0f + __expf(-o[c]));
+            }
         }
         fence_before_sync();
         __syncthreads();
@@ -418,7 +429,10 @@ struct BwdArgs {
 
 // TMEM columns: [0,64) activation accumulator | [64,128) dWc2 | [128,192) dWc1 | [192,256) dC1^T.F | [256,320) dC1^T.G | [320,384) dWs1 |
 // [384,448) dH1^T.F.  Every weight-gradient MMA is a full 64 x 64 (M = 64, N = 64) block; the flush picks the valid columns.
-__global__ void __launch_bounds__(128)
+// Per round the data-gradient MMAs are issued (and committed) FIRST and the weight-gradient MMAs after the commit, so the
+// latter run on the tensor pipe while the threads are already in the epilogue; the gradient tiles X / Y alternate, so the
+// epilogue never writes a tile the in-flight weight-gradient MMAs read.
+__global__ void __launch_bounds__(256)
 k_ngp_mlp_bwd(const BwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -427,12 +441,12 @@ k_ngp_mlp_bwd(const BwdArgs a) {
     uint8_t *tF = smem, *tH1 = tF + kTileBytes, *tG = tH1 + kTileBytes, *tC1 = tG + kTileBytes, *tC2 = tC1 + kTileBytes,
             *tX = tC2 + kTileBytes, *tY = tX + kTileBytes, *tWs0 = tY + kTileBytes, *tWc0 = tWs0 + kWTile, *tWc1 = tWc0 + kWTile,
             *tWs1 = tWc1 + kWTile, *tWc2 = tWs1 + kOTile;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, r = tid & 127, hf = tid >> 7;
     if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
     if (tid == 0) mbar_init(smem_u32(&s_mbar), 1);
     load_weights(tWs0, tWs1, tWc0, tWc1, tWc2, a.w);
     sync_tiles();
-    const uint32_t tmem = s_tmem, t_row = tmem + ((warp * 32u) << 16);
+    const uint32_t tmem = s_tmem, t_row = tmem + (((warp & 3u) * 32u) << 16);
     Issue is{smem_u32(&s_mbar), 0};
     const bool issuer = (tid == 0);
     const uint32_t aF = smem_u32(tF), aH1 = smem_u32(tH1), aG = smem_u32(tG), aC1 = smem_u32(tC1), aC2 = smem_u32(tC2), aX = smem_u32(tX), aY = smem_u32(tY);
@@ -443,70 +457,49 @@ k_ngp_mlp_bwd(const BwdArgs a) {
     bool first = true;
 
     for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, first = false) {
-        const uint32_t row = tile * kRows + tid;
+        const uint32_t row = tile * kRows + r;
         const bool in_range = row < a.M;
         // ---------------- recompute the forward, keeping every activation tile ----------------
-        load_feat_row(tF, a.feats, row, tid, in_range);
+        load_feat_half(tF, a.feats, row, r, hf, in_range);
         sync_tiles();
-        if (issuer) { for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, k), desc_kmajor(smem_u32(tWs0), k), id64, k > 0); }
-        is.commit_and_wait(issuer);
-#pragma unroll
-        for (uint32_t h = 0; h < 2; h++) {
-            float v[32];
-            tmem_ld32(t_row + h * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.0f);
-            store_half_row(tH1, tid, h, v);
-        }
+        if (issuer) { for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, k), desc_kmajor(smem_u32(tWs0), k), id64, k > 0); mma_commit(is.mbar); }
+        is.wait();
+        relu_to_tile(t_row, hf, tH1, r);
         sync_tiles();
-        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aH1, k), desc_kmajor(smem_u32(tWs1), k), id16, k > 0); }
-        is.commit_and_wait(issuer);
-        float h2[16];
-        tmem_ld16(t_row, h2);
-        {
-            float g[32];
+        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aH1, k), desc_kmajor(smem_u32(tWs1), k), id16, k > 0); mma_commit(is.mbar); }
+        is.wait();
+        float h0 = 0.0f;   // sigma logit (kept by warpgroup 0 for the trunc_exp backward)
+        if (hf == 0) {
+            float h2[16], g[32];
+            tmem_ld16(t_row, h2);
+            h0 = h2[0];
             float dx = 0.f, dy = 0.f, dz = 0.f;
             if (in_range) { dx = a.dirs[(size_t)row * 3]; dy = a.dirs[(size_t)row * 3 + 1]; dz = a.dirs[(size_t)row * 3 + 2]; }
             sh4(dx, dy, dz, g);
 #pragma unroll
             for (int i = 0; i < 15; i++) g[16 + i] = h2[1 + i];
             g[31] = 0.0f;
-            store_half_row(tG, tid, 0, g);
-            float z[32];
-#pragma unroll
-            for (int i = 0; i < 32; i++) z[i] = 0.0f;
-            store_half_row(tG, tid, 1, z);
+            store_half_row(tG, r, 0, g);
+        } else {
+            zero_half_row(tG, r, 1);
         }
         sync_tiles();
         if (issuer) {
             for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, 2 + k), desc_kmajor(smem_u32(tWc0), k), id64, k > 0);
             for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aG, k), desc_kmajor(smem_u32(tWc0), 2 + k), id64, true);
+            mma_commit(is.mbar);
         }
-        is.commit_and_wait(issuer);
-#pragma unroll
-        for (uint32_t h = 0; h < 2; h++) {
-            float v[32];
-            tmem_ld32(t_row + h * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.0f);
-            store_half_row(tC1, tid, h, v);
-        }
+        is.wait();
+        relu_to_tile(t_row, hf, tC1, r);
         sync_tiles();
-        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aC1, k), desc_kmajor(smem_u32(tWc1), k), id64, k > 0); }
-        is.commit_and_wait(issuer);
-#pragma unroll
-        for (uint32_t h = 0; h < 2; h++) {
-            float v[32];
-            tmem_ld32(t_row + h * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.0f);
-            store_half_row(tC2, tid, h, v);
-        }
+        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aC1, k), desc_kmajor(smem_u32(tWc1), k), id64, k > 0); mma_commit(is.mbar); }
+        is.wait();
+        relu_to_tile(t_row, hf, tC2, r);
         sync_tiles();
-        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aC2, k), desc_kmajor(smem_u32(tWc2), k), id16, k > 0); }
-        is.commit_and_wait(issuer);
-        // ---------------- output gradients -> tX (16 meaningful columns, zero padded) ----------------
-        {
+        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aC2, k), desc_kmajor(smem_u32(tWc2), k), id16, k > 0); mma_commit(is.mbar); }
+        is.wait();
+        // ---------------- output gradients -> tX (3 meaningful columns, zero padded) ----------------
+        if (hf == 0) {
             float o[16], d[32];
             tmem_ld16(t_row, o);
 #pragma unroll
@@ -514,145 +507,117 @@ k_ngp_mlp_bwd(const BwdArgs a) {
             if (in_range) {
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    const float s = 1.0f / (1.0f + __expf(-o[c]));
-                    d[c] = a.g_rgb[(size_t)row * 3 + c] * s * (1.0f - s);
+                    const float sg = 1.0f / (1.0f + __expf(-o[c]));
+                    d[c] = a.g_rgb[(size_t)row * 3 + c] * sg * (1.0f - sg);
                 }
             }
-            store_half_row(tX, tid, 0, d);
-#pragma unroll
-            for (int i = 0; i < 3; i++) d[i] = 0.0f;
-            store_half_row(tX, tid, 1, d);
+            store_half_row(tX, r, 0, d);
+        } else {
+            zero_half_row(tX, r, 1);
         }
         sync_tiles();
-        // dWc2 += dO^T . C2 ; dC2 = dO . Wc2
+        // dC2 = dO . Wc2 ;  dWc2 += dO^T . C2
         if (issuer) {
-            if (a.train_mlp) for (uint32_t k = 0; k < 8; k++) mma_f16(accC2, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aC2, k, kTileBytes), idw64, !(first && k == 0));
             mma_f16(tmem, desc_kmajor(aX, 0), desc_mnmajor(smem_u32(tWc2), 0, kOTile), id64t, false);
+            mma_commit(is.mbar);
+            if (a.train_mlp) for (uint32_t k = 0; k < 8; k++) mma_f16(accC2, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aC2, k, kTileBytes), idw64, !(first && k == 0));
         }
-        is.commit_and_wait(issuer);
-#pragma unroll
-        for (uint32_t h = 0; h < 2; h++) {
-            float v[32];
-            tmem_ld32(t_row + h * 32, v);
-#pragma unroll
-            for (uint32_t q = 0; q < 4; q++) {
-                float act[8];
-                unpack8(*reinterpret_cast<const uint4 *>(tC2 + sw128_off(tid, h * 4 + q)), act);
-#pragma unroll
-                for (int i = 0; i < 8; i++) v[q * 8 + i] = act[i] > 0.0f ? v[q * 8 + i] : 0.0f;
-            }
-            store_half_row(tY, tid, h, v);
-        }
+        is.wait();
+        masked_to_tile(t_row, hf, tC2, tY, r);
         sync_tiles();
-        // dWc1 += dC2^T . C1 ; dC1 = dC2 . Wc1
+        // dC1 = dC2 . Wc1 ;  dWc1 += dC2^T . C1
         if (issuer) {
-            if (a.train_mlp) for (uint32_t k = 0; k < 8; k++) mma_f16(accC1, desc_mnmajor(aY, k, kTileBytes), desc_mnmajor(aC1, k, kTileBytes), idw64, !(first && k == 0));
             for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aY, k), desc_mnmajor(smem_u32(tWc1), k, kWTile), id64t, k > 0);
+            mma_commit(is.mbar);
+            if (a.train_mlp) for (uint32_t k = 0; k < 8; k++) mma_f16(accC1, desc_mnmajor(aY, k, kTileBytes), desc_mnmajor(aC1, k, kTileBytes), idw64, !(first && k == 0));
         }
-        is.commit_and_wait(issuer);
-#pragma unroll
-        for (uint32_t h = 0; h < 2; h++) {
-            float v[32];
-            tmem_ld32(t_row + h * 32, v);
-#pragma unroll
-            for (uint32_t q = 0; q < 4; q++) {
-                float act[8];
-                unpack8(*reinterpret_cast<const uint4 *>(tC1 + sw128_off(tid, h * 4 + q)), act);
-#pragma unroll
-                for (int i = 0; i < 8; i++) v[q * 8 + i] = act[i] > 0.0f ? v[q * 8 + i] : 0.0f;
-            }
-            store_half_row(tX, tid, h, v);
-        }
+        is.wait();
+        masked_to_tile(t_row, hf, tC1, tX, r);
         sync_tiles();
-        // dWc0 += dC1^T . [colour feats | SH,geo] ; d[colour feats | SH | geo] = dC1 . Wc0p
+        // d[colour feats | SH | geo] = dC1 . Wc0p ;  dWc0 += dC1^T . [F | G]
         if (issuer) {
+            for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aX, k), desc_mnmajor(smem_u32(tWc0), k, kWTile), id64t, k > 0);
+            mma_commit(is.mbar);
             if (a.train_mlp) {
                 for (uint32_t k = 0; k < 8; k++) mma_f16(accC0f, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aF, k, kTileBytes), idw64, !(first && k == 0));
                 for (uint32_t k = 0; k < 8; k++) mma_f16(accC0g, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aG, k, kTileBytes), idw64, !(first && k == 0));
             }
-            for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aX, k), desc_mnmajor(smem_u32(tWc0), k, kWTile), id64t, k > 0);
         }
-        is.commit_and_wait(issuer);
-        float dfc[32];   // gradient w.r.t. the colour-grid features (dfeats cols 32..63)
-        tmem_ld32(t_row, dfc);
-        {
+        is.wait();
+        float dfc[32];   // warpgroup 1: gradient w.r.t. the colour-grid features (dfeats cols 32..63), kept in registers
+        if (hf == 1) {
+            tmem_ld32(t_row, dfc);
+            zero_half_row(tY, r, 1);
+        } else {
             float v[32], d[32];
             tmem_ld32(t_row + 32, v);  // cols 32-47 dSH (dropped), 48-62 dgeo
 #pragma unroll
             for (int i = 0; i < 32; i++) d[i] = 0.0f;
-            float gs = 0.0f;
-            if (in_range) gs = a.g_sigma[row] * a.density_scale * __expf(fminf(fmaxf(h2[0], -15.0f), 15.0f));  // trunc_exp backward
-            d[0] = gs;
+            if (in_range) d[0] = a.g_sigma[row] * a.density_scale * __expf(fminf(fmaxf(h0, -15.0f), 15.0f));  // trunc_exp backward
 #pragma unroll
             for (int i = 0; i < 15; i++) d[1 + i] = v[16 + i];
-            store_half_row(tY, tid, 0, d);
-#pragma unroll
-            for (int i = 0; i < 16; i++) d[i] = 0.0f;
-            store_half_row(tY, tid, 1, d);
+            store_half_row(tY, r, 0, d);
         }
         sync_tiles();
-        // dWs1 += dh2^T . H1 ; dH1 = dh2 . Ws1
+        // dH1 = dh2 . Ws1 ;  dWs1 += dh2^T . H1
         if (issuer) {
-            if (a.train_mlp) for (uint32_t k = 0; k < 8; k++) mma_f16(accS1, desc_mnmajor(aY, k, kTileBytes), desc_mnmajor(aH1, k, kTileBytes), idw64, !(first && k == 0));
             mma_f16(tmem, desc_kmajor(aY, 0), desc_mnmajor(smem_u32(tWs1), 0, kOTile), id64t, false);
+            mma_commit(is.mbar);
+            if (a.train_mlp) for (uint32_t k = 0; k < 8; k++) mma_f16(accS1, desc_mnmajor(aY, k, kTileBytes), desc_mnmajor(aH1, k, kTileBytes), idw64, !(first && k == 0));
         }
-        is.commit_and_wait(issuer);
-#pragma unroll
-        for (uint32_t h = 0; h < 2; h++) {
-            float v[32];
-            tmem_ld32(t_row + h * 32, v);
-#pragma unroll
-            for (uint32_t q = 0; q < 4; q++) {
-                float act[8];
-                unpack8(*reinterpret_cast<const uint4 *>(tH1 + sw128_off(tid, h * 4 + q)), act);
-#pragma unroll
-                for (int i = 0; i < 8; i++) v[q * 8 + i] = act[i] > 0.0f ? v[q * 8 + i] : 0.0f;
-            }
-            store_half_row(tX, tid, h, v);
-        }
+        is.wait();
+        masked_to_tile(t_row, hf, tH1, tX, r);
         sync_tiles();
-        // dWs0 += dH1^T . sigma feats ; d(sigma feats) = dH1 . Ws0p
+        // last round: weight gradient FIRST (the commit must cover it: the feature tile is overwritten by the next tile)
         if (issuer) {
             if (a.train_mlp) for (uint32_t k = 0; k < 8; k++) mma_f16(accS0, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aF, k, kTileBytes), idw64, !(first && k == 0));
             for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aX, k), desc_mnmajor(smem_u32(tWs0), k, kWTile), id64t, k > 0);
+            mma_commit(is.mbar);
         }
-        is.commit_and_wait(issuer);
-        {
+        is.wait();
+        if (hf == 0) {
             float dfs[32];
             tmem_ld32(t_row, dfs);
             if (in_range) {
                 uint4 *dst = reinterpret_cast<uint4 *>(a.dfeats + (size_t)row * 64);
 #pragma unroll
-                for (int i = 0; i < 32; i++) { dfs[i] *= a.out_scale; dfc[i] *= a.out_scale; }
+                for (int i = 0; i < 32; i++) dfs[i] *= a.out_scale;
 #pragma unroll
-                for (uint32_t q = 0; q < 4; q++) { dst[q] = pack8(dfs + q * 8); dst[4 + q] = pack8(dfc + q * 8); }
+                for (uint32_t q = 0; q < 4; q++) dst[q] = pack8(dfs + q * 8);
             }
+        } else if (in_range) {
+            uint4 *dst = reinterpret_cast<uint4 *>(a.dfeats + (size_t)row * 64) + 4;
+#pragma unroll
+            for (int i = 0; i < 32; i++) dfc[i] *= a.out_scale;
+#pragma unroll
+            for (uint32_t q = 0; q < 4; q++) dst[q] = pack8(dfc + q * 8);
         }
         fence_before_sync();
         __syncthreads();
         fence_after_sync();
     }
 
-    // ---- flush weight gradients: accumulator rows (M = 64) live in lanes 0..15 of every 32-lane sub-partition ----
+    // ---- flush weight gradients: accumulator rows (M = 64) live in lanes 0..15 of every 32-lane sub-partition;
+    //      warpgroup hf takes the columns [32*hf, 32*hf+32) of every block ----
     if (a.train_mlp && !first) {
-        const uint32_t lane = tid & 31, r = warp * 16 + lane;   // output feature
+        const uint32_t lane = tid & 31, rr = (warp & 3u) * 16 + lane;   // output feature
         const bool rowok = lane < 16;
-        for (uint32_t half = 0; half < 2; half++) {
-            float v[32];
-            tmem_ld32(t_row + 64 + half * 32, v);   // dWc2 [3 x 64]
-            if (rowok && r < 3) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c2 + r * 64 + half * 32 + i, v[i]);
-            tmem_ld32(t_row + 128 + half * 32, v);  // dWc1 [64 x 64]
-            if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c1 + r * 64 + half * 32 + i, v[i]);
-            tmem_ld32(t_row + 320 + half * 32, v);  // dWs1 [16 x 64]
-            if (rowok && r < 16) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s1 + r * 64 + half * 32 + i, v[i]);
-        }
         float v[32];
-        tmem_ld32(t_row + 192 + 32, v);             // dC1^T . F, columns 32..63 = colour-grid inputs = original columns 31..62
-        if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c0 + r * 63 + 31 + i, v[i]);
-        tmem_ld32(t_row + 256, v);                  // dC1^T . G, columns 0..30 = [SH | geo] = original columns 0..30
-        if (rowok) for (int i = 0; i < 31; i++) atomicAdd(a.gw_c0 + r * 63 + i, v[i]);
-        tmem_ld32(t_row + 384, v);                  // dH1^T . F, columns 0..31 = sigma-grid inputs
-        if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s0 + r * 32 + i, v[i]);
+        tmem_ld32(t_row + 64 + hf * 32, v);    // dWc2 [3 x 64]
+        if (rowok && rr < 3) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c2 + rr * 64 + hf * 32 + i, v[i]);
+        tmem_ld32(t_row + 128 + hf * 32, v);   // dWc1 [64 x 64]
+        if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c1 + rr * 64 + hf * 32 + i, v[i]);
+        tmem_ld32(t_row + 320 + hf * 32, v);   // dWs1 [16 x 64]
+        if (rowok && rr < 16) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s1 + rr * 64 + hf * 32 + i, v[i]);
+        if (hf == 1) {
+            tmem_ld32(t_row + 192 + 32, v);    // dC1^T . F, columns 32..63 = colour-grid inputs = original columns 31..62
+            if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c0 + rr * 63 + 31 + i, v[i]);
+        } else {
+            tmem_ld32(t_row + 256, v);         // dC1^T . G, columns 0..30 = [SH | geo] = original columns 0..30
+            if (rowok) for (int i = 0; i < 31; i++) atomicAdd(a.gw_c0 + rr * 63 + i, v[i]);
+            tmem_ld32(t_row + 384, v);         // dH1^T . F, columns 0..31 = sigma-grid inputs
+            if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s0 + rr * 32 + i, v[i]);
+        }
     }
     fence_before_sync();
     __syncthreads();
@@ -674,12 +639,19 @@ k_adam_tables(float2 *__restrict__ ps, float2 *__restrict__ pc, float4 *__restri
               uint2 *__restrict__ shadow4, size_t n, float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps, float gscale) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float4 g = g4[i];
-    g4[i] = make_float4(0, 0, 0, 0);
-    // dense Adam semantics: untouched entries still decay their moments and move with the stale momentum
-    float4 m = m4[i], v = v4[i];
+    const float4 g = g4[i];
+    float4 m = m4[i];
+    const bool gz = (g.x == 0.0f) & (g.y == 0.0f) & (g.z == 0.0f) & (g.w == 0.0f);
+    const bool mz = (m.x == 0.0f) & (m.y == 0.0f) & (m.z == 0.0f) & (m.w == 0.0f);
+    // An entry that has never received a gradient has g = m = v = 0 and dense Adam leaves it exactly unchanged
+    // (0 / (0 + eps) = 0): skipping it is bit-identical and saves 104 of its 136 bytes of traffic.  Entries that were
+    // touched once keep decaying their moments and moving, like torch.optim.Adam.
+    if (gz && mz) return;
+    if (!gz) g4[i] = make_float4(0, 0, 0, 0);
+    float4 v = v4[i];
     float2 s = ps[i], c = pc[i];
-    float *G = &g.x, *Mv = &m.x, *V = &v.x;
+    const float *G = &g.x;
+    float *Mv = &m.x, *V = &v.x;
     float P[4] = {s.x, s.y, c.x, c.y};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -737,7 +709,7 @@ S3D_API int s3d_ngp_mlp_forward(const void *feats, const float *dirs, uint32_t M
     a.w = MlpWeights{(const __half *)w_s0, (const __half *)w_s1, (const __half *)w_c0, (const __half *)w_c1, (const __half *)w_c2};
     a.sigma = sigma; a.rgb = rgb; a.geo = geo; a.M = M; a.n_tiles = div_up(M, kRows); a.density_scale = density_scale; a.sigma_only = sigma_only;
     const uint32_t grid = min(a.n_tiles, (uint32_t)sm_count() * 3u);
-    k_ngp_mlp_fwd<<<grid, 128, smem, as_stream(stream)>>>(a);
+    k_ngp_mlp_fwd<<<grid, 256, smem, as_stream(stream)>>>(a);
     S3D_RETURN_LAST();
 }
 
@@ -756,7 +728,7 @@ S3D_API int s3d_ngp_mlp_backward(const void *feats, const float *dirs, uint32_t 
     a.gw_s0 = gw_s0; a.gw_s1 = gw_s1; a.gw_c0 = gw_c0; a.gw_c1 = gw_c1; a.gw_c2 = gw_c2;
     a.M = M; a.n_tiles = div_up(M, kRows); a.density_scale = density_scale; a.out_scale = out_scale; a.train_mlp = train_mlp;
     const uint32_t grid = min(a.n_tiles, (uint32_t)sm_count());
-    k_ngp_mlp_bwd<<<grid, 128, smem, as_stream(stream)>>>(a);
+    k_ngp_mlp_bwd<<<grid, 256, smem, as_stream(stream)>>>(a);
     S3D_RETURN_LAST();
 }
 

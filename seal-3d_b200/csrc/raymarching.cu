@@ -225,32 +225,40 @@ __global__ void __launch_bounds__(128)
 k_march_count(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
               float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
               const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
-              int *__restrict__ rays) {
+              int *__restrict__ rays, uint32_t *__restrict__ block_sums) {
+    __shared__ uint32_t s_warp[4];
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const MarchCfg c = make_cfg(grid, bound, dt_gamma, max_steps, C, H);
-    const Ray r = load_ray(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
-    const float far = fars[n];
-    float t = perturbed_start(c, nears[n], noises ? noises[n] : 0.0f);
     uint32_t num = 0;
-    float x, y, z, dt;
-    while (t < far && num < max_steps) {
-        if (march_visit(c, r, t, x, y, z, dt)) { num++; t = __fadd_rn(t, dt); }
+    if (n < N) {
+        const MarchCfg c = make_cfg(grid, bound, dt_gamma, max_steps, C, H);
+        const Ray r = load_ray(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
+        const float far = fars[n];
+        float t = perturbed_start(c, nears[n], noises ? noises[n] : 0.0f);
+        float x, y, z, dt;
+        while (t < far && num < max_steps) {
+            if (march_visit(c, r, t, x, y, z, dt)) { num++; t = __fadd_rn(t, dt); }
+        }
+        rays[(size_t)n * 3] = (int)n;
+        rays[(size_t)n * 3 + 2] = (int)num;
     }
-    rays[(size_t)n * 3] = (int)n;
-    rays[(size_t)n * 3 + 2] = (int)num;
+    // per-CTA sample count for the two-level exclusive scan
+    uint32_t v = num;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = s_warp[0] + s_warp[1] + s_warp[2] + s_warp[3];
 }
 
-// single-CTA exclusive scan of rays[:,2] -> rays[:,1]; counter += (sum, N)
-__global__ void __launch_bounds__(1024) k_march_scan(int *__restrict__ rays, uint32_t N, int *__restrict__ counter) {
+// single-CTA exclusive scan of the per-CTA sums (N/128 values) in place; counter += (sum, N)
+__global__ void __launch_bounds__(1024) k_march_scan(uint32_t *__restrict__ block_sums, uint32_t nb, uint32_t N, int *__restrict__ counter) {
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t s_base;
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
-    const uint32_t chunk = div_up(N, nthr);
-    const uint32_t lo = min(tid * chunk, N), hi = min(lo + chunk, N);
+    const uint32_t chunk = div_up(nb, nthr);
+    const uint32_t lo = min(tid * chunk, nb), hi = min(lo + chunk, nb);
     uint32_t sum = 0;
-    for (uint32_t i = lo; i < hi; i++) sum += (uint32_t)rays[(size_t)i * 3 + 2];
-    // block exclusive scan of the per-thread sums
+    for (uint32_t i = lo; i < hi; i++) sum += block_sums[i];
     uint32_t incl = sum;
     const uint32_t lane = tid & 31, wid = tid >> 5;
 #pragma unroll
@@ -277,10 +285,28 @@ __global__ void __launch_bounds__(1024) k_march_scan(int *__restrict__ rays, uin
     __syncthreads();
     uint32_t run = s_base + warp_tot[wid] + (incl - sum);
     for (uint32_t i = lo; i < hi; i++) {
-        const uint32_t c = (uint32_t)rays[(size_t)i * 3 + 2];
-        rays[(size_t)i * 3 + 1] = (int)run;
+        const uint32_t c = block_sums[i];
+        block_sums[i] = run;
         run += c;
     }
+}
+
+// rays[:,1] = CTA offset + exclusive scan of the CTA's 128 counts
+__global__ void __launch_bounds__(128) k_march_offsets(int *__restrict__ rays, uint32_t N, const uint32_t *__restrict__ block_offs) {
+    __shared__ uint32_t s_warp[4];
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t c = n < N ? (uint32_t)rays[(size_t)n * 3 + 2] : 0;
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += v;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    uint32_t base = block_offs[blockIdx.x];
+    for (uint32_t w = 0; w < wid; w++) base += s_warp[w];
+    if (n < N) rays[(size_t)n * 3 + 1] = (int)(base + incl - c);
 }
 
 // pass 2: re-march and write the samples of every ray that fits (raymarching.cu:415-479)
@@ -346,44 +372,83 @@ k_march_rays(uint32_t n_alive, uint32_t n_step, const int *__restrict__ rays_ali
 // compositing
 // ---------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(128)
+// Training compositor: ONE WARP PER RAY.  Lanes take consecutive samples (coalesced 4/12/8-byte streams); the
+// transmittance T_before(i) = prod_{j<i} (1 - alpha_j) is a multiplicative warp scan carried across 32-sample chunks.
+// The reference is one thread per ray walking its samples serially (raymarching.cu:501-577): same arithmetic per
+// sample, products associated as a tree instead of a chain.  Early stop: a sample is accumulated iff the
+// transmittance before it is still >= T_thresh (the reference breaks AFTER the sample that drives T below it).
+__device__ __forceinline__ float warp_excl_prod(float v, uint32_t lane, float &total) {
+    float incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl *= o;
+    }
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    const float ex = __shfl_up_sync(0xffffffffu, incl, 1);
+    return lane == 0 ? 1.0f : ex;
+}
+__device__ __forceinline__ float warp_sum_all(float v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ float warp_incl_sum(float v, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (uint32_t)d) v += o;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
 k_composite_train_fwd(const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ deltas,
                       const int *__restrict__ rays, uint32_t M, uint32_t N, float T_thresh,
                       float *__restrict__ weights_sum, float *__restrict__ depth, float *__restrict__ image) {
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (n >= N) return;
     const uint32_t index = (uint32_t)rays[(size_t)n * 3], offset = (uint32_t)rays[(size_t)n * 3 + 1],
                    num = (uint32_t)rays[(size_t)n * 3 + 2];
-    float T = 1.0f, r = 0, g = 0, b = 0, ws = 0, t = 0, d = 0;
+    float r = 0, g = 0, b = 0, ws = 0, d = 0, T = 1.0f, t0 = 0.0f;
     if (num != 0 && offset + num <= M) {
         const float *s = sigmas + offset, *c = rgbs + (size_t)offset * 3;
         const float2 *dl = reinterpret_cast<const float2 *>(deltas) + offset;
-        for (uint32_t step = 0; step < num; step++) {
-            const float2 de = __ldg(dl + step);
-            const float alpha = 1.0f - __expf(-__ldg(s + step) * de.x);
-            const float w = alpha * T;
-            r = fmaf(w, __ldg(c + step * 3), r);
-            g = fmaf(w, __ldg(c + step * 3 + 1), g);
-            b = fmaf(w, __ldg(c + step * 3 + 2), b);
-            t += de.y;
-            d = fmaf(w, t, d);
-            ws += w;
-            T *= 1.0f - alpha;
-            if (T < T_thresh) break;
+        for (uint32_t base = 0; base < num; base += 32) {
+            const uint32_t i = base + lane;
+            const bool in = i < num;
+            float2 de = make_float2(0.f, 0.f);
+            float sg = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+            if (in) { de = __ldg(dl + i); sg = __ldg(s + i); c0 = __ldg(c + i * 3); c1 = __ldg(c + i * 3 + 1); c2 = __ldg(c + i * 3 + 2); }
+            const float alpha = in ? 1.0f - __expf(-sg * de.x) : 0.0f;
+            float tot;
+            const float Tb = T * warp_excl_prod(1.0f - alpha, lane, tot);   // transmittance before this sample
+            const float tt = t0 + warp_incl_sum(de.y, lane);               // accumulated "real delta" up to this sample
+            const bool take = in && (Tb >= T_thresh || i == 0);
+            const float w = take ? alpha * Tb : 0.0f;
+            r += w * c0; g += w * c1; b += w * c2; ws += w; d += w * tt;
+            T *= tot;
+            t0 = __shfl_sync(0xffffffffu, tt, 31);
+            if (T < T_thresh) break;   // warp-uniform: every later sample has T_before < T_thresh
         }
+        r = warp_sum_all(r); g = warp_sum_all(g); b = warp_sum_all(b); ws = warp_sum_all(ws); d = warp_sum_all(d);
     }
-    weights_sum[index] = ws;
-    depth[index] = d;
-    image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
+    if (lane == 0) {
+        weights_sum[index] = ws;
+        depth[index] = d;
+        image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
+    }
 }
 
-__global__ void __launch_bounds__(128)
+// Backward (raymarching.cu:602-682): grad_rgb_i = g * w_i ; grad_sigma_i = delta_i * (sum_c g_c (T_after_i c_i - (C_final - C_incl_i))
+// + g_ws (1 - ws_final)), written for the accumulated prefix only (later samples keep the caller's zeros).
+__global__ void __launch_bounds__(256)
 k_composite_train_bwd(const float *__restrict__ grad_ws, const float *__restrict__ grad_image,
                       const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ deltas,
                       const int *__restrict__ rays, const float *__restrict__ weights_sum,
                       const float *__restrict__ image, uint32_t M, uint32_t N, float T_thresh,
                       float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs) {
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (n >= N) return;
     const uint32_t index = (uint32_t)rays[(size_t)n * 3], offset = (uint32_t)rays[(size_t)n * 3 + 1],
                    num = (uint32_t)rays[(size_t)n * 3 + 2];
@@ -395,16 +460,26 @@ k_composite_train_bwd(const float *__restrict__ grad_ws, const float *__restrict
     const float *s = sigmas + offset, *c = rgbs + (size_t)offset * 3;
     const float2 *dl = reinterpret_cast<const float2 *>(deltas) + offset;
     float *gs = grad_sigmas + offset, *gc = grad_rgbs + (size_t)offset * 3;
-    float T = 1.0f, r = 0, g = 0, b = 0;
-    for (uint32_t step = 0; step < num; step++) {
-        const float2 de = __ldg(dl + step);
-        const float c0 = __ldg(c + step * 3), c1 = __ldg(c + step * 3 + 1), c2 = __ldg(c + step * 3 + 2);
-        const float alpha = 1.0f - __expf(-__ldg(s + step) * de.x);
-        const float w = alpha * T;
-        r = fmaf(w, c0, r); g = fmaf(w, c1, g); b = fmaf(w, c2, b);
-        T *= 1.0f - alpha;
-        gc[step * 3] = g0 * w; gc[step * 3 + 1] = g1 * w; gc[step * 3 + 2] = g2 * w;
-        gs[step] = de.x * (g0 * (T * c0 - (rf - r)) + g1 * (T * c1 - (gf - g)) + g2 * (T * c2 - (bf - b)) + tail);
+    float T = 1.0f, r0 = 0, gr0 = 0, b0 = 0;
+    for (uint32_t base = 0; base < num; base += 32) {
+        const uint32_t i = base + lane;
+        const bool in = i < num;
+        float2 de = make_float2(0.f, 0.f);
+        float sg = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        if (in) { de = __ldg(dl + i); sg = __ldg(s + i); c0 = __ldg(c + i * 3); c1 = __ldg(c + i * 3 + 1); c2 = __ldg(c + i * 3 + 2); }
+        const float alpha = in ? 1.0f - __expf(-sg * de.x) : 0.0f;
+        float tot;
+        const float Tb = T * warp_excl_prod(1.0f - alpha, lane, tot);
+        const bool take = in && (Tb >= T_thresh || i == 0);
+        const float w = take ? alpha * Tb : 0.0f;
+        const float Ta = Tb * (1.0f - alpha);
+        const float r = r0 + warp_incl_sum(w * c0, lane), g = gr0 + warp_incl_sum(w * c1, lane), b = b0 + warp_incl_sum(w * c2, lane);
+        if (take) {
+            gc[i * 3] = g0 * w; gc[i * 3 + 1] = g1 * w; gc[i * 3 + 2] = g2 * w;
+            gs[i] = de.x * (g0 * (Ta * c0 - (rf - r)) + g1 * (Ta * c1 - (gf - g)) + g2 * (Ta * c2 - (bf - b)) + tail);
+        }
+        T *= tot;
+        r0 = __shfl_sync(0xffffffffu, r, 31); gr0 = __shfl_sync(0xffffffffu, g, 31); b0 = __shfl_sync(0xffffffffu, b, 31);
         if (T < T_thresh) break;
     }
 }
@@ -477,6 +552,23 @@ S3D_API int s3d_packbits(const float *grid, uint32_t N, float density_thresh, ui
     S3D_RETURN_LAST();
 }
 
+namespace {
+int march_count_scan(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma, uint32_t max_steps,
+                     uint32_t N, uint32_t C, uint32_t H, const float *nears, const float *fars, const float *noises, int *rays,
+                     int *counter, cudaStream_t st) {
+    const uint32_t nb = div_up(N, 128u);
+    uint32_t *block_sums = nullptr;
+    cudaError_t e = cudaMallocAsync(&block_sums, (size_t)nb * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return (int)e;
+    k_march_count<<<nb, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, block_sums);
+    k_march_scan<<<1, 1024, 0, st>>>(block_sums, nb, N, counter);
+    k_march_offsets<<<nb, 128, 0, st>>>(rays, N, block_sums);
+    e = cudaPeekAtLastError();
+    cudaFreeAsync(block_sums, st);
+    return (int)e;
+}
+}  // namespace
+
 S3D_API int s3d_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
                                  float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
                                  const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
@@ -484,9 +576,7 @@ S3D_API int s3d_march_rays_train(const float *rays_o, const float *rays_d, const
     if (N == 0) return 0;
     if (C == 0 || H == 0 || max_steps == 0) return S3D_EINVAL;
     cudaStream_t st = as_stream(stream);
-    k_march_count<<<div_up(N, 128u), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears,
-                                                    fars, noises, rays);
-    k_march_scan<<<1, 1024, 0, st>>>(rays, N, counter);
+    if (int rc = march_count_scan(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, st)) return rc;
     k_march_write<<<div_up(N, 128u), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears,
                                                     fars, noises, rays, xyzs, dirs, deltas);
     S3D_RETURN_LAST();
@@ -500,11 +590,7 @@ S3D_API int s3d_march_rays_train_count(const float *rays_o, const float *rays_d,
                                        const float *noises, void *stream) {
     if (N == 0) return 0;
     if (C == 0 || H == 0 || max_steps == 0) return S3D_EINVAL;
-    cudaStream_t st = as_stream(stream);
-    k_march_count<<<div_up(N, 128u), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears,
-                                                    fars, noises, rays);
-    k_march_scan<<<1, 1024, 0, st>>>(rays, N, counter);
-    S3D_RETURN_LAST();
+    return march_count_scan(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, as_stream(stream));
 }
 
 S3D_API int s3d_march_rays_train_write(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
@@ -521,7 +607,7 @@ S3D_API int s3d_composite_rays_train_forward(const float *sigmas, const float *r
                                              const int *rays, uint32_t M, uint32_t N, float T_thresh,
                                              float *weights_sum, float *depth, float *image, void *stream) {
     if (N == 0) return 0;
-    k_composite_train_fwd<<<div_up(N, 128u), 128, 0, as_stream(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh,
+    k_composite_train_fwd<<<div_up(N, 8u), 256, 0, as_stream(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh,
                                                                           weights_sum, depth, image);
     S3D_RETURN_LAST();
 }
@@ -532,7 +618,7 @@ S3D_API int s3d_composite_rays_train_backward(const float *grad_weights_sum, con
                                               uint32_t N, float T_thresh, float *grad_sigmas, float *grad_rgbs,
                                               void *stream) {
     if (N == 0) return 0;
-    k_composite_train_bwd<<<div_up(N, 128u), 128, 0, as_stream(stream)>>>(
+    k_composite_train_bwd<<<div_up(N, 8u), 256, 0, as_stream(stream)>>>(
         grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs);
     S3D_RETURN_LAST();
 }

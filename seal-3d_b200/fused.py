@@ -135,20 +135,26 @@ class FusedNGP:
 class FusedDistillTrainer:
     """Same public steps as trainer.DistillTrainer (pretrain_step / finetune_step / distill_step), fused kernels inside."""
 
-    def __init__(self, student, teacher=None, lr=1e-2, loss_scale=128.0, bg_color=1.0, T_thresh=1e-4, max_steps=1024, dt_gamma=0.0,
+    def __init__(self, student, teacher=None, lr=1e-2, loss_scale=None, bg_color=1.0, T_thresh=1e-4, max_steps=1024, dt_gamma=0.0,
                  world_size=1, update_interval=16):
         self.student, self.teacher = student, teacher
         self.S = FusedNGP(student, trainable=True)
         self.T = FusedNGP(teacher, trainable=False) if teacher is not None else None
-        self.lr, self.loss_scale, self.bg_color, self.T_thresh = lr, float(loss_scale), float(bg_color), T_thresh
+        # gradient tiles are fp16 (fp32 accumulation): the loss is scaled so that they sit in fp16's normal range and
+        # the scale is divided out inside the Adam kernels.  The mean reductions make gradients ~ 1/units, so the
+        # default scale is 32 * units (rays for the photometric loss, samples for the pretraining loss).
+        self.lr, self.loss_scale, self.bg_color, self.T_thresh = lr, loss_scale, float(bg_color), T_thresh
         self.max_steps, self.dt_gamma, self.world_size, self.update_interval = max_steps, dt_gamma, world_size, update_interval
         self.loss_buf = torch.zeros(2, dtype=torch.float32, device=self.S.dev)
         self.global_step = 0
 
-    def _reduce_and_step(self, train_mlp=True):
+    def _scale(self, units):
+        return float(self.loss_scale) if self.loss_scale is not None else 32.0 * float(units)
+
+    def _reduce_and_step(self, scale, train_mlp=True):
         if self.world_size > 1:
             dist.all_reduce(self.S.grad)   # the single collective of the step
-        self.S.adam_step(self.lr, grad_scale=1.0 / (self.world_size * self.loss_scale), train_mlp=train_mlp)
+        self.S.adam_step(self.lr, grad_scale=1.0 / (self.world_size * scale), train_mlp=train_mlp)
         self.global_step += 1
 
     def _march(self, rays_o, rays_d, perturb, force_all_rays):
@@ -177,14 +183,14 @@ class FusedDistillTrainer:
         g_ws = torch.empty(N, dtype=torch.float32, device=dev)
         self.loss_buf.zero_()
         _lib.call("s3d_finetune_loss", comp, ws, depth, image_t, depth_t, N, self.bg_color, self.loss_buf, g_img, g_ws)
-        if self.loss_scale != 1.0:
-            g_img.mul_(self.loss_scale)
-            g_ws.mul_(self.loss_scale)
+        scale = self._scale(N)
+        g_img.mul_(scale)
+        g_ws.mul_(scale)
         g_sig = torch.zeros(M, dtype=torch.float32, device=dev)
         g_rgb = torch.zeros(M, 3, dtype=torch.float32, device=dev)
         _lib.call("s3d_composite_rays_train_backward", g_ws, g_img, sig_s, rgb_s, deltas, rays, ws, comp, M, N, float(self.T_thresh), g_sig, g_rgb)
         self.S.backward(xyzs, dirs, feats, g_sig, g_rgb)
-        return self.loss_buf
+        return self.loss_buf, scale
 
     def teacher_targets(self, xyzs, dirs, deltas, rays):
         """teacher on the student's samples: proxy map -> field -> colour edit -> composite (+ background)"""
@@ -204,8 +210,8 @@ class FusedDistillTrainer:
         xyzs, dirs, deltas, rays = self._march(rays_o, rays_d, perturb, force_all_rays)
         img_t, depth_t = self.teacher_targets(xyzs, dirs, deltas, rays)
         sig_s, rgb_s, feats = self.S.forward(xyzs, dirs)
-        loss = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, img_t, depth_t)
-        self._reduce_and_step()
+        loss, scale = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, img_t, depth_t)
+        self._reduce_and_step(scale)
         return loss
 
     @torch.no_grad()
@@ -214,8 +220,8 @@ class FusedDistillTrainer:
         rays_o, rays_d = rays_o.view(-1, 3), rays_d.view(-1, 3)
         xyzs, dirs, deltas, rays = self._march(rays_o, rays_d, perturb, force_all_rays)
         sig_s, rgb_s, feats = self.S.forward(xyzs, dirs)
-        loss = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, image_t, depth_t)
-        self._reduce_and_step()
+        loss, scale = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, image_t, depth_t)
+        self._reduce_and_step(scale)
         return loss
 
     @torch.no_grad()
@@ -227,11 +233,11 @@ class FusedDistillTrainer:
         g_c = torch.empty(M, 3, dtype=torch.float32, device=points.device)
         self.loss_buf.zero_()
         _lib.call("s3d_pretrain_loss", sig_s, rgb_s, sigma_t, rgb_t, M, self.loss_buf, g_s, g_c)
-        if self.loss_scale != 1.0:
-            g_s.mul_(self.loss_scale)
-            g_c.mul_(self.loss_scale)
+        scale = self._scale(M)
+        g_s.mul_(scale)
+        g_c.mul_(scale)
         self.S.backward(points, dirs, feats, g_s, g_c, train_mlp=False)
-        self._reduce_and_step(train_mlp=False)
+        self._reduce_and_step(scale, train_mlp=False)
         return self.loss_buf
 
     def _maybe_update_grid(self):

@@ -73,13 +73,37 @@ def test_fused_backward_matches_oracle(scene):
         f.forward(x0, d0, keep=True)
         ref = f.backward(gs, gc)
     g4 = npy(F.grad4).reshape(-1, 4)
-    for name, got in (("emb_sigma", g4[:, :2]), ("emb_color", g4[:, 2:])):
-        sc = np.abs(ref[name]).max()
-        assert np.abs(got - ref[name]).max() <= 2e-2 * sc, (name, np.abs(got - ref[name]).max(), sc)
     gw = [npy(g[:k]).reshape(w.shape) for g, (o, k), w in zip(F._gw(), F._w_off, F.weights)]
-    for name, got in zip(("w_s0", "w_s1", "w_c0", "w_c1", "w_c2"), gw):
+    report, bad = [], []
+    for name, got in [("emb_sigma", g4[:, :2]), ("emb_color", g4[:, 2:])] + list(zip(("w_s0", "w_s1", "w_c0", "w_c1", "w_c2"), gw)):
         sc = np.abs(ref[name]).max()
-        assert np.abs(got - ref[name]).max() <= 2e-2 * sc, (name, np.abs(got - ref[name]).max(), sc)
+        err = np.abs(got - ref[name]).max()
+        cos = float((got.astype(np.float64) * ref[name]).sum() / (np.linalg.norm(got.astype(np.float64)) * np.linalg.norm(ref[name].astype(np.float64)) + 1e-30))
+        report.append("%s: max|err|=%.3e max|ref|=%.3e rel=%.3e cos=%.6f" % (name, err, sc, err / sc, cos))
+        # fp16 feature rows / activations / gradient tiles with fp32 accumulation: 1% of the largest entry, direction to 1e-3
+        if err > 1e-2 * sc or cos < 0.999:
+            bad.append(name)
+    print("\n".join(report))
+    assert not bad, "\n".join(report)
+
+
+def test_fused_scatter_matches_oracle(scene):
+    """k_ngp_scatter alone: random fp16 feature gradients on ray-ordered samples vs the double-accumulating oracle"""
+    from seal3d_b200 import _lib
+    offsets, pls = scene["synth"].grid_offsets()
+    x0, _, _, _, M = _samples(scene, 1024)
+    x0 = x0[:60000]
+    df = oracle.round_to_half((np.random.default_rng(0).normal(size=(x0.shape[0], 64)) * 1e-2).astype(np.float32))
+    n = int(offsets[-1])
+    g4 = torch.zeros(n, 4, device=dev())
+    _lib.call("s3d_ngp_scatter", to(x0), to(df).half(), x0.shape[0], 1.0, g4, to(offsets), 16, float(np.log2(pls)), 16, 1.0)
+    u = ((x0 + 1) / 2).astype(np.float32)
+    with scaled(offsets, pls):
+        gs = oracle.grid_encode_backward(np.ascontiguousarray(df[:, :32].reshape(-1, 16, 2).transpose(1, 0, 2)), u, (n, 2), offsets, pls, 16)
+        gc = oracle.grid_encode_backward(np.ascontiguousarray(df[:, 32:].reshape(-1, 16, 2).transpose(1, 0, 2)), u, (n, 2), offsets, pls, 16)
+    got = npy(g4)
+    for name, a, b in (("sigma", got[:, :2], gs), ("colour", got[:, 2:], gc)):
+        assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max() + 1e-7, (name, np.abs(a - b).max(), np.abs(b).max())
 
 
 def test_fused_adam_tables_matches_torch():
@@ -112,13 +136,15 @@ def test_fused_trainer_tracks_autograd_trainer(scene):
     torch.backends.cuda.matmul.allow_tf32 = False
     t1, s1, _, _ = _networks(scene)
     t2, s2, _, _ = _networks(scene)
-    fused = FusedDistillTrainer(s1, t1, lr=1e-2, loss_scale=128.0, update_interval=0)
+    fused = FusedDistillTrainer(s1, t1, lr=1e-2, update_interval=0)
     plain = DistillTrainer(s2, t2, lr=1e-2, update_interval=0)
     o, d = to(scene["o"][:2048]), to(scene["d"][:2048])
     lf, lp = [], []
     for i in range(6):
         lf.append(float(npy(fused.distill_step(o, d, perturb=False, force_all_rays=True)).sum()))
         lp.append(float(npy(plain.distill_step(o, d, perturb=False, force_all_rays=True)).sum()))
+    print('fused', lf)
+    print('plain', lp)
     assert np.isfinite(lf).all() and lf[-1] < lf[0]
     np.testing.assert_allclose(lf, lp, rtol=0.15)       # fp16 tables/features vs fp32: same curve, not the same bits
     np.testing.assert_allclose(lf[0], lp[0], rtol=2e-2)
