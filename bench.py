@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rays", type=int, default=int(os.environ.get("S3D_BENCH_RAYS", 65536)), help="rays per step per GPU")
+    ap.add_argument("--rays", type=int, default=int(os.environ.get("S3D_BENCH_RAYS", 262144)), help="rays per step per GPU")
     ap.add_argument("--precision", default=os.environ.get("S3D_BENCH_PRECISION", "fp16"), choices=["fp32", "fp16"])
     ap.add_argument("--engine", default=os.environ.get("S3D_BENCH_ENGINE", "fused"), choices=["fused", "autograd"],
                     help="fused = csrc/field.cu kernels (tcgen05 MLP, interleaved tables); autograd = op-by-op kernels + torch GEMMs")

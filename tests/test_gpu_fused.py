@@ -74,17 +74,36 @@ def test_fused_backward_matches_oracle(scene):
         ref = f.backward(gs, gc)
     g4 = npy(F.grad4).reshape(-1, 4)
     gw = [npy(g[:k]).reshape(w.shape) for g, (o, k), w in zip(F._gw(), F._w_off, F.weights)]
-    report, bad = [], []
-    for name, got in [("emb_sigma", g4[:, :2]), ("emb_color", g4[:, 2:])] + list(zip(("w_s0", "w_s1", "w_c0", "w_c1", "w_c2"), gw)):
+    got_all = dict(zip(("emb_sigma", "emb_color", "w_s0", "w_s1", "w_c0", "w_c1", "w_c2"), [g4[:, :2], g4[:, 2:]] + gw))
+    # (1) against the oracle's exact fp32 backward: the fp16 feature / activation / gradient tiles cost a few percent of the
+    #     largest entry behind each ReLU mask (a numpy emulation of the same roundings shows 2-3.5 %, see emu below)
+    report = []
+    for name, got in got_all.items():
         sc = np.abs(ref[name]).max()
         err = np.abs(got - ref[name]).max()
         cos = float((got.astype(np.float64) * ref[name]).sum() / (np.linalg.norm(got.astype(np.float64)) * np.linalg.norm(ref[name].astype(np.float64)) + 1e-30))
         report.append("%s: max|err|=%.3e max|ref|=%.3e rel=%.3e cos=%.6f" % (name, err, sc, err / sc, cos))
-        # fp16 feature rows / activations / gradient tiles with fp32 accumulation: 1% of the largest entry, direction to 1e-3
-        if err > 1e-2 * sc or cos < 0.999:
-            bad.append(name)
+        assert err <= 6e-2 * sc and cos > 0.9995, "\n".join(report)
     print("\n".join(report))
-    assert not bad, "\n".join(report)
+    # (2) against a numpy emulation of the kernel's arithmetic (same fp16 roundings of features, activations and gradient
+    #     tiles, fp32 accumulation): this is the tight check of the tcgen05 data / weight gradient GEMMs
+    hh = oracle.round_to_half
+    ws0, ws1, wc0, wc1, wc2 = f.w
+    u, f_s, h1, h2, cin, c1, c2, rgb = f._saved
+    fs_q, fc_q = hh(f_s), hh(cin[:, 31:])
+    H1 = hh(np.maximum(fs_q @ ws0.T, 0)); H2 = H1 @ ws1.T
+    G = hh(np.concatenate([cin[:, :16], H2[:, 1:]], 1))
+    CIN = np.concatenate([G, fc_q], 1)
+    C1 = hh(np.maximum(CIN @ wc0.T, 0)); C2 = hh(np.maximum(C1 @ wc1.T, 0)); S = 1 / (1 + np.exp(-(C2 @ wc2.T)))
+    dO = hh(gc * S * (1 - S)); dC2 = hh((dO @ wc2) * (C2 > 0)); dC1 = hh((dC2 @ wc1) * (C1 > 0)); dcin = dC1 @ wc0
+    dh2 = np.zeros_like(H2); dh2[:, 0] = gs * np.exp(np.clip(H2[:, 0], -15, 15)); dh2[:, 1:] = dcin[:, 16:31]; dh2 = hh(dh2)
+    dH1 = hh((dh2 @ ws1) * (H1 > 0))
+    emu = dict(w_c2=dO.T @ C2, w_c1=dC2.T @ C1, w_c0=dC1.T @ CIN, w_s1=dh2.T @ H1, w_s0=dH1.T @ fs_q)
+    for name, e in emu.items():
+        sc = np.abs(e).max()
+        err = np.abs(got_all[name] - e).max()
+        print("emulation %s rel=%.3e" % (name, err / sc))
+        assert err <= 5e-3 * sc, (name, err, sc)    # remaining: ex2.approx sigmoid/exp, mask flips at |activation| ~ 0
 
 
 def test_fused_scatter_matches_oracle(scene):
@@ -115,7 +134,7 @@ def test_fused_adam_tables_matches_torch():
     opt = torch.optim.Adam([ref], lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
     g4 = torch.zeros(n, 4, device=dev())
     m4, v4 = torch.zeros(n, 4, device=dev()), torch.zeros(n, 4, device=dev())
-    t4 = torch.zeros(n, 4, device=dev(), dtype=torch.float16)
+    t4 = torch.cat([ps, pc], 1).half()      # the shadow is initialised from the tables (never-touched entries are skipped)
     for step in range(1, 4):
         gr = torch.randn(n, 4, device=dev(), generator=g)
         gr[::3] = 0          # untouched entries still decay (dense Adam semantics)
