@@ -170,8 +170,14 @@ int s3d_density_grid_ema(float *grid, const float *tmp_grid, uint32_t n, float d
 /* The higher-level seam of SURVEY.md 8b: samples -> (sigma, rgb) and back, four kernels, one 128-byte fp16 row per
  * sample between them.  table4 = both hash tables interleaved, fp16 [N] x {s0,s1,c0,c1}; grad4 = fp32, same layout. */
 int s3d_ngp_interleave_tables(const float *table_sigma, const float *table_color, void *table4, uint64_t n_entries, void *stream);
-int s3d_ngp_encode(const float *xyz, uint32_t M, float bound, const void *table4, const int *offsets, uint32_t L, float S, uint32_t H,
-                   void *feats, int sigma_only, void *stream);
+/* table entry i = {s0,s1,c0,c1} fp16 at table + i * table_stride (8: table4; 16: one half of a paired table8, pointer pre-offset) */
+int s3d_ngp_encode(const float *xyz, uint32_t M, float bound, const void *table, uint32_t table_stride, const int *offsets, uint32_t L,
+                   float S, uint32_t H, void *feats, int sigma_only, void *stream);
+/* teacher + student on the same samples: table8 [N] x {teacher entry | student entry} (16 B); xyz_teacher / mask (uint8) = the
+ * proxy-mapped positions and which samples moved (NULL: none) */
+int s3d_ngp_pair_tables(const void *teacher_table4, const void *student_table4, void *table8, uint64_t n_entries, void *stream);
+int s3d_ngp_encode_pair(const float *xyz, const float *xyz_teacher, const uint8_t *mask, uint32_t M, float bound, const void *table8,
+                        const int *offsets, uint32_t L, float S, uint32_t H, void *feats_teacher, void *feats_student, void *stream);
 /* weights: fp16 row-major nn.Linear matrices sigma_net.0 [64,32], sigma_net.1 [16,64], color_net.0 [64,63], .1 [64,64], .2 [3,64];
  * sigma = density_scale * exp(h[0]); geo [M,15] optional; rgb = sigmoid(...) */
 int s3d_ngp_mlp_forward(const void *feats, const float *dirs, uint32_t M, const void *w_s0, const void *w_s1, const void *w_c0,
@@ -183,8 +189,9 @@ int s3d_ngp_mlp_backward(const void *feats, const float *dirs, uint32_t M, const
                          float out_scale, float *gw_s0, float *gw_s1, float *gw_c0, float *gw_c1, float *gw_c2, int train_mlp, void *stream);
 int s3d_ngp_scatter(const float *xyz, const void *dfeats, uint32_t M, float bound, float *grad4, const int *offsets, uint32_t L, float S,
                     uint32_t H, float grad_scale, void *stream);
-int s3d_ngp_adam_tables(float *table_sigma, float *table_color, float *grad4, float *exp_avg4, float *exp_avg_sq4, void *table4,
-                        uint64_t n_entries, float lr, float beta1, float beta2, float eps, uint32_t step, float grad_scale, void *stream);
+int s3d_ngp_adam_tables(float *table_sigma, float *table_color, float *grad4, float *exp_avg4, float *exp_avg_sq4, void *shadow,
+                        uint32_t shadow_stride, uint64_t n_entries, float lr, float beta1, float beta2, float eps, uint32_t step,
+                        float grad_scale, void *stream);
 
 #ifdef __cplusplus
 }

@@ -50,11 +50,13 @@ _SIGS = {
     "s3d_density_cells_to_xyz": [P, U32, U32, F32, U32, P],
     "s3d_density_scatter": [P, P, U32, F32, P],
     "s3d_ngp_interleave_tables": [P, P, P, U64],
-    "s3d_ngp_encode": [P, U32, F32, P, P, U32, F32, U32, P, I32],
+    "s3d_ngp_encode": [P, U32, F32, P, U32, P, U32, F32, U32, P, I32],
+    "s3d_ngp_pair_tables": [P, P, P, U64],
+    "s3d_ngp_encode_pair": [P, P, P, U32, F32, P, P, U32, F32, U32, P, P],
     "s3d_ngp_mlp_forward": [P, P, U32, P, P, P, P, P, F32, P, P, P, I32],
     "s3d_ngp_mlp_backward": [P, P, U32, P, P, P, P, P, F32, P, P, P, F32, P, P, P, P, P, I32],
     "s3d_ngp_scatter": [P, P, U32, F32, P, P, U32, F32, U32, F32],
-    "s3d_ngp_adam_tables": [P, P, P, P, P, P, U64, F32, F32, F32, F32, U32, F32],
+    "s3d_ngp_adam_tables": [P, P, P, P, P, P, U32, U64, F32, F32, F32, F32, U32, F32],
 }
 _NO_STREAM = {"s3d_allocate_splitk": [SZ], "s3d_free_splitk": []}
 

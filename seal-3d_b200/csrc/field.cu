@@ -106,8 +106,14 @@ __device__ __forceinline__ bool to_unit(float x, float y, float z, float bound, 
 // ------------------------------------------------------------------------------------------------
 // encode: one thread per sample, both tables, all levels
 // ------------------------------------------------------------------------------------------------
+// table entries are {s0,s1,c0,c1} fp16 (8 bytes) at  table + idx * stride + off : stride 8 / off 0 for a stand-alone
+// model, stride 16 / off 0|8 for the teacher | student half of a paired table (see k_ngp_encode_pair)
+__device__ __forceinline__ uint2 ld_entry(const uint8_t *__restrict__ table, uint32_t idx, uint32_t stride) {
+    return __ldg(reinterpret_cast<const uint2 *>(table + (size_t)idx * stride));
+}
+
 __global__ void __launch_bounds__(256)
-k_ngp_encode(const float *__restrict__ xyz, uint32_t M, float bound, const uint2 *__restrict__ table4,
+k_ngp_encode(const float *__restrict__ xyz, uint32_t M, float bound, const uint8_t *__restrict__ table, uint32_t stride,
              const int *__restrict__ offsets, uint32_t L, float S, uint32_t H, __half *__restrict__ feats, int sigma_only) {
     __shared__ Geo g;
     geo_init(g, offsets, L, S, H);
@@ -127,7 +133,7 @@ k_ngp_encode(const float *__restrict__ xyz, uint32_t M, float bound, const uint2
                 locate(g, l, ux, uy, uz, c, nullptr);
                 uint2 v[8];
 #pragma unroll
-                for (int k = 0; k < 8; k++) v[k] = __ldg(table4 + c.idx[k]);
+                for (int k = 0; k < 8; k++) v[k] = ld_entry(table, c.idx[k], stride);
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&v[k].x));
@@ -141,6 +147,72 @@ k_ngp_encode(const float *__restrict__ xyz, uint32_t M, float bound, const uint2
         row[grp] = pack8(fs);
         if (!sigma_only) row[4 + grp] = pack8(fc);
     }
+}
+
+// Teacher and student on the same sample: ONE 128-bit load per corner from a paired table
+// {teacher s0,s1,c0,c1 | student s0,s1,c0,c1} feeds both feature rows, because both models share the level geometry and
+// (except for the ~1 % of samples the proxy mapping moved) the query point.  Moved samples (mask != 0) take a second
+// gather for the teacher at its mapped position.
+__device__ __forceinline__ void acc4(const uint2 v, float w, float &a0, float &a1, float &a2, float &a3) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&v.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&v.y));
+    a0 = __fmaf_rn(w, a.x, a0); a1 = __fmaf_rn(w, a.y, a1); a2 = __fmaf_rn(w, b.x, a2); a3 = __fmaf_rn(w, b.y, a3);
+}
+
+__global__ void __launch_bounds__(256)
+k_ngp_encode_pair(const float *__restrict__ xyz, const float *__restrict__ xyz_teacher, const uint8_t *__restrict__ mask, uint32_t M,
+                  float bound, const uint4 *__restrict__ table8, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H,
+                  __half *__restrict__ feats_teacher, __half *__restrict__ feats_student) {
+    __shared__ Geo g;
+    geo_init(g, offsets, L, S, H);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    float ux, uy, uz, tx = 0, ty = 0, tz = 0;
+    const bool ok = to_unit(xyz[(size_t)i * 3], xyz[(size_t)i * 3 + 1], xyz[(size_t)i * 3 + 2], bound, ux, uy, uz);
+    const bool moved = mask && mask[i];
+    bool tok = ok;
+    if (moved) tok = to_unit(xyz_teacher[(size_t)i * 3], xyz_teacher[(size_t)i * 3 + 1], xyz_teacher[(size_t)i * 3 + 2], bound, tx, ty, tz);
+    uint4 *row_t = reinterpret_cast<uint4 *>(feats_teacher + (size_t)i * 64), *row_s = reinterpret_cast<uint4 *>(feats_student + (size_t)i * 64);
+    for (uint32_t grp = 0; grp < 4; grp++) {
+        float ts[8], tc[8], ss[8], sc[8];
+#pragma unroll
+        for (uint32_t q = 0; q < 4; q++) {
+            const uint32_t l = grp * 4 + q;
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            if (ok && l < L) {
+                Cell c;
+                locate(g, l, ux, uy, uz, c, nullptr);
+                uint4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = __ldg(table8 + c.idx[k]);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    acc4(make_uint2(v[k].z, v[k].w), c.w[k], s0, s1, s2, s3);
+                    if (!moved) acc4(make_uint2(v[k].x, v[k].y), c.w[k], t0, t1, t2, t3);
+                }
+            }
+            if (moved && tok && l < L) {
+                Cell c;
+                locate(g, l, tx, ty, tz, c, nullptr);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint4 v = __ldg(table8 + c.idx[k]);
+                    acc4(make_uint2(v.x, v.y), c.w[k], t0, t1, t2, t3);
+                }
+            }
+            ts[q * 2] = t0; ts[q * 2 + 1] = t1; tc[q * 2] = t2; tc[q * 2 + 1] = t3;
+            ss[q * 2] = s0; ss[q * 2 + 1] = s1; sc[q * 2] = s2; sc[q * 2 + 1] = s3;
+        }
+        row_t[grp] = pack8(ts); row_t[4 + grp] = pack8(tc);
+        row_s[grp] = pack8(ss); row_s[4 + grp] = pack8(sc);
+    }
+}
+
+__global__ void k_pair_tables(const uint2 *__restrict__ teacher4, const uint2 *__restrict__ student4, uint4 *__restrict__ table8, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2 t = teacher4[i], s = student4[i];
+    table8[i] = make_uint4(t.x, t.y, s.x, s.y);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -636,7 +708,7 @@ __global__ void k_interleave_tables(const float2 *__restrict__ ts, const float2 
 // Adam over the two hash tables with an interleaved gradient / shadow layout
 __global__ void __launch_bounds__(256)
 k_adam_tables(float2 *__restrict__ ps, float2 *__restrict__ pc, float4 *__restrict__ g4, float4 *__restrict__ m4, float4 *__restrict__ v4,
-              uint2 *__restrict__ shadow4, size_t n, float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps, float gscale) {
+              uint8_t *__restrict__ shadow, uint32_t shadow_stride, size_t n, float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps, float gscale) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 g = g4[i];
@@ -663,7 +735,7 @@ k_adam_tables(float2 *__restrict__ ps, float2 *__restrict__ pc, float4 *__restri
     m4[i] = m; v4[i] = v;
     ps[i] = make_float2(P[0], P[1]); pc[i] = make_float2(P[2], P[3]);
     __half2 a = __floats2half2_rn(P[0], P[1]), b = __floats2half2_rn(P[2], P[3]);
-    shadow4[i] = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+    *reinterpret_cast<uint2 *>(shadow + i * shadow_stride) = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
 }
 
 size_t fwd_smem() { return 1024 + 2 * kTileBytes + 3 * kWTile + 2 * kOTile; }
@@ -678,12 +750,30 @@ int sm_count() {
 
 }  // namespace
 
-// table4: interleaved fp16 table [N] x {s0,s1,c0,c1}; feats [M,64] fp16 (sigma feats 0..31, colour feats 32..63)
-S3D_API int s3d_ngp_encode(const float *xyz, uint32_t M, float bound, const void *table4, const int *offsets, uint32_t L, float S,
-                           uint32_t H, void *feats, int sigma_only, void *stream) {
+// table: interleaved fp16 entries {s0,s1,c0,c1} at table + idx * table_stride (8 = stand-alone table4, 16 = one half of a
+// paired table: pass the pointer already offset by 0 | 8 bytes); feats [M,64] fp16 (sigma feats 0..31, colour feats 32..63)
+S3D_API int s3d_ngp_encode(const float *xyz, uint32_t M, float bound, const void *table, uint32_t table_stride, const int *offsets,
+                           uint32_t L, float S, uint32_t H, void *feats, int sigma_only, void *stream) {
     if (M == 0) return 0;
     if (L > kMaxLevels) return S3D_ENOTSUP;
-    k_ngp_encode<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, M, bound, (const uint2 *)table4, offsets, L, S, H, (__half *)feats, sigma_only);
+    if (table_stride != 8 && table_stride != 16) return S3D_EINVAL;
+    k_ngp_encode<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, M, bound, (const uint8_t *)table, table_stride, offsets, L, S, H, (__half *)feats, sigma_only);
+    S3D_RETURN_LAST();
+}
+
+// paired table8 [N] x {teacher s0,s1,c0,c1 | student s0,s1,c0,c1} fp16 (16 bytes).  xyz_teacher / mask may be NULL (no proxy).
+S3D_API int s3d_ngp_encode_pair(const float *xyz, const float *xyz_teacher, const uint8_t *mask, uint32_t M, float bound, const void *table8,
+                                const int *offsets, uint32_t L, float S, uint32_t H, void *feats_teacher, void *feats_student, void *stream) {
+    if (M == 0) return 0;
+    if (L > kMaxLevels) return S3D_ENOTSUP;
+    k_ngp_encode_pair<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, xyz_teacher, xyz_teacher ? mask : nullptr, M, bound, (const uint4 *)table8, offsets, L, S, H,
+                                                                     (__half *)feats_teacher, (__half *)feats_student);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_ngp_pair_tables(const void *teacher_table4, const void *student_table4, void *table8, uint64_t n_entries, void *stream) {
+    if (n_entries == 0) return 0;
+    k_pair_tables<<<(unsigned)div_up((size_t)n_entries, (size_t)256), 256, 0, as_stream(stream)>>>((const uint2 *)teacher_table4, (const uint2 *)student_table4, (uint4 *)table8, (size_t)n_entries);
     S3D_RETURN_LAST();
 }
 
@@ -739,13 +829,15 @@ S3D_API int s3d_ngp_interleave_tables(const float *table_sigma, const float *tab
 }
 
 // Adam (torch semantics, main_SealNeRF.py:283-284) over both tables at once: params fp32 [N,2] each, interleaved
-// grad / moments fp32 [N,4], interleaved fp16 shadow [N,4] refreshed in the same pass; the gradient is zeroed.
-S3D_API int s3d_ngp_adam_tables(float *table_sigma, float *table_color, float *grad4, float *exp_avg4, float *exp_avg_sq4, void *table4,
-                                uint64_t n_entries, float lr, float beta1, float beta2, float eps, uint32_t step, float grad_scale, void *stream) {
+// grad / moments fp32 [N,4]; the fp16 shadow entry {s0,s1,c0,c1} of entry i is written at shadow + i * shadow_stride
+// (8 = table4, 16 = the student half of a paired table8) in the same pass; the gradient is zeroed.
+S3D_API int s3d_ngp_adam_tables(float *table_sigma, float *table_color, float *grad4, float *exp_avg4, float *exp_avg_sq4, void *shadow,
+                                uint32_t shadow_stride, uint64_t n_entries, float lr, float beta1, float beta2, float eps, uint32_t step,
+                                float grad_scale, void *stream) {
     if (n_entries == 0) return 0;
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     k_adam_tables<<<(unsigned)div_up((size_t)n_entries, (size_t)256), 256, 0, as_stream(stream)>>>(
-        (float2 *)table_sigma, (float2 *)table_color, (float4 *)grad4, (float4 *)exp_avg4, (float4 *)exp_avg_sq4, (uint2 *)table4, (size_t)n_entries,
+        (float2 *)table_sigma, (float2 *)table_color, (float4 *)grad4, (float4 *)exp_avg4, (float4 *)exp_avg_sq4, (uint8_t *)shadow, shadow_stride, (size_t)n_entries,
         (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps, grad_scale);
     S3D_RETURN_LAST();
 }

@@ -130,6 +130,9 @@ __global__ void k_packbits(const float *__restrict__ grid, uint32_t N, float thr
 // marching
 // ---------------------------------------------------------------------------------------
 
+constexpr uint32_t kBitmapWords = 36;                       // 35 x 32 lattice bits + 1 flag word per ray
+constexpr uint32_t kBitmapBits = (kBitmapWords - 1) * 32;    // 1120 >= 1024 * bound + 1 lattice steps for bound <= 1
+
 struct MarchCfg {
     float bound, dt_gamma, dt_min, dt_max, rH, H3f, Hf, Hm1f, halfH;
     uint32_t C, H;
@@ -189,8 +192,9 @@ __device__ __forceinline__ float step_len(const MarchCfg &c, float t) {
 
 // One visit of the marching loop (raymarching.cu:359-400).  Occupied: returns true with the sample
 // position and dt (caller advances t).  Empty: advances t along the step lattice past the voxel.
+template <bool COUNT_LATTICE = false>
 __device__ __forceinline__ bool march_visit(const MarchCfg &c, const Ray &r, float &t, float &x, float &y, float &z,
-                                            float &dt) {
+                                            float &dt, uint32_t *lattice_k = nullptr) {
     x = clampf(__fmaf_rn(t, r.dx, r.ox), -c.bound, c.bound);
     y = clampf(__fmaf_rn(t, r.dy, r.oy), -c.bound, c.bound);
     z = clampf(__fmaf_rn(t, r.dz, r.oz), -c.bound, c.bound);
@@ -212,7 +216,7 @@ __device__ __forceinline__ bool march_visit(const MarchCfg &c, const Ray &r, flo
     const float ty = exit_dist(c, ny, r.sy, mip_bound, y, r.rdy);
     const float tz = exit_dist(c, nz, r.sz, mip_bound, z, r.rdz);
     const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
-    do { t = __fadd_rn(t, step_len(c, t)); } while (t < tt);
+    do { t = __fadd_rn(t, step_len(c, t)); if (COUNT_LATTICE) (*lattice_k)++; } while (t < tt);
     return false;
 }
 
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(128)
 k_march_count(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
               float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
               const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
-              int *__restrict__ rays, uint32_t *__restrict__ block_sums) {
+              int *__restrict__ rays, uint32_t *__restrict__ block_sums, uint32_t *__restrict__ bitmap) {
     __shared__ uint32_t s_warp[4];
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t num = 0;
@@ -235,8 +239,29 @@ k_march_count(const float *__restrict__ rays_o, const float *__restrict__ rays_d
         const float far = fars[n];
         float t = perturbed_start(c, nears[n], noises ? noises[n] : 0.0f);
         float x, y, z, dt;
-        while (t < far && num < max_steps) {
-            if (march_visit(c, r, t, x, y, z, dt)) { num++; t = __fadd_rn(t, dt); }
+        if (bitmap) {
+            // also record WHICH points of the ray's step lattice t_{k+1} = t_k + dt(t_k) are samples: the write pass then
+            // replays the lattice (one FADD per step) instead of repeating the voxel walk
+            uint32_t *bm = bitmap + (size_t)n * kBitmapWords;
+            uint32_t k = 0, word = 0, widx = 0;
+            bool overflow = false;
+            while (t < far && num < max_steps) {
+                const uint32_t k0 = k;
+                if (march_visit<true>(c, r, t, x, y, z, dt, &k)) {
+                    if (k0 < kBitmapBits) {
+                        const uint32_t wi = k0 >> 5;
+                        while (widx < wi) { bm[widx++] = word; word = 0; }
+                        word |= 1u << (k0 & 31);
+                    } else overflow = true;
+                    num++; t = __fadd_rn(t, dt); k++;
+                }
+            }
+            while (widx < kBitmapWords - 1) { bm[widx++] = word; word = 0; }
+            bm[kBitmapWords - 1] = overflow ? 0xFFFFFFFFu : 0u;   // last word = "lattice too long, re-walk this ray"
+        } else {
+            while (t < far && num < max_steps) {
+                if (march_visit(c, r, t, x, y, z, dt)) { num++; t = __fadd_rn(t, dt); }
+            }
         }
         rays[(size_t)n * 3] = (int)n;
         rays[(size_t)n * 3 + 2] = (int)num;
@@ -335,6 +360,55 @@ k_march_write(const float *__restrict__ rays_o, const float *__restrict__ rays_d
             *reinterpret_cast<float2 *>(pl) = make_float2(dt, __fsub_rn(t, last_t));
             last_t = t;
             px += 3; pd += 3; pl += 2; step++;
+        }
+    }
+}
+
+// pass 2 (bitmap variant): replay the step lattice and emit the recorded samples -- no voxel lookups, no DDA
+__global__ void __launch_bounds__(128)
+k_march_write_bitmap(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
+                     float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                     const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
+                     const int *__restrict__ rays, const uint32_t *__restrict__ bitmap, float *__restrict__ xyzs,
+                     float *__restrict__ dirs, float *__restrict__ deltas) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const uint32_t off = (uint32_t)rays[(size_t)n * 3 + 1], num = (uint32_t)rays[(size_t)n * 3 + 2];
+    if (num == 0 || off + num > M) return;
+    const MarchCfg c = make_cfg(grid, bound, dt_gamma, max_steps, C, H);
+    const Ray r = load_ray(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
+    const float far = fars[n];
+    float t = perturbed_start(c, nears[n], noises ? noises[n] : 0.0f);
+    float last_t = t, x, y, z, dt;
+    float *px = xyzs + (size_t)off * 3, *pd = dirs + (size_t)off * 3, *pl = deltas + (size_t)off * 2;
+    const uint32_t *bm = bitmap + (size_t)n * kBitmapWords;
+    uint32_t step = 0;
+    if (bm[kBitmapWords - 1] != 0u) {   // lattice longer than the bitmap: walk the voxels again for this ray
+        while (t < far && step < num) {
+            if (march_visit(c, r, t, x, y, z, dt)) {
+                px[0] = x; px[1] = y; px[2] = z; pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+                t = __fadd_rn(t, dt);
+                *reinterpret_cast<float2 *>(pl) = make_float2(dt, __fsub_rn(t, last_t));
+                last_t = t; px += 3; pd += 3; pl += 2; step++;
+            }
+        }
+        return;
+    }
+    for (uint32_t w = 0; w < kBitmapWords - 1 && step < num; w++) {
+        const uint32_t bits = __ldg(bm + w);
+#pragma unroll 4
+        for (uint32_t b = 0; b < 32; b++) {
+            dt = step_len(c, t);
+            if ((bits >> b) & 1u) {
+                x = clampf(__fmaf_rn(t, r.dx, r.ox), -c.bound, c.bound);
+                y = clampf(__fmaf_rn(t, r.dy, r.oy), -c.bound, c.bound);
+                z = clampf(__fmaf_rn(t, r.dz, r.oz), -c.bound, c.bound);
+                px[0] = x; px[1] = y; px[2] = z; pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+                const float tn = __fadd_rn(t, dt);
+                *reinterpret_cast<float2 *>(pl) = make_float2(dt, __fsub_rn(tn, last_t));
+                last_t = tn; px += 3; pd += 3; pl += 2; step++;
+            }
+            t = __fadd_rn(t, dt);
         }
     }
 }
@@ -555,12 +629,12 @@ S3D_API int s3d_packbits(const float *grid, uint32_t N, float density_thresh, ui
 namespace {
 int march_count_scan(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma, uint32_t max_steps,
                      uint32_t N, uint32_t C, uint32_t H, const float *nears, const float *fars, const float *noises, int *rays,
-                     int *counter, cudaStream_t st) {
+                     int *counter, cudaStream_t st, uint32_t *bitmap = nullptr) {
     const uint32_t nb = div_up(N, 128u);
     uint32_t *block_sums = nullptr;
     cudaError_t e = cudaMallocAsync(&block_sums, (size_t)nb * sizeof(uint32_t), st);
     if (e != cudaSuccess) return (int)e;
-    k_march_count<<<nb, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, block_sums);
+    k_march_count<<<nb, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, block_sums, bitmap);
     k_march_scan<<<1, 1024, 0, st>>>(block_sums, nb, N, counter);
     k_march_offsets<<<nb, 128, 0, st>>>(rays, N, block_sums);
     e = cudaPeekAtLastError();
@@ -576,10 +650,18 @@ S3D_API int s3d_march_rays_train(const float *rays_o, const float *rays_d, const
     if (N == 0) return 0;
     if (C == 0 || H == 0 || max_steps == 0) return S3D_EINVAL;
     cudaStream_t st = as_stream(stream);
-    if (int rc = march_count_scan(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, st)) return rc;
-    k_march_write<<<div_up(N, 128u), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears,
-                                                    fars, noises, rays, xyzs, dirs, deltas);
-    S3D_RETURN_LAST();
+    // the count pass records the sample positions on the ray's step lattice; the write pass replays the lattice
+    uint32_t *bitmap = nullptr;
+    cudaError_t e = cudaMallocAsync(&bitmap, (size_t)N * kBitmapWords * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return (int)e;
+    int rc = march_count_scan(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, st, bitmap);
+    if (rc == 0) {
+        k_march_write_bitmap<<<div_up(N, 128u), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears,
+                                                               fars, noises, rays, bitmap, xyzs, dirs, deltas);
+        rc = (int)cudaPeekAtLastError();
+    }
+    cudaFreeAsync(bitmap, st);
+    return rc;
 }
 
 // Two-phase variant of the same op for callers that want an exactly-sized sample buffer: phase 1 counts and

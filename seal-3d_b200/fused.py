@@ -49,6 +49,8 @@ class FusedNGP:
             self._w_off.append((off, k))
             off += k
         self.table4 = torch.empty(self.N, 4, dtype=torch.float16, device=self.dev)
+        # where the kernels read / the Adam kernel writes this model's fp16 entries: (tensor, byte offset, byte stride)
+        self._tbl, self._tbl_off, self._tbl_stride = self.table4, 0, 8
         self.sync_from_module()
         self.trainable = trainable
         if trainable:
@@ -72,6 +74,13 @@ class FusedNGP:
         _lib.call("s3d_ngp_interleave_tables", enc.embeddings.detach(), encc.embeddings.detach(), self.table4, self.N)
         _lib.call("s3d_cast_f32_to_f16", self.mlp32, self.mlp16, self.n_mlp)
 
+    def _table_ptr(self):
+        return self._tbl.data_ptr() + self._tbl_off
+
+    def use_paired_table(self, table8, half):
+        """read / refresh this model's entries inside a paired table [N, 8] fp16 (half 0 = teacher, 1 = student)"""
+        self._tbl, self._tbl_off, self._tbl_stride = table8, 8 * half, 16
+
     def _w16(self):
         return [self.mlp16[o:] for o, _ in self._w_off]
 
@@ -82,7 +91,7 @@ class FusedNGP:
     def encode(self, xyz, sigma_only=False):
         M = xyz.shape[0]
         feats = torch.empty(M, 64, dtype=torch.float16, device=self.dev)
-        _lib.call("s3d_ngp_encode", xyz, M, self.bound, self.table4, self.offsets, self.L, self.S, self.H, feats, int(sigma_only))
+        _lib.call("s3d_ngp_encode", xyz, M, self.bound, self._table_ptr(), self._tbl_stride, self.offsets, self.L, self.S, self.H, feats, int(sigma_only))
         return feats
 
     def mlp_forward(self, feats, dirs, sigma_only=False, want_geo=False):
@@ -101,6 +110,20 @@ class FusedNGP:
         feats = self.encode(xyz)
         sigma, rgb, _ = self.mlp_forward(feats, dirs)
         return sigma, rgb, feats
+
+    def field(self, xyz, dirs):
+        """drop-in for NeRFRenderer._field (includes the Seal proxy hooks of the wrapped module)"""
+        m = self.model
+        mx, md, mask = m._map_samples(xyz, dirs)
+        sigma, rgb, _ = self.forward(mx, md)
+        if mask is not None:
+            rgb = m._map_colors(mx, md, rgb, mask)
+        return sigma, rgb
+
+    @torch.no_grad()
+    def render_image(self, rays_o, rays_d, **kwargs):
+        """single-pass full-image render through the fused field (what proxy_dataset / evaluation need)"""
+        return self.model.render_single_pass(rays_o, rays_d, field=self.field, **kwargs)
 
     def density(self, xyz):
         """NeRFNetwork.density (nerf/network.py:130-147): {'sigma', 'geo_feat'} (sigma WITHOUT density_scale, like the module)"""
@@ -122,8 +145,8 @@ class FusedNGP:
     def adam_step(self, lr, grad_scale=1.0, beta1=0.9, beta2=0.99, eps=1e-15, train_mlp=True):
         enc, encc = self.model.encoder, self.model.encoder_color
         self.step_tables += 1
-        _lib.call("s3d_ngp_adam_tables", enc.embeddings.data, encc.embeddings.data, self.grad4, self.m4, self.v4, self.table4, self.N,
-                  float(lr), beta1, beta2, eps, self.step_tables, float(grad_scale))
+        _lib.call("s3d_ngp_adam_tables", enc.embeddings.data, encc.embeddings.data, self.grad4, self.m4, self.v4, self._table_ptr(), self._tbl_stride,
+                  self.N, float(lr), beta1, beta2, eps, self.step_tables, float(grad_scale))
         if train_mlp:
             self.step_mlp += 1
             _lib.call("s3d_adam_step", self.mlp32, self.gmlp, self.m_mlp, self.v_mlp, self.mlp16, self.n_mlp, float(lr), beta1, beta2, eps,
@@ -147,6 +170,12 @@ class FusedDistillTrainer:
         self.max_steps, self.dt_gamma, self.world_size, self.update_interval = max_steps, dt_gamma, world_size, update_interval
         self.loss_buf = torch.zeros(2, dtype=torch.float32, device=self.S.dev)
         self.global_step = 0
+        self.table8 = None
+        if self.T is not None and self.T.N == self.S.N and torch.equal(self.T.offsets, self.S.offsets):
+            # teacher and student share the level geometry: pair their fp16 tables so one 128-bit load serves both
+            self.table8 = torch.empty(self.S.N, 8, dtype=torch.float16, device=self.S.dev)
+            _lib.call("s3d_ngp_pair_tables", self.T.table4, self.S.table4, self.table8, self.S.N)
+            self.S.use_paired_table(self.table8, 1)
 
     def _scale(self, units):
         return float(self.loss_scale) if self.loss_scale is not None else 32.0 * float(units)
@@ -192,24 +221,40 @@ class FusedDistillTrainer:
         self.S.backward(xyzs, dirs, feats, g_sig, g_rgb)
         return self.loss_buf, scale
 
-    def teacher_targets(self, xyzs, dirs, deltas, rays):
-        """teacher on the student's samples: proxy map -> field -> colour edit -> composite (+ background)"""
+    def _teacher_composite(self, mx, md, mask, feats_t, deltas, rays):
         t = self.teacher
-        mx, md, mask = t._map_samples(xyzs, dirs)
-        sig_t, rgb_t, _ = self.T.forward(mx, md)
+        sig_t, rgb_t, _ = self.T.mlp_forward(feats_t, md)
         if mask is not None and t.seal_mapper is not None and t.seal_mapper.has_color_edit():
             t.seal_mapper.map_color_(rgb_t, mask)
         ws_t, depth_t, img_t = self._composite(sig_t, rgb_t, deltas, rays)
         img_t.add_((1 - ws_t).unsqueeze(-1) * self.bg_color)
         return img_t, depth_t
 
+    def teacher_targets(self, xyzs, dirs, deltas, rays):
+        """teacher on the student's samples: proxy map -> field -> colour edit -> composite (+ background)"""
+        mx, md, mask = self.teacher._map_samples(xyzs, dirs)
+        feats_t = self.T.encode(mx.contiguous().float())
+        return self._teacher_composite(mx, md.contiguous().float(), mask, feats_t, deltas, rays)
+
     @torch.no_grad()
     def distill_step(self, rays_o, rays_d, perturb=True, force_all_rays=False):
         self._maybe_update_grid()
         rays_o, rays_d = rays_o.view(-1, 3), rays_d.view(-1, 3)
         xyzs, dirs, deltas, rays = self._march(rays_o, rays_d, perturb, force_all_rays)
-        img_t, depth_t = self.teacher_targets(xyzs, dirs, deltas, rays)
-        sig_s, rgb_s, feats = self.S.forward(xyzs, dirs)
+        if self.table8 is not None:
+            # one gather pass for both models (moved samples take a second gather for the teacher)
+            M = xyzs.shape[0]
+            mx, md, mask = self.teacher._map_samples(xyzs, dirs)
+            feats_t = torch.empty(M, 64, dtype=torch.float16, device=xyzs.device)
+            feats = torch.empty(M, 64, dtype=torch.float16, device=xyzs.device)
+            m8 = mask.view(torch.uint8) if mask is not None else None
+            _lib.call("s3d_ngp_encode_pair", xyzs, mx if mask is not None else None, m8, M, self.S.bound, self.table8, self.S.offsets, self.S.L,
+                      self.S.S, self.S.H, feats_t, feats)
+            img_t, depth_t = self._teacher_composite(mx, md, mask, feats_t, deltas, rays)
+            sig_s, rgb_s, _ = self.S.mlp_forward(feats, dirs)
+        else:
+            img_t, depth_t = self.teacher_targets(xyzs, dirs, deltas, rays)
+            sig_s, rgb_s, feats = self.S.forward(xyzs, dirs)
         loss, scale = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, img_t, depth_t)
         self._reduce_and_step(scale)
         return loss

@@ -114,6 +114,27 @@ class NeRFRenderer(nn.Module):
         return results
 
     @torch.no_grad()
+    def render_single_pass(self, rays_o, rays_d, dt_gamma=0, bg_color=1, max_steps=1024, T_thresh=1e-4, field=None, **kwargs):
+        """Full-image / evaluation render WITHOUT the host loop of nerf/renderer.py:335-372: the reference marches
+        <= 8 steps per alive ray per iteration and compacts the alive list on the host every iteration (a boolean-mask
+        gather = a device sync), which exists to skip the field for samples behind an opaque surface.  Here every sample
+        of every ray is generated once (count -> scan -> write), the field runs once over all of them and the training
+        compositor applies the same early termination, so the image equals the loop's image (same samples, same
+        T_thresh); depth is converted to the eval convention (absolute t: + near * weights_sum, see
+        raymarching.cu:845,872).  `field(xyzs, dirs) -> (sigmas, rgbs)` defaults to this module's own field."""
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3)
+        rays_d = rays_d.contiguous().view(-1, 3)
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_infer, self.min_near)
+        xyzs, dirs, deltas, rays = raymarching.march_rays_train(rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size,
+                                                               nears, fars, None, -1, False, 128, True, dt_gamma, max_steps)
+        sigmas, rgbs = (field or self._field)(xyzs, dirs)
+        weights_sum, depth, image = raymarching.composite_rays_train(sigmas.float(), rgbs.float(), deltas, rays, T_thresh)
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        depth = depth + torch.where(weights_sum > 0, nears, torch.zeros_like(nears)) * weights_sum
+        return {"image": image.view(*prefix, 3), "depth": depth.view(*prefix), "weights_sum": weights_sum.view(*prefix)}
+
+    @torch.no_grad()
     def update_extra_state(self, decay=0.95, S=128, seed=None):
         """nerf/renderer.py:445-538: full sweep for the first 16 calls, then H^3/4 uniform + H^3/4 occupied cells;
         EMA-max into density_grid, mean density, packbits with min(mean, density_thresh), mean_count from the ring."""

@@ -125,6 +125,22 @@ def test_fused_scatter_matches_oracle(scene):
         assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max() + 1e-7, (name, np.abs(a - b).max(), np.abs(b).max())
 
 
+def test_fused_full_image_render_matches_loop(scene):
+    """proxy_dataset-style teacher render of 20 000 pixels of one view: fused single pass vs the reference-shaped eval loop"""
+    from seal3d_b200.fused import FusedNGP
+    t, s, _, _ = _networks(scene, hsv=[0.3, 0.0, 0.0])
+    o, d = scene["synth"].full_image_rays(3)
+    sel = np.random.default_rng(0).choice(o.shape[0], 20000, replace=False)
+    o, d = o[sel], d[sel]
+    t.eval()
+    with torch.no_grad():
+        loop = t.render(to(o)[None], to(d)[None], perturb=False, bg_color=1, T_thresh=1e-4)
+    fast = FusedNGP(t).render_image(to(o)[None], to(d)[None], bg_color=1, T_thresh=1e-4)
+    # fp16 tables / activations in the fused field vs the fp32 op-by-op field
+    np.testing.assert_allclose(npy(fast["image"]), npy(loop["image"]), rtol=0, atol=1.5e-2)
+    np.testing.assert_allclose(npy(fast["depth"]), npy(loop["depth"]), rtol=0, atol=3e-2)
+
+
 def test_fused_adam_tables_matches_torch():
     from seal3d_b200 import _lib
     n = 10007
@@ -141,7 +157,7 @@ def test_fused_adam_tables_matches_torch():
         ref.grad = gr.clone()
         opt.step()
         g4.copy_(gr * 4)
-        _lib.call("s3d_ngp_adam_tables", ps, pc, g4, m4, v4, t4, n, 1e-2, 0.9, 0.99, 1e-15, step, 0.25)
+        _lib.call("s3d_ngp_adam_tables", ps, pc, g4, m4, v4, t4, 8, n, 1e-2, 0.9, 0.99, 1e-15, step, 0.25)
         assert not g4.any()
     np.testing.assert_allclose(npy(torch.cat([ps, pc], 1)), npy(ref), rtol=1e-5, atol=1e-6)
     assert torch.equal(t4, torch.cat([ps, pc], 1).half())

@@ -109,6 +109,11 @@ def test_march_rays_train_bit_exact(scene, dt_gamma, perturb):
     assert x.shape[0] % 128 == 0 and x.shape[0] >= M
     assert np.array_equal(npy(x)[:M], x0[:M]) and np.array_equal(npy(dd)[:M], d0[:M]) and np.array_equal(npy(l)[:M], l0[:M])
     assert not npy(x)[M:].any()
+    # the single-call (budgeted) entry records the samples on the step lattice in the count pass and replays it: same bits
+    xb, db, lb, rb = rm().march_rays_train(to(o), to(d), 1.0, to(bits), 1, 128, to(n0), to(f0), None, M + 1000, perturb, 128, False,
+                                           dt_gamma, 1024, noises=to(noises))
+    assert np.array_equal(npy(rb), r0) and np.array_equal(npy(xb)[:M], x0[:M]) and np.array_equal(npy(db)[:M], d0[:M])
+    assert np.array_equal(npy(lb)[:M], l0[:M]) and not npy(xb)[M:].any()
     # vs the reference kernel: slot order is atomic-order dependent there -> compare the canonical per-ray view
     ref = refext.load("raymarching")
     Mr = M + 128
@@ -689,6 +694,13 @@ def test_teacher_render_and_hack_bitfield(scene):
     nears, _ = _rm.near_far_from_aabb(to(o), to(d), t.aabb_infer, t.min_near)
     np.testing.assert_allclose(npy(out["depth"])[0], npy(out2["depth"])[0] + npy(nears) * npy(out2["weights_sum"]), rtol=2e-3, atol=2e-3)
     assert npy(out["image"]).min() >= 0 and npy(out["image"]).max() <= 1 + 1e-5
+    # single-pass evaluation render (no host loop) == the reference-shaped eval loop
+    t.eval()
+    sp = t.render_single_pass(to(o)[None], to(d)[None], bg_color=1, T_thresh=1e-4)
+    # the eval compositor accumulates one more sample than the train compositor at termination (it tests the
+    # transmittance BEFORE the sample, raymarching.cu:868,882 vs :554-557): a weight of at most T_thresh
+    np.testing.assert_allclose(npy(sp["image"]), npy(out["image"]), rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose(npy(sp["depth"]), npy(out["depth"]), rtol=1e-4, atol=1e-3)
 
 
 def test_update_extra_state_and_distill_steps(scene):
