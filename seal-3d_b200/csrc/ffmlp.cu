@@ -437,7 +437,7 @@ S3D_API int s3d_ffmlp_backward(const void *grad, const void *inputs, const void 
     if (64 * (1 + 1 + (num_layers - 1) + in_blocks) > 512) return S3D_ENOTSUP;
     const size_t nW = (size_t)hidden_dim * input_dim + (size_t)hidden_dim * hidden_dim * (num_layers - 1) + (size_t)output_dim * hidden_dim;
     float *gw32 = nullptr;
-    cudaError_t e = cudaMallocAsync(&gw32, nW * sizeof(float), st);
+    cudaError_t e = scratch_alloc((void **)&gw32, nW * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
     cudaMemsetAsync(gw32, 0, nW * sizeof(float), st);
     const size_t smem = 1024 + kTileBytes + (size_t)in_blocks * (kTileBytes + kWTileBytes) + (size_t)(num_layers - 1) * kWTileBytes + kOTileBytes;

@@ -159,7 +159,7 @@ __device__ __forceinline__ void acc4(const uint2 v, float w, float &a0, float &a
     a0 = __fmaf_rn(w, a.x, a0); a1 = __fmaf_rn(w, a.y, a1); a2 = __fmaf_rn(w, b.x, a2); a3 = __fmaf_rn(w, b.y, a3);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_ngp_encode_pair(const float *__restrict__ xyz, const float *__restrict__ xyz_teacher, const uint8_t *__restrict__ mask, uint32_t M,
                   float bound, const uint4 *__restrict__ table8, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H,
                   __half *__restrict__ feats_teacher, __half *__restrict__ feats_student) {
@@ -389,8 +389,30 @@ __device__ __forceinline__ void masked_to_tile(uint32_t t_row, uint32_t hf, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// MLP forward
+// MLP kernels: 9 warps.  Warps 0-7 (two warpgroups) own the rows / column halves of the tiles and run the epilogues;
+// warp 8 is the MMA issuer: it allocates TMEM, builds the descriptors and issues every tcgen05.mma, so that descriptor
+// arithmetic and the (asynchronous) weight-gradient MMAs never sit on the critical path of the epilogue warps.
+// Every round:   epilogue warps write the operand tile -> fence -> __syncthreads -> issuer issues + commits ->
+//                epilogue warps wait on the mbarrier -> read the accumulator.
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t kMlpThreads = 288;
+constexpr uint32_t kIssuerWarp = 8;
+
+__device__ __forceinline__ void epi_publish() {   // epilogue warps: my tile writes are done
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+}
+__device__ __forceinline__ void iss_acquire() {   // issuer warp: all tile writes of this round are visible
+    __syncthreads();
+    fence_after_sync();
+}
+__device__ __forceinline__ void tile_end_sync() {  // both roles: accumulator reads done, tiles may be overwritten
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+}
+
 struct FwdArgs {
     const __half *feats;
     const float *dirs;
@@ -401,7 +423,7 @@ struct FwdArgs {
     int sigma_only;
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kMlpThreads)
 k_ngp_mlp_fwd(const FwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -409,79 +431,87 @@ k_ngp_mlp_fwd(const FwdArgs a) {
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *tF = smem, *tT = tF + kTileBytes, *tWs0 = tT + kTileBytes, *tWc0 = tWs0 + kWTile, *tWc1 = tWc0 + kWTile,
             *tWs1 = tWc1 + kWTile, *tWc2 = tWs1 + kOTile;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, r = tid & 127, hf = tid >> 7;
-    if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 64);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, r = tid & 127, hf = (tid >> 7) & 1u;
+    const bool is_issuer = (warp == kIssuerWarp);
+    if (is_issuer) tmem_alloc(smem_u32(&s_tmem), 64);
     if (tid == 0) mbar_init(smem_u32(&s_mbar), 1);
     load_weights(tWs0, tWs1, tWc0, tWc1, tWc2, a.w);
     sync_tiles();
     const uint32_t tmem = s_tmem, t_row = tmem + (((warp & 3u) * 32u) << 16);
     Issue is{smem_u32(&s_mbar), 0};
-    const bool issuer = (tid == 0);
     const uint32_t aF = smem_u32(tF), aT = smem_u32(tT);
     const uint32_t id64 = make_idesc(128, 64, false, false), id16 = make_idesc(128, 16, false, false);
 
-    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const uint32_t row = tile * kRows + r;
-        const bool in_range = row < a.M;
-        load_feat_half(tF, a.feats, row, r, hf, in_range);
-        sync_tiles();
-        // sigma layer 0: [128 x 32] . W_s0^T  (2 K-steps over the sigma features)
-        if (issuer) { for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, k), desc_kmajor(smem_u32(tWs0), k), id64, k > 0); mma_commit(is.mbar); }
-        is.wait();
-        relu_to_tile(t_row, hf, tT, r);
-        sync_tiles();
-        // sigma layer 1: [128 x 64] . W_s1^T -> 16
-        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(smem_u32(tWs1), k), id16, k > 0); mma_commit(is.mbar); }
-        is.wait();
-        if (hf == 0) {
-            float h2[16];
-            tmem_ld16(t_row, h2);
-            if (in_range) {
-                a.sigma[row] = a.density_scale * __expf(h2[0]);
-                if (a.geo) for (int i = 0; i < 15; i++) a.geo[(size_t)row * 15 + i] = h2[1 + i];
+    if (is_issuer) {
+        const bool lead = (tid & 31) == 0;
+        const uint32_t aWs0 = smem_u32(tWs0), aWs1 = smem_u32(tWs1), aWc0 = smem_u32(tWc0), aWc1 = smem_u32(tWc1), aWc2 = smem_u32(tWc2);
+        for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            iss_acquire();   // features loaded
+            if (lead) { for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, k), desc_kmajor(aWs0, k), id64, k > 0); mma_commit(is.mbar); }
+            iss_acquire();   // H1 written
+            if (lead) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(aWs1, k), id16, k > 0); mma_commit(is.mbar); }
+            if (a.sigma_only) { tile_end_sync(); continue; }
+            iss_acquire();   // [SH | geo] written
+            if (lead) {
+                for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, 2 + k), desc_kmajor(aWc0, k), id64, k > 0);
+                for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(aWc0, 2 + k), id64, true);
+                mma_commit(is.mbar);
             }
-            if (!a.sigma_only) {
-                // colour input, second half: [SH16 | geo15 | 0] -> columns 0..31 of the scratch tile
-                float g[32];
-                float dx = 0.f, dy = 0.f, dz = 0.f;
-                if (in_range) { dx = a.dirs[(size_t)row * 3]; dy = a.dirs[(size_t)row * 3 + 1]; dz = a.dirs[(size_t)row * 3 + 2]; }
-                sh4(dx, dy, dz, g);
+            iss_acquire();   // C1 written
+            if (lead) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(aWc1, k), id64, k > 0); mma_commit(is.mbar); }
+            iss_acquire();   // C2 written
+            if (lead) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(aWc2, k), id16, k > 0); mma_commit(is.mbar); }
+            tile_end_sync();
+        }
+    } else {
+        for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            const uint32_t row = tile * kRows + r;
+            const bool in_range = row < a.M;
+            load_feat_half(tF, a.feats, row, r, hf, in_range);
+            epi_publish();
+            is.wait();       // sigma layer 0 done
+            relu_to_tile(t_row, hf, tT, r);
+            epi_publish();
+            is.wait();       // sigma layer 1 done (16 outputs)
+            if (hf == 0) {
+                float h2[16];
+                tmem_ld16(t_row, h2);
+                if (in_range) {
+                    a.sigma[row] = a.density_scale * __expf(h2[0]);
+                    if (a.geo) for (int i = 0; i < 15; i++) a.geo[(size_t)row * 15 + i] = h2[1 + i];
+                }
+                if (!a.sigma_only) {
+                    float g[32];
+                    float dx = 0.f, dy = 0.f, dz = 0.f;
+                    if (in_range) { dx = a.dirs[(size_t)row * 3]; dy = a.dirs[(size_t)row * 3 + 1]; dz = a.dirs[(size_t)row * 3 + 2]; }
+                    sh4(dx, dy, dz, g);
 #pragma unroll
-                for (int i = 0; i < 15; i++) g[16 + i] = h2[1 + i];
-                g[31] = 0.0f;
-                store_half_row(tT, r, 0, g);
+                    for (int i = 0; i < 15; i++) g[16 + i] = h2[1 + i];
+                    g[31] = 0.0f;
+                    store_half_row(tT, r, 0, g);   // colour input, second half: [SH16 | geo15 | 0] -> scratch cols 0..31
+                }
             }
-        }
-        if (a.sigma_only) { fence_before_sync(); __syncthreads(); fence_after_sync(); continue; }
-        sync_tiles();
-        // colour layer 0: K-steps 0,1 = colour-grid feats (feature tile cols 32..63), K-steps 2,3 = [SH | geo] (scratch cols 0..31)
-        if (issuer) {
-            for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, 2 + k), desc_kmajor(smem_u32(tWc0), k), id64, k > 0);
-            for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(smem_u32(tWc0), 2 + k), id64, true);
-            mma_commit(is.mbar);
-        }
-        is.wait();
-        relu_to_tile(t_row, hf, tT, r);
-        sync_tiles();
-        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(smem_u32(tWc1), k), id64, k > 0); mma_commit(is.mbar); }
-        is.wait();
-        relu_to_tile(t_row, hf, tT, r);
-        sync_tiles();
-        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(smem_u32(tWc2), k), id16, k > 0); mma_commit(is.mbar); }
-        is.wait();
-        if (hf == 0) {
-            float o[16];
-            tmem_ld16(t_row, o);
-            if (in_range) {
+            if (a.sigma_only) { tile_end_sync(); continue; }
+            epi_publish();
+            is.wait();       // colour layer 0 done
+            relu_to_tile(t_row, hf, tT, r);
+            epi_publish();
+            is.wait();       // colour layer 1 done
+            relu_to_tile(t_row, hf, tT, r);
+            epi_publish();
+            is.wait();       // colour layer 2 done (3 outputs)
+            if (hf == 0) {
+                float o[16];
+                tmem_ld16(t_row, o);
+                if (in_range) {
 #pragma unroll
-                for (int c = 0; c < 3; c++) a.rgb[(size_t)row * 3 + c] = 1.0f / (1.0f + __expf(-o[c]));
+                    for (int c = 0; c < 3; c++) a.rgb[(size_t)row * 3 + c] = 1.0f / (1.0f + __expf(-o[c]));
+                }
             }
+            tile_end_sync();
         }
-        fence_before_sync();
-        __syncthreads();
-        fence_after_sync();
     }
-    if (warp == 0) tmem_dealloc(tmem, 64);
+    if (is_issuer) tmem_dealloc(tmem, 64);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -501,10 +531,11 @@ struct BwdArgs {
 
 // TMEM columns: [0,64) activation accumulator | [64,128) dWc2 | [128,192) dWc1 | [192,256) dC1^T.F | [256,320) dC1^T.G | [320,384) dWs1 |
 // [384,448) dH1^T.F.  Every weight-gradient MMA is a full 64 x 64 (M = 64, N = 64) block; the flush picks the valid columns.
-// Per round the data-gradient MMAs are issued (and committed) FIRST and the weight-gradient MMAs after the commit, so the
-// latter run on the tensor pipe while the threads are already in the epilogue; the gradient tiles X / Y alternate, so the
-// epilogue never writes a tile the in-flight weight-gradient MMAs read.
-__global__ void __launch_bounds__(256)
+// Per round the issuer sends the data-gradient MMAs first and commits, then the weight-gradient MMAs, which run on the
+// tensor pipe while the epilogue warps already work on the data gradient; the gradient tiles X / Y alternate, so an
+// epilogue never writes a tile the in-flight weight-gradient MMAs read.  In the last round the weight gradient goes
+// first (the commit must cover it: the feature tile is overwritten by the next tile's loads).
+__global__ void __launch_bounds__(kMlpThreads)
 k_ngp_mlp_bwd(const BwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -513,187 +544,201 @@ k_ngp_mlp_bwd(const BwdArgs a) {
     uint8_t *tF = smem, *tH1 = tF + kTileBytes, *tG = tH1 + kTileBytes, *tC1 = tG + kTileBytes, *tC2 = tC1 + kTileBytes,
             *tX = tC2 + kTileBytes, *tY = tX + kTileBytes, *tWs0 = tY + kTileBytes, *tWc0 = tWs0 + kWTile, *tWc1 = tWc0 + kWTile,
             *tWs1 = tWc1 + kWTile, *tWc2 = tWs1 + kOTile;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, r = tid & 127, hf = tid >> 7;
-    if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, r = tid & 127, hf = (tid >> 7) & 1u;
+    const bool is_issuer = (warp == kIssuerWarp);
+    if (is_issuer) tmem_alloc(smem_u32(&s_tmem), 512);
     if (tid == 0) mbar_init(smem_u32(&s_mbar), 1);
     load_weights(tWs0, tWs1, tWc0, tWc1, tWc2, a.w);
     sync_tiles();
     const uint32_t tmem = s_tmem, t_row = tmem + (((warp & 3u) * 32u) << 16);
     Issue is{smem_u32(&s_mbar), 0};
-    const bool issuer = (tid == 0);
-    const uint32_t aF = smem_u32(tF), aH1 = smem_u32(tH1), aG = smem_u32(tG), aC1 = smem_u32(tC1), aC2 = smem_u32(tC2), aX = smem_u32(tX), aY = smem_u32(tY);
-    const uint32_t id64 = make_idesc(128, 64, false, false), id16 = make_idesc(128, 16, false, false);
-    const uint32_t id64t = make_idesc(128, 64, false, true);        // B read MN-major (= W^T)
-    const uint32_t idw64 = make_idesc(64, 64, true, true);
-    const uint32_t accC2 = tmem + 64, accC1 = tmem + 128, accC0f = tmem + 192, accC0g = tmem + 256, accS1 = tmem + 320, accS0 = tmem + 384;
     bool first = true;
 
-    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, first = false) {
-        const uint32_t row = tile * kRows + r;
-        const bool in_range = row < a.M;
-        // ---------------- recompute the forward, keeping every activation tile ----------------
-        load_feat_half(tF, a.feats, row, r, hf, in_range);
-        sync_tiles();
-        if (issuer) { for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, k), desc_kmajor(smem_u32(tWs0), k), id64, k > 0); mma_commit(is.mbar); }
-        is.wait();
-        relu_to_tile(t_row, hf, tH1, r);
-        sync_tiles();
-        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aH1, k), desc_kmajor(smem_u32(tWs1), k), id16, k > 0); mma_commit(is.mbar); }
-        is.wait();
-        float h0 = 0.0f;   // sigma logit (kept by warpgroup 0 for the trunc_exp backward)
-        if (hf == 0) {
-            float h2[16], g[32];
-            tmem_ld16(t_row, h2);
-            h0 = h2[0];
-            float dx = 0.f, dy = 0.f, dz = 0.f;
-            if (in_range) { dx = a.dirs[(size_t)row * 3]; dy = a.dirs[(size_t)row * 3 + 1]; dz = a.dirs[(size_t)row * 3 + 2]; }
-            sh4(dx, dy, dz, g);
-#pragma unroll
-            for (int i = 0; i < 15; i++) g[16 + i] = h2[1 + i];
-            g[31] = 0.0f;
-            store_half_row(tG, r, 0, g);
-        } else {
-            zero_half_row(tG, r, 1);
-        }
-        sync_tiles();
-        if (issuer) {
-            for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, 2 + k), desc_kmajor(smem_u32(tWc0), k), id64, k > 0);
-            for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aG, k), desc_kmajor(smem_u32(tWc0), 2 + k), id64, true);
-            mma_commit(is.mbar);
-        }
-        is.wait();
-        relu_to_tile(t_row, hf, tC1, r);
-        sync_tiles();
-        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aC1, k), desc_kmajor(smem_u32(tWc1), k), id64, k > 0); mma_commit(is.mbar); }
-        is.wait();
-        relu_to_tile(t_row, hf, tC2, r);
-        sync_tiles();
-        if (issuer) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aC2, k), desc_kmajor(smem_u32(tWc2), k), id16, k > 0); mma_commit(is.mbar); }
-        is.wait();
-        // ---------------- output gradients -> tX (3 meaningful columns, zero padded) ----------------
-        if (hf == 0) {
-            float o[16], d[32];
-            tmem_ld16(t_row, o);
-#pragma unroll
-            for (int i = 0; i < 32; i++) d[i] = 0.0f;
-            if (in_range) {
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const float sg = 1.0f / (1.0f + __expf(-o[c]));
-                    d[c] = a.g_rgb[(size_t)row * 3 + c] * sg * (1.0f - sg);
+    if (is_issuer) {
+        const bool lead = (tid & 31) == 0;
+        const uint32_t aF = smem_u32(tF), aH1 = smem_u32(tH1), aG = smem_u32(tG), aC1 = smem_u32(tC1), aC2 = smem_u32(tC2), aX = smem_u32(tX), aY = smem_u32(tY);
+        const uint32_t aWs0 = smem_u32(tWs0), aWs1 = smem_u32(tWs1), aWc0 = smem_u32(tWc0), aWc1 = smem_u32(tWc1), aWc2 = smem_u32(tWc2);
+        const uint32_t id64 = make_idesc(128, 64, false, false), id16 = make_idesc(128, 16, false, false);
+        const uint32_t id64t = make_idesc(128, 64, false, true);        // B read MN-major (= W^T)
+        const uint32_t idw64 = make_idesc(64, 64, true, true);
+        const uint32_t accC2 = tmem + 64, accC1 = tmem + 128, accC0f = tmem + 192, accC0g = tmem + 256, accS1 = tmem + 320, accS0 = tmem + 384;
+        const bool tw = a.train_mlp != 0;
+        for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, first = false) {
+            // ---- forward recompute ----
+            iss_acquire();
+            if (lead) { for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, k), desc_kmajor(aWs0, k), id64, k > 0); mma_commit(is.mbar); }
+            iss_acquire();
+            if (lead) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aH1, k), desc_kmajor(aWs1, k), id16, k > 0); mma_commit(is.mbar); }
+            iss_acquire();
+            if (lead) {
+                for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, 2 + k), desc_kmajor(aWc0, k), id64, k > 0);
+                for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aG, k), desc_kmajor(aWc0, 2 + k), id64, true);
+                mma_commit(is.mbar);
+            }
+            iss_acquire();
+            if (lead) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aC1, k), desc_kmajor(aWc1, k), id64, k > 0); mma_commit(is.mbar); }
+            iss_acquire();
+            if (lead) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aC2, k), desc_kmajor(aWc2, k), id16, k > 0); mma_commit(is.mbar); }
+            // ---- backward ----
+            iss_acquire();   // dO in X:  dC2 = dO . Wc2 ;  dWc2 += dO^T . C2
+            if (lead) {
+                mma_f16(tmem, desc_kmajor(aX, 0), desc_mnmajor(aWc2, 0, kOTile), id64t, false);
+                mma_commit(is.mbar);
+                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accC2, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aC2, k, kTileBytes), idw64, !(first && k == 0));
+            }
+            iss_acquire();   // dC2 in Y:  dC1 = dC2 . Wc1 ;  dWc1 += dC2^T . C1
+            if (lead) {
+                for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aY, k), desc_mnmajor(aWc1, k, kWTile), id64t, k > 0);
+                mma_commit(is.mbar);
+                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accC1, desc_mnmajor(aY, k, kTileBytes), desc_mnmajor(aC1, k, kTileBytes), idw64, !(first && k == 0));
+            }
+            iss_acquire();   // dC1 in X:  d[colour feats | SH | geo] = dC1 . Wc0p ;  dWc0 += dC1^T . [F | G]
+            if (lead) {
+                for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aX, k), desc_mnmajor(aWc0, k, kWTile), id64t, k > 0);
+                mma_commit(is.mbar);
+                if (tw) {
+                    for (uint32_t k = 0; k < 8; k++) mma_f16(accC0f, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aF, k, kTileBytes), idw64, !(first && k == 0));
+                    for (uint32_t k = 0; k < 8; k++) mma_f16(accC0g, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aG, k, kTileBytes), idw64, !(first && k == 0));
                 }
             }
-            store_half_row(tX, r, 0, d);
-        } else {
-            zero_half_row(tX, r, 1);
-        }
-        sync_tiles();
-        // dC2 = dO . Wc2 ;  dWc2 += dO^T . C2
-        if (issuer) {
-            mma_f16(tmem, desc_kmajor(aX, 0), desc_mnmajor(smem_u32(tWc2), 0, kOTile), id64t, false);
-            mma_commit(is.mbar);
-            if (a.train_mlp) for (uint32_t k = 0; k < 8; k++) mma_f16(accC2, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aC2, k, kTileBytes), idw64, !(first && k == 0));
-        }
-        is.wait();
-        masked_to_tile(t_row, hf, tC2, tY, r);
-        sync_tiles();
-        // dC1 = dC2 . Wc1 ;  dWc1 += dC2^T . C1
-        if (issuer) {
-            for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aY, k), desc_mnmajor(smem_u32(tWc1), k, kWTile), id64t, k > 0);
-            mma_commit(is.mbar);
-            if (a.train_mlp) for (uint32_t k = 0; k < 8; k++) mma_f16(accC1, desc_mnmajor(aY, k, kTileBytes), desc_mnmajor(aC1, k, kTileBytes), idw64, !(first && k == 0));
-        }
-        is.wait();
-        masked_to_tile(t_row, hf, tC1, tX, r);
-        sync_tiles();
-        // d[colour feats | SH | geo] = dC1 . Wc0p ;  dWc0 += dC1^T . [F | G]
-        if (issuer) {
-            for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aX, k), desc_mnmajor(smem_u32(tWc0), k, kWTile), id64t, k > 0);
-            mma_commit(is.mbar);
-            if (a.train_mlp) {
-                for (uint32_t k = 0; k < 8; k++) mma_f16(accC0f, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aF, k, kTileBytes), idw64, !(first && k == 0));
-                for (uint32_t k = 0; k < 8; k++) mma_f16(accC0g, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aG, k, kTileBytes), idw64, !(first && k == 0));
+            iss_acquire();   // dh2 in Y:  dH1 = dh2 . Ws1 ;  dWs1 += dh2^T . H1
+            if (lead) {
+                mma_f16(tmem, desc_kmajor(aY, 0), desc_mnmajor(aWs1, 0, kOTile), id64t, false);
+                mma_commit(is.mbar);
+                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accS1, desc_mnmajor(aY, k, kTileBytes), desc_mnmajor(aH1, k, kTileBytes), idw64, !(first && k == 0));
             }
-        }
-        is.wait();
-        float dfc[32];   // warpgroup 1: gradient w.r.t. the colour-grid features (dfeats cols 32..63), kept in registers
-        if (hf == 1) {
-            tmem_ld32(t_row, dfc);
-            zero_half_row(tY, r, 1);
-        } else {
-            float v[32], d[32];
-            tmem_ld32(t_row + 32, v);  // cols 32-47 dSH (dropped), 48-62 dgeo
-#pragma unroll
-            for (int i = 0; i < 32; i++) d[i] = 0.0f;
-            if (in_range) d[0] = a.g_sigma[row] * a.density_scale * __expf(fminf(fmaxf(h0, -15.0f), 15.0f));  // trunc_exp backward
-#pragma unroll
-            for (int i = 0; i < 15; i++) d[1 + i] = v[16 + i];
-            store_half_row(tY, r, 0, d);
-        }
-        sync_tiles();
-        // dH1 = dh2 . Ws1 ;  dWs1 += dh2^T . H1
-        if (issuer) {
-            mma_f16(tmem, desc_kmajor(aY, 0), desc_mnmajor(smem_u32(tWs1), 0, kOTile), id64t, false);
-            mma_commit(is.mbar);
-            if (a.train_mlp) for (uint32_t k = 0; k < 8; k++) mma_f16(accS1, desc_mnmajor(aY, k, kTileBytes), desc_mnmajor(aH1, k, kTileBytes), idw64, !(first && k == 0));
-        }
-        is.wait();
-        masked_to_tile(t_row, hf, tH1, tX, r);
-        sync_tiles();
-        // last round: weight gradient FIRST (the commit must cover it: the feature tile is overwritten by the next tile)
-        if (issuer) {
-            if (a.train_mlp) for (uint32_t k = 0; k < 8; k++) mma_f16(accS0, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aF, k, kTileBytes), idw64, !(first && k == 0));
-            for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aX, k), desc_mnmajor(smem_u32(tWs0), k, kWTile), id64t, k > 0);
-            mma_commit(is.mbar);
-        }
-        is.wait();
-        if (hf == 0) {
-            float dfs[32];
-            tmem_ld32(t_row, dfs);
-            if (in_range) {
-                uint4 *dst = reinterpret_cast<uint4 *>(a.dfeats + (size_t)row * 64);
-#pragma unroll
-                for (int i = 0; i < 32; i++) dfs[i] *= a.out_scale;
-#pragma unroll
-                for (uint32_t q = 0; q < 4; q++) dst[q] = pack8(dfs + q * 8);
+            iss_acquire();   // dH1 in X (last round: weight gradient first)
+            if (lead) {
+                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accS0, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aF, k, kTileBytes), idw64, !(first && k == 0));
+                for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aX, k), desc_mnmajor(aWs0, k, kWTile), id64t, k > 0);
+                mma_commit(is.mbar);
             }
-        } else if (in_range) {
-            uint4 *dst = reinterpret_cast<uint4 *>(a.dfeats + (size_t)row * 64) + 4;
-#pragma unroll
-            for (int i = 0; i < 32; i++) dfc[i] *= a.out_scale;
-#pragma unroll
-            for (uint32_t q = 0; q < 4; q++) dst[q] = pack8(dfc + q * 8);
+            tile_end_sync();
         }
-        fence_before_sync();
-        __syncthreads();
-        fence_after_sync();
-    }
+    } else {
+        for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, first = false) {
+            const uint32_t row = tile * kRows + r;
+            const bool in_range = row < a.M;
+            // ---------------- recompute the forward, keeping every activation tile ----------------
+            load_feat_half(tF, a.feats, row, r, hf, in_range);
+            epi_publish();
+            is.wait();
+            relu_to_tile(t_row, hf, tH1, r);
+            epi_publish();
+            is.wait();
+            float h0 = 0.0f;   // sigma logit (kept by warpgroup 0 for the trunc_exp backward)
+            if (hf == 0) {
+                float h2[16], g[32];
+                tmem_ld16(t_row, h2);
+                h0 = h2[0];
+                float dx = 0.f, dy = 0.f, dz = 0.f;
+                if (in_range) { dx = a.dirs[(size_t)row * 3]; dy = a.dirs[(size_t)row * 3 + 1]; dz = a.dirs[(size_t)row * 3 + 2]; }
+                sh4(dx, dy, dz, g);
+#pragma unroll
+                for (int i = 0; i < 15; i++) g[16 + i] = h2[1 + i];
+                g[31] = 0.0f;
+                store_half_row(tG, r, 0, g);
+            } else {
+                zero_half_row(tG, r, 1);
+            }
+            epi_publish();
+            is.wait();
+            relu_to_tile(t_row, hf, tC1, r);
+            epi_publish();
+            is.wait();
+            relu_to_tile(t_row, hf, tC2, r);
+            epi_publish();
+            is.wait();
+            // ---------------- output gradients -> tX (3 meaningful columns, zero padded) ----------------
+            if (hf == 0) {
+                float o[16], d[32];
+                tmem_ld16(t_row, o);
+#pragma unroll
+                for (int i = 0; i < 32; i++) d[i] = 0.0f;
+                if (in_range) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float sg = 1.0f / (1.0f + __expf(-o[c]));
+                        d[c] = a.g_rgb[(size_t)row * 3 + c] * sg * (1.0f - sg);
+                    }
+                }
+                store_half_row(tX, r, 0, d);
+            } else {
+                zero_half_row(tX, r, 1);
+            }
+            epi_publish();
+            is.wait();
+            masked_to_tile(t_row, hf, tC2, tY, r);      // dC2
+            epi_publish();
+            is.wait();
+            masked_to_tile(t_row, hf, tC1, tX, r);      // dC1
+            epi_publish();
+            is.wait();
+            float dfc[32];   // warpgroup 1: gradient w.r.t. the colour-grid features (dfeats cols 32..63), kept in registers
+            if (hf == 1) {
+                tmem_ld32(t_row, dfc);
+                zero_half_row(tY, r, 1);
+            } else {
+                float v[32], d[32];
+                tmem_ld32(t_row + 32, v);  // cols 32-47 dSH (dropped), 48-62 dgeo
+#pragma unroll
+                for (int i = 0; i < 32; i++) d[i] = 0.0f;
+                if (in_range) d[0] = a.g_sigma[row] * a.density_scale * __expf(fminf(fmaxf(h0, -15.0f), 15.0f));  // trunc_exp backward
+#pragma unroll
+                for (int i = 0; i < 15; i++) d[1 + i] = v[16 + i];
+                store_half_row(tY, r, 0, d);            // dh2
+            }
+            epi_publish();
+            is.wait();
+            masked_to_tile(t_row, hf, tH1, tX, r);      // dH1
+            epi_publish();
+            is.wait();
+            if (hf == 0) {
+                float dfs[32];
+                tmem_ld32(t_row, dfs);
+                if (in_range) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(a.dfeats + (size_t)row * 64);
+#pragma unroll
+                    for (int i = 0; i < 32; i++) dfs[i] *= a.out_scale;
+#pragma unroll
+                    for (uint32_t q = 0; q < 4; q++) dst[q] = pack8(dfs + q * 8);
+                }
+            } else if (in_range) {
+                uint4 *dst = reinterpret_cast<uint4 *>(a.dfeats + (size_t)row * 64) + 4;
+#pragma unroll
+                for (int i = 0; i < 32; i++) dfc[i] *= a.out_scale;
+#pragma unroll
+                for (uint32_t q = 0; q < 4; q++) dst[q] = pack8(dfc + q * 8);
+            }
+            tile_end_sync();
+        }
 
-    // ---- flush weight gradients: accumulator rows (M = 64) live in lanes 0..15 of every 32-lane sub-partition;
-    //      warpgroup hf takes the columns [32*hf, 32*hf+32) of every block ----
-    if (a.train_mlp && !first) {
-        const uint32_t lane = tid & 31, rr = (warp & 3u) * 16 + lane;   // output feature
-        const bool rowok = lane < 16;
-        float v[32];
-        tmem_ld32(t_row + 64 + hf * 32, v);    // dWc2 [3 x 64]
-        if (rowok && rr < 3) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c2 + rr * 64 + hf * 32 + i, v[i]);
-        tmem_ld32(t_row + 128 + hf * 32, v);   // dWc1 [64 x 64]
-        if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c1 + rr * 64 + hf * 32 + i, v[i]);
-        tmem_ld32(t_row + 320 + hf * 32, v);   // dWs1 [16 x 64]
-        if (rowok && rr < 16) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s1 + rr * 64 + hf * 32 + i, v[i]);
-        if (hf == 1) {
-            tmem_ld32(t_row + 192 + 32, v);    // dC1^T . F, columns 32..63 = colour-grid inputs = original columns 31..62
-            if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c0 + rr * 63 + 31 + i, v[i]);
-        } else {
-            tmem_ld32(t_row + 256, v);         // dC1^T . G, columns 0..30 = [SH | geo] = original columns 0..30
-            if (rowok) for (int i = 0; i < 31; i++) atomicAdd(a.gw_c0 + rr * 63 + i, v[i]);
-            tmem_ld32(t_row + 384, v);         // dH1^T . F, columns 0..31 = sigma-grid inputs
-            if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s0 + rr * 32 + i, v[i]);
+        // ---- flush weight gradients: accumulator rows (M = 64) live in lanes 0..15 of every 32-lane sub-partition;
+        //      warpgroup hf takes the columns [32*hf, 32*hf+32) of every block ----
+        if (a.train_mlp && !first) {
+            const uint32_t lane = tid & 31, rr = (warp & 3u) * 16 + lane;   // output feature
+            const bool rowok = lane < 16;
+            float v[32];
+            tmem_ld32(t_row + 64 + hf * 32, v);    // dWc2 [3 x 64]
+            if (rowok && rr < 3) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c2 + rr * 64 + hf * 32 + i, v[i]);
+            tmem_ld32(t_row + 128 + hf * 32, v);   // dWc1 [64 x 64]
+            if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c1 + rr * 64 + hf * 32 + i, v[i]);
+            tmem_ld32(t_row + 320 + hf * 32, v);   // dWs1 [16 x 64]
+            if (rowok && rr < 16) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s1 + rr * 64 + hf * 32 + i, v[i]);
+            if (hf == 1) {
+                tmem_ld32(t_row + 192 + 32, v);    // dC1^T . F, columns 32..63 = colour-grid inputs = original columns 31..62
+                if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c0 + rr * 63 + 31 + i, v[i]);
+            } else {
+                tmem_ld32(t_row + 256, v);         // dC1^T . G, columns 0..30 = [SH | geo] = original columns 0..30
+                if (rowok) for (int i = 0; i < 31; i++) atomicAdd(a.gw_c0 + rr * 63 + i, v[i]);
+                tmem_ld32(t_row + 384, v);         // dH1^T . F, columns 0..31 = sigma-grid inputs
+                if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s0 + rr * 32 + i, v[i]);
+            }
         }
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
+    if (is_issuer) tmem_dealloc(tmem, 512);
 }
 
 // interleave two [N,2] fp32 tables into one [N,4] fp16 table {s0,s1,c0,c1}
@@ -799,7 +844,7 @@ S3D_API int s3d_ngp_mlp_forward(const void *feats, const float *dirs, uint32_t M
     a.w = MlpWeights{(const __half *)w_s0, (const __half *)w_s1, (const __half *)w_c0, (const __half *)w_c1, (const __half *)w_c2};
     a.sigma = sigma; a.rgb = rgb; a.geo = geo; a.M = M; a.n_tiles = div_up(M, kRows); a.density_scale = density_scale; a.sigma_only = sigma_only;
     const uint32_t grid = min(a.n_tiles, (uint32_t)sm_count() * 3u);
-    k_ngp_mlp_fwd<<<grid, 256, smem, as_stream(stream)>>>(a);
+    k_ngp_mlp_fwd<<<grid, kMlpThreads, smem, as_stream(stream)>>>(a);
     S3D_RETURN_LAST();
 }
 
@@ -818,7 +863,7 @@ S3D_API int s3d_ngp_mlp_backward(const void *feats, const float *dirs, uint32_t 
     a.gw_s0 = gw_s0; a.gw_s1 = gw_s1; a.gw_c0 = gw_c0; a.gw_c1 = gw_c1; a.gw_c2 = gw_c2;
     a.M = M; a.n_tiles = div_up(M, kRows); a.density_scale = density_scale; a.out_scale = out_scale; a.train_mlp = train_mlp;
     const uint32_t grid = min(a.n_tiles, (uint32_t)sm_count());
-    k_ngp_mlp_bwd<<<grid, 256, smem, as_stream(stream)>>>(a);
+    k_ngp_mlp_bwd<<<grid, kMlpThreads, smem, as_stream(stream)>>>(a);
     S3D_RETURN_LAST();
 }
 

@@ -632,7 +632,7 @@ int march_count_scan(const float *rays_o, const float *rays_d, const uint8_t *gr
                      int *counter, cudaStream_t st, uint32_t *bitmap = nullptr) {
     const uint32_t nb = div_up(N, 128u);
     uint32_t *block_sums = nullptr;
-    cudaError_t e = cudaMallocAsync(&block_sums, (size_t)nb * sizeof(uint32_t), st);
+    cudaError_t e = scratch_alloc((void **)&block_sums, (size_t)nb * sizeof(uint32_t), st);
     if (e != cudaSuccess) return (int)e;
     k_march_count<<<nb, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, block_sums, bitmap);
     k_march_scan<<<1, 1024, 0, st>>>(block_sums, nb, N, counter);
@@ -652,7 +652,7 @@ S3D_API int s3d_march_rays_train(const float *rays_o, const float *rays_d, const
     cudaStream_t st = as_stream(stream);
     // the count pass records the sample positions on the ray's step lattice; the write pass replays the lattice
     uint32_t *bitmap = nullptr;
-    cudaError_t e = cudaMallocAsync(&bitmap, (size_t)N * kBitmapWords * sizeof(uint32_t), st);
+    cudaError_t e = scratch_alloc((void **)&bitmap, (size_t)N * kBitmapWords * sizeof(uint32_t), st);
     if (e != cudaSuccess) return (int)e;
     int rc = march_count_scan(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, st, bitmap);
     if (rc == 0) {
