@@ -40,11 +40,12 @@ struct Geo {
     uint32_t offset[kMaxLevels];  // first entry of the level
     uint32_t hashed;              // bit l: level l uses the xor-prime hash
     uint32_t pow2;                // bit l: size is a power of two
+    uint32_t pair_ok;             // bit l: offset and size are even, so aligned entry pairs stay inside the level
 };
 
 __device__ void geo_init(Geo &g, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H) {
     const uint32_t l = threadIdx.x;
-    if (l == 0) { g.hashed = 0; g.pow2 = 0; }
+    if (l == 0) { g.hashed = 0; g.pow2 = 0; g.pair_ok = 0; }
     __syncthreads();
     if (l < L) {
         const uint32_t size = (uint32_t)(offsets[l + 1] - offsets[l]);
@@ -56,6 +57,7 @@ __device__ void geo_init(Geo &g, const int *__restrict__ offsets, uint32_t L, fl
         for (int d = 0; d < 3; d++) if (stride <= size) stride *= res1;
         if (stride > size) atomicOr(&g.hashed, 1u << l);
         if ((size & (size - 1)) == 0) atomicOr(&g.pow2, 1u << l);
+        if ((((uint32_t)offsets[l] | size) & 1u) == 0) atomicOr(&g.pair_ok, 1u << l);
     }
     __syncthreads();
 }
@@ -108,8 +110,58 @@ __device__ __forceinline__ bool to_unit(float x, float y, float z, float bound, 
 // ------------------------------------------------------------------------------------------------
 // table entries are {s0,s1,c0,c1} fp16 (8 bytes) at  table + idx * stride + off : stride 8 / off 0 for a stand-alone
 // model, stride 16 / off 0|8 for the teacher | student half of a paired table (see k_ngp_encode_pair)
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
 __device__ __forceinline__ uint2 ld_entry(const uint8_t *__restrict__ table, uint32_t idx, uint32_t stride) {
     return __ldg(reinterpret_cast<const uint2 *>(table + (size_t)idx * stride));
+}
+
+// The two x-corners of a cell, idx[2j] and idx[2j+1], are the halves of one ALIGNED entry pair whenever they differ in
+// bit 0 only (even x on hashed levels, even dense index otherwise): one double-width load then serves both.  The L1 tag
+// stage pays per (lane, sector), so this removes a quarter of the gather cost on average.  All loads are issued before any
+// use (the unmerged second load is predicated, not branched) so the 8 gathers of a level stay in flight together.
+__device__ __forceinline__ void gather_cell_e8(const uint8_t *__restrict__ table, const Cell &c, uint2 (&v)[8]) {
+    uint4 a[4];
+    bool merged[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        merged[j] = (c.idx[2 * j] ^ c.idx[2 * j + 1]) == 1u;
+        a[j] = __ldg(reinterpret_cast<const uint4 *>(table) + (c.idx[2 * j] >> 1));
+        if (!merged[j]) v[2 * j + 1] = __ldg(reinterpret_cast<const uint2 *>(table) + c.idx[2 * j + 1]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const bool odd = c.idx[2 * j] & 1u;
+        const uint2 lo = make_uint2(a[j].x, a[j].y), hi = make_uint2(a[j].z, a[j].w);
+        v[2 * j] = odd ? hi : lo;
+        if (merged[j]) v[2 * j + 1] = odd ? lo : hi;
+    }
+}
+
+__device__ __forceinline__ void ldg256(const void *p, uint4 &lo, uint4 &hi) {  // LDG.E.ENL2.256 (sm_100)
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(p));
+}
+
+// same for the 16-byte entries of a paired table: an aligned pair is one 32-byte sector
+__device__ __forceinline__ void gather_cell_e16(const uint4 *__restrict__ table8, const Cell &c, uint4 (&v)[8]) {
+    uint4 lo[4], hi[4];
+    bool merged[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        merged[j] = (c.idx[2 * j] ^ c.idx[2 * j + 1]) == 1u;
+        ldg256(table8 + (c.idx[2 * j] & ~1u), lo[j], hi[j]);
+        if (!merged[j]) v[2 * j + 1] = __ldg(table8 + c.idx[2 * j + 1]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const bool odd = c.idx[2 * j] & 1u;
+        v[2 * j] = odd ? hi[j] : lo[j];
+        if (merged[j]) v[2 * j + 1] = odd ? lo[j] : hi[j];
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -123,7 +175,7 @@ k_ngp_encode(const float *__restrict__ xyz, uint32_t M, float bound, const uint8
     const bool ok = to_unit(xyz[(size_t)i * 3], xyz[(size_t)i * 3 + 1], xyz[(size_t)i * 3 + 2], bound, ux, uy, uz);
     uint4 *row = reinterpret_cast<uint4 *>(feats + (size_t)i * 64);
     for (uint32_t grp = 0; grp < 4; grp++) {      // 4 levels -> one 16-byte chunk per table
-        float fs[8], fc[8];
+        uint32_t fs[4], fc[4];   // one packed half2 per level: 4 levels -> one 16-byte chunk per table
 #pragma unroll
         for (uint32_t q = 0; q < 4; q++) {
             const uint32_t l = grp * 4 + q;
@@ -132,8 +184,11 @@ k_ngp_encode(const float *__restrict__ xyz, uint32_t M, float bound, const uint8
                 Cell c;
                 locate(g, l, ux, uy, uz, c, nullptr);
                 uint2 v[8];
+                if (stride == 8 && ((g.pair_ok >> l) & 1u)) gather_cell_e8(table, c, v);
+                else {
 #pragma unroll
-                for (int k = 0; k < 8; k++) v[k] = ld_entry(table, c.idx[k], stride);
+                    for (int k = 0; k < 8; k++) v[k] = ld_entry(table, c.idx[k], stride);
+                }
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&v[k].x));
@@ -142,10 +197,10 @@ k_ngp_encode(const float *__restrict__ xyz, uint32_t M, float bound, const uint8
                     c0 = __fmaf_rn(c.w[k], b.x, c0); c1 = __fmaf_rn(c.w[k], b.y, c1);
                 }
             }
-            fs[q * 2] = s0; fs[q * 2 + 1] = s1; fc[q * 2] = c0; fc[q * 2 + 1] = c1;
+            fs[q] = pack2(s0, s1); fc[q] = pack2(c0, c1);
         }
-        row[grp] = pack8(fs);
-        if (!sigma_only) row[4 + grp] = pack8(fc);
+        row[grp] = make_uint4(fs[0], fs[1], fs[2], fs[3]);
+        if (!sigma_only) row[4 + grp] = make_uint4(fc[0], fc[1], fc[2], fc[3]);
     }
 }
 
@@ -159,7 +214,7 @@ __device__ __forceinline__ void acc4(const uint2 v, float w, float &a0, float &a
     a0 = __fmaf_rn(w, a.x, a0); a1 = __fmaf_rn(w, a.y, a1); a2 = __fmaf_rn(w, b.x, a2); a3 = __fmaf_rn(w, b.y, a3);
 }
 
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 k_ngp_encode_pair(const float *__restrict__ xyz, const float *__restrict__ xyz_teacher, const uint8_t *__restrict__ mask, uint32_t M,
                   float bound, const uint4 *__restrict__ table8, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H,
                   __half *__restrict__ feats_teacher, __half *__restrict__ feats_student) {
@@ -174,7 +229,7 @@ k_ngp_encode_pair(const float *__restrict__ xyz, const float *__restrict__ xyz_t
     if (moved) tok = to_unit(xyz_teacher[(size_t)i * 3], xyz_teacher[(size_t)i * 3 + 1], xyz_teacher[(size_t)i * 3 + 2], bound, tx, ty, tz);
     uint4 *row_t = reinterpret_cast<uint4 *>(feats_teacher + (size_t)i * 64), *row_s = reinterpret_cast<uint4 *>(feats_student + (size_t)i * 64);
     for (uint32_t grp = 0; grp < 4; grp++) {
-        float ts[8], tc[8], ss[8], sc[8];
+        uint32_t ts[4], tc[4], ss[4], sc[4];
 #pragma unroll
         for (uint32_t q = 0; q < 4; q++) {
             const uint32_t l = grp * 4 + q;
@@ -183,8 +238,11 @@ k_ngp_encode_pair(const float *__restrict__ xyz, const float *__restrict__ xyz_t
                 Cell c;
                 locate(g, l, ux, uy, uz, c, nullptr);
                 uint4 v[8];
+                if ((g.pair_ok >> l) & 1u) gather_cell_e16(table8, c, v);
+                else {
 #pragma unroll
-                for (int k = 0; k < 8; k++) v[k] = __ldg(table8 + c.idx[k]);
+                    for (int k = 0; k < 8; k++) v[k] = __ldg(table8 + c.idx[k]);
+                }
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     acc4(make_uint2(v[k].z, v[k].w), c.w[k], s0, s1, s2, s3);
@@ -200,11 +258,10 @@ k_ngp_encode_pair(const float *__restrict__ xyz, const float *__restrict__ xyz_t
                     acc4(make_uint2(v.x, v.y), c.w[k], t0, t1, t2, t3);
                 }
             }
-            ts[q * 2] = t0; ts[q * 2 + 1] = t1; tc[q * 2] = t2; tc[q * 2 + 1] = t3;
-            ss[q * 2] = s0; ss[q * 2 + 1] = s1; sc[q * 2] = s2; sc[q * 2 + 1] = s3;
+            ts[q] = pack2(t0, t1); tc[q] = pack2(t2, t3); ss[q] = pack2(s0, s1); sc[q] = pack2(s2, s3);
         }
-        row_t[grp] = pack8(ts); row_t[4 + grp] = pack8(tc);
-        row_s[grp] = pack8(ss); row_s[4 + grp] = pack8(sc);
+        row_t[grp] = make_uint4(ts[0], ts[1], ts[2], ts[3]); row_t[4 + grp] = make_uint4(tc[0], tc[1], tc[2], tc[3]);
+        row_s[grp] = make_uint4(ss[0], ss[1], ss[2], ss[3]); row_s[4 + grp] = make_uint4(sc[0], sc[1], sc[2], sc[3]);
     }
 }
 
@@ -218,6 +275,14 @@ __global__ void k_pair_tables(const uint2 *__restrict__ teacher4, const uint2 *_
 // ------------------------------------------------------------------------------------------------
 // scatter: dfeats -> interleaved fp32 gradient table
 // ------------------------------------------------------------------------------------------------
+// Warp-level pre-reduction.  Samples arrive ray-major, so on the coarse levels aligned groups of 2/4/8/16/32 lanes sit in
+// the same cell and address the same 8 entries.  Instead of reducing each of the 32 products (8 corners x 4 channels)
+// with its own shuffle tree (160 shuffles), the group splits the work while it reduces: at the xor-1 stage a lane hands
+// the four corners of the other z-face to its partner and receives the partner's share of its own face (16 shuffles), at
+// xor-2 it keeps one y-edge of that face (8), at xor-4 one corner (4); xor-8 / xor-16 fold whole corners (4 + 4).  A
+// uniform octet therefore ends with ONE 16-byte RED per lane -- 8 per octet instead of 64 -- after 28 shuffles.  A lane
+// whose group stops being uniform at some stage emits what it holds there.  Stages run only when enough groups profit
+// (a stage costs its shuffles for the whole warp; every merged lane saves half of its remaining REDs).
 __global__ void __launch_bounds__(256)
 k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, uint32_t M, float bound,
               float4 *__restrict__ grad4, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H, float grad_scale) {
@@ -228,7 +293,9 @@ k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, 
     bool ok = false;
     if (i < M) ok = to_unit(xyz[(size_t)i * 3], xyz[(size_t)i * 3 + 1], xyz[(size_t)i * 3 + 2], bound, ux, uy, uz);
     const uint32_t lane = lane_id();
+    const bool b0 = lane & 1u, b1 = lane & 2u, b2 = lane & 4u;
     const uint4 *row = reinterpret_cast<const uint4 *>(dfeats + (size_t)(i < M ? i : 0) * 64);
+    constexpr uint32_t kFull = 0xffffffffu;
     for (uint32_t grp = 0; grp < 4; grp++) {
         float ds[8], dc[8];
         if (ok) { unpack8(__ldg(row + grp), ds); unpack8(__ldg(row + 4 + grp), dc); }
@@ -240,36 +307,112 @@ k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, 
         for (uint32_t q = 0; q < 4; q++) {
             const uint32_t l = grp * 4 + q;
             if (l >= L) break;
-            Cell c;
-            unsigned long long key = ~0ull;
-            if (ok) locate(g, l, ux, uy, uz, c, &key);
-            else {
-#pragma unroll
-                for (int k = 0; k < 8; k++) { c.idx[k] = 0; c.w[k] = 0.f; }
-            }
-            const float g0 = ds[q * 2] * grad_scale, g1 = ds[q * 2 + 1] * grad_scale, g2 = dc[q * 2] * grad_scale, g3 = dc[q * 2 + 1] * grad_scale;
-            const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
-            const bool head = (lane == 0) || (prev != key);
-            const uint32_t heads = __ballot_sync(0xffffffffu, head);
-            if (__popc(heads) <= 16) {
-                // runs of equal cells: fold every run into its head lane (segmented suffix sums), then one RED per corner
-                const uint32_t after = heads >> 1 >> lane;
-                const uint32_t seg_left = after ? (uint32_t)(__ffs(after) - 1) : (31u - lane);
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    float a0 = c.w[k] * g0, a1 = c.w[k] * g1, a2 = c.w[k] * g2, a3 = c.w[k] * g3;
-#pragma unroll
-                    for (uint32_t d = 1; d < 32; d <<= 1) {
-                        const float o0 = __shfl_down_sync(0xffffffffu, a0, d), o1 = __shfl_down_sync(0xffffffffu, a1, d);
-                        const float o2 = __shfl_down_sync(0xffffffffu, a2, d), o3 = __shfl_down_sync(0xffffffffu, a3, d);
-                        if (d <= seg_left) { a0 += o0; a1 += o1; a2 += o2; a3 += o3; }
-                    }
-                    if (ok && head) atomicAdd(grad4 + c.idx[k], make_float4(a0, a1, a2, a3));
+            // cell of this sample in level l (same arithmetic as locate())
+            const float sc = g.scale[l];
+            const float px = __fmaf_rn(ux, sc, 0.5f), py = __fmaf_rn(uy, sc, 0.5f), pz = __fmaf_rn(uz, sc, 0.5f);
+            const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
+            const uint32_t gx = (uint32_t)fx0, gy = (uint32_t)fy0, gz = (uint32_t)fz0;
+            const float fx = ok ? __fsub_rn(px, fx0) : 0.f, fy = ok ? __fsub_rn(py, fy0) : 0.f, fz = ok ? __fsub_rn(pz, fz0) : 0.f;
+            const unsigned long long key = ok ? ((unsigned long long)gx | ((unsigned long long)gy << 21) | ((unsigned long long)gz << 42)) : ~0ull;
+            const uint32_t size = g.size[l], off = g.offset[l], r1 = g.res1[l];
+            const bool hashed = (g.hashed >> l) & 1u, p2 = (g.pow2 >> l) & 1u;
+            auto entry = [&](uint32_t x, uint32_t y, uint32_t z) -> uint32_t {
+                uint32_t id;
+                if (hashed) {
+                    id = x ^ (y * 2654435761u) ^ (z * 805459861u);
+                    id = p2 ? (id & (size - 1)) : (id % size);
+                } else {
+                    id = x + y * r1;
+                    if (r1 * r1 <= size) id += z * r1 * r1;
+                    id = id % size;
                 }
-            } else if (ok) {
+                return off + id;
+            };
+            auto emit = [&](uint32_t id, const float (&v)[4]) { atomicAdd(grad4 + id, make_float4(v[0], v[1], v[2], v[3])); };
+            const float gv[4] = {ds[q * 2] * grad_scale, ds[q * 2 + 1] * grad_scale, dc[q * 2] * grad_scale, dc[q * 2 + 1] * grad_scale};
+
+            // bit i of same: lane i sits in the cell of lane i-1; an aligned group of n lanes is uniform iff bits base+1 .. base+n-1 are set
+            const unsigned long long prev = __shfl_up_sync(kFull, key, 1);
+            const uint32_t same = __ballot_sync(kFull, lane != 0 && prev == key);
+            auto uniform = [&](uint32_t n) -> bool {
+                const uint32_t mask = ((1u << (n - 1)) - 1u) << ((lane & ~(n - 1)) + 1);
+                return (same & mask) == mask;
+            };
+            const bool u2 = uniform(2);
+            const uint32_t n2 = __popc(__ballot_sync(kFull, u2));
+            if (n2 < 6) {  // fewer than three mergeable pairs: every sample scatters its own eight corners
+                if (ok) {
 #pragma unroll
-                for (int k = 0; k < 8; k++) atomicAdd(grad4 + c.idx[k], make_float4(c.w[k] * g0, c.w[k] * g1, c.w[k] * g2, c.w[k] * g3));
+                    for (uint32_t k = 0; k < 8; k++) {
+                        const float w = ((k & 1u) ? fx : 1.0f - fx) * ((k & 2u) ? fy : 1.0f - fy) * ((k & 4u) ? fz : 1.0f - fz);
+                        const float v[4] = {w * gv[0], w * gv[1], w * gv[2], w * gv[3]};
+                        emit(entry(gx + (k & 1u), gy + ((k >> 1) & 1u), gz + (k >> 2)), v);
+                    }
+                }
+                continue;
             }
+            // "k" = the half this lane keeps at a stage, "s" = the half it sends: z by lane bit 0, y by bit 1, x by bit 2
+            const float wzk = b0 ? fz : 1.0f - fz, wzs = b0 ? 1.0f - fz : fz;
+            const float wyk = b1 ? fy : 1.0f - fy, wys = b1 ? 1.0f - fy : fy;
+            const float wxk = b2 ? fx : 1.0f - fx, wxs = b2 ? 1.0f - fx : fx;
+            const uint32_t zk = gz + (b0 ? 1u : 0u), zs = gz + (b0 ? 0u : 1u);
+            const uint32_t yk = gy + (b1 ? 1u : 0u), ys = gy + (b1 ? 0u : 1u);
+            const uint32_t xk = gx + (b2 ? 1u : 0u), xs = gx + (b2 ? 0u : 1u);
+            // face z = k: corners c[0] = (xk,yk) c[1] = (xs,yk) c[2] = (xk,ys) c[3] = (xs,ys); same order on the face z = s
+            float keep[4][4], send[4][4];
+            {
+                const float wxy[4] = {wxk * wyk, wxs * wyk, wxk * wys, wxs * wys};
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int ch = 0; ch < 4; ch++) { keep[c][ch] = wxy[c] * wzk * gv[ch]; send[c][ch] = wxy[c] * wzs * gv[ch]; }
+            }
+            // ---- xor 1: z faces ----
+            if (ok && !u2) {
+                emit(entry(xk, yk, zs), send[0]); emit(entry(xs, yk, zs), send[1]); emit(entry(xk, ys, zs), send[2]); emit(entry(xs, ys, zs), send[3]);
+                emit(entry(xk, yk, zk), keep[0]); emit(entry(xs, yk, zk), keep[1]); emit(entry(xk, ys, zk), keep[2]); emit(entry(xs, ys, zk), keep[3]);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) keep[c][ch] += __shfl_xor_sync(kFull, send[c][ch], 1);
+            bool active = ok && u2;
+            // ---- xor 2: y edges of the kept face (keep[0..1] stay, keep[2..3] go) ----
+            const bool u4 = uniform(4);
+            if (__popc(__ballot_sync(kFull, u4)) < 8) {  // fewer than two mergeable quads
+                if (active) { emit(entry(xk, yk, zk), keep[0]); emit(entry(xs, yk, zk), keep[1]); emit(entry(xk, ys, zk), keep[2]); emit(entry(xs, ys, zk), keep[3]); }
+                continue;
+            }
+            if (active && !u4) { emit(entry(xk, yk, zk), keep[0]); emit(entry(xs, yk, zk), keep[1]); emit(entry(xk, ys, zk), keep[2]); emit(entry(xs, ys, zk), keep[3]); }
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) keep[c][ch] += __shfl_xor_sync(kFull, keep[2 + c][ch], 2);
+            active = active && u4;
+            // ---- xor 4: x corners of the kept edge ----
+            const bool u8 = uniform(8);
+            if (!__any_sync(kFull, u8)) {
+                if (active) { emit(entry(xk, yk, zk), keep[0]); emit(entry(xs, yk, zk), keep[1]); }
+                continue;
+            }
+            if (active && !u8) { emit(entry(xk, yk, zk), keep[0]); emit(entry(xs, yk, zk), keep[1]); }
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++) keep[0][ch] += __shfl_xor_sync(kFull, keep[1][ch], 4);
+            active = active && u8;
+            // ---- xor 8 / xor 16: fold whole corners into the lower octet / half ----
+            const bool u16 = uniform(16);
+            if (__any_sync(kFull, u16)) {
+                if (active && !u16) { emit(entry(xk, yk, zk), keep[0]); active = false; }
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) keep[0][ch] += __shfl_xor_sync(kFull, keep[0][ch], 8);
+                active = active && !(lane & 8u);
+                if (same == 0xfffffffeu) {  // the whole warp in one cell
+#pragma unroll
+                    for (int ch = 0; ch < 4; ch++) keep[0][ch] += __shfl_xor_sync(kFull, keep[0][ch], 16);
+                    active = active && !(lane & 16u);
+                }
+            }
+            if (active) emit(entry(xk, yk, zk), keep[0]);
         }
     }
 }
@@ -331,15 +474,20 @@ __device__ __forceinline__ void sh4(float x, float y, float z, float *o) {
 // Thread layout of the MLP kernels: 256 threads = 2 warpgroups; thread t owns sample row (t & 127) and column half
 // hf = t >> 7 (columns 32*hf .. 32*hf+31) of every 64-wide tile / accumulator.  A warp may only read the 32 TMEM lanes
 // of its sub-partition (warp % 4), which is exactly rows 32*(warp%4) .. +31 for both warpgroups.
-__device__ __forceinline__ void load_feat_half(uint8_t *tile, const __half *__restrict__ feats, uint32_t row_g, uint32_t r, uint32_t hf, bool in_range) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(feats + (size_t)row_g * 64) + hf * 4;
+// Inputs of one tile held in registers: the loads for tile t+1 are issued at the top of tile t, so their DRAM latency
+// runs under the 5 / 11 tensor-core rounds of tile t instead of sitting at the head of every round that needs them.
+struct FeatPre {
+    uint4 f[4];
+    __device__ __forceinline__ void load(const __half *__restrict__ feats, uint32_t row_g, uint32_t hf, bool in_range) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(feats + (size_t)row_g * 64) + hf * 4;
 #pragma unroll
-    for (uint32_t q = 0; q < 4; q++) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (in_range) v = __ldg(src + q);
-        *reinterpret_cast<uint4 *>(tile + sw128_off(r, hf * 4 + q)) = v;
+        for (uint32_t q = 0; q < 4; q++) f[q] = in_range ? __ldg(src + q) : make_uint4(0, 0, 0, 0);
     }
-}
+    __device__ __forceinline__ void store(uint8_t *tile, uint32_t r, uint32_t hf) const {
+#pragma unroll
+        for (uint32_t q = 0; q < 4; q++) *reinterpret_cast<uint4 *>(tile + sw128_off(r, hf * 4 + q)) = f[q];
+    }
+};
 
 __device__ __forceinline__ void sync_tiles() {  // writers -> tensor core, tensor core results -> readers
     fence_async_smem();
@@ -464,10 +612,26 @@ k_ngp_mlp_fwd(const FwdArgs a) {
             tile_end_sync();
         }
     } else {
+        const bool want_dirs = (hf == 0) && !a.sigma_only;
+        FeatPre nf;
+        float ndx = 0.f, ndy = 0.f, ndz = 0.f;
+        {
+            const uint32_t row0 = blockIdx.x * kRows + r;
+            nf.load(a.feats, row0, hf, blockIdx.x < a.n_tiles && row0 < a.M);
+            if (want_dirs && blockIdx.x < a.n_tiles && row0 < a.M) { ndx = a.dirs[(size_t)row0 * 3]; ndy = a.dirs[(size_t)row0 * 3 + 1]; ndz = a.dirs[(size_t)row0 * 3 + 2]; }
+        }
         for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
             const uint32_t row = tile * kRows + r;
             const bool in_range = row < a.M;
-            load_feat_half(tF, a.feats, row, r, hf, in_range);
+            nf.store(tF, r, hf);
+            const float dx = ndx, dy = ndy, dz = ndz;
+            {   // next tile's inputs
+                const uint32_t nt = tile + gridDim.x, nrow = nt * kRows + r;
+                const bool nin = nt < a.n_tiles && nrow < a.M;
+                nf.load(a.feats, nrow, hf, nin);
+                ndx = ndy = ndz = 0.f;
+                if (want_dirs && nin) { ndx = a.dirs[(size_t)nrow * 3]; ndy = a.dirs[(size_t)nrow * 3 + 1]; ndz = a.dirs[(size_t)nrow * 3 + 2]; }
+            }
             epi_publish();
             is.wait();       // sigma layer 0 done
             relu_to_tile(t_row, hf, tT, r);
@@ -482,8 +646,6 @@ k_ngp_mlp_fwd(const FwdArgs a) {
                 }
                 if (!a.sigma_only) {
                     float g[32];
-                    float dx = 0.f, dy = 0.f, dz = 0.f;
-                    if (in_range) { dx = a.dirs[(size_t)row * 3]; dy = a.dirs[(size_t)row * 3 + 1]; dz = a.dirs[(size_t)row * 3 + 2]; }
                     sh4(dx, dy, dz, g);
 #pragma unroll
                     for (int i = 0; i < 15; i++) g[16 + i] = h2[1 + i];
@@ -616,11 +778,28 @@ k_ngp_mlp_bwd(const BwdArgs a) {
             tile_end_sync();
         }
     } else {
+        FeatPre nf;
+        float nin7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // warpgroup 0: dir xyz, dL/drgb, dL/dsigma of the next tile
+        auto prefetch = [&](uint32_t t) {
+            const uint32_t prow = t * kRows + r;
+            const bool pin = t < a.n_tiles && prow < a.M;
+            nf.load(a.feats, prow, hf, pin);
+            if (hf == 0) {
+#pragma unroll
+                for (int j = 0; j < 3; j++) { nin7[j] = pin ? a.dirs[(size_t)prow * 3 + j] : 0.f; nin7[3 + j] = pin ? a.g_rgb[(size_t)prow * 3 + j] : 0.f; }
+                nin7[6] = pin ? a.g_sigma[prow] : 0.f;
+            }
+        };
+        prefetch(blockIdx.x);
         for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, first = false) {
             const uint32_t row = tile * kRows + r;
             const bool in_range = row < a.M;
             // ---------------- recompute the forward, keeping every activation tile ----------------
-            load_feat_half(tF, a.feats, row, r, hf, in_range);
+            nf.store(tF, r, hf);
+            float in7[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) in7[j] = nin7[j];
+            prefetch(tile + gridDim.x);
             epi_publish();
             is.wait();
             relu_to_tile(t_row, hf, tH1, r);
@@ -631,9 +810,7 @@ k_ngp_mlp_bwd(const BwdArgs a) {
                 float h2[16], g[32];
                 tmem_ld16(t_row, h2);
                 h0 = h2[0];
-                float dx = 0.f, dy = 0.f, dz = 0.f;
-                if (in_range) { dx = a.dirs[(size_t)row * 3]; dy = a.dirs[(size_t)row * 3 + 1]; dz = a.dirs[(size_t)row * 3 + 2]; }
-                sh4(dx, dy, dz, g);
+                sh4(in7[0], in7[1], in7[2], g);
 #pragma unroll
                 for (int i = 0; i < 15; i++) g[16 + i] = h2[1 + i];
                 g[31] = 0.0f;
@@ -659,7 +836,7 @@ k_ngp_mlp_bwd(const BwdArgs a) {
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
                         const float sg = 1.0f / (1.0f + __expf(-o[c]));
-                        d[c] = a.g_rgb[(size_t)row * 3 + c] * sg * (1.0f - sg);
+                        d[c] = in7[3 + c] * sg * (1.0f - sg);
                     }
                 }
                 store_half_row(tX, r, 0, d);
@@ -683,7 +860,7 @@ k_ngp_mlp_bwd(const BwdArgs a) {
                 tmem_ld32(t_row + 32, v);  // cols 32-47 dSH (dropped), 48-62 dgeo
 #pragma unroll
                 for (int i = 0; i < 32; i++) d[i] = 0.0f;
-                if (in_range) d[0] = a.g_sigma[row] * a.density_scale * __expf(fminf(fmaxf(h0, -15.0f), 15.0f));  // trunc_exp backward
+                if (in_range) d[0] = in7[6] * a.density_scale * __expf(fminf(fmaxf(h0, -15.0f), 15.0f));  // trunc_exp backward
 #pragma unroll
                 for (int i = 0; i < 15; i++) d[1 + i] = v[16 + i];
                 store_half_row(tY, r, 0, d);            // dh2

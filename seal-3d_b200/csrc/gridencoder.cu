@@ -27,13 +27,16 @@ struct LevelInfo {
     uint32_t hashmap_size, resolution;
     float scale;
     bool hashed;  // gridtype==hash and the dense index range exceeds the level's table
+    bool pair_ok; // level starts at an even entry and holds an even number of entries: aligned entry pairs stay inside it
 };
 
 template <uint32_t D>
 __device__ __forceinline__ LevelInfo level_info(const int *__restrict__ offsets, uint32_t level, float S, uint32_t H,
                                                 uint32_t gridtype, bool align_corners) {
     LevelInfo li;
-    li.hashmap_size = (uint32_t)(__ldg(offsets + level + 1) - __ldg(offsets + level));
+    const uint32_t first = (uint32_t)__ldg(offsets + level);
+    li.hashmap_size = (uint32_t)__ldg(offsets + level + 1) - first;
+    li.pair_ok = ((first | li.hashmap_size) & 1u) == 0;
     li.scale = __fmaf_rn(exp2f((float)level * S), (float)H, -1.0f);
     li.resolution = (uint32_t)ceilf(li.scale) + 1;
     // stride after the d-loop of get_grid_index (gridencoder.cu:72-75): stops multiplying once it exceeds the table
@@ -108,6 +111,36 @@ __device__ __forceinline__ void load_entry(const T *__restrict__ grid, uint32_t 
     }
 }
 
+// Two entries that are the halves of one aligned entry pair, fetched with ONE double-width load.  Along x the two corners
+// of a cell are such a pair whenever the first index is even and the second is its successor: on hashed levels
+// (x ^ h) and ((x+1) ^ h) differ in bit 0 only for even x, on dense levels the index is x + ... itself.  The L1 tag
+// stage pays per (lane, sector), so a merged pair costs one lookup instead of two.
+template <typename T, uint32_t C> struct PairLoad { static constexpr bool kOk = false; };
+template <> struct PairLoad<float, 2> {
+    static constexpr bool kOk = true;
+    __device__ static __forceinline__ void load(const float *grid, uint32_t even_index, float (&lo)[2], float (&hi)[2]) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(grid) + (even_index >> 1));
+        lo[0] = t.x; lo[1] = t.y; hi[0] = t.z; hi[1] = t.w;
+    }
+};
+template <> struct PairLoad<__half, 2> {
+    static constexpr bool kOk = true;
+    __device__ static __forceinline__ void load(const __half *grid, uint32_t even_index, float (&lo)[2], float (&hi)[2]) {
+        const uint2 t = __ldg(reinterpret_cast<const uint2 *>(grid) + (even_index >> 1));
+        const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&t.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&t.y));
+        lo[0] = a.x; lo[1] = a.y; hi[0] = b.x; hi[1] = b.y;
+    }
+};
+template <> struct PairLoad<__half, 4> {
+    static constexpr bool kOk = true;
+    __device__ static __forceinline__ void load(const __half *grid, uint32_t even_index, float (&lo)[4], float (&hi)[4]) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4 *>(grid) + (even_index >> 1));
+        const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&t.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&t.y));
+        const float2 c = __half22float2(*reinterpret_cast<const __half2 *>(&t.z)), d = __half22float2(*reinterpret_cast<const __half2 *>(&t.w));
+        lo[0] = a.x; lo[1] = a.y; lo[2] = b.x; lo[3] = b.y; hi[0] = c.x; hi[1] = c.y; hi[2] = d.x; hi[3] = d.y;
+    }
+};
+
 template <typename T> __device__ __forceinline__ T from_float(float v);
 template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
 template <> __device__ __forceinline__ __half from_float<__half>(float v) { return __float2half_rn(v); }
@@ -162,12 +195,54 @@ __device__ __forceinline__ void encode_level(const float (&x)[D], const T *__res
 #pragma unroll
     for (uint32_t c = 0; c < C; c++) res[c] = 0.0f;
     float val[1u << D][C];
+    if constexpr (PairLoad<T, C>::kOk) {
+        if (li.pair_ok) {  // uniform per level
+            uint32_t i0[1u << (D - 1)], i1[1u << (D - 1)];
+            bool merged[1u << (D - 1)];
 #pragma unroll
-    for (uint32_t idx = 0; idx < (1u << D); idx++) {
-        uint32_t pl[D];
+            for (uint32_t j = 0; j < (1u << (D - 1)); j++) {
+                uint32_t pl[D];
+                pl[0] = pg[0];
 #pragma unroll
-        for (uint32_t d = 0; d < D; d++) pl[d] = pg[d] + ((idx >> d) & 1u);
-        load_entry<T, C>(grid_level, corner_index<D>(li, align_corners, pl), val[idx]);
+                for (uint32_t d = 1; d < D; d++) pl[d] = pg[d] + ((j >> (d - 1)) & 1u);
+                i0[j] = corner_index<D>(li, align_corners, pl);
+                pl[0] = pg[0] + 1;
+                i1[j] = corner_index<D>(li, align_corners, pl);
+                merged[j] = (i0[j] ^ i1[j]) == 1u;
+            }
+            // all loads first (the second one predicated off for merged pairs), then the selects
+            float lo[1u << (D - 1)][C], hi[1u << (D - 1)][C];
+#pragma unroll
+            for (uint32_t j = 0; j < (1u << (D - 1)); j++) {
+                PairLoad<T, C>::load(grid_level, i0[j] & ~1u, lo[j], hi[j]);
+                if (!merged[j]) load_entry<T, C>(grid_level, i1[j], val[2 * j + 1]);
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < (1u << (D - 1)); j++) {
+                const bool odd = i0[j] & 1u;
+#pragma unroll
+                for (uint32_t c = 0; c < C; c++) {
+                    val[2 * j][c] = odd ? hi[j][c] : lo[j][c];
+                    if (merged[j]) val[2 * j + 1][c] = odd ? lo[j][c] : hi[j][c];
+                }
+            }
+        } else {
+#pragma unroll
+            for (uint32_t idx = 0; idx < (1u << D); idx++) {
+                uint32_t pl[D];
+#pragma unroll
+                for (uint32_t d = 0; d < D; d++) pl[d] = pg[d] + ((idx >> d) & 1u);
+                load_entry<T, C>(grid_level, corner_index<D>(li, align_corners, pl), val[idx]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (uint32_t idx = 0; idx < (1u << D); idx++) {
+            uint32_t pl[D];
+#pragma unroll
+            for (uint32_t d = 0; d < D; d++) pl[d] = pg[d] + ((idx >> d) & 1u);
+            load_entry<T, C>(grid_level, corner_index<D>(li, align_corners, pl), val[idx]);
+        }
     }
 #pragma unroll
     for (uint32_t idx = 0; idx < (1u << D); idx++) {

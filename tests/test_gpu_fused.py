@@ -125,6 +125,33 @@ def test_fused_scatter_matches_oracle(scene):
         assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max() + 1e-7, (name, np.abs(a - b).max(), np.abs(b).max())
 
 
+def test_fused_scatter_merge_patterns(scene):
+    """every stage of the in-warp merge: runs of 1..70 identical / same-cell points at arbitrary alignment, out-of-range
+    points between them, a tail that does not fill a warp"""
+    from seal3d_b200 import _lib
+    offsets, pls = scene["synth"].grid_offsets()
+    rng = np.random.default_rng(5)
+    pts = []
+    for run in [70, 1, 2, 3, 4, 5, 8, 7, 16, 9, 32, 33, 2, 2, 2, 2, 4, 4, 8, 8, 8, 8, 16, 16, 1, 1, 64, 31, 6, 12, 24, 48] * 6:
+        c = rng.uniform(-0.95, 0.95, size=3)
+        jitter = rng.uniform(0, 1, size=(run, 3)) * rng.choice([0.0, 1e-4, 2e-3, 2e-2])   # same point / same fine cell / same coarse cell
+        pts.append(c + jitter)
+        if rng.uniform() < 0.2:
+            pts.append(np.full((int(rng.integers(1, 4)), 3), 1.5))   # out of range: contributes nothing
+    x0 = np.concatenate(pts).astype(np.float32)[:-5]
+    df = oracle.round_to_half((rng.normal(size=(x0.shape[0], 64)) * 1e-2).astype(np.float32))
+    n = int(offsets[-1])
+    g4 = torch.zeros(n, 4, device=dev())
+    _lib.call("s3d_ngp_scatter", to(x0), to(df).half(), x0.shape[0], 1.0, g4, to(offsets), 16, float(np.log2(pls)), 16, 1.0)
+    u = ((x0 + 1) / 2).astype(np.float32)
+    with scaled(offsets, pls):
+        gs = oracle.grid_encode_backward(np.ascontiguousarray(df[:, :32].reshape(-1, 16, 2).transpose(1, 0, 2)), u, (n, 2), offsets, pls, 16)
+        gc = oracle.grid_encode_backward(np.ascontiguousarray(df[:, 32:].reshape(-1, 16, 2).transpose(1, 0, 2)), u, (n, 2), offsets, pls, 16)
+    got = npy(g4)
+    for name, a, b in (("sigma", got[:, :2], gs), ("colour", got[:, 2:], gc)):
+        assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max() + 1e-7, (name, np.abs(a - b).max(), np.abs(b).max())
+
+
 def test_fused_full_image_render_matches_loop(scene):
     """proxy_dataset-style teacher render of 20 000 pixels of one view: fused single pass vs the reference-shaped eval loop"""
     from seal3d_b200.fused import FusedNGP
