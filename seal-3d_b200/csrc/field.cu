@@ -214,7 +214,8 @@ __device__ __forceinline__ void acc4(const uint2 v, float w, float &a0, float &a
     a0 = __fmaf_rn(w, a.x, a0); a1 = __fmaf_rn(w, a.y, a1); a2 = __fmaf_rn(w, b.x, a2); a3 = __fmaf_rn(w, b.y, a3);
 }
 
-__global__ void __launch_bounds__(256, 3)
+template <int V>
+__global__ void __launch_bounds__(256, V == 0 ? 4 : 3)
 k_ngp_encode_pair(const float *__restrict__ xyz, const float *__restrict__ xyz_teacher, const uint8_t *__restrict__ mask, uint32_t M,
                   float bound, const uint4 *__restrict__ table8, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H,
                   __half *__restrict__ feats_teacher, __half *__restrict__ feats_student) {
@@ -238,7 +239,7 @@ k_ngp_encode_pair(const float *__restrict__ xyz, const float *__restrict__ xyz_t
                 Cell c;
                 locate(g, l, ux, uy, uz, c, nullptr);
                 uint4 v[8];
-                if ((g.pair_ok >> l) & 1u) gather_cell_e16(table8, c, v);
+                if (V == 2 || (V == 1 && ((g.pair_ok >> l) & 1u))) gather_cell_e16(table8, c, v);
                 else {
 #pragma unroll
                     for (int k = 0; k < 8; k++) v[k] = __ldg(table8 + c.idx[k]);
@@ -413,6 +414,77 @@ k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, 
                 }
             }
             if (active) emit(entry(xk, yk, zk), keep[0]);
+        }
+    }
+}
+
+// run-based variant: every run of equal cells is folded into its head lane (segmented suffix sums), one RED per corner and run
+template <bool ADAPTIVE>
+__global__ void __launch_bounds__(256)
+k_ngp_scatter_runs(const float *__restrict__ xyz, const __half *__restrict__ dfeats, uint32_t M, float bound,
+              float4 *__restrict__ grad4, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H, float grad_scale) {
+    __shared__ Geo g;
+    geo_init(g, offsets, L, S, H);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // whole warps stay alive
+    float ux = 0, uy = 0, uz = 0;
+    bool ok = false;
+    if (i < M) ok = to_unit(xyz[(size_t)i * 3], xyz[(size_t)i * 3 + 1], xyz[(size_t)i * 3 + 2], bound, ux, uy, uz);
+    const uint32_t lane = lane_id();
+    const uint4 *row = reinterpret_cast<const uint4 *>(dfeats + (size_t)(i < M ? i : 0) * 64);
+    for (uint32_t grp = 0; grp < 4; grp++) {
+        float ds[8], dc[8];
+        if (ok) { unpack8(__ldg(row + grp), ds); unpack8(__ldg(row + 4 + grp), dc); }
+        else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) { ds[k] = 0.f; dc[k] = 0.f; }
+        }
+#pragma unroll
+        for (uint32_t q = 0; q < 4; q++) {
+            const uint32_t l = grp * 4 + q;
+            if (l >= L) break;
+            Cell c;
+            unsigned long long key = ~0ull;
+            if (ok) locate(g, l, ux, uy, uz, c, &key);
+            else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) { c.idx[k] = 0; c.w[k] = 0.f; }
+            }
+            const float g0 = ds[q * 2] * grad_scale, g1 = ds[q * 2 + 1] * grad_scale, g2 = dc[q * 2] * grad_scale, g3 = dc[q * 2 + 1] * grad_scale;
+            const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+            const bool head = (lane == 0) || (prev != key);
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+            if (__popc(heads) <= 16) {
+                // runs of equal cells: fold every run into its head lane (segmented suffix sums), then one RED per corner
+                const uint32_t after = heads >> 1 >> lane;
+                const uint32_t seg_left = after ? (uint32_t)(__ffs(after) - 1) : (31u - lane);
+                // number of doubling steps the longest run of this warp needs (a run of n lanes needs ceil(log2 n))
+                uint32_t nsteps = 5;
+                if (ADAPTIVE) {
+                    const uint32_t cont = ~heads;                 // bit i: lane i continues the run of lane i-1
+                    const uint32_t c2 = cont & (cont >> 1);       // some run longer than 2
+                    const uint32_t c4 = c2 & (c2 >> 2);           // >= 4 consecutive continuation bits: longer than 4
+                    const uint32_t c8 = c4 & (c4 >> 4);           // >= 8 consecutive: longer than 8
+                    const uint32_t c16 = c8 & (c8 >> 8);          // longer than 16
+                    nsteps = c16 ? 5 : (c8 ? 4 : (c4 ? 3 : (c2 ? 2 : 1)));
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    float a0 = c.w[k] * g0, a1 = c.w[k] * g1, a2 = c.w[k] * g2, a3 = c.w[k] * g3;
+#pragma unroll
+                    for (uint32_t st = 0; st < 5; st++) {
+                        if (st < nsteps) {
+                            const uint32_t d = 1u << st;
+                            const float o0 = __shfl_down_sync(0xffffffffu, a0, d), o1 = __shfl_down_sync(0xffffffffu, a1, d);
+                            const float o2 = __shfl_down_sync(0xffffffffu, a2, d), o3 = __shfl_down_sync(0xffffffffu, a3, d);
+                            if (d <= seg_left) { a0 += o0; a1 += o1; a2 += o2; a3 += o3; }
+                        }
+                    }
+                    if (ok && head) atomicAdd(grad4 + c.idx[k], make_float4(a0, a1, a2, a3));
+                }
+            } else if (ok) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) atomicAdd(grad4 + c.idx[k], make_float4(c.w[k] * g0, c.w[k] * g1, c.w[k] * g2, c.w[k] * g3));
+            }
         }
     }
 }
@@ -974,6 +1046,9 @@ int sm_count() {
 
 // table: interleaved fp16 entries {s0,s1,c0,c1} at table + idx * table_stride (8 = stand-alone table4, 16 = one half of a
 // paired table: pass the pointer already offset by 0 | 8 bytes); feats [M,64] fp16 (sigma feats 0..31, colour feats 32..63)
+static int g_variant[8] = {2, 1, 0, 0, 0, 0, 0, 0};   // experiment knobs (kernel variants), see scripts/kbench.py
+S3D_API int s3d_debug_variant(int which, int value) { if (which < 0 || which >= 8) return S3D_EINVAL; g_variant[which] = value; return 0; }
+
 S3D_API int s3d_ngp_encode(const float *xyz, uint32_t M, float bound, const void *table, uint32_t table_stride, const int *offsets,
                            uint32_t L, float S, uint32_t H, void *feats, int sigma_only, void *stream) {
     if (M == 0) return 0;
@@ -988,8 +1063,8 @@ S3D_API int s3d_ngp_encode_pair(const float *xyz, const float *xyz_teacher, cons
                                 const int *offsets, uint32_t L, float S, uint32_t H, void *feats_teacher, void *feats_student, void *stream) {
     if (M == 0) return 0;
     if (L > kMaxLevels) return S3D_ENOTSUP;
-    k_ngp_encode_pair<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, xyz_teacher, xyz_teacher ? mask : nullptr, M, bound, (const uint4 *)table8, offsets, L, S, H,
-                                                                     (__half *)feats_teacher, (__half *)feats_student);
+#define S3D_EP(V) k_ngp_encode_pair<V><<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, xyz_teacher, xyz_teacher ? mask : nullptr, M, bound, (const uint4 *)table8, offsets, L, S, H, (__half *)feats_teacher, (__half *)feats_student)
+    if (g_variant[0] == 0) S3D_EP(0); else if (g_variant[0] == 1) S3D_EP(1); else S3D_EP(2);
     S3D_RETURN_LAST();
 }
 
@@ -1004,7 +1079,9 @@ S3D_API int s3d_ngp_scatter(const float *xyz, const void *dfeats, uint32_t M, fl
                             float S, uint32_t H, float grad_scale, void *stream) {
     if (M == 0) return 0;
     if (L > kMaxLevels) return S3D_ENOTSUP;
-    k_ngp_scatter<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale);
+    if (g_variant[1] == 0) k_ngp_scatter_runs<false><<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale);
+    else if (g_variant[1] == 1) k_ngp_scatter_runs<true><<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale);
+    else k_ngp_scatter<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale);
     S3D_RETURN_LAST();
 }
 

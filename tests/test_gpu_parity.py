@@ -427,6 +427,24 @@ def test_grid_encode_full_size_linearity():
     np.testing.assert_allclose(npy(a[:, to(sub)]), ref, rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_grid_encode_staged_kernel_equals_per_point_kernel(dtype):
+    """B >= 2^20 takes the persistent kernel with the coarse levels staged in shared memory (TMA bulk copy): its output must
+    be bit-identical to the per-point kernel, which the same points reach in chunks below the threshold"""
+    offsets, pls, emb = _grid(seed=4)
+    B = (1 << 20) + 77
+    x = np.random.default_rng(18).uniform(0, 1, (B, 3)).astype(np.float32)
+    x[5] = [1.5, 0.2, 0.2]
+    x[B - 1] = [0.3, -0.1, 0.9]
+    x[1 << 19] = [1.0, 1.0, 1.0]
+    x[12345] = [0.0, 0.0, 0.0]
+    full, _ = _enc_raw(x, emb, offsets, pls, dtype=dtype)
+    for lo in range(0, B, 1 << 19):
+        part, _ = _enc_raw(x[lo:lo + (1 << 19)], emb, offsets, pls, dtype=dtype)
+        assert torch.equal(full[:, lo:lo + (1 << 19)], part), lo
+    assert not full[:, 5].any() and not full[:, B - 1].any()
+
+
 # --------------------------------------------------------------------------------- SH / freq
 
 
