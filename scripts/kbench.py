@@ -68,7 +68,7 @@ def main():
         r = measure(tr, resident)
         print(json.dumps({"variant": label, **{k.replace("s3d_", ""): round(r.get(k, 0.0), 4) for k in keys}}), flush=True)
 
-    for gv in (1, 0):   # stand-alone grid_encode_forward on 2^22 random points: 1 = per-point kernel, 0 = staged coarse levels
+    for gv in (0, 5, 2, 3, 4):   # stand-alone grid_encode_forward on 2^22 random points: 1 = per-point kernel, 0 = staged coarse levels
         lib.s3d_debug_grid_variant(gv)
         g = {p: bench.roofline_grid_encode(dev, p) for p in ("fp32", "fp16")}
         print(json.dumps({"grid_variant": gv, "fp32_ms": round(g["fp32"]["launch_ms"], 4), "fp32_frac": round(g["fp32"]["frac"], 4),
@@ -82,7 +82,7 @@ def main():
             lib.s3d_debug_variant(int(which), int(v))
             run("%s=%s" % (which, v))
         # back to the default of this knob
-        lib.s3d_debug_variant(int(which), defaults.get(int(which), {0: 2, 1: 1}.get(int(which), 0)))
+        lib.s3d_debug_variant(int(which), defaults.get(int(which), 0))
 
 
 if __name__ == "__main__":

@@ -115,22 +115,72 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<const uint32_t *>(&h);
 }
 
-__device__ __forceinline__ uint2 ld_entry(const uint8_t *__restrict__ table, uint32_t idx, uint32_t stride) {
-    return __ldg(reinterpret_cast<const uint2 *>(table + (size_t)idx * stride));
+// L2 residency hints.  Inside one of these kernels only the hash tables (and the gradient table) are reused; every
+// sample-sized stream (positions, feature rows, feature gradients) is touched exactly once but is several times larger
+// than the 126 MB L2, so without hints it evicts the tables and the gathers go to DRAM as random 32-byte sectors.
+//   HINT 0: none;  1: streams use evict-first loads / stores (ld/st.global.cs);  2: additionally the table gathers and the
+//   gradient REDs carry an L2 evict_last cache policy.
+template <int HINT>
+__device__ __forceinline__ uint64_t table_policy() {
+    uint64_t pol = 0;
+    if constexpr (HINT == 2) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <int HINT>
+__device__ __forceinline__ uint4 ld_table16(const uint4 *p, uint64_t pol) {
+    if constexpr (HINT == 2) {
+        uint4 v;
+        asm("ld.global.nc.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+        return v;
+    } else return __ldg(p);
+}
+template <int HINT>
+__device__ __forceinline__ uint2 ld_table8(const uint2 *p, uint64_t pol) {
+    if constexpr (HINT == 2) {
+        uint2 v;
+        asm("ld.global.nc.L2::cache_hint.v2.b32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+        return v;
+    } else return __ldg(p);
+}
+template <int HINT>
+__device__ __forceinline__ void red_table16(float4 *p, float a, float b, float c, float d, uint64_t pol) {
+    if constexpr (HINT == 2)
+        asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "l"(pol) : "memory");
+    else atomicAdd(p, make_float4(a, b, c, d));
+}
+template <int HINT, typename V>
+__device__ __forceinline__ V ld_stream(const V *p) {
+    if constexpr (HINT >= 1) return __ldcs(p);
+    else return __ldg(p);
+}
+template <int HINT, typename V>
+__device__ __forceinline__ void st_stream(V *p, const V v) {
+    if constexpr (HINT >= 1) __stcs(p, v);
+    else *p = v;
+}
+template <int HINT>
+__device__ __forceinline__ bool load_unit(const float *__restrict__ xyz, uint32_t i, float bound, float &ux, float &uy, float &uz) {
+    return to_unit(ld_stream<HINT>(xyz + (size_t)i * 3), ld_stream<HINT>(xyz + (size_t)i * 3 + 1), ld_stream<HINT>(xyz + (size_t)i * 3 + 2), bound, ux, uy, uz);
+}
+
+template <int HINT>
+__device__ __forceinline__ uint2 ld_entry(const uint8_t *__restrict__ table, uint32_t idx, uint32_t stride, uint64_t pol) {
+    return ld_table8<HINT>(reinterpret_cast<const uint2 *>(table + (size_t)idx * stride), pol);
 }
 
 // The two x-corners of a cell, idx[2j] and idx[2j+1], are the halves of one ALIGNED entry pair whenever they differ in
 // bit 0 only (even x on hashed levels, even dense index otherwise): one double-width load then serves both.  The L1 tag
 // stage pays per (lane, sector), so this removes a quarter of the gather cost on average.  All loads are issued before any
 // use (the unmerged second load is predicated, not branched) so the 8 gathers of a level stay in flight together.
-__device__ __forceinline__ void gather_cell_e8(const uint8_t *__restrict__ table, const Cell &c, uint2 (&v)[8]) {
+template <int HINT>
+__device__ __forceinline__ void gather_cell_e8(const uint8_t *__restrict__ table, const Cell &c, uint2 (&v)[8], uint64_t pol) {
     uint4 a[4];
     bool merged[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         merged[j] = (c.idx[2 * j] ^ c.idx[2 * j + 1]) == 1u;
-        a[j] = __ldg(reinterpret_cast<const uint4 *>(table) + (c.idx[2 * j] >> 1));
-        if (!merged[j]) v[2 * j + 1] = __ldg(reinterpret_cast<const uint2 *>(table) + c.idx[2 * j + 1]);
+        a[j] = ld_table16<HINT>(reinterpret_cast<const uint4 *>(table) + (c.idx[2 * j] >> 1), pol);
+        if (!merged[j]) v[2 * j + 1] = ld_table8<HINT>(reinterpret_cast<const uint2 *>(table) + c.idx[2 * j + 1], pol);
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -141,29 +191,7 @@ __device__ __forceinline__ void gather_cell_e8(const uint8_t *__restrict__ table
     }
 }
 
-__device__ __forceinline__ void ldg256(const void *p, uint4 &lo, uint4 &hi) {  // LDG.E.ENL2.256 (sm_100)
-    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(p));
-}
-
-// same for the 16-byte entries of a paired table: an aligned pair is one 32-byte sector
-__device__ __forceinline__ void gather_cell_e16(const uint4 *__restrict__ table8, const Cell &c, uint4 (&v)[8]) {
-    uint4 lo[4], hi[4];
-    bool merged[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        merged[j] = (c.idx[2 * j] ^ c.idx[2 * j + 1]) == 1u;
-        ldg256(table8 + (c.idx[2 * j] & ~1u), lo[j], hi[j]);
-        if (!merged[j]) v[2 * j + 1] = __ldg(table8 + c.idx[2 * j + 1]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const bool odd = c.idx[2 * j] & 1u;
-        v[2 * j] = odd ? hi[j] : lo[j];
-        if (merged[j]) v[2 * j + 1] = odd ? lo[j] : hi[j];
-    }
-}
-
+template <int HINT>
 __global__ void __launch_bounds__(256)
 k_ngp_encode(const float *__restrict__ xyz, uint32_t M, float bound, const uint8_t *__restrict__ table, uint32_t stride,
              const int *__restrict__ offsets, uint32_t L, float S, uint32_t H, __half *__restrict__ feats, int sigma_only) {
@@ -172,7 +200,8 @@ k_ngp_encode(const float *__restrict__ xyz, uint32_t M, float bound, const uint8
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
     float ux, uy, uz;
-    const bool ok = to_unit(xyz[(size_t)i * 3], xyz[(size_t)i * 3 + 1], xyz[(size_t)i * 3 + 2], bound, ux, uy, uz);
+    const bool ok = load_unit<HINT>(xyz, i, bound, ux, uy, uz);
+    const uint64_t pol = table_policy<HINT>();
     uint4 *row = reinterpret_cast<uint4 *>(feats + (size_t)i * 64);
     for (uint32_t grp = 0; grp < 4; grp++) {      // 4 levels -> one 16-byte chunk per table
         uint32_t fs[4], fc[4];   // one packed half2 per level: 4 levels -> one 16-byte chunk per table
@@ -184,10 +213,10 @@ k_ngp_encode(const float *__restrict__ xyz, uint32_t M, float bound, const uint8
                 Cell c;
                 locate(g, l, ux, uy, uz, c, nullptr);
                 uint2 v[8];
-                if (stride == 8 && ((g.pair_ok >> l) & 1u)) gather_cell_e8(table, c, v);
+                if (stride == 8 && ((g.pair_ok >> l) & 1u)) gather_cell_e8<HINT>(table, c, v, pol);
                 else {
 #pragma unroll
-                    for (int k = 0; k < 8; k++) v[k] = ld_entry(table, c.idx[k], stride);
+                    for (int k = 0; k < 8; k++) v[k] = ld_entry<HINT>(table, c.idx[k], stride, pol);
                 }
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
@@ -199,8 +228,8 @@ k_ngp_encode(const float *__restrict__ xyz, uint32_t M, float bound, const uint8
             }
             fs[q] = pack2(s0, s1); fc[q] = pack2(c0, c1);
         }
-        row[grp] = make_uint4(fs[0], fs[1], fs[2], fs[3]);
-        if (!sigma_only) row[4 + grp] = make_uint4(fc[0], fc[1], fc[2], fc[3]);
+        st_stream<HINT>(row + grp, make_uint4(fs[0], fs[1], fs[2], fs[3]));
+        if (!sigma_only) st_stream<HINT>(row + 4 + grp, make_uint4(fc[0], fc[1], fc[2], fc[3]));
     }
 }
 
@@ -214,8 +243,8 @@ __device__ __forceinline__ void acc4(const uint2 v, float w, float &a0, float &a
     a0 = __fmaf_rn(w, a.x, a0); a1 = __fmaf_rn(w, a.y, a1); a2 = __fmaf_rn(w, b.x, a2); a3 = __fmaf_rn(w, b.y, a3);
 }
 
-template <int V>
-__global__ void __launch_bounds__(256, V == 0 ? 4 : 3)
+template <int HINT>
+__global__ void __launch_bounds__(256, 4)
 k_ngp_encode_pair(const float *__restrict__ xyz, const float *__restrict__ xyz_teacher, const uint8_t *__restrict__ mask, uint32_t M,
                   float bound, const uint4 *__restrict__ table8, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H,
                   __half *__restrict__ feats_teacher, __half *__restrict__ feats_student) {
@@ -224,10 +253,11 @@ k_ngp_encode_pair(const float *__restrict__ xyz, const float *__restrict__ xyz_t
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
     float ux, uy, uz, tx = 0, ty = 0, tz = 0;
-    const bool ok = to_unit(xyz[(size_t)i * 3], xyz[(size_t)i * 3 + 1], xyz[(size_t)i * 3 + 2], bound, ux, uy, uz);
+    const bool ok = load_unit<HINT>(xyz, i, bound, ux, uy, uz);
     const bool moved = mask && mask[i];
     bool tok = ok;
-    if (moved) tok = to_unit(xyz_teacher[(size_t)i * 3], xyz_teacher[(size_t)i * 3 + 1], xyz_teacher[(size_t)i * 3 + 2], bound, tx, ty, tz);
+    if (moved) tok = load_unit<HINT>(xyz_teacher, i, bound, tx, ty, tz);
+    const uint64_t pol = table_policy<HINT>();
     uint4 *row_t = reinterpret_cast<uint4 *>(feats_teacher + (size_t)i * 64), *row_s = reinterpret_cast<uint4 *>(feats_student + (size_t)i * 64);
     for (uint32_t grp = 0; grp < 4; grp++) {
         uint32_t ts[4], tc[4], ss[4], sc[4];
@@ -239,11 +269,8 @@ k_ngp_encode_pair(const float *__restrict__ xyz, const float *__restrict__ xyz_t
                 Cell c;
                 locate(g, l, ux, uy, uz, c, nullptr);
                 uint4 v[8];
-                if (V == 2 || (V == 1 && ((g.pair_ok >> l) & 1u))) gather_cell_e16(table8, c, v);
-                else {
 #pragma unroll
-                    for (int k = 0; k < 8; k++) v[k] = __ldg(table8 + c.idx[k]);
-                }
+                for (int k = 0; k < 8; k++) v[k] = ld_table16<HINT>(table8 + c.idx[k], pol);
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     acc4(make_uint2(v[k].z, v[k].w), c.w[k], s0, s1, s2, s3);
@@ -255,14 +282,14 @@ k_ngp_encode_pair(const float *__restrict__ xyz, const float *__restrict__ xyz_t
                 locate(g, l, tx, ty, tz, c, nullptr);
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    const uint4 v = __ldg(table8 + c.idx[k]);
+                    const uint4 v = ld_table16<HINT>(table8 + c.idx[k], pol);
                     acc4(make_uint2(v.x, v.y), c.w[k], t0, t1, t2, t3);
                 }
             }
             ts[q] = pack2(t0, t1); tc[q] = pack2(t2, t3); ss[q] = pack2(s0, s1); sc[q] = pack2(s2, s3);
         }
-        row_t[grp] = make_uint4(ts[0], ts[1], ts[2], ts[3]); row_t[4 + grp] = make_uint4(tc[0], tc[1], tc[2], tc[3]);
-        row_s[grp] = make_uint4(ss[0], ss[1], ss[2], ss[3]); row_s[4 + grp] = make_uint4(sc[0], sc[1], sc[2], sc[3]);
+        st_stream<HINT>(row_t + grp, make_uint4(ts[0], ts[1], ts[2], ts[3])); st_stream<HINT>(row_t + 4 + grp, make_uint4(tc[0], tc[1], tc[2], tc[3]));
+        st_stream<HINT>(row_s + grp, make_uint4(ss[0], ss[1], ss[2], ss[3])); st_stream<HINT>(row_s + 4 + grp, make_uint4(sc[0], sc[1], sc[2], sc[3]));
     }
 }
 
@@ -276,14 +303,7 @@ __global__ void k_pair_tables(const uint2 *__restrict__ teacher4, const uint2 *_
 // ------------------------------------------------------------------------------------------------
 // scatter: dfeats -> interleaved fp32 gradient table
 // ------------------------------------------------------------------------------------------------
-// Warp-level pre-reduction.  Samples arrive ray-major, so on the coarse levels aligned groups of 2/4/8/16/32 lanes sit in
-// the same cell and address the same 8 entries.  Instead of reducing each of the 32 products (8 corners x 4 channels)
-// with its own shuffle tree (160 shuffles), the group splits the work while it reduces: at the xor-1 stage a lane hands
-// the four corners of the other z-face to its partner and receives the partner's share of its own face (16 shuffles), at
-// xor-2 it keeps one y-edge of that face (8), at xor-4 one corner (4); xor-8 / xor-16 fold whole corners (4 + 4).  A
-// uniform octet therefore ends with ONE 16-byte RED per lane -- 8 per octet instead of 64 -- after 28 shuffles.  A lane
-// whose group stops being uniform at some stage emits what it holds there.  Stages run only when enough groups profit
-// (a stage costs its shuffles for the whole warp; every merged lane saves half of its remaining REDs).
+template <int HINT>
 __global__ void __launch_bounds__(256)
 k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, uint32_t M, float bound,
               float4 *__restrict__ grad4, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H, float grad_scale) {
@@ -292,148 +312,13 @@ k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, 
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // whole warps stay alive
     float ux = 0, uy = 0, uz = 0;
     bool ok = false;
-    if (i < M) ok = to_unit(xyz[(size_t)i * 3], xyz[(size_t)i * 3 + 1], xyz[(size_t)i * 3 + 2], bound, ux, uy, uz);
-    const uint32_t lane = lane_id();
-    const bool b0 = lane & 1u, b1 = lane & 2u, b2 = lane & 4u;
-    const uint4 *row = reinterpret_cast<const uint4 *>(dfeats + (size_t)(i < M ? i : 0) * 64);
-    constexpr uint32_t kFull = 0xffffffffu;
-    for (uint32_t grp = 0; grp < 4; grp++) {
-        float ds[8], dc[8];
-        if (ok) { unpack8(__ldg(row + grp), ds); unpack8(__ldg(row + 4 + grp), dc); }
-        else {
-#pragma unroll
-            for (int k = 0; k < 8; k++) { ds[k] = 0.f; dc[k] = 0.f; }
-        }
-#pragma unroll
-        for (uint32_t q = 0; q < 4; q++) {
-            const uint32_t l = grp * 4 + q;
-            if (l >= L) break;
-            // cell of this sample in level l (same arithmetic as locate())
-            const float sc = g.scale[l];
-            const float px = __fmaf_rn(ux, sc, 0.5f), py = __fmaf_rn(uy, sc, 0.5f), pz = __fmaf_rn(uz, sc, 0.5f);
-            const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
-            const uint32_t gx = (uint32_t)fx0, gy = (uint32_t)fy0, gz = (uint32_t)fz0;
-            const float fx = ok ? __fsub_rn(px, fx0) : 0.f, fy = ok ? __fsub_rn(py, fy0) : 0.f, fz = ok ? __fsub_rn(pz, fz0) : 0.f;
-            const unsigned long long key = ok ? ((unsigned long long)gx | ((unsigned long long)gy << 21) | ((unsigned long long)gz << 42)) : ~0ull;
-            const uint32_t size = g.size[l], off = g.offset[l], r1 = g.res1[l];
-            const bool hashed = (g.hashed >> l) & 1u, p2 = (g.pow2 >> l) & 1u;
-            auto entry = [&](uint32_t x, uint32_t y, uint32_t z) -> uint32_t {
-                uint32_t id;
-                if (hashed) {
-                    id = x ^ (y * 2654435761u) ^ (z * 805459861u);
-                    id = p2 ? (id & (size - 1)) : (id % size);
-                } else {
-                    id = x + y * r1;
-                    if (r1 * r1 <= size) id += z * r1 * r1;
-                    id = id % size;
-                }
-                return off + id;
-            };
-            auto emit = [&](uint32_t id, const float (&v)[4]) { atomicAdd(grad4 + id, make_float4(v[0], v[1], v[2], v[3])); };
-            const float gv[4] = {ds[q * 2] * grad_scale, ds[q * 2 + 1] * grad_scale, dc[q * 2] * grad_scale, dc[q * 2 + 1] * grad_scale};
-
-            // bit i of same: lane i sits in the cell of lane i-1; an aligned group of n lanes is uniform iff bits base+1 .. base+n-1 are set
-            const unsigned long long prev = __shfl_up_sync(kFull, key, 1);
-            const uint32_t same = __ballot_sync(kFull, lane != 0 && prev == key);
-            auto uniform = [&](uint32_t n) -> bool {
-                const uint32_t mask = ((1u << (n - 1)) - 1u) << ((lane & ~(n - 1)) + 1);
-                return (same & mask) == mask;
-            };
-            const bool u2 = uniform(2);
-            const uint32_t n2 = __popc(__ballot_sync(kFull, u2));
-            if (n2 < 6) {  // fewer than three mergeable pairs: every sample scatters its own eight corners
-                if (ok) {
-#pragma unroll
-                    for (uint32_t k = 0; k < 8; k++) {
-                        const float w = ((k & 1u) ? fx : 1.0f - fx) * ((k & 2u) ? fy : 1.0f - fy) * ((k & 4u) ? fz : 1.0f - fz);
-                        const float v[4] = {w * gv[0], w * gv[1], w * gv[2], w * gv[3]};
-                        emit(entry(gx + (k & 1u), gy + ((k >> 1) & 1u), gz + (k >> 2)), v);
-                    }
-                }
-                continue;
-            }
-            // "k" = the half this lane keeps at a stage, "s" = the half it sends: z by lane bit 0, y by bit 1, x by bit 2
-            const float wzk = b0 ? fz : 1.0f - fz, wzs = b0 ? 1.0f - fz : fz;
-            const float wyk = b1 ? fy : 1.0f - fy, wys = b1 ? 1.0f - fy : fy;
-            const float wxk = b2 ? fx : 1.0f - fx, wxs = b2 ? 1.0f - fx : fx;
-            const uint32_t zk = gz + (b0 ? 1u : 0u), zs = gz + (b0 ? 0u : 1u);
-            const uint32_t yk = gy + (b1 ? 1u : 0u), ys = gy + (b1 ? 0u : 1u);
-            const uint32_t xk = gx + (b2 ? 1u : 0u), xs = gx + (b2 ? 0u : 1u);
-            // face z = k: corners c[0] = (xk,yk) c[1] = (xs,yk) c[2] = (xk,ys) c[3] = (xs,ys); same order on the face z = s
-            float keep[4][4], send[4][4];
-            {
-                const float wxy[4] = {wxk * wyk, wxs * wyk, wxk * wys, wxs * wys};
-#pragma unroll
-                for (int c = 0; c < 4; c++)
-#pragma unroll
-                    for (int ch = 0; ch < 4; ch++) { keep[c][ch] = wxy[c] * wzk * gv[ch]; send[c][ch] = wxy[c] * wzs * gv[ch]; }
-            }
-            // ---- xor 1: z faces ----
-            if (ok && !u2) {
-                emit(entry(xk, yk, zs), send[0]); emit(entry(xs, yk, zs), send[1]); emit(entry(xk, ys, zs), send[2]); emit(entry(xs, ys, zs), send[3]);
-                emit(entry(xk, yk, zk), keep[0]); emit(entry(xs, yk, zk), keep[1]); emit(entry(xk, ys, zk), keep[2]); emit(entry(xs, ys, zk), keep[3]);
-            }
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-#pragma unroll
-                for (int ch = 0; ch < 4; ch++) keep[c][ch] += __shfl_xor_sync(kFull, send[c][ch], 1);
-            bool active = ok && u2;
-            // ---- xor 2: y edges of the kept face (keep[0..1] stay, keep[2..3] go) ----
-            const bool u4 = uniform(4);
-            if (__popc(__ballot_sync(kFull, u4)) < 8) {  // fewer than two mergeable quads
-                if (active) { emit(entry(xk, yk, zk), keep[0]); emit(entry(xs, yk, zk), keep[1]); emit(entry(xk, ys, zk), keep[2]); emit(entry(xs, ys, zk), keep[3]); }
-                continue;
-            }
-            if (active && !u4) { emit(entry(xk, yk, zk), keep[0]); emit(entry(xs, yk, zk), keep[1]); emit(entry(xk, ys, zk), keep[2]); emit(entry(xs, ys, zk), keep[3]); }
-#pragma unroll
-            for (int c = 0; c < 2; c++)
-#pragma unroll
-                for (int ch = 0; ch < 4; ch++) keep[c][ch] += __shfl_xor_sync(kFull, keep[2 + c][ch], 2);
-            active = active && u4;
-            // ---- xor 4: x corners of the kept edge ----
-            const bool u8 = uniform(8);
-            if (!__any_sync(kFull, u8)) {
-                if (active) { emit(entry(xk, yk, zk), keep[0]); emit(entry(xs, yk, zk), keep[1]); }
-                continue;
-            }
-            if (active && !u8) { emit(entry(xk, yk, zk), keep[0]); emit(entry(xs, yk, zk), keep[1]); }
-#pragma unroll
-            for (int ch = 0; ch < 4; ch++) keep[0][ch] += __shfl_xor_sync(kFull, keep[1][ch], 4);
-            active = active && u8;
-            // ---- xor 8 / xor 16: fold whole corners into the lower octet / half ----
-            const bool u16 = uniform(16);
-            if (__any_sync(kFull, u16)) {
-                if (active && !u16) { emit(entry(xk, yk, zk), keep[0]); active = false; }
-#pragma unroll
-                for (int ch = 0; ch < 4; ch++) keep[0][ch] += __shfl_xor_sync(kFull, keep[0][ch], 8);
-                active = active && !(lane & 8u);
-                if (same == 0xfffffffeu) {  // the whole warp in one cell
-#pragma unroll
-                    for (int ch = 0; ch < 4; ch++) keep[0][ch] += __shfl_xor_sync(kFull, keep[0][ch], 16);
-                    active = active && !(lane & 16u);
-                }
-            }
-            if (active) emit(entry(xk, yk, zk), keep[0]);
-        }
-    }
-}
-
-// run-based variant: every run of equal cells is folded into its head lane (segmented suffix sums), one RED per corner and run
-template <bool ADAPTIVE>
-__global__ void __launch_bounds__(256)
-k_ngp_scatter_runs(const float *__restrict__ xyz, const __half *__restrict__ dfeats, uint32_t M, float bound,
-              float4 *__restrict__ grad4, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H, float grad_scale) {
-    __shared__ Geo g;
-    geo_init(g, offsets, L, S, H);
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // whole warps stay alive
-    float ux = 0, uy = 0, uz = 0;
-    bool ok = false;
-    if (i < M) ok = to_unit(xyz[(size_t)i * 3], xyz[(size_t)i * 3 + 1], xyz[(size_t)i * 3 + 2], bound, ux, uy, uz);
+    if (i < M) ok = load_unit<HINT>(xyz, i, bound, ux, uy, uz);
+    const uint64_t pol = table_policy<HINT>();
     const uint32_t lane = lane_id();
     const uint4 *row = reinterpret_cast<const uint4 *>(dfeats + (size_t)(i < M ? i : 0) * 64);
     for (uint32_t grp = 0; grp < 4; grp++) {
         float ds[8], dc[8];
-        if (ok) { unpack8(__ldg(row + grp), ds); unpack8(__ldg(row + 4 + grp), dc); }
+        if (ok) { unpack8(ld_stream<HINT>(row + grp), ds); unpack8(ld_stream<HINT>(row + 4 + grp), dc); }
         else {
 #pragma unroll
             for (int k = 0; k < 8; k++) { ds[k] = 0.f; dc[k] = 0.f; }
@@ -458,15 +343,12 @@ k_ngp_scatter_runs(const float *__restrict__ xyz, const __half *__restrict__ dfe
                 const uint32_t after = heads >> 1 >> lane;
                 const uint32_t seg_left = after ? (uint32_t)(__ffs(after) - 1) : (31u - lane);
                 // number of doubling steps the longest run of this warp needs (a run of n lanes needs ceil(log2 n))
-                uint32_t nsteps = 5;
-                if (ADAPTIVE) {
-                    const uint32_t cont = ~heads;                 // bit i: lane i continues the run of lane i-1
-                    const uint32_t c2 = cont & (cont >> 1);       // some run longer than 2
-                    const uint32_t c4 = c2 & (c2 >> 2);           // >= 4 consecutive continuation bits: longer than 4
-                    const uint32_t c8 = c4 & (c4 >> 4);           // >= 8 consecutive: longer than 8
-                    const uint32_t c16 = c8 & (c8 >> 8);          // longer than 16
-                    nsteps = c16 ? 5 : (c8 ? 4 : (c4 ? 3 : (c2 ? 2 : 1)));
-                }
+                const uint32_t cont = ~heads;                 // bit i: lane i continues the run of lane i-1
+                const uint32_t c2 = cont & (cont >> 1);       // some run longer than 2
+                const uint32_t c4 = c2 & (c2 >> 2);           // >= 4 consecutive continuation bits: longer than 4
+                const uint32_t c8 = c4 & (c4 >> 4);           // >= 8 consecutive: longer than 8
+                const uint32_t c16 = c8 & (c8 >> 8);          // longer than 16
+                const uint32_t nsteps = c16 ? 5 : (c8 ? 4 : (c4 ? 3 : (c2 ? 2 : 1)));
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     float a0 = c.w[k] * g0, a1 = c.w[k] * g1, a2 = c.w[k] * g2, a3 = c.w[k] * g3;
@@ -479,11 +361,11 @@ k_ngp_scatter_runs(const float *__restrict__ xyz, const __half *__restrict__ dfe
                             if (d <= seg_left) { a0 += o0; a1 += o1; a2 += o2; a3 += o3; }
                         }
                     }
-                    if (ok && head) atomicAdd(grad4 + c.idx[k], make_float4(a0, a1, a2, a3));
+                    if (ok && head) red_table16<HINT>(grad4 + c.idx[k], a0, a1, a2, a3, pol);
                 }
             } else if (ok) {
 #pragma unroll
-                for (int k = 0; k < 8; k++) atomicAdd(grad4 + c.idx[k], make_float4(c.w[k] * g0, c.w[k] * g1, c.w[k] * g2, c.w[k] * g3));
+                for (int k = 0; k < 8; k++) red_table16<HINT>(grad4 + c.idx[k], c.w[k] * g0, c.w[k] * g1, c.w[k] * g2, c.w[k] * g3, pol);
             }
         }
     }
@@ -1046,7 +928,7 @@ int sm_count() {
 
 // table: interleaved fp16 entries {s0,s1,c0,c1} at table + idx * table_stride (8 = stand-alone table4, 16 = one half of a
 // paired table: pass the pointer already offset by 0 | 8 bytes); feats [M,64] fp16 (sigma feats 0..31, colour feats 32..63)
-static int g_variant[8] = {2, 1, 0, 0, 0, 0, 0, 0};   // experiment knobs (kernel variants), see scripts/kbench.py
+static int g_variant[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // experiment knobs (kernel variants), see scripts/kbench.py
 S3D_API int s3d_debug_variant(int which, int value) { if (which < 0 || which >= 8) return S3D_EINVAL; g_variant[which] = value; return 0; }
 
 S3D_API int s3d_ngp_encode(const float *xyz, uint32_t M, float bound, const void *table, uint32_t table_stride, const int *offsets,
@@ -1054,7 +936,9 @@ S3D_API int s3d_ngp_encode(const float *xyz, uint32_t M, float bound, const void
     if (M == 0) return 0;
     if (L > kMaxLevels) return S3D_ENOTSUP;
     if (table_stride != 8 && table_stride != 16) return S3D_EINVAL;
-    k_ngp_encode<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, M, bound, (const uint8_t *)table, table_stride, offsets, L, S, H, (__half *)feats, sigma_only);
+#define S3D_EN(HINT) k_ngp_encode<HINT><<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, M, bound, (const uint8_t *)table, table_stride, offsets, L, S, H, (__half *)feats, sigma_only)
+    if (g_variant[2] == 0) S3D_EN(0); else if (g_variant[2] == 1) S3D_EN(1); else S3D_EN(2);
+#undef S3D_EN
     S3D_RETURN_LAST();
 }
 
@@ -1063,8 +947,9 @@ S3D_API int s3d_ngp_encode_pair(const float *xyz, const float *xyz_teacher, cons
                                 const int *offsets, uint32_t L, float S, uint32_t H, void *feats_teacher, void *feats_student, void *stream) {
     if (M == 0) return 0;
     if (L > kMaxLevels) return S3D_ENOTSUP;
-#define S3D_EP(V) k_ngp_encode_pair<V><<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, xyz_teacher, xyz_teacher ? mask : nullptr, M, bound, (const uint4 *)table8, offsets, L, S, H, (__half *)feats_teacher, (__half *)feats_student)
+#define S3D_EP(HINT) k_ngp_encode_pair<HINT><<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, xyz_teacher, xyz_teacher ? mask : nullptr, M, bound, (const uint4 *)table8, offsets, L, S, H, (__half *)feats_teacher, (__half *)feats_student)
     if (g_variant[0] == 0) S3D_EP(0); else if (g_variant[0] == 1) S3D_EP(1); else S3D_EP(2);
+#undef S3D_EP
     S3D_RETURN_LAST();
 }
 
@@ -1079,9 +964,9 @@ S3D_API int s3d_ngp_scatter(const float *xyz, const void *dfeats, uint32_t M, fl
                             float S, uint32_t H, float grad_scale, void *stream) {
     if (M == 0) return 0;
     if (L > kMaxLevels) return S3D_ENOTSUP;
-    if (g_variant[1] == 0) k_ngp_scatter_runs<false><<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale);
-    else if (g_variant[1] == 1) k_ngp_scatter_runs<true><<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale);
-    else k_ngp_scatter<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale);
+#define S3D_SC(HINT) k_ngp_scatter<HINT><<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale)
+    if (g_variant[1] == 0) S3D_SC(0); else if (g_variant[1] == 1) S3D_SC(1); else S3D_SC(2);
+#undef S3D_SC
     S3D_RETURN_LAST();
 }
 

@@ -158,10 +158,18 @@ template <typename T> __device__ __forceinline__ float to_float(T v);
 template <> __device__ __forceinline__ float to_float<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_float<__half>(__half v) { return __half2float(v); }
 
-template <typename T, uint32_t C>
+// STREAM: evict-first store (st.global.cs) -- the output is written once and is larger than L2; keeping it from
+// displacing the table is what lets the gathers hit L2
+template <typename T, uint32_t C, bool STREAM = false>
 __device__ __forceinline__ void store_vec(T *__restrict__ p, const float (&v)[C]) {
-    if constexpr (sizeof(T) == 4 && C == 2) { *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]); }
-    else if constexpr (sizeof(T) == 2 && C == 2) { *reinterpret_cast<__half2 *>(p) = __floats2half2_rn(v[0], v[1]); }
+    if constexpr (sizeof(T) == 4 && C == 2) {
+        if constexpr (STREAM) __stcs(reinterpret_cast<float2 *>(p), make_float2(v[0], v[1]));
+        else *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+    } else if constexpr (sizeof(T) == 2 && C == 2) {
+        const __half2 h = __floats2half2_rn(v[0], v[1]);
+        if constexpr (STREAM) __stcs(reinterpret_cast<unsigned int *>(p), *reinterpret_cast<const unsigned int *>(&h));
+        else *reinterpret_cast<__half2 *>(p) = h;
+    }
     else {
 #pragma unroll
         for (uint32_t c = 0; c < C; c++) p[c] = from_float<T>(v[c]);
@@ -285,7 +293,7 @@ __device__ __forceinline__ void encode_level(const float (&x)[D], const T *__res
 }
 
 // ALL_LEVELS: blockIdx.y unused, thread loops over levels.  Otherwise blockIdx.y = level.
-template <typename T, uint32_t D, uint32_t C, bool ALL_LEVELS>
+template <typename T, uint32_t D, uint32_t C, bool ALL_LEVELS, bool STREAM = false>
 __global__ void __launch_bounds__(256)
 k_grid_forward(const float *__restrict__ inputs, const T *__restrict__ grid, const int *__restrict__ offsets,
                T *__restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, T *__restrict__ dy_dx,
@@ -294,7 +302,7 @@ k_grid_forward(const float *__restrict__ inputs, const T *__restrict__ grid, con
     if (b >= B) return;
     float x[D];
 #pragma unroll
-    for (uint32_t d = 0; d < D; d++) x[d] = __ldg(inputs + (size_t)b * D + d);
+    for (uint32_t d = 0; d < D; d++) x[d] = STREAM ? __ldcs(inputs + (size_t)b * D + d) : __ldg(inputs + (size_t)b * D + d);
     const bool oob = out_of_range<D>(x);
     const uint32_t l0 = ALL_LEVELS ? 0 : blockIdx.y, l1 = ALL_LEVELS ? L : blockIdx.y + 1;
 #pragma unroll 2
@@ -310,7 +318,7 @@ k_grid_forward(const float *__restrict__ inputs, const T *__restrict__ grid, con
             const LevelInfo li = level_info<D>(offsets, level, S, H, gridtype, align_corners);
             encode_level<T, D, C>(x, grid + (size_t)(uint32_t)__ldg(offsets + level) * C, li, align_corners, interp, res, dd);
         }
-        store_vec<T, C>(outputs + ((size_t)level * B + b) * C, res);
+        store_vec<T, C, STREAM>(outputs + ((size_t)level * B + b) * C, res);
     }
 }
 
@@ -559,21 +567,25 @@ __global__ void k_level_scales(uint32_t L, float S, uint32_t H, float *__restric
 
 constexpr uint32_t kBigBatch = 1u << 17;     // from here one thread walks all levels of its point
 constexpr uint32_t kStagedBatch = 1u << 20;  // from here the persistent kernel with the coarse levels staged in shared memory pays
-int g_grid_variant = 0;                      // experiment knob: 1 = never use the staged kernel
+int g_grid_variant = 0;                      // experiment knob: 0 per-point kernel, 2/3/4 staged (48 KB / 160 KB / max), 5 per-point + stream hints
 
 template <typename T, uint32_t D, uint32_t C>
 int launch_forward(const float *inputs, const T *emb, const int *offsets, T *outputs, uint32_t B, uint32_t L, float S,
                    uint32_t H, T *dy_dx, uint32_t gridtype, bool ac, uint32_t interp, cudaStream_t st) {
-    if (B >= kStagedBatch && dy_dx == nullptr && g_grid_variant != 1) {
+    if (B >= kStagedBatch && dy_dx == nullptr && g_grid_variant >= 2 && g_grid_variant <= 4) {
         int dev = 0, sms = 0, max_smem = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        const int stage_bytes = (max_smem - 1024) & ~127;   // static shared memory (barrier) + alignment slack
+        int stage_bytes = (max_smem - 1024) & ~127;   // static shared memory (barrier) + alignment slack
+        if (g_grid_variant == 2) stage_bytes = 48 * 1024;
+        if (g_grid_variant == 3) stage_bytes = 160 * 1024;
         cudaError_t e = cudaFuncSetAttribute(k_grid_forward_staged<T, D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes);
         if (e != cudaSuccess) return (int)e;
         k_grid_forward_staged<T, D, C><<<sms, 1024, stage_bytes, st>>>(inputs, emb, offsets, outputs, B, L, S, H, gridtype, ac, interp, (uint32_t)stage_bytes);
-    } else if (B >= kBigBatch && dy_dx == nullptr)
+    } else if (B >= kBigBatch && dy_dx == nullptr && g_grid_variant == 5)
+        k_grid_forward<T, D, C, true, true><<<dim3(div_up(B, 256u), 1), 256, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac, interp);
+    else if (B >= kBigBatch && dy_dx == nullptr)
         k_grid_forward<T, D, C, true><<<dim3(div_up(B, 256u), 1), 256, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac, interp);
     else
         k_grid_forward<T, D, C, false><<<dim3(div_up(B, 256u), L), 256, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac, interp);
