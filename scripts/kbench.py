@@ -59,8 +59,9 @@ def main():
     if tr.student.mean_count <= 0:
         tr.refresh_occupancy()
     lib = _lib.lib()
-    lib.s3d_debug_variant.argtypes = [ctypes.c_int, ctypes.c_int]
-    lib.s3d_debug_grid_variant.argtypes = [ctypes.c_int]
+    has_knobs = hasattr(lib, "s3d_debug_variant")   # only present in experiment builds
+    if has_knobs:
+        lib.s3d_debug_variant.argtypes = [ctypes.c_int, ctypes.c_int]
     defaults = dict((int(k), int(v)) for k, v in (kv.split("=") for kv in args.defaults.split(",") if kv))
     keys = ("s3d_ngp_encode_pair", "s3d_ngp_scatter", "s3d_ngp_mlp_backward", "s3d_ngp_mlp_forward", "s3d_march_rays_train", "step_ms")
 
@@ -68,15 +69,13 @@ def main():
         r = measure(tr, resident)
         print(json.dumps({"variant": label, **{k.replace("s3d_", ""): round(r.get(k, 0.0), 4) for k in keys}}), flush=True)
 
-    for gv in (0, 5, 2, 3, 4):   # stand-alone grid_encode_forward on 2^22 random points: 1 = per-point kernel, 0 = staged coarse levels
-        lib.s3d_debug_grid_variant(gv)
-        g = {p: bench.roofline_grid_encode(dev, p) for p in ("fp32", "fp16")}
-        print(json.dumps({"grid_variant": gv, "fp32_ms": round(g["fp32"]["launch_ms"], 4), "fp32_frac": round(g["fp32"]["frac"], 4),
-                          "fp16_ms": round(g["fp16"]["launch_ms"], 4), "fp16_frac": round(g["fp16"]["frac"], 4)}), flush=True)
+    g = {p: bench.roofline_grid_encode(dev, p) for p in ("fp32", "fp16")}
+    print(json.dumps({"grid_forward": {p: {"ms": round(g[p]["launch_ms"], 4), "frac": round(g[p]["frac"], 4)} for p in g}}), flush=True)
     for k, v in defaults.items():
-        lib.s3d_debug_variant(k, v)
+        if has_knobs:
+            lib.s3d_debug_variant(k, v)
     run("defaults %s" % defaults)
-    for spec in args.set:
+    for spec in (args.set if has_knobs else []):
         which, vals = spec.split(":")
         for v in vals.split(","):
             lib.s3d_debug_variant(int(which), int(v))

@@ -115,72 +115,25 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<const uint32_t *>(&h);
 }
 
-// L2 residency hints.  Inside one of these kernels only the hash tables (and the gradient table) are reused; every
-// sample-sized stream (positions, feature rows, feature gradients) is touched exactly once but is several times larger
-// than the 126 MB L2, so without hints it evicts the tables and the gathers go to DRAM as random 32-byte sectors.
-//   HINT 0: none;  1: streams use evict-first loads / stores (ld/st.global.cs);  2: additionally the table gathers and the
-//   gradient REDs carry an L2 evict_last cache policy.
-template <int HINT>
-__device__ __forceinline__ uint64_t table_policy() {
-    uint64_t pol = 0;
-    if constexpr (HINT == 2) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
+__device__ __forceinline__ uint2 ld_entry(const uint8_t *__restrict__ table, uint32_t idx, uint32_t stride) {
+    return __ldg(reinterpret_cast<const uint2 *>(table + (size_t)idx * stride));
 }
-template <int HINT>
-__device__ __forceinline__ uint4 ld_table16(const uint4 *p, uint64_t pol) {
-    if constexpr (HINT == 2) {
-        uint4 v;
-        asm("ld.global.nc.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
-        return v;
-    } else return __ldg(p);
-}
-template <int HINT>
-__device__ __forceinline__ uint2 ld_table8(const uint2 *p, uint64_t pol) {
-    if constexpr (HINT == 2) {
-        uint2 v;
-        asm("ld.global.nc.L2::cache_hint.v2.b32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
-        return v;
-    } else return __ldg(p);
-}
-template <int HINT>
-__device__ __forceinline__ void red_table16(float4 *p, float a, float b, float c, float d, uint64_t pol) {
-    if constexpr (HINT == 2)
-        asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "l"(pol) : "memory");
-    else atomicAdd(p, make_float4(a, b, c, d));
-}
-template <int HINT, typename V>
-__device__ __forceinline__ V ld_stream(const V *p) {
-    if constexpr (HINT >= 1) return __ldcs(p);
-    else return __ldg(p);
-}
-template <int HINT, typename V>
-__device__ __forceinline__ void st_stream(V *p, const V v) {
-    if constexpr (HINT >= 1) __stcs(p, v);
-    else *p = v;
-}
-template <int HINT>
 __device__ __forceinline__ bool load_unit(const float *__restrict__ xyz, uint32_t i, float bound, float &ux, float &uy, float &uz) {
-    return to_unit(ld_stream<HINT>(xyz + (size_t)i * 3), ld_stream<HINT>(xyz + (size_t)i * 3 + 1), ld_stream<HINT>(xyz + (size_t)i * 3 + 2), bound, ux, uy, uz);
-}
-
-template <int HINT>
-__device__ __forceinline__ uint2 ld_entry(const uint8_t *__restrict__ table, uint32_t idx, uint32_t stride, uint64_t pol) {
-    return ld_table8<HINT>(reinterpret_cast<const uint2 *>(table + (size_t)idx * stride), pol);
+    return to_unit(xyz[(size_t)i * 3], xyz[(size_t)i * 3 + 1], xyz[(size_t)i * 3 + 2], bound, ux, uy, uz);
 }
 
 // The two x-corners of a cell, idx[2j] and idx[2j+1], are the halves of one ALIGNED entry pair whenever they differ in
 // bit 0 only (even x on hashed levels, even dense index otherwise): one double-width load then serves both.  The L1 tag
 // stage pays per (lane, sector), so this removes a quarter of the gather cost on average.  All loads are issued before any
 // use (the unmerged second load is predicated, not branched) so the 8 gathers of a level stay in flight together.
-template <int HINT>
-__device__ __forceinline__ void gather_cell_e8(const uint8_t *__restrict__ table, const Cell &c, uint2 (&v)[8], uint64_t pol) {
+__device__ __forceinline__ void gather_cell_e8(const uint8_t *__restrict__ table, const Cell &c, uint2 (&v)[8]) {
     uint4 a[4];
     bool merged[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         merged[j] = (c.idx[2 * j] ^ c.idx[2 * j + 1]) == 1u;
-        a[j] = ld_table16<HINT>(reinterpret_cast<const uint4 *>(table) + (c.idx[2 * j] >> 1), pol);
-        if (!merged[j]) v[2 * j + 1] = ld_table8<HINT>(reinterpret_cast<const uint2 *>(table) + c.idx[2 * j + 1], pol);
+        a[j] = __ldg(reinterpret_cast<const uint4 *>(table) + (c.idx[2 * j] >> 1));
+        if (!merged[j]) v[2 * j + 1] = __ldg(reinterpret_cast<const uint2 *>(table) + c.idx[2 * j + 1]);
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -191,7 +144,6 @@ __device__ __forceinline__ void gather_cell_e8(const uint8_t *__restrict__ table
     }
 }
 
-template <int HINT>
 __global__ void __launch_bounds__(256)
 k_ngp_encode(const float *__restrict__ xyz, uint32_t M, float bound, const uint8_t *__restrict__ table, uint32_t stride,
              const int *__restrict__ offsets, uint32_t L, float S, uint32_t H, __half *__restrict__ feats, int sigma_only) {
@@ -200,8 +152,7 @@ k_ngp_encode(const float *__restrict__ xyz, uint32_t M, float bound, const uint8
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
     float ux, uy, uz;
-    const bool ok = load_unit<HINT>(xyz, i, bound, ux, uy, uz);
-    const uint64_t pol = table_policy<HINT>();
+    const bool ok = load_unit(xyz, i, bound, ux, uy, uz);
     uint4 *row = reinterpret_cast<uint4 *>(feats + (size_t)i * 64);
     for (uint32_t grp = 0; grp < 4; grp++) {      // 4 levels -> one 16-byte chunk per table
         uint32_t fs[4], fc[4];   // one packed half2 per level: 4 levels -> one 16-byte chunk per table
@@ -213,10 +164,10 @@ k_ngp_encode(const float *__restrict__ xyz, uint32_t M, float bound, const uint8
                 Cell c;
                 locate(g, l, ux, uy, uz, c, nullptr);
                 uint2 v[8];
-                if (stride == 8 && ((g.pair_ok >> l) & 1u)) gather_cell_e8<HINT>(table, c, v, pol);
+                if (stride == 8 && ((g.pair_ok >> l) & 1u)) gather_cell_e8(table, c, v);
                 else {
 #pragma unroll
-                    for (int k = 0; k < 8; k++) v[k] = ld_entry<HINT>(table, c.idx[k], stride, pol);
+                    for (int k = 0; k < 8; k++) v[k] = ld_entry(table, c.idx[k], stride);
                 }
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
@@ -228,8 +179,8 @@ k_ngp_encode(const float *__restrict__ xyz, uint32_t M, float bound, const uint8
             }
             fs[q] = pack2(s0, s1); fc[q] = pack2(c0, c1);
         }
-        st_stream<HINT>(row + grp, make_uint4(fs[0], fs[1], fs[2], fs[3]));
-        if (!sigma_only) st_stream<HINT>(row + 4 + grp, make_uint4(fc[0], fc[1], fc[2], fc[3]));
+        row[grp] = make_uint4(fs[0], fs[1], fs[2], fs[3]);
+        if (!sigma_only) row[4 + grp] = make_uint4(fc[0], fc[1], fc[2], fc[3]);
     }
 }
 
@@ -243,7 +194,6 @@ __device__ __forceinline__ void acc4(const uint2 v, float w, float &a0, float &a
     a0 = __fmaf_rn(w, a.x, a0); a1 = __fmaf_rn(w, a.y, a1); a2 = __fmaf_rn(w, b.x, a2); a3 = __fmaf_rn(w, b.y, a3);
 }
 
-template <int HINT>
 __global__ void __launch_bounds__(256, 4)
 k_ngp_encode_pair(const float *__restrict__ xyz, const float *__restrict__ xyz_teacher, const uint8_t *__restrict__ mask, uint32_t M,
                   float bound, const uint4 *__restrict__ table8, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H,
@@ -253,11 +203,10 @@ k_ngp_encode_pair(const float *__restrict__ xyz, const float *__restrict__ xyz_t
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
     float ux, uy, uz, tx = 0, ty = 0, tz = 0;
-    const bool ok = load_unit<HINT>(xyz, i, bound, ux, uy, uz);
+    const bool ok = load_unit(xyz, i, bound, ux, uy, uz);
     const bool moved = mask && mask[i];
     bool tok = ok;
-    if (moved) tok = load_unit<HINT>(xyz_teacher, i, bound, tx, ty, tz);
-    const uint64_t pol = table_policy<HINT>();
+    if (moved) tok = load_unit(xyz_teacher, i, bound, tx, ty, tz);
     uint4 *row_t = reinterpret_cast<uint4 *>(feats_teacher + (size_t)i * 64), *row_s = reinterpret_cast<uint4 *>(feats_student + (size_t)i * 64);
     for (uint32_t grp = 0; grp < 4; grp++) {
         uint32_t ts[4], tc[4], ss[4], sc[4];
@@ -270,7 +219,7 @@ k_ngp_encode_pair(const float *__restrict__ xyz, const float *__restrict__ xyz_t
                 locate(g, l, ux, uy, uz, c, nullptr);
                 uint4 v[8];
 #pragma unroll
-                for (int k = 0; k < 8; k++) v[k] = ld_table16<HINT>(table8 + c.idx[k], pol);
+                for (int k = 0; k < 8; k++) v[k] = __ldg(table8 + c.idx[k]);
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     acc4(make_uint2(v[k].z, v[k].w), c.w[k], s0, s1, s2, s3);
@@ -282,14 +231,14 @@ k_ngp_encode_pair(const float *__restrict__ xyz, const float *__restrict__ xyz_t
                 locate(g, l, tx, ty, tz, c, nullptr);
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    const uint4 v = ld_table16<HINT>(table8 + c.idx[k], pol);
+                    const uint4 v = __ldg(table8 + c.idx[k]);
                     acc4(make_uint2(v.x, v.y), c.w[k], t0, t1, t2, t3);
                 }
             }
             ts[q] = pack2(t0, t1); tc[q] = pack2(t2, t3); ss[q] = pack2(s0, s1); sc[q] = pack2(s2, s3);
         }
-        st_stream<HINT>(row_t + grp, make_uint4(ts[0], ts[1], ts[2], ts[3])); st_stream<HINT>(row_t + 4 + grp, make_uint4(tc[0], tc[1], tc[2], tc[3]));
-        st_stream<HINT>(row_s + grp, make_uint4(ss[0], ss[1], ss[2], ss[3])); st_stream<HINT>(row_s + 4 + grp, make_uint4(sc[0], sc[1], sc[2], sc[3]));
+        row_t[grp] = make_uint4(ts[0], ts[1], ts[2], ts[3]); row_t[4 + grp] = make_uint4(tc[0], tc[1], tc[2], tc[3]);
+        row_s[grp] = make_uint4(ss[0], ss[1], ss[2], ss[3]); row_s[4 + grp] = make_uint4(sc[0], sc[1], sc[2], sc[3]);
     }
 }
 
@@ -303,7 +252,6 @@ __global__ void k_pair_tables(const uint2 *__restrict__ teacher4, const uint2 *_
 // ------------------------------------------------------------------------------------------------
 // scatter: dfeats -> interleaved fp32 gradient table
 // ------------------------------------------------------------------------------------------------
-template <int HINT>
 __global__ void __launch_bounds__(256)
 k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, uint32_t M, float bound,
               float4 *__restrict__ grad4, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H, float grad_scale) {
@@ -312,13 +260,12 @@ k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, 
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // whole warps stay alive
     float ux = 0, uy = 0, uz = 0;
     bool ok = false;
-    if (i < M) ok = load_unit<HINT>(xyz, i, bound, ux, uy, uz);
-    const uint64_t pol = table_policy<HINT>();
+    if (i < M) ok = load_unit(xyz, i, bound, ux, uy, uz);
     const uint32_t lane = lane_id();
     const uint4 *row = reinterpret_cast<const uint4 *>(dfeats + (size_t)(i < M ? i : 0) * 64);
     for (uint32_t grp = 0; grp < 4; grp++) {
         float ds[8], dc[8];
-        if (ok) { unpack8(ld_stream<HINT>(row + grp), ds); unpack8(ld_stream<HINT>(row + 4 + grp), dc); }
+        if (ok) { unpack8(__ldg(row + grp), ds); unpack8(__ldg(row + 4 + grp), dc); }
         else {
 #pragma unroll
             for (int k = 0; k < 8; k++) { ds[k] = 0.f; dc[k] = 0.f; }
@@ -361,11 +308,11 @@ k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, 
                             if (d <= seg_left) { a0 += o0; a1 += o1; a2 += o2; a3 += o3; }
                         }
                     }
-                    if (ok && head) red_table16<HINT>(grad4 + c.idx[k], a0, a1, a2, a3, pol);
+                    if (ok && head) atomicAdd(grad4 + c.idx[k], make_float4(a0, a1, a2, a3));
                 }
             } else if (ok) {
 #pragma unroll
-                for (int k = 0; k < 8; k++) red_table16<HINT>(grad4 + c.idx[k], c.w[k] * g0, c.w[k] * g1, c.w[k] * g2, c.w[k] * g3, pol);
+                for (int k = 0; k < 8; k++) atomicAdd(grad4 + c.idx[k], make_float4(c.w[k] * g0, c.w[k] * g1, c.w[k] * g2, c.w[k] * g3));
             }
         }
     }
@@ -928,17 +875,12 @@ int sm_count() {
 
 // table: interleaved fp16 entries {s0,s1,c0,c1} at table + idx * table_stride (8 = stand-alone table4, 16 = one half of a
 // paired table: pass the pointer already offset by 0 | 8 bytes); feats [M,64] fp16 (sigma feats 0..31, colour feats 32..63)
-static int g_variant[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // experiment knobs (kernel variants), see scripts/kbench.py
-S3D_API int s3d_debug_variant(int which, int value) { if (which < 0 || which >= 8) return S3D_EINVAL; g_variant[which] = value; return 0; }
-
 S3D_API int s3d_ngp_encode(const float *xyz, uint32_t M, float bound, const void *table, uint32_t table_stride, const int *offsets,
                            uint32_t L, float S, uint32_t H, void *feats, int sigma_only, void *stream) {
     if (M == 0) return 0;
     if (L > kMaxLevels) return S3D_ENOTSUP;
     if (table_stride != 8 && table_stride != 16) return S3D_EINVAL;
-#define S3D_EN(HINT) k_ngp_encode<HINT><<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, M, bound, (const uint8_t *)table, table_stride, offsets, L, S, H, (__half *)feats, sigma_only)
-    if (g_variant[2] == 0) S3D_EN(0); else if (g_variant[2] == 1) S3D_EN(1); else S3D_EN(2);
-#undef S3D_EN
+k_ngp_encode<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, M, bound, (const uint8_t *)table, table_stride, offsets, L, S, H, (__half *)feats, sigma_only);
     S3D_RETURN_LAST();
 }
 
@@ -947,9 +889,8 @@ S3D_API int s3d_ngp_encode_pair(const float *xyz, const float *xyz_teacher, cons
                                 const int *offsets, uint32_t L, float S, uint32_t H, void *feats_teacher, void *feats_student, void *stream) {
     if (M == 0) return 0;
     if (L > kMaxLevels) return S3D_ENOTSUP;
-#define S3D_EP(HINT) k_ngp_encode_pair<HINT><<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, xyz_teacher, xyz_teacher ? mask : nullptr, M, bound, (const uint4 *)table8, offsets, L, S, H, (__half *)feats_teacher, (__half *)feats_student)
-    if (g_variant[0] == 0) S3D_EP(0); else if (g_variant[0] == 1) S3D_EP(1); else S3D_EP(2);
-#undef S3D_EP
+k_ngp_encode_pair<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, xyz_teacher, xyz_teacher ? mask : nullptr, M, bound, (const uint4 *)table8, offsets, L, S, H,
+                                                                     (__half *)feats_teacher, (__half *)feats_student);
     S3D_RETURN_LAST();
 }
 
@@ -964,9 +905,7 @@ S3D_API int s3d_ngp_scatter(const float *xyz, const void *dfeats, uint32_t M, fl
                             float S, uint32_t H, float grad_scale, void *stream) {
     if (M == 0) return 0;
     if (L > kMaxLevels) return S3D_ENOTSUP;
-#define S3D_SC(HINT) k_ngp_scatter<HINT><<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale)
-    if (g_variant[1] == 0) S3D_SC(0); else if (g_variant[1] == 1) S3D_SC(1); else S3D_SC(2);
-#undef S3D_SC
+k_ngp_scatter<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale);
     S3D_RETURN_LAST();
 }
 

@@ -78,36 +78,29 @@ template <> struct Entry<__half, 2> { using V = __half2; };
 template <> struct Entry<__half, 4> { using V = uint2; };
 template <> struct Entry<__half, 8> { using V = uint4; };
 
-// NC = true: global table through the read-only path (LDG.E.CONSTANT); NC = false: plain loads (a table staged in shared memory)
-template <bool NC, typename V>
-__device__ __forceinline__ V ldv(const V *p) {
-    if constexpr (NC) return __ldg(p);
-    else return *p;
-}
-
-template <typename T, uint32_t C, bool NC = true>
+template <typename T, uint32_t C>
 __device__ __forceinline__ void load_entry(const T *__restrict__ grid, uint32_t index, float (&v)[C]) {
     if constexpr (sizeof(T) == 4) {
-        if constexpr (C == 1) { v[0] = ldv<NC>(grid + index); }
-        else if constexpr (C == 2) { const float2 t = ldv<NC>(reinterpret_cast<const float2 *>(grid) + index); v[0] = t.x; v[1] = t.y; }
+        if constexpr (C == 1) { v[0] = __ldg(grid + index); }
+        else if constexpr (C == 2) { const float2 t = __ldg(reinterpret_cast<const float2 *>(grid) + index); v[0] = t.x; v[1] = t.y; }
         else {
 #pragma unroll
             for (uint32_t q = 0; q < C / 4; q++) {
-                const float4 t = ldv<NC>(reinterpret_cast<const float4 *>(grid) + (size_t)index * (C / 4) + q);
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(grid) + (size_t)index * (C / 4) + q);
                 v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
             }
         }
     } else {
-        if constexpr (C == 1) { v[0] = __half2float(ldv<NC>(reinterpret_cast<const __half *>(grid) + index)); }
+        if constexpr (C == 1) { v[0] = __half2float(__ldg(reinterpret_cast<const __half *>(grid) + index)); }
         else if constexpr (C == 2) {
-            const float2 t = __half22float2(ldv<NC>(reinterpret_cast<const __half2 *>(grid) + index));
+            const float2 t = __half22float2(__ldg(reinterpret_cast<const __half2 *>(grid) + index));
             v[0] = t.x; v[1] = t.y;
         } else if constexpr (C == 4) {
-            const uint2 t = ldv<NC>(reinterpret_cast<const uint2 *>(grid) + index);
+            const uint2 t = __ldg(reinterpret_cast<const uint2 *>(grid) + index);
             const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&t.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&t.y));
             v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
         } else {
-            const uint4 t = ldv<NC>(reinterpret_cast<const uint4 *>(grid) + index);
+            const uint4 t = __ldg(reinterpret_cast<const uint4 *>(grid) + index);
             const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
             for (int q = 0; q < 4; q++) {
@@ -125,26 +118,23 @@ __device__ __forceinline__ void load_entry(const T *__restrict__ grid, uint32_t 
 template <typename T, uint32_t C> struct PairLoad { static constexpr bool kOk = false; };
 template <> struct PairLoad<float, 2> {
     static constexpr bool kOk = true;
-    template <bool NC>
     __device__ static __forceinline__ void load(const float *grid, uint32_t even_index, float (&lo)[2], float (&hi)[2]) {
-        const float4 t = ldv<NC>(reinterpret_cast<const float4 *>(grid) + (even_index >> 1));
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(grid) + (even_index >> 1));
         lo[0] = t.x; lo[1] = t.y; hi[0] = t.z; hi[1] = t.w;
     }
 };
 template <> struct PairLoad<__half, 2> {
     static constexpr bool kOk = true;
-    template <bool NC>
     __device__ static __forceinline__ void load(const __half *grid, uint32_t even_index, float (&lo)[2], float (&hi)[2]) {
-        const uint2 t = ldv<NC>(reinterpret_cast<const uint2 *>(grid) + (even_index >> 1));
+        const uint2 t = __ldg(reinterpret_cast<const uint2 *>(grid) + (even_index >> 1));
         const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&t.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&t.y));
         lo[0] = a.x; lo[1] = a.y; hi[0] = b.x; hi[1] = b.y;
     }
 };
 template <> struct PairLoad<__half, 4> {
     static constexpr bool kOk = true;
-    template <bool NC>
     __device__ static __forceinline__ void load(const __half *grid, uint32_t even_index, float (&lo)[4], float (&hi)[4]) {
-        const uint4 t = ldv<NC>(reinterpret_cast<const uint4 *>(grid) + (even_index >> 1));
+        const uint4 t = __ldg(reinterpret_cast<const uint4 *>(grid) + (even_index >> 1));
         const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&t.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&t.y));
         const float2 c = __half22float2(*reinterpret_cast<const __half2 *>(&t.z)), d = __half22float2(*reinterpret_cast<const __half2 *>(&t.w));
         lo[0] = a.x; lo[1] = a.y; lo[2] = b.x; lo[3] = b.y; hi[0] = c.x; hi[1] = c.y; hi[2] = d.x; hi[3] = d.y;
@@ -158,17 +148,12 @@ template <typename T> __device__ __forceinline__ float to_float(T v);
 template <> __device__ __forceinline__ float to_float<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_float<__half>(__half v) { return __half2float(v); }
 
-// STREAM: evict-first store (st.global.cs) -- the output is written once and is larger than L2; keeping it from
-// displacing the table is what lets the gathers hit L2
-template <typename T, uint32_t C, bool STREAM = false>
+template <typename T, uint32_t C>
 __device__ __forceinline__ void store_vec(T *__restrict__ p, const float (&v)[C]) {
     if constexpr (sizeof(T) == 4 && C == 2) {
-        if constexpr (STREAM) __stcs(reinterpret_cast<float2 *>(p), make_float2(v[0], v[1]));
-        else *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+        *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
     } else if constexpr (sizeof(T) == 2 && C == 2) {
-        const __half2 h = __floats2half2_rn(v[0], v[1]);
-        if constexpr (STREAM) __stcs(reinterpret_cast<unsigned int *>(p), *reinterpret_cast<const unsigned int *>(&h));
-        else *reinterpret_cast<__half2 *>(p) = h;
+        *reinterpret_cast<__half2 *>(p) = __floats2half2_rn(v[0], v[1]);
     }
     else {
 #pragma unroll
@@ -204,7 +189,7 @@ __device__ __forceinline__ bool out_of_range(const float (&x)[D]) {
 }
 
 // encode one (point, level): result[C] (fp32) and optionally dy_dx
-template <typename T, uint32_t D, uint32_t C, bool NC = true>
+template <typename T, uint32_t D, uint32_t C>
 __device__ __forceinline__ void encode_level(const float (&x)[D], const T *__restrict__ grid_level, const LevelInfo &li,
                                              bool align_corners, uint32_t interp, float (&res)[C], T *__restrict__ dy_dx_lvl) {
     float pos[D], deriv[D];
@@ -232,8 +217,8 @@ __device__ __forceinline__ void encode_level(const float (&x)[D], const T *__res
             float lo[1u << (D - 1)][C], hi[1u << (D - 1)][C];
 #pragma unroll
             for (uint32_t j = 0; j < (1u << (D - 1)); j++) {
-                PairLoad<T, C>::template load<NC>(grid_level, i0[j] & ~1u, lo[j], hi[j]);
-                if (!merged[j]) load_entry<T, C, NC>(grid_level, i1[j], val[2 * j + 1]);
+                PairLoad<T, C>::load(grid_level, i0[j] & ~1u, lo[j], hi[j]);
+                if (!merged[j]) load_entry<T, C>(grid_level, i1[j], val[2 * j + 1]);
             }
 #pragma unroll
             for (uint32_t j = 0; j < (1u << (D - 1)); j++) {
@@ -250,7 +235,7 @@ __device__ __forceinline__ void encode_level(const float (&x)[D], const T *__res
                 uint32_t pl[D];
 #pragma unroll
                 for (uint32_t d = 0; d < D; d++) pl[d] = pg[d] + ((idx >> d) & 1u);
-                load_entry<T, C, NC>(grid_level, corner_index<D>(li, align_corners, pl), val[idx]);
+                load_entry<T, C>(grid_level, corner_index<D>(li, align_corners, pl), val[idx]);
             }
         }
     } else {
@@ -259,7 +244,7 @@ __device__ __forceinline__ void encode_level(const float (&x)[D], const T *__res
             uint32_t pl[D];
 #pragma unroll
             for (uint32_t d = 0; d < D; d++) pl[d] = pg[d] + ((idx >> d) & 1u);
-            load_entry<T, C, NC>(grid_level, corner_index<D>(li, align_corners, pl), val[idx]);
+            load_entry<T, C>(grid_level, corner_index<D>(li, align_corners, pl), val[idx]);
         }
     }
 #pragma unroll
@@ -293,7 +278,7 @@ __device__ __forceinline__ void encode_level(const float (&x)[D], const T *__res
 }
 
 // ALL_LEVELS: blockIdx.y unused, thread loops over levels.  Otherwise blockIdx.y = level.
-template <typename T, uint32_t D, uint32_t C, bool ALL_LEVELS, bool STREAM = false>
+template <typename T, uint32_t D, uint32_t C, bool ALL_LEVELS>
 __global__ void __launch_bounds__(256)
 k_grid_forward(const float *__restrict__ inputs, const T *__restrict__ grid, const int *__restrict__ offsets,
                T *__restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, T *__restrict__ dy_dx,
@@ -302,7 +287,7 @@ k_grid_forward(const float *__restrict__ inputs, const T *__restrict__ grid, con
     if (b >= B) return;
     float x[D];
 #pragma unroll
-    for (uint32_t d = 0; d < D; d++) x[d] = STREAM ? __ldcs(inputs + (size_t)b * D + d) : __ldg(inputs + (size_t)b * D + d);
+    for (uint32_t d = 0; d < D; d++) x[d] = __ldg(inputs + (size_t)b * D + d);
     const bool oob = out_of_range<D>(x);
     const uint32_t l0 = ALL_LEVELS ? 0 : blockIdx.y, l1 = ALL_LEVELS ? L : blockIdx.y + 1;
 #pragma unroll 2
@@ -318,79 +303,7 @@ k_grid_forward(const float *__restrict__ inputs, const T *__restrict__ grid, con
             const LevelInfo li = level_info<D>(offsets, level, S, H, gridtype, align_corners);
             encode_level<T, D, C>(x, grid + (size_t)(uint32_t)__ldg(offsets + level) * C, li, align_corners, interp, res, dd);
         }
-        store_vec<T, C, STREAM>(outputs + ((size_t)level * B + b) * C, res);
-    }
-}
-
-// Persistent variant for large batches (no dy_dx): one 1024-thread CTA per SM first stages the leading levels whose
-// tables fit in shared memory -- levels 0-1 of the fp32 NGP table (150 KB), 0-2 of the fp16 one (201 KB) -- with TMA bulk
-// copies (cp.async.bulk -> mbarrier complete_tx), then walks its points.  The 8 gathers per point of a staged level are
-// shared-memory loads (a handful of bank-conflict wavefronts) instead of 6-8 L1 tag lookups + L2 sector requests per lane,
-// which is what bounds the kernel: every (lane, sector) of a divergent global load costs one L1 tag-stage slot.
-__device__ __forceinline__ uint32_t gsmem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-template <typename T, uint32_t D, uint32_t C>
-__global__ void __launch_bounds__(1024, 1)
-k_grid_forward_staged(const float *__restrict__ inputs, const T *__restrict__ grid, const int *__restrict__ offsets,
-                      T *__restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype,
-                      bool align_corners, uint32_t interp, uint32_t stage_bytes) {
-    extern __shared__ __align__(128) uint8_t stage_raw[];
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_nlev;
-    const T *stage = reinterpret_cast<const T *>(stage_raw);
-    if (threadIdx.x == 0) {
-        uint32_t n = 0;   // leading levels that fit (their end offset in bytes; 16-byte granular for the bulk copy)
-        while (n < L && (size_t)(uint32_t)offsets[n + 1] * C * sizeof(T) <= stage_bytes && (((size_t)(uint32_t)offsets[n + 1] * C * sizeof(T)) & 15u) == 0) n++;
-        if ((reinterpret_cast<size_t>(grid) & 15u) != 0 || offsets[0] != 0) n = 0;
-        s_nlev = n;
-        const uint32_t bar = gsmem_u32(&s_bar);
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t total = n ? (uint32_t)offsets[n] * C * (uint32_t)sizeof(T) : 0u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
-        for (uint32_t done = 0; done < total;) {   // bulk copies of at most 64 KB
-            const uint32_t chunk = min(total - done, 65536u);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-                         "r"(gsmem_u32(stage_raw + done)), "l"(reinterpret_cast<const uint8_t *>(grid) + done), "r"(chunk), "r"(bar) : "memory");
-            done += chunk;
-        }
-    }
-    __syncthreads();
-    {   // phase 0 completes when the expected bytes have landed (immediately if nothing was staged); bounded wait
-        const uint32_t bar = gsmem_u32(&s_bar);
-        uint32_t ok = 0;
-        for (uint32_t it = 0; it < (1u << 22) && !ok; it++)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar) : "memory");
-        if (!ok) __trap();
-    }
-    const uint32_t nlev = s_nlev;
-    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
-        float x[D];
-#pragma unroll
-        for (uint32_t d = 0; d < D; d++) x[d] = __ldg(inputs + (size_t)b * D + d);
-        const bool oob = out_of_range<D>(x);
-#pragma unroll 1
-        for (uint32_t level = 0; level < nlev; level++) {
-            float res[C];
-#pragma unroll
-            for (uint32_t c = 0; c < C; c++) res[c] = 0.0f;
-            if (!oob) {
-                const LevelInfo li = level_info<D>(offsets, level, S, H, gridtype, align_corners);
-                encode_level<T, D, C, false>(x, stage + (size_t)(uint32_t)__ldg(offsets + level) * C, li, align_corners, interp, res, nullptr);
-            }
-            store_vec<T, C>(outputs + ((size_t)level * B + b) * C, res);
-        }
-#pragma unroll 2
-        for (uint32_t level = nlev; level < L; level++) {
-            float res[C];
-#pragma unroll
-            for (uint32_t c = 0; c < C; c++) res[c] = 0.0f;
-            if (!oob) {
-                const LevelInfo li = level_info<D>(offsets, level, S, H, gridtype, align_corners);
-                encode_level<T, D, C, true>(x, grid + (size_t)(uint32_t)__ldg(offsets + level) * C, li, align_corners, interp, res, nullptr);
-            }
-            store_vec<T, C>(outputs + ((size_t)level * B + b) * C, res);
-        }
+        store_vec<T, C>(outputs + ((size_t)level * B + b) * C, res);
     }
 }
 
@@ -565,27 +478,12 @@ __global__ void k_level_scales(uint32_t L, float S, uint32_t H, float *__restric
 
 // ---- dispatch ----------------------------------------------------------------------------
 
-constexpr uint32_t kBigBatch = 1u << 17;     // from here one thread walks all levels of its point
-constexpr uint32_t kStagedBatch = 1u << 20;  // from here the persistent kernel with the coarse levels staged in shared memory pays
-int g_grid_variant = 0;                      // experiment knob: 0 per-point kernel, 2/3/4 staged (48 KB / 160 KB / max), 5 per-point + stream hints
+constexpr uint32_t kBigBatch = 1u << 17;  // from here one thread walks all levels of its point
 
 template <typename T, uint32_t D, uint32_t C>
 int launch_forward(const float *inputs, const T *emb, const int *offsets, T *outputs, uint32_t B, uint32_t L, float S,
                    uint32_t H, T *dy_dx, uint32_t gridtype, bool ac, uint32_t interp, cudaStream_t st) {
-    if (B >= kStagedBatch && dy_dx == nullptr && g_grid_variant >= 2 && g_grid_variant <= 4) {
-        int dev = 0, sms = 0, max_smem = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        int stage_bytes = (max_smem - 1024) & ~127;   // static shared memory (barrier) + alignment slack
-        if (g_grid_variant == 2) stage_bytes = 48 * 1024;
-        if (g_grid_variant == 3) stage_bytes = 160 * 1024;
-        cudaError_t e = cudaFuncSetAttribute(k_grid_forward_staged<T, D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes);
-        if (e != cudaSuccess) return (int)e;
-        k_grid_forward_staged<T, D, C><<<sms, 1024, stage_bytes, st>>>(inputs, emb, offsets, outputs, B, L, S, H, gridtype, ac, interp, (uint32_t)stage_bytes);
-    } else if (B >= kBigBatch && dy_dx == nullptr && g_grid_variant == 5)
-        k_grid_forward<T, D, C, true, true><<<dim3(div_up(B, 256u), 1), 256, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac, interp);
-    else if (B >= kBigBatch && dy_dx == nullptr)
+    if (B >= kBigBatch && dy_dx == nullptr)
         k_grid_forward<T, D, C, true><<<dim3(div_up(B, 256u), 1), 256, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac, interp);
     else
         k_grid_forward<T, D, C, false><<<dim3(div_up(B, 256u), L), 256, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac, interp);
@@ -620,8 +518,6 @@ int launch_backward(const T *grad, const float *inputs, const int *offsets, T *g
     }
 
 }  // namespace
-
-S3D_API int s3d_debug_grid_variant(int v) { g_grid_variant = v; return 0; }
 
 // the per-level scale exp2f(l*S)*H - 1 exactly as the kernels evaluate it (gridencoder.cu:138 of the reference);
 // diagnostic entry used by the parity tests (see oracle/seal_oracle.c: orc_set_level_scales)
