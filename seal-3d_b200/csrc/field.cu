@@ -1074,6 +1074,296 @@ k_ngp_mlp_bwd2(const BwdArgs a) {
     if (is_issuer) tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// MLP backward, two warp sets.  Same two chains and tile sets as k_ngp_mlp_bwd2, but each chain has its OWN eight
+// epilogue warps (threads 0-255: forward recompute of tile t+1, threads 256-511: backward of tile t, warp 16: issuer),
+// because ncu shows the epilogues -- TMEM reads, ReLU masks, fp16 packing, swizzled stores -- and not the tensor-core
+// latency bound the one-set kernels.  Hand-off: an epilogue set publishes a tile with bar.arrive on its named barrier
+// (1 = forward, 2 = backward) and goes straight to its mbarrier; the issuer bar.syncs on the two barriers alternately.
+// The sets meet once per iteration (named barrier 3) before the tile sets swap roles; the sigma logit travels from the
+// forward set to the backward set through shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kBwd3Threads = 544;
+constexpr uint32_t kBwd3Issuer = 16;
+
+__device__ __forceinline__ void bar_arrive(uint32_t id, uint32_t n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_sync_n(uint32_t id, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void set_publish(uint32_t id) {   // epilogue set: tile writes / accumulator reads of this round are done
+    fence_async_smem();
+    fence_before_sync();
+    bar_arrive(id, 288);
+}
+__device__ __forceinline__ void iss_acquire_n(uint32_t id) {
+    bar_sync_n(id, 288);
+    fence_after_sync();
+}
+
+__global__ void __launch_bounds__(kBwd3Threads, 1)
+k_ngp_mlp_bwd3(const BwdArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_mbar[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_h0[2][kRows];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *tWs0 = smem + 2 * kSetTiles * kTileBytes, *tWc0 = tWs0 + kWTile, *tWc1 = tWc0 + kWTile, *tWs1 = tWc1 + kWTile, *tWc2 = tWs1 + kOTile;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, r = tid & 127, hf = (tid >> 7) & 1u;
+    const bool is_issuer = (warp == kBwd3Issuer), is_fwd = tid < 256;
+    if (is_issuer) tmem_alloc(smem_u32(&s_tmem), 512);
+    if (tid == 0) { mbar_init(smem_u32(&s_mbar[0]), 1); mbar_init(smem_u32(&s_mbar[1]), 1); }
+    load_weights(tWs0, tWs1, tWc0, tWc1, tWc2, a.w);
+    sync_tiles();
+    const uint32_t tmem = s_tmem, t_row = tmem + (((warp & 3u) * 32u) << 16);
+    const uint32_t n_my = blockIdx.x < a.n_tiles ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t mbarF = smem_u32(&s_mbar[0]), mbarB = smem_u32(&s_mbar[1]);
+    constexpr uint32_t kAccF = 448, kAccB = 0;
+
+    if (is_issuer) {
+        const bool lead = (tid & 31) == 0;
+        const uint32_t base = smem_u32(smem);
+        const uint32_t aWs0 = smem_u32(tWs0), aWs1 = smem_u32(tWs1), aWc0 = smem_u32(tWc0), aWc1 = smem_u32(tWc1), aWc2 = smem_u32(tWc2);
+        const uint32_t id64 = make_idesc(128, 64, false, false), id16 = make_idesc(128, 16, false, false);
+        const uint32_t id64t = make_idesc(128, 64, false, true);        // B read MN-major (= W^T)
+        const uint32_t idw64 = make_idesc(64, 64, true, true);
+        const uint32_t accF = tmem + kAccF, accB = tmem + kAccB;
+        const uint32_t accC2 = tmem + 64, accC1 = tmem + 128, accC0f = tmem + 192, accC0g = tmem + 256, accS1 = tmem + 320, accS0 = tmem + 384;
+        const bool tw = a.train_mlp != 0;
+        for (uint32_t it = 0; it <= n_my; it++) {
+            const bool doF = it < n_my, doB = it > 0, firstB = (it == 1);
+            const uint32_t sf = base + (it & 1u) * kSetTiles * kTileBytes, sb = base + ((it & 1u) ^ 1u) * kSetTiles * kTileBytes;
+            const uint32_t fF = sf + kTF * kTileBytes, fH1 = sf + kTH1 * kTileBytes, fG = sf + kTG * kTileBytes, fC1 = sf + kTC1 * kTileBytes, fC2 = sf + kTC2 * kTileBytes;
+            const uint32_t bF = sb + kTF * kTileBytes, bH1 = sb + kTH1 * kTileBytes, bG = sb + kTG * kTileBytes, bC1 = sb + kTC1 * kTileBytes, bC2 = sb + kTC2 * kTileBytes, bX = sb + kTX * kTileBytes;
+            iss_acquire_n(1);   // features stored
+            if (lead) { if (doF) for (uint32_t k = 0; k < 2; k++) mma_f16(accF, desc_kmajor(fF, k), desc_kmajor(aWs0, k), id64, k > 0); mma_commit(mbarF); }
+            iss_acquire_n(2);   // dO in X (published before the sets met):  dC2 = dO . Wc2 ;  dWc2 += dO^T . C2
+            if (lead) {
+              if (doB) {
+                mma_f16(accB, desc_kmajor(bX, 0), desc_mnmajor(aWc2, 0, kOTile), id64t, false);
+                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accC2, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bC2, k, kTileBytes), idw64, !(firstB && k == 0));
+              }
+              mma_commit(mbarB);
+            }
+            iss_acquire_n(1);   // H1 written
+            if (lead) { if (doF) for (uint32_t k = 0; k < 4; k++) mma_f16(accF, desc_kmajor(fH1, k), desc_kmajor(aWs1, k), id16, k > 0); mma_commit(mbarF); }
+            iss_acquire_n(2);   // dC2 in X:  dC1 = dC2 . Wc1 ;  dWc1 += dC2^T . C1
+            if (lead) {
+              if (doB) {
+                for (uint32_t k = 0; k < 4; k++) mma_f16(accB, desc_kmajor(bX, k), desc_mnmajor(aWc1, k, kWTile), id64t, k > 0);
+                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accC1, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bC1, k, kTileBytes), idw64, !(firstB && k == 0));
+              }
+              mma_commit(mbarB);
+            }
+            iss_acquire_n(1);   // [SH | geo] written
+            if (lead) {
+                if (doF) {
+                    for (uint32_t k = 0; k < 2; k++) mma_f16(accF, desc_kmajor(fF, 2 + k), desc_kmajor(aWc0, k), id64, k > 0);
+                    for (uint32_t k = 0; k < 2; k++) mma_f16(accF, desc_kmajor(fG, k), desc_kmajor(aWc0, 2 + k), id64, true);
+                }
+                mma_commit(mbarF);
+            }
+            iss_acquire_n(2);   // dC1 in X:  d[colour feats | SH | geo] = dC1 . Wc0p ;  dWc0 += dC1^T . [F | G]
+            if (lead) {
+              if (doB) {
+                for (uint32_t k = 0; k < 4; k++) mma_f16(accB, desc_kmajor(bX, k), desc_mnmajor(aWc0, k, kWTile), id64t, k > 0);
+                if (tw) {
+                    for (uint32_t k = 0; k < 8; k++) mma_f16(accC0f, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bF, k, kTileBytes), idw64, !(firstB && k == 0));
+                    for (uint32_t k = 0; k < 8; k++) mma_f16(accC0g, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bG, k, kTileBytes), idw64, !(firstB && k == 0));
+                }
+              }
+              mma_commit(mbarB);
+            }
+            iss_acquire_n(1);   // C1 written
+            if (lead) { if (doF) for (uint32_t k = 0; k < 4; k++) mma_f16(accF, desc_kmajor(fC1, k), desc_kmajor(aWc1, k), id64, k > 0); mma_commit(mbarF); }
+            iss_acquire_n(2);   // dh2 in X:  dH1 = dh2 . Ws1 ;  dWs1 += dh2^T . H1
+            if (lead) {
+              if (doB) {
+                mma_f16(accB, desc_kmajor(bX, 0), desc_mnmajor(aWs1, 0, kOTile), id64t, false);
+                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accS1, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bH1, k, kTileBytes), idw64, !(firstB && k == 0));
+              }
+              mma_commit(mbarB);
+            }
+            iss_acquire_n(1);   // C2 written
+            if (lead) { if (doF) for (uint32_t k = 0; k < 4; k++) mma_f16(accF, desc_kmajor(fC2, k), desc_kmajor(aWc2, k), id16, k > 0); mma_commit(mbarF); }
+            iss_acquire_n(2);   // dH1 in X:  dF = dH1 . Ws0 ;  dWs0 += dH1^T . F
+            if (lead) {
+              if (doB) {
+                for (uint32_t k = 0; k < 4; k++) mma_f16(accB, desc_kmajor(bX, k), desc_mnmajor(aWs0, k, kWTile), id64t, k > 0);
+                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accS0, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bF, k, kTileBytes), idw64, !(firstB && k == 0));
+              }
+              mma_commit(mbarB);
+            }
+        }
+    } else if (is_fwd) {
+        // ================= forward recompute of tile it (set it & 1) =================
+        Issue isF{mbarF, 0};
+        const uint32_t accF = t_row + kAccF;
+        FeatPre nf;
+        float nin6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // warpgroup 0: dir xyz, dL/drgb of the next tile
+        auto prefetch = [&](uint32_t t) {
+            const uint32_t prow = t * kRows + r;
+            const bool pin = t < a.n_tiles && prow < a.M;
+            nf.load(a.feats, prow, hf, pin);
+            if (hf == 0) {
+#pragma unroll
+                for (int j = 0; j < 3; j++) { nin6[j] = pin ? a.dirs[(size_t)prow * 3 + j] : 0.f; nin6[3 + j] = pin ? a.g_rgb[(size_t)prow * 3 + j] : 0.f; }
+            }
+        };
+        prefetch(blockIdx.x);
+        for (uint32_t it = 0; it <= n_my; it++) {
+            const bool doF = it < n_my;
+            uint8_t *sF = smem + (it & 1u) * kSetTiles * kTileBytes;
+            uint8_t *fF = sF + kTF * kTileBytes, *fH1 = sF + kTH1 * kTileBytes, *fG = sF + kTG * kTileBytes, *fC1 = sF + kTC1 * kTileBytes, *fC2 = sF + kTC2 * kTileBytes, *fX = sF + kTX * kTileBytes;
+            const uint32_t tile_f = blockIdx.x + it * gridDim.x, row_f = tile_f * kRows + r;
+            const bool in_f = doF && row_f < a.M;
+            float in6[6];
+#pragma unroll
+            for (int j = 0; j < 6; j++) in6[j] = nin6[j];
+            if (doF) {
+                nf.store(fF, r, hf);
+                prefetch(tile_f + gridDim.x);
+            }
+            set_publish(1);
+            isF.wait();
+            if (doF) relu_to_tile(accF, hf, fH1, r);
+            set_publish(1);
+            isF.wait();
+            if (doF) {
+                if (hf == 0) {
+                    float h2[16], g[32];
+                    tmem_ld16(accF, h2);
+                    s_h0[it & 1u][r] = h2[0];
+                    sh4(in6[0], in6[1], in6[2], g);
+#pragma unroll
+                    for (int i = 0; i < 15; i++) g[16 + i] = h2[1 + i];
+                    g[31] = 0.0f;
+                    store_half_row(fG, r, 0, g);
+                } else {
+                    zero_half_row(fG, r, 1);
+                }
+            }
+            set_publish(1);
+            isF.wait();
+            if (doF) relu_to_tile(accF, hf, fC1, r);
+            set_publish(1);
+            isF.wait();
+            if (doF) relu_to_tile(accF, hf, fC2, r);
+            set_publish(1);
+            isF.wait();
+            if (doF) {
+                if (hf == 0) {   // output gradient dO (3 meaningful columns, zero padded)
+                    float o[16], d[32];
+                    tmem_ld16(accF, o);
+#pragma unroll
+                    for (int i = 0; i < 32; i++) d[i] = 0.0f;
+                    if (in_f) {
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            const float sg = 1.0f / (1.0f + __expf(-o[c]));
+                            d[c] = in6[3 + c] * sg * (1.0f - sg);
+                        }
+                    }
+                    store_half_row(fX, r, 0, d);
+                } else {
+                    zero_half_row(fX, r, 1);
+                }
+            }
+            fence_async_smem();
+            fence_before_sync();
+            bar_sync_n(3, 512);     // the sets meet: this set's tiles (and dO, h0) are complete, the other set is free
+            fence_after_sync();
+        }
+    } else {
+        // ================= backward of tile it - 1 (set (it - 1) & 1) =================
+        Issue isB{mbarB, 0};
+        const uint32_t accB = t_row + kAccB;
+        for (uint32_t it = 0; it <= n_my; it++) {
+            const bool doB = it > 0;
+            uint8_t *sB = smem + ((it & 1u) ^ 1u) * kSetTiles * kTileBytes;
+            uint8_t *bH1 = sB + kTH1 * kTileBytes, *bC1 = sB + kTC1 * kTileBytes, *bC2 = sB + kTC2 * kTileBytes, *bX = sB + kTX * kTileBytes;
+            const uint32_t tile_b = blockIdx.x + (it - 1) * gridDim.x, row_b = tile_b * kRows + r;
+            const bool in_b = doB && row_b < a.M;
+            float gs_b = 0.f, h0_b = 0.f;
+            if (in_b && hf == 0) { gs_b = a.g_sigma[row_b]; h0_b = s_h0[(it & 1u) ^ 1u][r]; }
+            set_publish(2);
+            isB.wait();
+            if (doB) masked_to_tile(accB, hf, bC2, bX, r);      // dC2
+            set_publish(2);
+            isB.wait();
+            if (doB) masked_to_tile(accB, hf, bC1, bX, r);      // dC1
+            set_publish(2);
+            isB.wait();
+            if (doB) {
+                if (hf == 1) {   // gradient w.r.t. the colour-grid features (dfeats cols 32..63)
+                    float dfc[32];
+                    tmem_ld32(accB, dfc);
+                    if (in_b) {
+                        uint4 *dst = reinterpret_cast<uint4 *>(a.dfeats + (size_t)row_b * 64) + 4;
+#pragma unroll
+                        for (int i = 0; i < 32; i++) dfc[i] *= a.out_scale;
+#pragma unroll
+                        for (uint32_t q = 0; q < 4; q++) dst[q] = pack8(dfc + q * 8);
+                    }
+                    zero_half_row(bX, r, 1);
+                } else {
+                    float v[32], d[32];
+                    tmem_ld32(accB + 32, v);  // cols 32-47 dSH (dropped), 48-62 dgeo
+#pragma unroll
+                    for (int i = 0; i < 32; i++) d[i] = 0.0f;
+                    if (in_b) d[0] = gs_b * a.density_scale * __expf(fminf(fmaxf(h0_b, -15.0f), 15.0f));  // trunc_exp backward
+#pragma unroll
+                    for (int i = 0; i < 15; i++) d[1 + i] = v[16 + i];
+                    store_half_row(bX, r, 0, d);            // dh2
+                }
+            }
+            set_publish(2);
+            isB.wait();
+            if (doB) masked_to_tile(accB, hf, bH1, bX, r);      // dH1
+            set_publish(2);
+            isB.wait();
+            if (doB) {
+                if (hf == 0) {
+                    float dfs[32];
+                    tmem_ld32(accB, dfs);
+                    if (in_b) {
+                        uint4 *dst = reinterpret_cast<uint4 *>(a.dfeats + (size_t)row_b * 64);
+#pragma unroll
+                        for (int i = 0; i < 32; i++) dfs[i] *= a.out_scale;
+#pragma unroll
+                        for (uint32_t q = 0; q < 4; q++) dst[q] = pack8(dfs + q * 8);
+                    }
+                }
+            }
+            fence_before_sync();
+            bar_sync_n(3, 512);
+            fence_after_sync();
+        }
+
+        // ---- flush weight gradients (same layout as k_ngp_mlp_bwd) ----
+        if (a.train_mlp && n_my > 0) {
+            const uint32_t lane = tid & 31, rr = (warp & 3u) * 16 + lane;   // output feature
+            const bool rowok = lane < 16;
+            float v[32];
+            tmem_ld32(t_row + 64 + hf * 32, v);    // dWc2 [3 x 64]
+            if (rowok && rr < 3) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c2 + rr * 64 + hf * 32 + i, v[i]);
+            tmem_ld32(t_row + 128 + hf * 32, v);   // dWc1 [64 x 64]
+            if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c1 + rr * 64 + hf * 32 + i, v[i]);
+            tmem_ld32(t_row + 320 + hf * 32, v);   // dWs1 [16 x 64]
+            if (rowok && rr < 16) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s1 + rr * 64 + hf * 32 + i, v[i]);
+            if (hf == 1) {
+                tmem_ld32(t_row + 192 + 32, v);    // dC1^T . F, columns 32..63 = colour-grid inputs = original columns 31..62
+                if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c0 + rr * 63 + 31 + i, v[i]);
+            } else {
+                tmem_ld32(t_row + 256, v);         // dC1^T . G, columns 0..30 = [SH | geo] = original columns 0..30
+                if (rowok) for (int i = 0; i < 31; i++) atomicAdd(a.gw_c0 + rr * 63 + i, v[i]);
+                tmem_ld32(t_row + 384, v);         // dH1^T . F, columns 0..31 = sigma-grid inputs
+                if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s0 + rr * 32 + i, v[i]);
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (is_issuer) tmem_dealloc(tmem, 512);
+}
+
 // interleave two [N,2] fp32 tables into one [N,4] fp16 table {s0,s1,c0,c1}
 __global__ void k_interleave_tables(const float2 *__restrict__ ts, const float2 *__restrict__ tc, uint2 *__restrict__ out, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1187,9 +1477,10 @@ S3D_API int s3d_ngp_mlp_backward(const void *feats, const float *dirs, uint32_t 
                                  void *dfeats, float out_scale, float *gw_s0, float *gw_s1, float *gw_c0, float *gw_c1, float *gw_c2,
                                  int train_mlp, void *stream) {
     if (M == 0) return 0;
-    static const int two_chains = [] { const char *v = getenv("S3D_MLP_BWD"); return v ? atoi(v) : 2; }();
-    const size_t smem = two_chains == 2 ? bwd2_smem() : bwd_smem();
-    cudaError_t e = two_chains == 2 ? cudaFuncSetAttribute(k_ngp_mlp_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+    static const int two_chains = [] { const char *v = getenv("S3D_MLP_BWD"); return v ? atoi(v) : 3; }();
+    const size_t smem = two_chains >= 2 ? bwd2_smem() : bwd_smem();
+    cudaError_t e = two_chains == 3 ? cudaFuncSetAttribute(k_ngp_mlp_bwd3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                  : two_chains == 2 ? cudaFuncSetAttribute(k_ngp_mlp_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                     : cudaFuncSetAttribute(k_ngp_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     BwdArgs a;
@@ -1199,7 +1490,8 @@ S3D_API int s3d_ngp_mlp_backward(const void *feats, const float *dirs, uint32_t 
     a.gw_s0 = gw_s0; a.gw_s1 = gw_s1; a.gw_c0 = gw_c0; a.gw_c1 = gw_c1; a.gw_c2 = gw_c2;
     a.M = M; a.n_tiles = div_up(M, kRows); a.density_scale = density_scale; a.out_scale = out_scale; a.train_mlp = train_mlp;
     const uint32_t grid = min(a.n_tiles, (uint32_t)sm_count());
-    if (two_chains == 2) k_ngp_mlp_bwd2<<<grid, kMlpThreads, smem, as_stream(stream)>>>(a);
+    if (two_chains == 3) k_ngp_mlp_bwd3<<<grid, kBwd3Threads, smem, as_stream(stream)>>>(a);
+    else if (two_chains == 2) k_ngp_mlp_bwd2<<<grid, kMlpThreads, smem, as_stream(stream)>>>(a);
     else k_ngp_mlp_bwd<<<grid, kMlpThreads, smem, as_stream(stream)>>>(a);
     S3D_RETURN_LAST();
 }
