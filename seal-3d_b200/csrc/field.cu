@@ -15,13 +15,14 @@
 //   k_ngp_mlp_bwd   recomputes the forward from feats (cheaper than storing 3x64 activations per sample), then
 //                   data gradients (weights read MN-major = transposed for free) and weight gradients (both
 //                   operands MN-major, K = the 128 samples of the tile) as tcgen05 MMAs; weight gradients
-//                   accumulate in TMEM across all tiles of the persistent CTA and are flushed once.
+//                   accumulate in TMEM across all tiles of the persistent CTA and are flushed once.  Two chains are
+//                   in flight per SM (backward of tile t, forward recompute of tile t+1), each with its own
+//                   epilogue warps, to cover the per-round tensor-core round trip.
 //   k_ngp_scatter   xyz + dfeats -> interleaved fp32 gradient table with the in-warp segmented pre-reduction
 //                   (ray-major samples share cells at coarse levels) and one 128-bit RED per corner.
 //
 // Level geometry follows gridencoder.cu:137-156 of the reference (D=3, linear interpolation,
 // align_corners=false); MLP semantics follow nerf/network.py:99-128 and activation.py:5-17.
-#include <stdlib.h>
 #include "tc05.cuh"
 
 namespace {
@@ -593,498 +594,29 @@ struct BwdArgs {
     int train_mlp;
 };
 
-// TMEM columns: [0,64) activation accumulator | [64,128) dWc2 | [128,192) dWc1 | [192,256) dC1^T.F | [256,320) dC1^T.G | [320,384) dWs1 |
-// [384,448) dH1^T.F.  Every weight-gradient MMA is a full 64 x 64 (M = 64, N = 64) block; the flush picks the valid columns.
-// Per round the issuer sends the data-gradient MMAs first and commits, then the weight-gradient MMAs, which run on the
-// tensor pipe while the epilogue warps already work on the data gradient; the gradient tiles X / Y alternate, so an
-// epilogue never writes a tile the in-flight weight-gradient MMAs read.  In the last round the weight gradient goes
-// first (the commit must cover it: the feature tile is overwritten by the next tile's loads).
-__global__ void __launch_bounds__(kMlpThreads)
-k_ngp_mlp_bwd(const BwdArgs a) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_mbar;
-    __shared__ uint32_t s_tmem;
-    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t *tF = smem, *tH1 = tF + kTileBytes, *tG = tH1 + kTileBytes, *tC1 = tG + kTileBytes, *tC2 = tC1 + kTileBytes,
-            *tX = tC2 + kTileBytes, *tY = tX + kTileBytes, *tWs0 = tY + kTileBytes, *tWc0 = tWs0 + kWTile, *tWc1 = tWc0 + kWTile,
-            *tWs1 = tWc1 + kWTile, *tWc2 = tWs1 + kOTile;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, r = tid & 127, hf = (tid >> 7) & 1u;
-    const bool is_issuer = (warp == kIssuerWarp);
-    if (is_issuer) tmem_alloc(smem_u32(&s_tmem), 512);
-    if (tid == 0) mbar_init(smem_u32(&s_mbar), 1);
-    load_weights(tWs0, tWs1, tWc0, tWc1, tWc2, a.w);
-    sync_tiles();
-    const uint32_t tmem = s_tmem, t_row = tmem + (((warp & 3u) * 32u) << 16);
-    Issue is{smem_u32(&s_mbar), 0};
-    bool first = true;
-
-    if (is_issuer) {
-        const bool lead = (tid & 31) == 0;
-        const uint32_t aF = smem_u32(tF), aH1 = smem_u32(tH1), aG = smem_u32(tG), aC1 = smem_u32(tC1), aC2 = smem_u32(tC2), aX = smem_u32(tX), aY = smem_u32(tY);
-        const uint32_t aWs0 = smem_u32(tWs0), aWs1 = smem_u32(tWs1), aWc0 = smem_u32(tWc0), aWc1 = smem_u32(tWc1), aWc2 = smem_u32(tWc2);
-        const uint32_t id64 = make_idesc(128, 64, false, false), id16 = make_idesc(128, 16, false, false);
-        const uint32_t id64t = make_idesc(128, 64, false, true);        // B read MN-major (= W^T)
-        const uint32_t idw64 = make_idesc(64, 64, true, true);
-        const uint32_t accC2 = tmem + 64, accC1 = tmem + 128, accC0f = tmem + 192, accC0g = tmem + 256, accS1 = tmem + 320, accS0 = tmem + 384;
-        const bool tw = a.train_mlp != 0;
-        for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, first = false) {
-            // ---- forward recompute ----
-            iss_acquire();
-            if (lead) { for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, k), desc_kmajor(aWs0, k), id64, k > 0); mma_commit(is.mbar); }
-            iss_acquire();
-            if (lead) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aH1, k), desc_kmajor(aWs1, k), id16, k > 0); mma_commit(is.mbar); }
-            iss_acquire();
-            if (lead) {
-                for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, 2 + k), desc_kmajor(aWc0, k), id64, k > 0);
-                for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aG, k), desc_kmajor(aWc0, 2 + k), id64, true);
-                mma_commit(is.mbar);
-            }
-            iss_acquire();
-            if (lead) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aC1, k), desc_kmajor(aWc1, k), id64, k > 0); mma_commit(is.mbar); }
-            iss_acquire();
-            if (lead) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aC2, k), desc_kmajor(aWc2, k), id16, k > 0); mma_commit(is.mbar); }
-            // ---- backward ----
-            iss_acquire();   // dO in X:  dC2 = dO . Wc2 ;  dWc2 += dO^T . C2
-            if (lead) {
-                mma_f16(tmem, desc_kmajor(aX, 0), desc_mnmajor(aWc2, 0, kOTile), id64t, false);
-                mma_commit(is.mbar);
-                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accC2, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aC2, k, kTileBytes), idw64, !(first && k == 0));
-            }
-            iss_acquire();   // dC2 in Y:  dC1 = dC2 . Wc1 ;  dWc1 += dC2^T . C1
-            if (lead) {
-                for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aY, k), desc_mnmajor(aWc1, k, kWTile), id64t, k > 0);
-                mma_commit(is.mbar);
-                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accC1, desc_mnmajor(aY, k, kTileBytes), desc_mnmajor(aC1, k, kTileBytes), idw64, !(first && k == 0));
-            }
-            iss_acquire();   // dC1 in X:  d[colour feats | SH | geo] = dC1 . Wc0p ;  dWc0 += dC1^T . [F | G]
-            if (lead) {
-                for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aX, k), desc_mnmajor(aWc0, k, kWTile), id64t, k > 0);
-                mma_commit(is.mbar);
-                if (tw) {
-                    for (uint32_t k = 0; k < 8; k++) mma_f16(accC0f, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aF, k, kTileBytes), idw64, !(first && k == 0));
-                    for (uint32_t k = 0; k < 8; k++) mma_f16(accC0g, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aG, k, kTileBytes), idw64, !(first && k == 0));
-                }
-            }
-            iss_acquire();   // dh2 in Y:  dH1 = dh2 . Ws1 ;  dWs1 += dh2^T . H1
-            if (lead) {
-                mma_f16(tmem, desc_kmajor(aY, 0), desc_mnmajor(aWs1, 0, kOTile), id64t, false);
-                mma_commit(is.mbar);
-                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accS1, desc_mnmajor(aY, k, kTileBytes), desc_mnmajor(aH1, k, kTileBytes), idw64, !(first && k == 0));
-            }
-            iss_acquire();   // dH1 in X (last round: weight gradient first)
-            if (lead) {
-                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accS0, desc_mnmajor(aX, k, kTileBytes), desc_mnmajor(aF, k, kTileBytes), idw64, !(first && k == 0));
-                for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aX, k), desc_mnmajor(aWs0, k, kWTile), id64t, k > 0);
-                mma_commit(is.mbar);
-            }
-            tile_end_sync();
-        }
-    } else {
-        FeatPre nf;
-        float nin7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // warpgroup 0: dir xyz, dL/drgb, dL/dsigma of the next tile
-        auto prefetch = [&](uint32_t t) {
-            const uint32_t prow = t * kRows + r;
-            const bool pin = t < a.n_tiles && prow < a.M;
-            nf.load(a.feats, prow, hf, pin);
-            if (hf == 0) {
-#pragma unroll
-                for (int j = 0; j < 3; j++) { nin7[j] = pin ? a.dirs[(size_t)prow * 3 + j] : 0.f; nin7[3 + j] = pin ? a.g_rgb[(size_t)prow * 3 + j] : 0.f; }
-                nin7[6] = pin ? a.g_sigma[prow] : 0.f;
-            }
-        };
-        prefetch(blockIdx.x);
-        for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, first = false) {
-            const uint32_t row = tile * kRows + r;
-            const bool in_range = row < a.M;
-            // ---------------- recompute the forward, keeping every activation tile ----------------
-            nf.store(tF, r, hf);
-            float in7[7];
-#pragma unroll
-            for (int j = 0; j < 7; j++) in7[j] = nin7[j];
-            prefetch(tile + gridDim.x);
-            epi_publish();
-            is.wait();
-            relu_to_tile(t_row, hf, tH1, r);
-            epi_publish();
-            is.wait();
-            float h0 = 0.0f;   // sigma logit (kept by warpgroup 0 for the trunc_exp backward)
-            if (hf == 0) {
-                float h2[16], g[32];
-                tmem_ld16(t_row, h2);
-                h0 = h2[0];
-                sh4(in7[0], in7[1], in7[2], g);
-#pragma unroll
-                for (int i = 0; i < 15; i++) g[16 + i] = h2[1 + i];
-                g[31] = 0.0f;
-                store_half_row(tG, r, 0, g);
-            } else {
-                zero_half_row(tG, r, 1);
-            }
-            epi_publish();
-            is.wait();
-            relu_to_tile(t_row, hf, tC1, r);
-            epi_publish();
-            is.wait();
-            relu_to_tile(t_row, hf, tC2, r);
-            epi_publish();
-            is.wait();
-            // ---------------- output gradients -> tX (3 meaningful columns, zero padded) ----------------
-            if (hf == 0) {
-                float o[16], d[32];
-                tmem_ld16(t_row, o);
-#pragma unroll
-                for (int i = 0; i < 32; i++) d[i] = 0.0f;
-                if (in_range) {
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        const float sg = 1.0f / (1.0f + __expf(-o[c]));
-                        d[c] = in7[3 + c] * sg * (1.0f - sg);
-                    }
-                }
-                store_half_row(tX, r, 0, d);
-            } else {
-                zero_half_row(tX, r, 1);
-            }
-            epi_publish();
-            is.wait();
-            masked_to_tile(t_row, hf, tC2, tY, r);      // dC2
-            epi_publish();
-            is.wait();
-            masked_to_tile(t_row, hf, tC1, tX, r);      // dC1
-            epi_publish();
-            is.wait();
-            float dfc[32];   // warpgroup 1: gradient w.r.t. the colour-grid features (dfeats cols 32..63), kept in registers
-            if (hf == 1) {
-                tmem_ld32(t_row, dfc);
-                zero_half_row(tY, r, 1);
-            } else {
-                float v[32], d[32];
-                tmem_ld32(t_row + 32, v);  // cols 32-47 dSH (dropped), 48-62 dgeo
-#pragma unroll
-                for (int i = 0; i < 32; i++) d[i] = 0.0f;
-                if (in_range) d[0] = in7[6] * a.density_scale * __expf(fminf(fmaxf(h0, -15.0f), 15.0f));  // trunc_exp backward
-#pragma unroll
-                for (int i = 0; i < 15; i++) d[1 + i] = v[16 + i];
-                store_half_row(tY, r, 0, d);            // dh2
-            }
-            epi_publish();
-            is.wait();
-            masked_to_tile(t_row, hf, tH1, tX, r);      // dH1
-            epi_publish();
-            is.wait();
-            if (hf == 0) {
-                float dfs[32];
-                tmem_ld32(t_row, dfs);
-                if (in_range) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(a.dfeats + (size_t)row * 64);
-#pragma unroll
-                    for (int i = 0; i < 32; i++) dfs[i] *= a.out_scale;
-#pragma unroll
-                    for (uint32_t q = 0; q < 4; q++) dst[q] = pack8(dfs + q * 8);
-                }
-            } else if (in_range) {
-                uint4 *dst = reinterpret_cast<uint4 *>(a.dfeats + (size_t)row * 64) + 4;
-#pragma unroll
-                for (int i = 0; i < 32; i++) dfc[i] *= a.out_scale;
-#pragma unroll
-                for (uint32_t q = 0; q < 4; q++) dst[q] = pack8(dfc + q * 8);
-            }
-            tile_end_sync();
-        }
-
-        // ---- flush weight gradients: accumulator rows (M = 64) live in lanes 0..15 of every 32-lane sub-partition;
-        //      warpgroup hf takes the columns [32*hf, 32*hf+32) of every block ----
-        if (a.train_mlp && !first) {
-            const uint32_t lane = tid & 31, rr = (warp & 3u) * 16 + lane;   // output feature
-            const bool rowok = lane < 16;
-            float v[32];
-            tmem_ld32(t_row + 64 + hf * 32, v);    // dWc2 [3 x 64]
-            if (rowok && rr < 3) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c2 + rr * 64 + hf * 32 + i, v[i]);
-            tmem_ld32(t_row + 128 + hf * 32, v);   // dWc1 [64 x 64]
-            if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c1 + rr * 64 + hf * 32 + i, v[i]);
-            tmem_ld32(t_row + 320 + hf * 32, v);   // dWs1 [16 x 64]
-            if (rowok && rr < 16) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s1 + rr * 64 + hf * 32 + i, v[i]);
-            if (hf == 1) {
-                tmem_ld32(t_row + 192 + 32, v);    // dC1^T . F, columns 32..63 = colour-grid inputs = original columns 31..62
-                if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c0 + rr * 63 + 31 + i, v[i]);
-            } else {
-                tmem_ld32(t_row + 256, v);         // dC1^T . G, columns 0..30 = [SH | geo] = original columns 0..30
-                if (rowok) for (int i = 0; i < 31; i++) atomicAdd(a.gw_c0 + rr * 63 + i, v[i]);
-                tmem_ld32(t_row + 384, v);         // dH1^T . F, columns 0..31 = sigma-grid inputs
-                if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s0 + rr * 32 + i, v[i]);
-            }
-        }
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (is_issuer) tmem_dealloc(tmem, 512);
-}
-
 // ------------------------------------------------------------------------------------------------
-// MLP backward, two chains in flight.  The backward of tile t (5 tensor-core rounds) and the forward recompute of
-// tile t+1 (5 rounds) are independent dependency chains; the epilogue warps alternate between them, so while the
-// tensor core (and the commit -> mbarrier round trip) works for one chain the warps run the epilogue of the other.
-// Two sets of six tiles {F, H1, G, C1, C2, X} alternate between consecutive tiles; the single gradient tile X of a set
-// is reused by every backward round, which is safe because each round's commit is issued after its weight-gradient
-// MMAs (the wait that guards the accumulator read also guarantees nothing still reads X).  TMEM: columns [0,64)
-// backward accumulator, [64,448) the six weight-gradient blocks, [448,512) forward accumulator.
+// MLP backward: two dependency chains in flight, one epilogue warp set per chain.
+//   * The backward of tile t (5 tensor-core rounds) and the forward recompute of tile t+1 (5 rounds) are independent
+//     chains.  Threads 0-255 (8 warps) run the forward epilogues, threads 256-511 the backward epilogues, warp 16 issues
+//     every tcgen05.mma.  ncu on the one-chain predecessor showed 41 % of the epilogue warps' samples on the
+//     MMA-completion mbarrier and a 20 % busy tensor pipe: the kernel is bound by the publish -> issue -> MMA -> commit ->
+//     wake round trip of each round, so the second chain fills that time.
+//   * Two sets of six [128 x 64] fp16 tiles {F, H1, G, C1, C2, X} alternate between consecutive tiles (192 KB + 28 KB of
+//     weights).  The single gradient tile X of a set is reused by every backward round: a round's commit follows its
+//     weight-gradient MMAs, so the wait that guards the accumulator read also guarantees nothing still reads X.
+//   * TMEM columns: [0,64) backward accumulator | [64,128) dWc2 | [128,192) dWc1 | [192,256) dC1^T.F | [256,320) dC1^T.G |
+//     [320,384) dWs1 | [384,448) dH1^T.F | [448,512) forward accumulator.  Weight gradients accumulate in TMEM over all
+//     tiles of the CTA (every block a full M = 64, N = 64 MMA) and are flushed once with fp32 atomics.
+//   * Hand-off: an epilogue set publishes with bar.arrive on its named barrier (1 = forward, 2 = backward) and goes
+//     straight to its mbarrier; the issuer bar.syncs on the two barriers alternately and always commits (an empty commit
+//     in the first / last iteration keeps the sets in lock step).  The sets meet once per iteration (named barrier 3)
+//     before the tile sets swap roles; the sigma logit travels forward set -> backward set through shared memory.
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kSetTiles = 6;
 enum : uint32_t { kTF = 0, kTH1 = 1, kTG = 2, kTC1 = 3, kTC2 = 4, kTX = 5 };
 
-__global__ void __launch_bounds__(kMlpThreads, 1)
-k_ngp_mlp_bwd2(const BwdArgs a) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_mbar[2];
-    __shared__ uint32_t s_tmem;
-    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t *tWs0 = smem + 2 * kSetTiles * kTileBytes, *tWc0 = tWs0 + kWTile, *tWc1 = tWc0 + kWTile, *tWs1 = tWc1 + kWTile, *tWc2 = tWs1 + kOTile;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, r = tid & 127, hf = (tid >> 7) & 1u;
-    const bool is_issuer = (warp == kIssuerWarp);
-    if (is_issuer) tmem_alloc(smem_u32(&s_tmem), 512);
-    if (tid == 0) { mbar_init(smem_u32(&s_mbar[0]), 1); mbar_init(smem_u32(&s_mbar[1]), 1); }
-    load_weights(tWs0, tWs1, tWc0, tWc1, tWc2, a.w);
-    sync_tiles();
-    const uint32_t tmem = s_tmem, t_row = tmem + (((warp & 3u) * 32u) << 16);
-    const uint32_t n_my = blockIdx.x < a.n_tiles ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const uint32_t mbarF = smem_u32(&s_mbar[0]), mbarB = smem_u32(&s_mbar[1]);
-    constexpr uint32_t kAccF = 448, kAccB = 0;
-
-    if (is_issuer) {
-        const bool lead = (tid & 31) == 0;
-        const uint32_t base = smem_u32(smem);
-        const uint32_t aWs0 = smem_u32(tWs0), aWs1 = smem_u32(tWs1), aWc0 = smem_u32(tWc0), aWc1 = smem_u32(tWc1), aWc2 = smem_u32(tWc2);
-        const uint32_t id64 = make_idesc(128, 64, false, false), id16 = make_idesc(128, 16, false, false);
-        const uint32_t id64t = make_idesc(128, 64, false, true);        // B read MN-major (= W^T)
-        const uint32_t idw64 = make_idesc(64, 64, true, true);
-        const uint32_t accF = tmem + kAccF, accB = tmem + kAccB;
-        const uint32_t accC2 = tmem + 64, accC1 = tmem + 128, accC0f = tmem + 192, accC0g = tmem + 256, accS1 = tmem + 320, accS0 = tmem + 384;
-        const bool tw = a.train_mlp != 0;
-        for (uint32_t it = 0; it <= n_my; it++) {
-            const bool doF = it < n_my, doB = it > 0, firstB = (it == 1);
-            const uint32_t sf = base + (it & 1u) * kSetTiles * kTileBytes, sb = base + ((it & 1u) ^ 1u) * kSetTiles * kTileBytes;
-            const uint32_t fF = sf + kTF * kTileBytes, fH1 = sf + kTH1 * kTileBytes, fG = sf + kTG * kTileBytes, fC1 = sf + kTC1 * kTileBytes, fC2 = sf + kTC2 * kTileBytes;
-            const uint32_t bF = sb + kTF * kTileBytes, bH1 = sb + kTH1 * kTileBytes, bG = sb + kTG * kTileBytes, bC1 = sb + kTC1 * kTileBytes, bC2 = sb + kTC2 * kTileBytes, bX = sb + kTX * kTileBytes;
-            iss_acquire();   // features of the forward tile stored; dO of the backward tile was published at the end of the previous iteration
-            if (lead && doF) { for (uint32_t k = 0; k < 2; k++) mma_f16(accF, desc_kmajor(fF, k), desc_kmajor(aWs0, k), id64, k > 0); mma_commit(mbarF); }
-            if (lead && doB) {   // dC2 = dO . Wc2 ;  dWc2 += dO^T . C2
-                mma_f16(accB, desc_kmajor(bX, 0), desc_mnmajor(aWc2, 0, kOTile), id64t, false);
-                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accC2, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bC2, k, kTileBytes), idw64, !(firstB && k == 0));
-                mma_commit(mbarB);
-            }
-            iss_acquire();   // H1 written
-            if (lead && doF) { for (uint32_t k = 0; k < 4; k++) mma_f16(accF, desc_kmajor(fH1, k), desc_kmajor(aWs1, k), id16, k > 0); mma_commit(mbarF); }
-            iss_acquire();   // dC2 in X:  dC1 = dC2 . Wc1 ;  dWc1 += dC2^T . C1
-            if (lead && doB) {
-                for (uint32_t k = 0; k < 4; k++) mma_f16(accB, desc_kmajor(bX, k), desc_mnmajor(aWc1, k, kWTile), id64t, k > 0);
-                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accC1, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bC1, k, kTileBytes), idw64, !(firstB && k == 0));
-                mma_commit(mbarB);
-            }
-            iss_acquire();   // [SH | geo] written
-            if (lead && doF) {
-                for (uint32_t k = 0; k < 2; k++) mma_f16(accF, desc_kmajor(fF, 2 + k), desc_kmajor(aWc0, k), id64, k > 0);
-                for (uint32_t k = 0; k < 2; k++) mma_f16(accF, desc_kmajor(fG, k), desc_kmajor(aWc0, 2 + k), id64, true);
-                mma_commit(mbarF);
-            }
-            iss_acquire();   // dC1 in X:  d[colour feats | SH | geo] = dC1 . Wc0p ;  dWc0 += dC1^T . [F | G]
-            if (lead && doB) {
-                for (uint32_t k = 0; k < 4; k++) mma_f16(accB, desc_kmajor(bX, k), desc_mnmajor(aWc0, k, kWTile), id64t, k > 0);
-                if (tw) {
-                    for (uint32_t k = 0; k < 8; k++) mma_f16(accC0f, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bF, k, kTileBytes), idw64, !(firstB && k == 0));
-                    for (uint32_t k = 0; k < 8; k++) mma_f16(accC0g, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bG, k, kTileBytes), idw64, !(firstB && k == 0));
-                }
-                mma_commit(mbarB);
-            }
-            iss_acquire();   // C1 written
-            if (lead && doF) { for (uint32_t k = 0; k < 4; k++) mma_f16(accF, desc_kmajor(fC1, k), desc_kmajor(aWc1, k), id64, k > 0); mma_commit(mbarF); }
-            iss_acquire();   // dh2 in X:  dH1 = dh2 . Ws1 ;  dWs1 += dh2^T . H1
-            if (lead && doB) {
-                mma_f16(accB, desc_kmajor(bX, 0), desc_mnmajor(aWs1, 0, kOTile), id64t, false);
-                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accS1, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bH1, k, kTileBytes), idw64, !(firstB && k == 0));
-                mma_commit(mbarB);
-            }
-            iss_acquire();   // C2 written
-            if (lead && doF) { for (uint32_t k = 0; k < 4; k++) mma_f16(accF, desc_kmajor(fC2, k), desc_kmajor(aWc2, k), id16, k > 0); mma_commit(mbarF); }
-            iss_acquire();   // dH1 in X:  dF = dH1 . Ws0 ;  dWs0 += dH1^T . F
-            if (lead && doB) {
-                for (uint32_t k = 0; k < 4; k++) mma_f16(accB, desc_kmajor(bX, k), desc_mnmajor(aWs0, k, kWTile), id64t, k > 0);
-                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accS0, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bF, k, kTileBytes), idw64, !(firstB && k == 0));
-                mma_commit(mbarB);
-            }
-            iss_acquire();   // end of the iteration: dO of the forward tile published, the backward set is free
-        }
-    } else {
-        Issue isF{mbarF, 0}, isB{mbarB, 0};
-        const uint32_t accF = t_row + kAccF, accB = t_row + kAccB;
-        FeatPre nf;
-        float nin7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // warpgroup 0: dir xyz, dL/drgb, dL/dsigma of the next forward tile
-        auto prefetch = [&](uint32_t t) {
-            const uint32_t prow = t * kRows + r;
-            const bool pin = t < a.n_tiles && prow < a.M;
-            nf.load(a.feats, prow, hf, pin);
-            if (hf == 0) {
-#pragma unroll
-                for (int j = 0; j < 3; j++) { nin7[j] = pin ? a.dirs[(size_t)prow * 3 + j] : 0.f; nin7[3 + j] = pin ? a.g_rgb[(size_t)prow * 3 + j] : 0.f; }
-                nin7[6] = pin ? a.g_sigma[prow] : 0.f;
-            }
-        };
-        prefetch(blockIdx.x);
-        float h0_b = 0.f, gs_b = 0.f;      // backward tile: sigma logit and dL/dsigma (warpgroup 0)
-        uint32_t row_b = 0;
-        bool in_b = false;
-        for (uint32_t it = 0; it <= n_my; it++) {
-            const bool doF = it < n_my, doB = it > 0;
-            uint8_t *sF = smem + (it & 1u) * kSetTiles * kTileBytes, *sB = smem + ((it & 1u) ^ 1u) * kSetTiles * kTileBytes;
-            uint8_t *fF = sF + kTF * kTileBytes, *fH1 = sF + kTH1 * kTileBytes, *fG = sF + kTG * kTileBytes, *fC1 = sF + kTC1 * kTileBytes, *fC2 = sF + kTC2 * kTileBytes, *fX = sF + kTX * kTileBytes;
-            uint8_t *bH1 = sB + kTH1 * kTileBytes, *bC1 = sB + kTC1 * kTileBytes, *bC2 = sB + kTC2 * kTileBytes, *bX = sB + kTX * kTileBytes;
-            const uint32_t tile_f = blockIdx.x + it * gridDim.x, row_f = tile_f * kRows + r;
-            const bool in_f = doF && row_f < a.M;
-            float in7[7], h0_f = 0.f;
-#pragma unroll
-            for (int j = 0; j < 7; j++) in7[j] = nin7[j];
-            if (doF) {
-                nf.store(fF, r, hf);
-                prefetch(tile_f + gridDim.x);
-            }
-            epi_publish();
-            // ---- F0 -> H1 ----
-            if (doF) { isF.wait(); relu_to_tile(accF, hf, fH1, r); }
-            epi_publish();
-            // ---- B0 -> dC2 ----
-            if (doB) { isB.wait(); masked_to_tile(accB, hf, bC2, bX, r); }
-            epi_publish();
-            // ---- F1 -> sigma logit, [SH | geo] ----
-            if (doF) {
-                isF.wait();
-                if (hf == 0) {
-                    float h2[16], g[32];
-                    tmem_ld16(accF, h2);
-                    h0_f = h2[0];
-                    sh4(in7[0], in7[1], in7[2], g);
-#pragma unroll
-                    for (int i = 0; i < 15; i++) g[16 + i] = h2[1 + i];
-                    g[31] = 0.0f;
-                    store_half_row(fG, r, 0, g);
-                } else {
-                    zero_half_row(fG, r, 1);
-                }
-            }
-            epi_publish();
-            // ---- B1 -> dC1 ----
-            if (doB) { isB.wait(); masked_to_tile(accB, hf, bC1, bX, r); }
-            epi_publish();
-            // ---- F2 -> C1 ----
-            if (doF) { isF.wait(); relu_to_tile(accF, hf, fC1, r); }
-            epi_publish();
-            // ---- B2 -> colour-feature gradient (stored), dh2 ----
-            if (doB) {
-                isB.wait();
-                if (hf == 1) {
-                    float dfc[32];
-                    tmem_ld32(accB, dfc);
-                    if (in_b) {
-                        uint4 *dst = reinterpret_cast<uint4 *>(a.dfeats + (size_t)row_b * 64) + 4;
-#pragma unroll
-                        for (int i = 0; i < 32; i++) dfc[i] *= a.out_scale;
-#pragma unroll
-                        for (uint32_t q = 0; q < 4; q++) dst[q] = pack8(dfc + q * 8);
-                    }
-                    zero_half_row(bX, r, 1);
-                } else {
-                    float v[32], d[32];
-                    tmem_ld32(accB + 32, v);  // cols 32-47 dSH (dropped), 48-62 dgeo
-#pragma unroll
-                    for (int i = 0; i < 32; i++) d[i] = 0.0f;
-                    if (in_b) d[0] = gs_b * a.density_scale * __expf(fminf(fmaxf(h0_b, -15.0f), 15.0f));  // trunc_exp backward
-#pragma unroll
-                    for (int i = 0; i < 15; i++) d[1 + i] = v[16 + i];
-                    store_half_row(bX, r, 0, d);            // dh2
-                }
-            }
-            epi_publish();
-            // ---- F3 -> C2 ----
-            if (doF) { isF.wait(); relu_to_tile(accF, hf, fC2, r); }
-            epi_publish();
-            // ---- B3 -> dH1 ----
-            if (doB) { isB.wait(); masked_to_tile(accB, hf, bH1, bX, r); }
-            epi_publish();
-            // ---- F4 -> output gradient dO (3 meaningful columns, zero padded) ----
-            if (doF) {
-                isF.wait();
-                if (hf == 0) {
-                    float o[16], d[32];
-                    tmem_ld16(accF, o);
-#pragma unroll
-                    for (int i = 0; i < 32; i++) d[i] = 0.0f;
-                    if (in_f) {
-#pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            const float sg = 1.0f / (1.0f + __expf(-o[c]));
-                            d[c] = in7[3 + c] * sg * (1.0f - sg);
-                        }
-                    }
-                    store_half_row(fX, r, 0, d);
-                } else {
-                    zero_half_row(fX, r, 1);
-                }
-            }
-            // ---- B4 -> sigma-feature gradient ----
-            if (doB) {
-                isB.wait();
-                if (hf == 0) {
-                    float dfs[32];
-                    tmem_ld32(accB, dfs);
-                    if (in_b) {
-                        uint4 *dst = reinterpret_cast<uint4 *>(a.dfeats + (size_t)row_b * 64);
-#pragma unroll
-                        for (int i = 0; i < 32; i++) dfs[i] *= a.out_scale;
-#pragma unroll
-                        for (uint32_t q = 0; q < 4; q++) dst[q] = pack8(dfs + q * 8);
-                    }
-                }
-            }
-            epi_publish();
-            h0_b = h0_f; gs_b = in7[6]; row_b = row_f; in_b = in_f;
-        }
-
-        // ---- flush weight gradients (same layout as k_ngp_mlp_bwd) ----
-        if (a.train_mlp && n_my > 0) {
-            const uint32_t lane = tid & 31, rr = (warp & 3u) * 16 + lane;   // output feature
-            const bool rowok = lane < 16;
-            float v[32];
-            tmem_ld32(t_row + 64 + hf * 32, v);    // dWc2 [3 x 64]
-            if (rowok && rr < 3) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c2 + rr * 64 + hf * 32 + i, v[i]);
-            tmem_ld32(t_row + 128 + hf * 32, v);   // dWc1 [64 x 64]
-            if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c1 + rr * 64 + hf * 32 + i, v[i]);
-            tmem_ld32(t_row + 320 + hf * 32, v);   // dWs1 [16 x 64]
-            if (rowok && rr < 16) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s1 + rr * 64 + hf * 32 + i, v[i]);
-            if (hf == 1) {
-                tmem_ld32(t_row + 192 + 32, v);    // dC1^T . F, columns 32..63 = colour-grid inputs = original columns 31..62
-                if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c0 + rr * 63 + 31 + i, v[i]);
-            } else {
-                tmem_ld32(t_row + 256, v);         // dC1^T . G, columns 0..30 = [SH | geo] = original columns 0..30
-                if (rowok) for (int i = 0; i < 31; i++) atomicAdd(a.gw_c0 + rr * 63 + i, v[i]);
-                tmem_ld32(t_row + 384, v);         // dH1^T . F, columns 0..31 = sigma-grid inputs
-                if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s0 + rr * 32 + i, v[i]);
-            }
-        }
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (is_issuer) tmem_dealloc(tmem, 512);
-}
-
-// ------------------------------------------------------------------------------------------------
-// MLP backward, two warp sets.  Same two chains and tile sets as k_ngp_mlp_bwd2, but each chain has its OWN eight
-// epilogue warps (threads 0-255: forward recompute of tile t+1, threads 256-511: backward of tile t, warp 16: issuer),
-// because ncu shows the epilogues -- TMEM reads, ReLU masks, fp16 packing, swizzled stores -- and not the tensor-core
-// latency bound the one-set kernels.  Hand-off: an epilogue set publishes a tile with bar.arrive on its named barrier
-// (1 = forward, 2 = backward) and goes straight to its mbarrier; the issuer bar.syncs on the two barriers alternately.
-// The sets meet once per iteration (named barrier 3) before the tile sets swap roles; the sigma logit travels from the
-// forward set to the backward set through shared memory.
-// ------------------------------------------------------------------------------------------------
-constexpr uint32_t kBwd3Threads = 544;
-constexpr uint32_t kBwd3Issuer = 16;
+constexpr uint32_t kBwdThreads = 544;
+constexpr uint32_t kBwdIssuer = 16;
 
 __device__ __forceinline__ void bar_arrive(uint32_t id, uint32_t n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_sync_n(uint32_t id, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -1098,8 +630,8 @@ __device__ __forceinline__ void iss_acquire_n(uint32_t id) {
     fence_after_sync();
 }
 
-__global__ void __launch_bounds__(kBwd3Threads, 1)
-k_ngp_mlp_bwd3(const BwdArgs a) {
+__global__ void __launch_bounds__(kBwdThreads, 1)
+k_ngp_mlp_bwd(const BwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar[2];
     __shared__ uint32_t s_tmem;
@@ -1107,7 +639,7 @@ k_ngp_mlp_bwd3(const BwdArgs a) {
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *tWs0 = smem + 2 * kSetTiles * kTileBytes, *tWc0 = tWs0 + kWTile, *tWc1 = tWc0 + kWTile, *tWs1 = tWc1 + kWTile, *tWc2 = tWs1 + kOTile;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, r = tid & 127, hf = (tid >> 7) & 1u;
-    const bool is_issuer = (warp == kBwd3Issuer), is_fwd = tid < 256;
+    const bool is_issuer = (warp == kBwdIssuer), is_fwd = tid < 256;
     if (is_issuer) tmem_alloc(smem_u32(&s_tmem), 512);
     if (tid == 0) { mbar_init(smem_u32(&s_mbar[0]), 1); mbar_init(smem_u32(&s_mbar[1]), 1); }
     load_weights(tWs0, tWs1, tWc0, tWc1, tWc2, a.w);
@@ -1337,7 +869,8 @@ k_ngp_mlp_bwd3(const BwdArgs a) {
             fence_after_sync();
         }
 
-        // ---- flush weight gradients (same layout as k_ngp_mlp_bwd) ----
+        // ---- flush weight gradients: accumulator rows (M = 64) live in lanes 0..15 of every 32-lane sub-partition;
+        //      warpgroup hf takes the columns [32*hf, 32*hf+32) of every block ----
         if (a.train_mlp && n_my > 0) {
             const uint32_t lane = tid & 31, rr = (warp & 3u) * 16 + lane;   // output feature
             const bool rowok = lane < 16;
@@ -1407,8 +940,7 @@ k_adam_tables(float2 *__restrict__ ps, float2 *__restrict__ pc, float4 *__restri
 }
 
 size_t fwd_smem() { return 1024 + 2 * kTileBytes + 3 * kWTile + 2 * kOTile; }
-size_t bwd_smem() { return 1024 + 7 * kTileBytes + 3 * kWTile + 2 * kOTile; }
-size_t bwd2_smem() { return 1024 + 2 * kSetTiles * kTileBytes + 3 * kWTile + 2 * kOTile; }
+size_t bwd_smem() { return 1024 + 2 * kSetTiles * kTileBytes + 3 * kWTile + 2 * kOTile; }
 
 int sm_count() {
     int dev = 0, sms = 148;
@@ -1477,11 +1009,8 @@ S3D_API int s3d_ngp_mlp_backward(const void *feats, const float *dirs, uint32_t 
                                  void *dfeats, float out_scale, float *gw_s0, float *gw_s1, float *gw_c0, float *gw_c1, float *gw_c2,
                                  int train_mlp, void *stream) {
     if (M == 0) return 0;
-    static const int two_chains = [] { const char *v = getenv("S3D_MLP_BWD"); return v ? atoi(v) : 3; }();
-    const size_t smem = two_chains >= 2 ? bwd2_smem() : bwd_smem();
-    cudaError_t e = two_chains == 3 ? cudaFuncSetAttribute(k_ngp_mlp_bwd3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                  : two_chains == 2 ? cudaFuncSetAttribute(k_ngp_mlp_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                    : cudaFuncSetAttribute(k_ngp_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = bwd_smem();
+    cudaError_t e = cudaFuncSetAttribute(k_ngp_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     BwdArgs a;
     a.feats = (const __half *)feats; a.dirs = dirs;
@@ -1490,9 +1019,7 @@ S3D_API int s3d_ngp_mlp_backward(const void *feats, const float *dirs, uint32_t 
     a.gw_s0 = gw_s0; a.gw_s1 = gw_s1; a.gw_c0 = gw_c0; a.gw_c1 = gw_c1; a.gw_c2 = gw_c2;
     a.M = M; a.n_tiles = div_up(M, kRows); a.density_scale = density_scale; a.out_scale = out_scale; a.train_mlp = train_mlp;
     const uint32_t grid = min(a.n_tiles, (uint32_t)sm_count());
-    if (two_chains == 3) k_ngp_mlp_bwd3<<<grid, kBwd3Threads, smem, as_stream(stream)>>>(a);
-    else if (two_chains == 2) k_ngp_mlp_bwd2<<<grid, kMlpThreads, smem, as_stream(stream)>>>(a);
-    else k_ngp_mlp_bwd<<<grid, kMlpThreads, smem, as_stream(stream)>>>(a);
+    k_ngp_mlp_bwd<<<grid, kBwdThreads, smem, as_stream(stream)>>>(a);
     S3D_RETURN_LAST();
 }
 
