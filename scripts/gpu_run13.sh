@@ -8,6 +8,6 @@ timeout 900 python bench.py > gpurun_out/bench_r13.log 2>&1; echo "bench rc=$?" 
 tail -1 gpurun_out/bench_r13.log >> gpurun_out/summary.txt
 timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_r13.log 2>&1; echo "bench ref rc=$?" >> gpurun_out/summary.txt
 tail -1 gpurun_out/bench_ref_r13.log >> gpurun_out/summary.txt
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 250 -c 120 --csv --log-file gpurun_out/launches_r13.csv python bench.py --rays 262144 --steps 2 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/ncu_launch13.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 120 --csv --log-file gpurun_out/launches_r13.csv python bench.py --rays 262144 --steps 2 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/ncu_launch13.log 2>&1
 echo "ncu launches rc=$?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt
