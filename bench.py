@@ -25,6 +25,10 @@ import time
 
 import numpy as np
 
+# the sample budget M changes a little at every occupancy refresh: round large torch allocations up to 1/16 of a power of
+# two so the refreshed buffers reuse the cached blocks instead of going to cudaMalloc inside the timed region
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "roundup_power2_divisions:16")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -117,9 +121,33 @@ def cpu_arm(n_rays, steps, warmup):
 
 
 class ClockSampler:
+    """SM clock + clock-event (throttle) reasons of one GPU, sampled DURING the timed region: NVML in a thread (the same
+    counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; an nvidia-smi process per sample is too slow
+    for a 0.2 s region on an 8-GPU box), nvidia-smi -lms as the fallback when pynvml is missing."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
+        self.p = self.f = self.thread = None
+        self.sm, self.reasons, self.mx = [], set(), None
+        try:
+            import threading
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nv = pynvml
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.stop_flag = False
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
@@ -127,8 +155,30 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.BITS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(2)
+            if self.sm:
+                out.update(sm_mhz=float(np.median(self.sm)), sm_max_mhz=self.mx, reasons=sorted(self.reasons), samples=len(self.sm), source="nvml")
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -149,7 +199,7 @@ class ClockSampler:
             except (ValueError, IndexError):
                 pass
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm), source="nvidia-smi")
         return out
 
 

@@ -26,7 +26,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-              "-I", CSRC, "-I", INCLUDE]
+              "-I", CSRC, "-I", INCLUDE] + os.environ.get("S3D_NVCC_EXTRA", "").split()   # e.g. -DS3D_TRACE (scripts/trace_bwd.py)
 SHIMS = ["raymarching", "gridencoder", "shencoder", "freqencoder", "ffmlp"]
 
 

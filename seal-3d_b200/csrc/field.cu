@@ -438,6 +438,24 @@ __device__ __forceinline__ void masked_to_tile(uint32_t t_row, uint32_t hf, cons
     }
     store_half_row(dst_tile, r, hf, v);
 }
+// the same in two phases: the masked, packed half row is built in registers first (while MMAs may still read the destination
+// tile) and stored once the caller knows the tile is free
+__device__ __forceinline__ void masked_half_row(uint32_t t_row, uint32_t hf, const uint8_t *act_tile, uint32_t r, uint4 (&out)[4]) {
+    float v[32];
+    tmem_ld32(t_row + hf * 32, v);
+#pragma unroll
+    for (uint32_t q = 0; q < 4; q++) {
+        float act[8];
+        unpack8(*reinterpret_cast<const uint4 *>(act_tile + sw128_off(r, hf * 4 + q)), act);
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[q * 8 + i] = act[i] > 0.0f ? v[q * 8 + i] : 0.0f;
+        out[q] = pack8(v + q * 8);
+    }
+}
+__device__ __forceinline__ void store_packed_half_row(uint8_t *tile, uint32_t r, uint32_t hf, const uint4 (&v)[4]) {
+#pragma unroll
+    for (uint32_t q = 0; q < 4; q++) *reinterpret_cast<uint4 *>(tile + sw128_off(r, hf * 4 + q)) = v[q];
+}
 
 // ------------------------------------------------------------------------------------------------
 // MLP kernels: 9 warps.  Warps 0-7 (two warpgroups) own the rows / column halves of the tiles and run the epilogues;
@@ -482,7 +500,7 @@ k_ngp_mlp_fwd(const FwdArgs a) {
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *tF = smem, *tT = tF + kTileBytes, *tWs0 = tT + kTileBytes, *tWc0 = tWs0 + kWTile, *tWc1 = tWc0 + kWTile,
             *tWs1 = tWc1 + kWTile, *tWc2 = tWs1 + kOTile;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, r = tid & 127, hf = (tid >> 7) & 1u;
+    const uint32_t tid = threadIdx.x, warp = warp_idx_sync(), r = tid & 127, hf = (tid >> 7) & 1u;
     const bool is_issuer = (warp == kIssuerWarp);
     if (is_issuer) tmem_alloc(smem_u32(&s_tmem), 64);
     if (tid == 0) mbar_init(smem_u32(&s_mbar), 1);
@@ -494,24 +512,24 @@ k_ngp_mlp_fwd(const FwdArgs a) {
     const uint32_t id64 = make_idesc(128, 64, false, false), id16 = make_idesc(128, 16, false, false);
 
     if (is_issuer) {
-        const bool lead = (tid & 31) == 0;
+        const bool lead = elect_one();
         const uint32_t aWs0 = smem_u32(tWs0), aWs1 = smem_u32(tWs1), aWc0 = smem_u32(tWc0), aWc1 = smem_u32(tWc1), aWc2 = smem_u32(tWc2);
         for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
             iss_acquire();   // features loaded
-            if (lead) { for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, k), desc_kmajor(aWs0, k), id64, k > 0); mma_commit(is.mbar); }
+            { for (uint32_t k = 0; k < 2; k++) mma_f16_if(lead, tmem, desc_kmajor(aF, k), desc_kmajor(aWs0, k), id64, k > 0); mma_commit_if(lead, is.mbar); }
             iss_acquire();   // H1 written
-            if (lead) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(aWs1, k), id16, k > 0); mma_commit(is.mbar); }
+            { for (uint32_t k = 0; k < 4; k++) mma_f16_if(lead, tmem, desc_kmajor(aT, k), desc_kmajor(aWs1, k), id16, k > 0); mma_commit_if(lead, is.mbar); }
             if (a.sigma_only) { tile_end_sync(); continue; }
             iss_acquire();   // [SH | geo] written
-            if (lead) {
-                for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aF, 2 + k), desc_kmajor(aWc0, k), id64, k > 0);
-                for (uint32_t k = 0; k < 2; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(aWc0, 2 + k), id64, true);
-                mma_commit(is.mbar);
+            {
+                for (uint32_t k = 0; k < 2; k++) mma_f16_if(lead, tmem, desc_kmajor(aF, 2 + k), desc_kmajor(aWc0, k), id64, k > 0);
+                for (uint32_t k = 0; k < 2; k++) mma_f16_if(lead, tmem, desc_kmajor(aT, k), desc_kmajor(aWc0, 2 + k), id64, true);
+                mma_commit_if(lead, is.mbar);
             }
             iss_acquire();   // C1 written
-            if (lead) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(aWc1, k), id64, k > 0); mma_commit(is.mbar); }
+            { for (uint32_t k = 0; k < 4; k++) mma_f16_if(lead, tmem, desc_kmajor(aT, k), desc_kmajor(aWc1, k), id64, k > 0); mma_commit_if(lead, is.mbar); }
             iss_acquire();   // C2 written
-            if (lead) { for (uint32_t k = 0; k < 4; k++) mma_f16(tmem, desc_kmajor(aT, k), desc_kmajor(aWc2, k), id16, k > 0); mma_commit(is.mbar); }
+            { for (uint32_t k = 0; k < 4; k++) mma_f16_if(lead, tmem, desc_kmajor(aT, k), desc_kmajor(aWc2, k), id16, k > 0); mma_commit_if(lead, is.mbar); }
             tile_end_sync();
         }
     } else {
@@ -615,6 +633,12 @@ struct BwdArgs {
 constexpr uint32_t kSetTiles = 6;
 enum : uint32_t { kTF = 0, kTH1 = 1, kTG = 2, kTC1 = 3, kTC2 = 4, kTX = 5 };
 
+#ifdef S3D_TRACE
+__device__ long long g_trace[1 << 15];
+#define S3D_TR(role, ev, it) do { if (blockIdx.x == 0 && (it) >= 2 && (it) < 8) { g_trace[(((it) - 2) * 3 + (role)) * 64 + (ev)] = clock64(); } } while (0)
+#else
+#define S3D_TR(role, ev, it) do { } while (0)
+#endif
 constexpr uint32_t kBwdThreads = 544;
 constexpr uint32_t kBwdIssuer = 16;
 
@@ -633,24 +657,24 @@ __device__ __forceinline__ void iss_acquire_n(uint32_t id) {
 __global__ void __launch_bounds__(kBwdThreads, 1)
 k_ngp_mlp_bwd(const BwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_mbar[2];
+    __shared__ __align__(8) uint64_t s_mbar[3];
     __shared__ uint32_t s_tmem;
     __shared__ float s_h0[2][kRows];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *tWs0 = smem + 2 * kSetTiles * kTileBytes, *tWc0 = tWs0 + kWTile, *tWc1 = tWc0 + kWTile, *tWs1 = tWc1 + kWTile, *tWc2 = tWs1 + kOTile;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, r = tid & 127, hf = (tid >> 7) & 1u;
-    const bool is_issuer = (warp == kBwdIssuer), is_fwd = tid < 256;
+    const uint32_t tid = threadIdx.x, warp = warp_idx_sync(), r = tid & 127, hf = (tid >> 7) & 1u;
+    const bool is_issuer = (warp == kBwdIssuer), is_fwd = warp < 8;
     if (is_issuer) tmem_alloc(smem_u32(&s_tmem), 512);
-    if (tid == 0) { mbar_init(smem_u32(&s_mbar[0]), 1); mbar_init(smem_u32(&s_mbar[1]), 1); }
+    if (tid == 0) { mbar_init(smem_u32(&s_mbar[0]), 1); mbar_init(smem_u32(&s_mbar[1]), 1); mbar_init(smem_u32(&s_mbar[2]), 1); }
     load_weights(tWs0, tWs1, tWc0, tWc1, tWc2, a.w);
     sync_tiles();
     const uint32_t tmem = s_tmem, t_row = tmem + (((warp & 3u) * 32u) << 16);
     const uint32_t n_my = blockIdx.x < a.n_tiles ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const uint32_t mbarF = smem_u32(&s_mbar[0]), mbarB = smem_u32(&s_mbar[1]);
+    const uint32_t mbarF = smem_u32(&s_mbar[0]), mbarB = smem_u32(&s_mbar[1]), mbarW = smem_u32(&s_mbar[2]);
     constexpr uint32_t kAccF = 448, kAccB = 0;
 
     if (is_issuer) {
-        const bool lead = (tid & 31) == 0;
+        const bool lead = elect_one();
         const uint32_t base = smem_u32(smem);
         const uint32_t aWs0 = smem_u32(tWs0), aWs1 = smem_u32(tWs1), aWc0 = smem_u32(tWc0), aWc1 = smem_u32(tWc1), aWc2 = smem_u32(tWc2);
         const uint32_t id64 = make_idesc(128, 64, false, false), id16 = make_idesc(128, 16, false, false);
@@ -664,64 +688,79 @@ k_ngp_mlp_bwd(const BwdArgs a) {
             const uint32_t sf = base + (it & 1u) * kSetTiles * kTileBytes, sb = base + ((it & 1u) ^ 1u) * kSetTiles * kTileBytes;
             const uint32_t fF = sf + kTF * kTileBytes, fH1 = sf + kTH1 * kTileBytes, fG = sf + kTG * kTileBytes, fC1 = sf + kTC1 * kTileBytes, fC2 = sf + kTC2 * kTileBytes;
             const uint32_t bF = sb + kTF * kTileBytes, bH1 = sb + kTH1 * kTileBytes, bG = sb + kTG * kTileBytes, bC1 = sb + kTC1 * kTileBytes, bC2 = sb + kTC2 * kTileBytes, bX = sb + kTX * kTileBytes;
-            iss_acquire_n(1);   // features stored
-            if (lead) { if (doF) for (uint32_t k = 0; k < 2; k++) mma_f16(accF, desc_kmajor(fF, k), desc_kmajor(aWs0, k), id64, k > 0); mma_commit(mbarF); }
-            iss_acquire_n(2);   // dO in X (published before the sets met):  dC2 = dO . Wc2 ;  dWc2 += dO^T . C2
-            if (lead) {
+            iss_acquire_n(1); S3D_TR(0, 0, it);   // features stored
+            { if (doF) for (uint32_t k = 0; k < 2; k++) mma_f16_if(lead, accF, desc_kmajor(fF, k), desc_kmajor(aWs0, k), id64, k > 0); mma_commit_if(lead, mbarF); S3D_TR(0, 1, it); }
+            iss_acquire_n(2); S3D_TR(0, 2, it);   // dO in X (published before the sets met):  dC2 = dO . Wc2 ;  dWc2 += dO^T . C2
+            {
               if (doB) {
-                mma_f16(accB, desc_kmajor(bX, 0), desc_mnmajor(aWc2, 0, kOTile), id64t, false);
-                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accC2, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bC2, k, kTileBytes), idw64, !(firstB && k == 0));
+                mma_f16_if(lead, accB, desc_kmajor(bX, 0), desc_mnmajor(aWc2, 0, kOTile), id64t, false);
               }
-              mma_commit(mbarB);
-            }
-            iss_acquire_n(1);   // H1 written
-            if (lead) { if (doF) for (uint32_t k = 0; k < 4; k++) mma_f16(accF, desc_kmajor(fH1, k), desc_kmajor(aWs1, k), id16, k > 0); mma_commit(mbarF); }
-            iss_acquire_n(2);   // dC2 in X:  dC1 = dC2 . Wc1 ;  dWc1 += dC2^T . C1
-            if (lead) {
+              mma_commit_if(lead, mbarB);
               if (doB) {
-                for (uint32_t k = 0; k < 4; k++) mma_f16(accB, desc_kmajor(bX, k), desc_mnmajor(aWc1, k, kWTile), id64t, k > 0);
-                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accC1, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bC1, k, kTileBytes), idw64, !(firstB && k == 0));
+                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16_if(lead, accC2, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bC2, k, kTileBytes), idw64, !(firstB && k == 0));
               }
-              mma_commit(mbarB);
+              mma_commit_if(lead, mbarW); S3D_TR(0, 3, it);
             }
-            iss_acquire_n(1);   // [SH | geo] written
-            if (lead) {
+            iss_acquire_n(1); S3D_TR(0, 4, it);   // H1 written
+            { if (doF) for (uint32_t k = 0; k < 4; k++) mma_f16_if(lead, accF, desc_kmajor(fH1, k), desc_kmajor(aWs1, k), id16, k > 0); mma_commit_if(lead, mbarF); S3D_TR(0, 5, it); }
+            iss_acquire_n(2); S3D_TR(0, 6, it);   // dC2 in X:  dC1 = dC2 . Wc1 ;  dWc1 += dC2^T . C1
+            {
+              if (doB) {
+                for (uint32_t k = 0; k < 4; k++) mma_f16_if(lead, accB, desc_kmajor(bX, k), desc_mnmajor(aWc1, k, kWTile), id64t, k > 0);
+              }
+              mma_commit_if(lead, mbarB);
+              if (doB) {
+                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16_if(lead, accC1, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bC1, k, kTileBytes), idw64, !(firstB && k == 0));
+              }
+              mma_commit_if(lead, mbarW); S3D_TR(0, 7, it);
+            }
+            iss_acquire_n(1); S3D_TR(0, 8, it);   // [SH | geo] written
+            {
                 if (doF) {
-                    for (uint32_t k = 0; k < 2; k++) mma_f16(accF, desc_kmajor(fF, 2 + k), desc_kmajor(aWc0, k), id64, k > 0);
-                    for (uint32_t k = 0; k < 2; k++) mma_f16(accF, desc_kmajor(fG, k), desc_kmajor(aWc0, 2 + k), id64, true);
+                    for (uint32_t k = 0; k < 2; k++) mma_f16_if(lead, accF, desc_kmajor(fF, 2 + k), desc_kmajor(aWc0, k), id64, k > 0);
+                    for (uint32_t k = 0; k < 2; k++) mma_f16_if(lead, accF, desc_kmajor(fG, k), desc_kmajor(aWc0, 2 + k), id64, true);
                 }
-                mma_commit(mbarF);
+                mma_commit_if(lead, mbarF); S3D_TR(0, 9, it);
             }
-            iss_acquire_n(2);   // dC1 in X:  d[colour feats | SH | geo] = dC1 . Wc0p ;  dWc0 += dC1^T . [F | G]
-            if (lead) {
+            iss_acquire_n(2); S3D_TR(0, 10, it);   // dC1 in X:  d[colour feats | SH | geo] = dC1 . Wc0p ;  dWc0 += dC1^T . [F | G]
+            {
               if (doB) {
-                for (uint32_t k = 0; k < 4; k++) mma_f16(accB, desc_kmajor(bX, k), desc_mnmajor(aWc0, k, kWTile), id64t, k > 0);
+                for (uint32_t k = 0; k < 4; k++) mma_f16_if(lead, accB, desc_kmajor(bX, k), desc_mnmajor(aWc0, k, kWTile), id64t, k > 0);
+              }
+              mma_commit_if(lead, mbarB);
+              if (doB) {
                 if (tw) {
-                    for (uint32_t k = 0; k < 8; k++) mma_f16(accC0f, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bF, k, kTileBytes), idw64, !(firstB && k == 0));
-                    for (uint32_t k = 0; k < 8; k++) mma_f16(accC0g, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bG, k, kTileBytes), idw64, !(firstB && k == 0));
+                    for (uint32_t k = 0; k < 8; k++) mma_f16_if(lead, accC0f, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bF, k, kTileBytes), idw64, !(firstB && k == 0));
+                    for (uint32_t k = 0; k < 8; k++) mma_f16_if(lead, accC0g, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bG, k, kTileBytes), idw64, !(firstB && k == 0));
                 }
               }
-              mma_commit(mbarB);
+              mma_commit_if(lead, mbarW); S3D_TR(0, 11, it);
             }
-            iss_acquire_n(1);   // C1 written
-            if (lead) { if (doF) for (uint32_t k = 0; k < 4; k++) mma_f16(accF, desc_kmajor(fC1, k), desc_kmajor(aWc1, k), id64, k > 0); mma_commit(mbarF); }
-            iss_acquire_n(2);   // dh2 in X:  dH1 = dh2 . Ws1 ;  dWs1 += dh2^T . H1
-            if (lead) {
+            iss_acquire_n(1); S3D_TR(0, 12, it);   // C1 written
+            { if (doF) for (uint32_t k = 0; k < 4; k++) mma_f16_if(lead, accF, desc_kmajor(fC1, k), desc_kmajor(aWc1, k), id64, k > 0); mma_commit_if(lead, mbarF); S3D_TR(0, 13, it); }
+            iss_acquire_n(2); S3D_TR(0, 14, it);   // dh2 in X:  dH1 = dh2 . Ws1 ;  dWs1 += dh2^T . H1
+            {
               if (doB) {
-                mma_f16(accB, desc_kmajor(bX, 0), desc_mnmajor(aWs1, 0, kOTile), id64t, false);
-                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accS1, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bH1, k, kTileBytes), idw64, !(firstB && k == 0));
+                mma_f16_if(lead, accB, desc_kmajor(bX, 0), desc_mnmajor(aWs1, 0, kOTile), id64t, false);
               }
-              mma_commit(mbarB);
+              mma_commit_if(lead, mbarB);
+              if (doB) {
+                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16_if(lead, accS1, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bH1, k, kTileBytes), idw64, !(firstB && k == 0));
+              }
+              mma_commit_if(lead, mbarW); S3D_TR(0, 15, it);
             }
-            iss_acquire_n(1);   // C2 written
-            if (lead) { if (doF) for (uint32_t k = 0; k < 4; k++) mma_f16(accF, desc_kmajor(fC2, k), desc_kmajor(aWc2, k), id16, k > 0); mma_commit(mbarF); }
-            iss_acquire_n(2);   // dH1 in X:  dF = dH1 . Ws0 ;  dWs0 += dH1^T . F
-            if (lead) {
+            iss_acquire_n(1); S3D_TR(0, 16, it);   // C2 written
+            { if (doF) for (uint32_t k = 0; k < 4; k++) mma_f16_if(lead, accF, desc_kmajor(fC2, k), desc_kmajor(aWc2, k), id16, k > 0); mma_commit_if(lead, mbarF); S3D_TR(0, 17, it); }
+            iss_acquire_n(2); S3D_TR(0, 18, it);   // dH1 in X:  dF = dH1 . Ws0 ;  dWs0 += dH1^T . F
+            {
               if (doB) {
-                for (uint32_t k = 0; k < 4; k++) mma_f16(accB, desc_kmajor(bX, k), desc_mnmajor(aWs0, k, kWTile), id64t, k > 0);
-                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16(accS0, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bF, k, kTileBytes), idw64, !(firstB && k == 0));
+                for (uint32_t k = 0; k < 4; k++) mma_f16_if(lead, accB, desc_kmajor(bX, k), desc_mnmajor(aWs0, k, kWTile), id64t, k > 0);
               }
-              mma_commit(mbarB);
+              mma_commit_if(lead, mbarB);
+              if (doB) {
+                if (tw) for (uint32_t k = 0; k < 8; k++) mma_f16_if(lead, accS0, desc_mnmajor(bX, k, kTileBytes), desc_mnmajor(bF, k, kTileBytes), idw64, !(firstB && k == 0));
+              }
+              mma_commit_if(lead, mbarW); S3D_TR(0, 19, it);
             }
         }
     } else if (is_fwd) {
@@ -753,11 +792,11 @@ k_ngp_mlp_bwd(const BwdArgs a) {
                 nf.store(fF, r, hf);
                 prefetch(tile_f + gridDim.x);
             }
-            set_publish(1);
-            isF.wait();
+            if (tid == 0) S3D_TR(1, 0, it); set_publish(1);
+            isF.wait(); if (tid == 0) S3D_TR(1, 1, it);
             if (doF) relu_to_tile(accF, hf, fH1, r);
-            set_publish(1);
-            isF.wait();
+            if (tid == 0) S3D_TR(1, 2, it); set_publish(1);
+            isF.wait(); if (tid == 0) S3D_TR(1, 3, it);
             if (doF) {
                 if (hf == 0) {
                     float h2[16], g[32];
@@ -772,14 +811,14 @@ k_ngp_mlp_bwd(const BwdArgs a) {
                     zero_half_row(fG, r, 1);
                 }
             }
-            set_publish(1);
-            isF.wait();
+            if (tid == 0) S3D_TR(1, 4, it); set_publish(1);
+            isF.wait(); if (tid == 0) S3D_TR(1, 5, it);
             if (doF) relu_to_tile(accF, hf, fC1, r);
-            set_publish(1);
-            isF.wait();
+            if (tid == 0) S3D_TR(1, 6, it); set_publish(1);
+            isF.wait(); if (tid == 0) S3D_TR(1, 7, it);
             if (doF) relu_to_tile(accF, hf, fC2, r);
-            set_publish(1);
-            isF.wait();
+            if (tid == 0) S3D_TR(1, 8, it); set_publish(1);
+            isF.wait(); if (tid == 0) S3D_TR(1, 9, it);
             if (doF) {
                 if (hf == 0) {   // output gradient dO (3 meaningful columns, zero padded)
                     float o[16], d[32];
@@ -800,12 +839,13 @@ k_ngp_mlp_bwd(const BwdArgs a) {
             }
             fence_async_smem();
             fence_before_sync();
+            if (tid == 0) S3D_TR(1, 20, it);
             bar_sync_n(3, 512);     // the sets meet: this set's tiles (and dO, h0) are complete, the other set is free
             fence_after_sync();
         }
     } else {
         // ================= backward of tile it - 1 (set (it - 1) & 1) =================
-        Issue isB{mbarB, 0};
+        Issue isB{mbarB, 0}, isW{mbarW, 0};
         const uint32_t accB = t_row + kAccB;
         for (uint32_t it = 0; it <= n_my; it++) {
             const bool doB = it > 0;
@@ -815,14 +855,14 @@ k_ngp_mlp_bwd(const BwdArgs a) {
             const bool in_b = doB && row_b < a.M;
             float gs_b = 0.f, h0_b = 0.f;
             if (in_b && hf == 0) { gs_b = a.g_sigma[row_b]; h0_b = s_h0[(it & 1u) ^ 1u][r]; }
-            set_publish(2);
-            isB.wait();
-            if (doB) masked_to_tile(accB, hf, bC2, bX, r);      // dC2
-            set_publish(2);
-            isB.wait();
-            if (doB) masked_to_tile(accB, hf, bC1, bX, r);      // dC1
-            set_publish(2);
-            isB.wait();
+            if (tid == 256) S3D_TR(2, 0, it); set_publish(2);
+            isB.wait(); if (tid == 256) S3D_TR(2, 1, it);
+            { uint4 pk[4]; if (doB) masked_half_row(accB, hf, bC2, r, pk); isW.wait(); if (doB) store_packed_half_row(bX, r, hf, pk); }      // dC2 (X is free once the weight-gradient MMAs of the round are done)
+            if (tid == 256) S3D_TR(2, 2, it); set_publish(2);
+            isB.wait(); if (tid == 256) S3D_TR(2, 3, it);
+            { uint4 pk[4]; if (doB) masked_half_row(accB, hf, bC1, r, pk); isW.wait(); if (doB) store_packed_half_row(bX, r, hf, pk); }      // dC1
+            if (tid == 256) S3D_TR(2, 4, it); set_publish(2);
+            isB.wait(); if (tid == 256) S3D_TR(2, 5, it);
             if (doB) {
                 if (hf == 1) {   // gradient w.r.t. the colour-grid features (dfeats cols 32..63)
                     float dfc[32];
@@ -834,6 +874,7 @@ k_ngp_mlp_bwd(const BwdArgs a) {
 #pragma unroll
                         for (uint32_t q = 0; q < 4; q++) dst[q] = pack8(dfc + q * 8);
                     }
+                    isW.wait();
                     zero_half_row(bX, r, 1);
                 } else {
                     float v[32], d[32];
@@ -843,14 +884,17 @@ k_ngp_mlp_bwd(const BwdArgs a) {
                     if (in_b) d[0] = gs_b * a.density_scale * __expf(fminf(fmaxf(h0_b, -15.0f), 15.0f));  // trunc_exp backward
 #pragma unroll
                     for (int i = 0; i < 15; i++) d[1 + i] = v[16 + i];
+                    isW.wait();
                     store_half_row(bX, r, 0, d);            // dh2
                 }
+            } else {
+                isW.wait();
             }
-            set_publish(2);
-            isB.wait();
-            if (doB) masked_to_tile(accB, hf, bH1, bX, r);      // dH1
-            set_publish(2);
-            isB.wait();
+            if (tid == 256) S3D_TR(2, 6, it); set_publish(2);
+            isB.wait(); if (tid == 256) S3D_TR(2, 7, it);
+            { uint4 pk[4]; if (doB) masked_half_row(accB, hf, bH1, r, pk); isW.wait(); if (doB) store_packed_half_row(bX, r, hf, pk); }      // dH1
+            if (tid == 256) S3D_TR(2, 8, it); set_publish(2);
+            isB.wait(); if (tid == 256) S3D_TR(2, 9, it);
             if (doB) {
                 if (hf == 0) {
                     float dfs[32];
@@ -864,9 +908,12 @@ k_ngp_mlp_bwd(const BwdArgs a) {
                     }
                 }
             }
+            isW.wait();   // the last weight-gradient MMAs still read this set's tiles
             fence_before_sync();
+            if (tid == 256) S3D_TR(2, 20, it);
             bar_sync_n(3, 512);
             fence_after_sync();
+            if (tid == 256) S3D_TR(2, 21, it);
         }
 
         // ---- flush weight gradients: accumulator rows (M = 64) live in lanes 0..15 of every 32-lane sub-partition;
@@ -1003,6 +1050,10 @@ S3D_API int s3d_ngp_mlp_forward(const void *feats, const float *dirs, uint32_t M
     k_ngp_mlp_fwd<<<grid, kMlpThreads, smem, as_stream(stream)>>>(a);
     S3D_RETURN_LAST();
 }
+
+#ifdef S3D_TRACE
+S3D_API int s3d_debug_trace(long long *host_out, int n) { return (int)cudaMemcpyFromSymbol(host_out, g_trace, (size_t)n * sizeof(long long)); }
+#endif
 
 S3D_API int s3d_ngp_mlp_backward(const void *feats, const float *dirs, uint32_t M, const void *w_s0, const void *w_s1, const void *w_c0,
                                  const void *w_c1, const void *w_c2, float density_scale, const float *g_sigma, const float *g_rgb,

@@ -60,6 +60,39 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64
         "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
         : "memory");
 }
+// warp index / elected lane in the form ptxas recognises as warp-uniform (what CUTLASS calls canonical_warp_idx_sync /
+// elect_one_sync): a role branch on `threadIdx.x >> 5` is divergent as far as the compiler can tell, and inside a divergent
+// region every tcgen05 operand is moved to a uniform register through an ELECT + R2UR loop (~25 instructions per MMA).
+__device__ __forceinline__ uint32_t warp_idx_sync() { return __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// Issue-predicated form for an issuer WARP: all 32 lanes run the surrounding code, which keeps the control flow warp-uniform
+// and therefore the descriptors / addresses in uniform registers (UTCHMMA takes its operands from URs; under a divergent
+// `if (lane == 0)` every operand costs a dependent R2UR, ~100 cycles per MMA measured); only the lane whose `issue` is true
+// executes the tcgen05 instruction itself.
+__device__ __forceinline__ void mma_f16_if(bool issue, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate), "r"((uint32_t)issue)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_if(bool issue, uint32_t mbar_addr) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}\n" ::"r"(mbar_addr), "r"((uint32_t)issue)
+        : "memory");
+}
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void mma_commit(uint32_t mbar_addr) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_addr) : "memory");

@@ -9,6 +9,8 @@ Adam moments and a flat fp32 arena for the MLP.  ``FusedDistillTrainer`` runs th
 gradient all-reduce per step for data-parallel runs.
 """
 import numpy as np
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -171,6 +173,12 @@ class FusedDistillTrainer:
         self.loss_buf = torch.zeros(2, dtype=torch.float32, device=self.S.dev)
         self.global_step = 0
         self.table8 = None
+        try:   # per-step buffers are sized by the sample budget, which moves a little at every occupancy refresh: let the
+            # caching allocator round large requests up (1/16 of a power of two) so refreshed sizes reuse cached blocks
+            if "roundup_power2_divisions" not in os.environ.get("PYTORCH_CUDA_ALLOC_CONF", ""):
+                torch.cuda.memory._set_allocator_settings("roundup_power2_divisions:16")
+        except Exception:
+            pass
         if self.T is not None and self.T.N == self.S.N and torch.equal(self.T.offsets, self.S.offsets):
             # teacher and student share the level geometry: pair their fp16 tables so one 128-bit load serves both
             self.table8 = torch.empty(self.S.N, 8, dtype=torch.float16, device=self.S.dev)
