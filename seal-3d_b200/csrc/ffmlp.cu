@@ -101,7 +101,7 @@ k_ffmlp_forward(const FwdParams p) {
     uint8_t *tWh = tW0 + in_blocks * kWTileBytes;
     uint8_t *tWo = tWh + (p.num_layers - 1) * kWTileBytes;
 
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, warp = warp_idx_sync();   // warp-uniform for the compiler (see tc05.cuh)
     const uint32_t mbar = smem_u32(&s_mbar);
     if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 64);
     if (tid == 0) mbar_init(mbar, 1);
@@ -129,21 +129,22 @@ k_ffmlp_forward(const FwdParams p) {
     const uint32_t n_mm = p.num_layers + 1;
     for (uint32_t l = 0; l < n_mm; l++) {
         const bool last = (l == n_mm - 1);
-        if (tid == 0) {
+        if (warp == 0) {
+            const bool lead = elect_one();
             const uint32_t idesc = make_idesc(128, last ? 16 : 64, false, false);
             if (l == 0) {
                 const uint32_t ksteps = (p.in_dim + 15) / 16;
                 for (uint32_t k = 0; k < ksteps; k++) {
                     const uint32_t blk = k >> 2, kk = k & 3;
-                    mma_f16(tmem, desc_kmajor(smem_u32(tA + blk * kTileBytes), kk), desc_kmajor(smem_u32(tW0 + blk * kWTileBytes), kk), idesc, k > 0);
+                    mma_f16_if(lead, tmem, desc_kmajor(smem_u32(tA + blk * kTileBytes), kk), desc_kmajor(smem_u32(tW0 + blk * kWTileBytes), kk), idesc, k > 0);
                 }
             } else {
                 const uint8_t *wt = last ? tWo : (tWh + (l - 1) * kWTileBytes);
                 const uint32_t ksteps = (p.hidden + 15) / 16;
                 for (uint32_t k = 0; k < ksteps; k++)
-                    mma_f16(tmem, desc_kmajor(smem_u32(tA), k), desc_kmajor(smem_u32(wt), k), idesc, k > 0);
+                    mma_f16_if(lead, tmem, desc_kmajor(smem_u32(tA), k), desc_kmajor(smem_u32(wt), k), idesc, k > 0);
             }
-            mma_commit(mbar);
+            mma_commit_if(lead, mbar);
         }
         mbar_wait(mbar, parity);
         parity ^= 1;
@@ -212,7 +213,7 @@ k_ffmlp_backward(const BwdParams p) {
     uint8_t *tWh = tW0 + in_blocks * kWTileBytes;
     uint8_t *tWo = tWh + n_hid * kWTileBytes;
 
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, warp = warp_idx_sync();   // warp-uniform for the compiler (see tc05.cuh)
     const uint32_t mbar = smem_u32(&s_mbar);
     const uint32_t n_acc = 1 + n_hid + in_blocks;              // weight-gradient accumulators
     uint32_t ncols = 64 * (1 + n_acc), alloc = 32;
@@ -259,28 +260,29 @@ k_ffmlp_backward(const BwdParams p) {
         // layer loop: s = 0 handles W_out, s = 1..n_hid the hidden matrices (top down), s = n_hid+1 the input layer
         for (uint32_t s = 0; s <= n_hid + 1; s++) {
             const bool is_out = (s == 0), is_in = (s == n_hid + 1);
-            if (tid == 0) {
+            if (warp == 0) {
+                const bool lead = elect_one();
                 // (1) weight gradient of this matrix: dW += dA^T . H     (K = 128 batch rows, 8 MMAs of 16 rows)
                 const uint32_t nblk = is_in ? in_blocks : 1;
                 for (uint32_t blk = 0; blk < nblk; blk++) {
                     const uint32_t acc = is_out ? acc_out : (is_in ? acc_in + 64 * blk : acc_hid + 64 * (n_hid - s));
                     for (uint32_t k = 0; k < kRows / 16; k++)
-                        mma_f16(acc, desc_mnmajor(smem_u32(tD), k, kTileBytes), desc_mnmajor(smem_u32(tH + blk * kTileBytes), k, kTileBytes),
+                        mma_f16_if(lead, acc, desc_mnmajor(smem_u32(tD), k, kTileBytes), desc_mnmajor(smem_u32(tH + blk * kTileBytes), k, kTileBytes),
                                 idesc_wg, !(first_tile && k == 0));
                 }
                 // (2) data gradient through this matrix: D = dA . W     (W tile read MN-major = W^T)
                 if (is_out) {
-                    mma_f16(tmem, desc_kmajor(smem_u32(tD), 0), desc_mnmajor(smem_u32(tWo), 0, kOTileBytes), make_idesc(128, 64, false, true), false);
+                    mma_f16_if(lead, tmem, desc_kmajor(smem_u32(tD), 0), desc_mnmajor(smem_u32(tWo), 0, kOTileBytes), make_idesc(128, 64, false, true), false);
                 } else if (!is_in) {
                     const uint8_t *wt = tWh + (n_hid - s) * kWTileBytes;
                     for (uint32_t k = 0; k < (p.hidden + 15) / 16; k++)
-                        mma_f16(tmem, desc_kmajor(smem_u32(tD), k), desc_mnmajor(smem_u32(wt), k, kWTileBytes), make_idesc(128, 64, false, true), k > 0);
+                        mma_f16_if(lead, tmem, desc_kmajor(smem_u32(tD), k), desc_mnmajor(smem_u32(wt), k, kWTileBytes), make_idesc(128, 64, false, true), k > 0);
                 } else if (p.grad_inputs) {
                     // grad_inputs block by block reuses the accumulator; handled below one block at a time
                     for (uint32_t k = 0; k < (p.hidden + 15) / 16; k++)
-                        mma_f16(tmem, desc_kmajor(smem_u32(tD), k), desc_mnmajor(smem_u32(tW0), k, kWTileBytes), make_idesc(128, 64, false, true), k > 0);
+                        mma_f16_if(lead, tmem, desc_kmajor(smem_u32(tD), k), desc_mnmajor(smem_u32(tW0), k, kWTileBytes), make_idesc(128, 64, false, true), k > 0);
                 }
-                mma_commit(mbar);
+                mma_commit_if(lead, mbar);
             }
             mbar_wait(mbar, parity);
             parity ^= 1;
@@ -318,10 +320,11 @@ k_ffmlp_backward(const BwdParams p) {
                         fence_before_sync();
                         __syncthreads();
                         fence_after_sync();
-                        if (tid == 0) {
+                        if (warp == 0) {
+                            const bool lead = elect_one();
                             for (uint32_t k = 0; k < (p.hidden + 15) / 16; k++)
-                                mma_f16(tmem, desc_kmajor(smem_u32(tD), k), desc_mnmajor(smem_u32(tW0 + blk * kWTileBytes), k, kWTileBytes), make_idesc(128, 64, false, true), k > 0);
-                            mma_commit(mbar);
+                                mma_f16_if(lead, tmem, desc_kmajor(smem_u32(tD), k), desc_mnmajor(smem_u32(tW0 + blk * kWTileBytes), k, kWTileBytes), make_idesc(128, 64, false, true), k > 0);
+                            mma_commit_if(lead, mbar);
                         }
                         mbar_wait(mbar, parity);
                         parity ^= 1;
