@@ -176,7 +176,8 @@ class FusedDistillTrainer:
         try:   # per-step buffers are sized by the sample budget, which moves a little at every occupancy refresh: let the
             # caching allocator round large requests up (1/16 of a power of two) so refreshed sizes reuse cached blocks
             if "roundup_power2_divisions" not in os.environ.get("PYTORCH_CUDA_ALLOC_CONF", ""):
-                torch.cuda.memory._set_allocator_settings("roundup_power2_divisions:16")
+                setter = getattr(torch._C, "_accelerator_setAllocatorSettings", None) or torch.cuda.memory._set_allocator_settings
+                setter("roundup_power2_divisions:16")
         except Exception:
             pass
         if self.T is not None and self.T.N == self.S.N and torch.equal(self.T.offsets, self.S.offsets):
