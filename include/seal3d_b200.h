@@ -140,6 +140,26 @@ int s3d_seal_bbox_map_to_origin(const float *points, const float *dirs, uint32_t
  * batch mean of V), in place on rows with mask != 0; d_stats = device float[2] scratch */
 int s3d_seal_map_color(float *rgbs, const uint8_t *mask, uint32_t M, const float *h_hsv_mod, const float *h_rgb_target,
                        float light_offset, float *d_stats, void *stream);
+/* SURVEY 8f-4.  SealBrushMapper.map_to_origin (seal_utils.py:408-453; map_mask :132-153 with the brush's own test
+ * direction): inside samples move by -normal_expand, plus |att - d| / att * normal_expand where the projected sample is
+ * closer than `attenuation_distance` to the nearest border point.  mode 0 = 'linear', 1 = 'dry'.  h_* host float[3],
+ * d_* device arrays (bounds [nb,2,3], tris [F,3,3], border points [K,3]). */
+int s3d_seal_brush_map_to_origin(const float *points, uint32_t P, const float *d_bounds, uint32_t nb, const float *d_tris, uint32_t F,
+                                 const float *h_test_dir, const float *h_normal_expand, const float *h_center,
+                                 const float *d_border_points, uint32_t K, float attenuation_distance, int mode,
+                                 float *out_points, uint8_t *mask, void *stream);
+/* SealAnchorMapper.map_to_origin (seal_utils.py:514-570): cone / plane-side test around the anchor, pull along v_h,
+ * per-axis scale about the anchor.  Like the reference, the map-region mask only gates an early exit: once any sample
+ * is inside, every sample takes the cone test and `mask` is the cone mask.  d_flag: device int scratch. */
+int s3d_seal_anchor_map_to_origin(const float *points, uint32_t P, const float *d_bounds, uint32_t nb, const float *d_tris, uint32_t F,
+                                  const float *h_test_dir, const float *h_v_anchor, const float *h_v_offset, const float *h_v_h,
+                                  float len_h, float radius, const float *h_scale, int *d_flag, float *out_points, uint8_t *mask,
+                                  void *stream);
+/* texture branch of SealMapper.map_color (seal_utils.py:58-79): target colour = image[pixel of the sample projected on
+ * the image plane], V re-lit around the batch mean like modify_rgb, blended with image_mask[pixel]. */
+int s3d_seal_map_color_image(float *rgbs, const float *points, const uint8_t *mask, uint32_t M, const float *d_image,
+                             const float *d_alpha, uint32_t H, uint32_t W, const float *h_norm, const float *h_o, const float *h_w,
+                             const float *h_h, float light_offset, float *d_stats, void *stream);
 /* SealNeRF/renderer.py:21-66 init_mapper + hack_bitfield: cells [h_cell_lo, h_cell_hi) -> bitfield bytes = 255 */
 int s3d_seal_force_fill_bitfield(uint8_t *bitfield, const int *h_cell_lo, const int *h_cell_hi, uint32_t H,
                                  uint32_t cascade_index, void *stream);
@@ -157,7 +177,20 @@ int s3d_finetune_loss(const float *comp_s, const float *ws_s, const float *depth
  * (or NULL) and zeroes the gradient when asked.  grad_dtype 0 = f32, 1 = f16. */
 int s3d_adam_step(float *params, void *grads, float *exp_avg, float *exp_avg_sq, void *shadow_f16, uint64_t n, float lr,
                   float beta1, float beta2, float eps, uint32_t step, float grad_scale, int zero_grad, int grad_dtype,
-                  void *stream);
+                  const float *scaler_state, void *stream);
+/* torch.cuda.amp.GradScaler as the reference trainer drives it (nerf/utils.py:361,857-859: scale(loss).backward(),
+ * step(optimizer), update()), kept ON THE DEVICE so a step never waits for the host:
+ *   scaler_state = float[8]: [0] loss scale  [1] growth tracker  [2] found_inf  [3] optimizer steps applied
+ *                            [4] 1/(1-beta1^t)  [5] 1/sqrt(1-beta2^t)   (t = [3], refreshed by _check)
+ * s3d_grad_scaler_check scans the (all-reduced) gradient arena for non-finite values, sets found_inf and, when the
+ * step will be applied, advances [3] and the bias corrections.  The Adam entry points, given scaler_state, divide the
+ * gradient by [0], use [4],[5] instead of the host `step`, and when found_inf is set only clear the gradient (the
+ * skipped step of GradScaler.step).  s3d_grad_scaler_update = GradScaler.update(): backoff on overflow, growth after
+ * growth_interval clean steps, found_inf reset.  scaler_state NULL = static scale through grad_scale (as before). */
+int s3d_grad_scaler_check(const float *grads, uint64_t n, float *scaler_state, float beta1, float beta2, void *stream);
+int s3d_grad_scaler_update(float *scaler_state, float growth_factor, float backoff_factor, uint32_t growth_interval, void *stream);
+/* torch_ema.ExponentialMovingAverage.update (nerf/utils.py:356-357,882-883): shadow -= (1 - decay) * (shadow - param) */
+int s3d_ema_update(float *shadow, const float *params, uint64_t n, float decay, void *stream);
 int s3d_cast_f32_to_f16(const float *src, void *dst, uint64_t n, void *stream);
 /* nerf/renderer.py:445-538 update_extra_state pieces */
 int s3d_density_cells_to_xyz(const int *cell_morton, uint32_t n, uint32_t H, float bound_cas, uint32_t seed, float *xyz,
@@ -191,7 +224,7 @@ int s3d_ngp_scatter(const float *xyz, const void *dfeats, uint32_t M, float boun
                     uint32_t H, float grad_scale, void *stream);
 int s3d_ngp_adam_tables(float *table_sigma, float *table_color, float *grad4, float *exp_avg4, float *exp_avg_sq4, void *shadow,
                         uint32_t shadow_stride, uint64_t n_entries, float lr, float beta1, float beta2, float eps, uint32_t step,
-                        float grad_scale, void *stream);
+                        float grad_scale, const float *scaler_state, void *stream);
 
 #ifdef __cplusplus
 }

@@ -443,3 +443,83 @@ def finetune_loss(image_s, depth_s, image_t, depth_t):
     dd = depth_s - depth_t
     loss = (dr ** 2).mean(-1).mean() + np.abs(dd).mean()
     return loss, 2 * dr / (3 * N), np.sign(dd) / N
+
+
+# ---------------------------------------------------------------------------- optimizer-side state
+class Optimizer:
+    """The reference's optimisation step restated in numpy float64 -> float32 (test infrastructure):
+      * torch.optim.Adam(betas=(0.9, 0.99), eps=1e-15)                     main_SealNeRF.py:283-284
+      * LambdaLR  lr_t = lr * 0.1 ** min(t / iters, 1), stepped every step  main_SealNeRF.py:287-288, nerf/utils.py:861-862
+      * torch.cuda.amp.GradScaler: scale(loss), step skipped on non-finite gradients, update (growth / backoff)
+                                                                            nerf/utils.py:361, 857-859
+      * torch_ema.ExponentialMovingAverage(decay=0.95).update()             nerf/utils.py:356-357, 882-883
+    torch and torch_ema are third-party (not in the reference tree); Adam / GradScaler / LambdaLR are pinned in
+    tests/test_gpu_fused.py against the installed torch itself, the EMA rule is torch_ema's published one (parity unpinned)."""
+
+    def __init__(self, params, lr, iters=None, init_scale=65536.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000,
+                 beta1=0.9, beta2=0.99, eps=1e-15, ema_decay=None):
+        self.p = np.array(params, dtype=np.float64)
+        self.m, self.v = np.zeros_like(self.p), np.zeros_like(self.p)
+        self.lr, self.iters, self.b1, self.b2, self.eps = lr, iters, beta1, beta2, eps
+        self.scale, self.growth, self.backoff, self.interval, self.tracker = float(init_scale), growth_factor, backoff_factor, growth_interval, 0
+        self.t_sched, self.t_opt = 0, 0
+        self.ema_decay, self.ema_n = ema_decay, 0
+        self.shadow = self.p.copy() if ema_decay is not None else None
+
+    def step(self, scaled_grad):
+        g = np.asarray(scaled_grad, dtype=np.float64)
+        lr_t = self.lr * (0.1 ** min(self.t_sched / float(self.iters), 1.0) if self.iters else 1.0)
+        found_inf = not np.isfinite(g).all()
+        if not found_inf:
+            g = g / self.scale
+            self.t_opt += 1
+            self.m = self.b1 * self.m + (1 - self.b1) * g
+            self.v = self.b2 * self.v + (1 - self.b2) * g * g
+            bc1, bc2 = 1 - self.b1 ** self.t_opt, 1 - self.b2 ** self.t_opt
+            self.p = self.p - (lr_t / bc1) * self.m / (np.sqrt(self.v) / np.sqrt(bc2) + self.eps)
+            self.tracker += 1
+            if self.tracker == self.interval:
+                self.scale *= self.growth
+                self.tracker = 0
+        else:
+            self.scale *= self.backoff
+            self.tracker = 0
+        self.t_sched += 1
+        return found_inf
+
+    def ema_update(self):
+        self.ema_n += 1
+        d = min(self.ema_decay, (1.0 + self.ema_n) / (10.0 + self.ema_n))
+        self.shadow = self.shadow - (1.0 - d) * (self.shadow - self.p)
+
+
+# ---------------------------------------------------------------------------- SURVEY 8f-4: brush / anchor / texture colour
+def seal_brush_map_to_origin(points, bounds, tris, normal_expand, center, border_points, attenuation_distance, mode="linear",
+                             test_dir=None):
+    """SealBrushMapper.map_to_origin (seal_utils.py:408-453); returns (points', mask)"""
+    points, bounds, tris, border = _f32(points), _f32(bounds).reshape(-1, 2, 3), _f32(tris), _f32(border_points).reshape(-1, 3)
+    out, mask = np.empty_like(points), np.empty(points.shape[0], dtype=np.uint8)
+    lib().orc_seal_brush_map_to_origin(_p(points), i64(points.shape[0]), _p(bounds), u32(bounds.shape[0]), _p(tris), u32(tris.shape[0]),
+                                       _p(_f32(test_dir)) if test_dir is not None else None, _p(_f32(normal_expand)), _p(_f32(center)),
+                                       _p(border), u32(border.shape[0]), f32(attenuation_distance), cint(0 if mode == "linear" else 1),
+                                       _p(out), _p(mask))
+    return out, mask.astype(bool)
+
+
+def seal_anchor_map_to_origin(points, bounds, tris, v_anchor, v_offset, v_h, len_h, radius, scale, test_dir=None):
+    """SealAnchorMapper.map_to_origin (seal_utils.py:514-570); returns (points', valid_mask)"""
+    points, bounds, tris = _f32(points), _f32(bounds).reshape(-1, 2, 3), _f32(tris)
+    out, mask = np.empty_like(points), np.empty(points.shape[0], dtype=np.uint8)
+    lib().orc_seal_anchor_map_to_origin(_p(points), i64(points.shape[0]), _p(bounds), u32(bounds.shape[0]), _p(tris), u32(tris.shape[0]),
+                                        _p(_f32(test_dir)) if test_dir is not None else None, _p(_f32(v_anchor)), _p(_f32(v_offset)),
+                                        _p(_f32(v_h)), f32(len_h), f32(radius), _p(_f32(scale)), _p(out), _p(mask))
+    return out, mask.astype(bool)
+
+
+def seal_map_color_image(points, rgb, image, image_mask, v_norm, v_o, v_w, v_h, light_offset=0.0):
+    """texture branch of SealMapper.map_color (seal_utils.py:58-79)"""
+    points, rgb, image, image_mask = _f32(points), _f32(rgb), _f32(image), _f32(image_mask)
+    out = np.empty_like(rgb)
+    lib().orc_seal_map_color_image(_p(points), _p(rgb), i64(rgb.shape[0]), _p(image), _p(image_mask), u32(image.shape[0]), u32(image.shape[1]),
+                                   _p(_f32(v_norm)), _p(_f32(v_o)), _p(_f32(v_w)), _p(_f32(v_h)), f32(light_offset), _p(out))
+    return out

@@ -968,3 +968,113 @@ ORC_API void orc_seal_modify_rgb(const float *rgb, int64_t P, const float *targe
     }
     free(vs);
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Brush / Anchor mappers and the texture colour map
+ * ------------------------------------------------------------------------------------------------------------- */
+/* seal_utils.py:728-736 project_points */
+static void project_point(const float *n, const float *o, const float *p, float *out) {
+    const float v[3] = {p[0] - o[0], p[1] - o[1], p[2] - o[2]};
+    const float s = (v[0] * n[0] + v[1] * n[1] + v[2] * n[2]) / (n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    out[0] = p[0] - s * n[0]; out[1] = p[1] - s * n[1]; out[2] = p[2] - s * n[2];
+}
+
+/* seal_utils.py:408-453 SealBrushMapper.map_to_origin.  mode 0 = 'linear', 1 = 'dry' (no space mapping).
+ * border [K,3]; distance = min_k ||proj - border_k|| (torch.cdist(...).min(1)), evaluated directly. */
+ORC_API void orc_seal_brush_map_to_origin(const float *points, int64_t P, const float *bounds, uint32_t nb, const float *tris,
+                                          uint32_t F, const float *test_dir, const float *normal_expand, const float *center,
+                                          const float *border, uint32_t K, float att_dist, int mode, float *out_points,
+                                          uint8_t *mask) {
+    orc_seal_map_mask(points, P, bounds, nb, tris, F, test_dir, mask);
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < P; p++) {
+        const float *x = points + p * 3;
+        float *ox = out_points + p * 3;
+        ox[0] = x[0]; ox[1] = x[1]; ox[2] = x[2];
+        if (!mask[p] || mode == 1) continue;
+        float pr[3];
+        project_point(normal_expand, center, x, pr);
+        float best = INFINITY;
+        for (uint32_t k = 0; k < K; k++) {
+            const float *b = border + k * 3;
+            const float dx = pr[0] - b[0], dy = pr[1] - b[1], dz = pr[2] - b[2];
+            const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+            if (d < best) best = d;
+        }
+        for (int i = 0; i < 3; i++) ox[i] = x[i] - normal_expand[i];
+        if (att_dist > best) {
+            const float c = fabsf(att_dist - best) / att_dist;
+            for (int i = 0; i < 3; i++) ox[i] += c * normal_expand[i];
+        }
+    }
+}
+
+/* seal_utils.py:514-570 SealAnchorMapper.map_to_origin.  Reference quirk kept: map_mask only gates the early exit
+ * (`if not map_mask.any(): return`); once any sample is inside the map region the cone test runs on ALL samples and
+ * the returned mask is the cone mask, not ANDed with map_mask. */
+ORC_API void orc_seal_anchor_map_to_origin(const float *points, int64_t P, const float *bounds, uint32_t nb, const float *tris,
+                                           uint32_t F, const float *test_dir, const float *v_anchor, const float *v_offset,
+                                           const float *v_h, float len_h, float radius, const float *scale, float *out_points,
+                                           uint8_t *mask) {
+    orc_seal_map_mask(points, P, bounds, nb, tris, F, test_dir, mask);
+    int any = 0;
+    for (int64_t p = 0; p < P; p++) any |= mask[p];
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < P; p++) {
+        const float *x = points + p * 3;
+        float *ox = out_points + p * 3;
+        ox[0] = x[0]; ox[1] = x[1]; ox[2] = x[2];
+        if (!any) { mask[p] = 0; continue; }
+        float pr[3];
+        project_point(v_h, v_anchor, x, pr);
+        const float vp[3] = {pr[0] - x[0], pr[1] - x[1], pr[2] - x[2]};
+        const float dist = sqrtf(vp[0] * vp[0] + vp[1] * vp[1] + vp[2] * vp[2]);
+        const float os = dist / len_h;
+        const float po[3] = {pr[0] - os * v_offset[0], pr[1] - os * v_offset[1], pr[2] - os * v_offset[2]};
+        const float q[3] = {po[0] - v_anchor[0], po[1] - v_anchor[1], po[2] - v_anchor[2]};
+        const float pad = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+        const int cone = (pad <= radius) && (dist / (radius - pad) < len_h / radius * 1.1f);
+        const int side = (vp[0] * v_h[0] + vp[1] * v_h[1] + vp[2] * v_h[2]) > 0.0f;
+        const int valid = cone && side;
+        mask[p] = (uint8_t)valid;
+        if (!valid) continue;
+        const float f = -((len_h - dist) / 10.0f);
+        for (int i = 0; i < 3; i++) {
+            const float vm = f * v_h[i] / len_h;
+            const float mp = po[i] - vm;
+            ox[i] = (mp - v_anchor[i]) * scale[i] + v_anchor[i];
+        }
+    }
+}
+
+/* seal_utils.py:58-79 texture branch of SealMapper.map_color: pixel = floor(<proj - o, w - o> / |w - o|^2 * W) clamped,
+ * colour = modify_rgb(colors, image[pixel]) (per-sample target; V re-lit around the mean V of the batch),
+ * blended with image_mask[pixel].  image [H,W,3], image_mask [H,W]. */
+ORC_API void orc_seal_map_color_image(const float *points, const float *rgb, int64_t P, const float *image, const float *image_mask,
+                                      uint32_t H, uint32_t W, const float *v_norm, const float *v_o, const float *v_w,
+                                      const float *v_hh, float light_offset, float *out) {
+    if (P == 0) return;
+    const float ow[3] = {v_w[0] - v_o[0], v_w[1] - v_o[1], v_w[2] - v_o[2]};
+    const float oh[3] = {v_hh[0] - v_o[0], v_hh[1] - v_o[1], v_hh[2] - v_o[2]};
+    const float low = sqrtf(ow[0] * ow[0] + ow[1] * ow[1] + ow[2] * ow[2]), loh = sqrtf(oh[0] * oh[0] + oh[1] * oh[1] + oh[2] * oh[2]);
+    double sum = 0;
+    for (int64_t p = 0; p < P; p++) { float hsv[3]; rgb2hsv(rgb + p * 3, hsv); sum += hsv[2]; }
+    const float mean = (float)(sum / (double)P);
+    for (int64_t p = 0; p < P; p++) {
+        float pr[3];
+        project_point(v_norm, v_o, points + p * 3, pr);
+        const float op[3] = {pr[0] - v_o[0], pr[1] - v_o[1], pr[2] - v_o[2]};
+        float fw = floorf((op[0] * ow[0] + op[1] * ow[1] + op[2] * ow[2]) / (low * low) * (float)W);
+        float fh = floorf((op[0] * oh[0] + op[1] * oh[1] + op[2] * oh[2]) / (loh * loh) * (float)H);
+        fw = fminf(fmaxf(0.0f, fw), (float)(W - 1));
+        fh = fminf(fmaxf(0.0f, fh), (float)(H - 1));
+        const size_t pix = (size_t)fh * W + (size_t)fw;
+        float hsv[3], thsv[3], mod[3];
+        rgb2hsv(rgb + p * 3, hsv);
+        rgb2hsv(image + pix * 3, thsv);
+        const float nh[3] = {thsv[0], thsv[1], fminf(1.0f, fmaxf(0.0f, thsv[2] + (hsv[2] - mean) + light_offset))};
+        hsv2rgb(nh, mod);
+        const float a = image_mask[pix];
+        for (int i = 0; i < 3; i++) out[p * 3 + i] = a * mod[i] + (1.0f - a) * rgb[p * 3 + i];
+    }
+}

@@ -956,9 +956,17 @@ __global__ void k_interleave_tables(const float2 *__restrict__ ts, const float2 
 // Adam over the two hash tables with an interleaved gradient / shadow layout
 __global__ void __launch_bounds__(256)
 k_adam_tables(float2 *__restrict__ ps, float2 *__restrict__ pc, float4 *__restrict__ g4, float4 *__restrict__ m4, float4 *__restrict__ v4,
-              uint8_t *__restrict__ shadow, uint32_t shadow_stride, size_t n, float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps, float gscale) {
+              uint8_t *__restrict__ shadow, uint32_t shadow_stride, size_t n, float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps, float gscale,
+              const float *__restrict__ scaler, float lr) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    bool skip = false;
+    if (scaler) {   // device-side GradScaler state (csrc/train.cu): scale, skip decision, bias corrections of the applied-step count
+        skip = scaler[2] != 0.0f;
+        gscale = gscale / scaler[0];
+        lr_over_bc1 = lr * scaler[4];
+        inv_sqrt_bc2 = scaler[5];
+    }
     const float4 g = g4[i];
     float4 m = m4[i];
     const bool gz = (g.x == 0.0f) & (g.y == 0.0f) & (g.z == 0.0f) & (g.w == 0.0f);
@@ -968,6 +976,7 @@ k_adam_tables(float2 *__restrict__ ps, float2 *__restrict__ pc, float4 *__restri
     // touched once keep decaying their moments and moving, like torch.optim.Adam.
     if (gz && mz) return;
     if (!gz) g4[i] = make_float4(0, 0, 0, 0);
+    if (skip) return;   // non-finite gradient somewhere: no update, gradient cleared
     float4 v = v4[i];
     float2 s = ps[i], c = pc[i];
     const float *G = &g.x;
@@ -1085,11 +1094,11 @@ S3D_API int s3d_ngp_interleave_tables(const float *table_sigma, const float *tab
 // (8 = table4, 16 = the student half of a paired table8) in the same pass; the gradient is zeroed.
 S3D_API int s3d_ngp_adam_tables(float *table_sigma, float *table_color, float *grad4, float *exp_avg4, float *exp_avg_sq4, void *shadow,
                                 uint32_t shadow_stride, uint64_t n_entries, float lr, float beta1, float beta2, float eps, uint32_t step,
-                                float grad_scale, void *stream) {
+                                float grad_scale, const float *scaler_state, void *stream) {
     if (n_entries == 0) return 0;
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     k_adam_tables<<<(unsigned)div_up((size_t)n_entries, (size_t)256), 256, 0, as_stream(stream)>>>(
         (float2 *)table_sigma, (float2 *)table_color, (float4 *)grad4, (float4 *)exp_avg4, (float4 *)exp_avg_sq4, (uint8_t *)shadow, shadow_stride, (size_t)n_entries,
-        (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps, grad_scale);
+        (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps, grad_scale, scaler_state, lr);
     S3D_RETURN_LAST();
 }

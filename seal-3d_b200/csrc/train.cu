@@ -67,9 +67,25 @@ __global__ void k_finetune_loss(const float *__restrict__ comp_s, const float *_
 template <typename G>
 __global__ void __launch_bounds__(256)
 k_adam(float *__restrict__ p, G *__restrict__ g, float *__restrict__ m, float *__restrict__ v, __half *__restrict__ shadow,
-       size_t n, float lr_over_bc1, float inv_sqrt_bc2, float beta1, float beta2, float eps, float grad_scale, int zero_grad) {
+       size_t n, float lr_over_bc1, float inv_sqrt_bc2, float beta1, float beta2, float eps, float grad_scale, int zero_grad,
+       const float *__restrict__ scaler, float lr) {
+    bool skip = false;
+    if (scaler) {   // GradScaler semantics (see s3d_grad_scaler_check): device-side scale, skip decision and bias corrections
+        skip = scaler[2] != 0.0f;
+        grad_scale = grad_scale / scaler[0];
+        lr_over_bc1 = lr * scaler[4];
+        inv_sqrt_bc2 = scaler[5];
+    }
     const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i0 >= n) return;
+    if (skip) {   // a non-finite gradient somewhere in the arena: the optimizer step is skipped, the gradient is still cleared
+        if (zero_grad)
+            for (size_t i = i0; i < n && i < i0 + 4; i++) {
+                if constexpr (sizeof(G) == 4) reinterpret_cast<float *>(g)[i] = 0.0f;
+                else reinterpret_cast<__half *>(g)[i] = __float2half_rn(0.0f);
+            }
+        return;
+    }
     const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                            reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(shadow) & 7) == 0;
     if (i0 + 4 <= n && sizeof(G) == 4 && aligned) {
@@ -107,6 +123,48 @@ k_adam(float *__restrict__ p, G *__restrict__ g, float *__restrict__ m, float *_
                 else reinterpret_cast<__half *>(g)[i] = __float2half_rn(0.0f);
             }
         }
+    }
+}
+
+// ---- GradScaler state on the device (torch.cuda.amp.GradScaler semantics, nerf/utils.py:857-859) ----------------
+// state[0] scale | [1] growth tracker | [2] found_inf | [3] optimizer steps applied so far | [4] 1/(1-beta1^t) | [5] 1/sqrt(1-beta2^t)
+__global__ void __launch_bounds__(256)
+k_found_inf(const float *__restrict__ g, size_t n, float *__restrict__ state) {
+    bool bad = false;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (size_t)gridDim.x * blockDim.x * 4) {
+        if (i + 4 <= n && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+            const float4 v = *reinterpret_cast<const float4 *>(g + i);
+            bad |= !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w));
+        } else {
+            for (size_t j = i; j < n && j < i + 4; j++) bad |= !isfinite(g[j]);
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) state[2] = 1.0f;
+}
+__global__ void k_scaler_prepare(float *__restrict__ state, float beta1, float beta2) {
+    if (state[2] == 0.0f) {   // the step will be applied: advance the optimizer's step count, refresh the bias corrections
+        const float t = state[3] + 1.0f;
+        state[3] = t;
+        state[4] = (float)(1.0 / (1.0 - pow((double)beta1, (double)t)));
+        state[5] = (float)(1.0 / sqrt(1.0 - pow((double)beta2, (double)t)));
+    }
+}
+__global__ void k_scaler_update(float *__restrict__ state, float growth, float backoff, float interval) {
+    if (state[2] != 0.0f) { state[0] *= backoff; state[1] = 0.0f; }
+    else {
+        const float tr = state[1] + 1.0f;
+        if (tr >= interval) { state[0] *= growth; state[1] = 0.0f; }
+        else state[1] = tr;
+    }
+    state[2] = 0.0f;
+}
+
+// torch_ema.ExponentialMovingAverage.update: shadow -= (1 - decay) * (shadow - param)
+__global__ void __launch_bounds__(256)
+k_ema_update(float *__restrict__ shadow, const float *__restrict__ param, size_t n, float one_minus_decay) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float sv = shadow[i];
+        shadow[i] = sv - one_minus_decay * (sv - param[i]);
     }
 }
 
@@ -179,17 +237,35 @@ S3D_API int s3d_finetune_loss(const float *comp_s, const float *ws_s, const floa
 // grad_dtype: 0 = float32, 1 = float16.  step >= 1 (bias correction).  shadow may be NULL.
 S3D_API int s3d_adam_step(float *params, void *grads, float *exp_avg, float *exp_avg_sq, void *shadow_f16, uint64_t n, float lr,
                           float beta1, float beta2, float eps, uint32_t step, float grad_scale, int zero_grad, int grad_dtype,
-                          void *stream) {
+                          const float *scaler_state, void *stream) {
     if (n == 0) return 0;
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     const float lr_over_bc1 = (float)((double)lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
     const unsigned blocks = (unsigned)div_up((size_t)n, (size_t)1024);
     if (grad_dtype == 0)
         k_adam<float><<<blocks, 256, 0, as_stream(stream)>>>(params, (float *)grads, exp_avg, exp_avg_sq, (__half *)shadow_f16, (size_t)n,
-                                                              lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, grad_scale, zero_grad);
+                                                              lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, grad_scale, zero_grad, scaler_state, lr);
     else
         k_adam<__half><<<blocks, 256, 0, as_stream(stream)>>>(params, (__half *)grads, exp_avg, exp_avg_sq, (__half *)shadow_f16, (size_t)n,
-                                                               lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, grad_scale, zero_grad);
+                                                               lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, grad_scale, zero_grad, scaler_state, lr);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_grad_scaler_check(const float *grads, uint64_t n, float *scaler_state, float beta1, float beta2, void *stream) {
+    cudaStream_t st = as_stream(stream);
+    if (n) k_found_inf<<<(unsigned)min((size_t)div_up((size_t)n, (size_t)1024), (size_t)2368), 256, 0, st>>>(grads, (size_t)n, scaler_state);
+    k_scaler_prepare<<<1, 1, 0, st>>>(scaler_state, beta1, beta2);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_grad_scaler_update(float *scaler_state, float growth_factor, float backoff_factor, uint32_t growth_interval, void *stream) {
+    k_scaler_update<<<1, 1, 0, as_stream(stream)>>>(scaler_state, growth_factor, backoff_factor, (float)growth_interval);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_ema_update(float *shadow, const float *params, uint64_t n, float decay, void *stream) {
+    if (n == 0) return 0;
+    k_ema_update<<<(unsigned)min((size_t)div_up((size_t)n, (size_t)256), (size_t)4736), 256, 0, as_stream(stream)>>>(shadow, params, (size_t)n, 1.0f - decay);
     S3D_RETURN_LAST();
 }
 

@@ -144,24 +144,88 @@ class FusedNGP:
                   1.0, gw[0], gw[1], gw[2], gw[3], gw[4], int(train_mlp))
         _lib.call("s3d_ngp_scatter", xyz, dfeats, M, self.bound, self.grad4, self.offsets, self.L, self.S, self.H, 1.0)
 
-    def adam_step(self, lr, grad_scale=1.0, beta1=0.9, beta2=0.99, eps=1e-15, train_mlp=True):
+    def adam_step(self, lr, grad_scale=1.0, beta1=0.9, beta2=0.99, eps=1e-15, train_mlp=True, scaler_state=None, lr_mlp=None):
+        """fused Adam over the tables (+ MLP arena).  `scaler_state` = device GradScaler state (see GradScalerState): the
+        kernels then take scale, skip decision and bias corrections from it instead of the host-side step counts."""
         enc, encc = self.model.encoder, self.model.encoder_color
         self.step_tables += 1
         _lib.call("s3d_ngp_adam_tables", enc.embeddings.data, encc.embeddings.data, self.grad4, self.m4, self.v4, self._table_ptr(), self._tbl_stride,
-                  self.N, float(lr), beta1, beta2, eps, self.step_tables, float(grad_scale))
+                  self.N, float(lr), beta1, beta2, eps, self.step_tables, float(grad_scale), scaler_state)
         if train_mlp:
             self.step_mlp += 1
-            _lib.call("s3d_adam_step", self.mlp32, self.gmlp, self.m_mlp, self.v_mlp, self.mlp16, self.n_mlp, float(lr), beta1, beta2, eps,
-                      self.step_mlp, float(grad_scale), 1, 0)
+            _lib.call("s3d_adam_step", self.mlp32, self.gmlp, self.m_mlp, self.v_mlp, self.mlp16, self.n_mlp, float(lr if lr_mlp is None else lr_mlp),
+                      beta1, beta2, eps, self.step_mlp, float(grad_scale), 1, 0, scaler_state)
         else:
             self.gmlp.zero_()
+
+    # ---- parameter views for EMA / checkpoints: (tensor, ...) in the order tables, MLP arena
+    def param_tensors(self):
+        return [self.model.encoder.embeddings.data, self.model.encoder_color.embeddings.data, self.mlp32]
+
+
+class GradScalerState:
+    """torch.cuda.amp.GradScaler (nerf/utils.py:361, 857-859) with its state on the device: float[8] =
+    [scale, growth_tracker, found_inf, optimizer_steps, 1/(1-b1^t), 1/sqrt(1-b2^t), -, -].  Nothing here syncs with the host."""
+
+    def __init__(self, device, init_scale=65536.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000):
+        self.state = torch.zeros(8, dtype=torch.float32, device=device)
+        self.state[0] = float(init_scale)
+        self.growth_factor, self.backoff_factor, self.growth_interval = float(growth_factor), float(backoff_factor), int(growth_interval)
+
+    @property
+    def scale_tensor(self):
+        return self.state[0]      # 0-dim device tensor: usable as a multiplier without a host read
+
+    def check(self, grad_arena, beta1=0.9, beta2=0.99):
+        _lib.call("s3d_grad_scaler_check", grad_arena, grad_arena.numel(), self.state, beta1, beta2)
+
+    def update(self):
+        _lib.call("s3d_grad_scaler_update", self.state, self.growth_factor, self.backoff_factor, self.growth_interval)
+
+    def get_scale(self):
+        return float(self.state[0].item())
+
+
+class ParamEMA:
+    """torch_ema.ExponentialMovingAverage as the reference uses it (nerf/utils.py:356-357 create, :882-883 update once per
+    epoch, :919-921 / :1010-1011 store + copy_to / restore around evaluation).  torch_ema is a third-party package that is
+    not in the reference tree (unpinned in requirements.txt); its published update rule with use_num_updates=True:
+        decay_t = min(decay, (1 + n) / (10 + n)),  n = number of updates so far (after increment)
+        shadow -= (1 - decay_t) * (shadow - param)"""
+
+    def __init__(self, tensors, decay=0.95):
+        self.tensors, self.decay, self.num_updates = list(tensors), float(decay), 0
+        self.shadow = [t.detach().clone() for t in self.tensors]
+        self.stored = None
+
+    def update(self):
+        self.num_updates += 1
+        d = min(self.decay, (1.0 + self.num_updates) / (10.0 + self.num_updates))
+        for sh, t in zip(self.shadow, self.tensors):
+            _lib.call("s3d_ema_update", sh, t, t.numel(), float(d))
+
+    def store(self):
+        self.stored = [t.detach().clone() for t in self.tensors]
+
+    def copy_to(self):
+        for sh, t in zip(self.shadow, self.tensors):
+            t.copy_(sh)
+
+    def restore(self):
+        for st, t in zip(self.stored, self.tensors):
+            t.copy_(st)
+        self.stored = None
 
 
 class FusedDistillTrainer:
     """Same public steps as trainer.DistillTrainer (pretrain_step / finetune_step / distill_step), fused kernels inside."""
 
     def __init__(self, student, teacher=None, lr=1e-2, loss_scale=None, bg_color=1.0, T_thresh=1e-4, max_steps=1024, dt_gamma=0.0,
-                 world_size=1, update_interval=16):
+                 world_size=1, update_interval=16, lr_decay_iters=None, ema_decay=None, scaler_kwargs=None):
+        """loss_scale: None = static 32 x batch units (default), a float = static, "dynamic" = GradScaler semantics on the
+        device (scaler_kwargs: init_scale / growth_factor / backoff_factor / growth_interval).  lr_decay_iters = the LambdaLR
+        of main_SealNeRF.py:287-288, lr * 0.1 ** min(step / iters, 1), stepped every step.  ema_decay = torch_ema decay
+        (0.95 in main_SealNeRF.py:292-302); call ema_update() once per epoch like nerf/utils.py:882-883."""
         self.student, self.teacher = student, teacher
         self.S = FusedNGP(student, trainable=True)
         self.T = FusedNGP(teacher, trainable=False) if teacher is not None else None
@@ -173,6 +237,9 @@ class FusedDistillTrainer:
         self.loss_buf = torch.zeros(2, dtype=torch.float32, device=self.S.dev)
         self.global_step = 0
         self.table8 = None
+        self.lr_decay_iters = lr_decay_iters
+        self.scaler = GradScalerState(self.S.dev, **(scaler_kwargs or {})) if loss_scale == "dynamic" else None
+        self.ema = ParamEMA(self.S.param_tensors(), ema_decay) if ema_decay is not None else None
         try:   # per-step buffers are sized by the sample budget, which moves a little at every occupancy refresh: let the
             # caching allocator round large requests up (1/16 of a power of two) so refreshed sizes reuse cached blocks
             if "roundup_power2_divisions" not in os.environ.get("PYTORCH_CUDA_ALLOC_CONF", ""):
@@ -187,13 +254,46 @@ class FusedDistillTrainer:
             self.S.use_paired_table(self.table8, 1)
 
     def _scale(self, units):
+        if self.scaler is not None:
+            return self.scaler.scale_tensor          # device scalar; divided out inside the Adam kernels
         return float(self.loss_scale) if self.loss_scale is not None else 32.0 * float(units)
+
+    def current_lr(self):
+        if not self.lr_decay_iters:
+            return self.lr
+        return self.lr * 0.1 ** min(self.global_step / float(self.lr_decay_iters), 1.0)
 
     def _reduce_and_step(self, scale, train_mlp=True):
         if self.world_size > 1:
             dist.all_reduce(self.S.grad)   # the single collective of the step
-        self.S.adam_step(self.lr, grad_scale=1.0 / (self.world_size * scale), train_mlp=train_mlp)
+        if self.scaler is not None:
+            # the check runs on the all-reduced arena, so every rank takes the same skip / backoff decision
+            self.scaler.check(self.S.grad)
+            self.S.adam_step(self.current_lr(), grad_scale=1.0 / self.world_size, train_mlp=train_mlp, scaler_state=self.scaler.state)
+            self.scaler.update()
+        else:
+            self.S.adam_step(self.current_lr(), grad_scale=1.0 / (self.world_size * scale), train_mlp=train_mlp)
         self.global_step += 1
+
+    def ema_update(self):
+        if self.ema is not None:
+            self.ema.update()
+
+    def ema_apply(self):
+        """evaluation with the averaged parameters (nerf/utils.py:919-921): store, copy_to, rebuild the fp16 shadows"""
+        self.ema.store()
+        self.ema.copy_to()
+        self.S.sync_from_module()
+        self._refresh_pairing()
+
+    def ema_restore(self):
+        self.ema.restore()
+        self.S.sync_from_module()
+        self._refresh_pairing()
+
+    def _refresh_pairing(self):
+        if self.table8 is not None:
+            _lib.call("s3d_ngp_pair_tables", self.T.table4, self.S.table4, self.table8, self.S.N)
 
     def _march(self, rays_o, rays_d, perturb, force_all_rays):
         s = self.student
@@ -234,7 +334,7 @@ class FusedDistillTrainer:
         t = self.teacher
         sig_t, rgb_t, _ = self.T.mlp_forward(feats_t, md)
         if mask is not None and t.seal_mapper is not None and t.seal_mapper.has_color_edit():
-            t.seal_mapper.map_color_(rgb_t, mask)
+            t.seal_mapper.map_color_(rgb_t, mask, mx)
         ws_t, depth_t, img_t = self._composite(sig_t, rgb_t, deltas, rays)
         img_t.add_((1 - ws_t).unsqueeze(-1) * self.bg_color)
         return img_t, depth_t

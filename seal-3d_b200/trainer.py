@@ -69,7 +69,7 @@ class ParamArena:
         for off, k, st in active:
             _lib.call("s3d_adam_step", self.flat[off:], self.grad[off:], self.exp_avg[off:], self.exp_avg_sq[off:],
                       self.shadow[off:] if self.shadow is not None else None, k, float(lr), beta1, beta2, eps,
-                      st, float(grad_scale), 1, 0)
+                      st, float(grad_scale), 1, 0, None)
         if only is not None:
             self.grad.zero_()
 

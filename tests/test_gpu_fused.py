@@ -184,7 +184,7 @@ def test_fused_adam_tables_matches_torch():
         ref.grad = gr.clone()
         opt.step()
         g4.copy_(gr * 4)
-        _lib.call("s3d_ngp_adam_tables", ps, pc, g4, m4, v4, t4, 8, n, 1e-2, 0.9, 0.99, 1e-15, step, 0.25)
+        _lib.call("s3d_ngp_adam_tables", ps, pc, g4, m4, v4, t4, 8, n, 1e-2, 0.9, 0.99, 1e-15, step, 0.25, None)
         assert not g4.any()
     np.testing.assert_allclose(npy(torch.cat([ps, pc], 1)), npy(ref), rtol=1e-5, atol=1e-6)
     assert torch.equal(t4, torch.cat([ps, pc], 1).half())
@@ -220,3 +220,96 @@ def test_fused_trainer_tracks_autograd_trainer(scene):
     sig_t, rgb_t, _ = fused.T.forward(pts, dirs)
     lpre = [float(npy(fused.pretrain_step(pts, dirs, sig_t, rgb_t))[0]) for _ in range(6)]
     assert lpre[-1] < lpre[0] and torch.equal(w_before, s1.sigma_net[0].weight.detach())
+
+
+def test_grad_scaler_adam_schedule_match_torch():
+    """the device-side GradScaler state + fused Adam + LambdaLR against torch's own GradScaler / Adam / LambdaLR
+    (what nerf/utils.py:857-862 runs), including skipped steps on injected infs, backoff and growth; and against the oracle"""
+    from seal3d_b200 import _lib
+    from seal3d_b200.fused import GradScalerState
+    n, lr0, iters = 10007, 1e-2, 8
+    gen = torch.Generator(device=dev()).manual_seed(3)
+    p0 = torch.randn(n, device=dev(), generator=gen)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=lr0, betas=(0.9, 0.99), eps=1e-15)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda it: 0.1 ** min(it / iters, 1))
+    scaler = torch.amp.GradScaler("cuda", init_scale=1024.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=3)
+    st = GradScalerState(dev(), init_scale=1024.0, growth_interval=3)
+    orc = oracle.Optimizer(npy(p0), lr0, iters=iters, init_scale=1024.0, growth_interval=3)
+    # flat arena path (s3d_adam_step) and interleaved table path (s3d_ngp_adam_tables) share the state
+    p, m, v = p0.clone(), torch.zeros(n, device=dev()), torch.zeros(n, device=dev())
+    nt = n // 4
+    ps, pc = p0[:nt * 2].clone().view(nt, 2), p0[nt * 2:nt * 4].clone().view(nt, 2)
+    m4, v4 = torch.zeros(nt, 4, device=dev()), torch.zeros(nt, 4, device=dev())
+    t4 = torch.cat([ps, pc], 1).half()
+    applied = 0
+    for it in range(12):
+        g = torch.randn(n, device=dev(), generator=gen)
+        if it in (2, 7, 8):
+            g[17] = float("inf") if it != 7 else float("nan")
+        loss = (p_ref * g).sum()
+        opt.zero_grad()
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        sched.step()
+        lr_t = lr0 * 0.1 ** min(it / iters, 1)
+        gg = (g * st.scale_tensor).contiguous()             # the scaled gradient the backward pass would have produced
+        g4 = torch.cat([gg[:nt * 2].view(nt, 2), gg[nt * 2:nt * 4].view(nt, 2)], 1).contiguous()
+        orc.step(npy(gg))
+        st.check(gg)
+        _lib.call("s3d_adam_step", p, gg, m, v, None, n, lr_t, 0.9, 0.99, 1e-15, 1, 1.0, 1, 0, st.state)
+        # the table kernel sees only its own slice; an inf outside of it must still skip the step (found_inf is global)
+        _lib.call("s3d_ngp_adam_tables", ps, pc, g4, m4, v4, t4, 8, nt, lr_t, 0.9, 0.99, 1e-15, 1, 1.0, st.state)
+        st.update()
+        assert not gg.any() and not g4.any()
+        applied += 0 if it in (2, 7, 8) else 1
+        assert st.get_scale() == scaler.get_scale() == orc.scale, (it, st.get_scale(), scaler.get_scale(), orc.scale)
+    assert int(st.state[3].item()) == applied == orc.t_opt
+    np.testing.assert_allclose(npy(p), npy(p_ref), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(npy(p), orc.p, rtol=2e-5, atol=2e-6)
+    tab = torch.cat([ps.reshape(-1), pc.reshape(-1)])
+    np.testing.assert_allclose(npy(tab), npy(p_ref)[:nt * 4], rtol=2e-5, atol=2e-6)
+    assert torch.equal(t4, torch.cat([ps, pc], 1).half())
+
+
+def test_param_ema_and_dynamic_scale_trainer(scene):
+    """torch_ema's update rule on the parameter arena (vs the oracle), store / copy_to / restore, and the fused trainer with
+    loss_scale="dynamic" + LambdaLR following the static-scale trainer"""
+    from seal3d_b200.fused import FusedDistillTrainer, ParamEMA
+    a = torch.randn(1000, device=dev())
+    ema = ParamEMA([a], decay=0.95)
+    orc = oracle.Optimizer(npy(a), 0.0, ema_decay=0.95)
+    for k in range(15):
+        a.add_(0.1 * torch.randn_like(a))
+        orc.p = npy(a).astype(np.float64)
+        ema.update()
+        orc.ema_update()
+    np.testing.assert_allclose(npy(ema.shadow[0]), orc.shadow, rtol=1e-5, atol=1e-6)
+    before = a.clone()
+    ema.store(); ema.copy_to()
+    assert torch.equal(a, ema.shadow[0])
+    ema.restore()
+    assert torch.equal(a, before)
+
+    o, d = scene["synth"].rays_for_step(0, 2048)
+    losses = {}
+    for mode in ("static", "dynamic"):
+        t, s, _, _ = _networks(scene)
+        tr = FusedDistillTrainer(s, t, lr=1e-2, loss_scale=(None if mode == "static" else "dynamic"), lr_decay_iters=20, ema_decay=0.95,
+                                 scaler_kwargs=(None if mode == "static" else dict(init_scale=65536.0, growth_interval=4)), update_interval=0)
+        ls = []
+        for i in range(8):
+            ls.append(npy(tr.distill_step(to(o), to(d), perturb=False, force_all_rays=True)).copy())
+        tr.ema_update()
+        losses[mode] = np.array(ls)
+        if mode == "dynamic":
+            applied = int(tr.scaler.state[3].item())
+            assert applied >= 6 and np.isfinite(tr.scaler.get_scale()) and tr.scaler.get_scale() >= 65536.0 * 0.25, (applied, tr.scaler.get_scale())
+            w0 = [x.clone() for x in tr.S.param_tensors()]
+            tr.ema_apply()
+            assert not torch.equal(tr.S.param_tensors()[0], w0[0])
+            tr.ema_restore()
+            assert all(torch.equal(x, y) for x, y in zip(tr.S.param_tensors(), w0))
+    assert np.isfinite(losses["dynamic"]).all() and losses["dynamic"][-1, 0] < losses["dynamic"][0, 0]
+    np.testing.assert_allclose(losses["dynamic"][:4], losses["static"][:4], rtol=5e-2, atol=1e-7)   # same scale for the first 4 steps

@@ -626,7 +626,7 @@ def test_losses_and_adam():
         p_ref.grad = g.clone()
         opt.step()
         gg = (g * 2).contiguous()
-        _lib.call("s3d_adam_step", p, gg, m, v, sh, n, 1e-2, 0.9, 0.99, 1e-15, step, 0.5, 1, 0)
+        _lib.call("s3d_adam_step", p, gg, m, v, sh, n, 1e-2, 0.9, 0.99, 1e-15, step, 0.5, 1, 0, None)
         assert not gg.any()
     np.testing.assert_allclose(npy(p), npy(p_ref), rtol=1e-5, atol=1e-6)
     assert torch.equal(sh, p.half())
@@ -776,3 +776,48 @@ def test_reference_named_extension_modules():
     np.testing.assert_allclose(npy(y), oracle.sh_encode_forward(d, 4)[0], rtol=2e-5, atol=2e-5)
     _ffmlp.allocate_splitk(3)
     assert hasattr(_freqencoder, "freq_encode_forward")
+
+
+# --------------------------------------------------------------------------------- brush / anchor / texture
+
+
+def test_brush_anchor_texture_mappers():
+    """kernels vs the oracle (exact masks, 1e-6 positions) and vs the reference's own code run on CPU torch (golden)"""
+    from seal3d_b200.seal import SealBrushMapper, SealAnchorMapper
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cpu_mappers.npz"))
+    pts = g["points"]
+    for mode in ("linear", "dry"):
+        m = SealBrushMapper({"map_bound": g["brush_bounds"], "normal_expand": g["brush_normal_expand"], "center": g["brush_center"],
+                             "border_points": g["brush_border"], "attenuation_distance": g["brush_att"], "attenuation_mode": mode}, g["brush_tris"])
+        p2, d2, mask = m.map_to_origin(to(pts), None)
+        ref_p, ref_m = oracle.seal_brush_map_to_origin(pts, g["brush_bounds"], g["brush_tris"], g["brush_normal_expand"], g["brush_center"],
+                                                       g["brush_border"], float(g["brush_att"]), mode, test_dir=g["brush_normal_expand"])
+        assert d2 is None and np.array_equal(npy(mask), ref_m) and np.array_equal(ref_m, g["brush_%s_mask" % mode])
+        np.testing.assert_allclose(npy(p2), ref_p, rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(npy(p2), g["brush_%s_points" % mode], rtol=0, atol=2e-4)    # torch.cdist's matmul route
+    with pytest.raises(NotImplementedError):
+        SealBrushMapper({"map_bound": g["brush_bounds"], "normal_expand": g["brush_normal_expand"], "center": g["brush_center"],
+                         "border_points": g["brush_border"], "attenuation_distance": 0.1, "attenuation_mode": "ease-in"}, g["brush_tris"])
+    am = SealAnchorMapper({"map_bound": g["anchor_bounds"], "v_anchor": g["anchor_v_anchor"], "v_offset": g["anchor_v_offset"], "v_h": g["anchor_v_h"],
+                           "len_h": g["anchor_len_h"], "radius": g["anchor_radius"], "scale": g["anchor_scale"]}, g["anchor_tris"])
+    p2, _, mask = am.map_to_origin(to(pts), None)
+    assert np.array_equal(npy(mask), g["anchor_mask"])
+    np.testing.assert_allclose(npy(p2), g["anchor_points"], rtol=1e-5, atol=1e-6)
+    far = (pts + 5.0).astype(np.float32)
+    p3, _, m3 = am.map_to_origin(to(far), None)       # nothing in the map region: identity, empty mask (the reference's early exit)
+    assert not m3.any() and np.array_equal(npy(p3), far)
+    tex = SealBrushMapper({"map_bound": g["brush_bounds"], "normal_expand": g["brush_normal_expand"], "center": g["brush_center"],
+                           "border_points": g["brush_border"], "attenuation_distance": g["brush_att"], "attenuation_mode": "dry",
+                           "image": g["tex_image"], "image_mask": g["tex_alpha"], "v_image_norm": g["tex_norm"], "v_image_o": g["tex_o"],
+                           "v_image_w": g["tex_w"], "v_image_h": g["tex_h"], "rgb_light_offset": g["tex_light"]}, g["brush_tris"])
+    out = tex.map_color(to(g["tex_points"]), None, to(g["tex_colors"]))
+    np.testing.assert_allclose(npy(out), g["tex_out"], rtol=1e-5, atol=3e-6)
+    # masked in-place form used by the renderers: untouched rows stay bit-identical
+    cols = to(g["tex_colors"]).clone()
+    msk = torch.zeros(cols.shape[0], dtype=torch.bool, device=dev())
+    msk[::3] = True
+    tex.map_color_(cols, msk, to(g["tex_points"]))
+    ref = oracle.seal_map_color_image(g["tex_points"][::3], g["tex_colors"][::3], g["tex_image"], g["tex_alpha"], g["tex_norm"], g["tex_o"],
+                                      g["tex_w"], g["tex_h"], float(g["tex_light"]))
+    np.testing.assert_allclose(npy(cols)[::3], ref, rtol=1e-5, atol=3e-6)
+    assert np.array_equal(npy(cols)[1::3], g["tex_colors"][1::3])

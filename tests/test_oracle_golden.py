@@ -201,3 +201,26 @@ def test_trunc_exp_semantics():
     g = load("cpu_trunc_exp.npz")
     np.testing.assert_allclose(np.exp(g["x"]), g["y"], rtol=1e-6)
     np.testing.assert_allclose(g["gy"] * np.exp(np.clip(g["x"], -15, 15)), g["gx"], rtol=1e-6)
+
+
+def test_brush_anchor_texture_vs_reference_code():
+    """SealBrushMapper / SealAnchorMapper.map_to_origin and the texture branch of SealMapper.map_color, lifted
+    from the reference and run on CPU torch (tests/golden/make_cpu_golden.py), against the oracle"""
+    g = load("cpu_mappers.npz")
+    for mode in ("linear", "dry"):
+        pts, mask = oracle.seal_brush_map_to_origin(g["points"], g["brush_bounds"], g["brush_tris"], g["brush_normal_expand"], g["brush_center"],
+                                                    g["brush_border"], float(g["brush_att"]), mode, test_dir=g["brush_normal_expand"])
+        assert np.array_equal(mask, g["brush_%s_mask" % mode])
+        # torch.cdist takes the matmul route (|a|^2 + |b|^2 - 2ab) for > 25 rows: its distances carry ~1e-4 of cancellation error
+        np.testing.assert_allclose(pts, g["brush_%s_points" % mode], rtol=0, atol=2e-4 if mode == "linear" else 0)
+    assert g["brush_linear_mask"].sum() > 500
+    pts, mask = oracle.seal_anchor_map_to_origin(g["points"], g["anchor_bounds"], g["anchor_tris"], g["anchor_v_anchor"], g["anchor_v_offset"],
+                                                 g["anchor_v_h"], float(g["anchor_len_h"]), float(g["anchor_radius"]), g["anchor_scale"])
+    assert np.array_equal(mask, g["anchor_mask"]) and mask.sum() > 100
+    np.testing.assert_allclose(pts, g["anchor_points"], rtol=1e-5, atol=1e-6)
+    far, fmask = oracle.seal_anchor_map_to_origin(g["points"] + 5.0, g["anchor_bounds"], g["anchor_tris"], g["anchor_v_anchor"], g["anchor_v_offset"],
+                                                  g["anchor_v_h"], float(g["anchor_len_h"]), float(g["anchor_radius"]), g["anchor_scale"])
+    assert not fmask.any() and np.array_equal(far, (g["points"] + 5.0).astype(np.float32))
+    out = oracle.seal_map_color_image(g["tex_points"], g["tex_colors"], g["tex_image"], g["tex_alpha"], g["tex_norm"], g["tex_o"], g["tex_w"],
+                                      g["tex_h"], float(g["tex_light"]))
+    np.testing.assert_allclose(out, g["tex_out"], rtol=1e-5, atol=2e-6)
