@@ -19,6 +19,9 @@ class _ColorEdits:
 
     def _init_color(self, md):
         self._stats = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self._h_hsv = _lib.host_f32(md["hsv"]) if "hsv" in md else None
+        self._h_rgb = _lib.host_f32(md["rgb"]) if "rgb" in md else None
+        self._light = float(md["rgb_light_offset"]) if "rgb_light_offset" in md else 0.0
         self._image = None
         if "image" in md:
             self._image = torch.from_numpy(np.ascontiguousarray(md["image"], dtype=np.float32)).to(self.device)
@@ -60,9 +63,6 @@ class SealBBoxMapper(_ColorEdits):
         self._h_test = _lib.host_f32(test_dir) if test_dir is not None else None
         self._h_src = _lib.host_f32(md["empty_bound"]) if "map_source" in md else None
         self._h_ms = _lib.host_f32(md["map_source"]) if "map_source" in md else None
-        self._h_hsv = _lib.host_f32(md["hsv"]) if "hsv" in md else None
-        self._h_rgb = _lib.host_f32(md["rgb"]) if "rgb" in md else None
-        self._light = float(md["rgb_light_offset"]) if "rgb_light_offset" in md else 0.0
         self.bounds = torch.from_numpy(md["map_bound"].reshape(-1, 2, 3)).to(self.device).contiguous()
         self.map_triangles = torch.from_numpy(np.asarray(triangles, np.float32).reshape(-1, 3, 3)).to(self.device).contiguous()
         self._init_color(md)
