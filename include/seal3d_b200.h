@@ -226,6 +226,25 @@ int s3d_ngp_adam_tables(float *table_sigma, float *table_color, float *grad4, fl
                         uint32_t shadow_stride, uint64_t n_entries, float lr, float beta1, float beta2, float eps, uint32_t step,
                         float grad_scale, const float *scaler_state, void *stream);
 
+/* ------------------------------------------------------------------ TensoRF VM field */
+/* The reference has no extension here: tensoRF/network.py:99-151 issues twelve F.grid_sample(bilinear, zeros,
+ * align_corners=True) calls per batch; these entries are the kernel form of that seam (get_sigma_feat / get_color_feat).
+ * Factor images are CHANNEL-LAST float32: plane i [H_i, W_i, R] (the reference's [1,R,H,W] parameter in torch channels_last
+ * memory format), line i [D_i, R].  h_dims = HOST int[9] = {H_i, W_i, D_i} for i = 0..2; plane i is indexed by
+ * (x[mat_ids[i][0]] -> W, x[mat_ids[i][1]] -> H), line i by x[vec_ids[i]] (network.py:37-38).  xyz [M,3] are world
+ * coordinates normalised with aabb (device float[6], network.py:158) or, if aabb is NULL, already in [-1,1].
+ * R % 4 == 0; reduce = 1 (sum over channels and planes, network.py:118-121) additionally needs R/4 a power of two <= 32. */
+int s3d_vm_forward(const float *xyz, uint32_t M, const float *aabb, const float *mat0, const float *mat1, const float *mat2,
+                   const float *vec0, const float *vec1, const float *vec2, const int *h_dims, uint32_t R, int reduce,
+                   float *out /* [M] or [M,3R] */, void *stream);
+/* autograd of the above (grid_sampler_2d_backward w.r.t. the input images): g_* accumulate, caller zero-fills */
+int s3d_vm_backward(const float *xyz, uint32_t M, const float *aabb, const float *mat0, const float *mat1, const float *mat2,
+                    const float *vec0, const float *vec1, const float *vec2, const int *h_dims, uint32_t R, int reduce,
+                    const float *grad, float *g_mat0, float *g_mat1, float *g_mat2, float *g_vec0, float *g_vec1, float *g_vec2,
+                    void *stream);
+/* tensoRF/network.py:263-270 upsample_params: F.interpolate(bilinear, align_corners=True) of one channel-last image */
+int s3d_vm_resize(const float *src, uint32_t H, uint32_t W, float *dst, uint32_t H2, uint32_t W2, uint32_t R, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

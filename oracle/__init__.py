@@ -425,6 +425,99 @@ class NGPField:
                     w_c0=g_wc0, w_c1=g_wc1, w_c2=g_wc2)
 
 
+# ---------------------------------------------------------------- TensoRF VM field (tensoRF/network.py:99-183)
+
+
+def _ptr_array(arrs):
+    return (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+def _vm_dims(mats, vecs):
+    """mats[i] [R, H_i, W_i], vecs[i] [R, D_i] (reference shapes [1,R,H,W] / [1,R,D,1] squeezed) -> int32 [9] = H, W, D per plane"""
+    return _i32([[m.shape[1], m.shape[2], v.shape[1]] for m, v in zip(mats, vecs)]).reshape(-1)
+
+
+def _vm_squeeze(mats, vecs):
+    mats = [_f32(np.asarray(m).reshape(m.shape[-3], m.shape[-2], m.shape[-1])) for m in mats]
+    vecs = [_f32(np.asarray(v).reshape(v.shape[1], v.shape[2]) if np.asarray(v).ndim == 4 else v) for v in vecs]
+    return mats, vecs
+
+
+def vm_forward(xyz, mats, vecs, reduce, aabb=None):
+    """get_sigma_feat (reduce=True, returns [M]) / the mat_feat * vec_feat product of get_color_feat (reduce=False,
+    returns [M, 3R]); xyz are world coordinates if aabb is given (normalised like network.py:158), else already in [-1,1]."""
+    xyz = _f32(xyz).reshape(-1, 3)
+    mats, vecs = _vm_squeeze(mats, vecs)
+    R, M = mats[0].shape[0], xyz.shape[0]
+    out = np.empty(M if reduce else (M, 3 * R), np.float32)
+    ab = _f32(aabb) if aabb is not None else None
+    lib().orc_vm_forward(_p(xyz), u32(M), _p(ab), _ptr_array(mats), _ptr_array(vecs), _p(_vm_dims(mats, vecs)), u32(R),
+                         cint(1 if reduce else 0), _p(out))
+    return out
+
+
+def vm_backward(xyz, mats, vecs, reduce, g, aabb=None):
+    """gradients (reference layouts [R,H,W] / [R,D]) of the planes and lines for an upstream gradient g"""
+    xyz = _f32(xyz).reshape(-1, 3)
+    mats, vecs = _vm_squeeze(mats, vecs)
+    R, M = mats[0].shape[0], xyz.shape[0]
+    g = _f32(g)
+    gm, gv = [np.empty_like(m) for m in mats], [np.empty_like(v) for v in vecs]
+    ab = _f32(aabb) if aabb is not None else None
+    lib().orc_vm_backward(_p(xyz), u32(M), _p(ab), _ptr_array(mats), _ptr_array(vecs), _p(_vm_dims(mats, vecs)), u32(R),
+                          cint(1 if reduce else 0), _p(g), _ptr_array(gm), _ptr_array(gv))
+    return gm, gv
+
+
+class TensoRFField:
+    """fp32 restatement of tensoRF/network.py NeRFNetwork.forward (:153-183): sigma = exp(sum of plane x line products),
+    rgb = sigmoid(MLP([freq2(basis_mat . products) | freq2(d)])) with bias-free 150-128-128-3 layers; backward (after
+    forward(keep=True)) returns the gradients of every parameter in the reference layouts."""
+
+    def __init__(self, sigma_mat, sigma_vec, color_mat, color_vec, basis_mat, color_net, aabb=(-1, -1, -1, 1, 1, 1), degree=2):
+        self.sm, self.sv = _vm_squeeze(sigma_mat, sigma_vec)
+        self.cm, self.cv = _vm_squeeze(color_mat, color_vec)
+        self.basis = _f32(basis_mat)
+        self.w = [_f32(w) for w in color_net]
+        self.aabb, self.degree = _f32(aabb), degree
+
+    def forward(self, x, d, keep=False):
+        sf = vm_forward(x, self.sm, self.sv, True, self.aabb)
+        sigma = np.exp(sf)
+        prod = vm_forward(x, self.cm, self.cv, False, self.aabb)
+        cf = prod @ self.basis.T
+        ecf, ed = freq_encode_forward(cf, self.degree), freq_encode_forward(d, self.degree)
+        h = [np.concatenate([ecf, ed], axis=1)]
+        for l, w in enumerate(self.w):
+            z = h[-1] @ w.T
+            h.append(np.maximum(z, 0) if l != len(self.w) - 1 else 1.0 / (1.0 + np.exp(-z)))
+        if keep:
+            self._saved = (_f32(x), sf, prod, cf, ecf, h)
+        return sigma.astype(np.float32), h[-1].astype(np.float32)
+
+    def density(self, x):
+        return np.exp(vm_forward(x, self.sm, self.sv, True, self.aabb)).astype(np.float32)
+
+    def backward(self, g_sigma, g_rgb):
+        x, sf, prod, cf, ecf, h = self._saved
+        rgb = h[-1]
+        g = _f32(g_rgb) * rgb * (1 - rgb)
+        g_w = [None] * len(self.w)
+        for l in range(len(self.w) - 1, -1, -1):
+            g_w[l] = g.T @ h[l]
+            g = g @ self.w[l]
+            if l > 0:
+                g = g * (h[l] > 0)
+        g_ecf = np.ascontiguousarray(g[:, :ecf.shape[1]])
+        g_cf = freq_encode_backward(g_ecf, ecf, cf.shape[1], self.degree)
+        g_basis = g_cf.T @ prod
+        g_prod = g_cf @ self.basis
+        g_cm, g_cv = vm_backward(x, self.cm, self.cv, False, g_prod, self.aabb)
+        g_sf = _f32(g_sigma) * np.exp(np.clip(sf, -15, 15))      # trunc_exp backward (activation.py:14-17)
+        g_sm, g_sv = vm_backward(x, self.sm, self.sv, True, g_sf, self.aabb)
+        return dict(sigma_mat=g_sm, sigma_vec=g_sv, color_mat=g_cm, color_vec=g_cv, basis_mat=g_basis, color_net=g_w)
+
+
 # ---------------------------------------------------------------- distillation losses (numpy)
 
 

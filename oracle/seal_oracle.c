@@ -1078,3 +1078,111 @@ ORC_API void orc_seal_map_color_image(const float *points, const float *rgb, int
         for (int i = 0; i < 3; i++) out[p * 3 + i] = a * mod[i] + (1.0f - a) * rgb[p * 3 + i];
     }
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* tensoRF/network.py -- vector-matrix (VM) decomposition lookups                         */
+/* ------------------------------------------------------------------------------------ */
+/*
+ * The reference has no kernel of its own here: get_sigma_feat / get_color_feat (tensoRF/network.py:99-151)
+ * call torch.nn.functional.grid_sample(mode='bilinear', padding_mode='zeros', align_corners=True) twelve
+ * times per query batch.  The arithmetic is ATen's grid_sampler_2d (third-party: torch, unpinned in the
+ * reference's requirements.txt:6; restated from its published algorithm, aten/src/ATen/native/GridSampler.h
+ * grid_sampler_unnormalize + GridSampler.cu grid_sampler_2d_kernel):
+ *     ix = ((x + 1) / 2) * (W - 1);  iy likewise with H
+ *     nw = (floor ix, floor iy), ne = nw + (1,0), sw = nw + (0,1), se = nw + (1,1)
+ *     w_nw = (ix_se - ix)(iy_se - iy), w_ne = (ix - ix_sw)(iy_sw - iy), w_sw = (ix_ne - ix)(iy - iy_ne), w_se = (ix - ix_nw)(iy - iy_nw)
+ *     out = sum over the in-bounds taps, in the order nw, ne, sw, se
+ * A "line" is a [R, D, 1] image sampled at x = 0 (network.py:106-107): ix = 0, so only the nw / sw taps of column 0
+ * are in bounds and the weights reduce to (iy_se - iy) and (iy - iy_ne).
+ * Pinned by tests/golden/cpu_tensorf.npz = the reference's own NeRFNetwork methods run on CPU torch.
+ *
+ * Layout here is the reference's: planes [R, H, W], lines [R, D].  Plane i uses coordinates
+ * (x[mat_ids[i][0]] -> W, x[mat_ids[i][1]] -> H), mat_ids = {0,1},{0,2},{1,2}; line i uses x[vec_ids[i]], vec_ids = {2,1,0}
+ * (network.py:37-38).  dims[i*3 + {0,1,2}] = H_i, W_i, D_i.
+ */
+static const int kMatId0[3] = {0, 0, 1}, kMatId1[3] = {1, 2, 2}, kVecId[3] = {2, 1, 0};
+
+typedef struct { int x0, y0; float w[4]; int ok[4]; } vm_taps2;   /* nw, ne, sw, se */
+
+static inline void vm_plane_taps(float gx, float gy, int H, int W, vm_taps2 *t) {
+    const float ix = ((gx + 1.0f) / 2.0f) * (float)(W - 1), iy = ((gy + 1.0f) / 2.0f) * (float)(H - 1);
+    const float fx = floorf(ix), fy = floorf(iy);
+    const float ix_nw = fx, iy_nw = fy, ix_se = fx + 1.0f, iy_se = fy + 1.0f;
+    t->x0 = (int)fx; t->y0 = (int)fy;
+    t->w[0] = (ix_se - ix) * (iy_se - iy);
+    t->w[1] = (ix - ix_nw) * (iy_se - iy);
+    t->w[2] = (ix_se - ix) * (iy - iy_nw);
+    t->w[3] = (ix - ix_nw) * (iy - iy_nw);
+    for (int k = 0; k < 4; k++) {
+        const int xx = t->x0 + (k & 1), yy = t->y0 + (k >> 1);
+        t->ok[k] = xx >= 0 && xx < W && yy >= 0 && yy < H;
+    }
+}
+
+/* aabb normalisation of tensoRF/network.py:158: x = 2 * (x - lo) / (hi - lo) - 1, elementwise float32 ops */
+static inline float vm_normalise(float x, float lo, float hi) { return (2.0f * (x - lo)) / (hi - lo) - 1.0f; }
+
+/* out_feat: [M, 3R] = mat_feat * vec_feat (plane-major, channel-minor: network.py:141-146) when reduce == 0,
+ * or [M] = sum over planes of sum over channels (network.py:118-121) when reduce != 0.
+ * xyz are world coordinates when aabb != NULL (normalised here), already-normalised coordinates otherwise. */
+ORC_API void orc_vm_forward(const float *xyz, uint32_t M, const float *aabb, const float *const *mats, const float *const *vecs,
+                            const int *dims, uint32_t R, int reduce, float *out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < (int64_t)M; m++) {
+        float x[3];
+        for (int d = 0; d < 3; d++) x[d] = aabb ? vm_normalise(xyz[m * 3 + d], aabb[d], aabb[3 + d]) : xyz[m * 3 + d];
+        float total = 0.0f;
+        for (int i = 0; i < 3; i++) {
+            const int H = dims[i * 3], W = dims[i * 3 + 1], D = dims[i * 3 + 2];
+            vm_taps2 tp, tl;
+            vm_plane_taps(x[kMatId0[i]], x[kMatId1[i]], H, W, &tp);
+            vm_plane_taps(0.0f, x[kVecId[i]], D, 1, &tl);
+            float plane_sum = 0.0f;
+            for (uint32_t r = 0; r < R; r++) {
+                const float *pm = mats[i] + (size_t)r * H * W, *pv = vecs[i] + (size_t)r * D;
+                float a = 0.0f, b = 0.0f;
+                for (int k = 0; k < 4; k++)
+                    if (tp.ok[k]) a = fmaf(pm[(size_t)(tp.y0 + (k >> 1)) * W + tp.x0 + (k & 1)], tp.w[k], a);
+                for (int k = 0; k < 4; k++)
+                    if (tl.ok[k]) b = fmaf(pv[tl.y0 + (k >> 1)], tl.w[k], b);
+                if (reduce) plane_sum += a * b;
+                else out[(size_t)m * 3 * R + (size_t)i * R + r] = a * b;
+            }
+            total += plane_sum;
+        }
+        if (reduce) out[m] = total;
+    }
+}
+
+/* gradients of the planes / lines for d(out) = g: g [M] (reduce) or [M, 3R].  Accumulated in double (the reference's
+ * grid_sampler backward uses float atomics in a nondeterministic order), rounded once.  g_mats / g_vecs are overwritten. */
+ORC_API void orc_vm_backward(const float *xyz, uint32_t M, const float *aabb, const float *const *mats, const float *const *vecs,
+                             const int *dims, uint32_t R, int reduce, const float *g, float *const *g_mats, float *const *g_vecs) {
+    for (int i = 0; i < 3; i++) {
+        const int H = dims[i * 3], W = dims[i * 3 + 1], D = dims[i * 3 + 2];
+        double *am = (double *)calloc((size_t)R * H * W, sizeof(double)), *av = (double *)calloc((size_t)R * D, sizeof(double));
+        for (int64_t m = 0; m < (int64_t)M; m++) {
+            float x[3];
+            for (int d = 0; d < 3; d++) x[d] = aabb ? vm_normalise(xyz[m * 3 + d], aabb[d], aabb[3 + d]) : xyz[m * 3 + d];
+            vm_taps2 tp, tl;
+            vm_plane_taps(x[kMatId0[i]], x[kMatId1[i]], H, W, &tp);
+            vm_plane_taps(0.0f, x[kVecId[i]], D, 1, &tl);
+            for (uint32_t r = 0; r < R; r++) {
+                const float *pm = mats[i] + (size_t)r * H * W, *pv = vecs[i] + (size_t)r * D;
+                double a = 0.0, b = 0.0;
+                for (int k = 0; k < 4; k++)
+                    if (tp.ok[k]) a += (double)pm[(size_t)(tp.y0 + (k >> 1)) * W + tp.x0 + (k & 1)] * tp.w[k];
+                for (int k = 0; k < 4; k++)
+                    if (tl.ok[k]) b += (double)pv[tl.y0 + (k >> 1)] * tl.w[k];
+                const double go = reduce ? (double)g[m] : (double)g[(size_t)m * 3 * R + (size_t)i * R + r];
+                for (int k = 0; k < 4; k++)
+                    if (tp.ok[k]) am[(size_t)r * H * W + (size_t)(tp.y0 + (k >> 1)) * W + tp.x0 + (k & 1)] += go * b * tp.w[k];
+                for (int k = 0; k < 4; k++)
+                    if (tl.ok[k]) av[(size_t)r * D + tl.y0 + (k >> 1)] += go * a * tl.w[k];
+            }
+        }
+        for (size_t j = 0; j < (size_t)R * H * W; j++) g_mats[i][j] = (float)am[j];
+        for (size_t j = 0; j < (size_t)R * D; j++) g_vecs[i][j] = (float)av[j];
+        free(am); free(av);
+    }
+}

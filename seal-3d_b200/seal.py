@@ -11,6 +11,7 @@ import torch
 from . import _lib
 from . import raymarching
 from .network import NeRFNetwork
+from .tensorf import TensoRFNetwork
 
 
 class _ColorEdits:
@@ -189,7 +190,7 @@ class SealRendererMixin:
             self.hack_bitfield()
 
 
-class TeacherNetwork(SealRendererMixin, NeRFNetwork):
+class SealTeacherMixin:
     """SealNeRFTeacherRenderer (SealNeRF/renderer.py:77-418): samples are mapped to the original space before the
     field query and the colours of mapped samples are edited afterwards."""
 
@@ -205,5 +206,18 @@ class TeacherNetwork(SealRendererMixin, NeRFNetwork):
         return self.seal_mapper.map_color_(rgbs, mask, xyzs.view(-1, 3) if xyzs is not None else None)
 
 
+# SealNeRF/network.py:7-50 get_network(backbone, character): the four backbone x character classes
+class TeacherNetwork(SealTeacherMixin, SealRendererMixin, NeRFNetwork):
+    """NeRFNetwork_NGP_Teacher"""
+
+
 class StudentNetwork(SealRendererMixin, NeRFNetwork):
-    """SealNeRFStudentRenderder (SealNeRF/renderer.py:421-424): plain renderer + the force-filled bitfield."""
+    """NeRFNetwork_NGP_Student -- SealNeRFStudentRenderder (SealNeRF/renderer.py:421-424): plain renderer + the force-filled bitfield."""
+
+
+class TensoRFTeacherNetwork(SealTeacherMixin, SealRendererMixin, TensoRFNetwork):
+    """NeRFNetwork_TensoRF_Teacher (main_SealTensoRF.py:173-183)"""
+
+
+class TensoRFStudentNetwork(SealRendererMixin, TensoRFNetwork):
+    """NeRFNetwork_TensoRF_Student (main_SealTensoRF.py:187-197)"""

@@ -21,9 +21,12 @@ class ParamArena:
     nerf/network.py:199-212 (encoder, sigma_net, encoder_color, encoder_dir, color_net); gradients as views of a
     second buffer, Adam moments in two more, and an fp16 shadow that the fused Adam kernel refreshes in the same pass."""
 
-    def __init__(self, model, with_half_shadow=True):
-        groups = model.get_params(0.0)
+    def __init__(self, model, with_half_shadow=True, n_lr=1):
+        # get_params(lr) for the NGP field, get_params(lr1, lr2) for TensoRF: pass the lr INDEX as the value to learn which
+        # learning rate each optimizer group uses
+        groups = [{"params": list(g["params"]), "lr": g["lr"]} for g in model.get_params(*[float(i) for i in range(n_lr)])]
         self.params = [p for g in groups for p in g["params"]]
+        self.lr_index = {id(p): int(g["lr"]) for g in groups for p in g["params"]}
         dev = self.params[0].device
         self.numel = sum(p.numel() for p in self.params)
         n = (self.numel + 7) // 8 * 8
@@ -36,9 +39,15 @@ class ParamArena:
         off = 0
         for p in self.params:
             k = p.numel()
-            self.flat[off:off + k].copy_(p.data.reshape(-1))
-            p.data = self.flat[off:off + k].view_as(p.data)
-            p.grad = self.grad[off:off + k].view_as(p.data)
+            # keep the parameter's physical layout (TensoRF factors are channels_last): view the segment in stride order
+            perm = sorted(range(p.dim()), key=lambda i: (p.shape[i] != 1, -p.stride(i), i))
+            inv = [perm.index(i) for i in range(p.dim())]
+            phys = p.data.permute(perm)
+            if not phys.is_contiguous():
+                raise ValueError("parameter with overlapping / non-dense strides cannot live in the arena")
+            self.flat[off:off + k].view(phys.shape).copy_(phys)
+            p.data = self.flat[off:off + k].view(phys.shape).permute(inv)
+            p.grad = self.grad[off:off + k].view(phys.shape).permute(inv)
             self.offsets[id(p)] = (off, k)
             off += k
         if self.shadow is not None:
@@ -55,20 +64,23 @@ class ParamArena:
     def adam_step(self, lr, beta1=0.9, beta2=0.99, eps=1e-15, grad_scale=1.0, only=None):
         """torch.optim.Adam(betas=(0.9,0.99), eps=1e-15) semantics (main_SealNeRF.py:283-284); zeroes the gradients.
         `only` restricts the update to a set of parameters (pretraining freezes the MLPs, trainer.py:472-488); every
-        parameter keeps its own step count for the bias correction, like torch does."""
+        parameter keeps its own step count for the bias correction, like torch does.  `lr` is one value or one per
+        learning-rate slot of get_params (TensoRF: factors, MLPs)."""
+        lrs = [float(v) for v in lr] if isinstance(lr, (tuple, list)) else None
         active = []
         for p in self.params:
             if only is not None and id(p) not in only:
                 continue
             off, k = self.offsets[id(p)]
             self.steps[id(p)] = self.steps.get(id(p), 0) + 1
-            if active and active[-1][0] + active[-1][1] == off and active[-1][2] == self.steps[id(p)]:
-                active[-1] = (active[-1][0], active[-1][1] + k, active[-1][2])
+            plr = lrs[self.lr_index[id(p)]] if lrs is not None else float(lr)
+            if active and active[-1][0] + active[-1][1] == off and active[-1][2] == self.steps[id(p)] and active[-1][3] == plr:
+                active[-1] = (active[-1][0], active[-1][1] + k, active[-1][2], plr)
             else:
-                active.append((off, k, self.steps[id(p)]))
-        for off, k, st in active:
+                active.append((off, k, self.steps[id(p)], plr))
+        for off, k, st, plr in active:
             _lib.call("s3d_adam_step", self.flat[off:], self.grad[off:], self.exp_avg[off:], self.exp_avg_sq[off:],
-                      self.shadow[off:] if self.shadow is not None else None, k, float(lr), beta1, beta2, eps,
+                      self.shadow[off:] if self.shadow is not None else None, k, plr, beta1, beta2, eps,
                       st, float(grad_scale), 1, 0, None)
         if only is not None:
             self.grad.zero_()
@@ -82,11 +94,13 @@ class DistillTrainer:
         self.precision, self.loss_scale = precision, float(loss_scale)
         self.world_size = world_size
         self.update_interval = update_interval
-        self.arena = ParamArena(student, with_half_shadow=(precision == "fp16"))
+        self.arena = ParamArena(student, with_half_shadow=(precision == "fp16"), n_lr=len(lr) if isinstance(lr, (tuple, list)) else 1)
         dev = self.arena.flat.device
         self.loss_buf = torch.zeros(2, dtype=torch.float32, device=dev)
         self.global_step = 0
-        self._tables_only = {id(student.encoder.embeddings), id(student.encoder_color.embeddings)}
+        # pretraining freezes the NGP MLPs (SealNeRF/trainer.py:472-488 freeze_mlp); for TensoRF nothing is frozen (:476-483)
+        self._tables_only = ({id(student.encoder.embeddings), id(student.encoder_color.embeddings)}
+                             if hasattr(student, "encoder_color") else None)
 
     # -- helpers ------------------------------------------------------------------------------
     def _autocast(self):

@@ -224,3 +224,48 @@ def test_brush_anchor_texture_vs_reference_code():
     out = oracle.seal_map_color_image(g["tex_points"], g["tex_colors"], g["tex_image"], g["tex_alpha"], g["tex_norm"], g["tex_o"], g["tex_w"],
                                       g["tex_h"], float(g["tex_light"]))
     np.testing.assert_allclose(out, g["tex_out"], rtol=1e-5, atol=2e-6)
+
+
+# ---- TensoRF VM field ------------------------------------------------------------------------------
+
+def _tensorf_from_golden(g, prefix="", aabb=(-1, -1, -1, 1, 1, 1)):
+    return oracle.TensoRFField([g["%ssigma_mat%d" % (prefix, i)] for i in range(3)], [g["%ssigma_vec%d" % (prefix, i)] for i in range(3)],
+                               [g["%scolor_mat%d" % (prefix, i)] for i in range(3)], [g["%scolor_vec%d" % (prefix, i)] for i in range(3)],
+                               g["basis_mat"], [g["color_net%d" % l] for l in range(3)], aabb=aabb)
+
+
+@pytest.mark.parametrize("tag", ["", "shrunk_"])
+def test_tensorf_field_matches_reference_network(tag):
+    """oracle restatement of grid_sample-based get_sigma_feat / get_color_feat / forward and their autograd gradients vs the
+    reference's own tensoRF/network.py::NeRFNetwork run on CPU torch (tests/golden/make_tensorf_golden.py)"""
+    g = load("cpu_tensorf.npz")
+    aabb = g["aabb_shrunk"] if tag else np.array([-1, -1, -1, 1, 1, 1], np.float32)
+    f = _tensorf_from_golden(g, aabb=aabb)
+    x, d = g["x"], g["d"]
+    np.testing.assert_allclose(oracle.vm_forward(x, f.sm, f.sv, True, aabb), g[tag + "sigma_feat"], rtol=1e-5, atol=1e-6)
+    prod = oracle.vm_forward(x, f.cm, f.cv, False, aabb)
+    np.testing.assert_allclose(prod @ g["basis_mat"].T, g[tag + "color_feat"], rtol=1e-4, atol=1e-6)
+    sigma, rgb = f.forward(x, d, keep=True)
+    np.testing.assert_allclose(sigma, g[tag + "sigma"], rtol=1e-5, atol=1e-6)
+    # the CUDA freqencoder evaluates cos as sin(x + pi/2) in float32 (freqencoder.cu:56-58); the golden used torch.cos
+    np.testing.assert_allclose(rgb, g[tag + "rgb"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(rgb[::3], g[tag + "color_masked"][::3], rtol=1e-5, atol=2e-6)
+    assert not g[tag + "color_masked"][1::3].any()
+    gr = f.backward(g[tag + "g_sigma"], g[tag + "g_rgb"])
+    for i in range(3):
+        for name in ("sigma_mat", "sigma_vec", "color_mat", "color_vec"):
+            ref = g["%sgrad_%s%d" % (tag, name, i)]
+            got = gr[name][i].reshape(ref.shape)
+            np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-5 * max(1.0, np.abs(ref).max()), err_msg="%s%d" % (name, i))
+    np.testing.assert_allclose(gr["basis_mat"], g[tag + "grad_basis_mat"], rtol=1e-4, atol=1e-5)
+    for l in range(3):
+        ref = g["%sgrad_color_net%d" % (tag, l)]
+        np.testing.assert_allclose(gr["color_net"][l], ref, rtol=1e-4, atol=1e-5 * max(1.0, np.abs(ref).max()))
+
+
+def test_tensorf_out_of_box_points_read_zero_padding():
+    g = load("cpu_tensorf.npz")
+    f = _tensorf_from_golden(g)
+    far = np.array([[1.5, 0.0, 0.0], [0.0, -1.7, 0.2], [3.0, 3.0, 3.0]], np.float32)
+    assert not oracle.vm_forward(far, f.sm, f.sv, True).any()            # a plane or its line is out of range in every term
+    assert not oracle.vm_forward(far[2:], f.cm, f.cv, False).any()
