@@ -313,3 +313,73 @@ def test_param_ema_and_dynamic_scale_trainer(scene):
             assert all(torch.equal(x, y) for x, y in zip(tr.S.param_tensors(), w0))
     assert np.isfinite(losses["dynamic"]).all() and losses["dynamic"][-1, 0] < losses["dynamic"][0, 0]
     np.testing.assert_allclose(losses["dynamic"][:4], losses["static"][:4], rtol=5e-2, atol=1e-7)   # same scale for the first 4 steps
+
+
+@pytest.mark.parametrize("engine", ["fused", "autograd"])
+def test_full_checkpoint_resumes_training_and_is_a_torch_adam_state(engine, tmp_path, scene):
+    """nerf/utils.py:1015-1136 with full=True: optimizer / scheduler / EMA / scaler state survive a save + load into a fresh
+    trainer (the resumed steps follow the uninterrupted run), and the optimizer entry is a genuine torch.optim.Adam state
+    dict: torch's own Adam loads it and its next step equals ours"""
+    from seal3d_b200 import checkpoint as ck, synth
+    from seal3d_b200.fused import FusedDistillTrainer
+    from seal3d_b200.trainer import DistillTrainer
+
+    import copy
+
+    def make():
+        teacher, student, _, _ = _networks(scene)
+        if engine == "fused":
+            return FusedDistillTrainer(student, teacher, lr=1e-2, update_interval=0, lr_decay_iters=100, ema_decay=0.95)
+        return DistillTrainer(student, teacher, lr=1e-2, update_interval=0)
+
+    def step(tr, i):
+        o, d = synth.rays_for_step(i, 2048)
+        return npy(tr.distill_step(to(o), to(d), perturb=False, force_all_rays=True)).copy()
+
+    a = make()
+    for i in range(3):
+        step(a, i)
+    if engine == "fused":
+        a.ema_update()
+    path = str(tmp_path / "run_ep0001.pth")
+    ck.save_checkpoint(path, a, epoch=1, full=True)
+    raw = torch.load(path, weights_only=False)
+    assert raw["global_step"] == 3 and set(raw["optimizer"]) == {"state", "param_groups"}
+    assert [g["params"] for g in raw["optimizer"]["param_groups"]] == [[0], [1, 2], [3], [], [4, 5, 6]]
+    assert float(raw["optimizer"]["state"][0]["step"]) == 3.0 and tuple(raw["optimizer"]["state"][3]["exp_avg_sq"].shape) == (6119864, 2)
+    if engine == "fused":
+        assert raw["ema"]["num_updates"] == 1 and len(raw["ema"]["shadow_params"]) == 7 and raw["lr_scheduler"]["last_epoch"] == 3
+    # torch's Adam accepts the state (clones of the parameters at the time of the save)
+    lr_now = a.current_lr() if engine == "fused" else a.lr
+    groups = [{"params": [p.detach().clone().requires_grad_() for p in g["params"]], "lr": g["lr"]} for g in a.student.get_params(lr_now)]
+    opt = torch.optim.Adam(groups, betas=(0.9, 0.99), eps=1e-15)
+    opt.load_state_dict(raw["optimizer"])
+    assert abs(opt.param_groups[0]["lr"] - lr_now) < 1e-12
+    cont = [step(a, 3), step(a, 4)]
+    b = make()
+    ck.load_checkpoint(path, b)
+    assert b.global_step == 3
+    if engine == "fused":
+        assert b.ema.num_updates == 1 and torch.equal(b.ema.shadow[0], a.ema.shadow[0])     # a's EMA has not moved since the save
+        assert b.S.step_tables == 3 and b.S.step_mlp == 3
+    else:
+        assert set(b.arena.steps.values()) == {3}
+    resumed = [step(b, 3), step(b, 4)]
+    # float atomics in the scatter make runs differ in the last bits only
+    np.testing.assert_allclose(np.array(resumed), np.array(cont), rtol=2e-3, atol=1e-9)
+    np.testing.assert_allclose(npy(b.student.encoder.embeddings), npy(a.student.encoder.embeddings), rtol=0, atol=2e-4)
+    # ... and continues it exactly like our Adam kernel: same gradients into both, one step each
+    c = make()
+    ck.load_checkpoint(path, c)
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    mine = [p for g in c.student.get_params(lr_now) for p in g["params"]]
+    theirs = [p for g in groups for p in g["params"]]
+    if engine == "autograd":
+        for p, q in zip(mine, theirs):
+            gr = (torch.randn(p.shape, generator=gen) * 1e-3).to(p.device)
+            p.grad.copy_(gr)
+            q.grad = gr.clone()
+        c.arena.adam_step(lr_now)
+        opt.step()
+        for p, q in zip(mine, theirs):
+            np.testing.assert_allclose(npy(p), npy(q), rtol=1e-5, atol=1e-7)

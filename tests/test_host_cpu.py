@@ -142,3 +142,36 @@ def test_data_parallel_gradient_equals_single_process_gloo():
         p.join(60)
         assert p.exitcode == 0
     assert err <= 1e-5 * scale and t == 2.0
+
+
+def test_checkpoint_model_roundtrip_in_reference_format(tmp_path):
+    """nerf/utils.py:1015-1136: dict layout, keys of SURVEY appendix B, latest-checkpoint lookup, bare state dicts;
+    TensoRF factors are written contiguous in the reference shape and land in channels_last storage, at the file's resolution"""
+    import torch
+    from seal3d_b200 import checkpoint as ck
+    from seal3d_b200.seal import StudentNetwork, TensoRFStudentNetwork
+    m = StudentNetwork(bound=1)
+    m.mean_count, m.mean_density = 4321, 0.25
+    ck.save_checkpoint(str(tmp_path / "ngp_ep0002.pth"), model=m, epoch=2)
+    ck.save_checkpoint(str(tmp_path / "ngp_ep0010.pth"), model=m, epoch=10)
+    assert ck.latest_checkpoint(str(tmp_path), "ngp").endswith("ngp_ep0010.pth")
+    raw = torch.load(str(tmp_path / "ngp_ep0010.pth"), weights_only=False)
+    assert {"epoch", "global_step", "stats", "mean_count", "mean_density", "model"} <= set(raw) and "optimizer" not in raw
+    assert tuple(raw["model"]["encoder.embeddings"].shape) == (6119864, 2) and tuple(raw["model"]["color_net.0.weight"].shape) == (64, 63)
+    assert raw["model"]["encoder.offsets"].tolist()[:3] == [0, 4920, 18744] and tuple(raw["model"]["density_bitfield"].shape) == (262144,)
+    m2 = StudentNetwork(bound=1)
+    missing, unexpected, _ = ck.load_checkpoint(str(tmp_path / "ngp_ep0010.pth"), model=m2)
+    assert not missing and not unexpected and m2.mean_count == 4321 and m2.mean_density == 0.25
+    assert torch.equal(m2.encoder_color.embeddings, m.encoder_color.embeddings)
+    torch.save(raw["model"], str(tmp_path / "bare.pth"))                    # a bare state dict loads too (:1082-1085)
+    m3 = StudentNetwork(bound=1)
+    ck.load_checkpoint(str(tmp_path / "bare.pth"), model=m3)
+    assert torch.equal(m3.sigma_net[1].weight, m.sigma_net[1].weight)
+    t = TensoRFStudentNetwork(resolution=[12, 14, 16])
+    ck.save_checkpoint(str(tmp_path / "t.pth"), model=t)
+    saved = torch.load(str(tmp_path / "t.pth"), weights_only=False)["model"]
+    assert tuple(saved["color_mat.0"].shape) == (1, 48, 14, 12) and saved["color_mat.0"].is_contiguous()
+    t2 = TensoRFStudentNetwork(resolution=[8, 8, 8])                        # e.g. a shrunk / upsampled checkpoint
+    ck.load_checkpoint(str(tmp_path / "t.pth"), model=t2)
+    assert t2.resolution == [12, 14, 16] and t2.color_mat[0].stride() == (14 * 12 * 48, 1, 12 * 48, 48)
+    assert torch.equal(t2.color_mat[0], t.color_mat[0]) and torch.equal(t2.sigma_vec[2], t.sigma_vec[2])
