@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=1024, help="rays per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true", help="march every batch inline instead of one step ahead on a side stream")
     return ap.parse_args()
 
 
@@ -341,11 +342,16 @@ def gpu_arm(args):
         torch.cuda.synchronize()
 
     # warm-up (first steps run in exact mode and set mean_count)
+    pipelined = args.engine == "fused" and not args.no_prefetch
     for i in range(args.warmup):
         o, d = resident[i % pool]
         tr.distill_step(o, d, perturb=True, force_all_rays=(i < 2))
     if tr.student.mean_count <= 0:
         tr.refresh_occupancy()
+    if pipelined:   # the side stream, its allocator pool and the pinned-copy path are created on first use: outside the timed legs
+        for src in (resident, host):
+            for i in range(3):
+                tr.distill_step(*src[i % pool], perturb=True, prefetch=src[(i + 1) % pool] if i < 2 else None)
     samples_per_step = float(tr.student.step_counter[:, 0].float().max().item())
 
     # -- leg 1: resident inputs ---------------------------------------------------------------
@@ -356,7 +362,10 @@ def gpu_arm(args):
     e0.record()
     for i in range(args.steps):
         o, d = resident[i % pool]
-        tr.distill_step(o, d, perturb=True)
+        if pipelined:   # the next batch is marched on a side stream under this step's field kernels (fused.py: _prefetch)
+            tr.distill_step(o, d, perturb=True, prefetch=resident[(i + 1) % pool] if i + 1 < args.steps else None)
+        else:
+            tr.distill_step(o, d, perturb=True)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -370,8 +379,11 @@ def gpu_arm(args):
     last = None
     for i in range(args.steps):
         ho, hd = host[i % pool]
-        o, d = ho.to(dev, non_blocking=True), hd.to(dev, non_blocking=True)
-        last = tr.distill_step(o, d, perturb=True).cpu()
+        if pipelined:   # pinned host buffers go in as they are: this step's copy + march were issued during the previous step
+            last = tr.distill_step(ho, hd, perturb=True, prefetch=host[(i + 1) % pool] if i + 1 < args.steps else None).cpu()
+        else:
+            o, d = ho.to(dev, non_blocking=True), hd.to(dev, non_blocking=True)
+            last = tr.distill_step(o, d, perturb=True).cpu()
     e1.record()
     barrier()
     ms_e2e = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
@@ -402,7 +414,7 @@ def gpu_arm(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "global_rays_per_step": n * world, "samples_per_step_per_gpu": samples_per_step,
                    "samples_per_ray": samples_per_step / n, "parallelism": "dp%d (ray shards, one grad all-reduce/step)" % world,
-                   "schedule": "fused teacher+student on shared samples; occupancy refresh every 16 steps",
+                   "schedule": "fused teacher+student on shared samples; occupancy refresh every 16 steps" + ("; next batch marched on a side stream under the current step" if pipelined else ""),
                    "l2_note": "each step streams > 126 MB (samples + 4 tables + arena) so successive steps do not reuse L2 contents"},
         "e2e": {"value": rays_total / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(getattr(_lib, "LAUNCHES", 0) - launches0) if hasattr(_lib, "LAUNCHES") else None,

@@ -135,13 +135,15 @@ class FusedNGP:
         return {"sigma": sigma / self.density_scale, "geo_feat": geo}
 
     # -- backward / optimizer ---------------------------------------------------------------------
-    def backward(self, xyz, dirs, feats, g_sigma, g_rgb, loss_scale=1.0, train_mlp=True):
-        """accumulates loss_scale * dL/dparams into the gradient arena"""
+    def backward(self, xyz, dirs, feats, g_sigma, g_rgb, loss_scale=1.0, train_mlp=True, before_scatter=None):
+        """accumulates loss_scale * dL/dparams into the gradient arena; `before_scatter()` is called between the two launches"""
         M = feats.shape[0]
         dfeats = torch.empty(M, 64, dtype=torch.float16, device=self.dev)
         w, gw = self._w16(), self._gw()
         _lib.call("s3d_ngp_mlp_backward", feats, dirs, M, w[0], w[1], w[2], w[3], w[4], self.density_scale, g_sigma, g_rgb, dfeats,
                   1.0, gw[0], gw[1], gw[2], gw[3], gw[4], int(train_mlp))
+        if before_scatter is not None:
+            before_scatter()
         _lib.call("s3d_ngp_scatter", xyz, dfeats, M, self.bound, self.grad4, self.offsets, self.L, self.S, self.H, 1.0)
 
     def adam_step(self, lr, grad_scale=1.0, beta1=0.9, beta2=0.99, eps=1e-15, train_mlp=True, scaler_state=None, lr_mlp=None):
@@ -237,6 +239,8 @@ class FusedDistillTrainer:
         self.loss_buf = torch.zeros(2, dtype=torch.float32, device=self.S.dev)
         self.global_step = 0
         self.table8 = None
+        self._side, self._pref = None, None     # side stream + the pre-marched next batch (see _prefetch)
+        self._cur = self._old = None            # pre-marched tensors in use by this / the previous step (kept alive, see _prefetch)
         self.lr_decay_iters = lr_decay_iters
         self.scaler = GradScalerState(self.S.dev, **(scaler_kwargs or {})) if loss_scale == "dynamic" else None
         self.ema = ParamEMA(self.S.param_tensors(), ema_decay) if ema_decay is not None else None
@@ -304,6 +308,49 @@ class FusedDistillTrainer:
         return raymarching.march_rays_train(rays_o, rays_d, s.bound, s.density_bitfield, s.cascade, s.grid_size, nears, fars, counter,
                                             s.mean_count, perturb, 128, force_all_rays, self.dt_gamma, self.max_steps)
 
+    # -- software pipelining of the marcher ---------------------------------------------------------------------
+    # Marching depends on the rays and the occupancy bitfield only, not on the parameters, so the samples of step n+1 can be
+    # generated while step n's gradient scatter and Adam run: the marcher is latency-bound (divergent per-ray DDA), the scatter
+    # is bound by L2 atomics, and they share the SMs well.  (Under the persistent MLP kernels it does not pay: their static
+    # tile schedule turns any SM the marcher delays into the kernel's tail -- measured, profiles/r1d_experiments.md.)  `prefetch=(rays_o, rays_d)` on a step hands the NEXT
+    # batch (device tensors or pinned host tensors; host tensors are copied on the side stream too) to a second stream.
+    # The pre-marched batch is used when the next call passes the same tensor objects.  Nothing is pre-marched across an
+    # occupancy refresh, so every march sees exactly the bitfield it would have seen without pipelining.
+    def _prefetch(self, rays, perturb, force_all_rays):
+        if rays is None or (self.update_interval and (self.global_step + 1) % self.update_interval == 0):
+            return
+        ro, rd = rays
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.S.dev)
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)        # ordered after everything issued so far (bitfield updates, the previous march)
+        # Tensors marched on the side stream live in its allocator pool.  They are kept referenced until the side stream has
+        # waited for the whole step that consumed them, then dropped -- so the pool can only hand their memory to a march
+        # that is ordered after their last reader, without record_stream (whose deferred frees make a host that runs ahead
+        # of the GPU allocate fresh memory every step).
+        self._old, self._cur = self._cur, None
+        with torch.cuda.stream(self._side):
+            o = ro.to(self.S.dev, non_blocking=True).view(-1, 3)
+            d = rd.to(self.S.dev, non_blocking=True).view(-1, 3)
+            res = self._march(o, d, perturb, force_all_rays)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        self._pref = (ro, rd, o, d, res, ev)
+
+    def _march_or_take(self, rays_o, rays_d, perturb, force_all_rays):
+        """-> device rays_o, rays_d and the march result, from the pre-marched batch if this is the batch that was handed in"""
+        pref, self._pref = self._pref, None
+        if pref is not None and pref[0] is rays_o and pref[1] is rays_d:
+            _, _, o, d, res, ev = pref
+            torch.cuda.current_stream().wait_event(ev)
+            self._cur = (o, d, res)
+            return o, d, res
+        if pref is not None:       # a different batch arrived: the pre-marched one is dropped, its ring slot is simply overwritten later
+            torch.cuda.current_stream().wait_event(pref[5])
+        o = rays_o.to(self.S.dev, non_blocking=True).view(-1, 3)
+        d = rays_d.to(self.S.dev, non_blocking=True).view(-1, 3)
+        return o, d, self._march(o, d, perturb, force_all_rays)
+
     def _composite(self, sigmas, rgbs, deltas, rays):
         M, N = sigmas.shape[0], rays.shape[0]
         dev = sigmas.device
@@ -313,7 +360,7 @@ class FusedDistillTrainer:
         _lib.call("s3d_composite_rays_train_forward", sigmas, rgbs, deltas, rays, M, N, float(self.T_thresh), ws, depth, image)
         return ws, depth, image
 
-    def _student_backward(self, xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, image_t, depth_t):
+    def _student_backward(self, xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, image_t, depth_t, before_scatter=None):
         M, N = sig_s.shape[0], rays.shape[0]
         dev = sig_s.device
         ws, depth, comp = self._composite(sig_s, rgb_s, deltas, rays)
@@ -327,7 +374,7 @@ class FusedDistillTrainer:
         g_sig = torch.zeros(M, dtype=torch.float32, device=dev)
         g_rgb = torch.zeros(M, 3, dtype=torch.float32, device=dev)
         _lib.call("s3d_composite_rays_train_backward", g_ws, g_img, sig_s, rgb_s, deltas, rays, ws, comp, M, N, float(self.T_thresh), g_sig, g_rgb)
-        self.S.backward(xyzs, dirs, feats, g_sig, g_rgb)
+        self.S.backward(xyzs, dirs, feats, g_sig, g_rgb, before_scatter=before_scatter)
         return self.loss_buf, scale
 
     def _teacher_composite(self, mx, md, mask, feats_t, deltas, rays):
@@ -346,10 +393,11 @@ class FusedDistillTrainer:
         return self._teacher_composite(mx, md.contiguous().float(), mask, feats_t, deltas, rays)
 
     @torch.no_grad()
-    def distill_step(self, rays_o, rays_d, perturb=True, force_all_rays=False):
+    def distill_step(self, rays_o, rays_d, perturb=True, force_all_rays=False, prefetch=None):
+        """prefetch = (rays_o, rays_d) of the NEXT step (optional): marched on a side stream under this step's kernels"""
         self._maybe_update_grid()
-        rays_o, rays_d = rays_o.view(-1, 3), rays_d.view(-1, 3)
-        xyzs, dirs, deltas, rays = self._march(rays_o, rays_d, perturb, force_all_rays)
+        rays_o, rays_d, (xyzs, dirs, deltas, rays) = self._march_or_take(rays_o, rays_d, perturb, force_all_rays)
+        ahead = (lambda: self._prefetch(prefetch, perturb, force_all_rays)) if prefetch is not None else None
         if self.table8 is not None:
             # one gather pass for both models (moved samples take a second gather for the teacher)
             M = xyzs.shape[0]
@@ -364,17 +412,17 @@ class FusedDistillTrainer:
         else:
             img_t, depth_t = self.teacher_targets(xyzs, dirs, deltas, rays)
             sig_s, rgb_s, feats = self.S.forward(xyzs, dirs)
-        loss, scale = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, img_t, depth_t)
+        loss, scale = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, img_t, depth_t, before_scatter=ahead)
         self._reduce_and_step(scale)
         return loss
 
     @torch.no_grad()
-    def finetune_step(self, rays_o, rays_d, image_t, depth_t=None, perturb=True, force_all_rays=False):
+    def finetune_step(self, rays_o, rays_d, image_t, depth_t=None, perturb=True, force_all_rays=False, prefetch=None):
         self._maybe_update_grid()
-        rays_o, rays_d = rays_o.view(-1, 3), rays_d.view(-1, 3)
-        xyzs, dirs, deltas, rays = self._march(rays_o, rays_d, perturb, force_all_rays)
+        rays_o, rays_d, (xyzs, dirs, deltas, rays) = self._march_or_take(rays_o, rays_d, perturb, force_all_rays)
+        ahead = (lambda: self._prefetch(prefetch, perturb, force_all_rays)) if prefetch is not None else None
         sig_s, rgb_s, feats = self.S.forward(xyzs, dirs)
-        loss, scale = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, image_t, depth_t)
+        loss, scale = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, image_t, depth_t, before_scatter=ahead)
         self._reduce_and_step(scale)
         return loss
 
@@ -401,6 +449,9 @@ class FusedDistillTrainer:
     @torch.no_grad()
     def refresh_occupancy(self, seed=None):
         seed = 1234 + self.global_step if seed is None else seed
+        if self._pref is not None:      # a batch pre-marched on the old bitfield is dropped
+            torch.cuda.current_stream().wait_event(self._pref[5])
+            self._pref = None
         orig = self.student.density
         self.student.density = self.S.density
         try:

@@ -383,3 +383,31 @@ def test_full_checkpoint_resumes_training_and_is_a_torch_adam_state(engine, tmp_
         opt.step()
         for p, q in zip(mine, theirs):
             np.testing.assert_allclose(npy(p), npy(q), rtol=1e-5, atol=1e-7)
+
+
+def test_marching_one_step_ahead_changes_nothing(scene):
+    """the pipelined schedule (next batch marched on a side stream, pinned host rays copied there too) produces the losses
+    and parameters of the inline schedule; no batch is pre-marched across an occupancy refresh"""
+    from seal3d_b200 import synth
+    from seal3d_b200.fused import FusedDistillTrainer
+    batches = [synth.rays_for_step(i, 4096) for i in range(7)]
+    host = [(torch.from_numpy(o).pin_memory(), torch.from_numpy(d).pin_memory()) for o, d in batches]
+    runs = []
+    for mode in ("inline", "ahead"):
+        t, s, _, _ = _networks(scene)
+        tr = FusedDistillTrainer(s, t, lr=1e-2, update_interval=4)
+        losses, took = [], []
+        for i, (o, d) in enumerate(host):
+            nxt = host[i + 1] if (mode == "ahead" and i + 1 < len(host)) else None
+            if mode == "ahead":
+                took.append(tr._pref is not None)
+                losses.append(npy(tr.distill_step(o, d, perturb=False, force_all_rays=(i < 2), prefetch=nxt)).copy())
+            else:
+                losses.append(npy(tr.distill_step(to(batches[i][0]), to(batches[i][1]), perturb=False, force_all_rays=(i < 2))).copy())
+        if mode == "ahead":
+            # steps 4 refreshes the occupancy grid (global_step % 4 == 0): its batch must not have been marched during step 3
+            assert took == [False, True, True, True, False, True, True], took
+        runs.append((np.array(losses), npy(s.encoder.embeddings).copy(), s.mean_count))
+    np.testing.assert_allclose(runs[1][0], runs[0][0], rtol=2e-3, atol=1e-9)      # float atomics: last-bit differences only
+    # (parameters are not compared entry by entry: Adam turns last-bit gradient differences of never-hit entries into +-lr steps)
+    assert runs[0][2] == runs[1][2] and runs[0][2] > 0
