@@ -11,7 +11,7 @@ import pytest
 import torch
 
 import oracle
-from test_gpu_parity import dev, to, npy, scene, _samples, _networks, scaled  # noqa: F401
+from test_gpu_parity import dev, to, npy, scene, _samples, _networks, scaled, rm  # noqa: F401
 
 pytestmark = pytest.mark.gpu
 
@@ -411,3 +411,47 @@ def test_marching_one_step_ahead_changes_nothing(scene):
     np.testing.assert_allclose(runs[1][0], runs[0][0], rtol=2e-3, atol=1e-9)      # float atomics: last-bit differences only
     # (parameters are not compared entry by entry: Adam turns last-bit gradient differences of never-hit entries into +-lr steps)
     assert runs[0][2] == runs[1][2] and runs[0][2] > 0
+
+
+@pytest.mark.parametrize("engine", ["fused", "autograd"])
+def test_seal_student_schedule_config3_in_miniature(engine, scene):
+    """BASELINE config 3 (pretraining epochs, then fine-tuning on the teacher's proxied views) at reduced size through
+    schedule.SealStudentSchedule: the cached sets obey the reference's selection rules, the pretraining loss falls with the
+    forced learning rate, fine-tuning brings the student's render of a view closer to the teacher's, timers are recorded"""
+    from seal3d_b200 import synth
+    from seal3d_b200.fused import FusedDistillTrainer
+    from seal3d_b200.trainer import DistillTrainer
+    from seal3d_b200.schedule import SealStudentSchedule
+    t, s, md, tris = _networks(scene, hsv=[0.3, 0.0, 0.0])
+    tr = FusedDistillTrainer(s, t, lr=1e-2, update_interval=16) if engine == "fused" else DistillTrainer(s, t, lr=1e-2, update_interval=16)
+    sch = SealStudentSchedule(tr, num_rays=4096, consistent_depth=True)
+    sch.init_pretraining(epochs=6, batch_size=1 << 16, lr=0.05, local_point_step=0.01, surrounding_point_step=0.03,
+                         surrounding_bounds_extend=0.1)
+    loc, sur = sch.pretraining_data["local"], sch.pretraining_data["surrounding"]
+    mapper = t.seal_mapper
+    assert loc["points"].shape[0] > 1000 and mapper.map_mask(loc["points"]).all()          # only points the edit moves
+    assert sur["points"].shape[0] > 1000 and not mapper.map_mask(sur["points"]).any()      # only points it does not touch
+    assert loc["steps"][0] == 0 and loc["steps"][-1] == loc["points"].shape[0] and loc["sigma"].shape[0] == loc["points"].shape[0]
+    assert torch.allclose(loc["dirs"].norm(dim=-1), torch.full_like(loc["dirs"][:, 0], 1 - 1e-5), atol=1e-6)
+    # the proxied training views: a 100 x 100 pixel lattice of 5 synthetic poses
+    pix = (np.arange(4, 800, 8)[:, None] * 800 + np.arange(4, 800, 8)[None, :]).reshape(-1)
+    poses = synth.poses()[:5]
+    rays_of_view = lambda pose: synth.rays_from_pixels(pose, pix)
+    images, depths = sch.proxy_dataset(poses, rays_of_view)
+    assert images.shape == (5, pix.shape[0], 3) and depths.shape == (5, pix.shape[0]) and torch.isfinite(images).all()
+    # the reference's own convention (eval depth = distance from the origin) differs by near * weights_sum
+    ref_sch = SealStudentSchedule(tr, num_rays=4096)
+    _, ref_depths = ref_sch.proxy_dataset(poses[:1], rays_of_view)
+    hit = depths[0] > 0
+    assert hit.sum() > 100 and (ref_depths[0] >= depths[0] - 1e-5).all() and float((ref_depths[0][hit] - depths[0][hit]).mean()) > 0.2
+
+    hist = sch.train(max_epochs=6 + 20)
+    pre = [v for k, v in hist if k == "pretrain"]
+    fin = np.array([v for k, v in hist if k == "train"])
+    assert len(pre) == 6 and len(fin) == 20 and not sch.is_pretraining
+    assert pre[-1] < 0.8 * pre[0], pre                            # the forced pretraining rate is in effect
+    assert tr.lr == 1e-2                                          # ... and set_lr(-1) restored the fine-tuning rate
+    # per-epoch [MSE, L1(depth)]: the photometric term falls; the depth term is reported but has no gradient (the
+    # compositor's backward drops grad_depth, raymarching.py:271-288), so it is only required to stay finite
+    assert np.isfinite(fin).all() and fin[-3:, 0].mean() < 0.5 * fin[:3, 0].mean(), fin
+    assert len(sch.timer["pretraining"]) == 6 and len(sch.timer["training"]) == 20 and sch.timer["proxy_dataset"] > 0

@@ -175,3 +175,25 @@ def test_checkpoint_model_roundtrip_in_reference_format(tmp_path):
     ck.load_checkpoint(str(tmp_path / "t.pth"), model=t2)
     assert t2.resolution == [12, 14, 16] and t2.color_mat[0].stride() == (14 * 12 * 48, 1, 12 * 48, 48)
     assert torch.equal(t2.color_mat[0], t.color_mat[0]) and torch.equal(t2.sigma_vec[2], t.sigma_vec[2])
+
+
+def test_pretraining_lattice_and_euler_directions_match_scipy():
+    """schedule.sample_points vs the reference's recipe (SealNeRF/trainer.py:609-635): torch.arange lattice per box and
+    scipy's Rotation.from_euler('xyz', grid, degrees=True).apply([1 - 1e-5, 0, 0]) -- scipy is what the reference calls"""
+    import numpy as np
+    import torch
+    from scipy.spatial.transform import Rotation
+    from seal3d_b200.schedule import sample_points
+    bounds = np.array([[[0.0, -0.1, 0.2], [0.031, -0.05, 0.26]], [[0.5, 0.5, 0.5], [0.52, 0.53, 0.51]]], np.float32)
+    pts, dirs = sample_points(bounds, 0.01, 90)
+    want = []
+    for lo, hi in bounds:
+        X, Y, Z = torch.meshgrid(*[torch.arange(float(lo[d]), float(hi[d]), step=0.01) for d in range(3)], indexing="ij")
+        want.append(torch.stack([X, Y, Z], -1).reshape(-1, 3))
+    assert torch.equal(pts, torch.cat(want).float()) and pts.shape[0] == 4 * 5 * 6 + 2 * 3 * 1
+    a = np.arange(0, 360, 90)
+    e = np.stack(np.meshgrid(a, a, a, indexing="ij"), -1).reshape(-1, 3)
+    ref = Rotation.from_euler("xyz", e, degrees=True).apply(np.array([1 - 1e-5, 0, 0]))
+    assert dirs.shape == (2 * 64, 3)
+    np.testing.assert_allclose(dirs[:64].numpy(), ref, atol=1e-7)
+    np.testing.assert_allclose(dirs[64:].numpy(), ref, atol=1e-7)
