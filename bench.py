@@ -271,8 +271,16 @@ def roofline_grid_encode(dev, precision):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ach = B * per_pt / t / 1e9
-    return dict(kernel="k_grid_forward<%s,3,2,all-levels>" % ("half" if s_el == 2 else "float"), bound="hbm", achieved=ach, peak=peak,
-                unit="GB/s", frac=ach / peak, traffic=None, peak_source="MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6.65 TB/s",
+    kname = "k_grid_forward<%s,3,2,all-levels>" % ("half" if s_el == 2 else "float")
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if kname in tj:
+            traffic = tj[kname]["dram_bytes_per_sample"] * B
+    except Exception:
+        pass
+    return dict(kernel=kname, bound="hbm", achieved=ach, peak=peak,
+                unit="GB/s", frac=ach / peak, traffic=traffic, peak_source="MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6.65 TB/s",
                 points=B, bytes_per_point=per_pt, launch_ms=t * 1e3)
 
 
@@ -309,6 +317,14 @@ def step_roofline(breakdown, samples_per_step, step_ms):
         per = ALGO_BYTES[name][1]
         ach = samples_per_step * per / (st["ms_per_call"] * 1e-3) / 1e9
         out.update(achieved=ach, frac=ach / peak, bytes_per_sample=per, samples_per_launch=samples_per_step)
+        try:   # DRAM traffic of this kernel from the committed ncu --set full capture, scaled by samples to this launch
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            t = tj.get(ALGO_BYTES[name][0])
+            if t:
+                out.update(traffic=t["dram_bytes_per_sample"] * samples_per_step, traffic_source=tj.get("_source"),
+                           algorithmic_bytes=per * samples_per_step)
+        except Exception:
+            pass
     else:
         out.update(achieved=None, frac=None)
     return out
