@@ -278,8 +278,8 @@ __device__ __forceinline__ void encode_level(const float (&x)[D], const T *__res
 }
 
 // ALL_LEVELS: blockIdx.y unused, thread loops over levels.  Otherwise blockIdx.y = level.
-template <typename T, uint32_t D, uint32_t C, bool ALL_LEVELS, int MINB = 0>
-__global__ void __launch_bounds__(256, MINB)
+template <typename T, uint32_t D, uint32_t C, bool ALL_LEVELS>
+__global__ void __launch_bounds__(256)
 k_grid_forward(const float *__restrict__ inputs, const T *__restrict__ grid, const int *__restrict__ offsets,
                T *__restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, T *__restrict__ dy_dx,
                uint32_t gridtype, bool align_corners, uint32_t interp) {
@@ -479,22 +479,12 @@ __global__ void k_level_scales(uint32_t L, float S, uint32_t H, float *__restric
 // ---- dispatch ----------------------------------------------------------------------------
 
 constexpr uint32_t kBigBatch = 1u << 17;  // from here one thread walks all levels of its point
-int g_variant = 0;   // EXPERIMENT knob
 
 template <typename T, uint32_t D, uint32_t C>
 int launch_forward(const float *inputs, const T *emb, const int *offsets, T *outputs, uint32_t B, uint32_t L, float S,
                    uint32_t H, T *dy_dx, uint32_t gridtype, bool ac, uint32_t interp, cudaStream_t st) {
-    if (B >= kBigBatch && dy_dx == nullptr) {
-        if constexpr (D == 3 && C == 2) {   // EXPERIMENT: occupancy / block-size variants
-            const uint32_t bs = (g_variant & 1) ? 128u : 256u;
-            if ((g_variant >> 1) == 1) { k_grid_forward<T, D, C, true, 5><<<dim3(div_up(B, bs), 1), bs, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac, interp); return (int)cudaPeekAtLastError(); }
-            if ((g_variant >> 1) == 2) { k_grid_forward<T, D, C, true, 6><<<dim3(div_up(B, bs), 1), bs, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac, interp); return (int)cudaPeekAtLastError(); }
-            if ((g_variant >> 1) == 3) { k_grid_forward<T, D, C, true, 8><<<dim3(div_up(B, bs), 1), bs, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac, interp); return (int)cudaPeekAtLastError(); }
-            k_grid_forward<T, D, C, true><<<dim3(div_up(B, bs), 1), bs, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac, interp);
-            return (int)cudaPeekAtLastError();
-        }
+    if (B >= kBigBatch && dy_dx == nullptr)
         k_grid_forward<T, D, C, true><<<dim3(div_up(B, 256u), 1), 256, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac, interp);
-    }
     else
         k_grid_forward<T, D, C, false><<<dim3(div_up(B, 256u), L), 256, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac, interp);
     return (int)cudaPeekAtLastError();
@@ -528,8 +518,6 @@ int launch_backward(const T *grad, const float *inputs, const int *offsets, T *g
     }
 
 }  // namespace
-
-S3D_API void s3d_debug_variant(int which, int value) { if (which == 10) g_variant = value; }   // EXPERIMENT builds only
 
 // the per-level scale exp2f(l*S)*H - 1 exactly as the kernels evaluate it (gridencoder.cu:138 of the reference);
 // diagnostic entry used by the parity tests (see oracle/seal_oracle.c: orc_set_level_scales)
