@@ -18,7 +18,8 @@
  * restatement is pinned against (1) the closed-form SH of testing/test_shencoder.py and the
  * pure-torch proxy/colour functions of SealNeRF/seal_utils.py + color_utils.py, imported in
  * the build container (tests/golden/make_cpu_golden.py), and (2) outputs of the unmodified
- * reference extensions (oracle/_ref) run on the B200 (tests/golden/make_gpu_golden.py).
+ * reference extensions (oracle/_ref) run on the B200 (tests/golden/make_gpu_golden.py -> tests/golden/gpu_ref.npz,
+ * checked on CPU by tests/test_oracle_golden.py).
  *
  * Build: gcc -O2 -fopenmp -ffp-contract=off -fno-fast-math -shared -fPIC seal_oracle.c -lm
  */
@@ -485,7 +486,7 @@ ORC_API void orc_grid_encode_forward(const float *inputs, const float *emb, cons
                         pl[gd] = pg[gd] + 1;
                         const uint32_t ir = grid_index(gridtype, align_corners, D, C, li.hashmap_size, li.resolution, pl);
                         for (uint32_t ch = 0; ch < C; ch++)
-                            rg[ch] += w * (grid[ir + ch] - grid[il + ch]) * (interp == 1 ? pos_deriv[gd] : 1.0f);
+                            rg[ch] += w * (grid[ir + ch] - grid[il + ch]) * pos_deriv[gd];   /* linear: {1,0,0,..}: only d/dx0 is non-zero, like the reference kernel's output (tests/golden/gpu_ref.npz) */
                     }
                     for (uint32_t ch = 0; ch < C; ch++) dd[gd * C + ch] = rg[ch];
                 }

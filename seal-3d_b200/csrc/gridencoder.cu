@@ -171,7 +171,9 @@ __device__ __forceinline__ void locate(const float (&x)[D], const LevelInfo &li,
         const float fl = floorf(p);
         pg[d] = (uint32_t)fl;
         float f = __fsub_rn(p, (float)pg[d]);
-        deriv[d] = 1.0f;
+        // `float pos_deriv[D] = {1.0f}` in the reference (gridencoder.cu:143) sets element 0 only: with linear interpolation
+        // dy_dx is non-zero for the first coordinate alone.  Reproduced (outputs of the reference kernel: tests/golden/gpu_ref.npz).
+        deriv[d] = d == 0 ? 1.0f : 0.0f;
         if (interp == 1) {
             deriv[d] = 6 * f * (1.0f - f);
             f = f * f * (3.0f - 2.0f * f);

@@ -269,3 +269,101 @@ def test_tensorf_out_of_box_points_read_zero_padding():
     far = np.array([[1.5, 0.0, 0.0], [0.0, -1.7, 0.2], [3.0, 3.0, 3.0]], np.float32)
     assert not oracle.vm_forward(far, f.sm, f.sv, True).any()            # a plane or its line is out of range in every term
     assert not oracle.vm_forward(far[2:], f.cm, f.cv, False).any()
+
+
+# ---- the oracle against outputs of the UNMODIFIED reference kernels (tests/golden/gpu_ref.npz) ----------------------
+# Generated on a B200 by tests/golden/make_gpu_golden.py from oracle/_ref/_ref_*.so (the reference's own .cu files,
+# compiled where they lie); inputs are re-created here from the same seeds (tests/golden/gpu_inputs.py).
+
+@pytest.fixture(scope="module")
+def gref():
+    import sys
+    sys.path.insert(0, G)
+    import gpu_inputs
+    return load("gpu_ref.npz"), gpu_inputs
+
+
+def test_oracle_marching_is_bit_exact_with_the_reference_kernels(gref):
+    g, gi = gref
+    sc = gi.scene()
+    nears, fars = oracle.near_far_from_aabb(sc["o"], sc["d"], gi.AABB, 0.2)
+    assert np.array_equal(nears, g["nears"]) and np.array_equal(fars, g["fars"])
+    for tag, nz in (("", None), ("perturb_", sc["noises"])):
+        x, d, l, r, c = oracle.march_rays_train(sc["o"], sc["d"], 1.0, sc["bits"], 1, 128, nears, fars, nz)
+        M = int(c[0])
+        assert np.array_equal(c, g[tag + "march_total"]) and M > 5000
+        assert np.array_equal(r[:, 2], g[tag + "march_counts"])                 # samples per ray
+        assert np.array_equal(x[:M], g[tag + "march_xyzs"])                      # every position, bit for bit (ray-major)
+        assert np.array_equal(l[:M], g[tag + "march_deltas"])
+    # inference marcher: first 8-step iteration of the eval loop
+    N = gi.N_RAYS
+    xi, di, li = oracle.march_rays(N, 8, np.arange(N, dtype=np.int32), nears.copy(), sc["o"], sc["d"], 1.0, sc["bits"], 1, 128, nears, fars, align=128)
+    assert np.array_equal(xi, g["infer_xyzs"]) and np.array_equal(li, g["infer_deltas"])
+    coords, grid = gi.morton_inputs()
+    assert np.array_equal(oracle.morton3D(coords), g["morton"]) and np.array_equal(oracle.morton3D_invert(g["morton"]), g["morton_invert"])
+    assert np.array_equal(g["morton_invert"], coords) and np.array_equal(oracle.packbits(grid, 10.0), g["packbits"])
+
+
+def test_oracle_compositing_matches_the_reference_kernels(gref):
+    g, gi = gref
+    counts = g["march_counts"].astype(np.int32)
+    N, M = counts.shape[0], int(counts.sum())
+    rays = np.stack([np.arange(N, dtype=np.int32), np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int32), counts], 1)
+    fv = gi.field_values(M, N)
+    for T in (1e-4, 0.0):
+        k = "T%g_" % T
+        ws, dp, im = oracle.composite_rays_train_forward(fv["sigmas"], fv["rgbs"], g["march_deltas"], rays, T)
+        np.testing.assert_allclose(ws, g[k + "ws"], rtol=1e-5, atol=1e-6)          # __expf vs expf: a few ulp per term
+        np.testing.assert_allclose(dp, g[k + "depth"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(im, g[k + "image"], rtol=1e-5, atol=1e-6)
+        gs, gc = oracle.composite_rays_train_backward(fv["g_ws"], fv["g_img"], fv["sigmas"], fv["rgbs"], g["march_deltas"], rays, ws, im, T)
+        np.testing.assert_allclose(gc, g[k + "g_rgbs"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(gs, g[k + "g_sigmas"], rtol=2e-3, atol=2e-4)    # differences of nearly equal running sums
+    # eval compositor (K10): in-place accumulation, ray kill
+    rng = np.random.default_rng(2)
+    Mi = g["infer_deltas"].shape[0]
+    si, ci = rng.uniform(0, 60, Mi).astype(np.float32), rng.uniform(0, 1, (Mi, 3)).astype(np.float32)
+    alive, rays_t = np.arange(N, dtype=np.int32), g["nears"].copy()
+    ws, dp, im = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, 3), np.float32)
+    oracle.composite_rays(N, 8, alive, rays_t, si, ci, g["infer_deltas"], ws, dp, im, 1e-2)
+    assert np.array_equal(alive, g["infer_alive"])
+    np.testing.assert_allclose(rays_t, g["infer_rays_t"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(ws, g["infer_ws"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(dp, g["infer_depth"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(im, g["infer_image"], rtol=1e-5, atol=1e-6)
+
+
+def test_oracle_grid_encoder_matches_the_reference_kernels(gref):
+    g, gi = gref
+    offsets, pls, emb, x, gr = gi.grid_inputs()
+    with oracle.level_scales(g["grid_level_scales"]):       # exp2f differs between CUDA and glibc by an ulp
+        out, dy = oracle.grid_encode_forward(x, emb, offsets, pls, 16, calc_grad_inputs=True)
+        outh, _ = oracle.grid_encode_forward(x, oracle.round_to_half(emb), offsets, pls, 16, half_accum=True)
+        ge = oracle.grid_encode_backward(gr, x[:128], emb.shape, offsets, pls, 16)
+    np.testing.assert_allclose(out, g["grid_fwd_f32"], rtol=1e-6, atol=1e-7)
+    assert not out[:, 1].any() and not out[:, 2].any() and not g["grid_fwd_f32"][:, 1].any()      # out-of-range rows
+    np.testing.assert_allclose(dy.reshape(g["grid_dy_dx"].shape), g["grid_dy_dx"], rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(outh, g["grid_fwd_f16"], rtol=0, atol=4e-3)                          # fp16 running sums
+    rows = g["grid_bwd_rows"]
+    touched = np.nonzero(np.abs(ge).sum(1))[0]
+    assert np.array_equal(touched, rows)
+    np.testing.assert_allclose(ge[rows], g["grid_bwd_vals"], rtol=1e-4, atol=1e-5)
+
+
+def test_oracle_sh_freq_ffmlp_match_the_reference_kernels(gref):
+    g, gi = gref
+    d, x, g_sh, g_fr = gi.sh_freq_inputs()
+    y, dy = oracle.sh_encode_forward(d, 4, True)
+    np.testing.assert_allclose(y, g["sh_fwd"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(oracle.sh_encode_backward(g_sh, d, 4, dy), g["sh_bwd"], rtol=2e-4, atol=2e-5)
+    yf = oracle.freq_encode_forward(x, 6)
+    np.testing.assert_allclose(yf, g["freq_fwd"], atol=2e-5)             # the reference builds freqencoder with -use_fast_math
+    np.testing.assert_allclose(oracle.freq_encode_backward(g_fr, g["freq_fwd"], 3, 6), g["freq_bwd"], rtol=1e-4, atol=1e-4)
+    c = gi.ffmlp_inputs()
+    ref, fb = oracle.ffmlp_forward(c["x"], c["W"], c["din"], c["dout"], c["dh"], c["nl"], 0, 6, round_half_act=True)
+    # the reference accumulates in fp16 (wmma accumulator __half): 2e-2 of the magnitude bounds the comparison
+    assert np.abs(ref - g["ffmlp_fwd"]).max() <= 2e-2 * max(1.0, np.abs(ref).max())
+    assert np.abs(fb - g["ffmlp_buffer"]).max() <= 2e-2 * max(1.0, np.abs(fb).max())
+    gw, gx, _ = oracle.ffmlp_backward(c["g"], c["x"], c["W"], g["ffmlp_buffer"], c["din"], c["dout"], c["dh"], c["nl"], 0)
+    assert np.abs(gx - g["ffmlp_gx"]).max() <= 3e-2 * np.abs(gx).max() + 1e-6
+    assert np.abs(gw - g["ffmlp_gw"]).max() <= 3e-2 * np.abs(gw).max() + 1e-6
