@@ -425,20 +425,7 @@ __device__ __forceinline__ void relu_to_tile(uint32_t t_row, uint32_t hf, uint8_
     for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.0f);
     store_half_row(tile, r, hf, v);
 }
-// gradient half: D (.) relu'(act) -> gradient tile
-__device__ __forceinline__ void masked_to_tile(uint32_t t_row, uint32_t hf, const uint8_t *act_tile, uint8_t *dst_tile, uint32_t r) {
-    float v[32];
-    tmem_ld32(t_row + hf * 32, v);
-#pragma unroll
-    for (uint32_t q = 0; q < 4; q++) {
-        float act[8];
-        unpack8(*reinterpret_cast<const uint4 *>(act_tile + sw128_off(r, hf * 4 + q)), act);
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[q * 8 + i] = act[i] > 0.0f ? v[q * 8 + i] : 0.0f;
-    }
-    store_half_row(dst_tile, r, hf, v);
-}
-// the same in two phases: the masked, packed half row is built in registers first (while MMAs may still read the destination
+// gradient half: D (.) relu'(act) -> gradient tile, in two phases: the masked, packed half row is built in registers first (while MMAs may still read the destination
 // tile) and stored once the caller knows the tile is free
 __device__ __forceinline__ void masked_half_row(uint32_t t_row, uint32_t hf, const uint8_t *act_tile, uint32_t r, uint4 (&out)[4]) {
     float v[32];

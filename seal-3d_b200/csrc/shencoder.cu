@@ -150,16 +150,23 @@ int launch_sh(const float *inputs, float *outputs, uint32_t B, uint32_t D, float
 
 // ---- frequency encoding (freqencoder.cu:30-94) ---------------------------------------------
 
-__global__ void k_freq_forward(const float *__restrict__ inputs, uint32_t B, uint32_t D, uint32_t deg, uint32_t C,
-                               float *__restrict__ outputs) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= B * C) return;
-    const uint32_t b = t / C, c = t - b * C;
-    if (c < D) { outputs[t] = inputs[(size_t)b * D + c]; return; }
-    const uint32_t col = c / D - 1, d = c % D, freq = col / 2;
-    const float phase = (float)(col & 1u) * 1.5707963267948966f;
-    // the reference builds this extension with -use_fast_math (freqencoder/backend.py:9): sin.approx
-    outputs[t] = __sinf(scalbnf(inputs[(size_t)b * D + d], (int)freq) + phase);
+// one thread per INPUT element (b, d): x is read once, the 2*deg+1 outputs of that element are written as runs of D
+// consecutive floats per (sample, column block) across the warp.  scalbnf(x, f) of the reference is a multiplication by
+// the exact power of two 2^f (same bits for every finite x that does not overflow); sin.approx like the reference's
+// -use_fast_math build (freqencoder/backend.py:9), cos as sin(x + pi/2) (freqencoder.cu:56-58).
+__global__ void __launch_bounds__(256)
+k_freq_forward(const float *__restrict__ inputs, uint32_t B, uint32_t D, uint32_t deg, uint32_t C, float *__restrict__ outputs) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)B * D) return;
+    const uint32_t b = (uint32_t)(t / D), d = (uint32_t)(t - (uint64_t)b * D);
+    const float x = __ldg(inputs + t);
+    float *o = outputs + (size_t)b * C + d;
+    o[0] = x;
+    for (uint32_t f = 0; f < deg; f++) {
+        const float xs = f < 127 ? __fmul_rn(x, __int_as_float((127 + f) << 23)) : scalbnf(x, (int)f);
+        o[(size_t)(1 + 2 * f) * D] = __sinf(xs);
+        o[(size_t)(2 + 2 * f) * D] = __sinf(__fadd_rn(xs, 1.5707963267948966f));
+    }
 }
 
 __global__ void k_freq_backward(const float *__restrict__ grad, const float *__restrict__ outputs, uint32_t B, uint32_t D,
@@ -212,7 +219,7 @@ S3D_API int s3d_freq_encode_forward(const float *inputs, uint32_t B, uint32_t D,
                                     void *stream) {
     if (B == 0) return 0;
     if (C != D + D * 2 * deg) return S3D_EINVAL;
-    k_freq_forward<<<div_up(B * C, 256u), 256, 0, as_stream(stream)>>>(inputs, B, D, deg, C, outputs);
+    k_freq_forward<<<(unsigned)div_up((uint64_t)B * D, (uint64_t)256), 256, 0, as_stream(stream)>>>(inputs, B, D, deg, C, outputs);
     S3D_RETURN_LAST();
 }
 
