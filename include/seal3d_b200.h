@@ -222,6 +222,10 @@ int s3d_ngp_mlp_backward(const void *feats, const float *dirs, uint32_t M, const
                          float out_scale, float *gw_s0, float *gw_s1, float *gw_c0, float *gw_c1, float *gw_c2, int train_mlp, void *stream);
 int s3d_ngp_scatter(const float *xyz, const void *dfeats, uint32_t M, float bound, float *grad4, const int *offsets, uint32_t L, float S,
                     uint32_t H, float grad_scale, void *stream);
+/* the scatter restricted to levels [level_begin, level_end), multiples of 4 (level_end may be L): data-parallel runs launch the
+ * levels in chunks and all-reduce each finished slice of grad4 under the next chunk */
+int s3d_ngp_scatter_levels(const float *xyz, const void *dfeats, uint32_t M, float bound, float *grad4, const int *offsets, uint32_t L,
+                           float S, uint32_t H, float grad_scale, uint32_t level_begin, uint32_t level_end, void *stream);
 int s3d_ngp_adam_tables(float *table_sigma, float *table_color, float *grad4, float *exp_avg4, float *exp_avg_sq4, void *shadow,
                         uint32_t shadow_stride, uint64_t n_entries, float lr, float beta1, float beta2, float eps, uint32_t step,
                         float grad_scale, const float *scaler_state, void *stream);

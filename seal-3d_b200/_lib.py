@@ -62,6 +62,7 @@ _SIGS = {
     "s3d_ngp_mlp_forward": [P, P, U32, P, P, P, P, P, F32, P, P, P, I32],
     "s3d_ngp_mlp_backward": [P, P, U32, P, P, P, P, P, F32, P, P, P, F32, P, P, P, P, P, I32],
     "s3d_ngp_scatter": [P, P, U32, F32, P, P, U32, F32, U32, F32],
+    "s3d_ngp_scatter_levels": [P, P, U32, F32, P, P, U32, F32, U32, F32, U32, U32],
     "s3d_ngp_adam_tables": [P, P, P, P, P, P, U32, U64, F32, F32, F32, F32, U32, F32, P],
     "s3d_vm_forward": [P, U32, P, P, P, P, P, P, P, P, U32, I32, P],
     "s3d_vm_backward": [P, U32, P, P, P, P, P, P, P, P, U32, I32, P, P, P, P, P, P, P],

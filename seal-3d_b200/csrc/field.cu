@@ -256,7 +256,8 @@ __global__ void k_pair_tables(const uint2 *__restrict__ teacher4, const uint2 *_
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, uint32_t M, float bound,
-              float4 *__restrict__ grad4, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H, float grad_scale) {
+              float4 *__restrict__ grad4, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H, float grad_scale,
+              uint32_t grp_begin, uint32_t grp_end) {
     __shared__ Geo g;
     geo_init(g, offsets, L, S, H);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // whole warps stay alive
@@ -265,7 +266,7 @@ k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, 
     if (i < M) ok = load_unit(xyz, i, bound, ux, uy, uz);
     const uint32_t lane = lane_id();
     const uint4 *row = reinterpret_cast<const uint4 *>(dfeats + (size_t)(i < M ? i : 0) * 64);
-    for (uint32_t grp = 0; grp < 4; grp++) {
+    for (uint32_t grp = grp_begin; grp < grp_end; grp++) {   // 4 levels per group; a launch may cover a sub-range (s3d_ngp_scatter_levels)
         float ds[8], dc[8];
         if (ok) { unpack8(__ldg(row + grp), ds); unpack8(__ldg(row + 4 + grp), dc); }
         else {
@@ -1026,7 +1027,19 @@ S3D_API int s3d_ngp_scatter(const float *xyz, const void *dfeats, uint32_t M, fl
                             float S, uint32_t H, float grad_scale, void *stream) {
     if (M == 0) return 0;
     if (L > kMaxLevels) return S3D_ENOTSUP;
-k_ngp_scatter<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale);
+k_ngp_scatter<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale, 0, 4);
+    S3D_RETURN_LAST();
+}
+
+// the same scatter restricted to levels [level_begin, level_end) (both multiples of 4): data-parallel training launches the
+// levels in a few chunks so that the all-reduce of a finished chunk's slice of the gradient table runs under the next chunk
+S3D_API int s3d_ngp_scatter_levels(const float *xyz, const void *dfeats, uint32_t M, float bound, float *grad4, const int *offsets, uint32_t L,
+                                   float S, uint32_t H, float grad_scale, uint32_t level_begin, uint32_t level_end, void *stream) {
+    if (M == 0 || level_begin >= level_end) return 0;
+    if (L > kMaxLevels) return S3D_ENOTSUP;
+    if ((level_begin & 3u) || ((level_end & 3u) && level_end != L) || level_end > L) return S3D_EINVAL;
+    k_ngp_scatter<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale,
+                                                                    level_begin / 4, div_up(level_end, 4u));
     S3D_RETURN_LAST();
 }
 

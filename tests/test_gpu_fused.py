@@ -455,3 +455,32 @@ def test_seal_student_schedule_config3_in_miniature(engine, scene):
     # compositor's backward drops grad_depth, raymarching.py:271-288), so it is only required to stay finite
     assert np.isfinite(fin).all() and fin[-3:, 0].mean() < 0.5 * fin[:3, 0].mean(), fin
     assert len(sch.timer["pretraining"]) == 6 and len(sch.timer["training"]) == 20 and sch.timer["proxy_dataset"] > 0
+
+
+def test_scatter_in_level_chunks_equals_one_launch(scene):
+    """data-parallel runs scatter the table gradient in level chunks (so that each finished slice can be all-reduced under the
+    next chunk): the chunks tile the gradient arena and add up to the single-launch gradient"""
+    from seal3d_b200.fused import FusedNGP
+    from seal3d_b200 import _lib
+    t, s, _, _ = _networks(scene)
+    s.encoder.embeddings.data.copy_(t.encoder.embeddings.data)
+    s.encoder_color.embeddings.data.copy_(t.encoder_color.embeddings.data)
+    F = FusedNGP(s, trainable=True)
+    x0, d0, _, _, M = _samples(scene, 512)
+    x0, d0 = x0[:40000], d0[:40000]
+    rng = np.random.default_rng(0)
+    gs, gc = to((rng.normal(size=x0.shape[0]) * 1e-2).astype(np.float32)), to((rng.normal(size=(x0.shape[0], 3)) * 1e-1).astype(np.float32))
+    sig, rgb, feats = F.forward(to(x0), to(d0))
+    F.backward(to(x0), to(d0), feats, gs, gc)
+    one = F.grad.clone()
+    for n in (2, 3, 8):
+        F.grad.zero_()
+        chunks = F.grad_chunks(n)
+        assert chunks[0][0] == 0 and chunks[-1][1] == F.L and chunks[0][2] == 0 and chunks[-1][3] == F.grad.numel()
+        assert all(a[1] == b[0] and a[3] == b[2] and a[0] % 4 == 0 for a, b in zip(chunks, chunks[1:]))
+        seen = []
+        F.backward(to(x0), to(d0), feats, gs, gc, chunks=chunks, after_chunk=lambda i, a0, a1: seen.append((i, a0, a1)))
+        assert seen == [(i, c[2], c[3]) for i, c in enumerate(chunks)]
+        np.testing.assert_allclose(npy(F.grad), npy(one), rtol=0, atol=2e-6 * float(one.abs().max()))
+    with pytest.raises(_lib.S3DError):       # level ranges are whole 4-level groups
+        _lib.call("s3d_ngp_scatter_levels", to(x0), feats, 128, F.bound, F.grad4, F.offsets, F.L, F.S, F.H, 1.0, 2, 8)
