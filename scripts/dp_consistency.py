@@ -3,7 +3,6 @@ replicas) and close to a single process that ran the whole batch (fp32 reduction
 import os
 import sys
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -11,7 +11,6 @@ nvcc cross-compiles without a GPU.  Outputs stay in-tree (git-ignored) so they t
 """
 import hashlib
 import os
-import shutil
 import subprocess
 import sys
 import sysconfig

@@ -9,7 +9,6 @@ import numpy as np
 import torch
 
 from . import _lib
-from . import raymarching
 from .network import NeRFNetwork
 from .tensorf import TensoRFNetwork
 

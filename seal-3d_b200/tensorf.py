@@ -13,7 +13,6 @@ that format; ``state_dict()`` returns the reference shapes.
 The colour MLP (150-128-128-3) and ``basis_mat`` are ``F.linear`` GEMMs like in the reference (tensoRF/network.py:148,
 :172-178); the background model (``bg_radius > 0``) is not built.
 """
-import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F

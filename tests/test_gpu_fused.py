@@ -11,7 +11,7 @@ import pytest
 import torch
 
 import oracle
-from test_gpu_parity import dev, to, npy, scene, _samples, _networks, scaled, rm  # noqa: F401
+from test_gpu_parity import dev, to, npy, scene, _samples, _networks, scaled  # noqa: F401
 
 pytestmark = pytest.mark.gpu
 
@@ -323,8 +323,6 @@ def test_full_checkpoint_resumes_training_and_is_a_torch_adam_state(engine, tmp_
     from seal3d_b200 import checkpoint as ck, synth
     from seal3d_b200.fused import FusedDistillTrainer
     from seal3d_b200.trainer import DistillTrainer
-
-    import copy
 
     def make():
         teacher, student, _, _ = _networks(scene)
