@@ -299,6 +299,24 @@ ALGO_BYTES = {
 }
 
 
+def whole_step_roofline(n_rays, samples_per_step, rays_per_s_per_gpu):
+    """the north star's second figure: the step as a fraction of the HBM-bandwidth roofline, with the algorithmic bytes
+    per ray of SURVEY.md 8(d) (fp16 tables): 68 B per ray + per sample 32 (sample buffer) + 2 x 512 teacher gathers + 2 x 512
+    student gathers + 2 x 512 student scatter + 16 (sigma, rgb) = 3120 B"""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    spr = samples_per_step / n_rays
+    bytes_per_ray = 68.0 + 3120.0 * spr
+    bound = peak * 1e9 / bytes_per_ray
+    return {"bytes_per_ray": bytes_per_ray, "samples_per_ray": spr, "hbm_bound_rays_per_s_per_gpu": bound,
+            "frac": rays_per_s_per_gpu / bound, "peak_GBps": peak,
+            "note": "algorithmic bytes per ray of SURVEY.md 8(d) / measured HBM copy bandwidth; tables are L2-resident, so this is not DRAM traffic"}
+
+
 def step_roofline(breakdown, samples_per_step, step_ms):
     """roofline of the step's dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events on the
     launching stream, measured live above), against the measured HBM copy bandwidth"""
@@ -437,6 +455,7 @@ def gpu_arm(args):
         "clocks": clk, "loss_last": [float(v) for v in last.numpy()] if last is not None else None,
     }
     line["config"]["engine"] = args.engine
+    line["step_hbm_roofline"] = whole_step_roofline(n, samples_per_step, n * args.steps / (ms * 1e-3))
     if breakdown:
         line["kernel_breakdown_ms_per_step"] = {k: round(v["ms_per_step"], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms_per_step"])}
         line["roofline"] = step_roofline(breakdown, samples_per_step, ms / args.steps)
