@@ -198,6 +198,11 @@ int s3d_density_cells_to_xyz(const int *cell_morton, uint32_t n, uint32_t H, flo
 int s3d_density_scatter(const int *cell_morton, const float *sigma, uint32_t n, float density_scale, float *tmp_grid,
                         void *stream);
 int s3d_density_grid_ema(float *grid, const float *tmp_grid, uint32_t n, float decay, float *sum_out, void *stream);
+/* nerf/renderer.py:379-443 mark_untrained_grid(poses, intrinsic): density_grid[c, cell] = -1 for every cell whose centre no camera
+ * sees (in front, inside the frustum widened by one cell).  poses device [B,4,4] cam2world (B <= 4000), kx = cx/fx, ky = cy/fy,
+ * count_out optional int32 [C, H^3] (morton order) = number of cameras per cell */
+int s3d_mark_untrained_grid(float *density_grid, const float *poses, uint32_t B, float kx, float ky, uint32_t C, uint32_t H, float bound,
+                            int *count_out, void *stream);
 
 /* ------------------------------------------------------------------ fused NGP field (nerf/network.py:99-128) */
 /* The higher-level seam of SURVEY.md 8b: samples -> (sigma, rgb) and back, four kernels, one 128-byte fp16 row per

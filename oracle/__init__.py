@@ -164,6 +164,15 @@ def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, we
                              _p(_f32(rgbs)), _p(_f32(deltas)), _p(weights_sum), _p(depth), _p(image))
 
 
+def mark_untrained_count(poses, intrinsic, cascade=1, H=128, bound=1.0):
+    """nerf/renderer.py:379-443: per-cell camera count [cascade, H^3] (morton order); the grid gets -1 where it is 0"""
+    poses = _f32(poses).reshape(-1, 4, 4)
+    fx, fy, cx, cy = [float(v) for v in intrinsic]
+    count = np.empty((cascade, H ** 3), np.int32)
+    lib().orc_mark_untrained_count(_p(poses), u32(poses.shape[0]), f32(cx / fx), f32(cy / fy), u32(cascade), u32(H), f32(bound), _p(count))
+    return count
+
+
 # ---------------------------------------------------------------- gridencoder
 
 

@@ -1187,3 +1187,34 @@ ORC_API void orc_vm_backward(const float *xyz, uint32_t M, const float *aabb, co
         free(am); free(av);
     }
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* nerf/renderer.py:379-443 mark_untrained_grid                                           */
+/* ------------------------------------------------------------------------------------ */
+/* count[cas, morton(cell)] = number of cameras that see the cell centre: cam = (x - t) . R (poses cam2world, row vector
+ * times R), in front (z > 0) and |cam.x| < cx/fx * z + 2*hgs, |cam.y| < cy/fy * z + 2*hgs; centre = (2c/(H-1) - 1)(bound - hgs)
+ * in float32 like the reference's tensor expressions.  The caller sets density_grid = -1 where count == 0.
+ * Pinned by tests/golden/cpu_untrained.npz (the reference method run on CPU torch). */
+ORC_API void orc_mark_untrained_count(const float *poses, uint32_t B, float kx, float ky, uint32_t C, uint32_t H, float bound, int32_t *count) {
+    const int64_t H3 = (int64_t)H * H * H;
+    for (uint32_t cas = 0; cas < C; cas++) {
+        const float bound_cas = fminf((float)(1u << cas), bound);
+        const float hgs = bound_cas / (float)H, sc = bound_cas - hgs, margin = hgs * 2.0f;
+#pragma omp parallel for schedule(static)
+        for (int64_t cell = 0; cell < H3; cell++) {
+            const uint32_t c3[3] = {(uint32_t)(cell / ((int64_t)H * H)), (uint32_t)((cell / H) % H), (uint32_t)(cell % H)};
+            float w[3];
+            for (int d = 0; d < 3; d++) w[d] = ((2.0f * (float)c3[d]) / (float)(H - 1) - 1.0f) * sc;
+            int n = 0;
+            for (uint32_t b = 0; b < B; b++) {
+                const float *P = poses + (size_t)b * 16;
+                const float dx = w[0] - P[3], dy = w[1] - P[7], dz = w[2] - P[11];
+                const float cx_ = (dx * P[0] + dy * P[4]) + dz * P[8];
+                const float cy_ = (dx * P[1] + dy * P[5]) + dz * P[9];
+                const float cz_ = (dx * P[2] + dy * P[6]) + dz * P[10];
+                n += (cz_ > 0.0f && fabsf(cx_) < kx * cz_ + margin && fabsf(cy_) < ky * cz_ + margin) ? 1 : 0;
+            }
+            count[(int64_t)cas * H3 + morton3(c3[0], c3[1], c3[2])] = n;
+        }
+    }
+}

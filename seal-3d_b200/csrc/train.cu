@@ -212,6 +212,52 @@ __global__ void k_density_cells_to_xyz(const int *__restrict__ cell_morton, uint
         xyz[(size_t)i * 3 + d] = base + (u * 2.0f - 1.0f) * hgs;
     }
 }
+// nerf/renderer.py:379-443 mark_untrained_grid: a cell of cascade `cas` is "trained" if its centre, taken to camera space
+// (cam = (x - t) . R, poses are cam2world), lies in front of at least one camera and inside its frustum widened by one cell:
+// |cam.x| < cx/fx * cam.z + 2*half_grid_size (and the same for y).  Cells no camera sees get density -1.  The reference does
+// this with a 5-level Python loop of batched matmuls; here one thread owns one (cascade, cell) and walks the cameras
+// (poses in shared memory).  Float32 with the reference's operation order: centre = (2*c/(H-1) - 1) * (bound - hgs).
+__global__ void __launch_bounds__(256)
+k_mark_untrained(float *__restrict__ grid, const float *__restrict__ poses, uint32_t B, float kx, float ky, uint32_t C, uint32_t H,
+                 float bound, int *__restrict__ count_out) {
+    extern __shared__ float s_pose[];   // per camera: R (9, row-major) + t (3)
+    for (uint32_t i = threadIdx.x; i < B * 12; i += blockDim.x) {
+        const uint32_t b = i / 12, k = i - b * 12;
+        s_pose[i] = k < 9 ? poses[(size_t)b * 16 + (k / 3) * 4 + (k % 3)] : poses[(size_t)b * 16 + (k - 9) * 4 + 3];
+    }
+    __syncthreads();
+    const uint32_t H3 = H * H * H;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= C * H3) return;
+    const uint32_t cas = t / H3, cell = t - cas * H3;
+    const uint32_t cx = cell / (H * H), cy = (cell / H) % H, cz = cell % H;
+    auto spread = [](uint32_t v) {
+        v = (v * 0x00010001u) & 0xFF0000FFu; v = (v * 0x00000101u) & 0x0F00F00Fu;
+        v = (v * 0x00000011u) & 0xC30C30C3u; v = (v * 0x00000005u) & 0x49249249u; return v; };
+    const uint32_t morton = spread(cx) | (spread(cy) << 1) | (spread(cz) << 2);
+    const float bound_cas = fminf((float)(1u << cas), bound);
+    const float hgs = __fdiv_rn(bound_cas, (float)H);
+    const float sc = __fsub_rn(bound_cas, hgs);
+    float w[3];
+    const uint32_t c3[3] = {cx, cy, cz};
+#pragma unroll
+    for (int d = 0; d < 3; d++) w[d] = __fmul_rn(__fsub_rn(__fdiv_rn(__fmul_rn(2.0f, (float)c3[d]), (float)(H - 1)), 1.0f), sc);
+    const float margin = __fmul_rn(hgs, 2.0f);
+    int count = 0;
+    for (uint32_t b = 0; b < B; b++) {
+        const float *P = s_pose + b * 12;
+        const float dx = __fsub_rn(w[0], P[9]), dy = __fsub_rn(w[1], P[10]), dz = __fsub_rn(w[2], P[11]);
+        // cam_j = dx*R[0][j] + dy*R[1][j] + dz*R[2][j]  (row vector times R)
+        const float camx = __fadd_rn(__fadd_rn(__fmul_rn(dx, P[0]), __fmul_rn(dy, P[3])), __fmul_rn(dz, P[6]));
+        const float camy = __fadd_rn(__fadd_rn(__fmul_rn(dx, P[1]), __fmul_rn(dy, P[4])), __fmul_rn(dz, P[7]));
+        const float camz = __fadd_rn(__fadd_rn(__fmul_rn(dx, P[2]), __fmul_rn(dy, P[5])), __fmul_rn(dz, P[8]));
+        const bool in = camz > 0.0f && fabsf(camx) < __fadd_rn(__fmul_rn(kx, camz), margin) && fabsf(camy) < __fadd_rn(__fmul_rn(ky, camz), margin);
+        count += in ? 1 : 0;
+    }
+    if (count_out) count_out[(size_t)cas * H3 + morton] = count;
+    if (count == 0) grid[(size_t)cas * H3 + morton] = -1.0f;
+}
+
 // tmp[cell_morton[i]] = sigma[i]
 __global__ void k_density_scatter(const int *__restrict__ cell_morton, const float *__restrict__ sigma, uint32_t n, float scale, float *__restrict__ tmp) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -284,6 +330,17 @@ S3D_API int s3d_density_grid_ema(float *grid, const float *tmp_grid, uint32_t n,
 S3D_API int s3d_density_cells_to_xyz(const int *cell_morton, uint32_t n, uint32_t H, float bound_cas, uint32_t seed, float *xyz, void *stream) {
     if (n == 0) return 0;
     k_density_cells_to_xyz<<<div_up(n, 256u), 256, 0, as_stream(stream)>>>(cell_morton, n, H, bound_cas, seed, xyz);
+    S3D_RETURN_LAST();
+}
+
+// nerf/renderer.py:379-443.  poses: device [B,4,4] cam2world; kx = cx/fx, ky = cy/fy; count_out (optional, int32 [C,H^3],
+// morton order) receives the number of cameras that see each cell; density_grid[c, cell] = -1 where that number is 0.
+S3D_API int s3d_mark_untrained_grid(float *density_grid, const float *poses, uint32_t B, float kx, float ky, uint32_t C, uint32_t H,
+                                    float bound, int *count_out, void *stream) {
+    if (C == 0 || H == 0) return S3D_EINVAL;
+    if (B > 4000) return S3D_ENOTSUP;     // poses are staged in shared memory (48 B each)
+    const uint32_t n = C * H * H * H;
+    k_mark_untrained<<<div_up(n, 256u), 256, (size_t)B * 12 * sizeof(float), as_stream(stream)>>>(density_grid, poses, B, kx, ky, C, H, bound, count_out);
     S3D_RETURN_LAST();
 }
 

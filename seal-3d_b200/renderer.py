@@ -135,6 +135,34 @@ class NeRFRenderer(nn.Module):
         return {"image": image.view(*prefix, 3), "depth": depth.view(*prefix), "weights_sum": weights_sum.view(*prefix)}
 
     @torch.no_grad()
+    def mark_untrained_grid(self, poses, intrinsic, S=64):
+        """nerf/renderer.py:379-443: poses [B,4,4] cam2world (array or tensor), intrinsic = (fx, fy, cx, cy).  Cells of the
+        density grid that no training camera sees are set to -1 so they never become occupied.  Returns the per-cell camera
+        count [cascade, H^3] (morton order); `S` (the reference's chunk size) is accepted and ignored."""
+        if not self.cuda_ray:
+            return None
+        dev = self.density_bitfield.device
+        poses = torch.as_tensor(poses, dtype=torch.float32).to(dev).contiguous().view(-1, 4, 4)
+        fx, fy, cx, cy = [float(v) for v in intrinsic]
+        count = torch.zeros(self.cascade, self.grid_size ** 3, dtype=torch.int32, device=dev)
+        grid = self.density_grid if self.density_grid.is_contiguous() else self.density_grid.contiguous()
+        if poses.shape[0] <= 4000:                     # one launch marks the grid directly
+            _lib.call("s3d_mark_untrained_grid", grid, poses, poses.shape[0], cx / fx, cy / fy, self.cascade, self.grid_size, float(self.bound), count)
+            if grid is not self.density_grid:
+                self.density_grid.copy_(grid)
+            return count
+        for b0 in range(0, poses.shape[0], 4000):      # shared-memory staging limit of the kernel; counts accumulate
+            part = torch.zeros_like(count)
+            tmp = grid.clone()
+            _lib.call("s3d_mark_untrained_grid", tmp, poses[b0:b0 + 4000].contiguous(), min(4000, poses.shape[0] - b0), cx / fx, cy / fy,
+                      self.cascade, self.grid_size, float(self.bound), part)
+            count += part
+        grid[count == 0] = -1
+        if grid is not self.density_grid:
+            self.density_grid.copy_(grid)
+        return count
+
+    @torch.no_grad()
     def update_extra_state(self, decay=0.95, S=128, seed=None):
         """nerf/renderer.py:445-538: full sweep for the first 16 calls, then H^3/4 uniform + H^3/4 occupied cells;
         EMA-max into density_grid, mean density, packbits with min(mean, density_thresh), mean_count from the ring."""

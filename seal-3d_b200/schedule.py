@@ -174,10 +174,13 @@ class SealStudentSchedule:
 
     # -- stage 3 ----------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def proxy_dataset(self, poses, rays_of_view, n_batch=1):
+    def proxy_dataset(self, poses, rays_of_view, n_batch=1, intrinsic=None):
         """SealNeRF/provider.py:19-70: teacher images / depths for every pose.  rays_of_view(pose) -> (rays_o, rays_d) [HW,3]
-        numpy or tensors.  Uses the fused field when the trainer has one."""
+        numpy or tensors.  Uses the fused field when the trainer has one.  With intrinsic = (fx, fy, cx, cy) the student's
+        density grid is also marked for the region no training camera sees (SealNeRF/trainer.py:285-287)."""
         t0 = time.perf_counter()
+        if intrinsic is not None:
+            self.student.mark_untrained_grid(np.stack([np.asarray(p, np.float32) for p in poses]), intrinsic)
         if not self.teacher.density_bitfield_hacked:
             self.teacher.hack_bitfield()
         fused_teacher = getattr(self.tr, "T", None)

@@ -435,7 +435,8 @@ def test_seal_student_schedule_config3_in_miniature(engine, scene):
     pix = (np.arange(4, 800, 8)[:, None] * 800 + np.arange(4, 800, 8)[None, :]).reshape(-1)
     poses = synth.poses()[:5]
     rays_of_view = lambda pose: synth.rays_from_pixels(pose, pix)
-    images, depths = sch.proxy_dataset(poses, rays_of_view)
+    images, depths = sch.proxy_dataset(poses, rays_of_view, intrinsic=(1111.111, 1111.111, 400.0, 400.0))
+    assert int((s.density_grid == -1).sum()) > 0            # cells outside every training frustum are marked untrained
     assert images.shape == (5, pix.shape[0], 3) and depths.shape == (5, pix.shape[0]) and torch.isfinite(images).all()
     # the reference's own convention (eval depth = distance from the origin) differs by near * weights_sum
     ref_sch = SealStudentSchedule(tr, num_rays=4096)

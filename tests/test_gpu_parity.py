@@ -821,3 +821,24 @@ def test_brush_anchor_texture_mappers():
                                       g["tex_w"], g["tex_h"], float(g["tex_light"]))
     np.testing.assert_allclose(npy(cols)[::3], ref, rtol=1e-5, atol=3e-6)
     assert np.array_equal(npy(cols)[1::3], g["tex_colors"][1::3])
+
+
+@pytest.mark.parametrize("tag,bound", [("b1_", 1), ("b2_", 2)])
+def test_mark_untrained_grid(tag, bound):
+    """kernel vs the oracle (exact: same float32 operation order) and vs the reference method's own result (golden)"""
+    from seal3d_b200.renderer import NeRFRenderer
+    g = np.load(os.path.join(G, "cpu_untrained.npz"))
+    r = NeRFRenderer(bound=bound, cuda_ray=True).to(dev())
+    r.density_grid.fill_(0.5)
+    count = r.mark_untrained_grid(g[tag + "poses"], g[tag + "intrinsic"])
+    ref = oracle.mark_untrained_count(g[tag + "poses"], g[tag + "intrinsic"], r.cascade, 128, float(bound))
+    assert np.array_equal(npy(count), ref)
+    grid = npy(r.density_grid)
+    assert np.array_equal(grid == -1, ref == 0) and ((grid == -1) | (grid == 0.5)).all()
+    want = np.unpackbits(g[tag + "mask_bits"])[:r.cascade * 128 ** 3].astype(bool).reshape(r.cascade, -1)
+    assert ((grid == -1) != want).sum() <= 1e-5 * want.size
+    # marked cells never become occupied: the EMA keeps -1 (nerf/renderer.py:523-524 valid_mask) -> packbits leaves them clear
+    bits = rm().packbits(r.density_grid, 0.01)
+    assert int(npy(bits).astype(np.uint32).sum()) > 0
+    cells = np.nonzero(grid[0] == -1)[0][:1000]
+    assert not ((npy(bits)[cells // 8] >> (cells % 8)) & 1).any()

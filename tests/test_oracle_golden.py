@@ -367,3 +367,19 @@ def test_oracle_sh_freq_ffmlp_match_the_reference_kernels(gref):
     gw, gx, _ = oracle.ffmlp_backward(c["g"], c["x"], c["W"], g["ffmlp_buffer"], c["din"], c["dout"], c["dh"], c["nl"], 0)
     assert np.abs(gx - g["ffmlp_gx"]).max() <= 3e-2 * np.abs(gx).max() + 1e-6
     assert np.abs(gw - g["ffmlp_gw"]).max() <= 3e-2 * np.abs(gw).max() + 1e-6
+
+
+@pytest.mark.parametrize("tag,bound", [("b1_", 1), ("b2_", 2)])
+def test_mark_untrained_grid_matches_reference_method(tag, bound):
+    """nerf/renderer.py:379-443 run on CPU torch (tests/golden/make_untrained_golden.py) vs the oracle restatement"""
+    g = load("cpu_untrained.npz")
+    cascade = 1 + int(np.ceil(np.log2(bound)))
+    count = oracle.mark_untrained_count(g[tag + "poses"], g[tag + "intrinsic"], cascade, 128, float(bound))
+    want = np.unpackbits(g[tag + "mask_bits"])[:cascade * 128 ** 3].astype(bool).reshape(cascade, -1)
+    got = count == 0
+    assert int(want.sum()) == int(g[tag + "n_marked"]) and want.sum() > 100000
+    # the reference's batched matmul may round a 3-term dot product differently: a handful of cells exactly on a frustum
+    # boundary may flip, and only cells seen by at most one camera can change their mark
+    diff = got != want
+    assert diff.sum() <= 1e-5 * want.size, int(diff.sum())
+    assert (count[diff] <= 1).all()
