@@ -350,7 +350,8 @@ class FusedDistillTrainer:
 
     # -- software pipelining of the marcher ---------------------------------------------------------------------
     # Marching depends on the rays and the occupancy bitfield only, not on the parameters, so the samples of step n+1 can be
-    # generated while step n's gradient scatter and Adam run: the marcher is latency-bound (divergent per-ray DDA), the scatter
+    # generated while step n's gradient scatter and Adam run (one GPU) or while its gradient all-reduce runs (data parallel:
+    # NCCL occupies a few SMs, the marcher gets the rest): the marcher is latency-bound (divergent per-ray DDA), the scatter
     # is bound by L2 atomics, and they share the SMs well.  (Under the persistent MLP kernels it does not pay: their static
     # tile schedule turns any SM the marcher delays into the kernel's tail -- measured, profiles/r1d_experiments.md.)  `prefetch=(rays_o, rays_d)` on a step hands the NEXT
     # batch (device tensors or pinned host tensors; host tensors are copied on the side stream too) to a second stream.
@@ -453,7 +454,10 @@ class FusedDistillTrainer:
         else:
             img_t, depth_t = self.teacher_targets(xyzs, dirs, deltas, rays)
             sig_s, rgb_s, feats = self.S.forward(xyzs, dirs)
-        loss, scale = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, img_t, depth_t, before_scatter=ahead)
+        loss, scale = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, img_t, depth_t,
+                                             before_scatter=ahead if self.world_size == 1 else None)
+        if ahead is not None and self.world_size > 1:
+            ahead()      # data parallel: the next batch is marched under the gradient all-reduce (NCCL needs only a few SMs)
         self._reduce_and_step(scale)
         return loss
 
@@ -463,7 +467,10 @@ class FusedDistillTrainer:
         rays_o, rays_d, (xyzs, dirs, deltas, rays) = self._march_or_take(rays_o, rays_d, perturb, force_all_rays)
         ahead = (lambda: self._prefetch(prefetch, perturb, force_all_rays)) if prefetch is not None else None
         sig_s, rgb_s, feats = self.S.forward(xyzs, dirs)
-        loss, scale = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, image_t, depth_t, before_scatter=ahead)
+        loss, scale = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, image_t, depth_t,
+                                             before_scatter=ahead if self.world_size == 1 else None)
+        if ahead is not None and self.world_size > 1:
+            ahead()
         self._reduce_and_step(scale)
         return loss
 
