@@ -197,3 +197,20 @@ def test_pretraining_lattice_and_euler_directions_match_scipy():
     assert dirs.shape == (2 * 64, 3)
     np.testing.assert_allclose(dirs[:64].numpy(), ref, atol=1e-7)
     np.testing.assert_allclose(dirs[64:].numpy(), ref, atol=1e-7)
+
+
+def test_gradient_arena_chunks_tile_the_levels():
+    """fused.FusedNGP.grad_chunks: whole 4-level blocks, contiguous arena slices, the MLP gradients ride on the last slice"""
+    import torch
+    from seal3d_b200 import synth
+    from seal3d_b200.fused import FusedNGP
+    off, _ = synth.grid_offsets()
+    stub = type("S", (), {})()
+    stub.offsets, stub.L, stub.grad = torch.from_numpy(off), 16, torch.zeros(int(off[-1]) * 4 + 11392)
+    for n in (1, 2, 3, 4, 8):
+        ch = FusedNGP.grad_chunks(stub, n)
+        assert 1 <= len(ch) <= min(n, 4) and ch[0][0] == 0 and ch[0][2] == 0 and ch[-1][1] == 16 and ch[-1][3] == stub.grad.numel()
+        for a, b in zip(ch, ch[1:]):
+            assert a[1] == b[0] and a[3] == b[2] and a[1] % 4 == 0 and a[3] == int(off[a[1]]) * 4
+    two = FusedNGP.grad_chunks(stub, 2)
+    assert abs((two[0][3] - two[0][2]) - (two[1][3] - two[1][2])) < 0.4 * stub.grad.numel()      # about equal bytes
