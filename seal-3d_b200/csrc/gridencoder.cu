@@ -148,12 +148,14 @@ template <typename T> __device__ __forceinline__ float to_float(T v);
 template <> __device__ __forceinline__ float to_float<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_float<__half>(__half v) { return __half2float(v); }
 
-template <typename T, uint32_t C>
+template <typename T, uint32_t C, bool CS = false>
 __device__ __forceinline__ void store_vec(T *__restrict__ p, const float (&v)[C]) {
     if constexpr (sizeof(T) == 4 && C == 2) {
-        *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+        if constexpr (CS) __stcs(reinterpret_cast<float2 *>(p), make_float2(v[0], v[1]));
+        else *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
     } else if constexpr (sizeof(T) == 2 && C == 2) {
-        *reinterpret_cast<__half2 *>(p) = __floats2half2_rn(v[0], v[1]);
+        if constexpr (CS) __stcs(reinterpret_cast<__half2 *>(p), __floats2half2_rn(v[0], v[1]));
+        else *reinterpret_cast<__half2 *>(p) = __floats2half2_rn(v[0], v[1]);
     }
     else {
 #pragma unroll
@@ -280,8 +282,8 @@ __device__ __forceinline__ void encode_level(const float (&x)[D], const T *__res
 }
 
 // ALL_LEVELS: blockIdx.y unused, thread loops over levels.  Otherwise blockIdx.y = level.
-template <typename T, uint32_t D, uint32_t C, bool ALL_LEVELS>
-__global__ void __launch_bounds__(256)
+template <typename T, uint32_t D, uint32_t C, bool ALL_LEVELS, int UNROLL = 2, bool CS = false, int MAXT = 256>
+__global__ void __launch_bounds__(MAXT)
 k_grid_forward(const float *__restrict__ inputs, const T *__restrict__ grid, const int *__restrict__ offsets,
                T *__restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, T *__restrict__ dy_dx,
                uint32_t gridtype, bool align_corners, uint32_t interp) {
@@ -292,7 +294,7 @@ k_grid_forward(const float *__restrict__ inputs, const T *__restrict__ grid, con
     for (uint32_t d = 0; d < D; d++) x[d] = __ldg(inputs + (size_t)b * D + d);
     const bool oob = out_of_range<D>(x);
     const uint32_t l0 = ALL_LEVELS ? 0 : blockIdx.y, l1 = ALL_LEVELS ? L : blockIdx.y + 1;
-#pragma unroll 2
+#pragma unroll UNROLL
     for (uint32_t level = l0; level < l1; level++) {
         float res[C];
         T *dd = dy_dx ? dy_dx + ((size_t)b * L + level) * D * C : nullptr;
@@ -305,7 +307,7 @@ k_grid_forward(const float *__restrict__ inputs, const T *__restrict__ grid, con
             const LevelInfo li = level_info<D>(offsets, level, S, H, gridtype, align_corners);
             encode_level<T, D, C>(x, grid + (size_t)(uint32_t)__ldg(offsets + level) * C, li, align_corners, interp, res, dd);
         }
-        store_vec<T, C>(outputs + ((size_t)level * B + b) * C, res);
+        store_vec<T, C, CS>(outputs + ((size_t)level * B + b) * C, res);
     }
 }
 
@@ -485,8 +487,10 @@ constexpr uint32_t kBigBatch = 1u << 17;  // from here one thread walks all leve
 template <typename T, uint32_t D, uint32_t C>
 int launch_forward(const float *inputs, const T *emb, const int *offsets, T *outputs, uint32_t B, uint32_t L, float S,
                    uint32_t H, T *dy_dx, uint32_t gridtype, bool ac, uint32_t interp, cudaStream_t st) {
+    // all-levels form: 512-thread CTAs and streaming (evict-first) stores of the level-major outputs -- the best of the
+    // measured launch variants (profiles/r1d_experiments.md, runs 27 and 37); the outputs are written once and never re-read
     if (B >= kBigBatch && dy_dx == nullptr)
-        k_grid_forward<T, D, C, true><<<dim3(div_up(B, 256u), 1), 256, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac, interp);
+        k_grid_forward<T, D, C, true, 2, true, 512><<<dim3(div_up(B, 512u), 1), 512, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac, interp);
     else
         k_grid_forward<T, D, C, false><<<dim3(div_up(B, 256u), L), 256, 0, st>>>(inputs, emb, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac, interp);
     return (int)cudaPeekAtLastError();
