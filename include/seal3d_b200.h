@@ -198,6 +198,11 @@ int s3d_density_cells_to_xyz(const int *cell_morton, uint32_t n, uint32_t H, flo
 int s3d_density_scatter(const int *cell_morton, const float *sigma, uint32_t n, float density_scale, float *tmp_grid,
                         void *stream);
 int s3d_density_grid_ema(float *grid, const float *tmp_grid, uint32_t n, float decay, float *sum_out, void *stream);
+/* nerf/utils.py:53-140 get_rays: poses device [B,4,4] cam2world, pixel ids inds device int64 [inds_rows, N] (row * W + col,
+ * inds_rows = 1 shares them across views like the reference's expand, = B per view) or NULL for all H*W pixels in order;
+ * rays_o / rays_d [B,N,3] (unit directions) */
+int s3d_get_rays(const float *poses, uint32_t B, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W, const long long *inds,
+                 uint32_t inds_rows, uint32_t N, float *rays_o, float *rays_d, void *stream);
 /* nerf/renderer.py:379-443 mark_untrained_grid(poses, intrinsic): density_grid[c, cell] = -1 for every cell whose centre no camera
  * sees (in front, inside the frustum widened by one cell).  poses device [B,4,4] cam2world (B <= 4000), kx = cx/fx, ky = cy/fy,
  * count_out optional int32 [C, H^3] (morton order) = number of cameras per cell */

@@ -164,6 +164,23 @@ def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, we
                              _p(_f32(rgbs)), _p(_f32(deltas)), _p(weights_sum), _p(depth), _p(image))
 
 
+def get_rays(poses, intrinsics, H, W, inds=None):
+    """nerf/utils.py:53-140: poses [B,4,4], intrinsics (fx, fy, cx, cy), inds int64 [N] / [B,N] or None (all pixels)
+    -> rays_o, rays_d [B,N,3]"""
+    poses = _f32(poses).reshape(-1, 4, 4)
+    B = poses.shape[0]
+    fx, fy, cx, cy = [float(v) for v in intrinsics]
+    if inds is not None:
+        inds = np.ascontiguousarray(inds, dtype=np.int64)
+        rows = 1 if inds.ndim == 1 else inds.shape[0]
+        N = inds.shape[-1]
+    else:
+        rows, N = 1, H * W
+    ro, rd = np.empty((B, N, 3), np.float32), np.empty((B, N, 3), np.float32)
+    lib().orc_get_rays(_p(poses), u32(B), f32(fx), f32(fy), f32(cx), f32(cy), u32(W), _p(inds), u32(rows), u32(N), _p(ro), _p(rd))
+    return ro, rd
+
+
 def mark_untrained_count(poses, intrinsic, cascade=1, H=128, bound=1.0):
     """nerf/renderer.py:379-443: per-cell camera count [cascade, H^3] (morton order); the grid gets -1 where it is 0"""
     poses = _f32(poses).reshape(-1, 4, 4)

@@ -1218,3 +1218,29 @@ ORC_API void orc_mark_untrained_count(const float *poses, uint32_t B, float kx, 
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* nerf/utils.py:53-140 get_rays                                                          */
+/* ------------------------------------------------------------------------------------ */
+/* pixel id = row * W + col -> i = col + 0.5, j = row + 0.5 (:64-66), d = ((i-cx)/fx, (j-cy)/fy, 1) / |.| (:123-128),
+ * rays_d = d @ R^T, rays_o = t (:129-132).  inds: int64 [inds_rows, N] (inds_rows 1 or B) or NULL = all pixels.
+ * Pinned by tests/golden/cpu_get_rays.npz (the reference function run on CPU torch). */
+ORC_API void orc_get_rays(const float *poses, uint32_t B, float fx, float fy, float cx, float cy, uint32_t W, const int64_t *inds,
+                          uint32_t inds_rows, uint32_t N, float *rays_o, float *rays_d) {
+    for (uint32_t b = 0; b < B; b++) {
+        const float *P = poses + (size_t)b * 16;
+#pragma omp parallel for schedule(static)
+        for (int64_t n = 0; n < (int64_t)N; n++) {
+            const int64_t pix = inds ? inds[(size_t)(inds_rows == 1 ? 0 : b) * N + n] : n;
+            const float i = (float)(pix % W) + 0.5f, j = (float)(pix / W) + 0.5f;
+            const float x = (i - cx) / fx, y = (j - cy) / fy;
+            const float norm = sqrtf((x * x + y * y) + 1.0f);
+            const float d[3] = {x / norm, y / norm, 1.0f / norm};
+            float *o = rays_o + ((size_t)b * N + n) * 3, *r = rays_d + ((size_t)b * N + n) * 3;
+            for (int k = 0; k < 3; k++) {
+                r[k] = (d[0] * P[k * 4] + d[1] * P[k * 4 + 1]) + d[2] * P[k * 4 + 2];
+                o[k] = P[k * 4 + 3];
+            }
+        }
+    }
+}

@@ -53,6 +53,7 @@ _SIGS = {
     "s3d_ema_update": [P, P, U64, F32],
     "s3d_cast_f32_to_f16": [P, P, U64],
     "s3d_density_grid_ema": [P, P, U32, F32, P],
+    "s3d_get_rays": [P, U32, F32, F32, F32, F32, U32, U32, P, U32, U32, P, P],
     "s3d_mark_untrained_grid": [P, P, U32, F32, F32, U32, U32, F32, P],
     "s3d_density_cells_to_xyz": [P, U32, U32, F32, U32, P],
     "s3d_density_scatter": [P, P, U32, F32, P],

@@ -258,6 +258,27 @@ k_mark_untrained(float *__restrict__ grid, const float *__restrict__ poses, uint
     if (count == 0) grid[(size_t)cas * H3 + morton] = -1.0f;
 }
 
+// nerf/utils.py:53-140 get_rays: pixel (row * W + col) of view b -> ray origin (the camera centre) and unit direction
+// d = R . normalize((col + 0.5 - cx) / fx, (row + 0.5 - cy) / fy, 1), float32 in the reference's operation order
+__global__ void k_get_rays(const float *__restrict__ poses, uint32_t B, float fx, float fy, float cx, float cy, uint32_t W,
+                           const long long *__restrict__ inds, uint32_t inds_stride, uint32_t N, float *__restrict__ rays_o,
+                           float *__restrict__ rays_d) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)B * N) return;
+    const uint32_t b = (uint32_t)(t / N), n = (uint32_t)(t - (uint64_t)b * N);
+    const long long pix = inds ? inds[(size_t)b * inds_stride + n] : (long long)n;
+    const float i = __fadd_rn((float)(pix % W), 0.5f), j = __fadd_rn((float)(pix / W), 0.5f);
+    const float x = __fdiv_rn(__fsub_rn(i, cx), fx), y = __fdiv_rn(__fsub_rn(j, cy), fy);
+    const float norm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), 1.0f));
+    const float dx = __fdiv_rn(x, norm), dy = __fdiv_rn(y, norm), dz = __fdiv_rn(1.0f, norm);
+    const float *P = poses + (size_t)b * 16;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        rays_d[t * 3 + k] = __fadd_rn(__fadd_rn(__fmul_rn(dx, P[k * 4]), __fmul_rn(dy, P[k * 4 + 1])), __fmul_rn(dz, P[k * 4 + 2]));
+        rays_o[t * 3 + k] = P[k * 4 + 3];
+    }
+}
+
 // tmp[cell_morton[i]] = sigma[i]
 __global__ void k_density_scatter(const int *__restrict__ cell_morton, const float *__restrict__ sigma, uint32_t n, float scale, float *__restrict__ tmp) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -341,6 +362,18 @@ S3D_API int s3d_mark_untrained_grid(float *density_grid, const float *poses, uin
     if (B > 4000) return S3D_ENOTSUP;     // poses are staged in shared memory (48 B each)
     const uint32_t n = C * H * H * H;
     k_mark_untrained<<<div_up(n, 256u), 256, (size_t)B * 12 * sizeof(float), as_stream(stream)>>>(density_grid, poses, B, kx, ky, C, H, bound, count_out);
+    S3D_RETURN_LAST();
+}
+
+// nerf/utils.py:53-140.  poses device [B,4,4]; inds device int64 [B or 1, N] (row * W + col; inds_rows == 1: shared by all
+// views like the reference's expand) or NULL = all H*W pixels in order (then N must be H*W); rays_o / rays_d [B,N,3]
+S3D_API int s3d_get_rays(const float *poses, uint32_t B, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
+                         const long long *inds, uint32_t inds_rows, uint32_t N, float *rays_o, float *rays_d, void *stream) {
+    if (B == 0 || N == 0) return 0;
+    if (W == 0 || H == 0 || (inds == nullptr && N != H * W) || (inds && inds_rows != 1 && inds_rows != B)) return S3D_EINVAL;
+    const uint64_t total = (uint64_t)B * N;
+    k_get_rays<<<(unsigned)div_up(total, (uint64_t)256), 256, 0, as_stream(stream)>>>(poses, B, fx, fy, cx, cy, W, inds,
+                                                                                       inds_rows == 1 ? 0u : N, N, rays_o, rays_d);
     S3D_RETURN_LAST();
 }
 

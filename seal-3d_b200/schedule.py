@@ -40,6 +40,17 @@ def sample_points(bounds, point_step=0.005, angle_step=45):
     return torch.cat(pts).float(), torch.from_numpy(dirs.astype(np.float32))
 
 
+def rays_from_camera(intrinsic, H, W, device="cuda"):
+    """-> rays_of_view(pose) for proxy_dataset / train_one_epoch: all H*W rays of a view through the get_rays kernel
+    (utils.get_rays, nerf/utils.py:53-140)"""
+    from .utils import get_rays
+
+    def rays_of_view(pose):
+        out = get_rays(torch.as_tensor(np.asarray(pose, np.float32)).to(device).view(1, 4, 4), intrinsic, H, W, -1)
+        return out["rays_o"][0], out["rays_d"][0]
+    return rays_of_view
+
+
 class SealStudentSchedule:
     def __init__(self, trainer, num_rays=4096, log=None, consistent_depth=False):
         """consistent_depth: the reference compares the student's TRAINING depth (distance from the ray's near point: the

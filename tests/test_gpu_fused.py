@@ -438,6 +438,12 @@ def test_seal_student_schedule_config3_in_miniature(engine, scene):
     images, depths = sch.proxy_dataset(poses, rays_of_view, intrinsic=(1111.111, 1111.111, 400.0, 400.0))
     assert int((s.density_grid == -1).sum()) > 0            # cells outside every training frustum are marked untrained
     assert images.shape == (5, pix.shape[0], 3) and depths.shape == (5, pix.shape[0]) and torch.isfinite(images).all()
+    # the same rays from the get_rays kernel (what a dataset-backed run uses): camera intrinsics of the synthetic views
+    from seal3d_b200.schedule import rays_from_camera
+    ko, kd = rays_from_camera((synth.FOCAL, synth.FOCAL, synth.CX, synth.CY), 800, 800, dev())(poses[0])
+    so, sd = rays_of_view(poses[0])
+    np.testing.assert_allclose(npy(kd)[pix], sd, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(npy(ko)[pix], so, rtol=0, atol=1e-6)
     # the reference's own convention (eval depth = distance from the origin) differs by near * weights_sum
     ref_sch = SealStudentSchedule(tr, num_rays=4096)
     _, ref_depths = ref_sch.proxy_dataset(poses[:1], rays_of_view)

@@ -842,3 +842,27 @@ def test_mark_untrained_grid(tag, bound):
     assert int(npy(bits).astype(np.uint32).sum()) > 0
     cells = np.nonzero(grid[0] == -1)[0][:1000]
     assert not ((npy(bits)[cells // 8] >> (cells % 8)) & 1).any()
+
+
+def test_get_rays():
+    """kernel vs the oracle (exact: same float32 operation order) and vs the reference function's own output (golden)"""
+    from seal3d_b200.utils import get_rays
+    from seal3d_b200 import _lib
+    g = np.load(os.path.join(G, "cpu_get_rays.npz"))
+    H, W = int(g["H"]), int(g["W"])
+    out = get_rays(to(g["poses"]), g["intr_full"], H, W, -1)
+    ro, rd = oracle.get_rays(g["poses"], g["intr_full"], H, W)
+    assert np.array_equal(npy(out["rays_o"]), ro) and np.array_equal(npy(out["rays_d"]), rd) and "inds" not in out
+    np.testing.assert_allclose(npy(out["rays_d"]), g["full_d"], rtol=2e-6, atol=2e-7)
+    intr = (1111.111, 1111.111, 400.0, 400.0)
+    for inds in (g["inds"], g["inds"][0]):
+        out = get_rays(to(g["poses"]), intr, 800, 800, inds=to(inds))
+        np.testing.assert_allclose(npy(out["rays_d"]), g["some_d"], rtol=2e-6, atol=2e-7)
+        assert np.array_equal(npy(out["rays_o"]), g["some_o"]) and np.array_equal(npy(out["inds"]), g["inds"])
+    gen = torch.Generator(device=dev()).manual_seed(3)
+    a = get_rays(to(g["poses"]), intr, 800, 800, 4096, generator=gen)
+    assert a["rays_d"].shape == (3, 4096, 3) and int(a["inds"].max()) < 640000 and torch.equal(a["inds"][0], a["inds"][2])
+    with pytest.raises(NotImplementedError):
+        get_rays(to(g["poses"]), intr, 800, 800, 64, patch_size=8)
+    with pytest.raises(_lib.S3DError):
+        get_rays(torch.from_numpy(g["poses"]), intr, 800, 800, 64)          # CPU tensor: the reference would fail in the kernel launch too

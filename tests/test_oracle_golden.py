@@ -383,3 +383,18 @@ def test_mark_untrained_grid_matches_reference_method(tag, bound):
     diff = got != want
     assert diff.sum() <= 1e-5 * want.size, int(diff.sum())
     assert (count[diff] <= 1).all()
+
+
+def test_get_rays_matches_reference_function():
+    """nerf/utils.py:53-140 run on CPU torch (tests/golden/make_get_rays_golden.py) vs the oracle restatement"""
+    g = load("cpu_get_rays.npz")
+    ro, rd = oracle.get_rays(g["poses"], g["intr_full"], int(g["H"]), int(g["W"]))
+    np.testing.assert_allclose(rd, g["full_d"], rtol=2e-6, atol=2e-7)           # torch.norm / matmul may round one ulp differently
+    assert np.array_equal(ro, g["full_o"])
+    np.testing.assert_allclose(np.linalg.norm(rd, axis=-1), 1.0, atol=1e-6)
+    ro, rd = oracle.get_rays(g["poses"], (1111.111, 1111.111, 400.0, 400.0), 800, 800, g["inds"])
+    np.testing.assert_allclose(rd, g["some_d"], rtol=2e-6, atol=2e-7)
+    assert np.array_equal(ro, g["some_o"])
+    assert np.array_equal(g["inds"][0], g["inds"][1])                            # the reference shares the pixel draw across views
+    ro1, rd1 = oracle.get_rays(g["poses"], (1111.111, 1111.111, 400.0, 400.0), 800, 800, g["inds"][0])
+    assert np.array_equal(rd1, rd)
