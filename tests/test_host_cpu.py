@@ -214,3 +214,40 @@ def test_gradient_arena_chunks_tile_the_levels():
             assert a[1] == b[0] and a[3] == b[2] and a[1] % 4 == 0 and a[3] == int(off[a[1]]) * 4
     two = FusedNGP.grad_chunks(stub, 2)
     assert abs((two[0][3] - two[0][2]) - (two[1][3] - two[1][2])) < 0.4 * stub.grad.numel()      # about equal bytes
+
+
+def test_c_abi_argument_errors_are_reported_before_any_launch():
+    """the C-ABI validates shapes before touching the device: < 0 return codes (S3D_EINVAL -22 / S3D_ENOTSUP -95) for the
+    configurations the reference rejects with std::runtime_error / TORCH_CHECK; zero-sized batches return 0.  No kernel is
+    launched by any of these calls, so they run without a GPU."""
+    import ctypes as C
+    from seal3d_b200 import _lib
+    lib = _lib.lib()
+    EINVAL, ENOTSUP, n = -22, -95, None
+    dims = (C.c_int * 9)(*([4] * 9))
+    # grid encoder: unknown dtype, unsupported (D, C), empty batch
+    assert lib.s3d_grid_encode_forward(n, n, n, n, 16, 3, 2, 16, 0.5, 16, n, 0, 0, 0, 7, n) == EINVAL
+    assert lib.s3d_grid_encode_forward(n, n, n, n, 16, 5, 2, 16, 0.5, 16, n, 0, 0, 0, 0, n) == EINVAL
+    assert lib.s3d_grid_encode_forward(n, n, n, n, 0, 3, 2, 16, 0.5, 16, n, 0, 0, 0, 0, n) == 0
+    assert lib.s3d_grad_total_variation(n, n, n, n, 1.0, 16, 3, 2, 16, 0.5, 16, 0, 0, 1, n) == ENOTSUP      # fp16 TV is not a reference path
+    # FFMLP: hidden 128 / 256 and outputs > 16 are not built, input width must be a multiple of 16
+    assert lib.s3d_ffmlp_forward(n, n, 128, 32, 16, 128, 2, 0, 6, n, n, n) == ENOTSUP
+    assert lib.s3d_ffmlp_forward(n, n, 128, 32, 32, 64, 2, 0, 6, n, n, n) == ENOTSUP
+    assert lib.s3d_ffmlp_forward(n, n, 128, 30, 16, 64, 2, 0, 6, n, n, n) == EINVAL
+    assert lib.s3d_ffmlp_backward(n, n, n, n, 128, 32, 16, 64, 2, 2, 6, 1, n, n, n, n) == ENOTSUP        # sine activation has no backward
+    # VM lookups: rank multiple of 4; the reduced form needs a power-of-two group
+    assert lib.s3d_vm_forward(n, 8, n, n, n, n, n, n, n, dims, 6, 1, n, n) == EINVAL
+    assert lib.s3d_vm_forward(n, 8, n, n, n, n, n, n, n, dims, 48, 1, n, n) == ENOTSUP
+    assert lib.s3d_vm_forward(n, 0, n, n, n, n, n, n, n, dims, 16, 1, n, n) == 0
+    assert lib.s3d_vm_resize(n, 0, 4, n, 8, 8, 16, n) == EINVAL
+    # fused field: level ranges are whole 4-level groups, at most 16 levels
+    assert lib.s3d_ngp_scatter_levels(n, n, 8, 1.0, n, n, 16, 0.5, 16, 1.0, 2, 8, n) == EINVAL
+    assert lib.s3d_ngp_scatter_levels(n, n, 8, 1.0, n, n, 20, 0.5, 16, 1.0, 0, 8, n) == ENOTSUP
+    assert lib.s3d_ngp_scatter_levels(n, n, 8, 1.0, n, n, 16, 0.5, 16, 1.0, 8, 8, n) == 0
+    assert lib.s3d_ngp_encode(n, 8, 1.0, n, 12, n, 16, 0.5, 16, n, 0, n) == EINVAL                          # entry stride is 8 or 16 bytes
+    # density grid / rays
+    assert lib.s3d_mark_untrained_grid(n, n, 3, 0.5, 0.5, 0, 128, 1.0, n, n) == EINVAL
+    assert lib.s3d_mark_untrained_grid(n, n, 5000, 0.5, 0.5, 1, 128, 1.0, n, n) == ENOTSUP
+    assert lib.s3d_get_rays(n, 2, 1.0, 1.0, 0.5, 0.5, 4, 4, n, 1, 7, n, n, n) == EINVAL                     # all-pixels form needs N = H*W
+    assert lib.s3d_march_rays_train(n, n, n, 1.0, 0.0, 0, 8, 1, 128, 8, n, n, n, n, n, n, n, n, n) == EINVAL  # max_steps = 0
+    assert lib.s3d_march_rays_train(n, n, n, 1.0, 0.0, 1024, 0, 1, 128, 8, n, n, n, n, n, n, n, n, n) == 0
