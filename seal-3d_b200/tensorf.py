@@ -107,7 +107,9 @@ class TensoRFNetwork(NeRFRenderer):
         return nn.ParameterList(mat), nn.ParameterList(vec)
 
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
-        # a shrunk / upsampled reference checkpoint has other resolutions than the constructor's: re-allocate first
+        # a shrunk / upsampled reference checkpoint has other resolutions than the constructor's: re-allocate first.  Like
+        # upsample_model / shrink_model this replaces nn.Parameter objects, so a trainer built before must be rebuilt
+        # afterwards (the reference re-creates its optimizer at the same points, tensoRF/utils.py:126-128)
         for name in ("sigma_mat", "sigma_vec", "color_mat", "color_vec"):
             plist = getattr(self, name)
             for i in range(3):
