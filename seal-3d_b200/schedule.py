@@ -242,6 +242,35 @@ class SealStudentSchedule:
             tot = loss.clone() if tot is None else tot + loss
         return (tot / len(order)).tolist()
 
+    # -- evaluation ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def psnr(pred, truth):
+        """nerf/utils.py:207-235 PSNRMeter.update for one image with values in [0, 1]: -10 log10(mean squared error)"""
+        return float(-10.0 * torch.log10(torch.mean((pred.float() - truth.float()) ** 2)))
+
+    @torch.no_grad()
+    def evaluate(self, views=None):
+        """nerf/utils.py:907-1013 evaluate_one_epoch reduced to its metric: render the proxied views with the student (EMA
+        parameters if the trainer keeps an EMA, :919-921) and return the mean PSNR against the teacher's images"""
+        views = range(len(self.poses)) if views is None else views
+        tr = self.tr
+        use_ema = getattr(tr, "ema", None) is not None and hasattr(tr, "ema_apply")
+        if use_ema:
+            tr.ema_apply()
+        try:
+            vals = []
+            for v in views:
+                o, d = self._rays_of_view(self.poses[v])
+                o = torch.as_tensor(o, dtype=torch.float32).to(self.dev).view(-1, 3)
+                d = torch.as_tensor(d, dtype=torch.float32).to(self.dev).view(-1, 3)
+                fused = getattr(tr, "S", None)
+                out = fused.render_image(o, d, bg_color=1) if fused is not None else self.student.render_single_pass(o, d, bg_color=1)
+                vals.append(self.psnr(out["image"], self.images[v]))
+        finally:
+            if use_ema:
+                tr.ema_restore()
+        return sum(vals) / max(len(vals), 1)
+
     def train(self, max_epochs):
         """SealNeRF/trainer.py:323-349: the first `pretraining_epochs` epochs pretrain, the rest fine-tune"""
         first = self.epoch + 1

@@ -251,3 +251,15 @@ def test_c_abi_argument_errors_are_reported_before_any_launch():
     assert lib.s3d_get_rays(n, 2, 1.0, 1.0, 0.5, 0.5, 4, 4, n, 1, 7, n, n, n) == EINVAL                     # all-pixels form needs N = H*W
     assert lib.s3d_march_rays_train(n, n, n, 1.0, 0.0, 0, 8, 1, 128, 8, n, n, n, n, n, n, n, n, n) == EINVAL  # max_steps = 0
     assert lib.s3d_march_rays_train(n, n, n, 1.0, 0.0, 1024, 0, 1, 128, 8, n, n, n, n, n, n, n, n, n) == 0
+
+
+def test_schedule_psnr_matches_the_reference_meter():
+    """nerf/utils.py:207-235: psnr = -10 log10(mean((pred - truth)^2)) on [0,1] images"""
+    import numpy as np
+    import torch
+    from seal3d_b200.schedule import SealStudentSchedule
+    rng = np.random.default_rng(0)
+    a, b = rng.uniform(0, 1, (50, 40, 3)).astype(np.float32), rng.uniform(0, 1, (50, 40, 3)).astype(np.float32)
+    want = -10 * np.log10(np.mean((a - b) ** 2))
+    assert abs(SealStudentSchedule.psnr(torch.from_numpy(a), torch.from_numpy(b)) - want) < 1e-4
+    assert abs(SealStudentSchedule.psnr(torch.from_numpy(a), torch.from_numpy(a + 0.1)) - 20.0) < 1e-3
