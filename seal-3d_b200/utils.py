@@ -1,17 +1,30 @@
-"""Ray generation for the cuda-ray path -- mirror of ``nerf/utils.py::get_rays`` (:53-140) for the sampling modes the
-Seal-3D trainers use: all pixels (``N = -1``, evaluation / proxy_dataset) and ``N`` uniformly random pixels shared by the
-views of the batch (training).  Patch sampling and error-map sampling are not built."""
+"""Ray generation for the cuda-ray path -- mirror of ``nerf/utils.py::get_rays`` (:53-140): all pixels (``N = -1``,
+evaluation / proxy_dataset), ``N`` uniformly random pixels shared by the views of the batch (training) and patch sampling
+(``patch_size > 1``).  Error-map sampling (``torch.multinomial`` on a 128 x 128 error grid) is not built."""
 import torch
 
 from . import _lib
+
+
+def patch_indices(H, W, N, patch_size, device="cpu", generator=None):
+    """nerf/utils.py:73-92: N // patch_size^2 random patch corners, each expanded to a patch_size x patch_size block of
+    flat pixel ids (row * W + col) -> int64 [num_patch * patch_size^2]"""
+    num_patch = N // (patch_size ** 2)
+    inds_x = torch.randint(0, H - patch_size, size=[num_patch], device=device, generator=generator)
+    inds_y = torch.randint(0, W - patch_size, size=[num_patch], device=device, generator=generator)
+    inds = torch.stack([inds_x, inds_y], dim=-1)
+    pi, pj = torch.meshgrid(torch.arange(patch_size, device=device), torch.arange(patch_size, device=device), indexing="ij")
+    offsets = torch.stack([pi.reshape(-1), pj.reshape(-1)], dim=-1)
+    inds = (inds.unsqueeze(1) + offsets.unsqueeze(0)).view(-1, 2)
+    return inds[:, 0] * W + inds[:, 1]
 
 
 @torch.no_grad()
 def get_rays(poses, intrinsics, H, W, N=-1, error_map=None, patch_size=1, generator=None, inds=None):
     """poses [B,4,4] cam2world (CUDA), intrinsics (fx, fy, cx, cy) -> {'rays_o', 'rays_d' [B,N,3], 'inds' [B,N] (if N > 0)}.
     `inds` (int64 [N] or [B,N]) overrides the random draw; `generator` seeds it."""
-    if error_map is not None or patch_size > 1:
-        raise NotImplementedError("error-map and patch sampling of get_rays are not built (nerf/utils.py:73-113)")
+    if error_map is not None:
+        raise NotImplementedError("error-map sampling of get_rays is not built (nerf/utils.py:97-113)")
     poses = poses.contiguous().float()
     _lib.check_cuda(poses)
     dev, B = poses.device, poses.shape[0]
@@ -20,7 +33,10 @@ def get_rays(poses, intrinsics, H, W, N=-1, error_map=None, patch_size=1, genera
     if N > 0 or inds is not None:
         if inds is None:
             N = min(N, H * W)
-            inds = torch.randint(0, H * W, size=[N], device=dev, generator=generator)      # may duplicate, like the reference
+            if patch_size > 1:
+                inds = patch_indices(H, W, N, patch_size, dev, generator)
+            else:
+                inds = torch.randint(0, H * W, size=[N], device=dev, generator=generator)  # may duplicate, like the reference
         inds = inds.to(dev).long().contiguous()
         rows = 1 if inds.dim() == 1 else inds.shape[0]
         n = inds.shape[-1]

@@ -862,7 +862,10 @@ def test_get_rays():
     gen = torch.Generator(device=dev()).manual_seed(3)
     a = get_rays(to(g["poses"]), intr, 800, 800, 4096, generator=gen)
     assert a["rays_d"].shape == (3, 4096, 3) and int(a["inds"].max()) < 640000 and torch.equal(a["inds"][0], a["inds"][2])
+    pt = get_rays(to(g["poses"]), intr, 800, 800, 4096, patch_size=8, generator=gen)
+    ids = npy(pt["inds"][0]).reshape(-1, 8, 8)
+    assert ids.shape[0] == 64 and np.all(np.diff(ids, axis=2) == 1) and np.all(np.diff(ids, axis=1) == 800)      # 8 x 8 pixel blocks
     with pytest.raises(NotImplementedError):
-        get_rays(to(g["poses"]), intr, 800, 800, 64, patch_size=8)
+        get_rays(to(g["poses"]), intr, 800, 800, 64, error_map=torch.ones(3, 128 * 128))
     with pytest.raises(_lib.S3DError):
         get_rays(torch.from_numpy(g["poses"]), intr, 800, 800, 64)          # CPU tensor: the reference would fail in the kernel launch too

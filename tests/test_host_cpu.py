@@ -263,3 +263,17 @@ def test_schedule_psnr_matches_the_reference_meter():
     want = -10 * np.log10(np.mean((a - b) ** 2))
     assert abs(SealStudentSchedule.psnr(torch.from_numpy(a), torch.from_numpy(b)) - want) < 1e-4
     assert abs(SealStudentSchedule.psnr(torch.from_numpy(a), torch.from_numpy(a + 0.1)) - 20.0) < 1e-3
+
+
+def test_patch_indices_form_contiguous_pixel_blocks():
+    """nerf/utils.py:73-92 (patch sampling of get_rays): N // p^2 patches of p x p pixels, inside the image"""
+    import torch
+    from seal3d_b200.utils import patch_indices
+    gen = torch.Generator().manual_seed(0)
+    H, W, p = 60, 90, 4
+    inds = patch_indices(H, W, 100, p, generator=gen)
+    assert inds.shape == (6 * 16,) and inds.dtype == torch.int64
+    blocks = inds.view(6, p, p)
+    rows, cols = blocks // W, blocks % W
+    assert (rows[:, 1:, :] - rows[:, :-1, :] == 1).all() and (cols[:, :, 1:] - cols[:, :, :-1] == 1).all()
+    assert rows.min() >= 0 and rows.max() < H and cols.min() >= 0 and cols.max() < W
