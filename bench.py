@@ -23,6 +23,13 @@ import sys
 import tempfile
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm (rank 0 only) is meant to use every host thread it can,
+# and libgomp / the BLAS behind numpy read the variable when they are loaded -- so it is set before numpy is imported
+if "reference" in sys.argv[1:]:
+    _ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(_ncpu)
+
 import numpy as np
 
 # the sample budget M changes a little at every occupancy refresh: round large torch allocations up to 1/16 of a power of
@@ -75,11 +82,15 @@ class CpuDistill:
         self.t = 0
         self.aabb = np.array([-1, -1, -1, 1, 1, 1], np.float32)
 
-    def step(self, i):
+    def loss_terms(self, i):
+        """(MSE, L1 depth) of the unperturbed step i before any update -- what smoke() checks the fused engine against"""
+        return self.step(i, perturb=False, update=False)
+
+    def step(self, i, perturb=True, update=True):
         oc = self.oracle
         o, d = self.synth.rays_for_step(i, self.n)
         n, f = oc.near_far_from_aabb(o, d, self.aabb, 0.2)
-        noise = np.random.default_rng(i).uniform(0, 1, self.n).astype(np.float32)
+        noise = np.random.default_rng(i).uniform(0, 1, self.n).astype(np.float32) if perturb else np.zeros(self.n, np.float32)
         # count first (M=0 writes nothing), then allocate exactly
         _, _, _, rays, cnt = oc.march_rays_train(o, d, 1.0, self.bits, 1, 128, n, f, noise, M=0)
         M = int(cnt[0])
@@ -91,6 +102,8 @@ class CpuDistill:
         sig_s, rgb_s = self.student.forward(xyzs, dirs, keep=True)
         ws, dep, comp = oc.composite_rays_train_forward(sig_s, rgb_s, deltas, rays)
         loss, g_img, _ = oc.finetune_loss(comp + (1 - ws)[:, None], dep, img_t, dep_t)
+        if not update:
+            return float(((comp + (1 - ws)[:, None] - img_t) ** 2).mean(-1).mean()), float(np.abs(dep - dep_t).mean())
         g_ws = -g_img.sum(1)
         gs, gc = oc.composite_rays_train_backward(g_ws, g_img, sig_s, rgb_s, deltas, rays, ws, comp)
         gr = self.student.backward(gs, gc)
@@ -106,6 +119,13 @@ class CpuDistill:
 
 def cpu_arm(n_rays, steps, warmup):
     import oracle
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    oracle.set_num_threads(ncpu)        # explicit: an inherited OMP_NUM_THREADS=1 (torchrun) must not decide the baseline
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=ncpu)
+    except Exception:
+        pass
     c = CpuDistill(n_rays)
     for i in range(warmup):
         c.step(i)
@@ -348,6 +368,117 @@ def step_roofline(breakdown, samples_per_step, step_ms):
     return out
 
 
+class _Timer:
+    """start/stop pair: CUDA events on the current stream of a CUDA device, the host clock otherwise (the CPU / gloo test of
+    this file's control flow, tests/test_host_cpu.py)"""
+
+    def __init__(self, dev):
+        import torch
+        self.cuda = dev.type == "cuda"
+        if self.cuda:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def start(self):
+        if self.cuda:
+            self.e0.record()
+        else:
+            self.t0 = time.perf_counter()
+
+    def stop(self):
+        if self.cuda:
+            self.e1.record()
+        else:
+            self.t1 = time.perf_counter()
+
+    def ms(self):      # after a synchronize
+        return self.e0.elapsed_time(self.e1) if self.cuda else 1e3 * (self.t1 - self.t0)
+
+
+def timed_legs(tr, resident, host, args, rank, world, dev, pipelined, profile_hook=None):
+    """Everything of the GPU arm that happens after the world is built: warm-up, leg 1 (resident inputs), leg 2 (end to end),
+    the per-kernel breakdown.  EVERY rank executes EVERY trainer step in here -- each step contains the gradient all-reduce,
+    so a step taken by a subset of the ranks is an unmatched collective (the round-1 driver runs at N = 2, 4, 8 hung on
+    exactly that).  `tr` needs distill_step(o, d, perturb=, force_all_rays=, prefetch=) -> loss tensor, refresh_occupancy(),
+    student.mean_count and student.step_counter; `profile_hook` = (begin(), end() -> [(name, ms)]) around the breakdown steps."""
+    import torch
+    import torch.distributed as dist
+    from seal3d_b200 import parallel
+    pool = len(resident)
+    n = args.rays
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+
+    # warm-up (first steps run in exact mode and set mean_count)
+    for i in range(args.warmup):
+        o, d = resident[i % pool]
+        tr.distill_step(o, d, perturb=True, force_all_rays=(i < 2))
+    if tr.student.mean_count <= 0:
+        tr.refresh_occupancy()
+    if pipelined:   # the side stream, its allocator pool and the pinned-copy path are created on first use: outside the timed legs
+        for src in (resident, host):
+            for i in range(3):
+                tr.distill_step(*src[i % pool], perturb=True, prefetch=src[(i + 1) % pool] if i < 2 else None)
+    samples_per_step = float(tr.student.step_counter[:, 0].float().max().item())
+
+    # -- leg 1: resident inputs ---------------------------------------------------------------
+    barrier()
+    clocks = ClockSampler(dev.index) if dev.type == "cuda" else None
+    from seal3d_b200 import _lib
+    launches0 = _lib.LAUNCHES
+    tm = _Timer(dev)
+    tm.start()
+    for i in range(args.steps):
+        o, d = resident[i % pool]
+        if pipelined:   # the next batch is marched on a side stream under this step's field kernels (fused.py: _prefetch)
+            tr.distill_step(o, d, perturb=True, prefetch=resident[(i + 1) % pool] if i + 1 < args.steps else None)
+        else:
+            tr.distill_step(o, d, perturb=True)
+    tm.stop()
+    barrier()
+    ms = parallel.max_over_ranks(tm.ms(), dev)
+    clk = clocks.stop() if clocks is not None else None
+    gpu_launches = int(_lib.LAUNCHES - launches0)     # kernels launched through the C-ABI inside the timed region of leg 1
+
+    # -- leg 2: end to end through the public call, host buffers in, loss out, every step -------
+    barrier()
+    tm.start()
+    last = None
+    for i in range(args.steps):
+        ho, hd = host[i % pool]
+        if pipelined:   # pinned host buffers go in as they are: this step's copy + march were issued during the previous step
+            last = tr.distill_step(ho, hd, perturb=True, prefetch=host[(i + 1) % pool] if i + 1 < args.steps else None).cpu()
+        else:
+            o, d = ho.to(dev, non_blocking=True), hd.to(dev, non_blocking=True)
+            last = tr.distill_step(o, d, perturb=True).cpu()
+    tm.stop()
+    barrier()
+    ms_e2e = parallel.max_over_ranks(tm.ms(), dev)
+
+    # -- per-kernel breakdown of one step (events around every C-ABI launch; separate from the timed legs) -------
+    breakdown = None
+    if not args.no_roofline:
+        barrier()
+        nprof = 3
+        if profile_hook:
+            profile_hook[0]()
+        for i in range(nprof):
+            o, d = resident[i % pool]
+            tr.distill_step(o, d, perturb=True)
+        barrier()
+        agg = {}
+        for name, ms_k in (profile_hook[1]() if profile_hook else []):
+            agg.setdefault(name, [0.0, 0])
+            agg[name][0] += ms_k
+            agg[name][1] += 1
+        breakdown = {k: {"ms_per_step": v[0] / nprof, "calls_per_step": v[1] / nprof, "ms_per_call": v[0] / v[1]} for k, v in agg.items()}
+    barrier()
+    return dict(ms=ms, ms_e2e=ms_e2e, clocks=clk, gpu_launches=gpu_launches, samples_per_step=samples_per_step, last=last, breakdown=breakdown)
+
+
 def gpu_arm(args):
     import torch
     from seal3d_b200 import synth, parallel, _lib
@@ -369,78 +500,20 @@ def gpu_arm(args):
         o, d = synth.rays_for_step(1000 * rank + b, n)
         host.append((torch.from_numpy(o).pin_memory(), torch.from_numpy(d).pin_memory()))
     resident = [(o.to(dev), d.to(dev)) for o, d in host]
-
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-
-    # warm-up (first steps run in exact mode and set mean_count)
     pipelined = args.engine == "fused" and not args.no_prefetch
-    for i in range(args.warmup):
-        o, d = resident[i % pool]
-        tr.distill_step(o, d, perturb=True, force_all_rays=(i < 2))
-    if tr.student.mean_count <= 0:
-        tr.refresh_occupancy()
-    if pipelined:   # the side stream, its allocator pool and the pinned-copy path are created on first use: outside the timed legs
-        for src in (resident, host):
-            for i in range(3):
-                tr.distill_step(*src[i % pool], perturb=True, prefetch=src[(i + 1) % pool] if i < 2 else None)
-    samples_per_step = float(tr.student.step_counter[:, 0].float().max().item())
 
-    # -- leg 1: resident inputs ---------------------------------------------------------------
-    barrier()
-    clocks = ClockSampler(local)
-    launches0 = _lib.LAUNCHES if hasattr(_lib, "LAUNCHES") else 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        o, d = resident[i % pool]
-        if pipelined:   # the next batch is marched on a side stream under this step's field kernels (fused.py: _prefetch)
-            tr.distill_step(o, d, perturb=True, prefetch=resident[(i + 1) % pool] if i + 1 < args.steps else None)
-        else:
-            tr.distill_step(o, d, perturb=True)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    ms = parallel.max_over_ranks(ms, dev)
-    clk = clocks.stop()
-
-    # -- leg 2: end to end through the public call, host buffers in, loss out, every step -------
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    last = None
-    for i in range(args.steps):
-        ho, hd = host[i % pool]
-        if pipelined:   # pinned host buffers go in as they are: this step's copy + march were issued during the previous step
-            last = tr.distill_step(ho, hd, perturb=True, prefetch=host[(i + 1) % pool] if i + 1 < args.steps else None).cpu()
-        else:
-            o, d = ho.to(dev, non_blocking=True), hd.to(dev, non_blocking=True)
-            last = tr.distill_step(o, d, perturb=True).cpu()
-    e1.record()
-    barrier()
-    ms_e2e = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
-
-    # -- per-kernel breakdown of one step (events around every C-ABI launch; separate from the timed legs) -------
-    breakdown = None
-    if rank == 0 and not args.no_roofline:
+    def prof_begin():
         _lib.PROFILE = []
-        torch.cuda.synchronize()
-        nprof = 3
-        for i in range(nprof):
-            o, d = resident[i % pool]
-            tr.distill_step(o, d, perturb=True)
-        torch.cuda.synchronize()
-        agg = {}
-        for name, a, b in _lib.PROFILE:
-            agg.setdefault(name, [0.0, 0])
-            agg[name][0] += a.elapsed_time(b)
-            agg[name][1] += 1
+
+    def prof_end():
+        rows = [(name, a.elapsed_time(b)) for name, a, b in _lib.PROFILE]
         _lib.PROFILE = None
-        breakdown = {k: {"ms_per_step": v[0] / nprof, "calls_per_step": v[1] / nprof, "ms_per_call": v[0] / v[1]} for k, v in agg.items()}
+        return rows
+
+    r = timed_legs(tr, resident, host, args, rank, world, dev, pipelined, profile_hook=(prof_begin, prof_end))
     if rank != 0:
         return None
+    ms, ms_e2e, samples_per_step, last, breakdown = r["ms"], r["ms_e2e"], r["samples_per_step"], r["last"], r["breakdown"]
     rays_total = n * world * args.steps
     line = {
         "metric": "training rays/sec (Lego 800x800, NGP L16/F2, distill on)", "value": rays_total / (ms * 1e-3), "unit": "rays/s",
@@ -451,8 +524,8 @@ def gpu_arm(args):
                    "schedule": "fused teacher+student on shared samples; occupancy refresh every 16 steps" + ("; next batch marched on a side stream under the current step" if pipelined else ""),
                    "l2_note": "each step streams > 126 MB (samples + 4 tables + arena) so successive steps do not reuse L2 contents"},
         "e2e": {"value": rays_total / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(getattr(_lib, "LAUNCHES", 0) - launches0) if hasattr(_lib, "LAUNCHES") else None,
-        "clocks": clk, "loss_last": [float(v) for v in last.numpy()] if last is not None else None,
+        "gpu_launches": r["gpu_launches"],
+        "clocks": r["clocks"], "loss_last": [float(v) for v in last.numpy()] if last is not None else None,
     }
     line["config"]["engine"] = args.engine
     line["step_hbm_roofline"] = whole_step_roofline(n, samples_per_step, n * args.steps / (ms * 1e-3))
@@ -478,9 +551,22 @@ def main():
                 "e2e": {"value": r["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
-    line = gpu_arm(args)
-    if line is None:
-        return
+    import torch
+    try:
+        line = gpu_arm(args)
+        if line is not None:
+            finish_line(args, line)
+    finally:
+        # every rank leaves through here: the ranks that have nothing to print wait for rank 0's single-GPU extras, then
+        # the process group is torn down on all of them (no rank exits with a communicator another rank still uses)
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            try:
+                torch.distributed.barrier()
+            finally:
+                torch.distributed.destroy_process_group()
+
+
+def finish_line(args, line):
     import torch
     if not args.no_roofline:
         d0 = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))

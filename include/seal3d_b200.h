@@ -180,23 +180,47 @@ int s3d_adam_step(float *params, void *grads, float *exp_avg, float *exp_avg_sq,
                   const float *scaler_state, void *stream);
 /* torch.cuda.amp.GradScaler as the reference trainer drives it (nerf/utils.py:361,857-859: scale(loss).backward(),
  * step(optimizer), update()), kept ON THE DEVICE so a step never waits for the host:
- *   scaler_state = float[8]: [0] loss scale  [1] growth tracker  [2] found_inf  [3] optimizer steps applied
- *                            [4] 1/(1-beta1^t)  [5] 1/sqrt(1-beta2^t)   (t = [3], refreshed by _check)
+ *   scaler_state = float[16], two 8-float blocks (torch.optim.Adam counts steps per parameter, so the hash tables and the
+ *   MLP arena -- frozen during pretraining, SealNeRF/trainer.py:484-488 -- each get their own count):
+ *     block 0 (tables / a flat arena): [0] loss scale  [1] growth tracker  [2] found_inf  [3] optimizer steps applied
+ *                                      [4] 1/(1-beta1^t)  [5] 1/sqrt(1-beta2^t)   (t = [3], refreshed by _check)
+ *     block 1 = scaler_state + 8 (MLP): [8] scale, [10] found_inf (copies), [11] steps, [12] [13] bias corrections
  * s3d_grad_scaler_check scans the (all-reduced) gradient arena for non-finite values, sets found_inf and, when the
- * step will be applied, advances [3] and the bias corrections.  The Adam entry points, given scaler_state, divide the
+ * step will be applied, advances [3] (and [11] when advance_mlp != 0) and the bias corrections.  The Adam entry points,
+ * given scaler_state (block 0) or scaler_state + 8 (block 1), divide the
  * gradient by [0], use [4],[5] instead of the host `step`, and when found_inf is set only clear the gradient (the
  * skipped step of GradScaler.step).  s3d_grad_scaler_update = GradScaler.update(): backoff on overflow, growth after
  * growth_interval clean steps, found_inf reset.  scaler_state NULL = static scale through grad_scale (as before). */
-int s3d_grad_scaler_check(const float *grads, uint64_t n, float *scaler_state, float beta1, float beta2, void *stream);
+int s3d_grad_scaler_check(const float *grads, uint64_t n, float *scaler_state, float beta1, float beta2, int advance_mlp, void *stream);
 int s3d_grad_scaler_update(float *scaler_state, float growth_factor, float backoff_factor, uint32_t growth_interval, void *stream);
 /* torch_ema.ExponentialMovingAverage.update (nerf/utils.py:356-357,882-883): shadow -= (1 - decay) * (shadow - param) */
 int s3d_ema_update(float *shadow, const float *params, uint64_t n, float decay, void *stream);
 int s3d_cast_f32_to_f16(const float *src, void *dst, uint64_t n, void *stream);
-/* nerf/renderer.py:445-538 update_extra_state pieces */
+/* nerf/renderer.py:445-538 update_extra_state as a chain of launches without a host read (csrc/density.cu):
+ *   s3d_density_pick_cells   :487-499 the partial update's cell list for one cascade: cells_out[0, n_uniform) = morton3D of
+ *                            uniformly drawn coords, [n_uniform, n_uniform + n_occ) = draws (with repetition) from the occupied
+ *                            cells {density_grid_cas > 0}, compacted on the device in ascending order (replaces torch.nonzero);
+ *                            n_occupied_out (device uint32, optional) receives the size of that set
+ *   s3d_density_cells_to_xyz :470-479 / :501-509 cell -> centre in the cascade + uniform jitter of half a cell, one rounding per
+ *                            torch op; cell_morton NULL = cells 0..n-1 (the full sweep of the first 16 refreshes)
+ *   s3d_density_scatter      :483 / :513 tmp_grid[cell] = sigma * density_scale; a cell drawn more than once keeps its largest
+ *                            value (the reference's index_put keeps an arbitrary one); cell_morton NULL = identity
+ *   s3d_density_grid_update  :521-524 + :528 grid = max(grid * decay, tmp) where both >= 0; stats_out[0] = mean(clamp(grid, 0)),
+ *                            stats_out[1] = min(mean, density_thresh), reduced in a fixed order (bit-identical across ranks)
+ *   s3d_packbits_dev_thresh  :529-530 packbits with the threshold read from device memory (stats_out + 1)
+ *   s3d_mean_count           :533-536 int(sum(step_counter[:total_step, 0]) / total_step) -> device int (-1 when total_step = 0)
+ * Draws are a counter-based hash of (seed, index): every data-parallel rank derives the same cells and jitter from the
+ * step-derived seed.  s3d_density_grid_ema is the older single-launch EMA with an atomically accumulated sum. */
+int s3d_density_pick_cells(const float *density_grid_cas, uint32_t H, uint32_t n_uniform, uint32_t n_occ, uint32_t seed, int *cells_out,
+                           uint32_t *n_occupied_out, void *stream);
 int s3d_density_cells_to_xyz(const int *cell_morton, uint32_t n, uint32_t H, float bound_cas, uint32_t seed, float *xyz,
                              void *stream);
 int s3d_density_scatter(const int *cell_morton, const float *sigma, uint32_t n, float density_scale, float *tmp_grid,
                         void *stream);
+int s3d_density_grid_update(float *grid, const float *tmp_grid, uint32_t n, float decay, float density_thresh, float *stats_out,
+                            void *stream);
+int s3d_packbits_dev_thresh(const float *grid, uint32_t N, const float *density_thresh_dev, uint8_t *bitfield, void *stream);
+int s3d_mean_count(const int *step_counter, uint32_t total_step, int *mean_count_out, void *stream);
 int s3d_density_grid_ema(float *grid, const float *tmp_grid, uint32_t n, float decay, float *sum_out, void *stream);
 /* nerf/utils.py:53-140 get_rays: poses device [B,4,4] cam2world, pixel ids inds device int64 [inds_rows, N] (row * W + col,
  * inds_rows = 1 shares them across views like the reference's expand, = B per view) or NULL for all H*W pixels in order;

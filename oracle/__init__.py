@@ -46,6 +46,11 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n):
+    """OpenMP thread count of the C restatement (bench.py's CPU arm sets it explicitly: torchrun exports OMP_NUM_THREADS=1)"""
+    lib().orc_set_num_threads(C.c_int(int(n)))
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -162,6 +167,96 @@ def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, we
         assert a.dtype == t and a.flags.c_contiguous
     lib().orc_composite_rays(u32(n_alive), u32(n_step), f32(T_thresh), _p(rays_alive), _p(rays_t), _p(_f32(sigmas)),
                              _p(_f32(rgbs)), _p(_f32(deltas)), _p(weights_sum), _p(depth), _p(image))
+
+
+# ---------------------------------------------------------------------------- density-grid refresh
+def pcg_hash(v):
+    """the counter-based hash the device kernels draw from (csrc/density.cu: pcg): the reference uses torch's unseeded global
+    generator (nerf/renderer.py:479, 492, 496), whose stream cannot be reproduced, so parity of update_extra_state is defined
+    on an INJECTED stream -- this function regenerates the device's stream so a test can inject it here"""
+    v = np.asarray(v, dtype=np.uint64)
+    v = (v * 747796405 + 2891336453) & 0xFFFFFFFF
+    w = (((v >> ((v >> 28) + 4)) ^ v) * 277803737) & 0xFFFFFFFF
+    return (((w >> 22) ^ w) & 0xFFFFFFFF).astype(np.uint32)
+
+
+def density_draws(seed, n_uniform, n_occ, H):
+    """-> dict(coords int32 [n_uniform,3] in [0,H), occ_u32 uint32 [n_occ], jitter float32 [n_uniform+n_occ,3] in [0,1))
+    for one cascade, from seed (the per-cascade seed, (seed + 7919 * cas) & 0xffffffff in renderer.update_extra_state)"""
+    seed = np.uint32(seed & 0xFFFFFFFF)
+    draw = lambda sd, ctr: pcg_hash(np.uint32(sd) ^ pcg_hash(ctr))
+    c = draw(seed, np.arange(n_uniform * 3, dtype=np.uint64))
+    coords = ((c.astype(np.uint64) * H) >> 32).astype(np.int32).reshape(n_uniform, 3)
+    occ = draw(int(seed) ^ 0x9e3779b9, np.arange(n_occ, dtype=np.uint64))
+    n = n_uniform + n_occ
+    j = draw(int(seed) ^ 0x85ebca6b, np.arange(n * 3, dtype=np.uint64))
+    jitter = ((j >> 8).astype(np.float32) * np.float32(1.0 / 16777216.0)).reshape(n, 3)
+    return dict(coords=coords, occ_u32=occ, jitter=jitter)
+
+
+def density_cells_and_xyz(density_grid_cas, H, bound_cas, draws=None, jitter=None):
+    """nerf/renderer.py:457-479 (full sweep, draws=None: every cell once, jitter [H^3,3] injected) and :487-509 (partial
+    update: uniform coords + occupied cells indexed by injected draws) for ONE cascade -> (cells int64 [n] morton, xyz [n,3])"""
+    f32 = np.float32
+    if draws is None:
+        cells = np.arange(H ** 3, dtype=np.int64)
+        coords = morton3D_invert(cells.astype(np.int32))
+    else:
+        idx_u = morton3D(draws["coords"]).astype(np.int64)                          # :492-493
+        occ = np.nonzero(density_grid_cas > 0)[0]                                  # :495 (ascending)
+        if occ.shape[0] > 0:
+            k = ((draws["occ_u32"].astype(np.uint64) * np.uint64(occ.shape[0])) >> np.uint64(32)).astype(np.int64)   # :496 randint(0, Nz)
+            idx_o = occ[k]                                                          # :497
+        else:      # the reference raises here (randint(0, 0)); the device repeats the uniform half
+            idx_o = idx_u[np.arange(draws["occ_u32"].shape[0]) % max(idx_u.shape[0], 1)]
+        cells = np.concatenate([idx_u, idx_o])                                      # :500
+        coords = np.concatenate([draws["coords"], morton3D_invert(idx_o.astype(np.int32))])   # :498, :501
+        jitter = draws["jitter"]
+    xyzs = f32(2) * coords.astype(f32) / f32(H - 1) - f32(1)                        # :470 / :503
+    hgs = f32(bound_cas) / f32(H)                                                   # :475 / :505 (python floats; exact for powers of two)
+    cas = xyzs * (f32(bound_cas) - hgs)                                             # :477 / :507
+    cas = cas + (jitter.astype(f32) * f32(2) - f32(1)) * hgs                        # :479 / :509
+    return cells, cas.astype(f32)
+
+
+def density_grid_update(density_grid, tmp_grid, decay=0.95, density_thresh=0.01):
+    """nerf/renderer.py:521-530: EMA-max where both valid, mean of clamp(grid, 0), threshold, packbits
+    -> (grid float32, mean_density float, thresh float, bitfield uint8)"""
+    g = density_grid.astype(np.float32).copy()
+    valid = (g >= 0) & (tmp_grid >= 0)
+    g[valid] = np.maximum(g[valid] * np.float32(decay), tmp_grid[valid])
+    mean = float(np.float32(np.clip(g, 0, None).astype(np.float64).mean()))
+    thresh = min(mean, float(density_thresh))
+    return g, mean, thresh, packbits(g.reshape(-1), thresh)
+
+
+def update_extra_state(density_grid, density_fn, H, bound, density_scale, density_thresh, iter_density, per_cascade, step_counter,
+                       local_step, decay=0.95, duplicates="max"):
+    """nerf/renderer.py:445-538 for all cascades.  per_cascade[c] = dict(jitter=...) for a full sweep (iter_density < 16) or the
+    dict of density_draws for a partial update.  density_fn(xyz [n,3] float32) -> sigma [n] (WITHOUT density_scale, like
+    self.density(...)['sigma']).  A cell drawn more than once keeps the largest of its values (the reference's index_put
+    keeps an arbitrary one of them; the device takes the max so the result is deterministic); duplicates="last" = the
+    serial last-write-wins of CPU torch, which is what the committed run of the reference method did (cpu_extra_state.npz).
+    -> dict(grid, mean_density, thresh, bitfield, mean_count (None when local_step == 0), cells, xyz)"""
+    C = density_grid.shape[0]
+    tmp = -np.ones_like(density_grid, dtype=np.float32)
+    all_cells, all_xyz = [], []
+    for cas in range(C):
+        bound_cas = min(2 ** cas, bound)
+        if iter_density < 16:
+            cells, xyz = density_cells_and_xyz(density_grid[cas], H, bound_cas, None, per_cascade[cas]["jitter"])
+        else:
+            cells, xyz = density_cells_and_xyz(density_grid[cas], H, bound_cas, per_cascade[cas])
+        sig = np.asarray(density_fn(xyz), dtype=np.float32).reshape(-1) * np.float32(density_scale)   # :481-482 / :511-512
+        if duplicates == "max":
+            np.maximum.at(tmp[cas], cells, sig)                                                       # :483 / :513
+        else:
+            tmp[cas][cells] = sig
+        all_cells.append(cells); all_xyz.append(xyz)
+    g, mean, thresh, bits = density_grid_update(density_grid, tmp, decay, density_thresh)
+    total = min(16, local_step)                                                                       # :533
+    mean_count = int(step_counter[:total, 0].sum() / total) if total > 0 else None                    # :534-535
+    return dict(grid=g, mean_density=mean, thresh=thresh, bitfield=bits, mean_count=mean_count, cells=all_cells, xyz=all_xyz, tmp=tmp)
 
 
 def get_rays(poses, intrinsics, H, W, inds=None):

@@ -46,6 +46,14 @@ ORC_API int orc_num_threads(void) {
 #endif
 }
 
+ORC_API void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* raymarching/src/raymarching.cu                                                         */
 /* ------------------------------------------------------------------------------------ */

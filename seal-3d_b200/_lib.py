@@ -48,7 +48,7 @@ _SIGS = {
     "s3d_pretrain_loss": [P, P, P, P, U32, P, P, P],
     "s3d_finetune_loss": [P, P, P, P, P, U32, F32, P, P, P],
     "s3d_adam_step": [P, P, P, P, P, U64, F32, F32, F32, F32, U32, F32, I32, I32, P],
-    "s3d_grad_scaler_check": [P, U64, P, F32, F32],
+    "s3d_grad_scaler_check": [P, U64, P, F32, F32, I32],
     "s3d_grad_scaler_update": [P, F32, F32, U32],
     "s3d_ema_update": [P, P, U64, F32],
     "s3d_cast_f32_to_f16": [P, P, U64],
@@ -57,6 +57,10 @@ _SIGS = {
     "s3d_mark_untrained_grid": [P, P, U32, F32, F32, U32, U32, F32, P],
     "s3d_density_cells_to_xyz": [P, U32, U32, F32, U32, P],
     "s3d_density_scatter": [P, P, U32, F32, P],
+    "s3d_density_pick_cells": [P, U32, U32, U32, U32, P, P],
+    "s3d_density_grid_update": [P, P, U32, F32, F32, P],
+    "s3d_packbits_dev_thresh": [P, U32, P, P],
+    "s3d_mean_count": [P, U32, P],
     "s3d_ngp_interleave_tables": [P, P, P, U64],
     "s3d_ngp_encode": [P, U32, F32, P, U32, P, U32, F32, U32, P, I32],
     "s3d_ngp_pair_tables": [P, P, P, U64],
@@ -75,7 +79,7 @@ _NO_STREAM = {"s3d_allocate_splitk": [SZ], "s3d_free_splitk": []}
 _lib = None
 LAUNCHES = 0  # kernels launched through this binding (bench.py reports the per-run delta)
 PROFILE = None  # set to a list to record (name, start_event, end_event) per call (bench.py's per-kernel breakdown)
-_KERNELS_PER_CALL = {"s3d_march_rays_train": 3, "s3d_march_rays_train_count": 2, "s3d_ffmlp_backward": 2, "s3d_seal_map_color": 2, "s3d_seal_anchor_map_to_origin": 2, "s3d_seal_map_color_image": 2}
+_KERNELS_PER_CALL = {"s3d_density_pick_cells": 4, "s3d_density_grid_update": 2, "s3d_march_rays_train": 3, "s3d_march_rays_train_count": 2, "s3d_ffmlp_backward": 2, "s3d_seal_map_color": 2, "s3d_seal_anchor_map_to_origin": 2, "s3d_seal_map_color_image": 2}
 
 
 class S3DError(RuntimeError):

@@ -49,10 +49,13 @@ def _moment_views(trainer):
         return out
     S = trainer.S                                     # fused.FusedDistillTrainer: [N,4] interleaved table moments + MLP arena
     m4, v4 = S.m4.view(S.N, 4), S.v4.view(S.N, 4)
-    out[id(S.model.encoder.embeddings)] = (S.step_tables, m4[:, 0:2], v4[:, 0:2])
-    out[id(S.model.encoder_color.embeddings)] = (S.step_tables, m4[:, 2:4], v4[:, 2:4])
+    st_t, st_m = S.step_tables, S.step_mlp
+    if getattr(trainer, "scaler", None) is not None:  # dynamic loss scale: the host counters also count skipped steps
+        st_t, st_m = trainer.scaler.steps()
+    out[id(S.model.encoder.embeddings)] = (st_t, m4[:, 0:2], v4[:, 0:2])
+    out[id(S.model.encoder_color.embeddings)] = (st_t, m4[:, 2:4], v4[:, 2:4])
     for w, (off, k) in zip(S.weights, S._w_off):
-        out[id(w)] = (S.step_mlp, S.m_mlp[off:off + k].view_as(w), S.v_mlp[off:off + k].view_as(w))
+        out[id(w)] = (st_m, S.m_mlp[off:off + k].view_as(w), S.v_mlp[off:off + k].view_as(w))
     return out
 
 
@@ -104,7 +107,7 @@ def load_optimizer_state_dict(trainer, sd):
 
 
 def _scheduler_state_dict(trainer):
-    step = int(trainer.global_step)
+    step = int(getattr(trainer, "sched_step", trainer.global_step))     # LambdaLR counts train steps only, not pretraining
     base = list(trainer.lr) if isinstance(trainer.lr, (tuple, list)) else [trainer.lr]
     now = trainer.current_lr() if hasattr(trainer, "current_lr") else trainer.lr
     last = [now] if not isinstance(now, (tuple, list)) else list(now)
@@ -179,11 +182,18 @@ def load_checkpoint(path, trainer=None, model=None, model_only=False, map_locati
     if model_only or trainer is None:
         return list(res.missing_keys), list(res.unexpected_keys), ck
     trainer.global_step = int(ck.get("global_step", 0))
+    if hasattr(trainer, "sched_step"):
+        trainer.sched_step = int(ck.get("lr_scheduler", {}).get("last_epoch", trainer.global_step))
     if "optimizer" in ck:
         load_optimizer_state_dict(trainer, ck["optimizer"])
     if getattr(trainer, "scaler", None) is not None and "scaler" in ck:
         trainer.scaler.state[0] = float(ck["scaler"]["scale"])
+        trainer.scaler.state_mlp[0] = float(ck["scaler"]["scale"])
         trainer.scaler.state[1] = float(ck["scaler"].get("_growth_tracker", 0))
+    if getattr(trainer, "scaler", None) is not None and hasattr(trainer, "S"):
+        # with a device-side scaler the Adam kernels take their bias corrections from its applied-step counts
+        # (skipped steps excluded), not from the host counters: restore them from the optimizer entry
+        trainer.scaler.set_steps(trainer.S.step_tables, trainer.S.step_mlp)
     return list(res.missing_keys), list(res.unexpected_keys), ck
 
 

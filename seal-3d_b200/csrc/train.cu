@@ -127,7 +127,13 @@ k_adam(float *__restrict__ p, G *__restrict__ g, float *__restrict__ m, float *_
 }
 
 // ---- GradScaler state on the device (torch.cuda.amp.GradScaler semantics, nerf/utils.py:857-859) ----------------
-// state[0] scale | [1] growth tracker | [2] found_inf | [3] optimizer steps applied so far | [4] 1/(1-beta1^t) | [5] 1/sqrt(1-beta2^t)
+// state = float[16], two 8-float blocks with the same slot meaning, one per parameter family (torch.optim.Adam keeps a step
+// count per parameter: after a pretraining stage that trains the hash tables only, nerf SealNeRF/trainer.py:484-488, the MLP's
+// bias correction must start at t = 1 while the tables' continues):
+//   block 0 (tables, and any flat arena):  [0] scale | [1] growth tracker | [2] found_inf | [3] optimizer steps applied so far
+//                                          | [4] 1/(1-beta1^t) | [5] 1/sqrt(1-beta2^t)
+//   block 1 (state + 8, the MLP arena):    [8] scale (copy) | [10] found_inf (copy) | [11] steps | [12], [13] bias corrections
+// The Adam kernels read slots 0, 2, 4, 5 of whichever block they are handed.
 __global__ void __launch_bounds__(256)
 k_found_inf(const float *__restrict__ g, size_t n, float *__restrict__ state) {
     bool bad = false;
@@ -141,13 +147,21 @@ k_found_inf(const float *__restrict__ g, size_t n, float *__restrict__ state) {
     }
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) state[2] = 1.0f;
 }
-__global__ void k_scaler_prepare(float *__restrict__ state, float beta1, float beta2) {
-    if (state[2] == 0.0f) {   // the step will be applied: advance the optimizer's step count, refresh the bias corrections
+__global__ void k_scaler_prepare(float *__restrict__ state, float beta1, float beta2, int advance_mlp) {
+    if (state[2] == 0.0f) {   // the step will be applied: advance the optimizer's step counts, refresh the bias corrections
         const float t = state[3] + 1.0f;
         state[3] = t;
         state[4] = (float)(1.0 / (1.0 - pow((double)beta1, (double)t)));
         state[5] = (float)(1.0 / sqrt(1.0 - pow((double)beta2, (double)t)));
+        if (advance_mlp) {
+            const float tm = state[11] + 1.0f;
+            state[11] = tm;
+            state[12] = (float)(1.0 / (1.0 - pow((double)beta1, (double)tm)));
+            state[13] = (float)(1.0 / sqrt(1.0 - pow((double)beta2, (double)tm)));
+        }
     }
+    state[8] = state[0];
+    state[10] = state[2];
 }
 __global__ void k_scaler_update(float *__restrict__ state, float growth, float backoff, float interval) {
     if (state[2] != 0.0f) { state[0] *= backoff; state[1] = 0.0f; }
@@ -157,6 +171,8 @@ __global__ void k_scaler_update(float *__restrict__ state, float growth, float b
         else state[1] = tr;
     }
     state[2] = 0.0f;
+    state[8] = state[0];
+    state[10] = 0.0f;
 }
 
 // torch_ema.ExponentialMovingAverage.update: shadow -= (1 - decay) * (shadow - param)
@@ -189,29 +205,6 @@ __global__ void k_density_ema(float *__restrict__ grid, const float *__restrict_
     if ((threadIdx.x & 31) == 0) atomicAdd(sum, acc);
 }
 
-// cell index (morton within cascade) -> jittered query position (nerf/renderer.py:470-479, 503-509)
-__device__ __forceinline__ uint32_t pcg(uint32_t v) {
-    v = v * 747796405u + 2891336453u;
-    const uint32_t w = ((v >> ((v >> 28u) + 4u)) ^ v) * 277803737u;
-    return (w >> 22u) ^ w;
-}
-__global__ void k_density_cells_to_xyz(const int *__restrict__ cell_morton, uint32_t n, uint32_t H, float bound_cas, uint32_t seed,
-                                       float *__restrict__ xyz) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t idx = (uint32_t)cell_morton[i];
-    auto compact = [](uint32_t x) {
-        x &= 0x49249249u; x = (x | (x >> 2)) & 0xc30c30c3u; x = (x | (x >> 4)) & 0x0f00f00fu;
-        x = (x | (x >> 8)) & 0xff0000ffu; x = (x | (x >> 16)) & 0x0000ffffu; return x; };
-    const uint32_t c[3] = {compact(idx), compact(idx >> 1), compact(idx >> 2)};
-    const float hgs = bound_cas / (float)H;
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-        const float u = (float)(pcg(seed ^ pcg(i * 3u + d)) >> 8) * (1.0f / 16777216.0f);  // [0,1)
-        const float base = (2.0f * (float)c[d] / (float)(H - 1) - 1.0f) * (bound_cas - hgs);
-        xyz[(size_t)i * 3 + d] = base + (u * 2.0f - 1.0f) * hgs;
-    }
-}
 // nerf/renderer.py:379-443 mark_untrained_grid: a cell of cascade `cas` is "trained" if its centre, taken to camera space
 // (cam = (x - t) . R, poses are cam2world), lies in front of at least one camera and inside its frustum widened by one cell:
 // |cam.x| < cx/fx * cam.z + 2*half_grid_size (and the same for y).  Cells no camera sees get density -1.  The reference does
@@ -279,11 +272,6 @@ __global__ void k_get_rays(const float *__restrict__ poses, uint32_t B, float fx
     }
 }
 
-// tmp[cell_morton[i]] = sigma[i]
-__global__ void k_density_scatter(const int *__restrict__ cell_morton, const float *__restrict__ sigma, uint32_t n, float scale, float *__restrict__ tmp) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) tmp[(uint32_t)cell_morton[i]] = sigma[i] * scale;
-}
 
 }  // namespace
 
@@ -318,10 +306,10 @@ S3D_API int s3d_adam_step(float *params, void *grads, float *exp_avg, float *exp
     S3D_RETURN_LAST();
 }
 
-S3D_API int s3d_grad_scaler_check(const float *grads, uint64_t n, float *scaler_state, float beta1, float beta2, void *stream) {
+S3D_API int s3d_grad_scaler_check(const float *grads, uint64_t n, float *scaler_state, float beta1, float beta2, int advance_mlp, void *stream) {
     cudaStream_t st = as_stream(stream);
     if (n) k_found_inf<<<(unsigned)min((size_t)div_up((size_t)n, (size_t)1024), (size_t)2368), 256, 0, st>>>(grads, (size_t)n, scaler_state);
-    k_scaler_prepare<<<1, 1, 0, st>>>(scaler_state, beta1, beta2);
+    k_scaler_prepare<<<1, 1, 0, st>>>(scaler_state, beta1, beta2, advance_mlp);
     S3D_RETURN_LAST();
 }
 
@@ -348,11 +336,6 @@ S3D_API int s3d_density_grid_ema(float *grid, const float *tmp_grid, uint32_t n,
     S3D_RETURN_LAST();
 }
 
-S3D_API int s3d_density_cells_to_xyz(const int *cell_morton, uint32_t n, uint32_t H, float bound_cas, uint32_t seed, float *xyz, void *stream) {
-    if (n == 0) return 0;
-    k_density_cells_to_xyz<<<div_up(n, 256u), 256, 0, as_stream(stream)>>>(cell_morton, n, H, bound_cas, seed, xyz);
-    S3D_RETURN_LAST();
-}
 
 // nerf/renderer.py:379-443.  poses: device [B,4,4] cam2world; kx = cx/fx, ky = cy/fy; count_out (optional, int32 [C,H^3],
 // morton order) receives the number of cameras that see each cell; density_grid[c, cell] = -1 where that number is 0.
@@ -377,8 +360,3 @@ S3D_API int s3d_get_rays(const float *poses, uint32_t B, float fx, float fy, flo
     S3D_RETURN_LAST();
 }
 
-S3D_API int s3d_density_scatter(const int *cell_morton, const float *sigma, uint32_t n, float density_scale, float *tmp_grid, void *stream) {
-    if (n == 0) return 0;
-    k_density_scatter<<<div_up(n, 256u), 256, 0, as_stream(stream)>>>(cell_morton, sigma, n, density_scale, tmp_grid);
-    S3D_RETURN_LAST();
-}

@@ -171,9 +171,11 @@ class FusedNGP:
             return
         _lib.call("s3d_ngp_scatter", xyz, dfeats, M, self.bound, self.grad4, self.offsets, self.L, self.S, self.H, 1.0)
 
-    def adam_step(self, lr, grad_scale=1.0, beta1=0.9, beta2=0.99, eps=1e-15, train_mlp=True, scaler_state=None, lr_mlp=None):
-        """fused Adam over the tables (+ MLP arena).  `scaler_state` = device GradScaler state (see GradScalerState): the
-        kernels then take scale, skip decision and bias corrections from it instead of the host-side step counts."""
+    def adam_step(self, lr, grad_scale=1.0, beta1=0.9, beta2=0.99, eps=1e-15, train_mlp=True, scaler_state=None, lr_mlp=None,
+                  scaler_state_mlp=None):
+        """fused Adam over the tables (+ MLP arena).  `scaler_state` / `scaler_state_mlp` = the two blocks of the device
+        GradScaler state (see GradScalerState): the kernels then take scale, skip decision and bias corrections from them
+        instead of the host-side step counts (which, with a dynamic scaler, also count skipped steps)."""
         enc, encc = self.model.encoder, self.model.encoder_color
         self.step_tables += 1
         _lib.call("s3d_ngp_adam_tables", enc.embeddings.data, encc.embeddings.data, self.grad4, self.m4, self.v4, self._table_ptr(), self._tbl_stride,
@@ -181,9 +183,11 @@ class FusedNGP:
         if train_mlp:
             self.step_mlp += 1
             _lib.call("s3d_adam_step", self.mlp32, self.gmlp, self.m_mlp, self.v_mlp, self.mlp16, self.n_mlp, float(lr if lr_mlp is None else lr_mlp),
-                      beta1, beta2, eps, self.step_mlp, float(grad_scale), 1, 0, scaler_state)
+                      beta1, beta2, eps, self.step_mlp, float(grad_scale), 1, 0, scaler_state_mlp if scaler_state is not None else None)
         else:
             self.gmlp.zero_()
+        # raw-pointer parameter updates do not bump torch's version counter: mark the modules' cached fp16 tables stale
+        enc._shadow_version = encc._shadow_version = -1
 
     # ---- parameter views for EMA / checkpoints: (tensor, ...) in the order tables, MLP arena
     def param_tensors(self):
@@ -191,20 +195,36 @@ class FusedNGP:
 
 
 class GradScalerState:
-    """torch.cuda.amp.GradScaler (nerf/utils.py:361, 857-859) with its state on the device: float[8] =
-    [scale, growth_tracker, found_inf, optimizer_steps, 1/(1-b1^t), 1/sqrt(1-b2^t), -, -].  Nothing here syncs with the host."""
+    """torch.cuda.amp.GradScaler (nerf/utils.py:361, 857-859) with its state on the device: float[16] = two blocks of
+    [scale, growth_tracker, found_inf, optimizer_steps, 1/(1-b1^t), 1/sqrt(1-b2^t), -, -] -- block 0 for the hash tables (or a
+    flat arena), block 1 (`state_mlp`) for the MLP arena, whose step count advances only when the MLP is trained (torch's
+    Adam keeps a step per parameter; pretraining freezes the MLP).  Nothing here syncs with the host."""
 
     def __init__(self, device, init_scale=65536.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000):
-        self.state = torch.zeros(8, dtype=torch.float32, device=device)
+        self._all = torch.zeros(16, dtype=torch.float32, device=device)
+        self.state, self.state_mlp = self._all[:8], self._all[8:]
         self.state[0] = float(init_scale)
+        self.state_mlp[0] = float(init_scale)
         self.growth_factor, self.backoff_factor, self.growth_interval = float(growth_factor), float(backoff_factor), int(growth_interval)
+
+    def set_steps(self, step_tables, step_mlp, beta1=0.9, beta2=0.99):
+        """resume: applied-step counts of the two parameter families + the bias corrections the Adam kernels read"""
+        for blk, t in ((self.state, int(step_tables)), (self.state_mlp, int(step_mlp))):
+            blk[3] = float(t)
+            blk[4] = 1.0 / (1.0 - beta1 ** t) if t > 0 else 0.0
+            blk[5] = 1.0 / (1.0 - beta2 ** t) ** 0.5 if t > 0 else 0.0
+
+    def steps(self):
+        """(tables, MLP) optimizer steps actually applied (skipped steps are not counted) -- one host read"""
+        st = self._all.detach().cpu()
+        return int(st[3]), int(st[11])
 
     @property
     def scale_tensor(self):
         return self.state[0]      # 0-dim device tensor: usable as a multiplier without a host read
 
-    def check(self, grad_arena, beta1=0.9, beta2=0.99):
-        _lib.call("s3d_grad_scaler_check", grad_arena, grad_arena.numel(), self.state, beta1, beta2)
+    def check(self, grad_arena, beta1=0.9, beta2=0.99, advance_mlp=True):
+        _lib.call("s3d_grad_scaler_check", grad_arena, grad_arena.numel(), self.state, beta1, beta2, int(advance_mlp))
 
     def update(self):
         _lib.call("s3d_grad_scaler_update", self.state, self.growth_factor, self.backoff_factor, self.growth_interval)
@@ -263,6 +283,9 @@ class FusedDistillTrainer:
         self.max_steps, self.dt_gamma, self.world_size, self.update_interval = max_steps, dt_gamma, world_size, update_interval
         self.loss_buf = torch.zeros(2, dtype=torch.float32, device=self.S.dev)
         self.global_step = 0
+        # LambdaLR position: advanced by finetune / distill steps only; pretraining runs at a forced constant lr and leaves
+        # the scheduler alone (SealNeRF/trainer.py:431-432, :491-503), so fine-tuning starts the decay from step 0
+        self.sched_step, self.lr_forced = 0, False
         self.table8 = None
         # data parallel: optionally (S3D_GRAD_CHUNKS = 2..4) the table gradient is scattered in level chunks and each finished
         # slice is all-reduced (async, NCCL's own stream) under the next chunk.  Measured on 8 B200s: 2 chunks 8.26 ms/step,
@@ -295,14 +318,14 @@ class FusedDistillTrainer:
         return float(self.loss_scale) if self.loss_scale is not None else 32.0 * float(units)
 
     def current_lr(self):
-        if not self.lr_decay_iters:
+        if not self.lr_decay_iters or self.lr_forced:
             return self.lr
-        return self.lr * 0.1 ** min(self.global_step / float(self.lr_decay_iters), 1.0)
+        return self.lr * 0.1 ** min(self.sched_step / float(self.lr_decay_iters), 1.0)
 
     def _start_reduce(self, i, a0, a1):
         self._pending.append(dist.all_reduce(self.S.grad[a0:a1], async_op=True))
 
-    def _reduce_and_step(self, scale, train_mlp=True):
+    def _reduce_and_step(self, scale, train_mlp=True, advance_schedule=True):
         if self.world_size > 1:
             if self._pending:              # the chunks of the gradient arena, each started right after its scatter launch
                 for w in self._pending:
@@ -312,12 +335,15 @@ class FusedDistillTrainer:
                 dist.all_reduce(self.S.grad)   # one collective over the whole arena
         if self.scaler is not None:
             # the check runs on the all-reduced arena, so every rank takes the same skip / backoff decision
-            self.scaler.check(self.S.grad)
-            self.S.adam_step(self.current_lr(), grad_scale=1.0 / self.world_size, train_mlp=train_mlp, scaler_state=self.scaler.state)
+            self.scaler.check(self.S.grad, advance_mlp=train_mlp)
+            self.S.adam_step(self.current_lr(), grad_scale=1.0 / self.world_size, train_mlp=train_mlp, scaler_state=self.scaler.state,
+                             scaler_state_mlp=self.scaler.state_mlp)
             self.scaler.update()
         else:
             self.S.adam_step(self.current_lr(), grad_scale=1.0 / (self.world_size * scale), train_mlp=train_mlp)
         self.global_step += 1
+        if advance_schedule:
+            self.sched_step += 1
 
     def ema_update(self):
         if self.ema is not None:
@@ -487,11 +513,12 @@ class FusedDistillTrainer:
         g_s.mul_(scale)
         g_c.mul_(scale)
         self.S.backward(points, dirs, feats, g_s, g_c, train_mlp=False)
-        self._reduce_and_step(scale, train_mlp=False)
+        self._reduce_and_step(scale, train_mlp=False, advance_schedule=False)
         return self.loss_buf
 
     def _maybe_update_grid(self):
-        if self.update_interval and self.global_step % self.update_interval == 0 and self.global_step > 0:
+        # nerf/utils.py:845-847: `global_step % update_extra_interval == 0`, step 0 included
+        if self.update_interval and self.global_step % self.update_interval == 0:
             self.refresh_occupancy()
 
     @torch.no_grad()

@@ -17,6 +17,8 @@ from . import raymarching
 class NeRFRenderer(nn.Module):
     def __init__(self, bound=1, cuda_ray=True, density_scale=1, min_near=0.2, density_thresh=0.01, bg_radius=-1):
         super().__init__()
+        self._density_stats = self._mean_count_dev = None
+        self._mean_density_host = 0
         self.bound = bound
         self.cascade = 1 + math.ceil(math.log2(bound))
         self.grid_size = 128
@@ -164,45 +166,58 @@ class NeRFRenderer(nn.Module):
 
     @torch.no_grad()
     def update_extra_state(self, decay=0.95, S=128, seed=None):
-        """nerf/renderer.py:445-538: full sweep for the first 16 calls, then H^3/4 uniform + H^3/4 occupied cells;
-        EMA-max into density_grid, mean density, packbits with min(mean, density_thresh), mean_count from the ring."""
+        """nerf/renderer.py:445-538: full sweep for the first 16 calls, then H^3/4 uniform + H^3/4 occupied cells; EMA-max
+        into density_grid, mean density, packbits with min(mean, density_thresh), mean_count from the ring.
+
+        One chain of launches (csrc/density.cu) with a single 4-byte host read at the end (mean_count, which sizes the next
+        march's sample buffers -- the reference reads it the same way, :536); the occupied-cell set is compacted on the
+        device instead of torch.nonzero, the bitfield threshold min(mean_density, density_thresh) stays in device memory,
+        and `mean_density` is read back only when somebody asks for it.  All draws (cells, jitter) are a counter-based hash
+        of `seed`, so data-parallel replicas that pass the same seed stay bit-identical without a broadcast; seed=None
+        draws one from torch's generator like the reference's unseeded calls.  `S` is accepted and ignored."""
         if not self.cuda_ray:
             return
         dev = self.density_bitfield.device
         H = self.grid_size
-        tmp_grid = -torch.ones_like(self.density_grid)
+        n_cells = H ** 3
+        tmp_grid = torch.full_like(self.density_grid, -1.0)
         seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if seed is None else int(seed)
+        full = self.iter_density < 16
+        n = n_cells if full else 2 * (n_cells // 4)
+        cells = None if full else torch.empty(n, dtype=torch.int32, device=dev)
+        xyz = torch.empty(n, 3, dtype=torch.float32, device=dev)
         for cas in range(self.cascade):
-            if self.iter_density < 16:
-                cells = torch.arange(H ** 3, dtype=torch.int32, device=dev)
-            else:
-                n = H ** 3 // 4
-                coords = torch.randint(0, H, (n, 3), device=dev)
-                rnd = raymarching.morton3D(coords)
-                occ = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
-                if occ.shape[0] > 0:
-                    pick = occ[torch.randint(0, occ.shape[0], [n], dtype=torch.long, device=dev)].int()
-                    cells = torch.cat([rnd, pick], dim=0)
-                else:
-                    cells = rnd
-            n = cells.shape[0]
+            cseed = (seed + 7919 * cas) & 0xFFFFFFFF
+            if not full:
+                _lib.call("s3d_density_pick_cells", self.density_grid[cas], H, n_cells // 4, n_cells // 4, cseed, cells, None)
             bound_cas = min(2 ** cas, self.bound)
-            xyz = torch.empty(n, 3, dtype=torch.float32, device=dev)
-            _lib.call("s3d_density_cells_to_xyz", cells, n, H, float(bound_cas), (seed + 7919 * cas) & 0xFFFFFFFF, xyz)
-            chunk = 1 << 21
-            for s in range(0, n, chunk):
-                sig = self.density(xyz[s:s + chunk])["sigma"].reshape(-1).detach().float().contiguous()
-                _lib.call("s3d_density_scatter", cells[s:s + chunk], sig, sig.shape[0], float(self.density_scale), tmp_grid[cas])
-        acc = torch.zeros(1, dtype=torch.float32, device=dev)
-        _lib.call("s3d_density_grid_ema", self.density_grid, tmp_grid, self.density_grid.numel(), float(decay), acc)
-        self.mean_density = float(acc.item()) / self.density_grid.numel()
+            _lib.call("s3d_density_cells_to_xyz", cells, n, H, float(bound_cas), cseed, xyz)
+            sig = self.density(xyz)["sigma"].reshape(-1).detach().float().contiguous()
+            _lib.call("s3d_density_scatter", cells, sig, n, float(self.density_scale), tmp_grid[cas])
+        if self._density_stats is None or self._density_stats.device != dev:
+            self._density_stats = torch.zeros(2, dtype=torch.float32, device=dev)
+            self._mean_count_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.call("s3d_density_grid_update", self.density_grid, tmp_grid, self.density_grid.numel(), float(decay), float(self.density_thresh),
+                  self._density_stats)
+        self._mean_density_host = None            # stale: the property reads stats[0] when asked
         self.iter_density += 1
-        density_thresh = min(self.mean_density, self.density_thresh)
-        self.density_bitfield = raymarching.packbits(self.density_grid, density_thresh, self.density_bitfield)
+        _lib.call("s3d_packbits_dev_thresh", self.density_grid, self.density_bitfield.numel(), self._density_stats[1:], self.density_bitfield)
         total_step = min(16, self.local_step)
         if total_step > 0:
-            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+            _lib.call("s3d_mean_count", self.step_counter, total_step, self._mean_count_dev)
+            self.mean_count = int(self._mean_count_dev.item())     # the one host read: it sizes the next march's buffers
         self.local_step = 0
+
+    # mean_density lives on the device after a refresh (stats[0]); reading the attribute is what costs the host read
+    @property
+    def mean_density(self):
+        if self._mean_density_host is None and self._density_stats is not None:
+            self._mean_density_host = float(self._density_stats[0].item())
+        return self._mean_density_host if self._mean_density_host is not None else 0
+
+    @mean_density.setter
+    def mean_density(self, v):
+        self._mean_density_host = v
 
     def render(self, rays_o, rays_d, **kwargs):
         if not self.cuda_ray:

@@ -77,10 +77,12 @@ class SealStudentSchedule:
             if getattr(self, "_cached_lr", None) is None:
                 return
             tr.lr, self._cached_lr = self._cached_lr, None
+            tr.lr_forced = False
         else:
             if getattr(self, "_cached_lr", None) is None:
                 self._cached_lr = tr.lr
             tr.lr = lr
+            tr.lr_forced = True       # a forced lr is constant: the trainer's LambdaLR factor is bypassed while it is set
 
     # -- stage 1 ----------------------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -57,6 +57,7 @@ class ParamArena:
                     o, k = self.offsets[id(mod.embeddings)]
                     mod.external_shadow = self.shadow[o:o + k].view(mod.embeddings.shape)
         self.steps = {}
+        self._shadowed = [mod for mod in model.modules() if hasattr(mod, "half_table") and hasattr(mod, "embeddings")]
 
     def segment(self, p):
         return self.offsets[id(p)]
@@ -84,11 +85,16 @@ class ParamArena:
                       st, float(grad_scale), 1, 0, None)
         if only is not None:
             self.grad.zero_()
+        if self.shadow is None:
+            # the kernels write the parameters through raw pointers, which does not bump torch's version counter: without an
+            # arena-kept shadow, tell the encoders their cached fp16 table (GridEncoder.half_table) is stale
+            for mod in self._shadowed:
+                mod._shadow_version = -1
 
 
 class DistillTrainer:
     def __init__(self, student, teacher=None, lr=1e-2, precision="fp32", loss_scale=1.0, bg_color=1.0, T_thresh=1e-4,
-                 max_steps=1024, dt_gamma=0.0, world_size=1, update_interval=16):
+                 max_steps=1024, dt_gamma=0.0, world_size=1, update_interval=16, lr_decay_iters=None):
         self.student, self.teacher = student, teacher
         self.lr, self.bg_color, self.T_thresh, self.max_steps, self.dt_gamma = lr, float(bg_color), T_thresh, max_steps, dt_gamma
         self.precision, self.loss_scale = precision, float(loss_scale)
@@ -98,6 +104,9 @@ class DistillTrainer:
         dev = self.arena.flat.device
         self.loss_buf = torch.zeros(2, dtype=torch.float32, device=dev)
         self.global_step = 0
+        # LambdaLR position (main_SealNeRF.py:287-288): only train steps advance it -- the reference's pretraining leaves the
+        # scheduler alone (SealNeRF/trainer.py:431-432, commented out) and runs at a forced, constant lr (:491-503)
+        self.sched_step, self.lr_decay_iters, self.lr_forced = 0, lr_decay_iters, False
         # pretraining freezes the NGP MLPs (SealNeRF/trainer.py:472-488 freeze_mlp); for TensoRF nothing is frozen (:476-483)
         self._tables_only = ({id(student.encoder.embeddings), id(student.encoder_color.embeddings)}
                              if hasattr(student, "encoder_color") else None)
@@ -106,11 +115,20 @@ class DistillTrainer:
     def _autocast(self):
         return torch.autocast(device_type="cuda", dtype=torch.float16, enabled=(self.precision == "fp16"))
 
-    def _reduce_and_step(self, only=None):
+    def current_lr(self):
+        """lr * 0.1 ** min(sched_step / iters, 1); a forced lr (pretraining) is not decayed"""
+        if not self.lr_decay_iters or self.lr_forced:
+            return self.lr
+        k = 0.1 ** min(self.sched_step / float(self.lr_decay_iters), 1.0)
+        return [v * k for v in self.lr] if isinstance(self.lr, (tuple, list)) else self.lr * k
+
+    def _reduce_and_step(self, only=None, advance_schedule=True):
         if self.world_size > 1:
             dist.all_reduce(self.arena.grad)  # the single collective of the step (NCCL over NVLink / NVSwitch)
-        self.arena.adam_step(self.lr, grad_scale=1.0 / (self.world_size * self.loss_scale), only=only)
+        self.arena.adam_step(self.current_lr(), grad_scale=1.0 / (self.world_size * self.loss_scale), only=only)
         self.global_step += 1
+        if advance_schedule:
+            self.sched_step += 1
 
     def _student_render(self, rays_o, rays_d, perturb, force_all_rays):
         s = self.student
@@ -152,7 +170,7 @@ class DistillTrainer:
             g_s.mul_(self.loss_scale)
             g_c.mul_(self.loss_scale)
         torch.autograd.backward([sig_s, rgb_s], [g_s, g_c])
-        self._reduce_and_step(only=self._tables_only)
+        self._reduce_and_step(only=self._tables_only, advance_schedule=False)
         return self.loss_buf
 
     def finetune_step(self, rays_o, rays_d, image_t, depth_t=None, perturb=True, force_all_rays=False):
@@ -189,7 +207,8 @@ class DistillTrainer:
         return loss
 
     def _maybe_update_grid(self):
-        if self.update_interval and self.global_step % self.update_interval == 0 and self.global_step > 0:
+        # nerf/utils.py:845-847: `global_step % update_extra_interval == 0`, step 0 included
+        if self.update_interval and self.global_step % self.update_interval == 0:
             self.refresh_occupancy()
 
     @torch.no_grad()

@@ -6,6 +6,8 @@ Tolerances: the fused path keeps tables, features and weights in fp16 (like the 
 fp32 accumulation, so results are compared against the oracle evaluated on the SAME fp16-rounded tables / weights;
 the remaining differences are the fp16 rounding of the 64 feature values and of the hidden activations
 (2^-11 relative each)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -381,6 +383,57 @@ def test_full_checkpoint_resumes_training_and_is_a_torch_adam_state(engine, tmp_
         opt.step()
         for p, q in zip(mine, theirs):
             np.testing.assert_allclose(npy(p), npy(q), rtol=1e-5, atol=1e-7)
+
+
+def test_dynamic_scale_resume_keeps_adam_step_counts_and_pretraining_leaves_the_schedule(scene):
+    """(1) loss_scale="dynamic": the Adam kernels take their bias corrections from the device scaler state; a resumed
+    trainer must continue from the APPLIED step counts (skipped steps excluded), per parameter family -- after a
+    tables-only pretraining stage the MLP's count starts at 1 like torch.optim.Adam's per-parameter step.
+    (2) pretraining steps run at the forced lr, undecayed, and do not advance the LambdaLR position
+    (SealNeRF/trainer.py:431-432, 491-503)."""
+    from seal3d_b200 import checkpoint as ck, synth
+    from seal3d_b200.fused import FusedDistillTrainer
+    from seal3d_b200.schedule import SealStudentSchedule
+
+    def make():
+        teacher, student, _, _ = _networks(scene)
+        return FusedDistillTrainer(student, teacher, lr=1e-2, update_interval=0, lr_decay_iters=10, loss_scale="dynamic",
+                                   scaler_kwargs=dict(init_scale=4096.0, growth_interval=1000))
+
+    a = make()
+    x0, d0, _, _, M = _samples(scene, 128)
+    pts, dirs = to(x0[:4096]), to(d0[:4096])
+    sig_t, rgb_t, _ = a.T.forward(pts, dirs)
+    sched = SealStudentSchedule(a)
+    sched.set_lr(0.05)
+    for _ in range(3):
+        a.pretrain_step(pts, dirs, sig_t, rgb_t)
+    assert a.current_lr() == 0.05 and a.sched_step == 0 and a.global_step == 3
+    sched.set_lr(-1)
+    assert a.current_lr() == 1e-2
+    o, d = synth.rays_for_step(0, 2048)
+    a.distill_step(to(o), to(d), perturb=False, force_all_rays=True)
+    a.S.grad[5] = float("inf")           # poisons the NEXT step's arena: that step is skipped, the scale backs off
+    a.distill_step(to(o), to(d), perturb=False, force_all_rays=True)
+    assert a.scaler.steps() == (4, 1) and a.scaler.get_scale() == 2048.0 and a.sched_step == 2
+    assert abs(a.current_lr() - 1e-2 * 0.1 ** 0.2) < 1e-12
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "dyn_ep0001.pth")
+        ck.save_checkpoint(path, a, epoch=1, full=True)
+        raw = torch.load(path, weights_only=False)
+        assert float(raw["optimizer"]["state"][0]["step"]) == 4.0 and float(raw["optimizer"]["state"][1]["step"]) == 1.0
+        assert raw["lr_scheduler"]["last_epoch"] == 2 and raw["scaler"]["scale"] == 2048.0
+        b = make()
+        ck.load_checkpoint(path, b)
+    assert b.scaler.steps() == (4, 1) and b.sched_step == 2 and b.scaler.get_scale() == 2048.0
+    st_a, st_b = npy(a.scaler._all), npy(b.scaler._all)
+    np.testing.assert_allclose(st_b[[4, 5, 12, 13]], st_a[[4, 5, 12, 13]], rtol=1e-6)
+    la = npy(a.distill_step(to(o), to(d), perturb=False, force_all_rays=True)).copy()
+    lb = npy(b.distill_step(to(o), to(d), perturb=False, force_all_rays=True)).copy()
+    np.testing.assert_allclose(lb, la, rtol=2e-3, atol=1e-9)
+    np.testing.assert_allclose(npy(b.student.sigma_net[0].weight), npy(a.student.sigma_net[0].weight), rtol=0, atol=2e-5)
+    np.testing.assert_allclose(npy(b.student.encoder.embeddings), npy(a.student.encoder.embeddings), rtol=0, atol=2e-4)
 
 
 def test_marching_one_step_ahead_changes_nothing(scene):

@@ -9,8 +9,13 @@ import numpy as np
 import pytest
 import torch
 
+import sys
+
 import oracle
 import refext
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -743,6 +748,83 @@ def test_update_extra_state_and_distill_steps(scene):
     lp = [float(npy(tr.pretrain_step(pts, dirs, sig_t.float().contiguous(), rgb_t.float().contiguous()))[0]) for _ in range(6)]
     assert lp[-1] < lp[0]
     assert torch.equal(w_before, s.sigma_net[0].weight.detach()) and not torch.equal(e_before, s.encoder.embeddings.detach())
+
+
+def test_sph_from_ray_vs_oracle_and_reference():
+    """raymarching.cu:163-201 (background sphere coordinates): kernel vs oracle vs the reference kernel"""
+    rng = np.random.default_rng(11)
+    o = rng.uniform(-0.8, 0.8, (5000, 3)).astype(np.float32)
+    d = rng.normal(size=(5000, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    for radius in (1.5, 4.0):
+        got = npy(rm().sph_from_ray(to(o), to(d), radius))
+        ref = oracle.sph_from_ray(o, d, radius)
+        assert np.isfinite(got).all() and np.abs(got).max() <= 1.0 + 1e-6
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=2e-6)
+        ext = refext.load("raymarching")
+        out = torch.empty(5000, 2, device=dev())
+        ext.sph_from_ray(to(o), to(d), radius, 5000, out)
+        np.testing.assert_allclose(got, npy(out), rtol=1e-5, atol=2e-6)
+
+
+def _analytic_sigma_torch(x):
+    """tests/golden/make_extra_state_golden.py::analytic_sigma on the device (eager torch: one rounding per op, like numpy)"""
+    a = x.abs()
+    m = torch.maximum(torch.maximum(a[:, 0], a[:, 1]), a[:, 2])
+    return 30.0 * torch.relu(0.55 - m) ** 2 + 3.0 * torch.relu(0.2 - (x[:, 0] - 0.5).abs())
+
+
+@pytest.mark.parametrize("tag", ["b1_full_", "b1_part_", "b2_full_", "b2_part_"])
+def test_update_extra_state_parity(tag):
+    """SURVEY 8 a7, nerf/renderer.py:445-538: the device chain (occupied-cell compaction, cell draws, jittered centres,
+    scatter, EMA-max, fixed-order mean, device-threshold packbits, mean_count) against (1) the oracle restatement on the
+    same injected draw stream -- cells, positions and the updated grid bit for bit -- and (2) the committed run of the
+    reference's own method (cpu_extra_state.npz), exact wherever the reference itself is deterministic"""
+    import test_oracle_golden as tg
+    from seal3d_b200 import _lib
+    from seal3d_b200.renderer import NeRFRenderer
+    from make_extra_state_golden import initial_grid, H
+    g = tg.load("cpu_extra_state.npz")
+    r = tg.extra_state_case(g, tag, "max")
+    bound, it, seed = int(g[tag + "bound"]), int(g[tag + "iter_density"]), int(g[tag + "seed"])
+    net = NeRFRenderer(bound=bound, density_thresh=float(g[tag + "density_thresh"])).to(dev())
+    net.density_scale = float(g[tag + "density_scale"])
+    net.density_grid.copy_(to(r["grid0"]))
+    net.iter_density = it
+    net.step_counter.copy_(to(r["step_counter"]))
+    net.local_step = int(g[tag + "local_step"])
+    seen = []
+    net.density = lambda x: (seen.append(x.clone()), {"sigma": _analytic_sigma_torch(x)})[1]
+    # the cell lists of the partial update, straight from the C-ABI
+    if it >= 16:
+        for cas in range(net.cascade):
+            cells = torch.empty(2 * (H ** 3 // 4), dtype=torch.int32, device=dev())
+            nz = torch.zeros(1, dtype=torch.int32, device=dev())
+            _lib.call("s3d_density_pick_cells", net.density_grid[cas], H, H ** 3 // 4, H ** 3 // 4, (seed + 7919 * cas) & 0xFFFFFFFF, cells, nz)
+            assert int(nz.item()) == int((r["grid0"][cas] > 0).sum())
+            assert np.array_equal(npy(cells).astype(np.int64), r["cells"][cas])
+    net.update_extra_state(seed=seed)
+    for cas in range(net.cascade):
+        assert np.array_equal(npy(seen[cas]), r["xyz"][cas]), "jittered cell centres differ from the oracle"
+    grid = npy(net.density_grid)
+    assert np.array_equal(grid, r["grid"]), "updated density grid differs from the oracle"
+    np.testing.assert_allclose(net.mean_density, r["mean_density"], rtol=1e-6)
+    thresh = min(net.mean_density, float(g[tag + "density_thresh"]))
+    bits = npy(net.density_bitfield)
+    diff = np.nonzero(np.unpackbits(bits ^ r["bitfield"], bitorder="little"))[0]
+    assert diff.size == 0 or np.all(np.abs(grid.reshape(-1)[diff] - thresh) <= 4e-6), diff[:10]
+    assert np.array_equal(bits, oracle.packbits(grid.reshape(-1), np.float32(thresh)))
+    assert net.mean_count == r["mean_count"] and net.local_step == 0 and net.iter_density == it + 1
+    tg.check_extra_state_against_golden(dict(grid=grid, bitfield=bits, mean_density=net.mean_density, mean_count=net.mean_count), r, g, tag,
+                                        float(g[tag + "density_scale"]))
+    # same seed -> bit-identical state (what keeps data-parallel replicas in step without a broadcast)
+    net2 = NeRFRenderer(bound=bound, density_thresh=float(g[tag + "density_thresh"])).to(dev())
+    net2.density_scale, net2.iter_density = net.density_scale, it
+    net2.density_grid.copy_(to(r["grid0"]))
+    net2.density = lambda x: {"sigma": _analytic_sigma_torch(x)}
+    net2.update_extra_state(seed=seed)
+    assert torch.equal(net2.density_grid, net.density_grid) and torch.equal(net2.density_bitfield, net.density_bitfield)
+    assert net2.mean_density == net.mean_density
 
 
 def test_reference_named_extension_modules():

@@ -144,6 +144,91 @@ def test_data_parallel_gradient_equals_single_process_gloo():
     assert err <= 1e-5 * scale and t == 2.0
 
 
+class _StubStudent:
+    def __init__(self):
+        import torch
+        self.mean_count = 0
+        self.step_counter = torch.zeros(16, 2, dtype=torch.int32)
+
+
+class _StubTrainer:
+    """a trainer whose every step contains one all-reduce, like FusedDistillTrainer._reduce_and_step"""
+
+    def __init__(self):
+        import torch
+        self.student, self.calls, self.grad = _StubStudent(), 0, torch.ones(64)
+
+    def distill_step(self, o, d, perturb=True, force_all_rays=False, prefetch=None):
+        import torch
+        import torch.distributed as dist
+        self.calls += 1
+        g = self.grad.clone()
+        dist.all_reduce(g)
+        self.student.step_counter[self.calls % 16, 0] = 1000 + self.calls
+        return torch.tensor([float(g[0]), float(self.calls)])
+
+    def refresh_occupancy(self):
+        self.student.mean_count = 1
+
+
+def _bench_flow_worker(rank, world, port, q, rank0_extra_step):
+    import datetime
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    import argparse
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=8))
+    import bench
+    tr = _StubTrainer()
+    batches = [(torch.zeros(4, 3), torch.zeros(4, 3)) for _ in range(4)]
+    args = argparse.Namespace(rays=4, steps=3, warmup=3, no_roofline=False)
+    rows = []
+    try:
+        r = bench.timed_legs(tr, batches, batches, args, rank, world, torch.device("cpu"), pipelined=True,
+                             profile_hook=(lambda: rows.clear(), lambda: [("s3d_stub", 1.0)] * 3))
+        if rank0_extra_step and rank == 0:
+            tr.distill_step(*batches[0])     # what round 1's bench did: a step (= a collective) on rank 0 alone
+        dist.barrier()
+        q.put((rank, "ok", tr.calls, r["ms"] > 0 and r["ms_e2e"] > 0, r["breakdown"], float(r["last"][0])))
+    except Exception as e:       # gloo reports the unmatched collective as a timeout
+        q.put((rank, "error", type(e).__name__, None, None, None))
+    finally:
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
+
+
+def _run_bench_flow(extra):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() + (17 if extra else 0)) % 90
+    ps = [ctx.Process(target=_bench_flow_worker, args=(r, 2, port, q, extra)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(60)
+    return out
+
+
+def test_bench_control_flow_issues_matched_collectives_gloo():
+    """bench.timed_legs (warm-up, both timed legs, the per-kernel breakdown) on 2 gloo ranks with a trainer whose step
+    all-reduces: both ranks must take the same number of steps and finish; round 1's rank-0-only breakdown steps hung here"""
+    out = _run_bench_flow(False)
+    assert [o[1] for o in out] == ["ok", "ok"], out
+    assert out[0][2] == out[1][2] == 3 + 6 + 3 + 3 + 3, out        # warm-up, pipeline priming, leg 1, leg 2, breakdown
+    assert all(o[3] for o in out) and out[0][5] == 2.0              # the all-reduce summed both ranks
+    assert out[0][4]["s3d_stub"]["calls_per_step"] == 1.0
+
+
+def test_bench_control_flow_test_detects_an_unmatched_collective_gloo():
+    """the negative control: one extra step on rank 0 alone must NOT pass silently (gloo times out)"""
+    out = _run_bench_flow(True)
+    assert any(o[1] == "error" for o in out), out
+
+
 def test_checkpoint_model_roundtrip_in_reference_format(tmp_path):
     """nerf/utils.py:1015-1136: dict layout, keys of SURVEY appendix B, latest-checkpoint lookup, bare state dicts;
     TensoRF factors are written contiguous in the reference shape and land in channels_last storage, at the file's resolution"""
