@@ -735,8 +735,10 @@ def test_update_extra_state_and_distill_steps(scene):
     for i in range(8):
         l = tr.distill_step(o, d, perturb=False, force_all_rays=(i < 4))
         losses.append(float(npy(l).sum()))
-    assert np.isfinite(losses).all() and losses[-1] < losses[0]
-    assert s.mean_count > 0 and s.iter_density >= 1
+    # the occupancy is refreshed at steps 0 and 4 (global_step % interval == 0, nerf/utils.py:845-847): losses are comparable
+    # between refreshes, where the sample set is fixed
+    assert np.isfinite(losses).all() and losses[3] < losses[0], losses
+    assert s.mean_count > 0 and s.iter_density == 2
     assert int(npy(s.density_bitfield).astype(np.int32).sum()) > 0
     # pretraining: only the tables move
     w_before = s.sigma_net[0].weight.detach().clone()
