@@ -68,12 +68,36 @@ def build_one(name):
     print("built", dst)
 
 
+WRAPPERS = {"raymarching": ["__init__.py", "raymarching.py"], "gridencoder": ["__init__.py", "grid.py"],
+            "shencoder": ["__init__.py", "sphere_harmonics.py"], "freqencoder": ["__init__.py", "freq.py"], "ffmlp": ["__init__.py", "ffmlp.py"]}
+
+
+def stage_wrappers():
+    """The reference's Python wrappers (gridencoder/grid.py, raymarching/raymarching.py, ...) are the other half of the
+    extension surface: `nerf/network.py` calls THEM, and they call `_gridencoder` / `_raymarching`.  Like the compiled
+    extensions they cannot be read from /root/reference on the GPU box, so the unmodified files are staged next to the
+    built `.so` files under the git-ignored oracle/_ref/py/ (never committed, never imported by the product); the GPU test
+    tests/test_gpu_reference_wrappers.py runs them once over the reference's extensions and once over this repo's."""
+    import shutil
+    for pkg, files in WRAPPERS.items():
+        dst = os.path.join(OUT, "py", pkg)
+        os.makedirs(dst, exist_ok=True)
+        for f in files:
+            shutil.copy2(os.path.join(REF, pkg, f), os.path.join(dst, f))
+    print("staged the reference wrappers under", os.path.join(OUT, "py"))
+
+
 def main():
     names = sys.argv[1:] or list(EXTS)
     if not os.path.isdir(REF):
         print("reference tree %s absent: nothing to build (prebuilt oracle/_ref/*.so are used as-is)" % REF)
         return 0
     os.makedirs(OUT, exist_ok=True)
+    if names == ["wrappers"]:
+        stage_wrappers()
+        return 0
+    if len(sys.argv) == 1:
+        stage_wrappers()
     if len(names) == 1:
         build_one(names[0])
         return 0

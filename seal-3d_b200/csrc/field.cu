@@ -24,6 +24,7 @@
 // Level geometry follows gridencoder.cu:137-156 of the reference (D=3, linear interpolation,
 // align_corners=false); MLP semantics follow nerf/network.py:99-128 and activation.py:5-17.
 #include "tc05.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -588,6 +589,146 @@ k_ngp_mlp_fwd(const FwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// MLP forward, activations in TMEM (the shipped forward).
+//   The chain feats -> H1 -> h2 -> [colour feats | SH | geo] -> C1 -> C2 -> rgb keeps its A operand in TENSOR MEMORY: the
+//   thread that owns a sample row packs its fp16 activations and writes them with tcgen05.st; the next layer's MMA takes A
+//   from TMEM (TS form, tc05.cuh) and only the weights from shared memory.  Against the SS-form kernel above (ncu: l1tex 67 %,
+//   tensor pipe 13 %: every M128 N64 K16 MMA pulled 4 KB of A + 2 KB of B through the 128 B/clk shared-memory port, 48 cycles
+//   for 32 cycles of math, plus the STS traffic of the activation tiles and a fence.proxy.async per round) there are no
+//   activation tiles at all: shared memory holds 28 KB of weights, nothing else.
+//   TMEM columns of a CTA (128): [0,64) fp32 accumulator | [64,96) H: hidden activations, 64 halfs (the sigma-grid features
+//   FS = 32 halfs alias its first 16 columns) | [96,128) CIN: colour-layer input = [colour-grid feats 32 | SH 16 | geo 15 | 0].
+//   Thread layout as above: thread (r, hf) owns row r and the column half hf of every 64-wide accumulator; a hidden
+//   activation half (32 values) packs into 16 TMEM columns.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kTsAcc = 0, kTsH = 64, kTsCin = 96, kTsCols = 128;
+
+__device__ __forceinline__ void relu_to_tmem(uint32_t t_acc_half, uint32_t t_dst) {
+    float v[32];
+    tmem_ld32(t_acc_half, v);
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) pk[i] = pack_half2(fmaxf(v[2 * i], 0.0f), fmaxf(v[2 * i + 1], 0.0f));
+    tmem_st16(t_dst, pk);
+}
+__device__ __forceinline__ void ts_publish() {   // epilogue warps: my TMEM stores / accumulator reads of this round are done
+    tmem_st_wait();
+    fence_before_sync();
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kMlpThreads)
+k_ngp_mlp_fwd_ts(const FwdArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ uint32_t s_tmem;
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *tWs0 = smem, *tWc0 = tWs0 + kWTile, *tWc1 = tWc0 + kWTile, *tWs1 = tWc1 + kWTile, *tWc2 = tWs1 + kOTile;
+    const uint32_t tid = threadIdx.x, warp = warp_idx_sync(), r = tid & 127, hf = (tid >> 7) & 1u;
+    const bool is_issuer = (warp == kIssuerWarp);
+    if (is_issuer) tmem_alloc(smem_u32(&s_tmem), kTsCols);
+    if (tid == 0) mbar_init(smem_u32(&s_mbar), 1);
+    load_weights(tWs0, tWs1, tWc0, tWc1, tWc2, a.w);
+    sync_tiles();
+    const uint32_t tmem = s_tmem, t_row = tmem + (((warp & 3u) * 32u) << 16);
+    Issue is{smem_u32(&s_mbar), 0};
+    const uint32_t id64 = make_idesc(128, 64, false, false), id16 = make_idesc(128, 16, false, false);
+
+    if (is_issuer) {
+        const bool lead = elect_one();
+        const uint32_t aWs0 = smem_u32(tWs0), aWs1 = smem_u32(tWs1), aWc0 = smem_u32(tWc0), aWc1 = smem_u32(tWc1), aWc2 = smem_u32(tWc2);
+        const uint32_t acc = tmem + kTsAcc, tH = tmem + kTsH, tC = tmem + kTsCin;
+        for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            iss_acquire();   // features stored: sigma layer 0, K = 32
+            { for (uint32_t k = 0; k < 2; k++) mma_f16_ts_if(lead, acc, tH + 8 * k, desc_kmajor(aWs0, k), id64, k > 0); mma_commit_if(lead, is.mbar); }
+            iss_acquire();   // H1 stored
+            { for (uint32_t k = 0; k < 4; k++) mma_f16_ts_if(lead, acc, tH + 8 * k, desc_kmajor(aWs1, k), id16, k > 0); mma_commit_if(lead, is.mbar); }
+            if (a.sigma_only) { tile_end_sync(); continue; }
+            iss_acquire();   // [SH | geo] stored next to the colour features
+            { for (uint32_t k = 0; k < 4; k++) mma_f16_ts_if(lead, acc, tC + 8 * k, desc_kmajor(aWc0, k), id64, k > 0); mma_commit_if(lead, is.mbar); }
+            iss_acquire();   // C1 stored
+            { for (uint32_t k = 0; k < 4; k++) mma_f16_ts_if(lead, acc, tH + 8 * k, desc_kmajor(aWc1, k), id64, k > 0); mma_commit_if(lead, is.mbar); }
+            iss_acquire();   // C2 stored
+            { for (uint32_t k = 0; k < 4; k++) mma_f16_ts_if(lead, acc, tH + 8 * k, desc_kmajor(aWc2, k), id16, k > 0); mma_commit_if(lead, is.mbar); }
+            tile_end_sync();
+        }
+    } else {
+        const bool want_dirs = (hf == 0) && !a.sigma_only;
+        const uint32_t t_acc = t_row + kTsAcc + hf * 32, t_h = t_row + kTsH + hf * 16;
+        // thread (r, hf) stages half of the row's features: hf 0 the sigma-grid half -> FS, hf 1 the colour-grid half -> CIN[0,16)
+        const uint32_t t_feat = t_row + (hf == 0 ? kTsH : kTsCin);
+        FeatPre nf;
+        float ndx = 0.f, ndy = 0.f, ndz = 0.f;
+        {
+            const uint32_t row0 = blockIdx.x * kRows + r;
+            nf.load(a.feats, row0, hf, blockIdx.x < a.n_tiles && row0 < a.M);
+            if (want_dirs && blockIdx.x < a.n_tiles && row0 < a.M) { ndx = a.dirs[(size_t)row0 * 3]; ndy = a.dirs[(size_t)row0 * 3 + 1]; ndz = a.dirs[(size_t)row0 * 3 + 2]; }
+        }
+        for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            const uint32_t row = tile * kRows + r;
+            const bool in_range = row < a.M;
+            {
+                uint32_t pk[16];
+#pragma unroll
+                for (uint32_t q = 0; q < 4; q++) { pk[4 * q] = nf.f[q].x; pk[4 * q + 1] = nf.f[q].y; pk[4 * q + 2] = nf.f[q].z; pk[4 * q + 3] = nf.f[q].w; }
+                if (hf == 0 || !a.sigma_only) tmem_st16(t_feat, pk);
+            }
+            const float dx = ndx, dy = ndy, dz = ndz;
+            {   // next tile's inputs
+                const uint32_t nt = tile + gridDim.x, nrow = nt * kRows + r;
+                const bool nin = nt < a.n_tiles && nrow < a.M;
+                nf.load(a.feats, nrow, hf, nin);
+                ndx = ndy = ndz = 0.f;
+                if (want_dirs && nin) { ndx = a.dirs[(size_t)nrow * 3]; ndy = a.dirs[(size_t)nrow * 3 + 1]; ndz = a.dirs[(size_t)nrow * 3 + 2]; }
+            }
+            ts_publish();
+            is.wait();       // sigma layer 0 done
+            relu_to_tmem(t_acc, t_h);
+            ts_publish();
+            is.wait();       // sigma layer 1 done (16 outputs)
+            if (hf == 0) {
+                float h2[16];
+                tmem_ld16(t_row + kTsAcc, h2);
+                if (in_range) {
+                    a.sigma[row] = a.density_scale * __expf(h2[0]);
+                    if (a.geo) for (int i = 0; i < 15; i++) a.geo[(size_t)row * 15 + i] = h2[1 + i];
+                }
+                if (!a.sigma_only) {
+                    float g[32];
+                    sh4(dx, dy, dz, g);
+#pragma unroll
+                    for (int i = 0; i < 15; i++) g[16 + i] = h2[1 + i];
+                    g[31] = 0.0f;
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) pk[i] = pack_half2(g[2 * i], g[2 * i + 1]);
+                    tmem_st16(t_row + kTsCin + 16, pk);   // colour input, second half: [SH16 | geo15 | 0]
+                }
+            }
+            if (a.sigma_only) { tile_end_sync(); continue; }
+            ts_publish();
+            is.wait();       // colour layer 0 done
+            relu_to_tmem(t_acc, t_h);
+            ts_publish();
+            is.wait();       // colour layer 1 done
+            relu_to_tmem(t_acc, t_h);
+            ts_publish();
+            is.wait();       // colour layer 2 done (3 outputs)
+            if (hf == 0) {
+                float o[16];
+                tmem_ld16(t_row + kTsAcc, o);
+                if (in_range) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) a.rgb[(size_t)row * 3 + c] = 1.0f / (1.0f + __expf(-o[c]));
+                }
+            }
+            tile_end_sync();
+        }
+    }
+    if (is_issuer) tmem_dealloc(tmem, kTsCols);
+}
+
+// ------------------------------------------------------------------------------------------------
 // MLP backward (persistent, 1 CTA / SM)
 // ------------------------------------------------------------------------------------------------
 struct BwdArgs {
@@ -1029,7 +1170,8 @@ S3D_API int s3d_ngp_scatter(const float *xyz, const void *dfeats, uint32_t M, fl
                             float S, uint32_t H, float grad_scale, void *stream) {
     if (M == 0) return 0;
     if (L > kMaxLevels) return S3D_ENOTSUP;
-    k_ngp_scatter<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale, 0, 4);
+    static const uint32_t blk = [] { const char *e = getenv("S3D_SCATTER_BLOCK"); const uint32_t v = e ? (uint32_t)atoi(e) : 256u; return (v >= 32 && v <= 1024 && v % 32 == 0) ? v : 256u; }();
+    k_ngp_scatter<<<div_up(M, blk), blk, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale, 0, 4);
     S3D_RETURN_LAST();
 }
 
@@ -1057,8 +1199,19 @@ S3D_API int s3d_ngp_mlp_forward(const void *feats, const float *dirs, uint32_t M
     a.feats = (const __half *)feats; a.dirs = dirs;
     a.w = MlpWeights{(const __half *)w_s0, (const __half *)w_s1, (const __half *)w_c0, (const __half *)w_c1, (const __half *)w_c2};
     a.sigma = sigma; a.rgb = rgb; a.geo = geo; a.M = M; a.n_tiles = div_up(M, kRows); a.density_scale = density_scale; a.sigma_only = sigma_only;
-    const uint32_t grid = min(a.n_tiles, (uint32_t)sm_count() * 3u);
-    k_ngp_mlp_fwd<<<grid, kMlpThreads, smem, as_stream(stream)>>>(a);
+    // S3D_MLP_FWD=ss selects the older kernel with activation tiles in shared memory (A/B runs); default = activations in TMEM
+    static const bool use_ss = [] { const char *e = getenv("S3D_MLP_FWD"); return e && e[0] == 's' && e[1] == 's'; }();
+    if (use_ss) {
+        const uint32_t grid = min(a.n_tiles, (uint32_t)sm_count() * 3u);
+        k_ngp_mlp_fwd<<<grid, kMlpThreads, smem, as_stream(stream)>>>(a);
+        S3D_RETURN_LAST();
+    }
+    const size_t smem_ts = 1024 + 3 * kWTile + 2 * kOTile;
+    e = cudaFuncSetAttribute(k_ngp_mlp_fwd_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts);
+    if (e != cudaSuccess) return (int)e;
+    static const uint32_t per_sm = [] { const char *e = getenv("S3D_MLP_FWD_CTAS"); const int v = e ? atoi(e) : 3; return (uint32_t)(v >= 1 && v <= 4 ? v : 3); }();
+    const uint32_t grid = min(a.n_tiles, (uint32_t)sm_count() * per_sm);
+    k_ngp_mlp_fwd_ts<<<grid, kMlpThreads, smem_ts, as_stream(stream)>>>(a);
     S3D_RETURN_LAST();
 }
 

@@ -168,6 +168,39 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- A operand in TMEM (tcgen05.mma "TS" form) -----------------------------------------------------------------------
+// An fp16 A tile [128 rows x K] lives in TMEM as lane = row, 32-bit column j = {A[row][2j] (low half), A[row][2j+1]}
+// (cute::UMMA::tmem_frg_1sm<half_t, half_t>: dense 16-bit values, K-major -- "A from TMEM can't be transposed").  One
+// K = 16 MMA consumes 8 columns.  The epilogue thread that owns a row stores its packed activations with tcgen05.st, so the
+// activation never touches shared memory: no STS, no fence.proxy.async, and the MMA reads only its B operand (2 KB per
+// M128 N64 K16 instruction = 16 cycles of shared-memory bandwidth against 32 cycles of tensor time) instead of A + B
+// (6 KB = 48 cycles), which is what made the SS-form MLP kernels shared-memory bound at 13 % tensor-pipe utilisation.
+__device__ __forceinline__ void mma_f16_ts_if(bool issue, uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate), "r"((uint32_t)issue)
+        : "memory");
+}
+// 32 lanes x 16 columns: thread i of the warp writes 16 packed half2 words into row (lane_base + i), columns col..col+15
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    __syncwarp();
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
 // pack 8 floats into one 16-byte chunk of fp16
 __device__ __forceinline__ uint4 pack8(const float *v) {
     uint4 u;

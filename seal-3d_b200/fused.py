@@ -152,13 +152,46 @@ class FusedNGP:
             out.append((a, b, off[a] * 4, off[b] * 4 if b < self.L else self.grad.numel()))
         return out
 
-    def backward(self, xyz, dirs, feats, g_sigma, g_rgb, loss_scale=1.0, train_mlp=True, before_scatter=None, chunks=None, after_chunk=None):
+    def _hi_stream(self):
+        if getattr(self, "_hi", None) is None:
+            # CUDA priorities: lower number = higher priority; torch's current stream has the lowest (0)
+            self._hi = torch.cuda.Stream(device=self.dev, priority=-1)
+        return self._hi
+
+    def backward(self, xyz, dirs, feats, g_sigma, g_rgb, loss_scale=1.0, train_mlp=True, before_scatter=None, chunks=None, after_chunk=None,
+                 sample_chunks=1):
         """accumulates loss_scale * dL/dparams into the gradient arena; `before_scatter()` is called between the two launches.
         chunks (from grad_chunks) + after_chunk(i, arena_begin, arena_end): scatter the levels chunk by chunk and report each
-        finished arena slice (the data-parallel trainer starts its all-reduce there)"""
+        finished arena slice (the data-parallel trainer starts its all-reduce there).
+
+        sample_chunks > 1: the samples are cut into that many slices; the MLP backward of slice k+1 (persistent, one CTA per
+        SM, tensor-core / latency bound, almost no LSU traffic) runs on a high-priority stream while the gradient scatter of
+        slice k (bound by the SMs' REDG issue rate) runs on the current stream: one scatter CTA fits next to the MLP CTA on
+        every SM (registers 544 x <= 80 + 256 x 64, shared memory 222 KB + 0.3 KB), so the two limiters overlap."""
         M = feats.shape[0]
         dfeats = torch.empty(M, 64, dtype=torch.float16, device=self.dev)
         w, gw = self._w16(), self._gw()
+        if sample_chunks > 1 and not chunks and M >= 128 * sample_chunks:
+            per = (M + sample_chunks - 1) // sample_chunks
+            per = (per + 127) // 128 * 128
+            main, hi = torch.cuda.current_stream(), self._hi_stream()
+            hi.wait_stream(main)
+            evs, spans = [], []
+            with torch.cuda.stream(hi):
+                for a in range(0, M, per):
+                    b = min(M, a + per)
+                    _lib.call("s3d_ngp_mlp_backward", feats[a:b], dirs[a:b], b - a, w[0], w[1], w[2], w[3], w[4], self.density_scale, g_sigma[a:b],
+                              g_rgb[a:b], dfeats[a:b], 1.0, gw[0], gw[1], gw[2], gw[3], gw[4], int(train_mlp))
+                    ev = torch.cuda.Event()
+                    ev.record(hi)
+                    evs.append(ev)
+                    spans.append((a, b))
+            if before_scatter is not None:
+                before_scatter()
+            for ev, (a, b) in zip(evs, spans):
+                main.wait_event(ev)
+                _lib.call("s3d_ngp_scatter", xyz[a:b], dfeats[a:b], b - a, self.bound, self.grad4, self.offsets, self.L, self.S, self.H, 1.0)
+            return
         _lib.call("s3d_ngp_mlp_backward", feats, dirs, M, w[0], w[1], w[2], w[3], w[4], self.density_scale, g_sigma, g_rgb, dfeats,
                   1.0, gw[0], gw[1], gw[2], gw[3], gw[4], int(train_mlp))
         if before_scatter is not None:
@@ -294,6 +327,7 @@ class FusedDistillTrainer:
         n_chunks = int(os.environ.get("S3D_GRAD_CHUNKS", 1))
         self.grad_chunks = self.S.grad_chunks(n_chunks) if (world_size > 1 and n_chunks > 1) else None
         self._pending = []
+        self.bwd_chunks = int(os.environ.get("S3D_BWD_CHUNKS", 1))   # MLP backward / scatter overlap (FusedNGP.backward)
         self._side, self._pref = None, None     # side stream + the pre-marched next batch (see _prefetch)
         self._cur = self._old = None            # pre-marched tensors in use by this / the previous step (kept alive, see _prefetch)
         self.lr_decay_iters = lr_decay_iters
@@ -442,7 +476,7 @@ class FusedDistillTrainer:
         g_rgb = torch.zeros(M, 3, dtype=torch.float32, device=dev)
         _lib.call("s3d_composite_rays_train_backward", g_ws, g_img, sig_s, rgb_s, deltas, rays, ws, comp, M, N, float(self.T_thresh), g_sig, g_rgb)
         self.S.backward(xyzs, dirs, feats, g_sig, g_rgb, before_scatter=before_scatter, chunks=self.grad_chunks,
-                        after_chunk=self._start_reduce if self.grad_chunks else None)
+                        after_chunk=self._start_reduce if self.grad_chunks else None, sample_chunks=self.bwd_chunks)
         return self.loss_buf, scale
 
     def _teacher_composite(self, mx, md, mask, feats_t, deltas, rays):
