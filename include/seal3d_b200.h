@@ -222,6 +222,14 @@ int s3d_density_grid_update(float *grid, const float *tmp_grid, uint32_t n, floa
 int s3d_packbits_dev_thresh(const float *grid, uint32_t N, const float *density_thresh_dev, uint8_t *bitfield, void *stream);
 int s3d_mean_count(const int *step_counter, uint32_t total_step, int *mean_count_out, void *stream);
 int s3d_density_grid_ema(float *grid, const float *tmp_grid, uint32_t n, float decay, float *sum_out, void *stream);
+/* The per-ray part of a training step in one launch (csrc/raymarching.cu k_distill_rays): composite_rays_train_forward of the
+ * teacher's sigma / rgb on the student's samples (sig_t, rgb_t; + background -> targets) or targets given as image_t [N,3] /
+ * depth_t [N] (NULL ok), composite_rays_train_forward of the student, the loss of nerf/utils.py:484-489,530 (loss[0] += MSE
+ * term, loss[1] += L1 depth term) and composite_rays_train_backward with the loss gradient times scale (*scale_dev if given).
+ * grad_sigmas [M], grad_rgbs [M,3] zero-initialised by the caller. */
+int s3d_distill_rays(const float *sig_t, const float *rgb_t, const float *image_t, const float *depth_t, const float *sig_s,
+                     const float *rgb_s, const float *deltas, const int *rays, uint32_t M, uint32_t N, float T_thresh, float bg_color,
+                     float scale, const float *scale_dev, float *loss, float *grad_sigmas, float *grad_rgbs, void *stream);
 /* nerf/utils.py:53-140 get_rays: poses device [B,4,4] cam2world, pixel ids inds device int64 [inds_rows, N] (row * W + col,
  * inds_rows = 1 shares them across views like the reference's expand, = B per view) or NULL for all H*W pixels in order;
  * rays_o / rays_d [B,N,3] (unit directions) */

@@ -57,6 +57,7 @@ _SIGS = {
     "s3d_mark_untrained_grid": [P, P, U32, F32, F32, U32, U32, F32, P],
     "s3d_density_cells_to_xyz": [P, U32, U32, F32, U32, P],
     "s3d_density_scatter": [P, P, U32, F32, P],
+    "s3d_distill_rays": [P, P, P, P, P, P, P, P, U32, U32, F32, F32, F32, P, P, P, P],
     "s3d_density_pick_cells": [P, U32, U32, U32, U32, P, P],
     "s3d_density_grid_update": [P, P, U32, F32, F32, P],
     "s3d_packbits_dev_thresh": [P, U32, P, P],

@@ -18,6 +18,12 @@
 //   * everything runs on the caller's stream; allocate_splitk/free_splitk are kept as no-ops.
 #include "tc05.cuh"
 
+int s3d_ffmlp_wide_forward(const __half *inputs, const __half *weights, uint32_t B, uint32_t in_dim, uint32_t out_dim, uint32_t hidden,
+                           uint32_t num_layers, uint32_t act, uint32_t out_act, __half *forward_buffer, __half *outputs, cudaStream_t st);
+int s3d_ffmlp_wide_backward(const __half *grad, const __half *inputs, const __half *weights, const __half *forward_buffer, uint32_t B,
+                            uint32_t in_dim, uint32_t out_dim, uint32_t hidden, uint32_t num_layers, uint32_t act, int calc_grad_inputs,
+                            __half *backward_buffer, __half *grad_inputs, __half *grad_weights, cudaStream_t st);
+
 namespace {
 
 using namespace tc05;
@@ -385,16 +391,21 @@ __global__ void k_f32_to_f16(const float *__restrict__ src, __half *__restrict__
 }
 
 int check_dims(uint32_t in_dim, uint32_t out_dim, uint32_t hidden, uint32_t num_layers) {
-    if (hidden != 16 && hidden != 32 && hidden != 64) return S3D_ENOTSUP;  // 128/256: not built yet
+    if (hidden != 16 && hidden != 32 && hidden != 64) return S3D_ENOTSUP;  // 128 / 256 and output > 16: ffmlp_wide.cu
     if (in_dim == 0 || in_dim % 16 != 0 || in_dim > 256) return S3D_EINVAL;
-    if (out_dim == 0 || out_dim > 16) return S3D_ENOTSUP;                  // reference: CUTLASS path for > 16
+    if (out_dim == 0 || out_dim > 16) return S3D_ENOTSUP;
     if (num_layers < 2 || num_layers > 5) return S3D_EINVAL;
     return 0;
 }
+// hidden 128 / 256 (ffmlp/src/ffmlp.cu:653-658) and output_dim > 16 (:661-670) take the wide kernels; so does a narrow network
+// that is deeper than the TMEM-resident weight-gradient accumulators of the narrow backward allow
+bool is_wide(uint32_t hidden, uint32_t out_dim, uint32_t num_layers) { return hidden > 64 || out_dim > 16 || num_layers > 5; }
 
 int run_forward(const __half *inputs, const __half *weights, uint32_t B, uint32_t in_dim, uint32_t out_dim, uint32_t hidden,
                 uint32_t num_layers, uint32_t act, uint32_t out_act, __half *forward_buffer, __half *outputs, cudaStream_t st) {
     if (B == 0) return 0;
+    if (is_wide(hidden, out_dim, num_layers))
+        return s3d_ffmlp_wide_forward(inputs, weights, B, in_dim, out_dim, hidden, num_layers, act, out_act, forward_buffer, outputs, st);
     if (int rc = check_dims(in_dim, out_dim, hidden, num_layers)) return rc;
     const uint32_t in_blocks = (in_dim + 63) / 64;
     const size_t smem = 1024 + (size_t)in_blocks * (kTileBytes + kWTileBytes) + (size_t)(num_layers - 1) * kWTileBytes + kOTileBytes;
@@ -433,11 +444,16 @@ S3D_API int s3d_ffmlp_backward(const void *grad, const void *inputs, const void 
                                void *grad_inputs, void *grad_weights, void *stream) {
     (void)output_activation;
     if (B == 0) return 0;
-    if (int rc = check_dims(input_dim, output_dim, hidden_dim, num_layers)) return rc;
-    if (activation == kSine) return S3D_ENOTSUP;
     cudaStream_t st = as_stream(stream);
     const uint32_t in_blocks = (input_dim + 63) / 64;
-    if (64 * (1 + 1 + (num_layers - 1) + in_blocks) > 512) return S3D_ENOTSUP;
+    if (is_wide(hidden_dim, output_dim, num_layers) || 64 * (1 + 1 + (num_layers - 1) + in_blocks) > 512)
+        return s3d_ffmlp_wide_backward((const __half *)grad, (const __half *)inputs, (const __half *)weights, (const __half *)forward_buffer, B, input_dim,
+                                       output_dim, hidden_dim, num_layers, activation, calc_grad_inputs, (__half *)backward_buffer,
+                                       (__half *)grad_inputs, (__half *)grad_weights, st);
+    if (int rc = check_dims(input_dim, output_dim, hidden_dim, num_layers)) return rc;
+    // sine needs the pre-activations, which the API does not store: the reference's backward returns without writing
+    // (ffmlp/src/utils.h:552-556, "assert(false)" commented out); here the call is refused
+    if (activation == kSine) return S3D_ENOTSUP;
     const size_t nW = (size_t)hidden_dim * input_dim + (size_t)hidden_dim * hidden_dim * (num_layers - 1) + (size_t)output_dim * hidden_dim;
     float *gw32 = nullptr;
     cudaError_t e = scratch_alloc((void **)&gw32, nW * sizeof(float), st);

@@ -558,6 +558,112 @@ k_composite_train_bwd(const float *__restrict__ grad_ws, const float *__restrict
     }
 }
 
+// One warp per ray, the whole per-ray part of a distillation / fine-tuning step in ONE launch:
+//   teacher forward scan (optional: sig_t / rgb_t on the student's samples -> target image + bg and target depth; otherwise the
+//   targets are read from image_t / depth_t), student forward scan, the photometric loss of nerf/utils.py:484-489, 530
+//   (mean_rays mean_c (rgb - gt)^2 + mean |depth - gt|) with its gradient, and the student backward scan
+//   (raymarching.cu:602-682) -- what the separate path does with composite_fwd x 2, a background add, finetune_loss, two
+//   gradient scalings and composite_bwd.  Arithmetic per sample is that of k_composite_train_fwd / _bwd and k_finetune_loss.
+//   grad_sigmas / grad_rgbs must be zero-initialised by the caller (samples past a ray's accumulated prefix keep the zeros).
+struct RayScan { float r, g, b, ws, d; };
+
+__device__ __forceinline__ RayScan ray_forward(const float *__restrict__ s, const float *__restrict__ c, const float2 *__restrict__ dl, uint32_t num,
+                                               uint32_t lane, float T_thresh) {
+    float r = 0, g = 0, b = 0, ws = 0, d = 0, T = 1.0f, t0 = 0.0f;
+    for (uint32_t base = 0; base < num; base += 32) {
+        const uint32_t i = base + lane;
+        const bool in = i < num;
+        float2 de = make_float2(0.f, 0.f);
+        float sg = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        if (in) { de = __ldg(dl + i); sg = __ldg(s + i); c0 = __ldg(c + i * 3); c1 = __ldg(c + i * 3 + 1); c2 = __ldg(c + i * 3 + 2); }
+        const float alpha = in ? 1.0f - __expf(-sg * de.x) : 0.0f;
+        float tot;
+        const float Tb = T * warp_excl_prod(1.0f - alpha, lane, tot);
+        const float tt = t0 + warp_incl_sum(de.y, lane);
+        const bool take = in && (Tb >= T_thresh || i == 0);
+        const float w = take ? alpha * Tb : 0.0f;
+        r += w * c0; g += w * c1; b += w * c2; ws += w; d += w * tt;
+        T *= tot;
+        t0 = __shfl_sync(0xffffffffu, tt, 31);
+        if (T < T_thresh) break;
+    }
+    RayScan o;
+    o.r = warp_sum_all(r); o.g = warp_sum_all(g); o.b = warp_sum_all(b); o.ws = warp_sum_all(ws); o.d = warp_sum_all(d);
+    return o;
+}
+
+__global__ void __launch_bounds__(256)
+k_distill_rays(const float *__restrict__ sig_t, const float *__restrict__ rgb_t, const float *__restrict__ image_t, const float *__restrict__ depth_t,
+               const float *__restrict__ sig_s, const float *__restrict__ rgb_s, const float *__restrict__ deltas, const int *__restrict__ rays,
+               uint32_t M, uint32_t N, float T_thresh, float bg, float scale, const float *__restrict__ scale_dev, float *__restrict__ loss,
+               float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    float a0 = 0.0f, a1 = 0.0f;
+    if (n < N) {
+        const uint32_t index = (uint32_t)rays[(size_t)n * 3], offset = (uint32_t)rays[(size_t)n * 3 + 1], num = (uint32_t)rays[(size_t)n * 3 + 2];
+        const bool live = num != 0 && offset + num <= M;
+        const float2 *dl = reinterpret_cast<const float2 *>(deltas) + offset;
+        RayScan S{0, 0, 0, 0, 0}, T{0, 0, 0, 0, 0};
+        if (live) S = ray_forward(sig_s + offset, rgb_s + (size_t)offset * 3, dl, num, lane, T_thresh);
+        float t0, t1, t2, td = 0.0f;
+        bool has_depth = true;
+        if (sig_t) {
+            if (live) T = ray_forward(sig_t + offset, rgb_t + (size_t)offset * 3, dl, num, lane, T_thresh);
+            const float back_t = (1.0f - T.ws) * bg;
+            t0 = T.r + back_t; t1 = T.g + back_t; t2 = T.b + back_t; td = T.d;
+        } else {
+            t0 = image_t[(size_t)index * 3]; t1 = image_t[(size_t)index * 3 + 1]; t2 = image_t[(size_t)index * 3 + 2];
+            has_depth = depth_t != nullptr;
+            if (has_depth) td = depth_t[index];
+        }
+        const float sc = scale_dev ? *scale_dev : scale;
+        const float inv_n = 1.0f / (float)N, k = 2.0f / (3.0f * (float)N);
+        const float back = (1.0f - S.ws) * bg;
+        const float d0 = S.r + back - t0, d1 = S.g + back - t1, d2 = S.b + back - t2;
+        a0 = (d0 * d0 + d1 * d1 + d2 * d2) * (inv_n / 3.0f);
+        if (has_depth) a1 = fabsf(S.d - td) * inv_n;
+        const float g0 = k * d0 * sc, g1 = k * d1 * sc, g2 = k * d2 * sc;
+        const float gws = -bg * (g0 + g1 + g2);
+        if (live) {
+            const float tail = gws * (1 - S.ws);
+            const float *s = sig_s + offset, *c = rgb_s + (size_t)offset * 3;
+            float *gs = grad_sigmas + offset, *gc = grad_rgbs + (size_t)offset * 3;
+            float Tr = 1.0f, r0 = 0, gr0 = 0, b0 = 0;
+            for (uint32_t base = 0; base < num; base += 32) {
+                const uint32_t i = base + lane;
+                const bool in = i < num;
+                float2 de = make_float2(0.f, 0.f);
+                float sg = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+                if (in) { de = __ldg(dl + i); sg = __ldg(s + i); c0 = __ldg(c + i * 3); c1 = __ldg(c + i * 3 + 1); c2 = __ldg(c + i * 3 + 2); }
+                const float alpha = in ? 1.0f - __expf(-sg * de.x) : 0.0f;
+                float tot;
+                const float Tb = Tr * warp_excl_prod(1.0f - alpha, lane, tot);
+                const bool take = in && (Tb >= T_thresh || i == 0);
+                const float w = take ? alpha * Tb : 0.0f;
+                const float Ta = Tb * (1.0f - alpha);
+                const float r = r0 + warp_incl_sum(w * c0, lane), g = gr0 + warp_incl_sum(w * c1, lane), b = b0 + warp_incl_sum(w * c2, lane);
+                if (take) {
+                    gc[i * 3] = g0 * w; gc[i * 3 + 1] = g1 * w; gc[i * 3 + 2] = g2 * w;
+                    gs[i] = de.x * (g0 * (Ta * c0 - (S.r - r)) + g1 * (Ta * c1 - (S.g - g)) + g2 * (Ta * c2 - (S.b - b)) + tail);
+                }
+                Tr *= tot;
+                r0 = __shfl_sync(0xffffffffu, r, 31); gr0 = __shfl_sync(0xffffffffu, g, 31); b0 = __shfl_sync(0xffffffffu, b, 31);
+                if (Tr < T_thresh) break;
+            }
+        }
+    }
+    // loss terms: one value per ray (lane 0 of its warp) -> CTA sum -> one atomic pair per CTA
+    __shared__ float s_a0[8], s_a1[8];
+    if (lane == 0) { s_a0[threadIdx.x >> 5] = a0; s_a1[threadIdx.x >> 5] = a1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float x = 0, y = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { x += s_a0[w]; y += s_a1[w]; }
+        atomicAdd(loss, x); atomicAdd(loss + 1, y);
+    }
+}
+
 __global__ void __launch_bounds__(128)
 k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int *__restrict__ rays_alive,
                  float *__restrict__ rays_t, const float *__restrict__ sigmas, const float *__restrict__ rgbs,
@@ -702,6 +808,20 @@ S3D_API int s3d_composite_rays_train_backward(const float *grad_weights_sum, con
     if (N == 0) return 0;
     k_composite_train_bwd<<<div_up(N, 8u), 256, 0, as_stream(stream)>>>(
         grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs);
+    S3D_RETURN_LAST();
+}
+
+// The per-ray part of a distillation (sig_t / rgb_t given: teacher composited on the same samples) or fine-tuning (image_t
+// [N,3] / depth_t [N] or NULL given) step in one launch: both forward scans, loss[0] += MSE term, loss[1] += L1 depth term,
+// and the student's compositor backward with the loss gradient times `scale` (*scale_dev when not NULL: device-side
+// GradScaler).  grad_sigmas [M] / grad_rgbs [M,3] must be zeroed by the caller.
+S3D_API int s3d_distill_rays(const float *sig_t, const float *rgb_t, const float *image_t, const float *depth_t, const float *sig_s,
+                             const float *rgb_s, const float *deltas, const int *rays, uint32_t M, uint32_t N, float T_thresh, float bg_color,
+                             float scale, const float *scale_dev, float *loss, float *grad_sigmas, float *grad_rgbs, void *stream) {
+    if (N == 0) return 0;
+    if (!sig_t && !image_t) return S3D_EINVAL;
+    k_distill_rays<<<div_up(N, 8u), 256, 0, as_stream(stream)>>>(sig_t, rgb_t, image_t, depth_t, sig_s, rgb_s, deltas, rays, M, N, T_thresh, bg_color,
+                                                                   scale, scale_dev, loss, grad_sigmas, grad_rgbs);
     S3D_RETURN_LAST();
 }
 

@@ -560,6 +560,47 @@ def test_ffmlp_backward(B, din, dh, nl, act):
         assert err <= 4e-3 * np.abs(ref).max() + 1e-7, (name, err, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("B,din,dh,dout,nl,act", [(256, 32, 128, 16, 2, 0), (1000, 64, 128, 16, 3, 0), (384, 32, 256, 16, 2, 0), (300, 160, 128, 3, 2, 0),
+                                                  (256, 32, 256, 16, 3, 0), (512, 32, 64, 48, 2, 0), (256, 48, 128, 40, 2, 3), (128, 32, 64, 16, 6, 0)])
+def test_ffmlp_wide_forward_backward(B, din, dh, dout, nl, act):
+    """ffmlp/src/ffmlp.cu:653-670: hidden 128 / 256 and output_dim > 16 (csrc/ffmlp_wide.cu: activations in TMEM, weights
+    resident or streamed per layer, split-K weight gradients) against the oracle, and against the reference kernels where the
+    reference's own constraints allow (batch a multiple of 128, output 16)"""
+    from seal3d_b200 import _lib
+    W, x = _ffmlp_case(B, din, dh, dout, nl, seed=3)
+    fb = torch.zeros(nl, B, dh, device=dev(), dtype=torch.float16)
+    out = torch.zeros(B, dout, device=dev(), dtype=torch.float16)
+    _lib.call("s3d_ffmlp_forward", to(x).half(), to(W).half(), B, din, dout, dh, nl, act, 6, fb, out)
+    ref, rfb = oracle.ffmlp_forward(x, W, din, dout, dh, nl, act, 6, round_half_act=True)
+    tol = 3e-3 * max(1.0, np.abs(ref).max())
+    assert np.abs(npy(fb.float()) - rfb).max() <= 3e-3 * max(1.0, np.abs(rfb).max())
+    assert np.abs(npy(out.float()) - ref).max() <= tol
+    out2 = torch.zeros_like(out)
+    _lib.call("s3d_ffmlp_inference", to(x).half(), to(W).half(), B, din, dout, dh, nl, act, 6, None, out2)
+    assert torch.equal(out, out2)
+    g = oracle.round_to_half((np.random.default_rng(4).normal(size=(B, dout)) / B).astype(np.float32))
+    bb = torch.zeros(nl, B, dh, device=dev(), dtype=torch.float16)
+    gi = torch.zeros(B, din, device=dev(), dtype=torch.float16)
+    gw = torch.zeros(W.shape[0], device=dev(), dtype=torch.float16)
+    _lib.call("s3d_ffmlp_backward", to(g).half(), to(x).half(), to(W).half(), fb, B, din, dout, dh, nl, act, 6, 1, bb, gi, gw)
+    rgw, rgi, rbb = oracle.ffmlp_backward(g, x, W, npy(fb.float()), din, dout, dh, nl, act)
+    for got, want, name in ((bb, rbb, "backward_buffer"), (gi, rgi, "grad_inputs"), (gw, rgw, "grad_weights")):
+        err = np.abs(npy(got.float()) - want).max()
+        assert err <= 4e-3 * np.abs(want).max() + 1e-7, (name, err, np.abs(want).max())
+    if B % 128 == 0 and dout == 16 and act == 0 and nl <= 5:
+        rext = refext.load("ffmlp")
+        rext.allocate_splitk(nl + 1)
+        rfb_, rout = torch.zeros_like(fb), torch.zeros_like(out)
+        rext.ffmlp_forward(to(x).half(), to(W).half(), B, din, dout, dh, nl, act, 6, rfb_, rout)
+        assert np.abs(npy(out.float()) - ref).max() <= np.abs(npy(rout.float()) - ref).max() + tol
+        rbb_, rgi_, rgw_ = torch.zeros_like(bb), torch.zeros_like(gi), torch.zeros_like(gw)
+        rext.ffmlp_backward(to(g).half(), to(x).half(), to(W).half(), rfb_, B, din, dout, dh, nl, act, 6, True, rbb_, rgi_, rgw_)
+        torch.cuda.synchronize()
+        # the reference's gradients (fp16 accumulation) against the oracle bound how close ours must be to the reference
+        e_ref = np.abs(npy(rgw_.float()) - rgw).max()
+        assert np.abs(npy(gw.float()) - npy(rgw_.float())).max() <= e_ref + 4e-3 * np.abs(rgw).max() + 1e-7
+
+
 # --------------------------------------------------------------------------------- proxy + losses + adam
 
 

@@ -315,11 +315,14 @@ def test_c_abi_argument_errors_are_reported_before_any_launch():
     assert lib.s3d_grid_encode_forward(n, n, n, n, 16, 5, 2, 16, 0.5, 16, n, 0, 0, 0, 0, n) == EINVAL
     assert lib.s3d_grid_encode_forward(n, n, n, n, 0, 3, 2, 16, 0.5, 16, n, 0, 0, 0, 0, n) == 0
     assert lib.s3d_grad_total_variation(n, n, n, n, 1.0, 16, 3, 2, 16, 0.5, 16, 0, 0, 1, n) == ENOTSUP      # fp16 TV is not a reference path
-    # FFMLP: hidden 128 / 256 and outputs > 16 are not built, input width must be a multiple of 16
-    assert lib.s3d_ffmlp_forward(n, n, 128, 32, 16, 128, 2, 0, 6, n, n, n) == ENOTSUP
-    assert lib.s3d_ffmlp_forward(n, n, 128, 32, 32, 64, 2, 0, 6, n, n, n) == ENOTSUP
+    # FFMLP: hidden width in {16, 32, 64, 128, 256} (ffmlp.cu:653-658 throws otherwise), input width a multiple of 16, output <= 256
+    assert lib.s3d_ffmlp_forward(n, n, 128, 32, 16, 100, 2, 0, 6, n, n, n) == ENOTSUP
+    assert lib.s3d_ffmlp_forward(n, n, 128, 32, 16, 512, 2, 0, 6, n, n, n) == ENOTSUP
+    assert lib.s3d_ffmlp_forward(n, n, 128, 32, 300, 128, 2, 0, 6, n, n, n) == EINVAL
     assert lib.s3d_ffmlp_forward(n, n, 128, 30, 16, 64, 2, 0, 6, n, n, n) == EINVAL
+    assert lib.s3d_ffmlp_forward(n, n, 0, 32, 16, 256, 3, 0, 6, n, n, n) == 0
     assert lib.s3d_ffmlp_backward(n, n, n, n, 128, 32, 16, 64, 2, 2, 6, 1, n, n, n, n) == ENOTSUP        # sine activation has no backward
+    assert lib.s3d_ffmlp_backward(n, n, n, n, 128, 32, 16, 128, 2, 2, 6, 1, n, n, n, n) == ENOTSUP
     # VM lookups: rank multiple of 4; the reduced form needs a power-of-two group
     assert lib.s3d_vm_forward(n, 8, n, n, n, n, n, n, n, dims, 6, 1, n, n) == EINVAL
     assert lib.s3d_vm_forward(n, 8, n, n, n, n, n, n, n, dims, 48, 1, n, n) == ENOTSUP
