@@ -222,6 +222,10 @@ int s3d_density_grid_update(float *grid, const float *tmp_grid, uint32_t n, floa
 int s3d_packbits_dev_thresh(const float *grid, uint32_t N, const float *density_thresh_dev, uint8_t *bitfield, void *stream);
 int s3d_mean_count(const int *step_counter, uint32_t total_step, int *mean_count_out, void *stream);
 int s3d_density_grid_ema(float *grid, const float *tmp_grid, uint32_t n, float decay, float *sum_out, void *stream);
+/* development / test switch of the train marcher: 1 (default) walks a ray only inside the widened bounding box of the occupied
+ * cells (single cascade, dt_gamma = 0; the step lattice before the box is jumped in closed form), 0 walks it from its near
+ * point like the reference.  The samples are identical either way (tests/test_gpu_parity.py compares them at full size). */
+int s3d_march_set_clip(int enable);
 /* The per-ray part of a training step in one launch (csrc/raymarching.cu k_distill_rays): composite_rays_train_forward of the
  * teacher's sigma / rgb on the student's samples (sig_t, rgb_t; + background -> targets) or targets given as image_t [N,3] /
  * depth_t [N] (NULL ok), composite_rays_train_forward of the student, the loss of nerf/utils.py:484-489,530 (loss[0] += MSE

@@ -75,7 +75,7 @@ _SIGS = {
     "s3d_vm_backward": [P, U32, P, P, P, P, P, P, P, P, U32, I32, P, P, P, P, P, P, P],
     "s3d_vm_resize": [P, U32, U32, P, U32, U32, U32],
 }
-_NO_STREAM = {"s3d_allocate_splitk": [SZ], "s3d_free_splitk": []}
+_NO_STREAM = {"s3d_allocate_splitk": [SZ], "s3d_free_splitk": [], "s3d_march_set_clip": [I32]}
 
 _lib = None
 LAUNCHES = 0  # kernels launched through this binding (bench.py reports the per-run delta)

@@ -190,6 +190,119 @@ __device__ __forceinline__ float step_len(const MarchCfg &c, float t) {
     return clampf(__fmul_rn(t, c.dt_gamma), c.dt_min, c.dt_max);
 }
 
+// ---- the step lattice in closed form (constant step) ----------------------------------------------------------------------
+// The reference advances a ray with a SERIAL chain of float additions, t_{k+1} = fl(t_k + dt) (raymarching.cu:396-399, :462),
+// and every sample sits on that lattice; reproducing the samples bit for bit means reproducing the chain.  With a constant
+// step d (dt_gamma = 0) the chain has an exact closed form: inside one binade [2^e, 2^(e+1)) every t is a multiple of
+// u = ulp(2^e) and fl(t + d) = t + q with q = round(d / u) * u, an exact addition, so j steps are t + j q exactly (one fmaf:
+// the result is a multiple of u below 2^(e+1), hence representable).  Only the step that crosses into the next binade rounds
+// on a coarser grid; that one is performed as a real addition.  A rounding tie (d mod u == u / 2, which would make q depend on
+// the parity of t / u) falls back to the serial loop.  Used to (a) jump from the ray's start to the occupied bounding box and
+// (b) replay empty stretches of the lattice in the write pass; a voxel-by-voxel skip is only ~4.6 steps long and stays serial.
+struct Binade {
+    float lim, q;
+    bool ok;
+};
+__device__ __forceinline__ Binade binade_of(float t, float d) {
+    Binade b;
+    const int e = (__float_as_int(t) >> 23) & 0xff;
+    b.ok = e > 24 && e < 254;
+    const float base = __int_as_float(e << 23), u = __int_as_float((e - 23) << 23);
+    b.lim = __int_as_float((e + 1) << 23);
+    b.q = __fsub_rn(__fadd_rn(base, d), base);
+    const float b1 = __fadd_rn(base, u);
+    b.ok = b.ok && b.q > 0.0f && __fsub_rn(__fadd_rn(b1, d), b1) == b.q;
+    return b;
+}
+// largest j >= 0 with t + j q < lim   (lim - t is exact: both are multiples of u below 2^(e+1))
+__device__ __forceinline__ float steps_inside(const Binade &b, float t) {
+    float jm = floorf(__fdividef(__fsub_rn(b.lim, t), b.q));
+    while (jm > 0.0f && __fmaf_rn(jm, b.q, t) >= b.lim) jm -= 1.0f;
+    while (__fmaf_rn(jm + 1.0f, b.q, t) < b.lim) jm += 1.0f;
+    return jm;
+}
+// exactly n steps
+__device__ __forceinline__ void lattice_advance(float d, float &t, uint32_t n) {
+    for (int guard = 0; guard < 40 && n > 0; guard++) {
+        const Binade b = binade_of(t, d);
+        if (!b.ok) break;
+        const float jm = steps_inside(b, t);
+        if ((float)n <= jm) { t = __fmaf_rn((float)n, b.q, t); return; }
+        t = __fadd_rn(__fmaf_rn(jm, b.q, t), d);
+        n -= (uint32_t)jm + 1u;
+    }
+    for (; n > 0; n--) t = __fadd_rn(t, d);
+}
+// while (t < target) t += d;   returns the number of steps (0 when t >= target already)
+__device__ __forceinline__ uint32_t lattice_advance_to(float d, float &t, float target) {
+    uint32_t adv = 0;
+    for (int guard = 0; guard < 40 && t < target; guard++) {
+        const Binade b = binade_of(t, d);
+        if (!b.ok) break;
+        const float jm = steps_inside(b, t);
+        float nf = fminf(ceilf(__fdividef(__fsub_rn(target, t), b.q)), jm + 1.0f);
+        nf = fmaxf(nf, 1.0f);
+        while (nf > 1.0f && __fmaf_rn(nf - 1.0f, b.q, t) >= target) nf -= 1.0f;
+        while (nf <= jm && __fmaf_rn(nf, b.q, t) < target) nf += 1.0f;
+        if (nf <= jm) { t = __fmaf_rn(nf, b.q, t); return adv + (uint32_t)nf; }
+        t = __fadd_rn(__fmaf_rn(jm, b.q, t), d);
+        adv += (uint32_t)jm + 1u;
+    }
+    while (t < target) { const float tn = __fadd_rn(t, d); adv++; if (tn == t) break; t = tn; }
+    return adv;
+}
+
+// Bounding box of the occupied cells of cascade 0 (cell units), by atomicMin / atomicMax: mm = {min x, y, z, max x, y, z},
+// initialised to {INT_MAX x 3, -1 x 3}.  One thread per bitfield byte (8 morton-consecutive cells).
+__global__ void k_occ_bbox(const uint8_t *__restrict__ grid, uint32_t n_bytes, int *__restrict__ mm) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {-1, -1, -1};
+    if (i < n_bytes) {
+        const uint32_t bits = grid[i];
+        for (uint32_t b = 0; b < 8; b++)
+            if ((bits >> b) & 1u) {
+                const uint32_t idx = i * 8 + b;
+                const int c[3] = {(int)compact_bits10(idx), (int)compact_bits10(idx >> 1), (int)compact_bits10(idx >> 2)};
+#pragma unroll
+                for (int d = 0; d < 3; d++) { lo[d] = min(lo[d], c[d]); hi[d] = max(hi[d], c[d]); }
+            }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const int l = __reduce_min_sync(0xffffffffu, lo[d]), h = __reduce_max_sync(0xffffffffu, hi[d]);
+        if ((threadIdx.x & 31) == 0 && h >= 0) { atomicMin(mm + d, l); atomicMax(mm + 3 + d, h); }
+    }
+}
+
+__global__ void k_occ_bbox_init(int *__restrict__ mm) {
+    if (threadIdx.x < 6) mm[threadIdx.x] = threadIdx.x < 3 ? 0x7fffffff : -1;
+}
+
+// Clip a ray to the occupied bounding box, widened by kBoxMargin cells on every side (single cascade, constant step only).
+// Everything outside the box is empty, so the reference's walk emits nothing there; jumping to the first lattice point inside
+// the widened box and stopping at its far side changes which EMPTY lattice points are visited, not the samples: two voxel
+// walks that stand in the same empty voxel jump to the same lattice point (the first one past the voxel's exit), so the walks
+// coincide again after at most a visit or two -- and the margin keeps those visits away from any occupied cell.
+// Returns false when the ray misses the box (no samples).  k receives the lattice index of the new t.
+constexpr int kBoxMargin = 3;
+__device__ __forceinline__ bool clip_to_occupied(const MarchCfg &c, const Ray &r, const int *__restrict__ mm, float &t, float &far, uint32_t &k) {
+    if (mm[3] < 0) return false;                       // nothing occupied
+    const float cell = __fmul_rn(2.0f, c.rH), mb = fminf(1.0f, c.bound);
+    float te = -INFINITY, tx = INFINITY;
+    const float o[3] = {r.ox, r.oy, r.oz}, rd[3] = {r.rdx, r.rdy, r.rdz};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float lo = ((float)(mm[a] - kBoxMargin) * cell - 1.0f) * mb, hi = ((float)(mm[3 + a] + 1 + kBoxMargin) * cell - 1.0f) * mb;
+        const float t1 = (lo - o[a]) * rd[a], t2 = (hi - o[a]) * rd[a];
+        te = fmaxf(te, fminf(t1, t2));                 // fminf / fmaxf drop a NaN operand (0 * inf on an axis-aligned ray)
+        tx = fminf(tx, fmaxf(t1, t2));
+    }
+    if (!(te <= tx) || !(tx > t)) return false;
+    far = fminf(far, tx);
+    if (t < te) k += lattice_advance_to(step_len(c, 0.0f), t, te);
+    return true;
+}
+
 // One visit of the marching loop (raymarching.cu:359-400).  Occupied: returns true with the sample
 // position and dt (caller advances t).  Empty: advances t along the step lattice past the voxel.
 template <bool COUNT_LATTICE = false>
@@ -229,21 +342,25 @@ __global__ void __launch_bounds__(128)
 k_march_count(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
               float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
               const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
-              int *__restrict__ rays, uint32_t *__restrict__ block_sums, uint32_t *__restrict__ bitmap) {
+              int *__restrict__ rays, uint32_t *__restrict__ block_sums, uint32_t *__restrict__ bitmap, const int *__restrict__ occ_mm) {
     __shared__ uint32_t s_warp[4];
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t num = 0;
     if (n < N) {
         const MarchCfg c = make_cfg(grid, bound, dt_gamma, max_steps, C, H);
         const Ray r = load_ray(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
-        const float far = fars[n];
+        float far = fars[n];
         float t = perturbed_start(c, nears[n], noises ? noises[n] : 0.0f);
         float x, y, z, dt;
+        uint32_t k = 0;
+        // single cascade + constant step: walk only the part of the ray inside the (widened) bounding box of the occupied cells
+        const bool hit = (occ_mm && c.C == 1 && c.dt_gamma == 0.0f) ? clip_to_occupied(c, r, occ_mm, t, far, k) : true;
+        if (!hit) far = t;       // no voxel walk at all
         if (bitmap) {
             // also record WHICH points of the ray's step lattice t_{k+1} = t_k + dt(t_k) are samples: the write pass then
-            // replays the lattice (one FADD per step) instead of repeating the voxel walk
+            // replays the lattice instead of repeating the voxel walk
             uint32_t *bm = bitmap + (size_t)n * kBitmapWords;
-            uint32_t k = 0, word = 0, widx = 0;
+            uint32_t word = 0, widx = 0;
             bool overflow = false;
             while (t < far && num < max_steps) {
                 const uint32_t k0 = k;
@@ -394,8 +511,11 @@ k_march_write_bitmap(const float *__restrict__ rays_o, const float *__restrict__
         }
         return;
     }
+    const bool const_step = c.dt_gamma == 0.0f;
+    const float d0 = step_len(c, 0.0f);
     for (uint32_t w = 0; w < kBitmapWords - 1 && step < num; w++) {
         const uint32_t bits = __ldg(bm + w);
+        if (bits == 0u && const_step) { lattice_advance(d0, t, 32u); continue; }   // 32 empty lattice points in closed form
 #pragma unroll 4
         for (uint32_t b = 0; b < 32; b++) {
             dt = step_len(c, t);
@@ -567,29 +687,46 @@ k_composite_train_bwd(const float *__restrict__ grad_ws, const float *__restrict
 //   grad_sigmas / grad_rgbs must be zero-initialised by the caller (samples past a ray's accumulated prefix keep the zeros).
 struct RayScan { float r, g, b, ws, d; };
 
-__device__ __forceinline__ RayScan ray_forward(const float *__restrict__ s, const float *__restrict__ c, const float2 *__restrict__ dl, uint32_t num,
-                                               uint32_t lane, float T_thresh) {
+// forward scan of one (S only) or two (S and T on the same samples) fields over the samples of a ray; the deltas are read once
+template <bool TWO>
+__device__ __forceinline__ void ray_forward(const float *__restrict__ s, const float *__restrict__ c, const float *__restrict__ s2, const float *__restrict__ c2,
+                                            const float2 *__restrict__ dl, uint32_t num, uint32_t lane, float T_thresh, RayScan &A, RayScan &B) {
     float r = 0, g = 0, b = 0, ws = 0, d = 0, T = 1.0f, t0 = 0.0f;
+    float r2 = 0, g2 = 0, b2 = 0, ws2 = 0, d2 = 0, T2 = 1.0f;
     for (uint32_t base = 0; base < num; base += 32) {
         const uint32_t i = base + lane;
         const bool in = i < num;
         float2 de = make_float2(0.f, 0.f);
-        float sg = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-        if (in) { de = __ldg(dl + i); sg = __ldg(s + i); c0 = __ldg(c + i * 3); c1 = __ldg(c + i * 3 + 1); c2 = __ldg(c + i * 3 + 2); }
-        const float alpha = in ? 1.0f - __expf(-sg * de.x) : 0.0f;
-        float tot;
-        const float Tb = T * warp_excl_prod(1.0f - alpha, lane, tot);
+        float sg = 0.f, c0 = 0.f, c1 = 0.f, cc2 = 0.f, sh = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f;
+        if (in) {
+            de = __ldg(dl + i); sg = __ldg(s + i); c0 = __ldg(c + i * 3); c1 = __ldg(c + i * 3 + 1); cc2 = __ldg(c + i * 3 + 2);
+            if (TWO) { sh = __ldg(s2 + i); e0 = __ldg(c2 + i * 3); e1 = __ldg(c2 + i * 3 + 1); e2 = __ldg(c2 + i * 3 + 2); }
+        }
         const float tt = t0 + warp_incl_sum(de.y, lane);
-        const bool take = in && (Tb >= T_thresh || i == 0);
-        const float w = take ? alpha * Tb : 0.0f;
-        r += w * c0; g += w * c1; b += w * c2; ws += w; d += w * tt;
-        T *= tot;
         t0 = __shfl_sync(0xffffffffu, tt, 31);
-        if (T < T_thresh) break;
+        const bool liveA = !(T < T_thresh), liveB = TWO && !(T2 < T_thresh);      // warp-uniform
+        if (liveA) {
+            const float alpha = in ? 1.0f - __expf(-sg * de.x) : 0.0f;
+            float tot;
+            const float Tb = T * warp_excl_prod(1.0f - alpha, lane, tot);
+            const bool take = in && (Tb >= T_thresh || i == 0);
+            const float w = take ? alpha * Tb : 0.0f;
+            r += w * c0; g += w * c1; b += w * cc2; ws += w; d += w * tt;
+            T *= tot;
+        }
+        if (liveB) {
+            const float alpha = in ? 1.0f - __expf(-sh * de.x) : 0.0f;
+            float tot;
+            const float Tb = T2 * warp_excl_prod(1.0f - alpha, lane, tot);
+            const bool take = in && (Tb >= T_thresh || i == 0);
+            const float w = take ? alpha * Tb : 0.0f;
+            r2 += w * e0; g2 += w * e1; b2 += w * e2; ws2 += w; d2 += w * tt;
+            T2 *= tot;
+        }
+        if (T < T_thresh && (!TWO || T2 < T_thresh)) break;
     }
-    RayScan o;
-    o.r = warp_sum_all(r); o.g = warp_sum_all(g); o.b = warp_sum_all(b); o.ws = warp_sum_all(ws); o.d = warp_sum_all(d);
-    return o;
+    A.r = warp_sum_all(r); A.g = warp_sum_all(g); A.b = warp_sum_all(b); A.ws = warp_sum_all(ws); A.d = warp_sum_all(d);
+    if (TWO) { B.r = warp_sum_all(r2); B.g = warp_sum_all(g2); B.b = warp_sum_all(b2); B.ws = warp_sum_all(ws2); B.d = warp_sum_all(d2); }
 }
 
 __global__ void __launch_bounds__(256)
@@ -604,11 +741,13 @@ k_distill_rays(const float *__restrict__ sig_t, const float *__restrict__ rgb_t,
         const bool live = num != 0 && offset + num <= M;
         const float2 *dl = reinterpret_cast<const float2 *>(deltas) + offset;
         RayScan S{0, 0, 0, 0, 0}, T{0, 0, 0, 0, 0};
-        if (live) S = ray_forward(sig_s + offset, rgb_s + (size_t)offset * 3, dl, num, lane, T_thresh);
+        if (live) {
+            if (sig_t) ray_forward<true>(sig_s + offset, rgb_s + (size_t)offset * 3, sig_t + offset, rgb_t + (size_t)offset * 3, dl, num, lane, T_thresh, S, T);
+            else ray_forward<false>(sig_s + offset, rgb_s + (size_t)offset * 3, nullptr, nullptr, dl, num, lane, T_thresh, S, T);
+        }
         float t0, t1, t2, td = 0.0f;
         bool has_depth = true;
         if (sig_t) {
-            if (live) T = ray_forward(sig_t + offset, rgb_t + (size_t)offset * 3, dl, num, lane, T_thresh);
             const float back_t = (1.0f - T.ws) * bg;
             t0 = T.r + back_t; t1 = T.g + back_t; t2 = T.b + back_t; td = T.d;
         } else {
@@ -733,14 +872,22 @@ S3D_API int s3d_packbits(const float *grid, uint32_t N, float density_thresh, ui
 }
 
 namespace {
+int g_march_clip = 1;   // s3d_march_set_clip: 0 walks every ray from its near point like the reference (tests compare the two)
 int march_count_scan(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma, uint32_t max_steps,
                      uint32_t N, uint32_t C, uint32_t H, const float *nears, const float *fars, const float *noises, int *rays,
                      int *counter, cudaStream_t st, uint32_t *bitmap = nullptr) {
     const uint32_t nb = div_up(N, 128u);
     uint32_t *block_sums = nullptr;
-    cudaError_t e = scratch_alloc((void **)&block_sums, (size_t)nb * sizeof(uint32_t), st);
+    cudaError_t e = scratch_alloc((void **)&block_sums, ((size_t)nb + 8) * sizeof(uint32_t), st);
     if (e != cudaSuccess) return (int)e;
-    k_march_count<<<nb, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, block_sums, bitmap);
+    int *occ_mm = nullptr;
+    if (g_march_clip && C == 1 && dt_gamma == 0.0f && H <= 1024) {   // occupied bounding box of the bitfield (stateless: recomputed per call, 262 KB read)
+        occ_mm = (int *)(block_sums + nb);
+        k_occ_bbox_init<<<1, 32, 0, st>>>(occ_mm);
+        const uint32_t n_bytes = H * H * H / 8;
+        k_occ_bbox<<<div_up(n_bytes, 256u), 256, 0, st>>>(grid, n_bytes, occ_mm);
+    }
+    k_march_count<<<nb, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, block_sums, bitmap, occ_mm);
     k_march_scan<<<1, 1024, 0, st>>>(block_sums, nb, N, counter);
     k_march_offsets<<<nb, 128, 0, st>>>(rays, N, block_sums);
     e = cudaPeekAtLastError();
@@ -748,6 +895,13 @@ int march_count_scan(const float *rays_o, const float *rays_d, const uint8_t *gr
     return (int)e;
 }
 }  // namespace
+
+// development / test switch: 1 (default) = rays are walked only inside the widened bounding box of the occupied cells
+// (single cascade, dt_gamma = 0), 0 = every ray is walked from its near point.  The samples are the same either way.
+S3D_API int s3d_march_set_clip(int enable) {
+    g_march_clip = enable ? 1 : 0;
+    return 0;
+}
 
 S3D_API int s3d_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
                                  float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,

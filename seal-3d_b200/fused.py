@@ -461,29 +461,33 @@ class FusedDistillTrainer:
         _lib.call("s3d_composite_rays_train_forward", sigmas, rgbs, deltas, rays, M, N, float(self.T_thresh), ws, depth, image)
         return ws, depth, image
 
-    def _student_backward(self, xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, image_t, depth_t, before_scatter=None):
+    def _student_backward(self, xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, image_t, depth_t, before_scatter=None, teacher=None):
+        """per-ray part (k_distill_rays: student composite, loss, compositor backward -- with teacher=(sig_t, rgb_t) also the
+        teacher's composite on the same samples) in one launch, then the field backward.  -> (loss buffer, loss scale)"""
         M, N = sig_s.shape[0], rays.shape[0]
         dev = sig_s.device
-        ws, depth, comp = self._composite(sig_s, rgb_s, deltas, rays)
-        g_img = torch.empty(N, 3, dtype=torch.float32, device=dev)
-        g_ws = torch.empty(N, dtype=torch.float32, device=dev)
         self.loss_buf.zero_()
-        _lib.call("s3d_finetune_loss", comp, ws, depth, image_t, depth_t, N, self.bg_color, self.loss_buf, g_img, g_ws)
         scale = self._scale(N)
-        g_img.mul_(scale)
-        g_ws.mul_(scale)
         g_sig = torch.zeros(M, dtype=torch.float32, device=dev)
         g_rgb = torch.zeros(M, 3, dtype=torch.float32, device=dev)
-        _lib.call("s3d_composite_rays_train_backward", g_ws, g_img, sig_s, rgb_s, deltas, rays, ws, comp, M, N, float(self.T_thresh), g_sig, g_rgb)
+        sig_t, rgb_t = teacher if teacher is not None else (None, None)
+        dyn = isinstance(scale, torch.Tensor)
+        _lib.call("s3d_distill_rays", sig_t, rgb_t, image_t, depth_t, sig_s, rgb_s, deltas, rays, M, N, float(self.T_thresh), self.bg_color,
+                  1.0 if dyn else float(scale), scale if dyn else None, self.loss_buf, g_sig, g_rgb)
         self.S.backward(xyzs, dirs, feats, g_sig, g_rgb, before_scatter=before_scatter, chunks=self.grad_chunks,
                         after_chunk=self._start_reduce if self.grad_chunks else None, sample_chunks=self.bwd_chunks)
         return self.loss_buf, scale
 
-    def _teacher_composite(self, mx, md, mask, feats_t, deltas, rays):
+    def _teacher_field(self, mx, md, mask, feats_t):
+        """teacher sigma / rgb on the (proxy-mapped) samples, colour edit applied"""
         t = self.teacher
         sig_t, rgb_t, _ = self.T.mlp_forward(feats_t, md)
         if mask is not None and t.seal_mapper is not None and t.seal_mapper.has_color_edit():
             t.seal_mapper.map_color_(rgb_t, mask, mx)
+        return sig_t, rgb_t
+
+    def _teacher_composite(self, mx, md, mask, feats_t, deltas, rays):
+        sig_t, rgb_t = self._teacher_field(mx, md, mask, feats_t)
         ws_t, depth_t, img_t = self._composite(sig_t, rgb_t, deltas, rays)
         img_t.add_((1 - ws_t).unsqueeze(-1) * self.bg_color)
         return img_t, depth_t
@@ -509,13 +513,14 @@ class FusedDistillTrainer:
             m8 = mask.view(torch.uint8) if mask is not None else None
             _lib.call("s3d_ngp_encode_pair", xyzs, mx if mask is not None else None, m8, M, self.S.bound, self.table8, self.S.offsets, self.S.L,
                       self.S.S, self.S.H, feats_t, feats)
-            img_t, depth_t = self._teacher_composite(mx, md, mask, feats_t, deltas, rays)
+            teacher_out = self._teacher_field(mx, md, mask, feats_t)
             sig_s, rgb_s, _ = self.S.mlp_forward(feats, dirs)
         else:
-            img_t, depth_t = self.teacher_targets(xyzs, dirs, deltas, rays)
+            mx, md, mask = self.teacher._map_samples(xyzs, dirs)
+            teacher_out = self._teacher_field(mx, md.contiguous().float(), mask, self.T.encode(mx.contiguous().float()))
             sig_s, rgb_s, feats = self.S.forward(xyzs, dirs)
-        loss, scale = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, img_t, depth_t,
-                                             before_scatter=ahead if self.world_size == 1 else None)
+        loss, scale = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, None, None,
+                                             before_scatter=ahead if self.world_size == 1 else None, teacher=teacher_out)
         if ahead is not None and self.world_size > 1:
             ahead()      # data parallel: the next batch is marched under the gradient all-reduce (NCCL needs only a few SMs)
         self._reduce_and_step(scale)

@@ -367,7 +367,10 @@ def test_full_checkpoint_resumes_training_and_is_a_torch_adam_state(engine, tmp_
     resumed = [step(b, 3), step(b, 4)]
     # float atomics in the scatter make runs differ in the last bits only
     np.testing.assert_allclose(np.array(resumed), np.array(cont), rtol=2e-3, atol=1e-9)
-    np.testing.assert_allclose(npy(b.student.encoder.embeddings), npy(a.student.encoder.embeddings), rtol=0, atol=2e-4)
+    # (Adam with eps = 1e-15 moves an entry by ~lr * sign(g) however small its gradient: the handful of entries whose summed
+    # gradient is at the rounding level of the float atomics may step differently in two runs)
+    diff = np.abs(npy(b.student.encoder.embeddings) - npy(a.student.encoder.embeddings))
+    assert (diff > 2e-4).mean() < 1e-5 and diff.max() < 2.5e-2, ((diff > 2e-4).sum(), diff.max())
     # ... and continues it exactly like our Adam kernel: same gradients into both, one step each
     c = make()
     ck.load_checkpoint(path, c)

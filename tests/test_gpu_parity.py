@@ -136,6 +136,35 @@ def test_march_rays_train_bit_exact(scene, dt_gamma, perturb):
         assert np.array_equal(xs[a:a + k], rx_[b:b + k]) and np.array_equal(ls[a:a + k], rl_[b:b + k])
 
 
+@pytest.mark.parametrize("perturb", [False, True])
+def test_march_occupied_box_clipping_changes_nothing_at_full_size(scene, perturb):
+    """the train marcher jumps a ray's step lattice in closed form to the (widened) bounding box of the occupied cells and
+    stops at its far side; at the benchmark's batch (262 144 rays) ray table, counter and every sample must be bit-identical
+    to walking every ray from its near point (s3d_march_set_clip(0)) -- also for an occupancy that touches the cube's faces"""
+    from seal3d_b200 import _lib
+    o, d = scene["synth"].rays_for_step(3, 262144)
+    o, d = to(o), to(d)
+    nears, fars = rm().near_far_from_aabb(o, d, to(AABB), 0.2)
+    noises = torch.rand(o.shape[0], device=dev(), generator=torch.Generator(device=dev()).manual_seed(5)) if perturb else None
+    grids = [scene["bits"]]
+    g2 = np.zeros(128 ** 3 // 8, np.uint8)
+    rng = np.random.default_rng(9)
+    g2[rng.integers(0, g2.shape[0], 3000)] = rng.integers(1, 256, 3000).astype(np.uint8)      # scattered cells all over the cube
+    grids.append(g2)
+    for bits in grids:
+        outs = []
+        for clip in (1, 0):
+            _lib.call_nostream("s3d_march_set_clip", clip)
+            try:
+                ctr = torch.zeros(2, dtype=torch.int32, device=dev())
+                outs.append(rm().march_rays_train(o, d, 1.0, to(bits), 1, 128, nears, fars, ctr, -1, perturb, 128, True, 0.0, 1024, noises=noises) + (ctr,))
+            finally:
+                _lib.call_nostream("s3d_march_set_clip", 1)
+        for a, b in zip(*outs):
+            assert torch.equal(a, b)
+        assert int(outs[0][4][0]) > 0
+
+
 def test_march_ragged_and_empty_batches(scene):
     """N not a multiple of the CTA size, N = 1, and a batch where no ray hits anything"""
     bits = scene["bits"]
