@@ -222,6 +222,16 @@ int s3d_density_grid_update(float *grid, const float *tmp_grid, uint32_t n, floa
 int s3d_packbits_dev_thresh(const float *grid, uint32_t N, const float *density_thresh_dev, uint8_t *bitfield, void *stream);
 int s3d_mean_count(const int *step_counter, uint32_t total_step, int *mean_count_out, void *stream);
 int s3d_density_grid_ema(float *grid, const float *tmp_grid, uint32_t n, float decay, float *sum_out, void *stream);
+/* Teacher + student NGP field forward on one sample buffer in ONE kernel (csrc/field.cu k_ngp_pair_fwd): hash-grid gather from
+ * the paired fp16 table (s3d_ngp_pair_tables) written straight into tensor memory + both tcgen05 MLP chains; the two halves of
+ * nerf/network.py:99-128 for SealNeRF's teacher (on the proxy-mapped samples) and student.  xyz_teacher / mask / dirs_teacher
+ * describe the moved samples (NULL: none / dirs); feats_student [M,64] fp16 is what s3d_ngp_mlp_backward recomputes from. */
+int s3d_ngp_pair_forward(const float *xyz, const float *xyz_teacher, const uint8_t *mask, const float *dirs, const float *dirs_teacher,
+                         uint32_t M, float bound, const void *table8, const int *offsets, uint32_t L, float S, uint32_t H,
+                         const void *t_s0, const void *t_s1, const void *t_c0, const void *t_c1, const void *t_c2, const void *s_s0,
+                         const void *s_s1, const void *s_c0, const void *s_c1, const void *s_c2, float density_scale_teacher,
+                         float density_scale_student, float *sigma_t, float *rgb_t, float *sigma_s, float *rgb_s, void *feats_student,
+                         void *stream);
 /* development / test switch of the train marcher: 1 (default) walks a ray only inside the widened bounding box of the occupied
  * cells (single cascade, dt_gamma = 0; the step lattice before the box is jumped in closed form), 0 walks it from its near
  * point like the reference.  The samples are identical either way (tests/test_gpu_parity.py compares them at full size). */

@@ -66,6 +66,7 @@ _SIGS = {
     "s3d_ngp_encode": [P, U32, F32, P, U32, P, U32, F32, U32, P, I32],
     "s3d_ngp_pair_tables": [P, P, P, U64],
     "s3d_ngp_encode_pair": [P, P, P, U32, F32, P, P, U32, F32, U32, P, P],
+    "s3d_ngp_pair_forward": [P, P, P, P, P, U32, F32, P, P, U32, F32, U32, P, P, P, P, P, P, P, P, P, P, F32, F32, P, P, P, P, P],
     "s3d_ngp_mlp_forward": [P, P, U32, P, P, P, P, P, F32, P, P, P, I32],
     "s3d_ngp_mlp_backward": [P, P, U32, P, P, P, P, P, F32, P, P, P, F32, P, P, P, P, P, I32],
     "s3d_ngp_scatter": [P, P, U32, F32, P, P, U32, F32, U32, F32],

@@ -255,6 +255,51 @@ __global__ void k_pair_tables(const uint2 *__restrict__ teacher4, const uint2 *_
 // ------------------------------------------------------------------------------------------------
 // scatter: dfeats -> interleaved fp32 gradient table
 // ------------------------------------------------------------------------------------------------
+// one level of one sample's gradient: in-warp segmented pre-reduction over runs of lanes that sit in the same cell (ray-major
+// samples share cells at the coarse levels), then one 128-bit RED per corner of every run.  Called by whole warps.
+__device__ __forceinline__ void scatter_level(const Geo &g, uint32_t l, bool ok, float ux, float uy, float uz, float g0, float g1, float g2, float g3,
+                                              uint32_t lane, float4 *__restrict__ grad4) {
+    Cell c;
+    unsigned long long key = ~0ull;
+    if (ok) locate(g, l, ux, uy, uz, c, &key);
+    else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) { c.idx[k] = 0; c.w[k] = 0.f; }
+    }
+    const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = (lane == 0) || (prev != key);
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    if (__popc(heads) <= 16) {
+        // runs of equal cells: fold every run into its head lane (segmented suffix sums), then one RED per corner
+        const uint32_t after = heads >> 1 >> lane;
+        const uint32_t seg_left = after ? (uint32_t)(__ffs(after) - 1) : (31u - lane);
+        // number of doubling steps the longest run of this warp needs (a run of n lanes needs ceil(log2 n))
+        const uint32_t cont = ~heads;                 // bit i: lane i continues the run of lane i-1
+        const uint32_t c2 = cont & (cont >> 1);       // some run longer than 2
+        const uint32_t c4 = c2 & (c2 >> 2);           // >= 4 consecutive continuation bits: longer than 4
+        const uint32_t c8 = c4 & (c4 >> 4);           // >= 8 consecutive: longer than 8
+        const uint32_t c16 = c8 & (c8 >> 8);          // longer than 16
+        const uint32_t nsteps = c16 ? 5 : (c8 ? 4 : (c4 ? 3 : (c2 ? 2 : 1)));
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            float a0 = c.w[k] * g0, a1 = c.w[k] * g1, a2 = c.w[k] * g2, a3 = c.w[k] * g3;
+#pragma unroll
+            for (uint32_t st = 0; st < 5; st++) {
+                if (st < nsteps) {
+                    const uint32_t d = 1u << st;
+                    const float o0 = __shfl_down_sync(0xffffffffu, a0, d), o1 = __shfl_down_sync(0xffffffffu, a1, d);
+                    const float o2 = __shfl_down_sync(0xffffffffu, a2, d), o3 = __shfl_down_sync(0xffffffffu, a3, d);
+                    if (d <= seg_left) { a0 += o0; a1 += o1; a2 += o2; a3 += o3; }
+                }
+            }
+            if (ok && head) atomicAdd(grad4 + c.idx[k], make_float4(a0, a1, a2, a3));
+        }
+    } else if (ok) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) atomicAdd(grad4 + c.idx[k], make_float4(c.w[k] * g0, c.w[k] * g1, c.w[k] * g2, c.w[k] * g3));
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, uint32_t M, float bound,
               float4 *__restrict__ grad4, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H, float grad_scale,
@@ -280,46 +325,8 @@ k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, 
             const uint32_t ps = q == 0 ? rs.x : (q == 1 ? rs.y : (q == 2 ? rs.z : rs.w));
             const uint32_t pc = q == 0 ? rc.x : (q == 1 ? rc.y : (q == 2 ? rc.z : rc.w));
             const float2 fs = __half22float2(*reinterpret_cast<const __half2 *>(&ps)), fc = __half22float2(*reinterpret_cast<const __half2 *>(&pc));
-            Cell c;
-            unsigned long long key = ~0ull;
-            if (ok) locate(g, l, ux, uy, uz, c, &key);
-            else {
-#pragma unroll
-                for (int k = 0; k < 8; k++) { c.idx[k] = 0; c.w[k] = 0.f; }
-            }
             const float g0 = fs.x * grad_scale, g1 = fs.y * grad_scale, g2 = fc.x * grad_scale, g3 = fc.y * grad_scale;
-            const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
-            const bool head = (lane == 0) || (prev != key);
-            const uint32_t heads = __ballot_sync(0xffffffffu, head);
-            if (__popc(heads) <= 16) {
-                // runs of equal cells: fold every run into its head lane (segmented suffix sums), then one RED per corner
-                const uint32_t after = heads >> 1 >> lane;
-                const uint32_t seg_left = after ? (uint32_t)(__ffs(after) - 1) : (31u - lane);
-                // number of doubling steps the longest run of this warp needs (a run of n lanes needs ceil(log2 n))
-                const uint32_t cont = ~heads;                 // bit i: lane i continues the run of lane i-1
-                const uint32_t c2 = cont & (cont >> 1);       // some run longer than 2
-                const uint32_t c4 = c2 & (c2 >> 2);           // >= 4 consecutive continuation bits: longer than 4
-                const uint32_t c8 = c4 & (c4 >> 4);           // >= 8 consecutive: longer than 8
-                const uint32_t c16 = c8 & (c8 >> 8);          // longer than 16
-                const uint32_t nsteps = c16 ? 5 : (c8 ? 4 : (c4 ? 3 : (c2 ? 2 : 1)));
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    float a0 = c.w[k] * g0, a1 = c.w[k] * g1, a2 = c.w[k] * g2, a3 = c.w[k] * g3;
-#pragma unroll
-                    for (uint32_t st = 0; st < 5; st++) {
-                        if (st < nsteps) {
-                            const uint32_t d = 1u << st;
-                            const float o0 = __shfl_down_sync(0xffffffffu, a0, d), o1 = __shfl_down_sync(0xffffffffu, a1, d);
-                            const float o2 = __shfl_down_sync(0xffffffffu, a2, d), o3 = __shfl_down_sync(0xffffffffu, a3, d);
-                            if (d <= seg_left) { a0 += o0; a1 += o1; a2 += o2; a3 += o3; }
-                        }
-                    }
-                    if (ok && head) atomicAdd(grad4 + c.idx[k], make_float4(a0, a1, a2, a3));
-                }
-            } else if (ok) {
-#pragma unroll
-                for (int k = 0; k < 8; k++) atomicAdd(grad4 + c.idx[k], make_float4(c.w[k] * g0, c.w[k] * g1, c.w[k] * g2, c.w[k] * g3));
-            }
+            scatter_level(g, l, ok, ux, uy, uz, g0, g1, g2, g3, lane, grad4);
         }
     }
 }
@@ -726,6 +733,204 @@ k_ngp_mlp_fwd_ts(const FwdArgs a) {
         }
     }
     if (is_issuer) tmem_dealloc(tmem, kTsCols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Teacher + student field forward in ONE kernel: hash-grid gather and both MLPs on the same SM at the same time.
+//
+//   The gather is bound by the SM's load pipe (one L1 wavefront per divergent 16-byte corner), the MLP by the tensor-core /
+//   TMEM round trips of its five dependent layers; run as two kernels they take 1.65 + 0.61 ms and each leaves the other's
+//   resource idle.  Here a persistent CTA (one per SM) owns two SLOTS of tensor memory (256 columns each: a teacher chain and
+//   a student chain laid out like k_ngp_mlp_fwd_ts).  Each slot has 8 generalist warps: they gather the 128 samples of a tile
+//   for both models from the paired table (thread (r, hf): sample r, levels 8 hf .. 8 hf + 7) and write the feature halves
+//   STRAIGHT INTO TENSOR MEMORY as the first layer's A operand (tcgen05.st; no [M,64] feature rows through HBM for the teacher,
+//   no shared-memory tile), then serve the epilogues of the slot's two MLP chains.  The two slots run half a period apart, so
+//   while one slot's warps wait on tensor-core round trips the other slot's warps keep the load pipe busy.  One issuer warp
+//   per slot issues that slot's MMAs; every hand-off is an mbarrier (bounded waits: a protocol error traps instead of hanging).
+//   The student's feature rows are also written to global memory: the backward recomputes the MLP from them.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kPairSlotThreads = 256, kPairSlots = 2;
+constexpr uint32_t kPairThreads = kPairSlots * kPairSlotThreads + kPairSlots * 32;   // + one issuer warp per slot
+
+struct PairArgs {
+    const float *xyz, *xyz_teacher, *dirs, *dirs_teacher;
+    const uint8_t *mask;
+    const uint4 *table8;
+    const int *offsets;
+    MlpWeights wt, ws;
+    float *sigma_t, *rgb_t, *sigma_s, *rgb_s;
+    __half *feats_s;
+    uint32_t M, n_tiles, L, H;
+    float bound, S, dscale_t, dscale_s;
+};
+
+__global__ void __launch_bounds__(kPairThreads, 1)
+k_ngp_pair_fwd(const PairArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ Geo g;
+    __shared__ __align__(8) uint64_t s_full[kPairSlots][2], s_done[kPairSlots][2];
+    __shared__ uint32_t s_tmem;
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr uint32_t kWBytes = 3 * kWTile + 2 * kOTile;
+    uint8_t *wT = smem, *wS = smem + kWBytes;
+    const uint32_t tid = threadIdx.x, warp = warp_idx_sync();
+    const bool is_issuer = warp >= kPairSlots * 8;
+    const uint32_t slot = is_issuer ? warp - kPairSlots * 8 : warp >> 3;
+    geo_init(g, a.offsets, a.L, a.S, a.H);
+    if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
+    if (tid == 32) {
+        for (uint32_t s = 0; s < kPairSlots; s++)
+            for (uint32_t c = 0; c < 2; c++) { mbar_init(smem_u32(&s_full[s][c]), kPairSlotThreads); mbar_init(smem_u32(&s_done[s][c]), 1); }
+    }
+    load_weights(wT, wT + 3 * kWTile, wT + kWTile, wT + 2 * kWTile, wT + 3 * kWTile + kOTile, a.wt);
+    load_weights(wS, wS + 3 * kWTile, wS + kWTile, wS + 2 * kWTile, wS + 3 * kWTile + kOTile, a.ws);
+    sync_tiles();
+    const uint32_t tmem = s_tmem;
+    const uint32_t id64 = make_idesc(128, 64, false, false), id16 = make_idesc(128, 16, false, false);
+    const uint32_t first = blockIdx.x * kPairSlots + slot, stride = gridDim.x * kPairSlots;
+
+    if (is_issuer) {
+        const bool lead = elect_one();
+        uint32_t par = 0;
+        for (uint32_t tile = first; tile < a.n_tiles; tile += stride) {
+            for (uint32_t round = 0; round < 5; round++) {
+#pragma unroll
+                for (uint32_t c = 0; c < 2; c++) {
+                    const uint32_t base = tmem + slot * 256 + c * 128, acc = base + kTsAcc, tH = base + kTsH, tC = base + kTsCin;
+                    const uint32_t w0 = smem_u32(c == 0 ? wT : wS);   // tile order inside a weight block: Ws0 | Wc0 | Wc1 | Ws1 | Wc2
+                    const uint32_t aWs0 = w0, aWc0 = w0 + kWTile, aWc1 = w0 + 2 * kWTile, aWs1 = w0 + 3 * kWTile, aWc2 = w0 + 3 * kWTile + kOTile;
+                    mbar_wait(smem_u32(&s_full[slot][c]), par);
+                    fence_after_sync();
+                    if (round == 0) { for (uint32_t k = 0; k < 2; k++) mma_f16_ts_if(lead, acc, tH + 8 * k, desc_kmajor(aWs0, k), id64, k > 0); }
+                    else if (round == 1) { for (uint32_t k = 0; k < 4; k++) mma_f16_ts_if(lead, acc, tH + 8 * k, desc_kmajor(aWs1, k), id16, k > 0); }
+                    else if (round == 2) { for (uint32_t k = 0; k < 4; k++) mma_f16_ts_if(lead, acc, tC + 8 * k, desc_kmajor(aWc0, k), id64, k > 0); }
+                    else if (round == 3) { for (uint32_t k = 0; k < 4; k++) mma_f16_ts_if(lead, acc, tH + 8 * k, desc_kmajor(aWc1, k), id64, k > 0); }
+                    else { for (uint32_t k = 0; k < 4; k++) mma_f16_ts_if(lead, acc, tH + 8 * k, desc_kmajor(aWc2, k), id16, k > 0); }
+                    mma_commit_if(lead, smem_u32(&s_done[slot][c]));
+                }
+                par ^= 1;
+            }
+        }
+    } else {
+        const uint32_t st = tid & (kPairSlotThreads - 1), r = st & 127, hf = st >> 7;
+        const uint32_t t_row = tmem + (((warp & 3u) * 32u) << 16) + slot * 256;
+        uint32_t par = 0;    // parity of the done barriers (flips once per round)
+        auto publish = [&](uint32_t c) {
+            tmem_st_wait();
+            fence_before_sync();
+            mbar_arrive(smem_u32(&s_full[slot][c]));
+        };
+        auto wait_done = [&](uint32_t c) {
+            mbar_wait(smem_u32(&s_done[slot][c]), par);
+            fence_after_sync();
+        };
+        for (uint32_t tile = first; tile < a.n_tiles; tile += stride) {
+            const uint32_t row = tile * kRows + r;
+            const bool in_range = row < a.M;
+            // ---------------- gather: levels 8 hf .. 8 hf + 7 of sample `row`, teacher and student ----------------
+            float ux = 0, uy = 0, uz = 0, tx = 0, ty = 0, tz = 0;
+            bool ok = false, moved = false, tok = false;
+            if (in_range) {
+                ok = load_unit(a.xyz, row, a.bound, ux, uy, uz);
+                moved = a.mask && a.mask[row];
+                tok = ok;
+                if (moved) tok = load_unit(a.xyz_teacher, row, a.bound, tx, ty, tz);
+            }
+            uint32_t pTs[8], pTc[8], pSs[8], pSc[8];
+#pragma unroll
+            for (uint32_t j = 0; j < 8; j++) {
+                const uint32_t l = hf * 8 + j;
+                float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                if (ok && l < a.L) {
+                    Cell c;
+                    locate(g, l, ux, uy, uz, c, nullptr);
+                    uint4 v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = __ldg(a.table8 + c.idx[k]);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        acc4(make_uint2(v[k].z, v[k].w), c.w[k], s0, s1, s2, s3);
+                        if (!moved) acc4(make_uint2(v[k].x, v[k].y), c.w[k], t0, t1, t2, t3);
+                    }
+                }
+                if (moved && tok && l < a.L) {
+                    Cell c;
+                    locate(g, l, tx, ty, tz, c, nullptr);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const uint4 v = __ldg(a.table8 + c.idx[k]);
+                        acc4(make_uint2(v.x, v.y), c.w[k], t0, t1, t2, t3);
+                    }
+                }
+                pTs[j] = pack2(t0, t1); pTc[j] = pack2(t2, t3); pSs[j] = pack2(s0, s1); pSc[j] = pack2(s2, s3);
+            }
+            // feature halves -> tensor memory (A operands of sigma layer 0 and colour layer 0), student rows -> global
+            tmem_st8(t_row + 0 * 128 + kTsH + 8 * hf, pTs);
+            tmem_st8(t_row + 0 * 128 + kTsCin + 8 * hf, pTc);
+            tmem_st8(t_row + 1 * 128 + kTsH + 8 * hf, pSs);
+            tmem_st8(t_row + 1 * 128 + kTsCin + 8 * hf, pSc);
+            if (in_range) {
+                uint4 *dst = reinterpret_cast<uint4 *>(a.feats_s + (size_t)row * 64);
+                dst[2 * hf] = make_uint4(pSs[0], pSs[1], pSs[2], pSs[3]); dst[2 * hf + 1] = make_uint4(pSs[4], pSs[5], pSs[6], pSs[7]);
+                dst[4 + 2 * hf] = make_uint4(pSc[0], pSc[1], pSc[2], pSc[3]); dst[4 + 2 * hf + 1] = make_uint4(pSc[4], pSc[5], pSc[6], pSc[7]);
+            }
+            float dT[3] = {0.f, 0.f, 0.f}, dS[3] = {0.f, 0.f, 0.f};
+            if (hf == 0 && in_range) {
+#pragma unroll
+                for (int i = 0; i < 3; i++) { dS[i] = a.dirs[(size_t)row * 3 + i]; dT[i] = a.dirs_teacher[(size_t)row * 3 + i]; }
+            }
+            publish(0); publish(1);
+            // ---------------- the two MLP chains, epilogues interleaved ----------------
+            // round 0: sigma layer 0 -> H1
+#pragma unroll
+            for (uint32_t c = 0; c < 2; c++) { wait_done(c); relu_to_tmem(t_row + c * 128 + kTsAcc + hf * 32, t_row + c * 128 + kTsH + hf * 16); publish(c); }
+            par ^= 1;
+            // round 1: sigma layer 1 -> sigma, [SH | geo]
+#pragma unroll
+            for (uint32_t c = 0; c < 2; c++) {
+                wait_done(c);
+                if (hf == 0) {
+                    float h2[16], gg[32];
+                    tmem_ld16(t_row + c * 128 + kTsAcc, h2);
+                    if (in_range) (c == 0 ? a.sigma_t : a.sigma_s)[row] = (c == 0 ? a.dscale_t : a.dscale_s) * __expf(h2[0]);
+                    const float *dd = c == 0 ? dT : dS;
+                    sh4(dd[0], dd[1], dd[2], gg);
+#pragma unroll
+                    for (int i = 0; i < 15; i++) gg[16 + i] = h2[1 + i];
+                    gg[31] = 0.0f;
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) pk[i] = pack_half2(gg[2 * i], gg[2 * i + 1]);
+                    tmem_st16(t_row + c * 128 + kTsCin + 16, pk);
+                }
+                publish(c);
+            }
+            par ^= 1;
+            // rounds 2, 3: colour layers 0, 1
+            for (uint32_t rr = 0; rr < 2; rr++) {
+#pragma unroll
+                for (uint32_t c = 0; c < 2; c++) { wait_done(c); relu_to_tmem(t_row + c * 128 + kTsAcc + hf * 32, t_row + c * 128 + kTsH + hf * 16); publish(c); }
+                par ^= 1;
+            }
+            // round 4: colour layer 2 -> rgb
+#pragma unroll
+            for (uint32_t c = 0; c < 2; c++) {
+                wait_done(c);
+                if (hf == 0) {
+                    float o[16];
+                    tmem_ld16(t_row + c * 128 + kTsAcc, o);
+                    if (in_range) {
+                        float *dst = (c == 0 ? a.rgb_t : a.rgb_s) + (size_t)row * 3;
+#pragma unroll
+                        for (int i = 0; i < 3; i++) dst[i] = 1.0f / (1.0f + __expf(-o[i]));
+                    }
+                }
+            }
+            par ^= 1;
+        }
+    }
+    tile_end_sync();
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1212,6 +1417,32 @@ S3D_API int s3d_ngp_mlp_forward(const void *feats, const float *dirs, uint32_t M
     static const uint32_t per_sm = [] { const char *e = getenv("S3D_MLP_FWD_CTAS"); const int v = e ? atoi(e) : 3; return (uint32_t)(v >= 1 && v <= 4 ? v : 3); }();
     const uint32_t grid = min(a.n_tiles, (uint32_t)sm_count() * per_sm);
     k_ngp_mlp_fwd_ts<<<grid, kMlpThreads, smem_ts, as_stream(stream)>>>(a);
+    S3D_RETURN_LAST();
+}
+
+// teacher + student forward on one sample buffer: gather from the paired table + both MLPs in one kernel (k_ngp_pair_fwd).
+// xyz_teacher / mask / dirs_teacher: the proxy-mapped positions / moved flags / mapped directions (xyz_teacher and mask may be
+// NULL: no sample moved; dirs_teacher NULL = dirs).  weights_*: the five fp16 nn.Linear matrices of each model.
+S3D_API int s3d_ngp_pair_forward(const float *xyz, const float *xyz_teacher, const uint8_t *mask, const float *dirs, const float *dirs_teacher,
+                                 uint32_t M, float bound, const void *table8, const int *offsets, uint32_t L, float S, uint32_t H,
+                                 const void *t_s0, const void *t_s1, const void *t_c0, const void *t_c1, const void *t_c2, const void *s_s0,
+                                 const void *s_s1, const void *s_c0, const void *s_c1, const void *s_c2, float density_scale_teacher,
+                                 float density_scale_student, float *sigma_t, float *rgb_t, float *sigma_s, float *rgb_s, void *feats_student,
+                                 void *stream) {
+    if (M == 0) return 0;
+    if (L > kMaxLevels) return S3D_ENOTSUP;
+    const size_t smem = 1024 + 2 * (3 * kWTile + 2 * kOTile);
+    cudaError_t e = cudaFuncSetAttribute(k_ngp_pair_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    PairArgs a;
+    a.xyz = xyz; a.xyz_teacher = xyz_teacher; a.mask = xyz_teacher ? mask : nullptr; a.dirs = dirs; a.dirs_teacher = dirs_teacher ? dirs_teacher : dirs;
+    a.table8 = (const uint4 *)table8; a.offsets = offsets;
+    a.wt = MlpWeights{(const __half *)t_s0, (const __half *)t_s1, (const __half *)t_c0, (const __half *)t_c1, (const __half *)t_c2};
+    a.ws = MlpWeights{(const __half *)s_s0, (const __half *)s_s1, (const __half *)s_c0, (const __half *)s_c1, (const __half *)s_c2};
+    a.sigma_t = sigma_t; a.rgb_t = rgb_t; a.sigma_s = sigma_s; a.rgb_s = rgb_s; a.feats_s = (__half *)feats_student;
+    a.M = M; a.n_tiles = div_up(M, kRows); a.L = L; a.H = H; a.bound = bound; a.S = S; a.dscale_t = density_scale_teacher; a.dscale_s = density_scale_student;
+    const uint32_t grid = min(div_up(a.n_tiles, kPairSlots), (uint32_t)sm_count());
+    k_ngp_pair_fwd<<<grid, kPairThreads, smem, as_stream(stream)>>>(a);
     S3D_RETURN_LAST();
 }
 

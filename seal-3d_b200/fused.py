@@ -169,8 +169,8 @@ class FusedNGP:
         slice k (bound by the SMs' REDG issue rate) runs on the current stream: one scatter CTA fits next to the MLP CTA on
         every SM (registers 544 x <= 80 + 256 x 64, shared memory 222 KB + 0.3 KB), so the two limiters overlap."""
         M = feats.shape[0]
-        dfeats = torch.empty(M, 64, dtype=torch.float16, device=self.dev)
         w, gw = self._w16(), self._gw()
+        dfeats = torch.empty(M, 64, dtype=torch.float16, device=self.dev)
         if sample_chunks > 1 and not chunks and M >= 128 * sample_chunks:
             per = (M + sample_chunks - 1) // sample_chunks
             per = (per + 127) // 128 * 128
@@ -327,6 +327,7 @@ class FusedDistillTrainer:
         n_chunks = int(os.environ.get("S3D_GRAD_CHUNKS", 1))
         self.grad_chunks = self.S.grad_chunks(n_chunks) if (world_size > 1 and n_chunks > 1) else None
         self._pending = []
+        self.fused_forward = os.environ.get("S3D_PAIR_FORWARD", "0") != "0"   # gather + both MLPs in one kernel (k_ngp_pair_fwd)
         self.bwd_chunks = int(os.environ.get("S3D_BWD_CHUNKS", 1))   # MLP backward / scatter overlap (FusedNGP.backward)
         self._side, self._pref = None, None     # side stream + the pre-marched next batch (see _prefetch)
         self._cur = self._old = None            # pre-marched tensors in use by this / the previous step (kept alive, see _prefetch)
@@ -508,13 +509,27 @@ class FusedDistillTrainer:
             # one gather pass for both models (moved samples take a second gather for the teacher)
             M = xyzs.shape[0]
             mx, md, mask = self.teacher._map_samples(xyzs, dirs)
-            feats_t = torch.empty(M, 64, dtype=torch.float16, device=xyzs.device)
             feats = torch.empty(M, 64, dtype=torch.float16, device=xyzs.device)
             m8 = mask.view(torch.uint8) if mask is not None else None
-            _lib.call("s3d_ngp_encode_pair", xyzs, mx if mask is not None else None, m8, M, self.S.bound, self.table8, self.S.offsets, self.S.L,
-                      self.S.S, self.S.H, feats_t, feats)
-            teacher_out = self._teacher_field(mx, md, mask, feats_t)
-            sig_s, rgb_s, _ = self.S.mlp_forward(feats, dirs)
+            if self.fused_forward:
+                # gather + both MLPs in one kernel: features go from the gather warps straight into tensor memory
+                dev = xyzs.device
+                sig_t, sig_s = torch.empty(M, dtype=torch.float32, device=dev), torch.empty(M, dtype=torch.float32, device=dev)
+                rgb_t, rgb_s = torch.empty(M, 3, dtype=torch.float32, device=dev), torch.empty(M, 3, dtype=torch.float32, device=dev)
+                wt, ws = self.T._w16(), self.S._w16()
+                _lib.call("s3d_ngp_pair_forward", xyzs, mx if mask is not None else None, m8, dirs, md if mask is not None else None, M, self.S.bound,
+                          self.table8, self.S.offsets, self.S.L, self.S.S, self.S.H, wt[0], wt[1], wt[2], wt[3], wt[4], ws[0], ws[1], ws[2], ws[3], ws[4],
+                          self.T.density_scale, self.S.density_scale, sig_t, rgb_t, sig_s, rgb_s, feats)
+                t = self.teacher
+                if mask is not None and t.seal_mapper is not None and t.seal_mapper.has_color_edit():
+                    t.seal_mapper.map_color_(rgb_t, mask, mx)
+                teacher_out = (sig_t, rgb_t)
+            else:
+                feats_t = torch.empty(M, 64, dtype=torch.float16, device=xyzs.device)
+                _lib.call("s3d_ngp_encode_pair", xyzs, mx if mask is not None else None, m8, M, self.S.bound, self.table8, self.S.offsets, self.S.L,
+                          self.S.S, self.S.H, feats_t, feats)
+                teacher_out = self._teacher_field(mx, md, mask, feats_t)
+                sig_s, rgb_s, _ = self.S.mlp_forward(feats, dirs)
         else:
             mx, md, mask = self.teacher._map_samples(xyzs, dirs)
             teacher_out = self._teacher_field(mx, md.contiguous().float(), mask, self.T.encode(mx.contiguous().float()))

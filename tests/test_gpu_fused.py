@@ -439,6 +439,34 @@ def test_dynamic_scale_resume_keeps_adam_step_counts_and_pretraining_leaves_the_
     np.testing.assert_allclose(npy(b.student.encoder.embeddings), npy(a.student.encoder.embeddings), rtol=0, atol=2e-4)
 
 
+def test_pair_forward_kernel_equals_separate_gather_and_mlps(scene):
+    """k_ngp_pair_fwd (gather + teacher / student MLP chains in one kernel, features written straight into tensor memory; kept
+    behind S3D_PAIR_FORWARD because it is slower than the separate kernels, profiles/r2_experiments.md) computes what
+    s3d_ngp_encode_pair + 2 x s3d_ngp_mlp_forward compute: same sigma / rgb for both models, bit-identical student feature rows"""
+    from seal3d_b200 import _lib
+    from seal3d_b200.fused import FusedDistillTrainer
+    t, s, _, _ = _networks(scene)
+    tr = FusedDistillTrainer(s, t, lr=1e-2, update_interval=0)
+    x0, d0, _, _, M = _samples(scene, 1024)
+    xyzs, dirs = to(x0), to(d0)
+    mx, md, mask = t._map_samples(xyzs, dirs)
+    assert mask is not None and bool(mask.any())
+    m8 = mask.view(torch.uint8)
+    feats_t = torch.empty(M, 64, dtype=torch.float16, device=dev())
+    feats = torch.empty(M, 64, dtype=torch.float16, device=dev())
+    _lib.call("s3d_ngp_encode_pair", xyzs, mx, m8, M, tr.S.bound, tr.table8, tr.S.offsets, tr.S.L, tr.S.S, tr.S.H, feats_t, feats)
+    sig_t, rgb_t, _ = tr.T.mlp_forward(feats_t, md)
+    sig_s, rgb_s, _ = tr.S.mlp_forward(feats, dirs)
+    o = [torch.empty(M, device=dev()), torch.empty(M, 3, device=dev()), torch.empty(M, device=dev()), torch.empty(M, 3, device=dev())]
+    feats2 = torch.empty_like(feats)
+    wt, ws = tr.T._w16(), tr.S._w16()
+    _lib.call("s3d_ngp_pair_forward", xyzs, mx, m8, dirs, md, M, tr.S.bound, tr.table8, tr.S.offsets, tr.S.L, tr.S.S, tr.S.H, wt[0], wt[1], wt[2], wt[3], wt[4],
+              ws[0], ws[1], ws[2], ws[3], ws[4], tr.T.density_scale, tr.S.density_scale, o[0], o[1], o[2], o[3], feats2)
+    assert torch.equal(feats2, feats)
+    for got, want in zip(o, (sig_t, rgb_t, sig_s, rgb_s)):
+        assert torch.equal(got, want)
+
+
 def test_marching_one_step_ahead_changes_nothing(scene):
     """the pipelined schedule (next batch marched on a side stream, pinned host rays copied there too) produces the losses
     and parameters of the inline schedule; no batch is pre-marched across an occupancy refresh"""
