@@ -232,6 +232,12 @@ int s3d_ngp_pair_forward(const float *xyz, const float *xyz_teacher, const uint8
                          const void *s_s1, const void *s_c0, const void *s_c1, const void *s_c2, float density_scale_teacher,
                          float density_scale_student, float *sigma_t, float *rgb_t, float *sigma_s, float *rgb_s, void *feats_student,
                          void *stream);
+/* One bias-free nn.Linear on tensor cores (the wide FFMLP kernels with no hidden layer): y [B,out] = x [B,in] . W^T, W [out,in]
+ * row-major, fp16 in / out, fp32 accumulation; in a multiple of 16 (<= 256), out <= 256.  TensoRF's basis_mat
+ * (tensoRF/network.py:42,155).  Backward: grad_x [B,in] (NULL = not wanted), grad_w [out,in] overwritten. */
+int s3d_linear_forward(const void *x, const void *w, uint32_t B, uint32_t in_dim, uint32_t out_dim, void *y, void *stream);
+int s3d_linear_backward(const void *grad_y, const void *x, const void *w, uint32_t B, uint32_t in_dim, uint32_t out_dim, void *grad_x,
+                        void *grad_w, void *stream);
 /* development / test switch of the train marcher: 1 (default) walks a ray only inside the widened bounding box of the occupied
  * cells (single cascade, dt_gamma = 0; the step lattice before the box is jumped in closed form), 0 walks it from its near
  * point like the reference.  The samples are identical either way (tests/test_gpu_parity.py compares them at full size). */

@@ -57,7 +57,8 @@ struct Dims {
 
 // matrix m of the network: 0 = input layer, 1 .. num_layers-1 = hidden, num_layers = output layer
 __device__ __forceinline__ void matrix_shape(const Dims &d, uint32_t m, uint32_t &rows, uint32_t &cols, uint32_t &pad_rows, size_t &goff) {
-    if (m == 0) { rows = d.hidden; cols = d.in_dim; pad_rows = d.hidden; goff = 0; }
+    if (d.num_layers == 0) { rows = d.out_dim; cols = d.in_dim; pad_rows = d.out_pad; goff = 0; }   // a single bias-free Linear (s3d_linear_*)
+    else if (m == 0) { rows = d.hidden; cols = d.in_dim; pad_rows = d.hidden; goff = 0; }
     else if (m < d.num_layers) { rows = d.hidden; cols = d.hidden; pad_rows = d.hidden; goff = (size_t)d.hidden * d.in_dim + (size_t)(m - 1) * d.hidden * d.hidden; }
     else { rows = d.out_dim; cols = d.hidden; pad_rows = d.out_pad; goff = (size_t)d.hidden * d.in_dim + (size_t)(d.num_layers - 1) * d.hidden * d.hidden; }
 }
@@ -168,7 +169,7 @@ k_wide_forward(const FwdP p) {
             }
             sync_all();                           // A stores + weights visible to the issuing thread
             const bool last = (m == n_mat - 1);
-            const uint32_t N = last ? d.out_pad : d.hidden, K = (m == 0) ? d.in_pad : d.hidden;
+            const uint32_t N = last ? d.out_pad : d.hidden, K = (m == 0) ? d.in_pad : d.hidden;   // num_layers = 0: m = 0 is also the last
             if (warp == 0) {
                 const bool lead = elect_one();
                 const uint32_t idesc = make_idesc(128, N, false, false);
@@ -241,7 +242,7 @@ k_wide_backward(const BwdP p) {
     const uint32_t mbar = smem_u32(&s_mbar);
     if (warp == 0) tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
     if (tid == 0) mbar_init(mbar, 1);
-    const uint32_t n_mat = d.num_layers + 1, n_hid = d.num_layers - 1;
+    const uint32_t n_mat = d.num_layers + 1;
     if (d.resident) {
         for (uint32_t m = 0; m < n_mat; m++) {
             uint32_t r, c, pr; size_t g;
@@ -254,7 +255,7 @@ k_wide_backward(const BwdP p) {
     const uint32_t tmem = s_tmem, t_row = tmem + ((warp * 32u) << 16);
     const uint32_t t_acc = t_row, t_a = t_row + p.a_col;
     uint32_t parity = 0;
-    const uint32_t n_steps = p.grad_inputs ? n_hid + 2 : n_hid + 1;
+    const uint32_t n_steps = d.num_layers + (p.grad_inputs ? 1u : 0u);
     for (uint32_t tile = blockIdx.x; tile < d.n_tiles; tile += gridDim.x) {
         const uint32_t row = tile * kRows + tid;
         const bool in_range = row < d.B;
@@ -417,15 +418,18 @@ uint32_t pow2_cols(uint32_t need) {
 }
 
 int make_dims(Dims &d, uint32_t B, uint32_t in_dim, uint32_t out_dim, uint32_t hidden, uint32_t num_layers, uint32_t act, uint32_t out_act, size_t &w_bytes) {
-    if (hidden != 16 && hidden != 32 && hidden != 64 && hidden != 128 && hidden != 256) return S3D_ENOTSUP;   // ffmlp.cu:658
+    const bool linear = num_layers == 0;       // s3d_linear_*: one matrix, no hidden layer
+    if (!linear && hidden != 16 && hidden != 32 && hidden != 64 && hidden != 128 && hidden != 256) return S3D_ENOTSUP;   // ffmlp.cu:658
     if (in_dim == 0 || in_dim % 16 != 0 || in_dim > 256) return S3D_EINVAL;
     if (out_dim == 0 || out_dim > 256) return S3D_EINVAL;
-    if (num_layers < 2 || num_layers > 8) return S3D_EINVAL;
+    if (!linear && (num_layers < 2 || num_layers > 8)) return S3D_EINVAL;
+    if (linear) hidden = 0;
     d.B = B; d.in_dim = in_dim; d.out_dim = out_dim; d.hidden = hidden; d.num_layers = num_layers; d.act = act; d.out_act = out_act;
     d.in_pad = in_dim; d.out_pad = (out_dim + 15) / 16 * 16;
     d.n_tiles = div_up(B, kRows);
-    const size_t total = matrix_bytes(hidden, in_dim) + (size_t)(num_layers - 1) * matrix_bytes(hidden, hidden) + matrix_bytes(d.out_pad, hidden);
-    const size_t largest = max(max((size_t)matrix_bytes(hidden, in_dim), (size_t)matrix_bytes(hidden, hidden)), (size_t)matrix_bytes(d.out_pad, hidden));
+    const size_t total = linear ? matrix_bytes(d.out_pad, in_dim)
+                                : matrix_bytes(hidden, in_dim) + (size_t)(num_layers - 1) * matrix_bytes(hidden, hidden) + matrix_bytes(d.out_pad, hidden);
+    const size_t largest = linear ? total : max(max((size_t)matrix_bytes(hidden, in_dim), (size_t)matrix_bytes(hidden, hidden)), (size_t)matrix_bytes(d.out_pad, hidden));
     d.resident = total <= 200 * 1024;
     w_bytes = d.resident ? total : largest;
     return 0;
@@ -448,6 +452,7 @@ int s3d_ffmlp_wide_forward(const __half *inputs, const __half *weights, uint32_t
     size_t w_bytes = 0;
     if (int rc = make_dims(p.d, B, in_dim, out_dim, hidden, num_layers, act, out_act, w_bytes)) return rc;
     p.inputs = inputs; p.weights = weights; p.forward_buffer = forward_buffer; p.outputs = outputs;
+    hidden = p.d.hidden;
     const uint32_t acc_cols = max(hidden, p.d.out_pad), a_cols = (max(max(p.d.in_pad, hidden), 32u) + 31) / 32 * 16;
     p.a_col = acc_cols;
     p.tmem_cols = pow2_cols(acc_cols + a_cols);
@@ -465,12 +470,13 @@ int s3d_ffmlp_wide_backward(const __half *grad, const __half *inputs, const __ha
                             __half *backward_buffer, __half *grad_inputs, __half *grad_weights, cudaStream_t st) {
     if (B == 0) return 0;
     if (act == kSine) return S3D_ENOTSUP;     // needs pre-activations the API does not store (ffmlp/src/utils.h:552-556: the reference returns garbage)
-    if (!backward_buffer || !forward_buffer) return S3D_EINVAL;
+    if (num_layers > 0 && (!backward_buffer || !forward_buffer)) return S3D_EINVAL;
     BwdP p;
     size_t w_bytes = 0;
     if (int rc = make_dims(p.d, B, in_dim, out_dim, hidden, num_layers, act, 6, w_bytes)) return rc;
     p.grad = grad; p.weights = weights; p.forward_buffer = forward_buffer; p.backward_buffer = backward_buffer;
     p.grad_inputs = calc_grad_inputs ? grad_inputs : nullptr;
+    hidden = p.d.hidden;
     const uint32_t acc_cols = max(hidden, p.d.in_pad), a_cols = (max(max(p.d.out_pad, hidden), 32u) + 31) / 32 * 16;
     p.a_col = acc_cols;
     p.tmem_cols = pow2_cols(acc_cols + a_cols);
@@ -484,12 +490,13 @@ int s3d_ffmlp_wide_backward(const __half *grad, const __half *inputs, const __ha
     e = cudaPeekAtLastError();
     if (e != cudaSuccess) return (int)e;
     // weight gradients: one split-K GEMM per matrix over the buffers the data pass just wrote
-    const size_t nW = (size_t)hidden * in_dim + (size_t)hidden * hidden * (num_layers - 1) + (size_t)out_dim * hidden;
+    const size_t nW = num_layers == 0 ? (size_t)out_dim * in_dim
+                                      : (size_t)hidden * in_dim + (size_t)hidden * hidden * (num_layers - 1) + (size_t)out_dim * hidden;
     float *gw32 = nullptr;
     e = scratch_alloc((void **)&gw32, nW * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
     cudaMemsetAsync(gw32, 0, nW * sizeof(float), st);
-    const uint32_t n_hid = num_layers - 1;
+    const uint32_t n_hid = num_layers > 0 ? num_layers - 1 : 0;
     for (uint32_t m = 0; m <= num_layers; m++) {
         WgP w;
         w.B = B; w.n_tiles = p.d.n_tiles;
@@ -515,4 +522,16 @@ int s3d_ffmlp_wide_backward(const __half *grad, const __half *inputs, const __ha
     }
     cudaFreeAsync(gw32, st);
     return (int)e;
+}
+
+// A single bias-free Linear on the same kernels (num_layers = 0): y [B,out] = x [B,in] . W^T, W [out,in] row-major, all fp16,
+// fp32 accumulation.  in a multiple of 16 (<= 256), out <= 256.  Used for TensoRF's basis_mat (tensoRF/network.py:42, :155).
+S3D_API int s3d_linear_forward(const void *x, const void *w, uint32_t B, uint32_t in_dim, uint32_t out_dim, void *y, void *stream) {
+    return s3d_ffmlp_wide_forward((const __half *)x, (const __half *)w, B, in_dim, out_dim, 0, 0, kNone, kNone, nullptr, (__half *)y, as_stream(stream));
+}
+// grad_x [B,in] (NULL: not wanted), grad_w [out,in] (overwritten)
+S3D_API int s3d_linear_backward(const void *grad_y, const void *x, const void *w, uint32_t B, uint32_t in_dim, uint32_t out_dim, void *grad_x,
+                                void *grad_w, void *stream) {
+    return s3d_ffmlp_wide_backward((const __half *)grad_y, (const __half *)x, (const __half *)w, nullptr, B, in_dim, out_dim, 0, 0, kNone,
+                                   grad_x != nullptr, nullptr, (__half *)grad_x, (__half *)grad_w, as_stream(stream));
 }

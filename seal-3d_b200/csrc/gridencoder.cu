@@ -520,7 +520,11 @@ int launch_backward(const T *grad, const float *inputs, const int *offsets, T *g
         case 4 * 16 + 2: { constexpr uint32_t kD = 4, kC = 2; CALL; } break;      \
         case 4 * 16 + 4: { constexpr uint32_t kD = 4, kC = 4; CALL; } break;      \
         case 4 * 16 + 8: { constexpr uint32_t kD = 4, kC = 8; CALL; } break;      \
-        default: return S3D_EINVAL; /* reference: D in 2..5, C in {1,2,4,8}; D=5 not built here */ \
+        case 5 * 16 + 1: { constexpr uint32_t kD = 5, kC = 1; CALL; } break;      \
+        case 5 * 16 + 2: { constexpr uint32_t kD = 5, kC = 2; CALL; } break;      \
+        case 5 * 16 + 4: { constexpr uint32_t kD = 5, kC = 4; CALL; } break;      \
+        case 5 * 16 + 8: { constexpr uint32_t kD = 5, kC = 8; CALL; } break;      \
+        default: return S3D_EINVAL; /* reference: D in 2..5 (gridencoder.cu:388-396), C in {1,2,4,8} (:373-379) */ \
     }
 
 }  // namespace

@@ -533,6 +533,87 @@ k_march_write_bitmap(const float *__restrict__ rays_o, const float *__restrict__
     }
 }
 
+// pass 2, constant step (dt_gamma = 0): ONE THREAD PER SAMPLE.  The ray-per-thread replay above writes each ray's samples with
+// 4-byte stores at a stride of one ray per lane (8 store instructions per sample, a sector per lane each); here consecutive
+// threads own consecutive samples, so xyzs / dirs / deltas are written fully coalesced.  A thread finds its ray by binary
+// search over the (monotone) sample offsets, its lattice index as the (j+1)-th set bit of the ray's bitmap, and its t -- the
+// value the reference's serial chain of additions reaches after k steps -- in closed form (lattice_advance).  Rays whose
+// lattice outgrew the bitmap are left to k_march_write_overflow.
+__global__ void __launch_bounds__(256)
+k_march_write_samples(const float *__restrict__ rays_o, const float *__restrict__ rays_d, float bound, uint32_t max_steps, uint32_t N,
+                      uint32_t C, uint32_t H, uint32_t M, const float *__restrict__ nears, const float *__restrict__ noises,
+                      const int *__restrict__ rays, const int *__restrict__ counter_total, const uint32_t *__restrict__ bitmap,
+                      float *__restrict__ xyzs, float *__restrict__ dirs, float *__restrict__ deltas) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    // counter[0] after the scan = end of this call's samples; they start at the first ray's offset (the counter's value
+    // before the call, 0 when the caller zeroed it like nerf/renderer.py:267 does)
+    const uint32_t end = (uint32_t)*counter_total;
+    if (s >= M || s >= end || s < (uint32_t)__ldg(rays + 1)) return;
+    // last ray with offset <= s
+    uint32_t lo = 0, hi = N;            // invariant: off[lo] <= s, off[hi] > s or hi = N
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((uint32_t)__ldg(rays + (size_t)mid * 3 + 1) <= s) lo = mid; else hi = mid;
+    }
+    const uint32_t n = lo, off = (uint32_t)rays[(size_t)n * 3 + 1], num = (uint32_t)rays[(size_t)n * 3 + 2];
+    if (off + num > M) return;                                   // dropped ray (budget overflow): its slots stay zero
+    const uint32_t *bm = bitmap + (size_t)n * kBitmapWords;
+    if (__ldg(bm + kBitmapWords - 1) != 0u) return;               // re-walked by k_march_write_overflow
+    const uint32_t j = s - off;
+    // lattice indices of sample j (k) and of the sample before it (kp)
+    uint32_t cum = 0, k = 0, kp = 0;
+    bool have_prev = false;
+    for (uint32_t w = 0; w < kBitmapWords - 1; w++) {
+        const uint32_t bits = __ldg(bm + w), c = __popc(bits);
+        if (j > 0 && !have_prev && cum + c >= j) { kp = w * 32 + __fns(bits, 0, j - cum); have_prev = true; }   // the j-th set bit
+        if (cum + c > j) { k = w * 32 + __fns(bits, 0, j - cum + 1); break; }
+        cum += c;
+    }
+    const MarchCfg c = make_cfg(nullptr, bound, 0.0f, max_steps, C, H);
+    const Ray r = load_ray(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
+    const float d0 = step_len(c, 0.0f);
+    const float t0 = perturbed_start(c, nears[n], noises ? noises[n] : 0.0f);
+    float t = t0;
+    lattice_advance(d0, t, k);
+    float last_t = t0;
+    if (j > 0) lattice_advance(d0, last_t, kp + 1);
+    const float x = clampf(__fmaf_rn(t, r.dx, r.ox), -c.bound, c.bound);
+    const float y = clampf(__fmaf_rn(t, r.dy, r.oy), -c.bound, c.bound);
+    const float z = clampf(__fmaf_rn(t, r.dz, r.oz), -c.bound, c.bound);
+    const float tn = __fadd_rn(t, d0);
+    xyzs[(size_t)s * 3] = x; xyzs[(size_t)s * 3 + 1] = y; xyzs[(size_t)s * 3 + 2] = z;
+    dirs[(size_t)s * 3] = r.dx; dirs[(size_t)s * 3 + 1] = r.dy; dirs[(size_t)s * 3 + 2] = r.dz;
+    reinterpret_cast<float2 *>(deltas)[s] = make_float2(d0, __fsub_rn(tn, last_t));
+}
+
+// rays whose step lattice is longer than the bitmap (bound > 1 scenes): walk the voxels again, one thread per ray
+__global__ void __launch_bounds__(128)
+k_march_write_overflow(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
+                       float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                       const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
+                       const int *__restrict__ rays, const uint32_t *__restrict__ bitmap, float *__restrict__ xyzs,
+                       float *__restrict__ dirs, float *__restrict__ deltas) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N || bitmap[(size_t)n * kBitmapWords + kBitmapWords - 1] == 0u) return;
+    const uint32_t off = (uint32_t)rays[(size_t)n * 3 + 1], num = (uint32_t)rays[(size_t)n * 3 + 2];
+    if (num == 0 || off + num > M) return;
+    const MarchCfg c = make_cfg(grid, bound, dt_gamma, max_steps, C, H);
+    const Ray r = load_ray(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
+    const float far = fars[n];
+    float t = perturbed_start(c, nears[n], noises ? noises[n] : 0.0f);
+    float last_t = t, x, y, z, dt;
+    float *px = xyzs + (size_t)off * 3, *pd = dirs + (size_t)off * 3, *pl = deltas + (size_t)off * 2;
+    uint32_t step = 0;
+    while (t < far && step < num) {
+        if (march_visit(c, r, t, x, y, z, dt)) {
+            px[0] = x; px[1] = y; px[2] = z; pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            t = __fadd_rn(t, dt);
+            *reinterpret_cast<float2 *>(pl) = make_float2(dt, __fsub_rn(t, last_t));
+            last_t = t; px += 3; pd += 3; pl += 2; step++;
+        }
+    }
+}
+
 // inference marcher: n_step samples per alive ray at a fixed stride (raymarching.cu:701-805)
 __global__ void __launch_bounds__(128)
 k_march_rays(uint32_t n_alive, uint32_t n_step, const int *__restrict__ rays_alive, const float *__restrict__ rays_t,
@@ -916,8 +997,16 @@ S3D_API int s3d_march_rays_train(const float *rays_o, const float *rays_d, const
     if (e != cudaSuccess) return (int)e;
     int rc = march_count_scan(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, st, bitmap);
     if (rc == 0) {
-        k_march_write_bitmap<<<div_up(N, 128u), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears,
-                                                               fars, noises, rays, bitmap, xyzs, dirs, deltas);
+        if (dt_gamma == 0.0f && g_march_clip) {
+            // constant step: one thread per sample (coalesced stores, t in closed form)
+            k_march_write_samples<<<div_up(M, 256u), 256, 0, st>>>(rays_o, rays_d, bound, max_steps, N, C, H, M, nears, noises, rays, counter, bitmap,
+                                                                   xyzs, dirs, deltas);
+            k_march_write_overflow<<<div_up(N, 128u), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, noises, rays,
+                                                                    bitmap, xyzs, dirs, deltas);
+        } else {
+            k_march_write_bitmap<<<div_up(N, 128u), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears,
+                                                                   fars, noises, rays, bitmap, xyzs, dirs, deltas);
+        }
         rc = (int)cudaPeekAtLastError();
     }
     cudaFreeAsync(bitmap, st);

@@ -10,8 +10,10 @@ torch's ``channels_last`` format, i.e. physically ``[H,W,R]`` / ``[D,R]``, which
 ``F.grid_sample`` calls with R scattered scalar gathers per tap.  ``load_state_dict`` of a reference checkpoint copies into
 that format; ``state_dict()`` returns the reference shapes.
 
-The colour MLP (150-128-128-3) and ``basis_mat`` are ``F.linear`` GEMMs like in the reference (tensoRF/network.py:148,
-:172-178); the background model (``bg_radius > 0``) is not built.
+Under fp16 autocast (the reference's ``--fp16``) ``basis_mat`` and the colour MLP (150-128-128-3) run on the tcgen05 kernels
+of csrc/ffmlp_wide.cu (``_linear_tc``, ``_mlp_head_tc``: fp16 operands, fp32 accumulation, like the autocast ``F.linear`` GEMMs
+of tensoRF/network.py:148, :172-178 they replace); in fp32 they are ``F.linear`` like in the reference.  The background model
+(``bg_radius > 0``) is not built.
 """
 import torch
 import torch.nn as nn
@@ -69,6 +71,71 @@ class _vm_lookup(Function):
         grads = [torch.zeros_like(im) for im in imgs]      # preserve_format: channels_last like the parameter
         _lib.call("s3d_vm_backward", x, x.shape[0], aabb, *imgs, hd[1], R, 1 if reduce else 0, g, *grads)
         return (None, None, None, *grads)
+
+
+class _linear_tc(Function):
+    """bias-free nn.Linear on tensor cores (s3d_linear_*, csrc/ffmlp_wide.cu): fp16 operands, fp32 accumulation -- what the
+    reference's autocast F.linear does through cuBLAS (tensoRF/network.py:155 basis_mat)"""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        x16, w16 = x.detach().to(torch.float16).contiguous(), weight.detach().to(torch.float16).contiguous()
+        B, cin = x16.shape
+        y = torch.empty(B, w16.shape[0], dtype=torch.float16, device=x.device)
+        _lib.call("s3d_linear_forward", x16, w16, B, cin, w16.shape[0], y)
+        ctx.save_for_backward(x16, w16)
+        ctx.in_dtype = x.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x16, w16 = ctx.saved_tensors
+        B, cin = x16.shape
+        g16 = g.to(torch.float16).contiguous()
+        gx = torch.empty_like(x16) if ctx.needs_input_grad[0] else None
+        gw = torch.empty_like(w16)
+        _lib.call("s3d_linear_backward", g16, x16, w16, B, cin, w16.shape[0], gx, gw)
+        return (gx.to(ctx.in_dtype) if gx is not None else None), gw.float()
+
+
+class _mlp_head_tc(Function):
+    """The colour MLP of tensoRF/network.py:53-67, 172-178 (bias-free Linear + ReLU chain, any hidden width the FFMLP kernels
+    take) as ONE fused tensor-core launch per direction: the nn.Linear matrices are packed into the flat fp16 layout of
+    ffmlp/ffmlp.py:121-122 (input columns zero padded to a multiple of 16, output rows to 16), s3d_ffmlp_forward / _backward do
+    the rest; gradients are unpacked back onto the separate nn.Linear weights, so state dicts keep the reference's shapes."""
+
+    @staticmethod
+    def forward(ctx, h, *weights):
+        B, cin = h.shape
+        hidden, nl, cout = weights[0].shape[0], len(weights) - 1, weights[-1].shape[0]
+        in_pad, out_pad = (cin + 15) // 16 * 16, 16
+        w16 = [w.detach().to(torch.float16) for w in weights]
+        flat = torch.cat([F.pad(w16[0], (0, in_pad - cin)).reshape(-1)] + [w.reshape(-1) for w in w16[1:-1]] +
+                         [F.pad(w16[-1], (0, 0, 0, out_pad - cout)).reshape(-1)]).contiguous()
+        x16 = F.pad(h.detach().to(torch.float16), (0, in_pad - cin)).contiguous()
+        fb = torch.empty(nl, B, hidden, dtype=torch.float16, device=h.device)
+        out = torch.empty(B, out_pad, dtype=torch.float16, device=h.device)
+        _lib.call("s3d_ffmlp_forward", x16, flat, B, in_pad, out_pad, hidden, nl, 0, 6, fb, out)
+        ctx.save_for_backward(x16, flat, fb)
+        ctx.cfg = (cin, in_pad, cout, out_pad, hidden, nl, h.dtype)
+        return out[:, :cout]
+
+    @staticmethod
+    def backward(ctx, g):
+        x16, flat, fb = ctx.saved_tensors
+        cin, in_pad, cout, out_pad, hidden, nl, in_dtype = ctx.cfg
+        B = x16.shape[0]
+        g16 = F.pad(g.to(torch.float16), (0, out_pad - cout)).contiguous()
+        bb = torch.empty(nl, B, hidden, dtype=torch.float16, device=g.device)
+        gx = torch.empty(B, in_pad, dtype=torch.float16, device=g.device)
+        gw = torch.empty_like(flat)
+        _lib.call("s3d_ffmlp_backward", g16, x16, flat, fb, B, in_pad, out_pad, hidden, nl, 0, 6, 1, bb, gx, gw)
+        grads, off = [], 0
+        grads.append(gw[off:off + hidden * in_pad].view(hidden, in_pad)[:, :cin].float()); off += hidden * in_pad
+        for _ in range(nl - 1):
+            grads.append(gw[off:off + hidden * hidden].view(hidden, hidden).float()); off += hidden * hidden
+        grads.append(gw[off:off + out_pad * hidden].view(out_pad, hidden)[:cout].float())
+        return (gx[:, :cin].to(in_dtype), *grads)
 
 
 class TensoRFNetwork(NeRFRenderer):
@@ -133,6 +200,12 @@ class TensoRFNetwork(NeRFRenderer):
         return self.basis_mat(self._lookup(x, self.color_mat, self.color_vec, False, aabb))
 
     def _color_mlp(self, x, d, aabb):
+        if torch.is_autocast_enabled() and x.is_cuda and self.hidden_dim in (16, 32, 64, 128, 256) and self.num_layers >= 3:
+            # fp16 step (the reference's --fp16): basis_mat and the colour MLP on the tcgen05 kernels instead of cuBLAS GEMMs
+            feat = _linear_tc.apply(self._lookup(x, self.color_mat, self.color_vec, False, aabb), self.basis_mat.weight)
+            with torch.autocast("cuda", enabled=False):
+                h = torch.cat([self.encoder(feat.float()), self.encoder_dir(d.float())], dim=-1)
+                return torch.sigmoid(_mlp_head_tc.apply(h, *[lin.weight for lin in self.color_net]).float())
         h = torch.cat([self.encoder(self.get_color_feat(x, aabb)), self.encoder_dir(d)], dim=-1)
         for l in range(self.num_layers):
             h = self.color_net[l](h)

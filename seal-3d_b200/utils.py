@@ -19,12 +19,24 @@ def patch_indices(H, W, N, patch_size, device="cpu", generator=None):
     return inds[:, 0] * W + inds[:, 1]
 
 
+def error_map_indices(error_map, H, W, N, generator=None):
+    """nerf/utils.py:99-115: weighted sampling on the 128 x 128 error grid (multinomial without replacement per view), each pick
+    mapped to a uniformly random pixel of its coarse cell.  error_map [B, 128*128] -> (inds [B,N], inds_coarse [B,N])"""
+    B = error_map.shape[0]
+    dev = error_map.device
+    inds_coarse = torch.multinomial(error_map, N, replacement=False, generator=generator)            # [B, N] in [0, 128*128)
+    inds_x, inds_y = inds_coarse // 128, inds_coarse % 128
+    sx, sy = H / 128, W / 128
+    inds_x = (inds_x * sx + torch.rand(B, N, device=dev, generator=generator) * sx).long().clamp(max=H - 1)
+    inds_y = (inds_y * sy + torch.rand(B, N, device=dev, generator=generator) * sy).long().clamp(max=W - 1)
+    return inds_x * W + inds_y, inds_coarse
+
+
 @torch.no_grad()
 def get_rays(poses, intrinsics, H, W, N=-1, error_map=None, patch_size=1, generator=None, inds=None):
     """poses [B,4,4] cam2world (CUDA), intrinsics (fx, fy, cx, cy) -> {'rays_o', 'rays_d' [B,N,3], 'inds' [B,N] (if N > 0)}.
-    `inds` (int64 [N] or [B,N]) overrides the random draw; `generator` seeds it."""
-    if error_map is not None:
-        raise NotImplementedError("error-map sampling of get_rays is not built (nerf/utils.py:97-113)")
+    `inds` (int64 [N] or [B,N]) overrides the random draw; `generator` seeds it; `error_map` [B, 128*128] selects the
+    reference's error-weighted sampling (adds 'inds_coarse')."""
     poses = poses.contiguous().float()
     _lib.check_cuda(poses)
     dev, B = poses.device, poses.shape[0]
@@ -35,6 +47,8 @@ def get_rays(poses, intrinsics, H, W, N=-1, error_map=None, patch_size=1, genera
             N = min(N, H * W)
             if patch_size > 1:
                 inds = patch_indices(H, W, N, patch_size, dev, generator)
+            elif error_map is not None:
+                inds, results["inds_coarse"] = error_map_indices(error_map.to(dev), H, W, N, generator)
             else:
                 inds = torch.randint(0, H * W, size=[N], device=dev, generator=generator)  # may duplicate, like the reference
         inds = inds.to(dev).long().contiguous()

@@ -313,7 +313,7 @@ def test_grid_encode_forward_config1():
 
 
 @pytest.mark.parametrize("D,C,gridtype,ac,interp", [(2, 1, 0, False, 0), (2, 4, 1, True, 0), (3, 8, 0, False, 1), (3, 1, 1, False, 1),
-                                                    (4, 2, 0, False, 0), (3, 4, 0, True, 0)])
+                                                    (4, 2, 0, False, 0), (3, 4, 0, True, 0), (5, 2, 0, False, 0), (5, 1, 1, True, 0)])
 def test_grid_encode_forward_shapes(D, C, gridtype, ac, interp):
     offsets, pls = oracle.grid_offsets(input_dim=D, num_levels=6, level_dim=C, log2_hashmap_size=14, desired_resolution=256, align_corners=ac)
     rng = np.random.default_rng(D * 10 + C)
@@ -1019,7 +1019,16 @@ def test_get_rays():
     pt = get_rays(to(g["poses"]), intr, 800, 800, 4096, patch_size=8, generator=gen)
     ids = npy(pt["inds"][0]).reshape(-1, 8, 8)
     assert ids.shape[0] == 64 and np.all(np.diff(ids, axis=2) == 1) and np.all(np.diff(ids, axis=1) == 800)      # 8 x 8 pixel blocks
-    with pytest.raises(NotImplementedError):
-        get_rays(to(g["poses"]), intr, 800, 800, 64, error_map=torch.ones(3, 128 * 128))
+    # error-map sampling (nerf/utils.py:99-115): picks follow the map, each lands inside its coarse cell, no cell twice per view
+    em = torch.zeros(3, 128 * 128, device=dev())
+    hot = torch.tensor([5 * 128 + 7, 100 * 128 + 64, 127 * 128 + 127], device=dev())
+    em[:, hot] = 1.0
+    em[1] = 1.0
+    e = get_rays(to(g["poses"]), intr, 800, 800, 3, error_map=em, generator=gen)
+    assert e["rays_d"].shape == (3, 3, 3) and e["inds_coarse"].shape == (3, 3)
+    assert set(npy(e["inds_coarse"][0]).tolist()) == set(npy(hot).tolist()) and len(set(npy(e["inds_coarse"][1]).tolist())) == 3
+    px, py = npy(e["inds"]) // 800, npy(e["inds"]) % 800
+    cx_, cy_ = npy(e["inds_coarse"]) // 128, npy(e["inds_coarse"]) % 128
+    assert np.all(px >= np.floor(cx_ * 6.25)) and np.all(px < np.ceil((cx_ + 1) * 6.25)) and np.all(py >= np.floor(cy_ * 6.25)) and np.all(py < np.ceil((cy_ + 1) * 6.25))
     with pytest.raises(_lib.S3DError):
         get_rays(torch.from_numpy(g["poses"]), intr, 800, 800, 64)          # CPU tensor: the reference would fail in the kernel launch too

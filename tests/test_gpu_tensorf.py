@@ -191,6 +191,39 @@ def test_full_size_properties():
         assert abs(got_m - want) < 1e-5 * scale and abs(got_v - want) < 1e-5 * scale, (which, want, got_m, got_v, scale)
 
 
+def test_colour_head_on_tensor_cores_matches_the_linear_path():
+    """under fp16 autocast basis_mat and the 150-128-128-3 colour MLP run on the tcgen05 kernels (s3d_linear_*, wide FFMLP:
+    _linear_tc / _mlp_head_tc) instead of autocast F.linear: same rgb and the same gradients for every parameter, to the
+    fp16 rounding both paths share (the reference's own fp16 step is the F.linear path, tensoRF/network.py:148-178)"""
+    from seal3d_b200 import tensorf as tf
+    torch.manual_seed(1)
+    net = golden_net(res=[40, 36, 44])
+    x = (torch.rand(5000, 3, device=dev()) * 1.9 - 0.95)
+    d = torch.nn.functional.normalize(torch.randn(5000, 3, device=dev()), dim=-1)
+    g = torch.randn(5000, 3, device=dev()) * 64.0          # a loss-scaled upstream gradient
+    outs = []
+    for tc in (True, False):
+        net.zero_grad(set_to_none=True)
+        orig = tf.TensoRFNetwork.num_layers if hasattr(tf.TensoRFNetwork, "num_layers") else None
+        if not tc:
+            net.hidden_dim_saved, net.hidden_dim = net.hidden_dim, -1          # disables the tensor-core branch of _color_mlp
+        try:
+            with torch.autocast("cuda", dtype=torch.float16):
+                sigma, rgb = net(x, d)
+        finally:
+            if not tc:
+                net.hidden_dim = net.hidden_dim_saved
+        rgb.float().backward(g)
+        grads = {n: p.grad.detach().clone().float() for n, p in net.named_parameters() if p.grad is not None}
+        outs.append((rgb.float().detach(), grads))
+    (rgb_tc, g_tc), (rgb_ref, g_ref) = outs
+    np.testing.assert_allclose(npy(rgb_tc), npy(rgb_ref), rtol=0, atol=3e-3)
+    assert set(g_tc) == set(g_ref) and any(k.startswith("color_net") for k in g_tc) and "basis_mat.weight" in g_tc
+    for k in g_ref:
+        a, b = npy(g_tc[k]), npy(g_ref[k])
+        assert np.abs(a - b).max() <= 2e-2 * np.abs(b).max() + 1e-6, (k, np.abs(a - b).max(), np.abs(b).max())
+
+
 def test_distillation_with_tensorf_teacher_and_student():
     """config 5 in miniature: TensoRF teacher (proxy-mapped, colour edit) -> TensoRF student on shared samples through the same
     trainer as the NGP backbone; the loss falls, the arena keeps the channels_last layout, two learning rates are applied"""

@@ -312,7 +312,7 @@ def test_c_abi_argument_errors_are_reported_before_any_launch():
     dims = (C.c_int * 9)(*([4] * 9))
     # grid encoder: unknown dtype, unsupported (D, C), empty batch
     assert lib.s3d_grid_encode_forward(n, n, n, n, 16, 3, 2, 16, 0.5, 16, n, 0, 0, 0, 7, n) == EINVAL
-    assert lib.s3d_grid_encode_forward(n, n, n, n, 16, 5, 2, 16, 0.5, 16, n, 0, 0, 0, 0, n) == EINVAL
+    assert lib.s3d_grid_encode_forward(n, n, n, n, 16, 6, 2, 16, 0.5, 16, n, 0, 0, 0, 0, n) == EINVAL
     assert lib.s3d_grid_encode_forward(n, n, n, n, 0, 3, 2, 16, 0.5, 16, n, 0, 0, 0, 0, n) == 0
     assert lib.s3d_grad_total_variation(n, n, n, n, 1.0, 16, 3, 2, 16, 0.5, 16, 0, 0, 1, n) == ENOTSUP      # fp16 TV is not a reference path
     # FFMLP: hidden width in {16, 32, 64, 128, 256} (ffmlp.cu:653-658 throws otherwise), input width a multiple of 16, output <= 256
