@@ -190,7 +190,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.02)
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
@@ -431,11 +431,17 @@ def timed_legs(tr, resident, host, args, rank, world, dev, pipelined, profile_ho
         for src in (resident, host):
             for i in range(3):
                 tr.distill_step(*src[i % pool], perturb=True, prefetch=src[(i + 1) % pool] if i < 2 else None)
+    if world > 1:   # NCCL picks / tunes its all-reduce channels over the first collectives of this size: keep that out of the timed legs too
+        for i in range(4):
+            tr.distill_step(*resident[i % pool], perturb=True)
     samples_per_step = float(tr.student.step_counter[:, 0].float().max().item())
 
     # -- leg 1: resident inputs ---------------------------------------------------------------
     barrier()
-    clocks = ClockSampler(dev.index) if dev.type == "cuda" else None
+    # rank 0 samples its GPU's clocks during the timed region (the line reports that GPU).  The other ranks do not: eight
+    # processes polling NVML at once contend on the driver's global lock and slow every rank's kernel launches -- measured on
+    # 8 GPUs as 7.78 ms/step in this leg against 7.18 in the next one, which has no sampler
+    clocks = ClockSampler(dev.index) if (dev.type == "cuda" and rank == 0) else None
     from seal3d_b200 import _lib
     launches0 = _lib.LAUNCHES
     tm = _Timer(dev)

@@ -218,7 +218,7 @@ def test_bench_control_flow_issues_matched_collectives_gloo():
     all-reduces: both ranks must take the same number of steps and finish; round 1's rank-0-only breakdown steps hung here"""
     out = _run_bench_flow(False)
     assert [o[1] for o in out] == ["ok", "ok"], out
-    assert out[0][2] == out[1][2] == 3 + 6 + 3 + 3 + 3, out        # warm-up, pipeline priming, leg 1, leg 2, breakdown
+    assert out[0][2] == out[1][2] == 3 + 6 + 4 + 3 + 3 + 3, out    # warm-up, pipeline priming, collective warm-up, leg 1, leg 2, breakdown
     assert all(o[3] for o in out) and out[0][5] == 2.0              # the all-reduce summed both ranks
     assert out[0][4]["s3d_stub"]["calls_per_step"] == 1.0
 
