@@ -238,6 +238,13 @@ int s3d_ngp_pair_forward(const float *xyz, const float *xyz_teacher, const uint8
 int s3d_linear_forward(const void *x, const void *w, uint32_t B, uint32_t in_dim, uint32_t out_dim, void *y, void *stream);
 int s3d_linear_backward(const void *grad_y, const void *x, const void *w, uint32_t B, uint32_t in_dim, uint32_t out_dim, void *grad_x,
                         void *grad_w, void *stream);
+/* TensoRF colour head glue (tensoRF/network.py:170-172): h = cat([freq(color_feat), freq(dirs)]) zero padded to K columns, fp16,
+ * in one launch (feat fp16 [B, ld_feat] with Fd valid columns -- the zero-padded output rows of s3d_linear_forward --, dirs fp32
+ * [B,3], both encoders `frequency` with multires = deg); backward: grad_feat fp16 [B, ld_feat] from grad_h and the stored h. */
+int s3d_tensorf_head_encode(const void *feat, uint32_t Fd, uint32_t ld_feat, const float *dirs, uint32_t B, uint32_t deg, uint32_t K, void *h,
+                            void *stream);
+int s3d_tensorf_head_encode_backward(const void *grad_h, const void *h, uint32_t Fd, uint32_t ld_feat, uint32_t B, uint32_t deg, uint32_t K,
+                                     void *grad_feat, void *stream);
 /* development / test switch of the train marcher: 1 (default) walks a ray only inside the widened bounding box of the occupied
  * cells (single cascade, dt_gamma = 0; the step lattice before the box is jumped in closed form), 0 walks it from its near
  * point like the reference.  The samples are identical either way (tests/test_gpu_parity.py compares them at full size). */

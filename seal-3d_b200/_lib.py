@@ -76,6 +76,8 @@ _SIGS = {
     "s3d_ngp_adam_tables": [P, P, P, P, P, P, U32, U64, F32, F32, F32, F32, U32, F32, P],
     "s3d_vm_forward": [P, U32, P, P, P, P, P, P, P, P, U32, I32, P],
     "s3d_vm_backward": [P, U32, P, P, P, P, P, P, P, P, U32, I32, P, P, P, P, P, P, P],
+    "s3d_tensorf_head_encode": [P, U32, U32, P, U32, U32, U32, P],
+    "s3d_tensorf_head_encode_backward": [P, P, U32, U32, U32, U32, U32, P],
     "s3d_vm_resize": [P, U32, U32, P, U32, U32, U32],
 }
 _NO_STREAM = {"s3d_allocate_splitk": [SZ], "s3d_free_splitk": [], "s3d_march_set_clip": [I32]}

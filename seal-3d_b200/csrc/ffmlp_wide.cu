@@ -100,28 +100,40 @@ __device__ __forceinline__ void sync_all() {
     fence_after_sync();
 }
 
-// thread `row` stores `n_half` fp16 values of a global row (zero padded to a multiple of 32) into TMEM as an A operand
-__device__ __forceinline__ void row_to_tmem(uint32_t t_a, const __half *__restrict__ g_row, uint32_t n_half, bool in_range) {
-    for (uint32_t c0 = 0; c0 < n_half; c0 += 32) {
-        uint32_t pk[16];
+// thread `row` stores `n_half` fp16 values of a global row (zero padded to a multiple of 32) into TMEM as an A operand.
+// The loads of four 32-value chunks (16 x 16 bytes) are issued before the first tcgen05.st: one exposed global-memory
+// latency per 128 values instead of one per chunk (ncu: the kernel's warps sat on the long scoreboard at 12 % occupancy).
+// `half_sel` = 0 / 1: the thread's warpgroup takes the 32-value chunks with an even / odd chunk index
+__device__ __forceinline__ void row_to_tmem(uint32_t t_a, const __half *__restrict__ g_row, uint32_t n_half, bool in_range, uint32_t half_sel) {
+    const bool vec = (n_half & 7u) == 0;
+    // this thread's chunks: 32 * (2 i + half_sel), i = 0, 1, ...; staged four at a time
+    for (uint32_t i0 = 0; 32 * (2 * i0 + half_sel) < n_half; i0 += 4) {
+        uint4 v[16];
 #pragma unroll
-        for (uint32_t q = 0; q < 4; q++) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            const uint32_t col = c0 + q * 8;
+        for (uint32_t q = 0; q < 16; q++) {
+            v[q] = make_uint4(0, 0, 0, 0);
+            const uint32_t col = 32 * (2 * (i0 + q / 4) + half_sel) + (q & 3u) * 8;
             if (in_range && col < n_half) {
-                if (col + 8 <= n_half && (n_half & 7u) == 0) v = __ldg(reinterpret_cast<const uint4 *>(g_row + col));
+                if (vec && col + 8 <= n_half) v[q] = __ldg(reinterpret_cast<const uint4 *>(g_row + col));
                 else {
                     __half h[8];
                     for (uint32_t j = 0; j < 8; j++) h[j] = (col + j < n_half) ? g_row[col + j] : __float2half_rn(0.0f);
-                    v = *reinterpret_cast<const uint4 *>(h);
+                    v[q] = *reinterpret_cast<const uint4 *>(h);
                 }
             }
-            pk[4 * q] = v.x; pk[4 * q + 1] = v.y; pk[4 * q + 2] = v.z; pk[4 * q + 3] = v.w;
         }
-        tmem_st16(t_a + c0 / 2, pk);
+#pragma unroll
+        for (uint32_t ch = 0; ch < 4; ch++) {
+            const uint32_t c0 = 32 * (2 * (i0 + ch) + half_sel);
+            if (c0 < n_half) {
+                uint32_t pk[16];
+#pragma unroll
+                for (uint32_t q = 0; q < 4; q++) { pk[4 * q] = v[ch * 4 + q].x; pk[4 * q + 1] = v[ch * 4 + q].y; pk[4 * q + 2] = v[ch * 4 + q].z; pk[4 * q + 3] = v[ch * 4 + q].w; }
+                tmem_st16(t_a + c0 / 2, pk);
+            }
+        }
     }
 }
-
 struct FwdP {
     const __half *inputs, *weights;
     __half *forward_buffer, *outputs;
@@ -129,7 +141,10 @@ struct FwdP {
     uint32_t tmem_cols, a_col;    // accumulator at column 0, A operand at a_col
 };
 
-__global__ void __launch_bounds__(128)
+// 256 threads: thread (r, hf) owns batch row r = tid & 127 of the tile and the 32-value chunks with chunk index % 2 == hf of
+// every row it touches (input staging, accumulator read-back, activation store) -- two warpgroups per chain halve the serial
+// epilogue of a layer and double the loads / stores in flight (TMEM allows only two 208-column chains per SM at hidden 128)
+__global__ void __launch_bounds__(256)
 k_wide_forward(const FwdP p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -150,13 +165,14 @@ k_wide_forward(const FwdP p) {
         fence_async_smem();
     }
     sync_all();
-    const uint32_t tmem = s_tmem, t_row = tmem + ((warp * 32u) << 16);
+    const uint32_t r = tid & 127u, hf = tid >> 7;
+    const uint32_t tmem = s_tmem, t_row = tmem + (((warp & 3u) * 32u) << 16);
     const uint32_t t_acc = t_row, t_a = t_row + p.a_col;
     uint32_t parity = 0;
     for (uint32_t tile = blockIdx.x; tile < d.n_tiles; tile += gridDim.x) {
-        const uint32_t row = tile * kRows + tid;
+        const uint32_t row = tile * kRows + r;
         const bool in_range = row < d.B;
-        row_to_tmem(t_a, p.inputs + (size_t)row * d.in_dim, d.in_pad, in_range && true);
+        row_to_tmem(t_a, p.inputs + (size_t)row * d.in_dim, d.in_pad, in_range, hf);
         tmem_st_wait();
         for (uint32_t m = 0; m < n_mat; m++) {
             uint32_t r, c, pr; size_t g;
@@ -183,7 +199,7 @@ k_wide_forward(const FwdP p) {
             fence_after_sync();
             if (!last) {
                 __half *fb = (p.forward_buffer && in_range) ? p.forward_buffer + ((size_t)m * d.B + row) * d.hidden : nullptr;
-                for (uint32_t c0 = 0; c0 < d.hidden; c0 += 32) {
+                for (uint32_t c0 = hf * 32; c0 < d.hidden; c0 += 64) {
                     float v[32];
                     tmem_ld32(t_acc + c0, v);
                     uint32_t pk[16];
@@ -192,12 +208,13 @@ k_wide_forward(const FwdP p) {
                     tmem_st16(t_a + c0 / 2, pk);
                     if (fb) {
 #pragma unroll
-                        for (uint32_t q = 0; q < 4; q++) *reinterpret_cast<uint4 *>(fb + c0 + q * 8) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                        for (uint32_t q = 0; q < 4; q++)
+                            if (c0 + q * 8 < d.hidden) *reinterpret_cast<uint4 *>(fb + c0 + q * 8) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                     }
                 }
                 tmem_st_wait();
             } else {
-                for (uint32_t c0 = 0; c0 < d.out_pad; c0 += 16) {
+                for (uint32_t c0 = hf * 16; c0 < d.out_pad; c0 += 32) {
                     float v[16];
                     tmem_ld16(t_acc + c0, v);
                     if (in_range) {
@@ -231,7 +248,7 @@ struct BwdP {
 // data gradients, top down.  step s = 0: through W_out (K = out_pad, N = hidden); s = 1 .. n_hid: through hidden matrix
 // num_layers - s; s = n_hid + 1: through W_0 (N = in_dim), only for grad_inputs.  backward_buffer[s] = dL/d(pre-activation of
 // hidden activation num_layers-1-s) as in the narrow kernel (ffmlp.cu).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_wide_backward(const BwdP p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -252,14 +269,15 @@ k_wide_backward(const BwdP p) {
         fence_async_smem();
     }
     sync_all();
-    const uint32_t tmem = s_tmem, t_row = tmem + ((warp * 32u) << 16);
+    const uint32_t r = tid & 127u, hf = tid >> 7;
+    const uint32_t tmem = s_tmem, t_row = tmem + (((warp & 3u) * 32u) << 16);
     const uint32_t t_acc = t_row, t_a = t_row + p.a_col;
     uint32_t parity = 0;
     const uint32_t n_steps = d.num_layers + (p.grad_inputs ? 1u : 0u);
     for (uint32_t tile = blockIdx.x; tile < d.n_tiles; tile += gridDim.x) {
-        const uint32_t row = tile * kRows + tid;
+        const uint32_t row = tile * kRows + r;
         const bool in_range = row < d.B;
-        row_to_tmem(t_a, p.grad + (size_t)row * d.out_dim, d.out_dim, in_range);
+        row_to_tmem(t_a, p.grad + (size_t)row * d.out_dim, d.out_dim, in_range, hf);
         tmem_st_wait();
         for (uint32_t s = 0; s < n_steps; s++) {
             const uint32_t m = d.num_layers - s;           // matrix the gradient flows through
@@ -289,29 +307,41 @@ k_wide_backward(const BwdP p) {
                 // dA = D (.) act'(h), h = hidden activation m-1 (forward_buffer[m-1])
                 const __half *h = p.forward_buffer + ((size_t)(m - 1) * d.B + row) * d.hidden;
                 __half *bb = (p.backward_buffer && in_range) ? p.backward_buffer + ((size_t)s * d.B + row) * d.hidden : nullptr;
-                for (uint32_t c0 = 0; c0 < d.hidden; c0 += 32) {
-                    float v[32];
-                    tmem_ld32(t_acc + c0, v);
-                    uint32_t pk[16];
+                for (uint32_t i0 = 0; 32 * (2 * i0 + hf) < d.hidden; i0 += 4) {
+                    uint4 hu[16];        // this thread's chunks of the activation row, four at a time: all loads in flight before the accumulator is read
 #pragma unroll
-                    for (uint32_t q = 0; q < 4; q++) {
-                        float hv[8];
-                        uint4 hu = make_uint4(0, 0, 0, 0);
-                        if (in_range) hu = __ldg(reinterpret_cast<const uint4 *>(h + c0 + q * 8));
-                        unpack8(hu, hv);
-#pragma unroll
-                        for (int i = 0; i < 4; i++)
-                            pk[4 * q + i] = pack_half2(v[q * 8 + 2 * i] * wact_bwd(d.act, hv[2 * i]), v[q * 8 + 2 * i + 1] * wact_bwd(d.act, hv[2 * i + 1]));
+                    for (uint32_t q = 0; q < 16; q++) {
+                        hu[q] = make_uint4(0, 0, 0, 0);
+                        const uint32_t col = 32 * (2 * (i0 + q / 4) + hf) + (q & 3u) * 8;
+                        if (in_range && col < d.hidden) hu[q] = __ldg(reinterpret_cast<const uint4 *>(h + col));
                     }
-                    tmem_st16(t_a + c0 / 2, pk);
-                    if (bb) {
 #pragma unroll
-                        for (uint32_t q = 0; q < 4; q++) *reinterpret_cast<uint4 *>(bb + c0 + q * 8) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    for (uint32_t ch = 0; ch < 4; ch++) {
+                        const uint32_t c0 = 32 * (2 * (i0 + ch) + hf);
+                        if (c0 < d.hidden) {
+                            float v[32];
+                            tmem_ld32(t_acc + c0, v);
+                            uint32_t pk[16];
+#pragma unroll
+                            for (uint32_t q = 0; q < 4; q++) {
+                                float hv[8];
+                                unpack8(hu[ch * 4 + q], hv);
+#pragma unroll
+                                for (int i = 0; i < 4; i++)
+                                    pk[4 * q + i] = pack_half2(v[q * 8 + 2 * i] * wact_bwd(d.act, hv[2 * i]), v[q * 8 + 2 * i + 1] * wact_bwd(d.act, hv[2 * i + 1]));
+                            }
+                            tmem_st16(t_a + c0 / 2, pk);
+                            if (bb) {
+#pragma unroll
+                                for (uint32_t q = 0; q < 4; q++)
+                                    if (c0 + q * 8 < d.hidden) *reinterpret_cast<uint4 *>(bb + c0 + q * 8) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                            }
+                        }
                     }
                 }
                 tmem_st_wait();
             } else {
-                for (uint32_t c0 = 0; c0 < d.in_pad; c0 += 16) {
+                for (uint32_t c0 = hf * 16; c0 < d.in_pad; c0 += 32) {
                     float v[16];
                     tmem_ld16(t_acc + c0, v);
                     if (in_range && c0 < d.in_dim) {
@@ -341,23 +371,38 @@ struct WgP {
 __device__ void load_rows_sw128(uint8_t *smem, const __half *__restrict__ g, uint32_t ld, uint32_t n_rows, uint32_t n_cols, uint32_t row0,
                                 uint32_t col0, uint32_t blocks) {
     const bool vec = (ld & 7u) == 0;
-    for (uint32_t i = threadIdx.x; i < blocks * kRows * 8; i += blockDim.x) {
-        const uint32_t blk = i / (kRows * 8), rem = i - blk * kRows * 8, r = rem >> 3, c16 = rem & 7;
-        const uint32_t row = row0 + r, col = col0 + blk * 64 + c16 * 8;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (row < n_rows && col < n_cols) {
-            if (vec && col + 8 <= n_cols) v = __ldg(reinterpret_cast<const uint4 *>(g + (size_t)row * ld + col));
-            else {
-                __half h[8];
-                for (uint32_t j = 0; j < 8; j++) h[j] = (col + j < n_cols) ? g[(size_t)row * ld + col + j] : __float2half_rn(0.0f);
-                v = *reinterpret_cast<const uint4 *>(h);
+    const uint32_t total = blocks * kRows * 8;
+    for (uint32_t i0 = threadIdx.x; i0 < total; i0 += blockDim.x * 8) {
+        uint4 v[8];
+        uint32_t dst[8];
+#pragma unroll
+        for (uint32_t u = 0; u < 8; u++) {     // eight 16-byte loads in flight per thread before the first shared-memory store
+            const uint32_t i = i0 + u * blockDim.x;
+            v[u] = make_uint4(0, 0, 0, 0);
+            dst[u] = 0xffffffffu;
+            if (i < total) {
+                const uint32_t blk = i / (kRows * 8), rem = i - blk * kRows * 8, r = rem >> 3, c16 = rem & 7;
+                const uint32_t row = row0 + r, col = col0 + blk * 64 + c16 * 8;
+                dst[u] = blk * (kRows * 128) + sw128_off(r, c16);
+                if (row < n_rows && col < n_cols) {
+                    if (vec && col + 8 <= n_cols) v[u] = __ldg(reinterpret_cast<const uint4 *>(g + (size_t)row * ld + col));
+                    else {
+                        __half h[8];
+                        for (uint32_t j = 0; j < 8; j++) h[j] = (col + j < n_cols) ? g[(size_t)row * ld + col + j] : __float2half_rn(0.0f);
+                        v[u] = *reinterpret_cast<const uint4 *>(h);
+                    }
+                }
             }
         }
-        *reinterpret_cast<uint4 *>(smem + blk * (kRows * 128) + sw128_off(r, c16)) = v;
+#pragma unroll
+        for (uint32_t u = 0; u < 8; u++)
+            if (dst[u] != 0xffffffffu) *reinterpret_cast<uint4 *>(smem + dst[u]) = v[u];
     }
 }
 
-__global__ void __launch_bounds__(128)
+// 256 threads: twice the loads in flight while a tile pair is staged (the kernel is bound by the latency of its global loads,
+// ncu: long scoreboard 23 cycles per issue at 12 % occupancy); warps 0-3 / 4-7 flush the low / high half of the accumulator columns
+__global__ void __launch_bounds__(256)
 k_wide_wgrad(const WgP p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -368,7 +413,7 @@ k_wide_wgrad(const WgP p) {
     if (warp == 0) tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
     if (tid == 0) mbar_init(mbar, 1);
     sync_all();
-    const uint32_t tmem = s_tmem, t_row = tmem + ((warp * 32u) << 16);
+    const uint32_t tmem = s_tmem, t_row = tmem + (((warp & 3u) * 32u) << 16);
     const uint32_t r0 = blockIdx.x * 128, c_blocks = (p.C + 63) / 64, Npad = c_blocks * 64;
     uint8_t *tA = smem, *tH = smem + 2 * kRows * 128;
     uint32_t parity = 0;
@@ -391,8 +436,9 @@ k_wide_wgrad(const WgP p) {
         fence_after_sync();
     }
     if (!first) {
-        const uint32_t rr = r0 + tid;     // M = 128: accumulator row i lives in lane i
-        for (uint32_t c0 = 0; c0 < Npad; c0 += 32) {
+        const uint32_t rr = r0 + (tid & 127u);     // M = 128: accumulator row i lives in lane i
+        const uint32_t half = tid >> 7;            // column half handled by this warpgroup
+        for (uint32_t c0 = half * 32; c0 < Npad; c0 += 64) {
             float v[32];
             tmem_ld32(t_row + c0, v);
             if (rr < p.R) {
@@ -461,7 +507,7 @@ int s3d_ffmlp_wide_forward(const __half *inputs, const __half *weights, uint32_t
     cudaError_t e = cudaFuncSetAttribute(k_wide_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const uint32_t per_sm = max(1u, min(512u / p.tmem_cols, (uint32_t)((220 * 1024) / smem)));
-    k_wide_forward<<<min(p.d.n_tiles, (uint32_t)sm_count_w() * per_sm), 128, smem, st>>>(p);
+    k_wide_forward<<<min(p.d.n_tiles, (uint32_t)sm_count_w() * per_sm), 256, smem, st>>>(p);
     return (int)cudaPeekAtLastError();
 }
 
@@ -486,7 +532,7 @@ int s3d_ffmlp_wide_backward(const __half *grad, const __half *inputs, const __ha
     if (e != cudaSuccess) return (int)e;
     const uint32_t per_sm = max(1u, min(512u / p.tmem_cols, (uint32_t)((220 * 1024) / smem)));
     const int sms = sm_count_w();
-    k_wide_backward<<<min(p.d.n_tiles, (uint32_t)sms * per_sm), 128, smem, st>>>(p);
+    k_wide_backward<<<min(p.d.n_tiles, (uint32_t)sms * per_sm), 256, smem, st>>>(p);
     e = cudaPeekAtLastError();
     if (e != cudaSuccess) return (int)e;
     // weight gradients: one split-K GEMM per matrix over the buffers the data pass just wrote
@@ -514,7 +560,7 @@ int s3d_ffmlp_wide_backward(const __half *grad, const __half *inputs, const __ha
         if (e != cudaSuccess) break;
         const uint32_t m_blocks = div_up(w.R, 128u);
         const uint32_t slices = max(1u, min(w.n_tiles, (uint32_t)(2 * sms) / m_blocks));
-        k_wide_wgrad<<<dim3(m_blocks, slices), 128, smem_w, st>>>(w);
+        k_wide_wgrad<<<dim3(m_blocks, slices), 256, smem_w, st>>>(w);
     }
     if (e == cudaSuccess) {
         k_wide_f32_to_f16<<<(unsigned)div_up(nW, (size_t)256), 256, 0, st>>>(gw32, grad_weights, nW);

@@ -232,3 +232,81 @@ S3D_API int s3d_vm_resize(const float *src, uint32_t H, uint32_t W, float *dst, 
     k_vm_resize<<<(unsigned)div_up(n, (uint64_t)256), 256, 0, as_stream(stream)>>>(src, (int)H, (int)W, dst, (int)H2, (int)W2, R);
     S3D_RETURN_LAST();
 }
+
+// ---- TensoRF colour head: frequency encodings + concatenation + padding in one launch ------------------------------------
+// tensoRF/network.py:170-172:  h = cat([encoder(color_feat), encoder_dir(d)])  with both encoders `frequency`, multires = deg
+// (freqencoder layout: [x | sin(2^0 x) | cos(2^0 x) | sin(2^1 x) | cos(2^1 x) ...], freqencoder.cu:30-60).  feat arrives fp16
+// from the tensor-core basis_mat, h leaves fp16, zero padded to K columns, ready to be the A operand of the colour MLP:
+// replaces two encoder launches, a concatenation, a pad and two casts.
+namespace {
+// One WARP per row: lane d < Fd encodes feature d, lanes Fd .. Fd+2 the direction components, each writing its 1 + 2 deg values
+// into a shared-memory image of the row; the warp then stores the row with coalesced 4-byte stores.  (One thread per output
+// column pays two integer divisions and a sine per value: 1.2 ms for 1.36 M rows; this form 0.1 ms.)  Needs Fd + 3 <= 32.
+constexpr uint32_t kHeadMaxK = 512;
+__global__ void __launch_bounds__(256)
+k_head_encode(const __half *__restrict__ feat, uint32_t Fd, uint32_t ld_feat, const float *__restrict__ dirs, uint32_t B, uint32_t deg, uint32_t K,
+              __half *__restrict__ h) {
+    __shared__ __align__(16) __half s_row[8][kHeadMaxK];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t C1 = Fd * (1 + 2 * deg), C2 = 3 * (1 + 2 * deg);
+    __half *row = s_row[wib];
+    for (uint32_t c = C1 + C2 + lane; c < K; c += 32) row[c] = __float2half_rn(0.0f);     // the zero padding, written once
+    __syncwarp();
+    for (uint32_t b = blockIdx.x * 8 + wib; b < B; b += gridDim.x * 8) {
+        if (lane < Fd + 3) {
+            const bool is_dir = lane >= Fd;
+            const uint32_t D = is_dir ? 3u : Fd, d = is_dir ? lane - Fd : lane;
+            const float x = is_dir ? __ldg(dirs + (size_t)b * 3 + d) : __half2float(feat[(size_t)b * ld_feat + d]);
+            __half *o = row + (is_dir ? C1 : 0u) + d;
+            o[0] = __float2half_rn(x);
+            for (uint32_t f = 0; f < deg; f++) {
+                const float xs = __fmul_rn(x, __int_as_float((127 + f) << 23));
+                o[(1 + 2 * f) * D] = __float2half_rn(__sinf(xs));
+                o[(2 + 2 * f) * D] = __float2half_rn(__sinf(__fadd_rn(xs, 1.5707963267948966f)));
+            }
+        }
+        __syncwarp();
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(row);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(h + (size_t)b * K);
+        for (uint32_t c = lane; c < K / 2; c += 32) dst[c] = src[c];
+        __syncwarp();
+    }
+}
+// d feat = g_x + sum_f 2^f (g_sin cos - g_cos sin), sin / cos taken from the stored encoding (freqencoder.cu:63-94)
+__global__ void __launch_bounds__(256)
+k_head_encode_bwd(const __half *__restrict__ gh, const __half *__restrict__ h, uint32_t Fd, uint32_t ld_feat, uint32_t B, uint32_t deg, uint32_t K,
+                  __half *__restrict__ gfeat) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)B * ld_feat) return;
+    const uint32_t b = (uint32_t)(t / ld_feat), d = (uint32_t)(t - (uint64_t)b * ld_feat);
+    float r = 0.0f;
+    if (d < Fd) {
+        const __half *g = gh + (size_t)b * K, *o = h + (size_t)b * K;
+        r = __half2float(g[d]);
+        for (uint32_t f = 0; f < deg; f++) {
+            const uint32_t is = (1 + 2 * f) * Fd + d, ic = (2 + 2 * f) * Fd + d;
+            r += __int_as_float((127 + f) << 23) * (__half2float(g[is]) * __half2float(o[ic]) - __half2float(g[ic]) * __half2float(o[is]));
+        }
+    }
+    gfeat[t] = __float2half_rn(r);           // columns Fd .. ld_feat-1 (padding of the feature rows) get zero
+}
+}  // namespace
+
+// feat fp16 [B, ld_feat] (Fd valid columns), dirs fp32 [B,3] -> h fp16 [B,K] = [freq(feat) | freq(dirs) | 0 ...],  K even, >= (Fd + 3)(1 + 2 deg)
+S3D_API int s3d_tensorf_head_encode(const void *feat, uint32_t Fd, uint32_t ld_feat, const float *dirs, uint32_t B, uint32_t deg, uint32_t K, void *h,
+                                    void *stream) {
+    if (B == 0) return 0;
+    if (K < (Fd + 3) * (1 + 2 * deg) || (K & 1u) || deg > 16 || ld_feat < Fd) return S3D_EINVAL;
+    if (Fd + 3 > 32 || K > kHeadMaxK) return S3D_ENOTSUP;
+    k_head_encode<<<min(div_up(B, 8u), 148u * 16u), 256, 0, as_stream(stream)>>>((const __half *)feat, Fd, ld_feat, dirs, B, deg, K, (__half *)h);
+    S3D_RETURN_LAST();
+}
+// grad_feat fp16 [B, ld_feat] (padding columns zeroed)
+S3D_API int s3d_tensorf_head_encode_backward(const void *grad_h, const void *h, uint32_t Fd, uint32_t ld_feat, uint32_t B, uint32_t deg, uint32_t K,
+                                             void *grad_feat, void *stream) {
+    if (B == 0) return 0;
+    if (K < (Fd + 3) * (1 + 2 * deg) || deg > 16 || ld_feat < Fd) return S3D_EINVAL;
+    k_head_encode_bwd<<<(unsigned)div_up((uint64_t)B * ld_feat, (uint64_t)256), 256, 0, as_stream(stream)>>>((const __half *)grad_h, (const __half *)h, Fd, ld_feat, B, deg, K,
+                                                                                                            (__half *)grad_feat);
+    S3D_RETURN_LAST();
+}

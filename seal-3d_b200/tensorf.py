@@ -79,23 +79,55 @@ class _linear_tc(Function):
 
     @staticmethod
     def forward(ctx, x, weight):
-        x16, w16 = x.detach().to(torch.float16).contiguous(), weight.detach().to(torch.float16).contiguous()
+        """-> y fp16 [B, out_pad]: out_pad = out rounded up to 16 (zero weight rows), so rows are 32-byte aligned vector stores;
+        the caller uses the first `out` columns"""
+        cout = weight.shape[0]
+        out_pad = (cout + 15) // 16 * 16
+        x16 = x.detach().to(torch.float16).contiguous()
+        w16 = F.pad(weight.detach().to(torch.float16), (0, 0, 0, out_pad - cout)).contiguous()
         B, cin = x16.shape
-        y = torch.empty(B, w16.shape[0], dtype=torch.float16, device=x.device)
-        _lib.call("s3d_linear_forward", x16, w16, B, cin, w16.shape[0], y)
+        y = torch.empty(B, out_pad, dtype=torch.float16, device=x.device)
+        _lib.call("s3d_linear_forward", x16, w16, B, cin, out_pad, y)
         ctx.save_for_backward(x16, w16)
-        ctx.in_dtype = x.dtype
+        ctx.cfg = (x.dtype, cout)
         return y
 
     @staticmethod
     def backward(ctx, g):
         x16, w16 = ctx.saved_tensors
+        in_dtype, cout = ctx.cfg
         B, cin = x16.shape
         g16 = g.to(torch.float16).contiguous()
         gx = torch.empty_like(x16) if ctx.needs_input_grad[0] else None
         gw = torch.empty_like(w16)
         _lib.call("s3d_linear_backward", g16, x16, w16, B, cin, w16.shape[0], gx, gw)
-        return (gx.to(ctx.in_dtype) if gx is not None else None), gw.float()
+        return (gx.to(in_dtype) if gx is not None else None), gw[:cout].float()
+
+
+class _head_encode(Function):
+    """h = cat([encoder(feat), encoder_dir(d)]) (both `frequency`, tensoRF/network.py:170-172) zero padded to a multiple of 16
+    columns, fp16, in one launch (s3d_tensorf_head_encode); gradient flows to feat only (directions are data)"""
+
+    @staticmethod
+    def forward(ctx, feat16, d, deg, Fd):
+        """feat16 [B, ld] fp16 with Fd valid columns (the padded rows of _linear_tc)"""
+        feat16 = feat16.contiguous()
+        B, ld = feat16.shape
+        K = ((Fd + 3) * (1 + 2 * deg) + 15) // 16 * 16
+        h = torch.empty(B, K, dtype=torch.float16, device=feat16.device)
+        _lib.call("s3d_tensorf_head_encode", feat16, Fd, ld, d.contiguous().float(), B, deg, K, h)
+        ctx.save_for_backward(h)
+        ctx.cfg = (Fd, ld, deg, K)
+        return h
+
+    @staticmethod
+    def backward(ctx, gh):
+        (h,) = ctx.saved_tensors
+        Fd, ld, deg, K = ctx.cfg
+        B = h.shape[0]
+        gf = torch.empty(B, ld, dtype=torch.float16, device=h.device)
+        _lib.call("s3d_tensorf_head_encode_backward", gh.to(torch.float16).contiguous(), h, Fd, ld, B, deg, K, gf)
+        return gf, None, None, None
 
 
 class _mlp_head_tc(Function):
@@ -112,9 +144,14 @@ class _mlp_head_tc(Function):
         w16 = [w.detach().to(torch.float16) for w in weights]
         flat = torch.cat([F.pad(w16[0], (0, in_pad - cin)).reshape(-1)] + [w.reshape(-1) for w in w16[1:-1]] +
                          [F.pad(w16[-1], (0, 0, 0, out_pad - cout)).reshape(-1)]).contiguous()
-        x16 = F.pad(h.detach().to(torch.float16), (0, in_pad - cin)).contiguous()
-        fb = torch.empty(nl, B, hidden, dtype=torch.float16, device=h.device)
+        x16 = h.detach()
+        if x16.dtype != torch.float16 or in_pad != cin or not x16.is_contiguous():
+            x16 = F.pad(x16.to(torch.float16), (0, in_pad - cin)).contiguous()
         out = torch.empty(B, out_pad, dtype=torch.float16, device=h.device)
+        if not any(ctx.needs_input_grad):          # the frozen teacher: no activation buffers to write
+            _lib.call("s3d_ffmlp_inference", x16, flat, B, in_pad, out_pad, hidden, nl, 0, 6, None, out)
+            return out[:, :cout]
+        fb = torch.empty(nl, B, hidden, dtype=torch.float16, device=h.device)
         _lib.call("s3d_ffmlp_forward", x16, flat, B, in_pad, out_pad, hidden, nl, 0, 6, fb, out)
         ctx.save_for_backward(x16, flat, fb)
         ctx.cfg = (cin, in_pad, cout, out_pad, hidden, nl, h.dtype)
@@ -135,7 +172,7 @@ class _mlp_head_tc(Function):
         for _ in range(nl - 1):
             grads.append(gw[off:off + hidden * hidden].view(hidden, hidden).float()); off += hidden * hidden
         grads.append(gw[off:off + out_pad * hidden].view(out_pad, hidden)[:cout].float())
-        return (gx[:, :cin].to(in_dtype), *grads)
+        return ((gx if (cin == in_pad and in_dtype == torch.float16) else gx[:, :cin].to(in_dtype)), *grads)
 
 
 class TensoRFNetwork(NeRFRenderer):
@@ -204,8 +241,16 @@ class TensoRFNetwork(NeRFRenderer):
             # fp16 step (the reference's --fp16): basis_mat and the colour MLP on the tcgen05 kernels instead of cuBLAS GEMMs
             feat = _linear_tc.apply(self._lookup(x, self.color_mat, self.color_vec, False, aabb), self.basis_mat.weight)
             with torch.autocast("cuda", enabled=False):
-                h = torch.cat([self.encoder(feat.float()), self.encoder_dir(d.float())], dim=-1)
-                return torch.sigmoid(_mlp_head_tc.apply(h, *[lin.weight for lin in self.color_net]).float())
+                deg = getattr(self.encoder, "degree", None)
+                if deg is not None and deg == getattr(self.encoder_dir, "degree", None):
+                    h = _head_encode.apply(feat, d, deg, self.color_feat_dim)   # [N, 160] fp16: both encodings + padding in one launch
+                    w0 = self.color_net[0].weight
+                    w0 = F.pad(w0, (0, h.shape[1] - w0.shape[1]))       # the padded columns meet zero weights
+                    out = _mlp_head_tc.apply(h, w0, *[lin.weight for lin in self.color_net[1:]])
+                else:
+                    h = torch.cat([self.encoder(feat[:, :self.color_feat_dim].float()), self.encoder_dir(d.float())], dim=-1)
+                    out = _mlp_head_tc.apply(h, *[lin.weight for lin in self.color_net])
+                return torch.sigmoid(out.float())
         h = torch.cat([self.encoder(self.get_color_feat(x, aabb)), self.encoder_dir(d)], dim=-1)
         for l in range(self.num_layers):
             h = self.color_net[l](h)

@@ -590,7 +590,7 @@ def test_ffmlp_backward(B, din, dh, nl, act):
 
 
 @pytest.mark.parametrize("B,din,dh,dout,nl,act", [(256, 32, 128, 16, 2, 0), (1000, 64, 128, 16, 3, 0), (384, 32, 256, 16, 2, 0), (300, 160, 128, 3, 2, 0),
-                                                  (256, 32, 256, 16, 3, 0), (512, 32, 64, 48, 2, 0), (256, 48, 128, 40, 2, 3), (128, 32, 64, 16, 6, 0)])
+                                                  (256, 32, 256, 16, 3, 0), (512, 32, 64, 48, 2, 0), (256, 48, 128, 40, 2, 3), (128, 32, 64, 16, 6, 0), (200, 16, 16, 16, 7, 0), (300, 32, 32, 24, 2, 0)])
 def test_ffmlp_wide_forward_backward(B, din, dh, dout, nl, act):
     """ffmlp/src/ffmlp.cu:653-670: hidden 128 / 256 and output_dim > 16 (csrc/ffmlp_wide.cu: activations in TMEM, weights
     resident or streamed per layer, split-K weight gradients) against the oracle, and against the reference kernels where the
