@@ -276,6 +276,7 @@ __global__ void k_occ_bbox(const uint8_t *__restrict__ grid, uint32_t n_bytes, i
 
 __global__ void k_occ_bbox_init(int *__restrict__ mm) {
     if (threadIdx.x < 6) mm[threadIdx.x] = threadIdx.x < 3 ? 0x7fffffff : -1;
+    if (threadIdx.x == 6) mm[6] = 0;     // the walk list's counter lives behind the box
 }
 
 // Clip a ray to the occupied bounding box, widened by kBoxMargin cells on every side (single cascade, constant step only).
@@ -385,6 +386,87 @@ k_march_count(const float *__restrict__ rays_o, const float *__restrict__ rays_d
     }
     // per-CTA sample count for the two-level exclusive scan
     uint32_t v = num;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = s_warp[0] + s_warp[1] + s_warp[2] + s_warp[3];
+}
+
+// ---- pass 1 in compacted form (single cascade, constant step) -----------------------------------------------------------
+// Most rays of a batch miss the (widened) bounding box of the occupied cells -- about two thirds on the Lego-shaped scene -- and
+// inside k_march_count their lanes idle while the rest of the warp walks voxels (the pass is instruction-bound, so idle lanes
+// are lost issue slots).  Here a first kernel clips every ray (cheap, no divergence) and COMPACTS the rays that enter the box
+// into a work list with a warp ballot + one atomic per warp; the voxel walk then runs on the list, densely packed.  Results
+// are written by ray id, so the (non-deterministic) list order changes nothing; block sums for the scan come from a third
+// tiny kernel.
+struct WalkItem { uint32_t n; float t, far; uint32_t k; };
+
+__global__ void __launch_bounds__(128)
+k_march_clip(const float *__restrict__ rays_o, const float *__restrict__ rays_d, float bound, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+             const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises, const int *__restrict__ occ_mm,
+             int *__restrict__ rays, WalkItem *__restrict__ items, uint32_t *__restrict__ n_items) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    bool hit = false;
+    WalkItem it{n, 0.0f, 0.0f, 0u};
+    if (n < N) {
+        const MarchCfg c = make_cfg(nullptr, bound, 0.0f, max_steps, C, H);
+        const Ray r = load_ray(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
+        it.far = fars[n];
+        it.t = perturbed_start(c, nears[n], noises ? noises[n] : 0.0f);
+        hit = clip_to_occupied(c, r, occ_mm, it.t, it.far, it.k) && it.t < it.far;
+        rays[(size_t)n * 3] = (int)n;
+        rays[(size_t)n * 3 + 2] = 0;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+    uint32_t base = 0;
+    if (lane == 0 && m) base = atomicAdd(n_items, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (hit) items[base + __popc(m & ((1u << lane) - 1u))] = it;
+}
+
+__global__ void __launch_bounds__(128)
+k_march_walk(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid, float bound, uint32_t max_steps,
+             uint32_t C, uint32_t H, const WalkItem *__restrict__ items, const uint32_t *__restrict__ n_items, int *__restrict__ rays,
+             uint32_t *__restrict__ bitmap) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *n_items) return;
+    const WalkItem it = items[i];
+    const uint32_t n = it.n;
+    const MarchCfg c = make_cfg(grid, bound, 0.0f, max_steps, C, H);
+    const Ray r = load_ray(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
+    float t = it.t, x, y, z, dt;
+    const float far = it.far;
+    uint32_t k = it.k, num = 0;
+    if (bitmap) {
+        uint32_t *bm = bitmap + (size_t)n * kBitmapWords;
+        uint32_t word = 0, widx = 0;
+        bool overflow = false;
+        while (t < far && num < max_steps) {
+            const uint32_t k0 = k;
+            if (march_visit<true>(c, r, t, x, y, z, dt, &k)) {
+                if (k0 < kBitmapBits) {
+                    const uint32_t wi = k0 >> 5;
+                    while (widx < wi) { bm[widx++] = word; word = 0; }
+                    word |= 1u << (k0 & 31);
+                } else overflow = true;
+                num++; t = __fadd_rn(t, dt); k++;
+            }
+        }
+        while (widx < kBitmapWords - 1) { bm[widx++] = word; word = 0; }
+        bm[kBitmapWords - 1] = overflow ? 0xFFFFFFFFu : 0u;
+    } else {
+        while (t < far && num < max_steps) {
+            if (march_visit(c, r, t, x, y, z, dt)) { num++; t = __fadd_rn(t, dt); }
+        }
+    }
+    rays[(size_t)n * 3 + 2] = (int)num;
+}
+
+__global__ void __launch_bounds__(128) k_march_block_sums(const int *__restrict__ rays, uint32_t N, uint32_t *__restrict__ block_sums) {
+    __shared__ uint32_t s_warp[4];
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t v = n < N ? (uint32_t)rays[(size_t)n * 3 + 2] : 0u;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
     if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
@@ -557,7 +639,7 @@ k_march_write_samples(const float *__restrict__ rays_o, const float *__restrict_
     }
     const uint32_t n = lo, off = (uint32_t)rays[(size_t)n * 3 + 1], num = (uint32_t)rays[(size_t)n * 3 + 2];
     if (off + num > M) return;                                   // dropped ray (budget overflow): its slots stay zero
-    const uint32_t *bm = bitmap + (size_t)n * kBitmapWords;
+    const uint32_t *bm = bitmap + (size_t)n * kBitmapWords;      // (a ray with samples was walked: its bitmap is initialised)
     if (__ldg(bm + kBitmapWords - 1) != 0u) return;               // re-walked by k_march_write_overflow
     const uint32_t j = s - off;
     // lattice indices of sample j (k) and of the sample before it (kp)
@@ -594,9 +676,10 @@ k_march_write_overflow(const float *__restrict__ rays_o, const float *__restrict
                        const int *__restrict__ rays, const uint32_t *__restrict__ bitmap, float *__restrict__ xyzs,
                        float *__restrict__ dirs, float *__restrict__ deltas) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N || bitmap[(size_t)n * kBitmapWords + kBitmapWords - 1] == 0u) return;
+    if (n >= N) return;
     const uint32_t off = (uint32_t)rays[(size_t)n * 3 + 1], num = (uint32_t)rays[(size_t)n * 3 + 2];
-    if (num == 0 || off + num > M) return;
+    if (num == 0 || off + num > M) return;        // rays without samples may never have been walked: their bitmap is not read
+    if (bitmap[(size_t)n * kBitmapWords + kBitmapWords - 1] == 0u) return;
     const MarchCfg c = make_cfg(grid, bound, dt_gamma, max_steps, C, H);
     const Ray r = load_ray(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
     const float far = fars[n];
@@ -961,14 +1044,23 @@ int march_count_scan(const float *rays_o, const float *rays_d, const uint8_t *gr
     uint32_t *block_sums = nullptr;
     cudaError_t e = scratch_alloc((void **)&block_sums, ((size_t)nb + 8) * sizeof(uint32_t), st);
     if (e != cudaSuccess) return (int)e;
-    int *occ_mm = nullptr;
-    if (g_march_clip && C == 1 && dt_gamma == 0.0f && H <= 1024) {   // occupied bounding box of the bitfield (stateless: recomputed per call, 262 KB read)
-        occ_mm = (int *)(block_sums + nb);
+    if (g_march_clip && C == 1 && dt_gamma == 0.0f && H <= 1024) {
+        // occupied bounding box of the bitfield (stateless: recomputed per call, 262 KB read), clip + compact, walk the list
+        int *occ_mm = (int *)(block_sums + nb);               // 6 ints + the list counter in the 8 spare words
+        uint32_t *n_items = (uint32_t *)(occ_mm + 6);
+        WalkItem *items = nullptr;
+        e = scratch_alloc((void **)&items, (size_t)N * sizeof(WalkItem), st);
+        if (e != cudaSuccess) { cudaFreeAsync(block_sums, st); return (int)e; }
         k_occ_bbox_init<<<1, 32, 0, st>>>(occ_mm);
         const uint32_t n_bytes = H * H * H / 8;
         k_occ_bbox<<<div_up(n_bytes, 256u), 256, 0, st>>>(grid, n_bytes, occ_mm);
+        k_march_clip<<<nb, 128, 0, st>>>(rays_o, rays_d, bound, max_steps, N, C, H, nears, fars, noises, occ_mm, rays, items, n_items);
+        k_march_walk<<<nb, 128, 0, st>>>(rays_o, rays_d, grid, bound, max_steps, C, H, items, n_items, rays, bitmap);
+        k_march_block_sums<<<nb, 128, 0, st>>>(rays, N, block_sums);
+        cudaFreeAsync(items, st);
+    } else {
+        k_march_count<<<nb, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, block_sums, bitmap, nullptr);
     }
-    k_march_count<<<nb, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, block_sums, bitmap, occ_mm);
     k_march_scan<<<1, 1024, 0, st>>>(block_sums, nb, N, counter);
     k_march_offsets<<<nb, 128, 0, st>>>(rays, N, block_sums);
     e = cudaPeekAtLastError();
