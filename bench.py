@@ -164,6 +164,7 @@ class ClockSampler:
             self.nv = pynvml
             self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
             self.stop_flag = False
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)   # the first query of a process is slow (~0.1 s): not inside the timed region
             self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
             return
@@ -190,7 +191,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.01)
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])

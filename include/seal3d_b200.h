@@ -295,6 +295,18 @@ int s3d_ngp_scatter(const float *xyz, const void *dfeats, uint32_t M, float boun
  * levels in chunks and all-reduce each finished slice of grad4 under the next chunk */
 int s3d_ngp_scatter_levels(const float *xyz, const void *dfeats, uint32_t M, float bound, float *grad4, const int *offsets, uint32_t L,
                            float S, uint32_t H, float grad_scale, uint32_t level_begin, uint32_t level_end, void *stream);
+/* Deterministic mode (no counterpart in the reference, whose gridencoder.cu:246-337 backward is float atomics): gradients are
+ * accumulated as 64-bit fixed point (2^-32) with integer reductions, so the result does not depend on the order the reductions
+ * arrive in and two runs of one step are bit-identical.  fixed4 [N_entries*4] / gw_* (fixed-point, the fp32 matrices' element
+ * layout) are accumulated into; *nonfinite (device word) is raised by an inf / NaN / out-of-range contribution.
+ * s3d_fixed_to_float: grad[i] += fixed[i] * 2^-32, fixed[i] = 0; a raised *nonfinite becomes a NaN in grad[0] and is cleared. */
+int s3d_ngp_scatter_fixed(const float *xyz, const void *dfeats, uint32_t M, float bound, long long *fixed4, const int *offsets, uint32_t L,
+                          float S, uint32_t H, float grad_scale, uint32_t *nonfinite, void *stream);
+int s3d_ngp_mlp_backward_fixed(const void *feats, const float *dirs, uint32_t M, const void *w_s0, const void *w_s1, const void *w_c0,
+                               const void *w_c1, const void *w_c2, float density_scale, const float *g_sigma, const float *g_rgb,
+                               void *dfeats, float out_scale, long long *gw_s0, long long *gw_s1, long long *gw_c0, long long *gw_c1,
+                               long long *gw_c2, int train_mlp, uint32_t *nonfinite, void *stream);
+int s3d_fixed_to_float(long long *fixed, float *grad, size_t n, uint32_t *nonfinite, void *stream);
 int s3d_ngp_adam_tables(float *table_sigma, float *table_color, float *grad4, float *exp_avg4, float *exp_avg_sq4, void *shadow,
                         uint32_t shadow_stride, uint64_t n_entries, float lr, float beta1, float beta2, float eps, uint32_t step,
                         float grad_scale, const float *scaler_state, void *stream);
@@ -315,6 +327,13 @@ int s3d_vm_backward(const float *xyz, uint32_t M, const float *aabb, const float
                     const float *vec0, const float *vec1, const float *vec2, const int *h_dims, uint32_t R, int reduce,
                     const float *grad, float *g_mat0, float *g_mat1, float *g_mat2, float *g_vec0, float *g_vec1, float *g_vec2,
                     void *stream);
+/* the unreduced lookup with fp16 output [M, 3R] / fp16 output gradient: the colour features of an fp16 (autocast) step, rounded
+ * once on the way out like the fp16 cast the reference's autocast basis_mat applies (tensoRF/network.py:155) */
+int s3d_vm_forward_f16(const float *xyz, uint32_t M, const float *aabb, const float *mat0, const float *mat1, const float *mat2,
+                       const float *vec0, const float *vec1, const float *vec2, const int *h_dims, uint32_t R, void *out, void *stream);
+int s3d_vm_backward_f16(const float *xyz, uint32_t M, const float *aabb, const float *mat0, const float *mat1, const float *mat2,
+                        const float *vec0, const float *vec1, const float *vec2, const int *h_dims, uint32_t R, const void *grad,
+                        float *g_mat0, float *g_mat1, float *g_mat2, float *g_vec0, float *g_vec1, float *g_vec2, void *stream);
 /* tensoRF/network.py:263-270 upsample_params: F.interpolate(bilinear, align_corners=True) of one channel-last image */
 int s3d_vm_resize(const float *src, uint32_t H, uint32_t W, float *dst, uint32_t H2, uint32_t W2, uint32_t R, void *stream);
 

@@ -257,8 +257,30 @@ __global__ void k_pair_tables(const uint2 *__restrict__ teacher4, const uint2 *_
 // ------------------------------------------------------------------------------------------------
 // one level of one sample's gradient: in-warp segmented pre-reduction over runs of lanes that sit in the same cell (ray-major
 // samples share cells at the coarse levels), then one 128-bit RED per corner of every run.  Called by whole warps.
+// Fixed-point accumulation (the deterministic mode): a contribution is rounded once to a multiple of 2^-32 and added as a 64-bit
+// integer -- integer addition is associative, so the table no longer depends on the order in which the SMs' reductions reach L2
+// and two runs of the same step are bit-identical.  Range: |sum| < 2^31 per value; non-finite contributions (an fp16 overflow the
+// GradScaler must see) raise a flag word that k_fixed_to_float turns back into a NaN.
+constexpr float kFixedOne = 4294967296.0f;   // 2^32
+__device__ __forceinline__ void fixed_add(long long *__restrict__ p, float v, uint32_t *__restrict__ nonfinite) {
+    if (!(fabsf(v) < 2147483648.0f)) { atomicOr(nonfinite, 1u); return; }   // inf, NaN or out of range
+    const long long q = __float2ll_rn(v * kFixedOne);
+    if (q != 0) atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)q);
+}
+
+template <bool FIXED>
+__device__ __forceinline__ void red_entry(float4 *__restrict__ grad4, uint32_t idx, float a0, float a1, float a2, float a3, uint32_t *__restrict__ nonfinite) {
+    if constexpr (FIXED) {
+        long long *e = reinterpret_cast<long long *>(grad4) + (size_t)idx * 4;
+        fixed_add(e, a0, nonfinite); fixed_add(e + 1, a1, nonfinite); fixed_add(e + 2, a2, nonfinite); fixed_add(e + 3, a3, nonfinite);
+    } else {
+        atomicAdd(grad4 + idx, make_float4(a0, a1, a2, a3));
+    }
+}
+
+template <bool FIXED = false>
 __device__ __forceinline__ void scatter_level(const Geo &g, uint32_t l, bool ok, float ux, float uy, float uz, float g0, float g1, float g2, float g3,
-                                              uint32_t lane, float4 *__restrict__ grad4) {
+                                              uint32_t lane, float4 *__restrict__ grad4, uint32_t *__restrict__ nonfinite = nullptr) {
     Cell c;
     unsigned long long key = ~0ull;
     if (ok) locate(g, l, ux, uy, uz, c, &key);
@@ -292,18 +314,19 @@ __device__ __forceinline__ void scatter_level(const Geo &g, uint32_t l, bool ok,
                     if (d <= seg_left) { a0 += o0; a1 += o1; a2 += o2; a3 += o3; }
                 }
             }
-            if (ok && head) atomicAdd(grad4 + c.idx[k], make_float4(a0, a1, a2, a3));
+            if (ok && head) red_entry<FIXED>(grad4, c.idx[k], a0, a1, a2, a3, nonfinite);
         }
     } else if (ok) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) atomicAdd(grad4 + c.idx[k], make_float4(c.w[k] * g0, c.w[k] * g1, c.w[k] * g2, c.w[k] * g3));
+        for (int k = 0; k < 8; k++) red_entry<FIXED>(grad4, c.idx[k], c.w[k] * g0, c.w[k] * g1, c.w[k] * g2, c.w[k] * g3, nonfinite);
     }
 }
 
+template <bool FIXED>
 __global__ void __launch_bounds__(256)
 k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, uint32_t M, float bound,
               float4 *__restrict__ grad4, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H, float grad_scale,
-              uint32_t grp_begin, uint32_t grp_end) {
+              uint32_t grp_begin, uint32_t grp_end, uint32_t *__restrict__ nonfinite) {
     __shared__ Geo g;
     geo_init(g, offsets, L, S, H);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // whole warps stay alive
@@ -326,9 +349,21 @@ k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, 
             const uint32_t pc = q == 0 ? rc.x : (q == 1 ? rc.y : (q == 2 ? rc.z : rc.w));
             const float2 fs = __half22float2(*reinterpret_cast<const __half2 *>(&ps)), fc = __half22float2(*reinterpret_cast<const __half2 *>(&pc));
             const float g0 = fs.x * grad_scale, g1 = fs.y * grad_scale, g2 = fc.x * grad_scale, g3 = fc.y * grad_scale;
-            scatter_level(g, l, ok, ux, uy, uz, g0, g1, g2, g3, lane, grad4);
+            scatter_level<FIXED>(g, l, ok, ux, uy, uz, g0, g1, g2, g3, lane, grad4, nonfinite);
         }
     }
+}
+
+// fixed-point arena -> fp32 gradient arena (accumulated into), arena cleared; *nonfinite -> NaN in grad[0]
+__global__ void k_fixed_to_float(long long *__restrict__ fx, float *__restrict__ grad, size_t n, uint32_t *__restrict__ nonfinite) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long q = fx[i];
+    if (q != 0) {
+        grad[i] = __fadd_rn(grad[i], __double2float_rn(__dmul_rn(__ll2double_rn(q), 1.0 / 4294967296.0)));
+        fx[i] = 0;
+    }
+    if (i == 0 && *nonfinite) { grad[0] = __int_as_float(0x7fc00000); *nonfinite = 0u; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -946,6 +981,7 @@ struct BwdArgs {
     uint32_t M, n_tiles;
     float density_scale, out_scale;  // out_scale multiplies dfeats (keeps fp16 gradients in range)
     int train_mlp;
+    uint32_t *nonfinite;             // non-NULL: deterministic mode, gw_* point at 64-bit fixed-point values (see fixed_add)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -990,6 +1026,7 @@ __device__ __forceinline__ void iss_acquire_n(uint32_t id) {
     fence_after_sync();
 }
 
+template <bool FIXED>   // FIXED: the weight gradients are flushed as 64-bit fixed point (deterministic mode)
 __global__ void __launch_bounds__(kBwdThreads, 1)
 k_ngp_mlp_bwd(const BwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1258,20 +1295,25 @@ k_ngp_mlp_bwd(const BwdArgs a) {
             const uint32_t lane = tid & 31, rr = (warp & 3u) * 16 + lane;   // output feature
             const bool rowok = lane < 16;
             float v[32];
+            uint32_t *const nf = a.nonfinite;
+            auto add = [nf](float *base, uint32_t idx, float x) {
+                if constexpr (FIXED) fixed_add(reinterpret_cast<long long *>(base) + idx, x, nf);
+                else atomicAdd(base + idx, x);
+            };
             tmem_ld32(t_row + 64 + hf * 32, v);    // dWc2 [3 x 64]
-            if (rowok && rr < 3) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c2 + rr * 64 + hf * 32 + i, v[i]);
+            if (rowok && rr < 3) for (int i = 0; i < 32; i++) add(a.gw_c2, rr * 64 + hf * 32 + i, v[i]);
             tmem_ld32(t_row + 128 + hf * 32, v);   // dWc1 [64 x 64]
-            if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c1 + rr * 64 + hf * 32 + i, v[i]);
+            if (rowok) for (int i = 0; i < 32; i++) add(a.gw_c1, rr * 64 + hf * 32 + i, v[i]);
             tmem_ld32(t_row + 320 + hf * 32, v);   // dWs1 [16 x 64]
-            if (rowok && rr < 16) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s1 + rr * 64 + hf * 32 + i, v[i]);
+            if (rowok && rr < 16) for (int i = 0; i < 32; i++) add(a.gw_s1, rr * 64 + hf * 32 + i, v[i]);
             if (hf == 1) {
                 tmem_ld32(t_row + 192 + 32, v);    // dC1^T . F, columns 32..63 = colour-grid inputs = original columns 31..62
-                if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_c0 + rr * 63 + 31 + i, v[i]);
+                if (rowok) for (int i = 0; i < 32; i++) add(a.gw_c0, rr * 63 + 31 + i, v[i]);
             } else {
                 tmem_ld32(t_row + 256, v);         // dC1^T . G, columns 0..30 = [SH | geo] = original columns 0..30
-                if (rowok) for (int i = 0; i < 31; i++) atomicAdd(a.gw_c0 + rr * 63 + i, v[i]);
+                if (rowok) for (int i = 0; i < 31; i++) add(a.gw_c0, rr * 63 + i, v[i]);
                 tmem_ld32(t_row + 384, v);         // dH1^T . F, columns 0..31 = sigma-grid inputs
-                if (rowok) for (int i = 0; i < 32; i++) atomicAdd(a.gw_s0 + rr * 32 + i, v[i]);
+                if (rowok) for (int i = 0; i < 32; i++) add(a.gw_s0, rr * 32 + i, v[i]);
             }
         }
     }
@@ -1376,7 +1418,7 @@ S3D_API int s3d_ngp_scatter(const float *xyz, const void *dfeats, uint32_t M, fl
     if (M == 0) return 0;
     if (L > kMaxLevels) return S3D_ENOTSUP;
     static const uint32_t blk = [] { const char *e = getenv("S3D_SCATTER_BLOCK"); const uint32_t v = e ? (uint32_t)atoi(e) : 256u; return (v >= 32 && v <= 1024 && v % 32 == 0) ? v : 256u; }();
-    k_ngp_scatter<<<div_up(M, blk), blk, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale, 0, 4);
+    k_ngp_scatter<false><<<div_up(M, blk), blk, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale, 0, 4, nullptr);
     S3D_RETURN_LAST();
 }
 
@@ -1387,8 +1429,28 @@ S3D_API int s3d_ngp_scatter_levels(const float *xyz, const void *dfeats, uint32_
     if (M == 0 || level_begin >= level_end) return 0;
     if (L > kMaxLevels) return S3D_ENOTSUP;
     if ((level_begin & 3u) || ((level_end & 3u) && level_end != L) || level_end > L) return S3D_EINVAL;
-    k_ngp_scatter<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale,
-                                                                    level_begin / 4, div_up(level_end, 4u));
+    k_ngp_scatter<false><<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale,
+                                                                           level_begin / 4, div_up(level_end, 4u), nullptr);
+    S3D_RETURN_LAST();
+}
+
+// Deterministic mode.  fixed4: [N] x {s0,s1,c0,c1} as 64-bit fixed point (2^-32), accumulated into with integer reductions;
+// nonfinite: one device word, set when a contribution was inf / NaN / out of range.
+S3D_API int s3d_ngp_scatter_fixed(const float *xyz, const void *dfeats, uint32_t M, float bound, long long *fixed4, const int *offsets, uint32_t L,
+                                  float S, uint32_t H, float grad_scale, uint32_t *nonfinite, void *stream) {
+    if (M == 0) return 0;
+    if (L > kMaxLevels) return S3D_ENOTSUP;
+    if (!fixed4 || !nonfinite) return S3D_EINVAL;
+    k_ngp_scatter<true><<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)fixed4, offsets, L, S, H, grad_scale, 0, 4,
+                                                                          nonfinite);
+    S3D_RETURN_LAST();
+}
+
+// grad[i] += fixed[i] * 2^-32, fixed[i] = 0 (n values); a raised *nonfinite becomes a NaN in grad[0] and is cleared
+S3D_API int s3d_fixed_to_float(long long *fixed, float *grad, size_t n, uint32_t *nonfinite, void *stream) {
+    if (n == 0) return 0;
+    if (!fixed || !grad || !nonfinite) return S3D_EINVAL;
+    k_fixed_to_float<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(fixed, grad, n, nonfinite);
     S3D_RETURN_LAST();
 }
 
@@ -1450,13 +1512,13 @@ S3D_API int s3d_ngp_pair_forward(const float *xyz, const float *xyz_teacher, con
 S3D_API int s3d_debug_trace(long long *host_out, int n) { return (int)cudaMemcpyFromSymbol(host_out, g_trace, (size_t)n * sizeof(long long)); }
 #endif
 
-S3D_API int s3d_ngp_mlp_backward(const void *feats, const float *dirs, uint32_t M, const void *w_s0, const void *w_s1, const void *w_c0,
-                                 const void *w_c1, const void *w_c2, float density_scale, const float *g_sigma, const float *g_rgb,
-                                 void *dfeats, float out_scale, float *gw_s0, float *gw_s1, float *gw_c0, float *gw_c1, float *gw_c2,
-                                 int train_mlp, void *stream) {
+static int mlp_backward_launch(const void *feats, const float *dirs, uint32_t M, const void *w_s0, const void *w_s1, const void *w_c0,
+                               const void *w_c1, const void *w_c2, float density_scale, const float *g_sigma, const float *g_rgb,
+                               void *dfeats, float out_scale, float *gw_s0, float *gw_s1, float *gw_c0, float *gw_c1, float *gw_c2,
+                               int train_mlp, uint32_t *nonfinite, void *stream) {
     if (M == 0) return 0;
     const size_t smem = bwd_smem();
-    cudaError_t e = cudaFuncSetAttribute(k_ngp_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(nonfinite ? k_ngp_mlp_bwd<true> : k_ngp_mlp_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     BwdArgs a;
     a.feats = (const __half *)feats; a.dirs = dirs;
@@ -1464,9 +1526,30 @@ S3D_API int s3d_ngp_mlp_backward(const void *feats, const float *dirs, uint32_t 
     a.g_sigma = g_sigma; a.g_rgb = g_rgb; a.dfeats = (__half *)dfeats;
     a.gw_s0 = gw_s0; a.gw_s1 = gw_s1; a.gw_c0 = gw_c0; a.gw_c1 = gw_c1; a.gw_c2 = gw_c2;
     a.M = M; a.n_tiles = div_up(M, kRows); a.density_scale = density_scale; a.out_scale = out_scale; a.train_mlp = train_mlp;
+    a.nonfinite = nonfinite;
     const uint32_t grid = min(a.n_tiles, (uint32_t)sm_count());
-    k_ngp_mlp_bwd<<<grid, kBwdThreads, smem, as_stream(stream)>>>(a);
+    if (nonfinite) k_ngp_mlp_bwd<true><<<grid, kBwdThreads, smem, as_stream(stream)>>>(a);
+    else k_ngp_mlp_bwd<false><<<grid, kBwdThreads, smem, as_stream(stream)>>>(a);
     S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_ngp_mlp_backward(const void *feats, const float *dirs, uint32_t M, const void *w_s0, const void *w_s1, const void *w_c0,
+                                 const void *w_c1, const void *w_c2, float density_scale, const float *g_sigma, const float *g_rgb,
+                                 void *dfeats, float out_scale, float *gw_s0, float *gw_s1, float *gw_c0, float *gw_c1, float *gw_c2,
+                                 int train_mlp, void *stream) {
+    return mlp_backward_launch(feats, dirs, M, w_s0, w_s1, w_c0, w_c1, w_c2, density_scale, g_sigma, g_rgb, dfeats, out_scale, gw_s0, gw_s1, gw_c0, gw_c1,
+                               gw_c2, train_mlp, nullptr, stream);
+}
+
+// Deterministic mode: the weight gradients of the CTAs are added as 64-bit fixed point (2^-32; same element layout as the fp32
+// matrices) so that their sum does not depend on the order the CTAs finish in; dfeats is unchanged.
+S3D_API int s3d_ngp_mlp_backward_fixed(const void *feats, const float *dirs, uint32_t M, const void *w_s0, const void *w_s1, const void *w_c0,
+                                       const void *w_c1, const void *w_c2, float density_scale, const float *g_sigma, const float *g_rgb,
+                                       void *dfeats, float out_scale, long long *gw_s0, long long *gw_s1, long long *gw_c0, long long *gw_c1,
+                                       long long *gw_c2, int train_mlp, uint32_t *nonfinite, void *stream) {
+    if (!nonfinite) return S3D_EINVAL;
+    return mlp_backward_launch(feats, dirs, M, w_s0, w_s1, w_c0, w_c1, w_c2, density_scale, g_sigma, g_rgb, dfeats, out_scale, (float *)gw_s0, (float *)gw_s1,
+                               (float *)gw_c0, (float *)gw_c1, (float *)gw_c2, train_mlp, nonfinite, stream);
 }
 
 S3D_API int s3d_ngp_interleave_tables(const float *table_sigma, const float *table_color, void *table4, uint64_t n_entries, void *stream) {

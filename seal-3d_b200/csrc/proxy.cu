@@ -236,8 +236,15 @@ __global__ void k_modify_hsv(float *__restrict__ rgbs, const uint8_t *__restrict
     rgbs[(size_t)i * 3] = o.x; rgbs[(size_t)i * 3 + 1] = o.y; rgbs[(size_t)i * 3 + 2] = o.z;
 }
 
-// stats[0] += sum of V over masked rows, stats[1] += count
-__global__ void k_v_stats(const float *__restrict__ rgbs, const uint8_t *__restrict__ mask, uint32_t M, float *__restrict__ stats) {
+// mean V of the masked rows, in a fixed order (no float atomics: the edited colours -- the distillation targets -- are then the same
+// bits on every run): every CTA leaves one (sum, count) pair, the last CTA to finish adds the pairs in index order.
+constexpr uint32_t kStatBlocks = 1024;
+// part: per-call scratch, kStatBlocks pairs followed by the ticket word (zero on entry)
+__global__ void __launch_bounds__(256) k_v_stats(const float *__restrict__ rgbs, const uint8_t *__restrict__ mask, uint32_t M, float *__restrict__ stats,
+                                                 float2 *__restrict__ part) {
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(part + kStatBlocks);
+    __shared__ float2 s_part[8];
+    __shared__ bool s_last;
     float s = 0.0f, n = 0.0f;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
         if (mask && !mask[i]) continue;
@@ -246,7 +253,35 @@ __global__ void k_v_stats(const float *__restrict__ rgbs, const uint8_t *__restr
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, d); n += __shfl_xor_sync(0xffffffffu, n, d); }
-    if ((threadIdx.x & 31) == 0 && n > 0.0f) { atomicAdd(stats, s); atomicAdd(stats + 1, n); }
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = make_float2(s, n);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float2 t = s_part[0];
+        for (int w = 1; w < 8; w++) { t.x += s_part[w].x; t.y += s_part[w].y; }
+        part[blockIdx.x] = t;
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // last CTA: warp 0 sums the pairs in a fixed tree (lane-strided partial sums, then a butterfly)
+    if (threadIdx.x < 32) {
+        float a = 0.0f, b = 0.0f;
+        for (uint32_t i = threadIdx.x; i < gridDim.x; i += 32) { const float2 t = __ldcg(part + i); a += t.x; b += t.y; }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
+        if (threadIdx.x == 0) { stats[0] = a; stats[1] = b; }
+    }
+}
+
+static cudaError_t v_stats_launch(const float *rgbs, const uint8_t *mask, uint32_t M, float *d_stats, cudaStream_t st) {
+    float2 *part = nullptr;
+    cudaError_t e = scratch_alloc((void **)&part, (kStatBlocks + 1) * sizeof(float2), st);
+    if (e != cudaSuccess) return e;
+    cudaMemsetAsync(part + kStatBlocks, 0, sizeof(float2), st);
+    k_v_stats<<<min(div_up(M, 256u), kStatBlocks), 256, 0, st>>>(rgbs, mask, M, d_stats, part);
+    return cudaFreeAsync(part, st);
 }
 
 __global__ void k_modify_rgb(float *__restrict__ rgbs, const uint8_t *__restrict__ mask, uint32_t M, float3 target_hsv,
@@ -355,7 +390,7 @@ S3D_API int s3d_seal_map_color(float *rgbs, const uint8_t *mask, uint32_t M, con
     if (h_rgb_target) {
         if (!d_stats) return S3D_EINVAL;
         cudaMemsetAsync(d_stats, 0, 2 * sizeof(float), st);
-        k_v_stats<<<min(div_up(M, 256u), 1024u), 256, 0, st>>>(rgbs, mask, M, d_stats);
+        { cudaError_t e = v_stats_launch(rgbs, mask, M, d_stats, st); if (e != cudaSuccess) return (int)e; }
         k_modify_rgb<<<div_up(M, 256u), 256, 0, st>>>(rgbs, mask, M, rgb2hsv_host(h_rgb_target), light_offset, d_stats);
     }
     S3D_RETURN_LAST();
@@ -441,7 +476,7 @@ S3D_API int s3d_seal_map_color_image(float *rgbs, const float *points, const uin
     c.light = light_offset; c.H = H; c.W = W;
     cudaStream_t st = as_stream(stream);
     cudaMemsetAsync(d_stats, 0, 2 * sizeof(float), st);
-    k_v_stats<<<min(div_up(M, 256u), 1024u), 256, 0, st>>>(rgbs, mask, M, d_stats);
+    { cudaError_t e = v_stats_launch(rgbs, mask, M, d_stats, st); if (e != cudaSuccess) return (int)e; }
     k_modify_rgb_image<<<div_up(M, 256u), 256, 0, st>>>(rgbs, points, mask, M, c, d_image, d_alpha, d_stats);
     S3D_RETURN_LAST();
 }

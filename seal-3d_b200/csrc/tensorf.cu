@@ -98,10 +98,12 @@ __device__ __forceinline__ void factors(const VmArgs &a, int i, const float (&x)
 }
 
 // thread = (sample, 4-channel group); G = R / 4 lanes per sample.  REDUCE: out[M] (G a power of two <= 32), else out[M, 3R].
-template <bool REDUCE>
+// T = float, or __half for the unreduced colour features of an fp16 step: the product is rounded to fp16 once on the way out --
+// the same value the reference's autocast F.linear (basis_mat) makes of it -- instead of in a separate cast pass.
+template <bool REDUCE, typename T = float>
 __global__ void __launch_bounds__(256)
 k_vm_forward(const float *__restrict__ xyz, uint32_t M, const float *__restrict__ aabb, VmArgs a, uint32_t R, uint32_t G,
-             float *__restrict__ out) {
+             T *__restrict__ out) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;   // whole warps stay alive for the shuffles
     const bool live = t < (uint64_t)M * G;
     const uint32_t m = live ? (uint32_t)(t / G) : 0, g = live ? (uint32_t)(t % G) : 0;
@@ -119,16 +121,22 @@ k_vm_forward(const float *__restrict__ xyz, uint32_t M, const float *__restrict_
             for (uint32_t o = 1; o < G; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             total += s;
         } else if (live) {
-            reinterpret_cast<float4 *>(out + (size_t)m * 3 * R + (size_t)i * R)[g] = p;
+            if constexpr (sizeof(T) == 2) {
+                const __half2 lo = __floats2half2_rn(p.x, p.y), hi = __floats2half2_rn(p.z, p.w);
+                reinterpret_cast<uint2 *>(out + (size_t)m * 3 * R + (size_t)i * R)[g] =
+                    make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
+            } else {
+                reinterpret_cast<float4 *>(out + (size_t)m * 3 * R + (size_t)i * R)[g] = p;
+            }
         }
     }
-    if (REDUCE && live && g == 0) out[m] = total;
+    if constexpr (REDUCE) { if (live && g == 0) out[m] = total; }
 }
 
-template <bool REDUCE>
+template <bool REDUCE, typename T = float>
 __global__ void __launch_bounds__(256)
 k_vm_backward(const float *__restrict__ xyz, uint32_t M, const float *__restrict__ aabb, VmArgs a, uint32_t R, uint32_t G,
-              const float *__restrict__ grad, VmGradArgs ga) {
+              const T *__restrict__ grad, VmGradArgs ga) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (uint64_t)M * G) return;
     const uint32_t m = (uint32_t)(t / G), g = (uint32_t)(t % G);
@@ -141,7 +149,15 @@ k_vm_backward(const float *__restrict__ xyz, uint32_t M, const float *__restrict
         Taps tp, tl;
         float4 fm, fv;
         factors(a, i, x, R, g, tp, tl, fm, fv);
-        if constexpr (!REDUCE) go = __ldg(reinterpret_cast<const float4 *>(grad + (size_t)m * 3 * R + (size_t)i * R) + g);
+        if constexpr (!REDUCE) {
+            if constexpr (sizeof(T) == 2) {
+                const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(grad + (size_t)m * 3 * R + (size_t)i * R) + g);
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x)), hi = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+                go = make_float4(lo.x, lo.y, hi.x, hi.y);
+            } else {
+                go = __ldg(reinterpret_cast<const float4 *>(grad + (size_t)m * 3 * R + (size_t)i * R) + g);
+            }
+        }
         const float4 gm = make_float4(go.x * fv.x, go.y * fv.y, go.z * fv.z, go.w * fv.w);   // d/d(plane factor)
         const float4 gv = make_float4(go.x * fm.x, go.y * fm.y, go.z * fm.z, go.w * fm.w);   // d/d(line factor)
 #pragma unroll
@@ -204,6 +220,32 @@ S3D_API int s3d_vm_forward(const float *xyz, uint32_t M, const float *aabb, cons
     const unsigned blocks = (unsigned)div_up((uint64_t)M * G, (uint64_t)256);
     if (reduce) k_vm_forward<true><<<blocks, 256, 0, as_stream(stream)>>>(xyz, M, aabb, a, R, G, out);
     else k_vm_forward<false><<<blocks, 256, 0, as_stream(stream)>>>(xyz, M, aabb, a, R, G, out);
+    S3D_RETURN_LAST();
+}
+
+// the unreduced lookup with fp16 output [M, 3R] / fp16 output gradient (the colour features of an fp16 step)
+S3D_API int s3d_vm_forward_f16(const float *xyz, uint32_t M, const float *aabb, const float *mat0, const float *mat1, const float *mat2,
+                               const float *vec0, const float *vec1, const float *vec2, const int *h_dims, uint32_t R, void *out, void *stream) {
+    if (M == 0) return 0;
+    VmArgs a;
+    uint32_t G;
+    if (int rc = fill_args(a, mat0, mat1, mat2, vec0, vec1, vec2, h_dims, R, 0, G)) return rc;
+    const unsigned blocks = (unsigned)div_up((uint64_t)M * G, (uint64_t)256);
+    k_vm_forward<false, __half><<<blocks, 256, 0, as_stream(stream)>>>(xyz, M, aabb, a, R, G, (__half *)out);
+    S3D_RETURN_LAST();
+}
+
+S3D_API int s3d_vm_backward_f16(const float *xyz, uint32_t M, const float *aabb, const float *mat0, const float *mat1, const float *mat2,
+                                const float *vec0, const float *vec1, const float *vec2, const int *h_dims, uint32_t R, const void *grad,
+                                float *g_mat0, float *g_mat1, float *g_mat2, float *g_vec0, float *g_vec1, float *g_vec2, void *stream) {
+    if (M == 0) return 0;
+    VmArgs a;
+    uint32_t G;
+    if (int rc = fill_args(a, mat0, mat1, mat2, vec0, vec1, vec2, h_dims, R, 0, G)) return rc;
+    VmGradArgs ga;
+    ga.mat[0] = g_mat0; ga.mat[1] = g_mat1; ga.mat[2] = g_mat2; ga.vec[0] = g_vec0; ga.vec[1] = g_vec1; ga.vec[2] = g_vec2;
+    const unsigned blocks = (unsigned)div_up((uint64_t)M * G, (uint64_t)256);
+    k_vm_backward<false, __half><<<blocks, 256, 0, as_stream(stream)>>>(xyz, M, aabb, a, R, G, (const __half *)grad, ga);
     S3D_RETURN_LAST();
 }
 

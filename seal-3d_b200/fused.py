@@ -21,8 +21,13 @@ _MLP = ("sigma_net.0", "sigma_net.1", "color_net.0", "color_net.1", "color_net.2
 
 
 class FusedNGP:
-    def __init__(self, model, trainable=False):
+    def __init__(self, model, trainable=False, deterministic=None):
+        """deterministic (default: S3D_DETERMINISTIC=1): accumulate the table / weight gradients as 64-bit fixed point with integer
+        reductions (s3d_ngp_scatter_fixed, s3d_ngp_mlp_backward_fixed) instead of float atomics: two runs of the same steps then
+        end with bit-identical parameters (the float scatter differs run to run in the last bits); about 2x the scatter time and
+        a second, 8-byte-per-value arena."""
         self.model = model
+        self.deterministic = (os.environ.get("S3D_DETERMINISTIC", "0") == "1") if deterministic is None else bool(deterministic)
         enc, encc = model.encoder, model.encoder_color
         assert enc.level_dim == 2 and encc.level_dim == 2 and enc.input_dim == 3 and enc.gridtype_id == 0 and not enc.align_corners
         assert torch.equal(enc.offsets, encc.offsets), "the fused field needs both grids to share their level geometry"
@@ -68,6 +73,9 @@ class FusedNGP:
             self.v_mlp = torch.zeros(self.n_mlp, dtype=torch.float32, device=self.dev)
             self.step_tables = 0
             self.step_mlp = 0
+            if self.deterministic:
+                self.fixed = torch.zeros(self.N * 4 + self.n_mlp, dtype=torch.int64, device=self.dev)
+                self.nonfinite = torch.zeros(1, dtype=torch.int32, device=self.dev)
 
     # -- state --------------------------------------------------------------------------------
     def sync_from_module(self):
@@ -171,7 +179,7 @@ class FusedNGP:
         M = feats.shape[0]
         w, gw = self._w16(), self._gw()
         dfeats = torch.empty(M, 64, dtype=torch.float16, device=self.dev)
-        if sample_chunks > 1 and not chunks and M >= 128 * sample_chunks:
+        if sample_chunks > 1 and not chunks and not self.deterministic and M >= 128 * sample_chunks:
             per = (M + sample_chunks - 1) // sample_chunks
             per = (per + 127) // 128 * 128
             main, hi = torch.cuda.current_stream(), self._hi_stream()
@@ -191,6 +199,19 @@ class FusedNGP:
             for ev, (a, b) in zip(evs, spans):
                 main.wait_event(ev)
                 _lib.call("s3d_ngp_scatter", xyz[a:b], dfeats[a:b], b - a, self.bound, self.grad4, self.offsets, self.L, self.S, self.H, 1.0)
+            return
+        if self.deterministic:
+            fx = self.fixed
+            gf = [fx[self.N * 4 + o:] for o, _ in self._w_off]
+            _lib.call("s3d_ngp_mlp_backward_fixed", feats, dirs, M, w[0], w[1], w[2], w[3], w[4], self.density_scale, g_sigma, g_rgb, dfeats,
+                      1.0, gf[0], gf[1], gf[2], gf[3], gf[4], int(train_mlp), self.nonfinite)
+            if before_scatter is not None:
+                before_scatter()
+            _lib.call("s3d_ngp_scatter_fixed", xyz, dfeats, M, self.bound, fx, self.offsets, self.L, self.S, self.H, 1.0, self.nonfinite)
+            _lib.call("s3d_fixed_to_float", fx, self.grad, fx.numel(), self.nonfinite)
+            if chunks and after_chunk is not None:   # the data-parallel trainer all-reduces the finished arena slices
+                for i, (l0, l1, a0, a1) in enumerate(chunks):
+                    after_chunk(i, a0, a1)
             return
         _lib.call("s3d_ngp_mlp_backward", feats, dirs, M, w[0], w[1], w[2], w[3], w[4], self.density_scale, g_sigma, g_rgb, dfeats,
                   1.0, gw[0], gw[1], gw[2], gw[3], gw[4], int(train_mlp))
@@ -301,13 +322,13 @@ class FusedDistillTrainer:
     """Same public steps as trainer.DistillTrainer (pretrain_step / finetune_step / distill_step), fused kernels inside."""
 
     def __init__(self, student, teacher=None, lr=1e-2, loss_scale=None, bg_color=1.0, T_thresh=1e-4, max_steps=1024, dt_gamma=0.0,
-                 world_size=1, update_interval=16, lr_decay_iters=None, ema_decay=None, scaler_kwargs=None):
-        """loss_scale: None = static 32 x batch units (default), a float = static, "dynamic" = GradScaler semantics on the
+                 world_size=1, update_interval=16, lr_decay_iters=None, ema_decay=None, scaler_kwargs=None, deterministic=None):
+        """deterministic: see FusedNGP (fixed-point gradient accumulation, bit-identical runs).  loss_scale: None = static 32 x batch units (default), a float = static, "dynamic" = GradScaler semantics on the
         device (scaler_kwargs: init_scale / growth_factor / backoff_factor / growth_interval).  lr_decay_iters = the LambdaLR
         of main_SealNeRF.py:287-288, lr * 0.1 ** min(step / iters, 1), stepped every step.  ema_decay = torch_ema decay
         (0.95 in main_SealNeRF.py:292-302); call ema_update() once per epoch like nerf/utils.py:882-883."""
         self.student, self.teacher = student, teacher
-        self.S = FusedNGP(student, trainable=True)
+        self.S = FusedNGP(student, trainable=True, deterministic=deterministic)
         self.T = FusedNGP(teacher, trainable=False) if teacher is not None else None
         # gradient tiles are fp16 (fp32 accumulation): the loss is scaled so that they sit in fp16's normal range and
         # the scale is divided out inside the Adam kernels.  The mean reductions make gradients ~ 1/units, so the

@@ -47,6 +47,7 @@ class _vm_lookup(Function):
 
     @staticmethod
     def forward(ctx, x, aabb, reduce, *imgs):
+        """reduce: True -> [M] fp32 (sigma), False -> [M, 3R] fp32, "half" -> [M, 3R] fp16 (colour features of an fp16 step)"""
         x = x.contiguous().float()
         _lib.check_cuda(x)
         for im in imgs:
@@ -57,8 +58,12 @@ class _vm_lookup(Function):
         dims = [[m.shape[2], m.shape[3], v.shape[2]] for m, v in zip(mats, vecs)]
         hd = _lib.host_i32(dims)
         M = x.shape[0]
-        out = torch.empty(M if reduce else (M, 3 * R), dtype=torch.float32, device=x.device)
-        _lib.call("s3d_vm_forward", x, M, aabb, *mats, *vecs, hd[1], R, 1 if reduce else 0, out)
+        if reduce == "half":
+            out = torch.empty(M, 3 * R, dtype=torch.float16, device=x.device)
+            _lib.call("s3d_vm_forward_f16", x, M, aabb, *mats, *vecs, hd[1], R, out)
+        else:
+            out = torch.empty(M if reduce else (M, 3 * R), dtype=torch.float32, device=x.device)
+            _lib.call("s3d_vm_forward", x, M, aabb, *mats, *vecs, hd[1], R, 1 if reduce else 0, out)
         ctx.save_for_backward(x, aabb, *imgs)
         ctx.cfg = (hd, R, reduce)
         return out
@@ -67,9 +72,11 @@ class _vm_lookup(Function):
     def backward(ctx, g):
         x, aabb, *imgs = ctx.saved_tensors
         hd, R, reduce = ctx.cfg
-        g = g.contiguous().float()
         grads = [torch.zeros_like(im) for im in imgs]      # preserve_format: channels_last like the parameter
-        _lib.call("s3d_vm_backward", x, x.shape[0], aabb, *imgs, hd[1], R, 1 if reduce else 0, g, *grads)
+        if reduce == "half":
+            _lib.call("s3d_vm_backward_f16", x, x.shape[0], aabb, *imgs, hd[1], R, g.contiguous().to(torch.float16), *grads)
+        else:
+            _lib.call("s3d_vm_backward", x, x.shape[0], aabb, *imgs, hd[1], R, 1 if reduce else 0, g.contiguous().float(), *grads)
         return (None, None, None, *grads)
 
 
@@ -239,7 +246,7 @@ class TensoRFNetwork(NeRFRenderer):
     def _color_mlp(self, x, d, aabb):
         if torch.is_autocast_enabled() and x.is_cuda and self.hidden_dim in (16, 32, 64, 128, 256) and self.num_layers >= 3:
             # fp16 step (the reference's --fp16): basis_mat and the colour MLP on the tcgen05 kernels instead of cuBLAS GEMMs
-            feat = _linear_tc.apply(self._lookup(x, self.color_mat, self.color_vec, False, aabb), self.basis_mat.weight)
+            feat = _linear_tc.apply(self._lookup(x, self.color_mat, self.color_vec, "half", aabb), self.basis_mat.weight)
             with torch.autocast("cuda", enabled=False):
                 deg = getattr(self.encoder, "degree", None)
                 if deg is not None and deg == getattr(self.encoder_dir, "degree", None):

@@ -573,3 +573,83 @@ def test_scatter_in_level_chunks_equals_one_launch(scene):
         np.testing.assert_allclose(npy(F.grad), npy(one), rtol=0, atol=2e-6 * float(one.abs().max()))
     with pytest.raises(_lib.S3DError):       # level ranges are whole 4-level groups
         _lib.call("s3d_ngp_scatter_levels", to(x0), feats, 128, F.bound, F.grad4, F.offsets, F.L, F.S, F.H, 1.0, 2, 8)
+
+
+def test_deterministic_mode_gradients_are_bit_identical_and_equal_the_float_path(scene):
+    """FusedNGP(deterministic=True): table and weight gradients accumulated as 64-bit fixed point (integer reductions).  Two
+    backward passes over the same samples give the same BITS (the float scatter only agrees to rounding), the values agree with
+    the float path and the float64 oracle, and a non-finite contribution reaches the gradient arena as a NaN (GradScaler)."""
+    from seal3d_b200.fused import FusedNGP
+    from seal3d_b200 import _lib
+    t, s, _, _ = _networks(scene)
+    s.encoder.embeddings.data.copy_(t.encoder.embeddings.data)
+    s.encoder_color.embeddings.data.copy_(t.encoder_color.embeddings.data)
+    F = FusedNGP(s, trainable=True, deterministic=True)
+    G = FusedNGP(s, trainable=True, deterministic=False)
+    x0, d0, _, _, M = _samples(scene, 1024)
+    x0, d0 = x0[:150000], d0[:150000]
+    rng = np.random.default_rng(0)
+    gs, gc = to((rng.normal(size=x0.shape[0]) * 1e-2).astype(np.float32)), to((rng.normal(size=(x0.shape[0], 3)) * 1e-1).astype(np.float32))
+    sig, rgb, feats = F.forward(to(x0), to(d0))
+    runs = []
+    for _ in range(3):
+        F.grad.zero_()
+        F.backward(to(x0), to(d0), feats, gs, gc)
+        runs.append(F.grad.clone())
+        assert int(F.fixed.abs().max()) == 0 and int(F.nonfinite[0]) == 0       # the fixed-point arena is handed back cleared
+    assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+    G.backward(to(x0), to(d0), feats, gs, gc)
+    a, b = npy(runs[0]), npy(G.grad)
+    nt = F.N * 4
+    assert np.abs(a[:nt] - b[:nt]).max() <= 2e-6 * np.abs(b[:nt]).max()          # tables: fp32 summation order vs exact integer sums
+    assert np.abs(a[nt:] - b[nt:]).max() <= 2e-5 * np.abs(b[nt:]).max()          # weights: 148 fp32 partial sums per element
+
+    # scatter alone against the double-accumulating oracle, like test_fused_scatter_matches_oracle
+    offsets, pls = scene["synth"].grid_offsets()
+    xs = x0[:60000]
+    df = oracle.round_to_half((rng.normal(size=(xs.shape[0], 64)) * 1e-2).astype(np.float32))
+    n = int(offsets[-1])
+    fx = torch.zeros(n * 4, dtype=torch.int64, device=dev())
+    flag = torch.zeros(1, dtype=torch.int32, device=dev())
+    g4 = torch.zeros(n, 4, device=dev())
+    _lib.call("s3d_ngp_scatter_fixed", to(xs), to(df).half(), xs.shape[0], 1.0, fx, to(offsets), 16, float(np.log2(pls)), 16, 1.0, flag)
+    _lib.call("s3d_fixed_to_float", fx, g4, n * 4, flag)
+    u = ((xs + 1) / 2).astype(np.float32)
+    with scaled(offsets, pls):
+        os_ = oracle.grid_encode_backward(np.ascontiguousarray(df[:, :32].reshape(-1, 16, 2).transpose(1, 0, 2)), u, (n, 2), offsets, pls, 16)
+        oc = oracle.grid_encode_backward(np.ascontiguousarray(df[:, 32:].reshape(-1, 16, 2).transpose(1, 0, 2)), u, (n, 2), offsets, pls, 16)
+    got = npy(g4)
+    for name, p, q in (("sigma", got[:, :2], os_), ("colour", got[:, 2:], oc)):
+        assert np.abs(p - q).max() <= 1e-4 * np.abs(q).max() + 1e-7, (name, np.abs(p - q).max(), np.abs(q).max())
+
+    # an overflowed (inf) feature gradient must not disappear in the integer sum
+    dfi = to(df).half()
+    dfi[1234, 5] = float("inf")
+    _lib.call("s3d_ngp_scatter_fixed", to(xs), dfi, xs.shape[0], 1.0, fx, to(offsets), 16, float(np.log2(pls)), 16, 1.0, flag)
+    assert int(flag[0]) == 1
+    g4.zero_()
+    _lib.call("s3d_fixed_to_float", fx, g4, n * 4, flag)
+    assert bool(torch.isnan(g4.reshape(-1)[0])) and int(flag[0]) == 0 and int(fx.abs().max()) == 0
+
+
+def test_deterministic_trainer_runs_end_with_the_same_bits(scene):
+    """two fused trainers from the same state, same rays, same seeds, deterministic=True: identical parameters and fp16 shadows
+    after several distillation steps (occupancy refresh included); and the deterministic run follows the default one"""
+    from seal3d_b200.fused import FusedDistillTrainer
+    o, d = to(scene["o"][:4096]), to(scene["d"][:4096])
+
+    def run(deterministic):
+        torch.manual_seed(0)
+        t, s, _, _ = _networks(scene)
+        tr = FusedDistillTrainer(s, t, lr=1e-2, update_interval=2, deterministic=deterministic)
+        losses = [npy(tr.distill_step(o, d, perturb=True, force_all_rays=True)).copy() for _ in range(5)]
+        return s, tr, np.stack(losses)
+
+    s1, tr1, l1 = run(True)
+    s2, tr2, l2 = run(True)
+    for p, q in zip(s1.parameters(), s2.parameters()):
+        assert torch.equal(p, q)
+    assert torch.equal(tr1.S.m4, tr2.S.m4) and torch.equal(tr1.S.v4, tr2.S.v4) and torch.equal(tr1.S.mlp16, tr2.S.mlp16)
+    assert torch.equal(s1.density_bitfield, s2.density_bitfield)
+    s3, tr3, l3 = run(False)
+    np.testing.assert_allclose(l1, l3, rtol=2e-2)
