@@ -1,6 +1,7 @@
 """BASELINE config 5 in numbers: TensoRF teacher -> TensoRF student distillation steps (colour edit in a bbox) on one B200,
-through trainer.DistillTrainer (VM lookup kernels + frequency encoder kernels + the marcher / compositor / proxy / loss /
-Adam kernels; the 150-128-128-3 MLP and basis_mat are F.linear GEMMs like in the reference).  Prints one JSON line.
+through trainer.DistillTrainer (VM lookup kernels with fp16 colour features, basis_mat on s3d_linear_*, one-launch frequency
+encodings, the 150-128-128-3 MLP on the wide FFMLP kernels, marcher / compositor / proxy / loss / Adam kernels).  Prints one JSON
+line; "torch_gemm_and_glue_ms" = step time minus the time inside this library's launches.
 Development / measurement tool; the headline bench (bench.py) stays on the NGP backbone the metric is quoted on."""
 import json
 import os

@@ -13,7 +13,10 @@ def t(fn, n=5):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-for (cin, hid, cout, nl) in ((160, 128, 16, 2), (32, 64, 16, 6), (32, 256, 16, 2)):
+SHAPES = ((160, 128, 16, 2), (32, 64, 16, 6), (32, 256, 16, 2))
+if os.environ.get('SHAPE'):
+    SHAPES = (SHAPES[int(os.environ['SHAPE'])],)
+for (cin, hid, cout, nl) in SHAPES:
     x = torch.randn(B, cin, device=dev).half()
     w = (torch.randn(hid * cin + hid * hid * (nl - 1) + cout * hid, device=dev) * 0.05).half()
     fb = torch.empty(nl, B, hid, device=dev, dtype=torch.float16)

@@ -104,34 +104,52 @@ __device__ __forceinline__ void sync_all() {
 // The loads of four 32-value chunks (16 x 16 bytes) are issued before the first tcgen05.st: one exposed global-memory
 // latency per 128 values instead of one per chunk (ncu: the kernel's warps sat on the long scoreboard at 12 % occupancy).
 // `half_sel` = 0 / 1: the thread's warpgroup takes the 32-value chunks with an even / odd chunk index
-__device__ __forceinline__ void row_to_tmem(uint32_t t_a, const __half *__restrict__ g_row, uint32_t n_half, bool in_range, uint32_t half_sel) {
+// G = chunks per staging group (4 * G sixteen-byte loads in flight per thread).  row_load / row_store are the two halves of one
+// group, so that a caller can issue the loads of the NEXT tile before it waits for the current tile's last MMA.
+template <uint32_t G>
+__device__ __forceinline__ void row_load(uint4 (&v)[4 * G], const __half *__restrict__ g_row, uint32_t n_half, bool in_range, uint32_t half_sel, uint32_t i0) {
     const bool vec = (n_half & 7u) == 0;
-    // this thread's chunks: 32 * (2 i + half_sel), i = 0, 1, ...; staged four at a time
-    for (uint32_t i0 = 0; 32 * (2 * i0 + half_sel) < n_half; i0 += 4) {
-        uint4 v[16];
+    const bool wide = (n_half & 15u) == 0 && aligned32(g_row);     // rows are multiples of 32 bytes: 256-bit loads
 #pragma unroll
-        for (uint32_t q = 0; q < 16; q++) {
-            v[q] = make_uint4(0, 0, 0, 0);
-            const uint32_t col = 32 * (2 * (i0 + q / 4) + half_sel) + (q & 3u) * 8;
-            if (in_range && col < n_half) {
-                if (vec && col + 8 <= n_half) v[q] = __ldg(reinterpret_cast<const uint4 *>(g_row + col));
+    for (uint32_t q = 0; q < 4 * G; q += 2) {
+        v[q] = make_uint4(0, 0, 0, 0);
+        v[q + 1] = make_uint4(0, 0, 0, 0);
+        const uint32_t col = 32 * (2 * (i0 + q / 4) + half_sel) + (q & 3u) * 8;
+        if (in_range && wide && col + 16 <= n_half) { ldg256(g_row + col, v[q], v[q + 1]); continue; }
+#pragma unroll
+        for (uint32_t u = 0; u < 2; u++) {
+            const uint32_t cu = col + 8 * u;
+            if (in_range && cu < n_half) {
+                if (vec && cu + 8 <= n_half) v[q + u] = __ldg(reinterpret_cast<const uint4 *>(g_row + cu));
                 else {
                     __half h[8];
-                    for (uint32_t j = 0; j < 8; j++) h[j] = (col + j < n_half) ? g_row[col + j] : __float2half_rn(0.0f);
-                    v[q] = *reinterpret_cast<const uint4 *>(h);
+                    for (uint32_t j = 0; j < 8; j++) h[j] = (cu + j < n_half) ? g_row[cu + j] : __float2half_rn(0.0f);
+                    v[q + u] = *reinterpret_cast<const uint4 *>(h);
                 }
             }
         }
+    }
+}
+template <uint32_t G>
+__device__ __forceinline__ void row_store(uint32_t t_a, const uint4 (&v)[4 * G], uint32_t n_half, uint32_t half_sel, uint32_t i0) {
 #pragma unroll
-        for (uint32_t ch = 0; ch < 4; ch++) {
-            const uint32_t c0 = 32 * (2 * (i0 + ch) + half_sel);
-            if (c0 < n_half) {
-                uint32_t pk[16];
+    for (uint32_t ch = 0; ch < G; ch++) {
+        const uint32_t c0 = 32 * (2 * (i0 + ch) + half_sel);
+        if (c0 < n_half) {
+            uint32_t pk[16];
 #pragma unroll
-                for (uint32_t q = 0; q < 4; q++) { pk[4 * q] = v[ch * 4 + q].x; pk[4 * q + 1] = v[ch * 4 + q].y; pk[4 * q + 2] = v[ch * 4 + q].z; pk[4 * q + 3] = v[ch * 4 + q].w; }
-                tmem_st16(t_a + c0 / 2, pk);
-            }
+            for (uint32_t q = 0; q < 4; q++) { pk[4 * q] = v[ch * 4 + q].x; pk[4 * q + 1] = v[ch * 4 + q].y; pk[4 * q + 2] = v[ch * 4 + q].z; pk[4 * q + 3] = v[ch * 4 + q].w; }
+            tmem_st16(t_a + c0 / 2, pk);
         }
+    }
+}
+// groups [i_begin, ...) of a row, loaded and stored in place
+template <uint32_t G>
+__device__ __forceinline__ void row_to_tmem(uint32_t t_a, const __half *__restrict__ g_row, uint32_t n_half, bool in_range, uint32_t half_sel, uint32_t i_begin = 0) {
+    for (uint32_t i0 = i_begin; 32 * (2 * i0 + half_sel) < n_half; i0 += G) {
+        uint4 v[4 * G];
+        row_load<G>(v, g_row, n_half, in_range, half_sel, i0);
+        row_store<G>(t_a, v, n_half, half_sel, i0);
     }
 }
 struct FwdP {
@@ -144,7 +162,7 @@ struct FwdP {
 // 256 threads: thread (r, hf) owns batch row r = tid & 127 of the tile and the 32-value chunks with chunk index % 2 == hf of
 // every row it touches (input staging, accumulator read-back, activation store) -- two warpgroups per chain halve the serial
 // epilogue of a layer and double the loads / stores in flight (TMEM allows only two 208-column chains per SM at hidden 128)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_wide_forward(const FwdP p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -169,10 +187,15 @@ k_wide_forward(const FwdP p) {
     const uint32_t tmem = s_tmem, t_row = tmem + (((warp & 3u) * 32u) << 16);
     const uint32_t t_acc = t_row, t_a = t_row + p.a_col;
     uint32_t parity = 0;
+    // the first 192 input values of a row (group 0: three chunks per thread) are loaded one tile ahead: issued before the wait for the previous tile's
+    // last layer, so their latency runs under that MMA and epilogue instead of in front of this tile's first MMA
+    uint4 nx[12];
+    row_load<3>(nx, p.inputs + (size_t)(blockIdx.x * kRows + r) * d.in_dim, d.in_pad, blockIdx.x * kRows + r < d.B, hf, 0);
     for (uint32_t tile = blockIdx.x; tile < d.n_tiles; tile += gridDim.x) {
         const uint32_t row = tile * kRows + r;
         const bool in_range = row < d.B;
-        row_to_tmem(t_a, p.inputs + (size_t)row * d.in_dim, d.in_pad, in_range, hf);
+        row_store<3>(t_a, nx, d.in_pad, hf, 0);
+        row_to_tmem<3>(t_a, p.inputs + (size_t)row * d.in_dim, d.in_pad, in_range, hf, 3);
         tmem_st_wait();
         for (uint32_t m = 0; m < n_mat; m++) {
             uint32_t r, c, pr; size_t g;
@@ -194,6 +217,10 @@ k_wide_forward(const FwdP p) {
                     mma_f16_ts_if(lead, tmem, tmem + p.a_col + 8 * k, desc_kmajor(wbase + (k >> 2) * tile_bytes, k & 3), idesc, k > 0);
                 mma_commit_if(lead, mbar);
             }
+            if (last) {
+                const uint32_t nrow = row + gridDim.x * kRows;      // (r is shadowed by the matrix shape here)
+                row_load<3>(nx, p.inputs + (size_t)nrow * d.in_dim, d.in_pad, tile + gridDim.x < d.n_tiles && nrow < d.B, hf, 0);
+            }
             mbar_wait(mbar, parity);
             parity ^= 1;
             fence_after_sync();
@@ -208,8 +235,11 @@ k_wide_forward(const FwdP p) {
                     tmem_st16(t_a + c0 / 2, pk);
                     if (fb) {
 #pragma unroll
-                        for (uint32_t q = 0; q < 4; q++)
-                            if (c0 + q * 8 < d.hidden) *reinterpret_cast<uint4 *>(fb + c0 + q * 8) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                        for (uint32_t q = 0; q < 4; q += 2) {
+                            const uint4 lo = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]), hi = make_uint4(pk[4 * q + 4], pk[4 * q + 5], pk[4 * q + 6], pk[4 * q + 7]);
+                            if (c0 + q * 8 + 16 <= d.hidden) stg_pair(fb + c0 + q * 8, lo, hi);
+                            else if (c0 + q * 8 < d.hidden) *reinterpret_cast<uint4 *>(fb + c0 + q * 8) = lo;
+                        }
                     }
                 }
                 tmem_st_wait();
@@ -223,8 +253,7 @@ k_wide_forward(const FwdP p) {
                             float w[16];
 #pragma unroll
                             for (int i = 0; i < 16; i++) w[i] = wact_fwd(d.out_act, v[i]);
-                            reinterpret_cast<uint4 *>(o)[0] = pack8(w);
-                            reinterpret_cast<uint4 *>(o)[1] = pack8(w + 8);
+                            stg_pair(o, pack8(w), pack8(w + 8));
                         } else {
                             for (uint32_t i = 0; i < 16 && c0 + i < d.out_dim; i++) o[i] = __float2half_rn(wact_fwd(d.out_act, v[i]));
                         }
@@ -238,6 +267,14 @@ k_wide_forward(const FwdP p) {
     if (warp == 0) tmem_dealloc(tmem, p.tmem_cols);
 }
 
+#ifdef S3D_WTRACE
+__device__ long long g_wtrace[4096];
+// tile index within the CTA (it), step, event -> clock64 of thread 0 / thread 128 (who = 0 / 1) of CTA 0
+#define S3D_WT(who_tid, it, step, ev) do { if (blockIdx.x == 0 && threadIdx.x == (who_tid) && (it) >= 2 && (it) < 6) g_wtrace[((((it) - 2) * 2 + ((who_tid) ? 1 : 0)) * 4 + (step)) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define S3D_WT(who_tid, it, step, ev) do { } while (0)
+#endif
+
 struct BwdP {
     const __half *grad, *weights, *forward_buffer;
     __half *backward_buffer, *grad_inputs;
@@ -248,7 +285,7 @@ struct BwdP {
 // data gradients, top down.  step s = 0: through W_out (K = out_pad, N = hidden); s = 1 .. n_hid: through hidden matrix
 // num_layers - s; s = n_hid + 1: through W_0 (N = in_dim), only for grad_inputs.  backward_buffer[s] = dL/d(pre-activation of
 // hidden activation num_layers-1-s) as in the narrow kernel (ffmlp.cu).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_wide_backward(const BwdP p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -274,11 +311,20 @@ k_wide_backward(const BwdP p) {
     const uint32_t t_acc = t_row, t_a = t_row + p.a_col;
     uint32_t parity = 0;
     const uint32_t n_steps = d.num_layers + (p.grad_inputs ? 1u : 0u);
-    for (uint32_t tile = blockIdx.x; tile < d.n_tiles; tile += gridDim.x) {
+    // Loads that do not depend on the running MMA are issued BEFORE its completion wait (the kernel was bound by exposed
+    // global-load latency: 2 CTAs x 8 warps per SM): the first 128 gradient values of the next tile's row during the last step,
+    // the activation row a step's ReLU mask needs while that step's MMA runs.
+    uint4 ng[8];
+    row_load<2>(ng, p.grad + (size_t)(blockIdx.x * kRows + r) * d.out_dim, d.out_dim, blockIdx.x * kRows + r < d.B, hf, 0);
+    uint32_t wt_it = 0;
+    for (uint32_t tile = blockIdx.x; tile < d.n_tiles; tile += gridDim.x, wt_it++) {
         const uint32_t row = tile * kRows + r;
         const bool in_range = row < d.B;
-        row_to_tmem(t_a, p.grad + (size_t)row * d.out_dim, d.out_dim, in_range, hf);
+        S3D_WT(0, wt_it, 3, 0);
+        row_store<2>(t_a, ng, d.out_dim, hf, 0);
+        row_to_tmem<2>(t_a, p.grad + (size_t)row * d.out_dim, d.out_dim, in_range, hf, 2);
         tmem_st_wait();
+        S3D_WT(0, wt_it, 3, 1);
         for (uint32_t s = 0; s < n_steps; s++) {
             const uint32_t m = d.num_layers - s;           // matrix the gradient flows through
             uint32_t r, c, pr; size_t g;
@@ -289,7 +335,9 @@ k_wide_backward(const BwdP p) {
                 load_w(smem, p.weights + g, r, c, pr);
                 fence_async_smem();
             }
+            S3D_WT(0, wt_it, s, 0); S3D_WT(128, wt_it, s, 0);
             sync_all();
+            S3D_WT(0, wt_it, s, 1); S3D_WT(128, wt_it, s, 1);
             const uint32_t K = pr;                          // rows of the matrix = width of the incoming gradient (padded)
             const uint32_t N = (m == 0) ? d.in_pad : d.hidden;
             if (warp == 0) {
@@ -300,23 +348,27 @@ k_wide_backward(const BwdP p) {
                     mma_f16_ts_if(lead, tmem, tmem + p.a_col + 8 * k, desc_mnmajor(wbase, k, tile_bytes), idesc, k > 0);
                 mma_commit_if(lead, mbar);
             }
+            S3D_WT(0, wt_it, s, 2);
+            // h = hidden activation m-1 (forward_buffer[m-1]); this thread's chunks, two at a time
+            const __half *h = m > 0 ? p.forward_buffer + ((size_t)(m - 1) * d.B + row) * d.hidden : nullptr;
+            uint4 hu[8];
+            if (m > 0) row_load<2>(hu, h, d.hidden, in_range, hf, 0);
+            if (s + 1 == n_steps) {
+                const uint32_t nrow = row + gridDim.x * kRows;      // (r is shadowed by the matrix shape here)
+                row_load<2>(ng, p.grad + (size_t)nrow * d.out_dim, d.out_dim, tile + gridDim.x < d.n_tiles && nrow < d.B, hf, 0);
+            }
+            S3D_WT(0, wt_it, s, 3); S3D_WT(128, wt_it, s, 3);
             mbar_wait(mbar, parity);
             parity ^= 1;
             fence_after_sync();
+            S3D_WT(0, wt_it, s, 4); S3D_WT(128, wt_it, s, 4);
             if (m > 0) {
-                // dA = D (.) act'(h), h = hidden activation m-1 (forward_buffer[m-1])
-                const __half *h = p.forward_buffer + ((size_t)(m - 1) * d.B + row) * d.hidden;
+                // dA = D (.) act'(h)
                 __half *bb = (p.backward_buffer && in_range) ? p.backward_buffer + ((size_t)s * d.B + row) * d.hidden : nullptr;
-                for (uint32_t i0 = 0; 32 * (2 * i0 + hf) < d.hidden; i0 += 4) {
-                    uint4 hu[16];        // this thread's chunks of the activation row, four at a time: all loads in flight before the accumulator is read
+                for (uint32_t i0 = 0; 32 * (2 * i0 + hf) < d.hidden; i0 += 2) {
+                    if (i0 > 0) row_load<2>(hu, h, d.hidden, in_range, hf, i0);
 #pragma unroll
-                    for (uint32_t q = 0; q < 16; q++) {
-                        hu[q] = make_uint4(0, 0, 0, 0);
-                        const uint32_t col = 32 * (2 * (i0 + q / 4) + hf) + (q & 3u) * 8;
-                        if (in_range && col < d.hidden) hu[q] = __ldg(reinterpret_cast<const uint4 *>(h + col));
-                    }
-#pragma unroll
-                    for (uint32_t ch = 0; ch < 4; ch++) {
+                    for (uint32_t ch = 0; ch < 2; ch++) {
                         const uint32_t c0 = 32 * (2 * (i0 + ch) + hf);
                         if (c0 < d.hidden) {
                             float v[32];
@@ -333,21 +385,24 @@ k_wide_backward(const BwdP p) {
                             tmem_st16(t_a + c0 / 2, pk);
                             if (bb) {
 #pragma unroll
-                                for (uint32_t q = 0; q < 4; q++)
-                                    if (c0 + q * 8 < d.hidden) *reinterpret_cast<uint4 *>(bb + c0 + q * 8) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                                for (uint32_t q = 0; q < 4; q += 2) {
+                                    const uint4 lo = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]), hi = make_uint4(pk[4 * q + 4], pk[4 * q + 5], pk[4 * q + 6], pk[4 * q + 7]);
+                                    if (c0 + q * 8 + 16 <= d.hidden) stg_pair(bb + c0 + q * 8, lo, hi);
+                                    else if (c0 + q * 8 < d.hidden) *reinterpret_cast<uint4 *>(bb + c0 + q * 8) = lo;
+                                }
                             }
                         }
                     }
                 }
                 tmem_st_wait();
+                S3D_WT(0, wt_it, s, 5); S3D_WT(128, wt_it, s, 5);
             } else {
                 for (uint32_t c0 = hf * 16; c0 < d.in_pad; c0 += 32) {
                     float v[16];
                     tmem_ld16(t_acc + c0, v);
                     if (in_range && c0 < d.in_dim) {
                         __half *o = p.grad_inputs + (size_t)row * d.in_dim + c0;
-                        reinterpret_cast<uint4 *>(o)[0] = pack8(v);
-                        reinterpret_cast<uint4 *>(o)[1] = pack8(v + 8);
+                        stg_pair(o, pack8(v), pack8(v + 8));
                     }
                 }
             }
@@ -452,6 +507,94 @@ k_wide_wgrad(const WgP p) {
     if (warp == 0) tmem_dealloc(tmem, p.tmem_cols);
 }
 
+// ---- the same split-K weight gradient as a cp.async pipeline -----------------------------------------------------------------
+// k_wide_wgrad stages a tile pair through registers and waits for it before every MMA group: with 2-3 CTAs per SM the global
+// loads were not deep enough to cover their latency (3 GEMMs of the 160-128-128-16 head: 0.59 ms against 0.29 ms of HBM time).
+// Here one CTA per SM keeps S stages of (dA tile, H tile) in shared memory; 16-byte cp.async copies land directly in the
+// swizzled operand layout (zero-filled outside the matrix), S - 1 tiles are in flight while the tensor core consumes one.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void stage_rows_async(uint32_t smem_addr, const __half *__restrict__ g, uint32_t ld, uint32_t n_rows, uint32_t n_cols,
+                                                 uint32_t row0, uint32_t col0, uint32_t blocks) {
+    const uint32_t total = blocks * kRows * 8;
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+        const uint32_t blk = i / (kRows * 8), rem = i - blk * kRows * 8, r = rem >> 3, c16 = rem & 7;
+        const uint32_t row = row0 + r, col = col0 + blk * 64 + c16 * 8;
+        const bool ok = row < n_rows && col < n_cols;      // n_cols is a multiple of 8 here: a chunk is inside or outside
+        cp_async16(smem_addr + blk * (kRows * 128) + sw128_off(r, c16), ok ? (const void *)(g + (size_t)row * ld + col) : (const void *)g, ok ? 16u : 0u);
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(256, 1)
+k_wide_wgrad_pipe(const WgP p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ uint32_t s_tmem;
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t tid = threadIdx.x, warp = warp_idx_sync();
+    const uint32_t mbar = smem_u32(&s_mbar);
+    if (warp == 0) tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
+    if (tid == 0) mbar_init(mbar, 1);
+    sync_all();
+    const uint32_t tmem = s_tmem, t_row = tmem + (((warp & 3u) * 32u) << 16);
+    const uint32_t r0 = blockIdx.x * 128, c_blocks = (p.C + 63) / 64, Npad = c_blocks * 64;
+    const uint32_t stage_bytes = (2 + c_blocks) * kRows * 128, base = smem_u32(smem);
+    const uint32_t n_my = blockIdx.y < p.n_tiles ? (p.n_tiles - blockIdx.y + gridDim.y - 1) / gridDim.y : 0;
+    auto stage = [&](uint32_t j) {     // tile j of this CTA -> stage j % S
+        const uint32_t a = base + (j % S) * stage_bytes, row0 = (blockIdx.y + j * gridDim.y) * kRows;
+        stage_rows_async(a, p.dA, p.ldA, p.B, p.R, row0, r0, 2);
+        stage_rows_async(a + 2 * kRows * 128, p.H, p.ldH, p.B, p.C, row0, 0, c_blocks);
+    };
+    for (uint32_t j = 0; j + 1 < S; j++) {
+        if (j < n_my) stage(j);
+        cp_async_commit();
+    }
+    uint32_t parity = 0;
+    for (uint32_t j = 0; j < n_my; j++) {
+        if (j > 0) {                    // the MMAs of tile j - 1 are done: its stage is the one refilled below
+            mbar_wait(mbar, parity);
+            parity ^= 1;
+            fence_after_sync();
+        }
+        if (j + S - 1 < n_my) stage(j + S - 1);
+        cp_async_commit();
+        cp_async_wait<S - 1>();         // this thread's copies of tile j have landed
+        fence_async_smem();
+        sync_all();                     // ... and everybody's
+        if (warp == 0) {
+            const bool lead = elect_one();
+            const uint32_t idesc = make_idesc(128, Npad, true, true);
+            const uint32_t a = base + (j % S) * stage_bytes;
+            for (uint32_t k = 0; k < kRows / 16; k++)
+                mma_f16_if(lead, tmem, desc_mnmajor(a, k, kRows * 128), desc_mnmajor(a + 2 * kRows * 128, k, kRows * 128), idesc, !(j == 0 && k == 0));
+            mma_commit_if(lead, mbar);
+        }
+    }
+    if (n_my > 0) {
+        mbar_wait(mbar, parity);
+        fence_after_sync();
+        const uint32_t rr = r0 + (tid & 127u);     // M = 128: accumulator row i lives in lane i
+        const uint32_t half = tid >> 7;            // column half handled by this warpgroup
+        for (uint32_t c0 = half * 32; c0 < Npad; c0 += 64) {
+            float v[32];
+            tmem_ld32(t_row + c0, v);
+            if (rr < p.R) {
+#pragma unroll
+                for (int i = 0; i < 32; i++)
+                    if (c0 + i < p.C) atomicAdd(p.gw + (size_t)rr * p.C + c0 + i, v[i]);
+            }
+        }
+    }
+    sync_all();
+    if (warp == 0) tmem_dealloc(tmem, p.tmem_cols);
+}
+
 __global__ void k_wide_f32_to_f16(const float *__restrict__ src, __half *__restrict__ dst, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = __float2half_rn(src[i]);
@@ -489,6 +632,10 @@ int sm_count_w() {
 }
 
 }  // namespace
+
+#ifdef S3D_WTRACE
+S3D_API int s3d_debug_wtrace(long long *host_out, int n) { return (int)cudaMemcpyFromSymbol(host_out, g_wtrace, (size_t)n * sizeof(long long)); }
+#endif
 
 // called by the s3d_ffmlp_* entry points of ffmlp.cu for hidden > 64 or output_dim > 16
 int s3d_ffmlp_wide_forward(const __half *inputs, const __half *weights, uint32_t B, uint32_t in_dim, uint32_t out_dim, uint32_t hidden,
@@ -555,6 +702,25 @@ int s3d_ffmlp_wide_backward(const __half *grad, const __half *inputs, const __ha
         }
         const uint32_t c_blocks = (w.C + 63) / 64;
         w.tmem_cols = pow2_cols(c_blocks * 64);
+        static const bool no_pipe = [] { const char *e = getenv("S3D_WGRAD_PIPE"); return e && e[0] == '0'; }();
+        if (!no_pipe && !((w.ldA | w.ldH | w.R | w.C) & 7u)) {
+            // cp.async pipeline: S stages of (2 + c_blocks) 16 KB tiles, one CTA per SM
+            const size_t stage_bytes = (size_t)(2 + c_blocks) * kRows * 128;
+            const int S = (int)min((size_t)4, (size_t)(200 * 1024) / stage_bytes);
+            if (S >= 2) {
+                const size_t smem_p = 1024 + S * stage_bytes;
+                const uint32_t m_blocks = div_up(w.R, 128u);
+                const dim3 grid(m_blocks, max(1u, min(w.n_tiles, (uint32_t)sms / m_blocks)));
+                auto launch = [&](auto kern) {
+                    cudaError_t ee = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
+                    if (ee == cudaSuccess) kern<<<grid, 256, smem_p, st>>>(w);
+                    return ee;
+                };
+                e = S == 2 ? launch(k_wide_wgrad_pipe<2>) : (S == 3 ? launch(k_wide_wgrad_pipe<3>) : launch(k_wide_wgrad_pipe<4>));
+                if (e != cudaSuccess) break;
+                continue;
+            }
+        }
         const size_t smem_w = 1024 + (size_t)(2 + c_blocks) * kRows * 128;
         e = cudaFuncSetAttribute(k_wide_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
         if (e != cudaSuccess) break;

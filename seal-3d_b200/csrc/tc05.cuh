@@ -205,6 +205,26 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar_addr) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar_addr) : "memory");
 }
+// ---- 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256) --------------------------------------------------------------
+// The MLP kernels own one matrix ROW per thread (TMEM lane = row), so a warp-wide access touches 32 different lines and costs 32
+// L1 wavefronts whatever its width: moving a row's contiguous bytes 32 at a time instead of 16 halves the wavefronts (the wide
+// FFMLP epilogues were bound by exactly that, see profiles/r2_experiments.md).  The address must be 32-byte aligned.
+__device__ __forceinline__ bool aligned32(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
+__device__ __forceinline__ void ldg256(const void *p, uint4 &a, uint4 &b) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256(void *p, const uint4 &a, const uint4 &b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+                 "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+// two adjacent 16-byte pieces of a row: one 256-bit store when the address allows it
+__device__ __forceinline__ void stg_pair(void *p, const uint4 &a, const uint4 &b) {
+    if (aligned32(p)) stg256(p, a, b);
+    else { reinterpret_cast<uint4 *>(p)[0] = a; reinterpret_cast<uint4 *>(p)[1] = b; }
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);

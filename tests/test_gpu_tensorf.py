@@ -125,6 +125,39 @@ def test_vm_backward_kernel_matches_oracle_double_accumulation():
             np.testing.assert_allclose(npy(grads[3 + i])[0, :, :, 0], gv[i], rtol=1e-4, atol=1e-5 * np.abs(gv[i]).max())
 
 
+def test_vm_lookup_fp16_io_is_the_fp32_lookup_rounded_once():
+    """s3d_vm_forward_f16 / _backward_f16 (the colour features of an fp16 step): the forward is bit for bit the fp32 lookup cast
+    to fp16 (what the reference's autocast basis_mat does to it, tensoRF/network.py:155); the backward with an fp16 output
+    gradient equals the fp32 kernel fed the same values"""
+    from seal3d_b200 import _lib
+    net = golden_net()
+    rng = np.random.default_rng(11)
+    M = 20000
+    x = to(rng.uniform(-1.02, 1.02, (M, 3)).astype(np.float32))
+    mats, vecs = net.color_mat, net.color_vec
+    R = mats[0].shape[1]
+    dims = _lib.host_i32([[m.shape[2], m.shape[3], v.shape[2]] for m, v in zip(mats, vecs)])
+    out32 = torch.empty(M, 3 * R, device=dev())
+    out16 = torch.empty(M, 3 * R, device=dev(), dtype=torch.float16)
+    _lib.call("s3d_vm_forward", x, M, None, *mats, *vecs, dims[1], R, 0, out32)
+    _lib.call("s3d_vm_forward_f16", x, M, None, *mats, *vecs, dims[1], R, out16)
+    assert torch.equal(out16, out32.half())
+    g16 = to(rng.normal(size=(M, 3 * R)).astype(np.float32)).half()
+    ga = [torch.zeros_like(p) for p in list(mats) + list(vecs)]
+    gb = [torch.zeros_like(p) for p in list(mats) + list(vecs)]
+    _lib.call("s3d_vm_backward", x, M, None, *mats, *vecs, dims[1], R, 0, g16.float(), *ga)
+    _lib.call("s3d_vm_backward_f16", x, M, None, *mats, *vecs, dims[1], R, g16, *gb)
+    for a, b in zip(ga, gb):
+        assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max())      # same products, atomics in a different order
+    # through the module: "half" output + fp16 upstream gradient
+    out = net._lookup(x, mats, vecs, "half")
+    assert out.dtype == torch.float16 and torch.equal(out, out16)
+    net.zero_grad(set_to_none=True)
+    out.backward(g16)
+    for p, a in zip(list(mats) + list(vecs), ga):
+        assert float((p.grad - a).abs().max()) <= 1e-5 * float(a.abs().max())
+
+
 def test_out_of_box_and_argument_errors():
     from seal3d_b200 import _lib
     net = golden_net()
