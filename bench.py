@@ -323,6 +323,7 @@ ALGO_BYTES = {
     "s3d_grid_encode_backward": ("k_grid_backward", 12 + 16 * 8 * 4 + 64),
 }
 ALGO_BYTES_ALT = {"s3d_ngp_scatter": ("achieved_fp32_entries", 12 + 128 + 16 * 8 * 16)}
+RED_RATE_PEAK_G = 149.0     # measured: random global reductions per second (1e9) on one B200, independent of their width
 
 
 def whole_step_roofline(n_rays, samples_per_step, rays_per_s_per_gpu):
@@ -529,6 +530,15 @@ def gpu_arm(args):
     r = timed_legs(tr, resident, host, args, rank, world, dev, pipelined, profile_hook=(prof_begin, prof_end))
     if rank != 0:
         return None
+    red = None
+    if args.engine == "fused" and not args.no_roofline:
+        # the scatter's real unit of work: global reductions per launch (the same run detection as the kernel, counted by
+        # s3d_ngp_scatter_count on one batch marched like the step marches it; no collective, rank 0 only)
+        xyzs = tr._march(resident[0][0], resident[0][1], True, False)[0]
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        S = tr.S
+        _lib.call("s3d_ngp_scatter_count", xyzs, xyzs.shape[0], S.bound, S.offsets, S.L, S.S, S.H, cnt)
+        red = (int(cnt.item()), int(xyzs.shape[0]))
     ms, ms_e2e, samples_per_step, last, breakdown = r["ms"], r["ms_e2e"], r["samples_per_step"], r["last"], r["breakdown"]
     rays_total = n * world * args.steps
     line = {
@@ -548,6 +558,14 @@ def gpu_arm(args):
     if breakdown:
         line["kernel_breakdown_ms_per_step"] = {k: round(v["ms_per_step"], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms_per_step"])}
         line["roofline"] = step_roofline(breakdown, samples_per_step, ms / args.steps)
+        if red and line["roofline"].get("kernel") == "k_ngp_scatter":
+            n_red = red[0] * samples_per_step / red[1]
+            ach = n_red / (line["roofline"]["launch_ms"] * 1e-3) / 1e9
+            line["roofline"]["reduction_rate"] = {
+                "reductions_per_sample": red[0] / red[1], "reductions_per_launch": n_red, "achieved": ach, "peak": RED_RATE_PEAK_G, "unit": "G reductions/s",
+                "frac": ach / RED_RATE_PEAK_G,
+                "peak_source": "scripts/r2/red_micro.cu on a B200 (profiles/r2_red_rate_micro_run30.log): random RED.32 / .64 / .128 / f16x2 into a "
+                               "98 MB table all retire 149 G/s -- the L2 reduction rate, not bytes, bounds this kernel (its table stays in L2)"}
     return line
 
 

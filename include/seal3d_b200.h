@@ -307,6 +307,9 @@ int s3d_ngp_mlp_backward_fixed(const void *feats, const float *dirs, uint32_t M,
                                void *dfeats, float out_scale, long long *gw_s0, long long *gw_s1, long long *gw_c0, long long *gw_c1,
                                long long *gw_c2, int train_mlp, uint32_t *nonfinite, void *stream);
 int s3d_fixed_to_float(long long *fixed, float *grad, size_t n, uint32_t *nonfinite, void *stream);
+/* measurement aid: *count (device, 64-bit) += the number of global reductions s3d_ngp_scatter issues for these samples */
+int s3d_ngp_scatter_count(const float *xyz, uint32_t M, float bound, const int *offsets, uint32_t L, float S, uint32_t H,
+                          unsigned long long *count, void *stream);
 int s3d_ngp_adam_tables(float *table_sigma, float *table_color, float *grad4, float *exp_avg4, float *exp_avg_sq4, void *shadow,
                         uint32_t shadow_stride, uint64_t n_entries, float lr, float beta1, float beta2, float eps, uint32_t step,
                         float grad_scale, const float *scaler_state, void *stream);

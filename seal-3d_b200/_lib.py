@@ -76,6 +76,7 @@ _SIGS = {
     "s3d_ngp_scatter_fixed": [P, P, U32, F32, P, P, U32, F32, U32, F32, P],
     "s3d_ngp_mlp_backward_fixed": [P, P, U32, P, P, P, P, P, F32, P, P, P, F32, P, P, P, P, P, I32, P],
     "s3d_fixed_to_float": [P, P, U64, P],
+    "s3d_ngp_scatter_count": [P, U32, F32, P, U32, F32, U32, P],
     "s3d_ngp_adam_tables": [P, P, P, P, P, P, U32, U64, F32, F32, F32, F32, U32, F32, P],
     "s3d_vm_forward": [P, U32, P, P, P, P, P, P, P, P, U32, I32, P],
     "s3d_vm_backward": [P, U32, P, P, P, P, P, P, P, P, U32, I32, P, P, P, P, P, P, P],

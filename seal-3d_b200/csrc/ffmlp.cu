@@ -77,13 +77,19 @@ __device__ void load_matrix_sw128(uint8_t *smem, const __half *__restrict__ g, u
 // thread `row` loads its batch row (cols halves, zero padded to 64*blocks) into the activation tile(s)
 __device__ __forceinline__ void load_row_sw128(uint8_t *tile, const __half *__restrict__ g_row, uint32_t row, uint32_t cols,
                                                uint32_t blocks, bool in_range) {
+    const bool wide = aligned32(g_row);      // 256-bit loads: a row-per-thread access costs 32 L1 wavefronts whatever its width
     for (uint32_t blk = 0; blk < blocks; blk++) {
 #pragma unroll
-        for (uint32_t c16 = 0; c16 < 8; c16++) {
+        for (uint32_t c16 = 0; c16 < 8; c16 += 2) {
             const uint32_t col = blk * 64 + c16 * 8;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (in_range && col < cols) v = __ldg(reinterpret_cast<const uint4 *>(g_row + col));
+            uint4 v = make_uint4(0, 0, 0, 0), w = v;
+            if (in_range && wide && col + 16 <= cols) ldg256(g_row + col, v, w);
+            else {
+                if (in_range && col < cols) v = __ldg(reinterpret_cast<const uint4 *>(g_row + col));
+                if (in_range && col + 8 < cols) w = __ldg(reinterpret_cast<const uint4 *>(g_row + col + 8));
+            }
             *reinterpret_cast<uint4 *>(tile + blk * kTileBytes + sw128_off(row, c16)) = v;
+            *reinterpret_cast<uint4 *>(tile + blk * kTileBytes + sw128_off(row, c16 + 1)) = w;
         }
     }
 }
@@ -166,11 +172,15 @@ k_ffmlp_forward(const FwdParams p) {
 #pragma unroll
                 for (int i = 0; i < 32; i++) v[i] = act_fwd(p.act, v[i]);
 #pragma unroll
-                for (uint32_t q = 0; q < 4; q++) {
+                for (uint32_t q = 0; q < 4; q += 2) {
                     const uint32_t c16 = half * 4 + q;
-                    const uint4 u = pack8(v + q * 8);
+                    const uint4 u = pack8(v + q * 8), u2 = pack8(v + q * 8 + 8);
                     *reinterpret_cast<uint4 *>(tA + sw128_off(tid, c16)) = u;
-                    if (fb && in_range && c16 * 8 < p.hidden) *reinterpret_cast<uint4 *>(fb + c16 * 8) = u;
+                    *reinterpret_cast<uint4 *>(tA + sw128_off(tid, c16 + 1)) = u2;
+                    if (fb && in_range) {
+                        if (c16 * 8 + 16 <= p.hidden) stg_pair(fb + c16 * 8, u, u2);
+                        else if (c16 * 8 < p.hidden) *reinterpret_cast<uint4 *>(fb + c16 * 8) = u;
+                    }
                 }
             }
             fence_async_smem();
@@ -182,8 +192,7 @@ k_ffmlp_forward(const FwdParams p) {
             if (in_range) {
                 __half *o = p.outputs + (size_t)row * p.out_dim;
                 if (p.out_dim == 16) {
-                    reinterpret_cast<uint4 *>(o)[0] = pack8(v);
-                    reinterpret_cast<uint4 *>(o)[1] = pack8(v + 8);
+                    stg_pair(o, pack8(v), pack8(v + 8));
                 } else {
                     for (uint32_t i = 0; i < p.out_dim; i++) o[i] = __float2half_rn(v[i]);
                 }
@@ -303,15 +312,22 @@ k_ffmlp_backward(const BwdParams p) {
                     float v[32];
                     tmem_ld32(t_row + half * 32, v);
 #pragma unroll
-                    for (uint32_t q = 0; q < 4; q++) {
+                    for (uint32_t q = 0; q < 4; q += 2) {
                         const uint32_t c16 = half * 4 + q;
-                        float h[8];
-                        unpack8(*reinterpret_cast<const uint4 *>(tH + sw128_off(tid, c16)), h);
+                        uint4 u[2];
 #pragma unroll
-                        for (int i = 0; i < 8; i++) v[q * 8 + i] *= act_bwd(p.act, h[i]);
-                        const uint4 u = pack8(v + q * 8);
-                        *reinterpret_cast<uint4 *>(tD + sw128_off(tid, c16)) = u;
-                        if (bb && in_range && c16 * 8 < p.hidden) *reinterpret_cast<uint4 *>(bb + c16 * 8) = u;
+                        for (uint32_t e = 0; e < 2; e++) {
+                            float h[8];
+                            unpack8(*reinterpret_cast<const uint4 *>(tH + sw128_off(tid, c16 + e)), h);
+#pragma unroll
+                            for (int i = 0; i < 8; i++) v[(q + e) * 8 + i] *= act_bwd(p.act, h[i]);
+                            u[e] = pack8(v + (q + e) * 8);
+                            *reinterpret_cast<uint4 *>(tD + sw128_off(tid, c16 + e)) = u[e];
+                        }
+                        if (bb && in_range) {
+                            if (c16 * 8 + 16 <= p.hidden) stg_pair(bb + c16 * 8, u[0], u[1]);
+                            else if (c16 * 8 < p.hidden) *reinterpret_cast<uint4 *>(bb + c16 * 8) = u[0];
+                        }
                     }
                 }
                 // next forward activation: h_{k-1}, or the network inputs for the last step
@@ -341,9 +357,11 @@ k_ffmlp_backward(const BwdParams p) {
                         float v[32];
                         tmem_ld32(t_row + half * 32, v);
 #pragma unroll
-                        for (uint32_t q = 0; q < 4; q++) {
+                        for (uint32_t q = 0; q < 4; q += 2) {
                             const uint32_t col = blk * 64 + (half * 4 + q) * 8;
-                            if (in_range && col < p.in_dim) *reinterpret_cast<uint4 *>(p.grad_inputs + (size_t)row * p.in_dim + col) = pack8(v + q * 8);
+                            __half *o = p.grad_inputs + (size_t)row * p.in_dim + col;
+                            if (in_range && col + 16 <= p.in_dim) stg_pair(o, pack8(v + q * 8), pack8(v + q * 8 + 8));
+                            else if (in_range && col < p.in_dim) *reinterpret_cast<uint4 *>(o) = pack8(v + q * 8);
                         }
                     }
                 }

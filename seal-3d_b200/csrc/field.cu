@@ -335,12 +335,23 @@ k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, 
     if (i < M) ok = load_unit(xyz, i, bound, ux, uy, uz);
     const uint32_t lane = lane_id();
     const uint4 *row = reinterpret_cast<const uint4 *>(dfeats + (size_t)(i < M ? i : 0) * 64);
+    const bool wide = aligned32(row);
+    // gradient rows of an aligned PAIR of groups: one 256-bit load per table (row-per-thread accesses cost 32 L1 wavefronts per
+    // instruction whatever their width)
+    uint4 rs_lo = make_uint4(0, 0, 0, 0), rs_hi = rs_lo, rc_lo = rs_lo, rc_hi = rs_lo;
     for (uint32_t grp = grp_begin; grp < grp_end; grp++) {   // 4 levels per group; a launch may cover a sub-range (s3d_ngp_scatter_levels)
         // gradient rows of the group's 4 levels: one half2 per (level, table), kept packed -- the level loop is NOT unrolled:
         // unrolled, the kernel is ~3900 instructions (63 KB) and ncu shows 16 % of its stall samples on instruction fetch
         // (2.24 ms per 5.35 M samples); with one level per iteration it is ~1250 instructions and takes 2.03 ms
-        uint4 rs = make_uint4(0, 0, 0, 0), rc = rs;
-        if (ok) { rs = __ldg(row + grp); rc = __ldg(row + 4 + grp); }
+        const bool odd = grp & 1u;
+        if (ok) {
+            if (wide && !odd && grp + 1 < grp_end) { ldg256(row + grp, rs_lo, rs_hi); ldg256(row + 4 + grp, rc_lo, rc_hi); }
+            else if (!wide || !odd || grp == grp_begin) {
+                const uint4 a = __ldg(row + grp), b = __ldg(row + 4 + grp);
+                if (odd) { rs_hi = a; rc_hi = b; } else { rs_lo = a; rc_lo = b; }
+            }
+        }
+        const uint4 rs = odd ? rs_hi : rs_lo, rc = odd ? rc_hi : rc_lo;
 #pragma unroll 1
         for (uint32_t q = 0; q < 4; q++) {
             const uint32_t l = grp * 4 + q;
@@ -352,6 +363,32 @@ k_ngp_scatter(const float *__restrict__ xyz, const __half *__restrict__ dfeats, 
             scatter_level<FIXED>(g, l, ok, ux, uy, uz, g0, g1, g2, g3, lane, grad4, nonfinite);
         }
     }
+}
+
+// How many reductions k_ngp_scatter issues for a batch (same run detection, nothing written): the kernel's real unit of work.
+// B200 retires ~149 G random global reductions per second whatever their width (scripts/r2/red_micro.cu), so
+// reductions / time against that rate is the roofline that actually bounds the scatter.
+__global__ void __launch_bounds__(256)
+k_ngp_scatter_count(const float *__restrict__ xyz, uint32_t M, float bound, const int *__restrict__ offsets, uint32_t L, float S, uint32_t H,
+                    unsigned long long *__restrict__ count) {
+    __shared__ Geo g;
+    geo_init(g, offsets, L, S, H);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float ux = 0, uy = 0, uz = 0;
+    bool ok = false;
+    if (i < M) ok = load_unit(xyz, i, bound, ux, uy, uz);
+    const uint32_t lane = lane_id();
+    uint32_t n = 0;
+    for (uint32_t l = 0; l < L; l++) {
+        Cell c;
+        unsigned long long key = ~0ull;
+        if (ok) locate(g, l, ux, uy, uz, c, &key);
+        const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool head = (lane == 0) || (prev != key);
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        n += 8u * __popc(__ballot_sync(0xffffffffu, ok && (head || __popc(heads) > 16)));
+    }
+    if (lane == 0 && n) atomicAdd(count, (unsigned long long)n);
 }
 
 // fixed-point arena -> fp32 gradient arena (accumulated into), arena cleared; *nonfinite -> NaN in grad[0]
@@ -429,6 +466,9 @@ struct FeatPre {
     uint4 f[4];
     __device__ __forceinline__ void load(const __half *__restrict__ feats, uint32_t row_g, uint32_t hf, bool in_range) {
         const uint4 *src = reinterpret_cast<const uint4 *>(feats + (size_t)row_g * 64) + hf * 4;
+        // a thread's half row is 64 contiguous bytes: two 256-bit loads (a row-per-thread access costs one L1 wavefront per lane
+        // whatever its width)
+        if (in_range && aligned32(src)) { ldg256(src, f[0], f[1]); ldg256(src + 2, f[2], f[3]); return; }
 #pragma unroll
         for (uint32_t q = 0; q < 4; q++) f[q] = in_range ? __ldg(src + q) : make_uint4(0, 0, 0, 0);
     }
@@ -1245,7 +1285,7 @@ k_ngp_mlp_bwd(const BwdArgs a) {
 #pragma unroll
                         for (int i = 0; i < 32; i++) dfc[i] *= a.out_scale;
 #pragma unroll
-                        for (uint32_t q = 0; q < 4; q++) dst[q] = pack8(dfc + q * 8);
+                        for (uint32_t q = 0; q < 4; q += 2) stg_pair(dst + q, pack8(dfc + q * 8), pack8(dfc + q * 8 + 8));
                     }
                     isW.wait();
                     zero_half_row(bX, r, 1);
@@ -1277,7 +1317,7 @@ k_ngp_mlp_bwd(const BwdArgs a) {
 #pragma unroll
                         for (int i = 0; i < 32; i++) dfs[i] *= a.out_scale;
 #pragma unroll
-                        for (uint32_t q = 0; q < 4; q++) dst[q] = pack8(dfs + q * 8);
+                        for (uint32_t q = 0; q < 4; q += 2) stg_pair(dst + q, pack8(dfs + q * 8), pack8(dfs + q * 8 + 8));
                     }
                 }
             }
@@ -1443,6 +1483,16 @@ S3D_API int s3d_ngp_scatter_fixed(const float *xyz, const void *dfeats, uint32_t
     if (!fixed4 || !nonfinite) return S3D_EINVAL;
     k_ngp_scatter<true><<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)fixed4, offsets, L, S, H, grad_scale, 0, 4,
                                                                           nonfinite);
+    S3D_RETURN_LAST();
+}
+
+// *count (device, 64-bit) += the number of global reductions s3d_ngp_scatter issues for these samples (measurement aid)
+S3D_API int s3d_ngp_scatter_count(const float *xyz, uint32_t M, float bound, const int *offsets, uint32_t L, float S, uint32_t H,
+                                  unsigned long long *count, void *stream) {
+    if (M == 0) return 0;
+    if (L > kMaxLevels) return S3D_ENOTSUP;
+    if (!count) return S3D_EINVAL;
+    k_ngp_scatter_count<<<div_up(M, 256u), 256, 0, as_stream(stream)>>>(xyz, M, bound, offsets, L, S, H, count);
     S3D_RETURN_LAST();
 }
 

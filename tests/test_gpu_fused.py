@@ -653,3 +653,29 @@ def test_deterministic_trainer_runs_end_with_the_same_bits(scene):
     assert torch.equal(s1.density_bitfield, s2.density_bitfield)
     s3, tr3, l3 = run(False)
     np.testing.assert_allclose(l1, l3, rtol=2e-2)
+
+
+def test_scatter_reduction_count(scene):
+    """s3d_ngp_scatter_count = the number of global reductions the scatter issues (bench.py's reduction-rate roofline): a warp of
+    identical points folds into one run per level (8 corner reductions), scattered random points share nothing at any level
+    (16 levels x 8 corners each), out-of-range points issue none"""
+    from seal3d_b200 import _lib
+    offsets, pls = scene["synth"].grid_offsets()
+    off = to(offsets)
+    S = float(np.log2(pls))
+
+    def count(x):
+        c = torch.zeros(1, dtype=torch.int64, device=dev())
+        _lib.call("s3d_ngp_scatter_count", to(x.astype(np.float32)), x.shape[0], 1.0, off, 16, S, 16, c)
+        return int(c.item())
+
+    same = np.tile(np.array([[0.123, -0.456, 0.789]]), (64, 1))
+    assert count(same) == 2 * 16 * 8
+    rng = np.random.default_rng(0)
+    far = rng.uniform(-0.99, 0.99, (4096, 3))
+    n = count(far)
+    assert 0.9 * 4096 * 128 < n <= 4096 * 128          # random points: (nearly) no two neighbouring lanes in one cell, even at level 0
+    assert count(np.full((100, 3), 1.5)) == 0
+    x0, _, _, _, M = _samples(scene, 256)
+    per_sample = count(x0) / x0.shape[0]
+    assert 40 < per_sample < 100                       # ray-ordered samples: the coarse levels fold (about 60 per sample instead of 128)
