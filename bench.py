@@ -141,6 +141,101 @@ def cpu_arm(n_rays, steps, warmup):
 # ------------------------------------------------------------------------------------------ clocks
 
 
+_SAMPLER_CHILD = r"""
+import json, select, sys, time
+import pynvml as nv
+nv.nvmlInit()
+key = sys.argv[1]
+try:
+    h = nv.nvmlDeviceGetHandleByUUID(key if key.startswith("GPU-") else "GPU-" + key)
+except Exception:
+    h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[2]))
+mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+print("ready", flush=True)
+on, sm, reasons = False, [], set()
+while True:
+    r, _, _ = select.select([sys.stdin], [], [], 0.005)
+    if r:
+        line = sys.stdin.readline().strip()
+        if line == "start":
+            on, sm, reasons = True, [], set()
+        elif line == "stop":
+            on = False
+            print(json.dumps({"sm": sm, "mx": mx, "reasons": sorted(reasons)}), flush=True)
+        elif line in ("quit", ""):
+            break
+    if on:
+        try:
+            sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for bit, name in BITS.items():
+                if mask & bit:
+                    reasons.add(name)
+        except Exception:
+            pass
+"""
+
+
+class ClockSamplerProcess:
+    """The same NVML counters as ClockSampler, polled every 5 ms by a HELPER PROCESS: NVML calls made from the training process
+    itself contend with its kernel launches on the driver's locks -- on 8 GPUs rank 0's in-process sampler cost the whole job
+    4 % of the leg it ran in (every rank waits for the slowest at the step's barriers).  The helper is started early (NVML
+    initialisation takes a few hundred ms) and told over a pipe when the timed region starts and stops."""
+
+    def __init__(self, gpu_index):
+        import torch
+        self.p = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+            self.p = subprocess.Popen([sys.executable, "-c", _SAMPLER_CHILD, uuid, str(gpu_index)], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True, bufsize=1)
+            import select
+            r, _, _ = select.select([self.p.stdout], [], [], 20.0)
+            if not r or self.p.stdout.readline().strip() != "ready":
+                raise RuntimeError("sampler helper did not start")
+        except Exception:
+            self.close()
+            self.p = None
+
+    def ok(self):
+        return self.p is not None
+
+    def start(self):
+        self.p.stdin.write("start\n")
+        self.p.stdin.flush()
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        try:
+            self.p.stdin.write("stop\n")
+            self.p.stdin.flush()
+            d = json.loads(self.p.stdout.readline())
+            if d["sm"]:
+                out.update(sm_mhz=float(np.median(d["sm"])), sm_max_mhz=d["mx"], reasons=d["reasons"], samples=len(d["sm"]), source="nvml (helper process)")
+        except Exception:
+            pass
+        self.close()
+        return out
+
+    def close(self):
+        if self.p is not None:
+            try:
+                self.p.stdin.write("quit\n")
+                self.p.stdin.flush()
+                self.p.wait(2)
+            except Exception:
+                try:
+                    self.p.kill()
+                except Exception:
+                    pass
+            self.p = None
+
+
 class ClockSampler:
     """SM clock + clock-event (throttle) reasons of one GPU, sampled DURING the timed region: NVML in a thread (the same
     counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; an nvidia-smi process per sample is too slow
@@ -405,12 +500,13 @@ class _Timer:
         return self.e0.elapsed_time(self.e1) if self.cuda else 1e3 * (self.t1 - self.t0)
 
 
-def timed_legs(tr, resident, host, args, rank, world, dev, pipelined, profile_hook=None):
+def timed_legs(tr, resident, host, args, rank, world, dev, pipelined, profile_hook=None, helper=None):
     """Everything of the GPU arm that happens after the world is built: warm-up, leg 1 (resident inputs), leg 2 (end to end),
     the per-kernel breakdown.  EVERY rank executes EVERY trainer step in here -- each step contains the gradient all-reduce,
     so a step taken by a subset of the ranks is an unmatched collective (the round-1 driver runs at N = 2, 4, 8 hung on
     exactly that).  `tr` needs distill_step(o, d, perturb=, force_all_rays=, prefetch=) -> loss tensor, refresh_occupancy(),
-    student.mean_count and student.step_counter; `profile_hook` = (begin(), end() -> [(name, ms)]) around the breakdown steps."""
+    student.mean_count and student.step_counter; `profile_hook` = (begin(), end() -> [(name, ms)]) around the breakdown steps;
+    `helper` = rank 0's ClockSamplerProcess (started by the caller well before the timed region)."""
     import torch
     import torch.distributed as dist
     from seal3d_b200 import parallel
@@ -443,7 +539,13 @@ def timed_legs(tr, resident, host, args, rank, world, dev, pipelined, profile_ho
     # rank 0 samples its GPU's clocks during the timed region (the line reports that GPU).  The other ranks do not: eight
     # processes polling NVML at once contend on the driver's global lock and slow every rank's kernel launches -- measured on
     # 8 GPUs as 7.78 ms/step in this leg against 7.18 in the next one, which has no sampler
-    clocks = ClockSampler(dev.index) if (dev.type == "cuda" and rank == 0) else None
+    clocks = None
+    if dev.type == "cuda" and rank == 0:
+        if helper is not None and helper.ok():
+            helper.start()
+            clocks = helper
+        else:
+            clocks = ClockSampler(dev.index)
     from seal3d_b200 import _lib
     launches0 = _lib.LAUNCHES
     tm = _Timer(dev)
@@ -527,7 +629,12 @@ def gpu_arm(args):
         _lib.PROFILE = None
         return rows
 
-    r = timed_legs(tr, resident, host, args, rank, world, dev, pipelined, profile_hook=(prof_begin, prof_end))
+    helper = ClockSamplerProcess(dev.index) if rank == 0 else None
+    try:
+        r = timed_legs(tr, resident, host, args, rank, world, dev, pipelined, profile_hook=(prof_begin, prof_end), helper=helper)
+    finally:
+        if helper is not None:
+            helper.close()
     if rank != 0:
         return None
     red = None
@@ -535,10 +642,10 @@ def gpu_arm(args):
         # the scatter's real unit of work: global reductions per launch (the same run detection as the kernel, counted by
         # s3d_ngp_scatter_count on one batch marched like the step marches it; no collective, rank 0 only)
         xyzs = tr._march(resident[0][0], resident[0][1], True, False)[0]
-        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        cnt = torch.zeros(2, dtype=torch.int64, device=dev)
         S = tr.S
         _lib.call("s3d_ngp_scatter_count", xyzs, xyzs.shape[0], S.bound, S.offsets, S.L, S.S, S.H, cnt)
-        red = (int(cnt.item()), int(xyzs.shape[0]))
+        red = (int(cnt[0].item()), int(xyzs.shape[0]), int(cnt[1].item()))
     ms, ms_e2e, samples_per_step, last, breakdown = r["ms"], r["ms_e2e"], r["samples_per_step"], r["last"], r["breakdown"]
     rays_total = n * world * args.steps
     line = {
@@ -559,13 +666,17 @@ def gpu_arm(args):
         line["kernel_breakdown_ms_per_step"] = {k: round(v["ms_per_step"], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms_per_step"])}
         line["roofline"] = step_roofline(breakdown, samples_per_step, ms / args.steps)
         if red and line["roofline"].get("kernel") == "k_ngp_scatter":
-            n_red = red[0] * samples_per_step / red[1]
-            ach = n_red / (line["roofline"]["launch_ms"] * 1e-3) / 1e9
+            n_red, n_hashed = red[0] * samples_per_step / red[1], red[2] * samples_per_step / red[1]
+            launch_s = line["roofline"]["launch_ms"] * 1e-3
+            floor_ms = n_hashed / (RED_RATE_PEAK_G * 1e9) * 1e3
             line["roofline"]["reduction_rate"] = {
-                "reductions_per_sample": red[0] / red[1], "reductions_per_launch": n_red, "achieved": ach, "peak": RED_RATE_PEAK_G, "unit": "G reductions/s",
-                "frac": ach / RED_RATE_PEAK_G,
-                "peak_source": "scripts/r2/red_micro.cu on a B200 (profiles/r2_red_rate_micro_run30.log): random RED.32 / .64 / .128 / f16x2 into a "
-                               "98 MB table all retire 149 G/s -- the L2 reduction rate, not bytes, bounds this kernel (its table stays in L2)"}
+                "reductions_per_sample": red[0] / red[1], "hashed_level_reductions_per_sample": red[2] / red[1],
+                "achieved": n_red / launch_s / 1e9, "unit": "G reductions/s", "random_address_rate": RED_RATE_PEAK_G,
+                "random_reductions_floor_ms": floor_ms, "frac_of_launch_at_that_floor": floor_ms / line["roofline"]["launch_ms"],
+                "note": "B200 retires 149 G global reductions per second to random addresses whatever their width (scripts/r2/red_micro.cu, "
+                        "profiles/r2_red_rate_micro_run30.log: RED.32 / .64 / .128 / f16x2 into a 98 MB table); the reductions of the hashed levels "
+                        "are such addresses, so their count / that rate is a floor for this kernel that no byte-saving can lower (its table stays in "
+                        "L2); dense-level reductions of a warp share lines and are cheaper"}
     return line
 
 

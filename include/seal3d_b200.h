@@ -307,12 +307,22 @@ int s3d_ngp_mlp_backward_fixed(const void *feats, const float *dirs, uint32_t M,
                                void *dfeats, float out_scale, long long *gw_s0, long long *gw_s1, long long *gw_c0, long long *gw_c1,
                                long long *gw_c2, int train_mlp, uint32_t *nonfinite, void *stream);
 int s3d_fixed_to_float(long long *fixed, float *grad, size_t n, uint32_t *nonfinite, void *stream);
-/* measurement aid: *count (device, 64-bit) += the number of global reductions s3d_ngp_scatter issues for these samples */
+/* measurement aid: count[0] += the number of global reductions s3d_ngp_scatter issues for these samples, count[1] += those on
+ * hashed levels (pseudo-random addresses); device, 64-bit each */
 int s3d_ngp_scatter_count(const float *xyz, uint32_t M, float bound, const int *offsets, uint32_t L, float S, uint32_t H,
                           unsigned long long *count, void *stream);
 int s3d_ngp_adam_tables(float *table_sigma, float *table_color, float *grad4, float *exp_avg4, float *exp_avg_sq4, void *shadow,
                         uint32_t shadow_stride, uint64_t n_entries, float lr, float beta1, float beta2, float eps, uint32_t step,
                         float grad_scale, const float *scaler_state, void *stream);
+/* Data parallel over NVLink peer memory (new functionality: the reference's DDP path, nerf/utils.py:330-332, 940-954, is dead code):
+ * this rank's shard [entry_begin, entry_end) of the tables is reduced over the `world` gradient arenas in array order, stepped
+ * with Adam and written to every rank's fp32 tables and fp16 shadows in one launch.  *_peers are HOST arrays of `world` device
+ * pointers (peer-mapped, e.g. from a symmetric-memory rendezvous), the same order on every rank; the caller brackets the launch
+ * with cross-rank barriers and clears its own arena afterwards.  s3d_peer_sum: out = sum of the ranks' vectors, array order. */
+int s3d_ngp_peer_adam_tables(const void *const *grad4_peers, void *const *sigma_peers, void *const *color_peers, void *const *shadow_peers,
+                             uint32_t world, uint32_t rank, float *exp_avg4, float *exp_avg_sq4, uint32_t shadow_stride, uint64_t entry_begin,
+                             uint64_t entry_end, float lr, float beta1, float beta2, float eps, uint32_t step, float grad_scale, void *stream);
+int s3d_peer_sum(const void *const *src_peers, uint32_t world, float *out, uint64_t n, void *stream);
 
 /* ------------------------------------------------------------------ TensoRF VM field */
 /* The reference has no extension here: tensoRF/network.py:99-151 issues twelve F.grid_sample(bilinear, zeros,

@@ -77,6 +77,8 @@ _SIGS = {
     "s3d_ngp_mlp_backward_fixed": [P, P, U32, P, P, P, P, P, F32, P, P, P, F32, P, P, P, P, P, I32, P],
     "s3d_fixed_to_float": [P, P, U64, P],
     "s3d_ngp_scatter_count": [P, U32, F32, P, U32, F32, U32, P],
+    "s3d_ngp_peer_adam_tables": [P, P, P, P, U32, U32, P, P, U32, U64, U64, F32, F32, F32, F32, U32, F32],
+    "s3d_peer_sum": [P, U32, P, U64],
     "s3d_ngp_adam_tables": [P, P, P, P, P, P, U32, U64, F32, F32, F32, F32, U32, F32, P],
     "s3d_vm_forward": [P, U32, P, P, P, P, P, P, P, P, U32, I32, P],
     "s3d_vm_backward": [P, U32, P, P, P, P, P, P, P, P, U32, I32, P, P, P, P, P, P, P],
@@ -132,6 +134,13 @@ def host_f32(values):
     """small host-side constant block (float32 array) for the few by-value arguments of the C-ABI"""
     import numpy as np
     arr = np.ascontiguousarray(np.asarray(values, dtype=np.float32).reshape(-1))
+    return arr, arr.ctypes.data
+
+
+def host_ptrs(values):
+    """host array of device pointers (ints or tensors) for the *_peers arguments; keep the returned array alive across the call"""
+    import numpy as np
+    arr = np.ascontiguousarray(np.asarray([v.data_ptr() if isinstance(v, torch.Tensor) else int(v) for v in values], dtype=np.uint64))
     return arr, arr.ctypes.data
 
 

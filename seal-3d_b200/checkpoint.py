@@ -142,6 +142,9 @@ def save_checkpoint(path, trainer=None, model=None, epoch=0, stats=None, full=Fa
         state["mean_count"] = model.mean_count
         state["mean_density"] = model.mean_density
     if full and trainer is not None:
+        if getattr(trainer, "peer", None) is not None and getattr(trainer, "_moments_gathered_at", None) != trainer.global_step:
+            # peer-memory data parallel keeps each entry's Adam moments on its owner rank only
+            raise RuntimeError("call trainer.gather_optimizer_state() on EVERY rank before saving a full checkpoint of a peer-mode trainer")
         state["optimizer"] = optimizer_state_dict(trainer)
         state["lr_scheduler"] = _scheduler_state_dict(trainer)
         if getattr(trainer, "scaler", None) is not None:

@@ -378,7 +378,7 @@ k_ngp_scatter_count(const float *__restrict__ xyz, uint32_t M, float bound, cons
     bool ok = false;
     if (i < M) ok = load_unit(xyz, i, bound, ux, uy, uz);
     const uint32_t lane = lane_id();
-    uint32_t n = 0;
+    uint32_t n = 0, nh = 0;      // all levels / hashed levels only (count[0], count[1])
     for (uint32_t l = 0; l < L; l++) {
         Cell c;
         unsigned long long key = ~0ull;
@@ -386,9 +386,11 @@ k_ngp_scatter_count(const float *__restrict__ xyz, uint32_t M, float bound, cons
         const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
         const bool head = (lane == 0) || (prev != key);
         const uint32_t heads = __ballot_sync(0xffffffffu, head);
-        n += 8u * __popc(__ballot_sync(0xffffffffu, ok && (head || __popc(heads) > 16)));
+        const uint32_t k = 8u * __popc(__ballot_sync(0xffffffffu, ok && (head || __popc(heads) > 16)));
+        n += k;
+        if ((g.hashed >> l) & 1u) nh += k;
     }
-    if (lane == 0 && n) atomicAdd(count, (unsigned long long)n);
+    if (lane == 0 && n) { atomicAdd(count, (unsigned long long)n); atomicAdd(count + 1, (unsigned long long)nh); }
 }
 
 // fixed-point arena -> fp32 gradient arena (accumulated into), arena cleared; *nonfinite -> NaN in grad[0]
@@ -1413,6 +1415,76 @@ k_adam_tables(float2 *__restrict__ ps, float2 *__restrict__ pc, float4 *__restri
     *reinterpret_cast<uint2 *>(shadow + i * shadow_stride) = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Data parallel over NVLink peer memory: reduce + Adam + broadcast of the tables in ONE kernel
+// ------------------------------------------------------------------------------------------------
+// With N replicas the step used to end in all_reduce(98 MB gradient arena) (0.38 ms on 8 B200s) followed by every rank running
+// the same Adam pass over all 6.1 M entries (0.135 ms).  Here every rank owns a contiguous 1/N of the entries.  For each entry of
+// its shard it loads the N ranks' gradient vectors straight from their arenas over NVLink (peer pointers from a symmetric-memory
+// rendezvous), adds them in rank order -- a fixed order, so every replica receives the same bits -- runs Adam with its shard of the
+// moments, and stores the new fp32 entry and its fp16 shadow into every rank's tables.  Per rank: 7/8 of 98 MB in, 7/8 of the
+// TOUCHED entries x 24 B out, both directions of the links in use at once, and no second pass over the parameters.
+// Ordering is the caller's: a cross-rank barrier before (all scatters done) and after (all shards written, all arenas read) the
+// launch; the local arena is cleared after the second barrier (its entries are read by their owners only).
+constexpr int kMaxPeers = 16;
+struct PeerTables {
+    const float4 *grad[kMaxPeers];
+    float2 *ps[kMaxPeers], *pc[kMaxPeers];
+    uint8_t *shadow[kMaxPeers];
+};
+
+__global__ void __launch_bounds__(256)
+k_peer_adam_tables(const PeerTables P, uint32_t world, uint32_t self, float4 *__restrict__ m4, float4 *__restrict__ v4, uint32_t shadow_stride, size_t e0, size_t e1,
+                   float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps, float gscale) {
+    const size_t i = e0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= e1) return;
+    float4 gr[kMaxPeers];
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; r++)
+        if (r < (int)world) gr[r] = __ldcg(P.grad[r] + i);          // all loads in flight before the first add
+    float4 g = gr[0];
+#pragma unroll
+    for (int r = 1; r < kMaxPeers; r++)
+        if (r < (int)world) { g.x += gr[r].x; g.y += gr[r].y; g.z += gr[r].z; g.w += gr[r].w; }
+    float4 m = m4[i];
+    const bool gz = (g.x == 0.0f) & (g.y == 0.0f) & (g.z == 0.0f) & (g.w == 0.0f);
+    const bool mz = (m.x == 0.0f) & (m.y == 0.0f) & (m.z == 0.0f) & (m.w == 0.0f);
+    if (gz && mz) return;        // never touched on any rank: dense Adam leaves it exactly unchanged (see k_adam_tables)
+    float4 v = v4[i];
+    const float2 s = P.ps[self][i], c = P.pc[self][i];      // replicas hold identical parameters: read the local copy
+    const float *G = &g.x;
+    float *Mv = &m.x, *V = &v.x;
+    float Q[4] = {s.x, s.y, c.x, c.y};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float x = G[k] * gscale;
+        Mv[k] = b1 * Mv[k] + (1.0f - b1) * x;
+        V[k] = b2 * V[k] + (1.0f - b2) * x * x;
+        Q[k] -= lr_over_bc1 * Mv[k] / (sqrtf(V[k]) * inv_sqrt_bc2 + eps);
+    }
+    m4[i] = m; v4[i] = v;
+    const __half2 a = __floats2half2_rn(Q[0], Q[1]), b = __floats2half2_rn(Q[2], Q[3]);
+    const uint2 sh = make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b));
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; r++) {
+        if (r < (int)world) {
+            P.ps[r][i] = make_float2(Q[0], Q[1]);
+            P.pc[r][i] = make_float2(Q[2], Q[3]);
+            *reinterpret_cast<uint2 *>(P.shadow[r] + i * shadow_stride) = sh;
+        }
+    }
+}
+
+struct PeerVec { const float *src[kMaxPeers]; };
+// out[i] = sum over ranks (in the order given) of src[r][i]: the MLP's 12 K weight gradients, summed by every rank for itself
+__global__ void k_peer_sum(const PeerVec P, uint32_t world, float *__restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a = __ldcg(P.src[0] + i);
+    for (uint32_t r = 1; r < world; r++) a += __ldcg(P.src[r] + i);
+    out[i] = a;
+}
+
 size_t fwd_smem() { return 1024 + 2 * kTileBytes + 3 * kWTile + 2 * kOTile; }
 size_t bwd_smem() { return 1024 + 2 * kSetTiles * kTileBytes + 3 * kWTile + 2 * kOTile; }
 
@@ -1486,7 +1558,8 @@ S3D_API int s3d_ngp_scatter_fixed(const float *xyz, const void *dfeats, uint32_t
     S3D_RETURN_LAST();
 }
 
-// *count (device, 64-bit) += the number of global reductions s3d_ngp_scatter issues for these samples (measurement aid)
+// count[0] += the number of global reductions s3d_ngp_scatter issues for these samples, count[1] += those on hashed levels
+// (pseudo-random addresses); device, 64-bit each (measurement aid)
 S3D_API int s3d_ngp_scatter_count(const float *xyz, uint32_t M, float bound, const int *offsets, uint32_t L, float S, uint32_t H,
                                   unsigned long long *count, void *stream) {
     if (M == 0) return 0;
@@ -1619,5 +1692,40 @@ S3D_API int s3d_ngp_adam_tables(float *table_sigma, float *table_color, float *g
     k_adam_tables<<<(unsigned)div_up((size_t)n_entries, (size_t)256), 256, 0, as_stream(stream)>>>(
         (float2 *)table_sigma, (float2 *)table_color, (float4 *)grad4, (float4 *)exp_avg4, (float4 *)exp_avg_sq4, (uint8_t *)shadow, shadow_stride, (size_t)n_entries,
         (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps, grad_scale, scaler_state, lr);
+    S3D_RETURN_LAST();
+}
+
+// Data parallel, peer-memory form of s3d_ngp_adam_tables (see k_peer_adam_tables).  *_peers: HOST arrays of `world` device
+// pointers in rank order (the gradient sum is taken in array order: the same order on every rank gives every replica the same
+// bits); `rank` = this process's index in them (its own tables are the ones read).  Entries [entry_begin, entry_end) are this rank's shard; exp_avg4 / exp_avg_sq4
+// are local full-size moment tables of which only the shard is used.  grad_scale divides out the loss scale and the world size.
+// The gradient arenas are NOT cleared (the caller clears its own after the closing barrier).
+S3D_API int s3d_ngp_peer_adam_tables(const void *const *grad4_peers, void *const *sigma_peers, void *const *color_peers, void *const *shadow_peers,
+                                     uint32_t world, uint32_t rank, float *exp_avg4, float *exp_avg_sq4, uint32_t shadow_stride, uint64_t entry_begin,
+                                     uint64_t entry_end, float lr, float beta1, float beta2, float eps, uint32_t step, float grad_scale, void *stream) {
+    if (entry_end <= entry_begin) return 0;
+    if (rank >= world) return S3D_EINVAL;
+    if (world == 0 || world > (uint32_t)kMaxPeers || !grad4_peers || !sigma_peers || !color_peers || !shadow_peers) return S3D_EINVAL;
+    PeerTables P;
+    for (uint32_t r = 0; r < (uint32_t)kMaxPeers; r++) {
+        const uint32_t q = r < world ? r : 0;
+        P.grad[r] = (const float4 *)grad4_peers[q]; P.ps[r] = (float2 *)sigma_peers[q]; P.pc[r] = (float2 *)color_peers[q]; P.shadow[r] = (uint8_t *)shadow_peers[q];
+        if (!P.grad[r] || !P.ps[r] || !P.pc[r] || !P.shadow[r]) return S3D_EINVAL;
+    }
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    const size_t n = (size_t)(entry_end - entry_begin);
+    k_peer_adam_tables<<<(unsigned)div_up(n, (size_t)256), 256, 0, as_stream(stream)>>>(P, world, rank, (float4 *)exp_avg4, (float4 *)exp_avg_sq4, shadow_stride,
+                                                                                          (size_t)entry_begin, (size_t)entry_end, (float)((double)lr / bc1),
+                                                                                          (float)(1.0 / sqrt(bc2)), beta1, beta2, eps, grad_scale);
+    S3D_RETURN_LAST();
+}
+
+// out[i] = src_peers[0][i] + src_peers[1][i] + ... (array order), n floats; src_peers: HOST array of `world` device pointers
+S3D_API int s3d_peer_sum(const void *const *src_peers, uint32_t world, float *out, uint64_t n, void *stream) {
+    if (n == 0) return 0;
+    if (world == 0 || world > (uint32_t)kMaxPeers || !src_peers || !out) return S3D_EINVAL;
+    PeerVec P;
+    for (uint32_t r = 0; r < (uint32_t)kMaxPeers; r++) { P.src[r] = (const float *)src_peers[r < world ? r : 0]; if (!P.src[r]) return S3D_EINVAL; }
+    k_peer_sum<<<(unsigned)div_up((size_t)n, (size_t)256), 256, 0, as_stream(stream)>>>(P, world, out, (size_t)n);
     S3D_RETURN_LAST();
 }

@@ -367,6 +367,92 @@ class FusedDistillTrainer:
             self.table8 = torch.empty(self.S.N, 8, dtype=torch.float16, device=self.S.dev)
             _lib.call("s3d_ngp_pair_tables", self.T.table4, self.S.table4, self.table8, self.S.N)
             self.S.use_paired_table(self.table8, 1)
+        self.peer, self._moments_gathered_at = None, None
+        if world_size > 1 and self.scaler is None and os.environ.get("S3D_PEER_ADAM", "1") != "0" and self.S.dev.type == "cuda":
+            self._setup_peer_step()
+
+    # -- data parallel over NVLink peer memory -----------------------------------------------------------------------------
+    # Instead of all_reduce(gradient arena) + a full Adam pass on every rank, every rank owns 1/world of the table entries:
+    # one kernel (s3d_ngp_peer_adam_tables) reads the entry's gradient from every rank's arena through peer pointers, sums in
+    # rank order, steps Adam with its shard of the moments and writes the new entry + fp16 shadow into every rank's tables.
+    # The gradient arena, the two fp32 tables and the fp16 table live in symmetric memory for that (parallel.PeerBuffer); the
+    # MLP's 12 K gradients are summed by every rank for itself (s3d_peer_sum) and stepped locally.  Two device-side barriers per
+    # step order the peers (after the scatters, after the updates); no NCCL call is left in the step.
+    # Static loss scale only (a dynamic scaler needs a cross-rank found-inf decision: that path keeps the all-reduce);
+    # S3D_PEER_ADAM=0 or a failing rendezvous also keep the all-reduce.
+    def _setup_peer_step(self):
+        from .parallel import PeerBuffer, shard_bounds
+        S = self.S
+        try:
+            g = PeerBuffer(S.grad.numel(), torch.float32, S.dev)
+            par = PeerBuffer(S.N * 4, torch.float32, S.dev)
+            tbl = PeerBuffer(S._tbl.numel(), torch.float16, S.dev)
+        except Exception as e:      # no symmetric memory on this system / group: the NCCL path stays
+            if not dist.is_initialized() or dist.get_rank() == 0:
+                print("seal3d_b200: peer-memory optimizer step unavailable (%s: %s); using all_reduce" % (type(e).__name__, e), flush=True)
+            return
+        enc, encc = S.model.encoder, S.model.encoder_color
+        g.local.zero_()
+        par.local[:S.N * 2].copy_(enc.embeddings.data.reshape(-1))
+        par.local[S.N * 2:].copy_(encc.embeddings.data.reshape(-1))
+        tbl.local.copy_(S._tbl.reshape(-1))
+        # re-home the arena, the parameters and the fp16 table (same values, peer-visible storage)
+        S.grad = g.local
+        S.grad4, S.gmlp = S.grad[:S.N * 4], S.grad[S.N * 4:]
+        enc.embeddings.data = par.local[:S.N * 2].view(S.N, 2)
+        encc.embeddings.data = par.local[S.N * 2:].view(S.N, 2)
+        new_tbl = tbl.local.view_as(S._tbl)
+        if self.table8 is not None:
+            self.table8 = new_tbl
+        else:
+            S.table4 = new_tbl
+        S._tbl = new_tbl
+        if self.ema is not None:
+            self.ema = ParamEMA(S.param_tensors(), self.ema.decay)
+        W, rank = g.world, g.rank
+        e0, e1 = shard_bounds(S.N, rank, W)
+        hp = _lib.host_ptrs
+        self.peer = dict(
+            g=g, par=par, tbl=tbl, world=W, rank=rank, shard=(e0, e1),
+            grad=hp(g.ptrs), sigma=hp(par.ptrs), color=hp([p + S.N * 2 * 4 for p in par.ptrs]), shadow=hp([p + S._tbl_off for p in tbl.ptrs]),
+            gmlp=hp([p + S.N * 4 * 4 for p in g.ptrs]), gmlp_sum=torch.zeros(S.n_mlp, dtype=torch.float32, device=S.dev))
+        g.barrier(0)
+
+    def _peer_step(self, scale, train_mlp):
+        S, P = self.S, self.peer
+        lr, gs = self.current_lr(), 1.0 / (self.world_size * scale)
+        P["g"].barrier(0)                       # every rank's scatter / weight-gradient flush has finished
+        S.step_tables += 1
+        _lib.call("s3d_ngp_peer_adam_tables", P["grad"][1], P["sigma"][1], P["color"][1], P["shadow"][1], P["world"], P["rank"], S.m4, S.v4,
+                  S._tbl_stride, P["shard"][0], P["shard"][1], float(lr), 0.9, 0.99, 1e-15, S.step_tables, float(gs))
+        if train_mlp:
+            S.step_mlp += 1
+            _lib.call("s3d_peer_sum", P["gmlp"][1], P["world"], P["gmlp_sum"], S.n_mlp)
+            _lib.call("s3d_adam_step", S.mlp32, P["gmlp_sum"], S.m_mlp, S.v_mlp, S.mlp16, S.n_mlp, float(lr), 0.9, 0.99, 1e-15, S.step_mlp, float(gs), 1, 0, None)
+        else:
+            pass                                # (the MLP part of the arena is cleared with the rest below)
+        P["g"].barrier(1)                       # every shard is written everywhere, every arena has been read
+        S.grad.zero_()
+        # raw-pointer parameter updates do not bump torch's version counter: mark the modules' cached fp16 tables stale
+        S.model.encoder._shadow_version = S.model.encoder_color._shadow_version = -1
+        self._moments_gathered_at = None
+
+    def gather_optimizer_state(self):
+        """peer mode keeps each entry's Adam moments on the rank that owns it: bring every rank's copy up to date (checkpoints)"""
+        if self.peer is None:
+            return
+        from .parallel import shard_bounds
+        S = self.S
+        for r in range(self.peer["world"]):
+            a, b = shard_bounds(S.N, r, self.peer["world"])
+            dist.broadcast(S.m4[a * 4:b * 4], src=r)
+            dist.broadcast(S.v4[a * 4:b * 4], src=r)
+        self._moments_gathered_at = self.global_step
+
+    def _march_under_scatter(self):
+        """where the next batch is marched (side stream): under the gradient scatter + optimizer kernels on one GPU and in peer
+        mode (whose reduce + Adam kernel fills the SMs), under the NCCL all-reduce (a few SMs) on the all-reduce path"""
+        return self.world_size == 1 or self.peer is not None
 
     def _scale(self, units):
         if self.scaler is not None:
@@ -382,6 +468,12 @@ class FusedDistillTrainer:
         self._pending.append(dist.all_reduce(self.S.grad[a0:a1], async_op=True))
 
     def _reduce_and_step(self, scale, train_mlp=True, advance_schedule=True):
+        if self.peer is not None:
+            self._peer_step(scale, train_mlp)
+            self.global_step += 1
+            if advance_schedule:
+                self.sched_step += 1
+            return
         if self.world_size > 1:
             if self._pending:              # the chunks of the gradient arena, each started right after its scatter launch
                 for w in self._pending:
@@ -556,8 +648,8 @@ class FusedDistillTrainer:
             teacher_out = self._teacher_field(mx, md.contiguous().float(), mask, self.T.encode(mx.contiguous().float()))
             sig_s, rgb_s, feats = self.S.forward(xyzs, dirs)
         loss, scale = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, None, None,
-                                             before_scatter=ahead if self.world_size == 1 else None, teacher=teacher_out)
-        if ahead is not None and self.world_size > 1:
+                                             before_scatter=ahead if self._march_under_scatter() else None, teacher=teacher_out)
+        if ahead is not None and not self._march_under_scatter():
             ahead()      # data parallel: the next batch is marched under the gradient all-reduce (NCCL needs only a few SMs)
         self._reduce_and_step(scale)
         return loss
@@ -569,8 +661,8 @@ class FusedDistillTrainer:
         ahead = (lambda: self._prefetch(prefetch, perturb, force_all_rays)) if prefetch is not None else None
         sig_s, rgb_s, feats = self.S.forward(xyzs, dirs)
         loss, scale = self._student_backward(xyzs, dirs, feats, sig_s, rgb_s, deltas, rays, image_t, depth_t,
-                                             before_scatter=ahead if self.world_size == 1 else None)
-        if ahead is not None and self.world_size > 1:
+                                             before_scatter=ahead if self._march_under_scatter() else None)
+        if ahead is not None and not self._march_under_scatter():
             ahead()
         self._reduce_and_step(scale)
         return loss

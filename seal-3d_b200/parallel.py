@@ -45,3 +45,28 @@ def max_over_ranks(value, device):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+class PeerBuffer:
+    """One symmetric-memory allocation per rank + rendezvous (torch.distributed._symmetric_memory: cuMem allocations whose
+    handles the ranks exchange and map into their own address space): `.local` is this rank's tensor, `.ptrs[r]` the device address
+    of rank r's copy as seen from THIS process -- kernels launched here load and store through them over NVLink.  `.barrier()`
+    enqueues a cross-rank barrier on the current stream (signal pads in the same allocation, system-scope release / acquire), so
+    peer reads and writes of consecutive kernels are ordered without a host round trip or an NCCL launch.  Collective: every
+    rank of the group constructs its PeerBuffers in the same order."""
+
+    def __init__(self, numel, dtype, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.local = symm.empty(int(numel), dtype=dtype, device=device)
+        try:
+            self.hdl = symm.rendezvous(self.local, group)
+        except TypeError:
+            self.hdl = symm.rendezvous(self.local, group.group_name)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
+        if len(self.ptrs) != self.world or self.ptrs[self.rank] != self.local.data_ptr():
+            raise RuntimeError("symmetric memory rendezvous returned unexpected pointers")
+
+    def barrier(self, channel=0):
+        self.hdl.barrier(channel=channel)

@@ -665,9 +665,10 @@ def test_scatter_reduction_count(scene):
     S = float(np.log2(pls))
 
     def count(x):
-        c = torch.zeros(1, dtype=torch.int64, device=dev())
+        c = torch.zeros(2, dtype=torch.int64, device=dev())
         _lib.call("s3d_ngp_scatter_count", to(x.astype(np.float32)), x.shape[0], 1.0, off, 16, S, 16, c)
-        return int(c.item())
+        assert 0 <= int(c[1]) <= int(c[0])          # c[1]: the reductions on hashed levels
+        return int(c[0].item())
 
     same = np.tile(np.array([[0.123, -0.456, 0.789]]), (64, 1))
     assert count(same) == 2 * 16 * 8
@@ -679,3 +680,60 @@ def test_scatter_reduction_count(scene):
     x0, _, _, _, M = _samples(scene, 256)
     per_sample = count(x0) / x0.shape[0]
     assert 40 < per_sample < 100                       # ray-ordered samples: the coarse levels fold (about 60 per sample instead of 128)
+
+
+def test_peer_adam_kernel_equals_allreduce_then_adam_on_one_gpu():
+    """s3d_ngp_peer_adam_tables (the data-parallel step over NVLink peer memory) with the 'ranks' simulated by separate buffers
+    of ONE GPU -- the kernel only sees pointers: for every shard owner, reduce-in-rank-order + Adam + write-to-all equals
+    sum -> s3d_ngp_adam_tables bit for bit, untouched entries stay untouched, and s3d_peer_sum adds in array order.  (The
+    real multi-GPU run is scripts/dp_peer_check.py: bit-identical to the all-reduce path on 2 GPUs, 2e-7 on 8.)"""
+    from seal3d_b200 import _lib
+    from seal3d_b200.parallel import shard_bounds
+    torch.manual_seed(0)
+    N, W = 50000, 3
+    d = dev()
+    grads = [torch.randn(N, 4, device=d) * 1e-3 for _ in range(W)]
+    for g in grads:
+        g[1000:30000:7] = 0.0                                   # entries nobody touched
+    ps0, pc0 = torch.randn(N, 2, device=d) * 1e-4, torch.randn(N, 2, device=d) * 1e-4
+    m0, v0 = torch.randn(N, 4, device=d) * 1e-4, torch.rand(N, 4, device=d) * 1e-8
+    m0[1000:30000:7] = 0.0
+    v0[1000:30000:7] = 0.0
+    lr, b1, b2, eps, step, gs = 1e-2, 0.9, 0.99, 1e-15, 3, 1.0 / (W * 64.0)
+
+    # reference: sum in rank order, then the single-GPU kernel
+    gsum = grads[0].clone()
+    for g in grads[1:]:
+        gsum += g
+    ps_r, pc_r, m_r, v_r = ps0.clone(), pc0.clone(), m0.clone(), v0.clone()
+    sh_r = torch.zeros(N, 4, dtype=torch.float16, device=d)
+    _lib.call("s3d_ngp_adam_tables", ps_r, pc_r, gsum.clone(), m_r, v_r, sh_r, 8, N, lr, b1, b2, eps, step, gs, None)
+
+    # 'ranks': each has its own tables / shadow (paired layout: stride 16, student half at +8) / moments
+    ps = [ps0.clone() for _ in range(W)]
+    pc = [pc0.clone() for _ in range(W)]
+    sh = [torch.zeros(N, 8, dtype=torch.float16, device=d) for _ in range(W)]
+    m = [m0.clone() for _ in range(W)]
+    v = [v0.clone() for _ in range(W)]
+    gp, sp, cp = _lib.host_ptrs(grads), _lib.host_ptrs(ps), _lib.host_ptrs(pc)
+    shp = _lib.host_ptrs([t.data_ptr() + 8 for t in sh])
+    for r in range(W):
+        e0, e1 = shard_bounds(N, r, W)
+        _lib.call("s3d_ngp_peer_adam_tables", gp[1], sp[1], cp[1], shp[1], W, r, m[r], v[r], 16, e0, e1, lr, b1, b2, eps, step, gs)
+    for r in range(W):
+        assert torch.equal(ps[r], ps_r) and torch.equal(pc[r], pc_r)                  # every replica, every shard: the reference's bits
+        assert torch.equal(sh[r][:, 4:], sh_r) and not sh[r][:, :4].any()            # student half written, teacher half untouched
+        e0, e1 = shard_bounds(N, r, W)
+        assert torch.equal(m[r][e0:e1], m_r[e0:e1]) and torch.equal(v[r][e0:e1], v_r[e0:e1])   # moments live on the owner
+        others = torch.ones(N, dtype=torch.bool, device=d)
+        others[e0:e1] = False
+        assert torch.equal(m[r][others], m0[others])
+    assert torch.equal(ps_r[1000:30000:7], ps0[1000:30000:7])                          # never-touched entries do not move
+    assert all(torch.equal(g, g) for g in grads)                                       # arenas are left for the caller to clear
+
+    vecs = [torch.randn(12496, device=d) for _ in range(W)]
+    out = torch.empty(12496, device=d)
+    _lib.call("s3d_peer_sum", _lib.host_ptrs(vecs)[1], W, out, 12496)
+    assert torch.equal(out, (vecs[0] + vecs[1]) + vecs[2])
+    with pytest.raises(_lib.S3DError):
+        _lib.call("s3d_ngp_peer_adam_tables", gp[1], sp[1], cp[1], shp[1], W, W, m[0], v[0], 16, 0, 10, lr, b1, b2, eps, step, gs)   # rank outside the world
