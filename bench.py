@@ -653,7 +653,8 @@ def gpu_arm(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "global_rays_per_step": n * world, "samples_per_step_per_gpu": samples_per_step,
-                   "samples_per_ray": samples_per_step / n, "parallelism": "dp%d (ray shards, one grad all-reduce/step)" % world,
+                   "samples_per_ray": samples_per_step / n, "parallelism": ("dp%d (ray shards; gradients reduced + Adam + tables broadcast by one kernel over NVLink peer memory, no collective call in the step)" % world)
+                   if getattr(tr, "peer", None) is not None else ("dp%d (ray shards, one grad all-reduce/step)" % world),
                    "schedule": "fused teacher+student on shared samples; occupancy refresh every 16 steps" + ("; next batch marched on a side stream under the current step" if pipelined else ""),
                    "l2_note": "each step streams > 126 MB (samples + 4 tables + arena) so successive steps do not reuse L2 contents"},
         "e2e": {"value": rays_total / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
