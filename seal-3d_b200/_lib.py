@@ -93,7 +93,7 @@ _NO_STREAM = {"s3d_allocate_splitk": [SZ], "s3d_free_splitk": [], "s3d_march_set
 _lib = None
 LAUNCHES = 0  # kernels launched through this binding (bench.py reports the per-run delta)
 PROFILE = None  # set to a list to record (name, start_event, end_event) per call (bench.py's per-kernel breakdown)
-_KERNELS_PER_CALL = {"s3d_linear_backward": 3, "s3d_density_pick_cells": 4, "s3d_density_grid_update": 2, "s3d_march_rays_train": 7, "s3d_march_rays_train_count": 5, "s3d_ffmlp_backward": 2, "s3d_seal_map_color": 2, "s3d_seal_anchor_map_to_origin": 2, "s3d_seal_map_color_image": 2}
+_KERNELS_PER_CALL = {"s3d_linear_backward": 3, "s3d_density_pick_cells": 4, "s3d_density_grid_update": 2, "s3d_march_rays_train": 9, "s3d_march_rays_train_count": 7, "s3d_ffmlp_backward": 2, "s3d_seal_map_color": 2, "s3d_seal_anchor_map_to_origin": 2, "s3d_seal_map_color_image": 2}
 
 
 class S3DError(RuntimeError):
