@@ -418,7 +418,24 @@ ALGO_BYTES = {
     "s3d_grid_encode_backward": ("k_grid_backward", 12 + 16 * 8 * 4 + 64),
 }
 ALGO_BYTES_ALT = {"s3d_ngp_scatter": ("achieved_fp32_entries", 12 + 128 + 16 * 8 * 16)}
-RED_RATE_PEAK_G = 149.0     # measured: random global reductions per second (1e9) on one B200, independent of their width
+# measured on one B200 (scripts/r2/red_micro.cu, profiles/r2_red_rate_micro_run36.log), in 1e9 reductions per second, into a 98 MB table:
+RED_RATE_RANDOM_G = 152.0   # isolated random entries -- the same for RED.32 / .64 / .128 / packed fp16: width does not matter
+RED_RATE_PAIRED_G = 213.0   # two (or four) adjacent 16-byte entries of one sector: the pattern of a grid cell's x-corner pairs
+
+
+def reduction_rate_block(red, samples_per_step, launch_ms):
+    """red = (reductions, samples, reductions on hashed levels) counted by s3d_ngp_scatter_count on one batch -> the scatter's
+    reduction-rate roofline for a launch of samples_per_step samples that took launch_ms"""
+    n_red = red[0] * samples_per_step / red[1]
+    floor_ms = n_red / (RED_RATE_PAIRED_G * 1e9) * 1e3
+    return {
+        "reductions_per_sample": red[0] / red[1], "hashed_level_reductions_per_sample": red[2] / red[1], "reductions_per_launch": n_red,
+        "achieved": n_red / (launch_ms * 1e-3) / 1e9, "peak": RED_RATE_PAIRED_G, "unit": "G reductions/s", "frac": floor_ms / launch_ms,
+        "floor_ms": floor_ms, "random_address_rate": RED_RATE_RANDOM_G,
+        "note": "the gradient table stays in L2, so this kernel is bound by the chip's global-reduction RATE, not by bytes: isolated random "
+                "reductions retire at 152 G/s whatever their width (RED.32 / .64 / .128 / f16x2), same-sector pairs -- the two x-corners of a cell, "
+                "which is how this kernel's reductions come -- at 213 G/s (scripts/r2/red_micro.cu, profiles/r2_red_rate_micro_run36.log); "
+                "frac = (reductions / 213 G/s) / launch time"}
 
 
 def whole_step_roofline(n_rays, samples_per_step, rays_per_s_per_gpu):
@@ -667,17 +684,7 @@ def gpu_arm(args):
         line["kernel_breakdown_ms_per_step"] = {k: round(v["ms_per_step"], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms_per_step"])}
         line["roofline"] = step_roofline(breakdown, samples_per_step, ms / args.steps)
         if red and line["roofline"].get("kernel") == "k_ngp_scatter":
-            n_red, n_hashed = red[0] * samples_per_step / red[1], red[2] * samples_per_step / red[1]
-            launch_s = line["roofline"]["launch_ms"] * 1e-3
-            floor_ms = n_hashed / (RED_RATE_PEAK_G * 1e9) * 1e3
-            line["roofline"]["reduction_rate"] = {
-                "reductions_per_sample": red[0] / red[1], "hashed_level_reductions_per_sample": red[2] / red[1],
-                "achieved": n_red / launch_s / 1e9, "unit": "G reductions/s", "random_address_rate": RED_RATE_PEAK_G,
-                "random_reductions_floor_ms": floor_ms, "frac_of_launch_at_that_floor": floor_ms / line["roofline"]["launch_ms"],
-                "note": "B200 retires 149 G global reductions per second to random addresses whatever their width (scripts/r2/red_micro.cu, "
-                        "profiles/r2_red_rate_micro_run30.log: RED.32 / .64 / .128 / f16x2 into a 98 MB table); the reductions of the hashed levels "
-                        "are such addresses, so their count / that rate is a floor for this kernel that no byte-saving can lower (its table stays in "
-                        "L2); dense-level reductions of a warp share lines and are cheaper"}
+            line["roofline"]["reduction_rate"] = reduction_rate_block(red, samples_per_step, line["roofline"]["launch_ms"])
     return line
 
 
