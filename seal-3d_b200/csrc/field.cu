@@ -1433,44 +1433,56 @@ struct PeerTables {
     uint8_t *shadow[kMaxPeers];
 };
 
+// E entries per thread (consecutive 256-entry slabs of a CTA's span), all E x world gradient loads issued before the first add: a
+// remote load takes microseconds, so small worlds (few loads per entry) need more entries per thread to keep the links busy
+// (world 2: 0.154 ms with E = 1 for half of the table -- slower than the whole local Adam pass)
+template <int E, int WMAX>      // WMAX: the largest world this instantiation serves (bounds the register arrays)
 __global__ void __launch_bounds__(256)
 k_peer_adam_tables(const PeerTables P, uint32_t world, uint32_t self, float4 *__restrict__ m4, float4 *__restrict__ v4, uint32_t shadow_stride, size_t e0, size_t e1,
                    float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps, float gscale) {
-    const size_t i = e0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= e1) return;
-    float4 gr[kMaxPeers];
+    const size_t base = e0 + (size_t)blockIdx.x * (256 * E) + threadIdx.x;
+    float4 gr[E][WMAX];
 #pragma unroll
-    for (int r = 0; r < kMaxPeers; r++)
-        if (r < (int)world) gr[r] = __ldcg(P.grad[r] + i);          // all loads in flight before the first add
-    float4 g = gr[0];
+    for (int u = 0; u < E; u++) {
+        const size_t i = base + (size_t)u * 256;
 #pragma unroll
-    for (int r = 1; r < kMaxPeers; r++)
-        if (r < (int)world) { g.x += gr[r].x; g.y += gr[r].y; g.z += gr[r].z; g.w += gr[r].w; }
-    float4 m = m4[i];
-    const bool gz = (g.x == 0.0f) & (g.y == 0.0f) & (g.z == 0.0f) & (g.w == 0.0f);
-    const bool mz = (m.x == 0.0f) & (m.y == 0.0f) & (m.z == 0.0f) & (m.w == 0.0f);
-    if (gz && mz) return;        // never touched on any rank: dense Adam leaves it exactly unchanged (see k_adam_tables)
-    float4 v = v4[i];
-    const float2 s = P.ps[self][i], c = P.pc[self][i];      // replicas hold identical parameters: read the local copy
-    const float *G = &g.x;
-    float *Mv = &m.x, *V = &v.x;
-    float Q[4] = {s.x, s.y, c.x, c.y};
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const float x = G[k] * gscale;
-        Mv[k] = b1 * Mv[k] + (1.0f - b1) * x;
-        V[k] = b2 * V[k] + (1.0f - b2) * x * x;
-        Q[k] -= lr_over_bc1 * Mv[k] / (sqrtf(V[k]) * inv_sqrt_bc2 + eps);
+        for (int r = 0; r < WMAX; r++)
+            if (r < (int)world && i < e1) gr[u][r] = __ldcg(P.grad[r] + i);
     }
-    m4[i] = m; v4[i] = v;
-    const __half2 a = __floats2half2_rn(Q[0], Q[1]), b = __floats2half2_rn(Q[2], Q[3]);
-    const uint2 sh = make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b));
 #pragma unroll
-    for (int r = 0; r < kMaxPeers; r++) {
-        if (r < (int)world) {
-            P.ps[r][i] = make_float2(Q[0], Q[1]);
-            P.pc[r][i] = make_float2(Q[2], Q[3]);
-            *reinterpret_cast<uint2 *>(P.shadow[r] + i * shadow_stride) = sh;
+    for (int u = 0; u < E; u++) {
+        const size_t i = base + (size_t)u * 256;
+        if (i >= e1) continue;
+        float4 g = gr[u][0];
+#pragma unroll
+        for (int r = 1; r < WMAX; r++)
+            if (r < (int)world) { g.x += gr[u][r].x; g.y += gr[u][r].y; g.z += gr[u][r].z; g.w += gr[u][r].w; }
+        float4 m = m4[i];
+        const bool gz = (g.x == 0.0f) & (g.y == 0.0f) & (g.z == 0.0f) & (g.w == 0.0f);
+        const bool mz = (m.x == 0.0f) & (m.y == 0.0f) & (m.z == 0.0f) & (m.w == 0.0f);
+        if (gz && mz) continue;      // never touched on any rank: dense Adam leaves it exactly unchanged (see k_adam_tables)
+        float4 v = v4[i];
+        const float2 s = P.ps[self][i], c = P.pc[self][i];      // replicas hold identical parameters: read the local copy
+        const float *G = &g.x;
+        float *Mv = &m.x, *V = &v.x;
+        float Q[4] = {s.x, s.y, c.x, c.y};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float x = G[k] * gscale;
+            Mv[k] = b1 * Mv[k] + (1.0f - b1) * x;
+            V[k] = b2 * V[k] + (1.0f - b2) * x * x;
+            Q[k] -= lr_over_bc1 * Mv[k] / (sqrtf(V[k]) * inv_sqrt_bc2 + eps);
+        }
+        m4[i] = m; v4[i] = v;
+        const __half2 a = __floats2half2_rn(Q[0], Q[1]), b = __floats2half2_rn(Q[2], Q[3]);
+        const uint2 sh = make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b));
+#pragma unroll
+        for (int r = 0; r < WMAX; r++) {
+            if (r < (int)world) {
+                P.ps[r][i] = make_float2(Q[0], Q[1]);
+                P.pc[r][i] = make_float2(Q[2], Q[3]);
+                *reinterpret_cast<uint2 *>(P.shadow[r] + i * shadow_stride) = sh;
+            }
         }
     }
 }
@@ -1714,9 +1726,13 @@ S3D_API int s3d_ngp_peer_adam_tables(const void *const *grad4_peers, void *const
     }
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     const size_t n = (size_t)(entry_end - entry_begin);
-    k_peer_adam_tables<<<(unsigned)div_up(n, (size_t)256), 256, 0, as_stream(stream)>>>(P, world, rank, (float4 *)exp_avg4, (float4 *)exp_avg_sq4, shadow_stride,
-                                                                                          (size_t)entry_begin, (size_t)entry_end, (float)((double)lr / bc1),
-                                                                                          (float)(1.0 / sqrt(bc2)), beta1, beta2, eps, grad_scale);
+    const float a1 = (float)((double)lr / bc1), a2 = (float)(1.0 / sqrt(bc2));
+    cudaStream_t st = as_stream(stream);
+    // entries per thread: about 8 gradient loads in flight per thread whatever the world size
+    if (world <= 2) k_peer_adam_tables<4, 2><<<(unsigned)div_up(n, (size_t)1024), 256, 0, st>>>(P, world, rank, (float4 *)exp_avg4, (float4 *)exp_avg_sq4, shadow_stride, (size_t)entry_begin, (size_t)entry_end, a1, a2, beta1, beta2, eps, grad_scale);
+    else if (world <= 4) k_peer_adam_tables<2, 4><<<(unsigned)div_up(n, (size_t)512), 256, 0, st>>>(P, world, rank, (float4 *)exp_avg4, (float4 *)exp_avg_sq4, shadow_stride, (size_t)entry_begin, (size_t)entry_end, a1, a2, beta1, beta2, eps, grad_scale);
+    else if (world <= 8) k_peer_adam_tables<1, 8><<<(unsigned)div_up(n, (size_t)256), 256, 0, st>>>(P, world, rank, (float4 *)exp_avg4, (float4 *)exp_avg_sq4, shadow_stride, (size_t)entry_begin, (size_t)entry_end, a1, a2, beta1, beta2, eps, grad_scale);
+    else k_peer_adam_tables<1, kMaxPeers><<<(unsigned)div_up(n, (size_t)256), 256, 0, st>>>(P, world, rank, (float4 *)exp_avg4, (float4 *)exp_avg_sq4, shadow_stride, (size_t)entry_begin, (size_t)entry_end, a1, a2, beta1, beta2, eps, grad_scale);
     S3D_RETURN_LAST();
 }
 

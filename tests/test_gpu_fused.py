@@ -682,7 +682,8 @@ def test_scatter_reduction_count(scene):
     assert 40 < per_sample < 100                       # ray-ordered samples: the coarse levels fold (about 60 per sample instead of 128)
 
 
-def test_peer_adam_kernel_equals_allreduce_then_adam_on_one_gpu():
+@pytest.mark.parametrize("W", [2, 3, 5, 9])      # one kernel instantiation each: (4 entries per thread, <= 2 ranks), (2, <= 4), (1, <= 8), (1, <= 16)
+def test_peer_adam_kernel_equals_allreduce_then_adam_on_one_gpu(W):
     """s3d_ngp_peer_adam_tables (the data-parallel step over NVLink peer memory) with the 'ranks' simulated by separate buffers
     of ONE GPU -- the kernel only sees pointers: for every shard owner, reduce-in-rank-order + Adam + write-to-all equals
     sum -> s3d_ngp_adam_tables bit for bit, untouched entries stay untouched, and s3d_peer_sum adds in array order.  (The
@@ -690,7 +691,7 @@ def test_peer_adam_kernel_equals_allreduce_then_adam_on_one_gpu():
     from seal3d_b200 import _lib
     from seal3d_b200.parallel import shard_bounds
     torch.manual_seed(0)
-    N, W = 50000, 3
+    N = 50021
     d = dev()
     grads = [torch.randn(N, 4, device=d) * 1e-3 for _ in range(W)]
     for g in grads:
@@ -734,6 +735,9 @@ def test_peer_adam_kernel_equals_allreduce_then_adam_on_one_gpu():
     vecs = [torch.randn(12496, device=d) for _ in range(W)]
     out = torch.empty(12496, device=d)
     _lib.call("s3d_peer_sum", _lib.host_ptrs(vecs)[1], W, out, 12496)
-    assert torch.equal(out, (vecs[0] + vecs[1]) + vecs[2])
+    ref = vecs[0].clone()
+    for t in vecs[1:]:
+        ref = ref + t
+    assert torch.equal(out, ref)
     with pytest.raises(_lib.S3DError):
         _lib.call("s3d_ngp_peer_adam_tables", gp[1], sp[1], cp[1], shp[1], W, W, m[0], v[0], 16, 0, 10, lr, b1, b2, eps, step, gs)   # rank outside the world
