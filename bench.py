@@ -559,9 +559,12 @@ def timed_legs(tr, resident, host, args, rank, world, dev, pipelined, profile_ho
     clocks = None
     if dev.type == "cuda" and rank == 0:
         if helper is not None and helper.ok():
-            helper.start()
-            clocks = helper
-        else:
+            try:
+                helper.start()
+                clocks = helper
+            except Exception:       # the helper died after it reported ready: sample in-process instead
+                clocks = None
+        if clocks is None:
             clocks = ClockSampler(dev.index)
     from seal3d_b200 import _lib
     launches0 = _lib.LAUNCHES

@@ -383,13 +383,22 @@ class FusedDistillTrainer:
     def _setup_peer_step(self):
         from .parallel import PeerBuffer, shard_bounds
         S = self.S
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() != self.world_size:
+            return
+        err = None
         try:
             g = PeerBuffer(S.grad.numel(), torch.float32, S.dev)
             par = PeerBuffer(S.N * 4, torch.float32, S.dev)
             tbl = PeerBuffer(S._tbl.numel(), torch.float16, S.dev)
         except Exception as e:      # no symmetric memory on this system / group: the NCCL path stays
-            if not dist.is_initialized() or dist.get_rank() == 0:
-                print("seal3d_b200: peer-memory optimizer step unavailable (%s: %s); using all_reduce" % (type(e).__name__, e), flush=True)
+            err = e
+        # every rank must take the same path: one that could not set up its buffers sends everybody to the all-reduce
+        ok = torch.tensor([0.0 if err is not None else 1.0], device=S.dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0.0:
+            if dist.get_rank() == 0:
+                print("seal3d_b200: peer-memory optimizer step unavailable (%s); using all_reduce" %
+                      ("%s: %s" % (type(err).__name__, err) if err is not None else "another rank could not set it up"), flush=True)
             return
         enc, encc = S.model.encoder, S.model.encoder_color
         g.local.zero_()
