@@ -1541,7 +1541,8 @@ S3D_API int s3d_ngp_scatter(const float *xyz, const void *dfeats, uint32_t M, fl
                             float S, uint32_t H, float grad_scale, void *stream) {
     if (M == 0) return 0;
     if (L > kMaxLevels) return S3D_ENOTSUP;
-    static const uint32_t blk = [] { const char *e = getenv("S3D_SCATTER_BLOCK"); const uint32_t v = e ? (uint32_t)atoi(e) : 256u; return (v >= 32 && v <= 1024 && v % 32 == 0) ? v : 256u; }();
+    // 128-thread CTAs: 1.92 ms against 1.98 with 256 (the kernel is warp-granular; smaller CTAs drain and refill the SMs more evenly)
+    static const uint32_t blk = [] { const char *e = getenv("S3D_SCATTER_BLOCK"); const uint32_t v = e ? (uint32_t)atoi(e) : 128u; return (v >= 32 && v <= 256 && v % 32 == 0) ? v : 128u; }();
     k_ngp_scatter<false><<<div_up(M, blk), blk, 0, as_stream(stream)>>>(xyz, (const __half *)dfeats, M, bound, (float4 *)grad4, offsets, L, S, H, grad_scale, 0, 4, nullptr);
     S3D_RETURN_LAST();
 }
