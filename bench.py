@@ -154,18 +154,25 @@ mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
 nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
 BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 print("ready", flush=True)
-on, sm, reasons = False, [], set()
-while True:
-    r, _, _ = select.select([sys.stdin], [], [], 0.005)
+on, sm, reasons, buf, done = False, [], set(), b"", False
+import os
+while not done:
+    r, _, _ = select.select([0], [], [], 0.02)
     if r:
-        line = sys.stdin.readline().strip()
-        if line == "start":
-            on, sm, reasons = True, [], set()
-        elif line == "stop":
-            on = False
-            print(json.dumps({"sm": sm, "mx": mx, "reasons": sorted(reasons)}), flush=True)
-        elif line in ("quit", ""):
+        chunk = os.read(0, 4096)        # raw reads: a buffered readline could swallow a second command that select never reports
+        if not chunk:
             break
+        buf += chunk
+        while b"\n" in buf:
+            line, buf = buf.split(b"\n", 1)
+            line = line.strip().decode()
+            if line == "start":
+                on, sm, reasons = True, [], set()
+            elif line == "stop":
+                on = False
+                print(json.dumps({"sm": sm, "mx": mx, "reasons": sorted(reasons)}), flush=True)
+            elif line == "quit":
+                done = True
     if on:
         try:
             sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
@@ -182,7 +189,7 @@ while True:
 
 
 class ClockSamplerProcess:
-    """The same NVML counters as ClockSampler, polled every 5 ms by a HELPER PROCESS: NVML calls made from the training process
+    """The same NVML counters as ClockSampler, polled every 20 ms (six or seven samples in a 20-step timed leg) by a HELPER PROCESS: NVML calls made from the training process
     itself contend with its kernel launches on the driver's locks -- on 8 GPUs rank 0's in-process sampler cost the whole job
     4 % of the leg it ran in (every rank waits for the slowest at the step's barriers).  The helper is started early (NVML
     initialisation takes a few hundred ms) and told over a pipe when the timed region starts and stops."""
@@ -214,6 +221,10 @@ class ClockSamplerProcess:
         try:
             self.p.stdin.write("stop\n")
             self.p.stdin.flush()
+            import select
+            r, _, _ = select.select([self.p.stdout], [], [], 5.0)      # never hang the bench on a dead helper
+            if not r:
+                raise RuntimeError("sampler helper did not answer")
             d = json.loads(self.p.stdout.readline())
             if d["sm"]:
                 out.update(sm_mhz=float(np.median(d["sm"])), sm_max_mhz=d["mx"], reasons=d["reasons"], samples=len(d["sm"]), source="nvml (helper process)")

@@ -365,3 +365,45 @@ def test_patch_indices_form_contiguous_pixel_blocks():
     rows, cols = blocks // W, blocks % W
     assert (rows[:, 1:, :] - rows[:, :-1, :] == 1).all() and (cols[:, :, 1:] - cols[:, :, :-1] == 1).all()
     assert rows.min() >= 0 and rows.max() < H and cols.min() >= 0 and cols.max() < W
+
+
+def test_clock_sampler_helper_process_protocol(tmp_path):
+    """bench.ClockSamplerProcess's child (NVML polled from a helper process so that the training process's launches are not
+    disturbed): ready / start / stop / quit over the pipes, with a stand-in pynvml (no GPU here)"""
+    import json
+    import subprocess
+    import sys
+    import textwrap
+    import time
+    import bench
+    (tmp_path / "pynvml.py").write_text(textwrap.dedent('''
+        NVML_CLOCK_SM = 1
+        def nvmlInit(): pass
+        def nvmlDeviceGetHandleByUUID(u): return 1
+        def nvmlDeviceGetHandleByIndex(i): return 1
+        def nvmlDeviceGetMaxClockInfo(h, c): return 1965
+        def nvmlDeviceGetClockInfo(h, c): return 1950
+        def nvmlDeviceGetCurrentClocksEventReasons(h): return 0x4 | 0x40
+    '''))
+    env = dict(os.environ, PYTHONPATH=str(tmp_path))
+    p = subprocess.Popen([sys.executable, "-c", bench._SAMPLER_CHILD, "GPU-test", "0"], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, bufsize=1, env=env)
+    try:
+        assert p.stdout.readline().strip() == "ready"
+        p.stdin.write("start\n"); p.stdin.flush()
+        time.sleep(0.25)
+        p.stdin.write("stop\n"); p.stdin.flush()
+        d = json.loads(p.stdout.readline())
+        assert len(d["sm"]) >= 3 and set(d["sm"]) == {1950.0} and d["mx"] == 1965.0
+        assert d["reasons"] == ["hw_thermal_slowdown", "sw_power_cap"]
+        p.stdin.write("start\n"); p.stdin.flush()        # a second window starts empty
+        p.stdin.write("stop\n"); p.stdin.flush()
+        assert len(json.loads(p.stdout.readline())["sm"]) <= 2
+        p.stdin.write("quit\n"); p.stdin.flush()
+        assert p.wait(5) == 0
+    finally:
+        if p.poll() is None:
+            p.kill()
+    # without a GPU the wrapper reports "not available" and bench falls back to the in-process sampler
+    h = bench.ClockSamplerProcess(0)
+    assert not h.ok()
+    h.close()
