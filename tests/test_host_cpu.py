@@ -407,3 +407,30 @@ def test_clock_sampler_helper_process_protocol(tmp_path):
     h = bench.ClockSamplerProcess(0)
     assert not h.ok()
     h.close()
+
+
+def test_shards_tile_the_table_and_reduction_rate_block():
+    """host arithmetic behind the peer-memory step and the bench line: shard_bounds tiles [0, n) for every world size, the largest
+    and smallest shard differ by at most one entry; bench.reduction_rate_block scales a counted batch to a launch"""
+    from seal3d_b200.parallel import shard_bounds
+    import bench
+    for n in (0, 1, 7, 6119864, 50021):
+        for world in (1, 2, 3, 4, 8, 16):
+            spans = [shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1 and min(sizes) >= 0
+    b = bench.reduction_rate_block((400, 10, 300), 1000.0, 2.0)       # 40 reductions per sample, 1000 samples, 2 ms
+    assert b["reductions_per_sample"] == 40 and b["hashed_level_reductions_per_sample"] == 30 and b["reductions_per_launch"] == 40000
+    assert abs(b["achieved"] - 40000 / 2e-3 / 1e9) < 1e-12 and b["peak"] == bench.RED_RATE_PAIRED_G
+    assert abs(b["frac"] - (40000 / (bench.RED_RATE_PAIRED_G * 1e9) * 1e3) / 2.0) < 1e-12
+
+
+def test_host_pointer_arrays_for_the_peer_entry_points():
+    import numpy as np
+    import torch
+    from seal3d_b200 import _lib
+    t = [torch.zeros(4), torch.zeros(8)]
+    arr, addr = _lib.host_ptrs(t + [12345])
+    assert arr.dtype == np.uint64 and list(arr) == [t[0].data_ptr(), t[1].data_ptr(), 12345] and addr == arr.ctypes.data
